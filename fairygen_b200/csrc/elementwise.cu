@@ -1,0 +1,484 @@
+// fairygen_b200 — fused memory-bound kernels of the DiT block (sm_100a).
+//
+// These replace chains of ATen elementwise/reduction kernels in the reference
+// (animation/diffsynth/models/wan_video_dit.py, "DIT"; pipelines/wan_video.py, "PIPE";
+// diffusion/flow_match.py, "FM") with one pass over HBM each: every row is read once with 16-byte
+// loads (12 in flight per lane at D = 3072), reduced with warp shuffles, and written once.
+// Arithmetic is fp32 with the reference's bf16 rounding points reproduced in registers.
+#include "common.cuh"
+#include "host.h"
+
+namespace fgb {
+
+constexpr int kRowWarps = 4;  // rows per CTA (one warp per row)
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_bf16(f[0], f[1]);
+  v.y = pack_bf16(f[2], f[3]);
+  v.z = pack_bf16(f[4], f[5]);
+  v.w = pack_bf16(f[6], f[7]);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (no affine) + adaLN modulate, or LayerNorm with affine.      DIT:205-207, 63-64, 224-227
+// NV = dim / 256 16-byte vectors per lane.
+// ---------------------------------------------------------------------------------------------
+template <int NV, bool AFFINE>
+__global__ void __launch_bounds__(kRowWarps * 32)
+ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy, int rows,
+          float eps, const __nv_bfloat16* __restrict__ shift0, const __nv_bfloat16* __restrict__ scale0,
+          const __nv_bfloat16* __restrict__ shift1, const __nv_bfloat16* __restrict__ scale1, int rows_mod0) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int D = NV * 256;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
+  uint4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = ldg_nc_v4(xr + i * 32 + lane);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8];
+    unpack8(v[i], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += f[e];
+  }
+  const float mean = warp_sum(sum) * (1.0f / D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8];
+    unpack8(v[i], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = f[e] - mean;
+      sq += d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+  // AFFINE: (shift0, scale0) carry (bias, weight). Otherwise pick the modulation row of this token.
+  const bool first = AFFINE || row < rows_mod0;
+  const uint4* sh = reinterpret_cast<const uint4*>(first ? shift0 : shift1);
+  const uint4* sc = reinterpret_cast<const uint4*>(first ? scale0 : scale1);
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<int64_t>(row) * ldy);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8], a[8], b[8];
+    unpack8(v[i], f);
+    unpack8(__ldg(sc + i * 32 + lane), a);
+    unpack8(__ldg(sh + i * 32 + lane), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (AFFINE) {
+        // F.layer_norm with weight/bias: one fp32 expression, one rounding
+        f[e] = (f[e] - mean) * rstd * a[e] + b[e];
+      } else {
+        // norm(x) -> bf16 ; (1 + scale) -> bf16 ; product -> bf16 ; + shift -> bf16   (DIT:63-64)
+        const float n = round_bf16((f[e] - mean) * rstd);
+        const float s1 = round_bf16(1.0f + a[e]);
+        f[e] = round_bf16(n * s1) + b[e];
+      }
+    }
+    yr[i * 32 + lane] = pack8(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm over the full row (all heads) + optional 3-D RoPE, in place.      DIT:91-110, 140-144
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowWarps * 32)
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float eps,
+                    const __nv_bfloat16* __restrict__ weight, const float2* __restrict__ rope_tab, int gf, int gh,
+                    int gw, int token_offset) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int D = NV * 256;
+  uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ldx);
+  uint4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8];
+    unpack8(v[i], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sq += f[e] * f[e];
+  }
+  const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+
+  // Every vector of this lane starts at column (i*32+lane)*8, i.e. head-local complex lanes
+  // c0..c0+3 with c0 = (lane % 16) * 4 — the same four rotation angles for all NV vectors.
+  float cs[4], sn[4];
+  bool rotate = false;
+  if (rope_tab != nullptr) {
+    const int t = token_offset + row;
+    if (t < gf * gh * gw) {
+      rotate = true;
+      const int fi = t / (gh * gw);
+      const int hi = (t / gw) % gh;
+      const int wi = t % gw;
+      const int c0 = (lane & 15) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        const int pos = c < 22 ? fi : (c < 43 ? hi : wi);
+        const float2 e = __ldg(rope_tab + pos * 64 + c);
+        cs[j] = e.x;
+        sn[j] = e.y;
+      }
+    }
+  }
+  const uint4* wr = reinterpret_cast<const uint4*>(weight);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8], w[8];
+    unpack8(v[i], f);
+    unpack8(__ldg(wr + i * 32 + lane), w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = round_bf16(round_bf16(f[e] * rs) * w[e]);  // norm -> bf16, * weight -> bf16
+    if (rotate) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = f[2 * j], b = f[2 * j + 1];
+        f[2 * j] = a * cs[j] - b * sn[j];
+        f[2 * j + 1] = a * sn[j] + b * cs[j];
+      }
+    }
+    xr[i * 32 + lane] = pack8(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CFG combine + flow-match Euler update + first-frame restore.          PIPE:302, 307-309; FM:144-154
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cfg_fm_one(float x, float np, float nn, bool has_neg, float cfg, float dsig) {
+  float n = np;
+  if (has_neg) n = round_bf16(nn + round_bf16(cfg * round_bf16(np - nn)));
+  return x + round_bf16(n * dsig);  // caller rounds the sum
+}
+
+__global__ void cfg_fm_step_kernel(__nv_bfloat16* __restrict__ lat, const __nv_bfloat16* __restrict__ npos,
+                                   const __nv_bfloat16* __restrict__ nneg, const __nv_bfloat16* __restrict__ first,
+                                   float cfg, float dsig, int channels, int frames, int hw, int vec) {
+  // one thread per `vec` (8 or 1) consecutive elements of the innermost (hw) axis
+  const int64_t per_plane = hw / vec;
+  const int64_t total = static_cast<int64_t>(channels) * frames * per_plane;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t plane = idx / per_plane;  // c * frames + f
+    const int f = static_cast<int>(plane % frames);
+    const int c = static_cast<int>(plane / frames);
+    const int64_t off = idx * vec;
+    if (vec == 8) {
+      uint4 out;
+      if (f == 0 && first != nullptr) {
+        out = *reinterpret_cast<const uint4*>(first + static_cast<int64_t>(c) * hw + (idx % per_plane) * 8);
+      } else {
+        float x[8], a[8], b[8];
+        unpack8(*reinterpret_cast<const uint4*>(lat + off), x);
+        unpack8(ldg_nc_v4(npos + off), a);
+        if (nneg) unpack8(ldg_nc_v4(nneg + off), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = cfg_fm_one(x[e], a[e], nneg ? b[e] : 0.f, nneg != nullptr, cfg, dsig);
+        out = pack8(x);
+      }
+      *reinterpret_cast<uint4*>(lat + off) = out;
+    } else {
+      if (f == 0 && first != nullptr) {
+        lat[off] = first[static_cast<int64_t>(c) * hw + (idx % per_plane)];
+      } else {
+        const float r = cfg_fm_one(__bfloat162float(lat[off]), __bfloat162float(npos[off]),
+                                   nneg ? __bfloat162float(nneg[off]) : 0.f, nneg != nullptr, cfg, dsig);
+        lat[off] = __float2bfloat16_rn(r);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// patchify (im2row for the k=s=(1,2,2) Conv3d) and unpatchify.                DIT:305, 338-351
+// ---------------------------------------------------------------------------------------------
+__global__ void patchify_rows_kernel(const __nv_bfloat16* __restrict__ lat, __nv_bfloat16* __restrict__ rows_out,
+                                     int64_t ld_rows, int channels, int gf, int gh, int gw, int token_offset,
+                                     int rows) {
+  const int64_t total = static_cast<int64_t>(rows) * channels;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % channels);
+  const int r = static_cast<int>(idx / channels);
+  const int t = token_offset + r;
+  uint2 out = make_uint2(0, 0);
+  if (t < gf * gh * gw) {
+    const int f = t / (gh * gw), h = (t / gw) % gh, w = t % gw;
+    const int64_t W2 = 2 * gw, H2 = 2 * gh;
+    const __nv_bfloat16* src = lat + ((static_cast<int64_t>(c) * gf + f) * H2 + 2 * h) * W2 + 2 * w;
+    out.x = *reinterpret_cast<const uint32_t*>(src);       // y = 0, z = 0..1
+    out.y = *reinterpret_cast<const uint32_t*>(src + W2);  // y = 1, z = 0..1
+  }
+  *reinterpret_cast<uint2*>(rows_out + static_cast<int64_t>(r) * ld_rows + c * 4) = out;
+}
+
+__global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ rows_in, int64_t ld_rows,
+                                  __nv_bfloat16* __restrict__ out, int channels, int gf, int gh, int gw) {
+  // one thread per (c, f, row of the latent, patch column) -> two adjacent output elements
+  const int64_t H2 = 2 * gh;
+  const int64_t total = static_cast<int64_t>(channels) * gf * H2 * gw;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int w = static_cast<int>(idx % gw);
+  const int hy = static_cast<int>((idx / gw) % H2);
+  const int f = static_cast<int>((idx / (gw * H2)) % gf);
+  const int c = static_cast<int>(idx / (gw * H2 * gf));
+  const int h = hy >> 1, y = hy & 1;
+  const int64_t t = (static_cast<int64_t>(f) * gh + h) * gw + w;
+  const __nv_bfloat16* src = rows_in + t * ld_rows + y * 2 * channels + c;
+  __nv_bfloat162 v;
+  v.x = src[0];         // z = 0
+  v.y = src[channels];  // z = 1
+  *reinterpret_cast<__nv_bfloat162*>(out + ((static_cast<int64_t>(c) * gf + f) * H2 + hy) * (2 * gw) + 2 * w) = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small embedding helpers                                                   DIT:67-71, 312-318
+// ---------------------------------------------------------------------------------------------
+__global__ void sinusoid_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int rows, int dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * dim) return;
+  const int r = idx / dim, j = idx % dim, half = dim / 2;
+  const int i = j < half ? j : j - half;
+  const double w = pow(10000.0, -static_cast<double>(i) / static_cast<double>(half));
+  const double a = static_cast<double>(t[r]) * w;
+  out[idx] = __float2bfloat16_rn(static_cast<float>(j < half ? cos(a) : sin(a)));
+}
+
+__global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  const float v = __bfloat162float(x[idx]);
+  y[idx] = __float2bfloat16_rn(v / (1.0f + expf(-v)));
+}
+
+__global__ void add_bcast_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                 __nv_bfloat16* __restrict__ out, int64_t n, int64_t cols, int64_t period) {
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  out[idx] = __float2bfloat16_rn(__bfloat162float(a[idx]) + __bfloat162float(b[(idx % cols) % period]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ulysses head re-partition pack / unpack                       xdit_context_parallel.py:125-146
+// ---------------------------------------------------------------------------------------------
+template <bool PACK>
+__global__ void sp_heads_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ buf,
+                                int s_local, int heads, int world) {
+  // buf is [world][s_local][heads/world * 128]; 16 vectors of 16 B per head row
+  const int hpr = heads / world;
+  const int64_t total = static_cast<int64_t>(s_local) * heads * 16;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(idx & 15);
+    const int head = static_cast<int>((idx >> 4) % heads);
+    const int64_t s = (idx >> 4) / heads;
+    const int peer = head / hpr, hh = head % hpr;
+    uint4* xp = reinterpret_cast<uint4*>(x + s * ldx + head * 128) + vec;
+    uint4* bp = reinterpret_cast<uint4*>(buf + ((static_cast<int64_t>(peer) * s_local + s) * hpr + hh) * 128) + vec;
+    if (PACK) *bp = *xp; else *xp = *bp;
+  }
+}
+
+static inline int grid_1d(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
+
+template <bool AFFINE>
+static int launch_ln(int nv, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, int64_t ldx, __nv_bfloat16* y,
+                     int64_t ldy, int rows, float eps, const __nv_bfloat16* sh0, const __nv_bfloat16* sc0,
+                     const __nv_bfloat16* sh1, const __nv_bfloat16* sc1, int rows_mod0) {
+#define FGB_LN_CASE(NV)                                                                                    \
+  case NV:                                                                                                 \
+    ln_kernel<NV, AFFINE><<<grid, kRowWarps * 32, 0, s>>>(x, ldx, y, ldy, rows, eps, sh0, sc0, sh1, sc1, rows_mod0); \
+    break;
+  switch (nv) {
+    FGB_LN_CASE(1) FGB_LN_CASE(2) FGB_LN_CASE(4) FGB_LN_CASE(6) FGB_LN_CASE(8) FGB_LN_CASE(12) FGB_LN_CASE(16)
+    FGB_LN_CASE(20)
+    default:
+      return set_error(FGB_ERR_UNSUPPORTED, "layer norm: dim %d is not one of 256*{1,2,4,6,8,12,16,20}", nv * 256);
+  }
+#undef FGB_LN_CASE
+  FGB_LAUNCH_CHECK("ln_kernel");
+  return FGB_OK;
+}
+
+}  // namespace fgb
+
+using namespace fgb;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int fgb_ln_modulate(fgb_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows,
+                               int32_t dim, float eps, const void* shift0, const void* scale0, const void* shift1,
+                               const void* scale1, int32_t rows_mod0, void* stream) {
+  FGB_CHECK_ARG(ctx && x && y && shift0 && scale0 && shift1 && scale1, "fgb_ln_modulate: NULL argument");
+  FGB_CHECK_ARG(rows > 0 && dim > 0 && dim % 256 == 0, "fgb_ln_modulate: rows=%d dim=%d (dim must be a multiple of 256)", rows, dim);
+  FGB_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(shift0) && aligned16(scale0) &&
+                    aligned16(shift1) && aligned16(scale1),
+                "fgb_ln_modulate: operands must be 16-byte aligned");
+  dim3 grid((rows + kRowWarps - 1) / kRowWarps);
+  return launch_ln<false>(dim / 256, grid, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), ldx,
+                          static_cast<bf16*>(y), ldy, rows, eps, static_cast<const bf16*>(shift0),
+                          static_cast<const bf16*>(scale0), static_cast<const bf16*>(shift1),
+                          static_cast<const bf16*>(scale1), rows_mod0);
+}
+
+extern "C" int fgb_ln_affine(fgb_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t dim,
+                             float eps, const void* weight, const void* bias, void* stream) {
+  FGB_CHECK_ARG(ctx && x && y && weight && bias, "fgb_ln_affine: NULL argument");
+  FGB_CHECK_ARG(rows > 0 && dim > 0 && dim % 256 == 0, "fgb_ln_affine: rows=%d dim=%d (dim must be a multiple of 256)", rows, dim);
+  FGB_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(weight) && aligned16(bias),
+                "fgb_ln_affine: operands must be 16-byte aligned");
+  dim3 grid((rows + kRowWarps - 1) / kRowWarps);
+  return launch_ln<true>(dim / 256, grid, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), ldx,
+                         static_cast<bf16*>(y), ldy, rows, eps, static_cast<const bf16*>(bias),
+                         static_cast<const bf16*>(weight), static_cast<const bf16*>(bias),
+                         static_cast<const bf16*>(weight), rows);
+}
+
+extern "C" int fgb_rmsnorm_rope(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows, int32_t dim, float eps,
+                                const void* weight, const void* rope_tab, int32_t gf, int32_t gh, int32_t gw,
+                                int32_t token_offset, void* stream) {
+  FGB_CHECK_ARG(ctx && x && weight, "fgb_rmsnorm_rope: NULL argument");
+  FGB_CHECK_ARG(rows > 0 && dim > 0 && dim % 256 == 0, "fgb_rmsnorm_rope: rows=%d dim=%d (dim must be a multiple of 256)", rows, dim);
+  FGB_CHECK_ARG(ldx % 8 == 0 && aligned16(x) && aligned16(weight), "fgb_rmsnorm_rope: operands must be 16-byte aligned");
+  if (rope_tab) {
+    FGB_CHECK_ARG(gf > 0 && gh > 0 && gw > 0 && gf <= 1024 && gh <= 1024 && gw <= 1024,
+                  "fgb_rmsnorm_rope: grid (%d,%d,%d) outside the 1024-position RoPE table", gf, gh, gw);
+    FGB_CHECK_ARG(token_offset >= 0, "fgb_rmsnorm_rope: negative token offset");
+  }
+  dim3 grid((rows + kRowWarps - 1) / kRowWarps);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bf16* xp = static_cast<bf16*>(x);
+  const bf16* wp = static_cast<const bf16*>(weight);
+  const float2* tab = static_cast<const float2*>(rope_tab);
+#define FGB_RMS_CASE(NV)                                                                                         \
+  case NV:                                                                                                       \
+    rmsnorm_rope_kernel<NV><<<grid, kRowWarps * 32, 0, s>>>(xp, ldx, rows, eps, wp, tab, gf, gh, gw, token_offset); \
+    break;
+  switch (dim / 256) {
+    FGB_RMS_CASE(1) FGB_RMS_CASE(2) FGB_RMS_CASE(4) FGB_RMS_CASE(6) FGB_RMS_CASE(8) FGB_RMS_CASE(12) FGB_RMS_CASE(16)
+    FGB_RMS_CASE(20)
+    default:
+      return set_error(FGB_ERR_UNSUPPORTED, "rmsnorm: dim %d is not one of 256*{1,2,4,6,8,12,16,20}", dim);
+  }
+#undef FGB_RMS_CASE
+  FGB_LAUNCH_CHECK("rmsnorm_rope_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_cfg_fm_step(fgb_ctx* ctx, void* latents, const void* noise_pos, const void* noise_neg,
+                               const void* first_frame, float cfg_scale, float sigma_delta, int32_t channels,
+                               int32_t frames, int32_t hw, void* stream) {
+  FGB_CHECK_ARG(ctx && latents && noise_pos, "fgb_cfg_fm_step: NULL argument");
+  FGB_CHECK_ARG(channels > 0 && frames > 0 && hw > 0, "fgb_cfg_fm_step: empty latent");
+  const bool vec8 = hw % 8 == 0 && aligned16(latents) && aligned16(noise_pos) && (!noise_neg || aligned16(noise_neg)) &&
+                    (!first_frame || aligned16(first_frame));
+  const int vec = vec8 ? 8 : 1;
+  const int64_t total = static_cast<int64_t>(channels) * frames * (hw / vec);
+  int grid = grid_1d(total, 256);
+  if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+  cfg_fm_step_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(latents), static_cast<const bf16*>(noise_pos), static_cast<const bf16*>(noise_neg),
+      static_cast<const bf16*>(first_frame), cfg_scale, sigma_delta, channels, frames, hw, vec);
+  FGB_LAUNCH_CHECK("cfg_fm_step_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_patchify_rows(fgb_ctx* ctx, const void* latents, void* rows_out, int64_t ld_rows, int32_t channels,
+                                 int32_t gf, int32_t gh, int32_t gw, int32_t token_offset, int32_t rows, void* stream) {
+  FGB_CHECK_ARG(ctx && latents && rows_out, "fgb_patchify_rows: NULL argument");
+  FGB_CHECK_ARG(channels > 0 && gf > 0 && gh > 0 && gw > 0 && rows > 0 && token_offset >= 0, "fgb_patchify_rows: bad shape");
+  FGB_CHECK_ARG(ld_rows >= channels * 4 && ld_rows % 4 == 0 && (reinterpret_cast<uintptr_t>(rows_out) & 7) == 0 &&
+                    (reinterpret_cast<uintptr_t>(latents) & 3) == 0,
+                "fgb_patchify_rows: alignment");
+  const int64_t total = static_cast<int64_t>(rows) * channels;
+  patchify_rows_kernel<<<grid_1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(latents), static_cast<bf16*>(rows_out), ld_rows, channels, gf, gh, gw, token_offset, rows);
+  FGB_LAUNCH_CHECK("patchify_rows_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_unpatchify(fgb_ctx* ctx, const void* head_rows, int64_t ld_rows, void* out, int32_t channels,
+                              int32_t gf, int32_t gh, int32_t gw, void* stream) {
+  FGB_CHECK_ARG(ctx && head_rows && out, "fgb_unpatchify: NULL argument");
+  FGB_CHECK_ARG(channels > 0 && gf > 0 && gh > 0 && gw > 0 && ld_rows >= 4 * channels, "fgb_unpatchify: bad shape");
+  FGB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 3) == 0, "fgb_unpatchify: out must be 4-byte aligned");
+  const int64_t total = static_cast<int64_t>(channels) * gf * 2 * gh * gw;
+  unpatchify_kernel<<<grid_1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(head_rows), ld_rows, static_cast<bf16*>(out), channels, gf, gh, gw);
+  FGB_LAUNCH_CHECK("unpatchify_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_sinusoidal_embedding(fgb_ctx* ctx, const void* timesteps_f32, void* out, int32_t rows, int32_t dim,
+                                        void* stream) {
+  FGB_CHECK_ARG(ctx && timesteps_f32 && out, "fgb_sinusoidal_embedding: NULL argument");
+  FGB_CHECK_ARG(rows > 0 && dim > 0 && dim % 2 == 0, "fgb_sinusoidal_embedding: rows=%d dim=%d", rows, dim);
+  sinusoid_kernel<<<grid_1d(static_cast<int64_t>(rows) * dim, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(timesteps_f32), static_cast<bf16*>(out), rows, dim);
+  FGB_LAUNCH_CHECK("sinusoid_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_silu(fgb_ctx* ctx, const void* x, void* y, int64_t n, void* stream) {
+  FGB_CHECK_ARG(ctx && x && y && n > 0, "fgb_silu: bad argument");
+  silu_kernel<<<grid_1d(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x),
+                                                                                static_cast<bf16*>(y), n);
+  FGB_LAUNCH_CHECK("silu_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_add_bcast(fgb_ctx* ctx, const void* a, const void* b, void* out, int64_t rows, int64_t cols,
+                             int64_t period, void* stream) {
+  FGB_CHECK_ARG(ctx && a && b && out && rows > 0 && cols > 0 && period > 0, "fgb_add_bcast: bad argument");
+  const int64_t n = rows * cols;
+  add_bcast_kernel<<<grid_1d(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(a), static_cast<const bf16*>(b), static_cast<bf16*>(out), n, cols, period);
+  FGB_LAUNCH_CHECK("add_bcast_kernel");
+  return FGB_OK;
+}
+
+static int sp_heads(fgb_ctx* ctx, bool pack, void* x, int64_t ldx, void* buf, int32_t s_local, int32_t heads,
+                    int32_t world, void* stream) {
+  FGB_CHECK_ARG(ctx && x && buf, "fgb_sp_(un)pack_heads: NULL argument");
+  FGB_CHECK_ARG(s_local > 0 && heads > 0 && world > 0 && heads % world == 0,
+                "fgb_sp_(un)pack_heads: heads=%d must divide by world=%d", heads, world);
+  FGB_CHECK_ARG(ldx % 8 == 0 && aligned16(x) && aligned16(buf), "fgb_sp_(un)pack_heads: alignment");
+  const int64_t total = static_cast<int64_t>(s_local) * heads * 16;
+  int grid = grid_1d(total, 256);
+  if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pack)
+    sp_heads_kernel<true><<<grid, 256, 0, s>>>(static_cast<bf16*>(x), ldx, static_cast<bf16*>(buf), s_local, heads, world);
+  else
+    sp_heads_kernel<false><<<grid, 256, 0, s>>>(static_cast<bf16*>(x), ldx, static_cast<bf16*>(buf), s_local, heads, world);
+  FGB_LAUNCH_CHECK("sp_heads_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_sp_pack_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* send, int32_t s_local, int32_t heads,
+                                 int32_t world, void* stream) {
+  return sp_heads(ctx, true, const_cast<void*>(x), ldx, send, s_local, heads, world, stream);
+}
+
+extern "C" int fgb_sp_unpack_heads(fgb_ctx* ctx, const void* recv, void* x, int64_t ldx, int32_t s_local, int32_t heads,
+                                   int32_t world, void* stream) {
+  return sp_heads(ctx, false, x, ldx, const_cast<void*>(recv), s_local, heads, world, stream);
+}

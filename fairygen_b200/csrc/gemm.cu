@@ -1,0 +1,294 @@
+// fairygen_b200 — bf16 GEMM with fused epilogues on tcgen05 tensor cores (sm_100a).
+//
+//   C[m,n] = epilogue(A[m,k] · W[n,k]ᵀ + bias[n])
+//
+// Replaces every nn.Linear of the DiT block (reference: animation/diffsynth/models/wan_video_dit.py
+// :140-146 q/k/v/o, :176-185 cross q/k/v/o, :208-209 ffn, :258 head, :305 patch embedding as a
+// GEMM, :307-318 time/text embeddings) together with the elementwise ops that follow them
+// (GELU-tanh :208, GateModule :192-193, residual add :226).
+//
+// Design (one persistent CTA per SM, warp-specialised, 192 threads):
+//   warp 0      TMA producer: A tile [128 x 64] and W tile [256 x 64] (128-byte swizzle) into a
+//               4-stage shared-memory ring, completion on mbarriers.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16, bf16 -> fp32) with
+//               the accumulator in TMEM; two 256-column accumulators so the epilogue of tile i
+//               overlaps the main loop of tile i+1. tcgen05.commit frees ring slots.
+//   warps 2-5   epilogue: tcgen05.ld (one accumulator row per thread), bias / GELU / gate /
+//               residual in fp32 with the reference's bf16 rounding points, 16-byte global stores.
+// Tiles are rasterised in groups of 8 M-blocks so the CTAs resident at one time share A and W
+// tiles through the 126 MB L2.
+#include "common.cuh"
+#include "host.h"
+
+namespace fgb {
+
+constexpr int kBM = 128;
+constexpr int kBN = 256;
+constexpr int kBK = 64;
+constexpr int kStages = 4;
+constexpr int kGroupM = 8;
+constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+constexpr int kBBytes = kBN * kBK * 2;  // 32 KB
+constexpr int kGemmThreads = 192;
+constexpr int kGemmSmem = kStages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* c;
+  const __nv_bfloat16* gate0;
+  const __nv_bfloat16* gate1;
+  int64_t ldc;
+  int32_t m, n, k;
+  int32_t rows_gate0;
+  int32_t m_blocks, n_blocks, tiles, k_blocks;
+};
+
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
+  const int group_size = kGroupM * p.n_blocks;
+  const int group = tile / group_size;
+  const int first_m = group * kGroupM;
+  const int gsz = min(p.m_blocks - first_m, kGroupM);
+  const int in_group = tile - group * group_size;
+  m_blk = first_m + in_group % gsz;
+  n_blk = in_group / gsz;
+}
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  — nn.GELU(approximate='tanh')
+  const float kAlpha = 0.7978845608028654f, kBeta = 0.044715f;
+  float inner = kAlpha * (x + kBeta * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  return 0.5f * x * (1.0f + t);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytes));
+  uint64_t* full = bars;                   // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + kStages;        // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kStages;      // [2]   MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * kStages + 2; // [2]   epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------- TMA producer -------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(p, tile, m_blk, n_blk);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], kABytes + kBBytes);
+          tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full[stage], kb * kBK, m_blk * kBM, kEvictNormal);
+          tma_load_2d(smem_b + stage * kBBytes, &tmap_b, &full[stage], kb * kBK, n_blk * kBN, kEvictLast);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------- MMA issuer ---------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kBN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adesc = make_sdesc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = make_sdesc_sw128(b_addr + k * 32, 16, 1024);
+            umma_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty[stage]);  // ring slot reusable once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tmem_full[acc]);  // accumulator complete
+      }
+    }
+  } else {
+    // --------------------------------- epilogue -----------------------------------
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are visible to this warp
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
+      int m_blk, n_blk;
+      tile_coords(p, tile, m_blk, n_blk);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * kBM + quarter * 32 + lane;
+      const bool row_ok = row < p.m;
+      __nv_bfloat16* crow = p.c + static_cast<int64_t>(row) * p.ldc;
+      const __nv_bfloat16* gate = nullptr;
+      if (EPI == FGB_EPI_GATED_RESIDUAL) gate = (row < p.rows_gate0) ? p.gate0 : p.gate1;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN;
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        const int col0 = n_blk * kBN + c * 32;
+        if (col0 >= p.n) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = col0 + g * 8;
+          if (col >= p.n) break;
+          float y[8];
+          uint4 bv = make_uint4(0, 0, 0, 0);
+          if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+          const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            y[2 * i] = round_bf16(__uint_as_float(r[g * 8 + 2 * i]) + bf16_lo(bw[i]));
+            y[2 * i + 1] = round_bf16(__uint_as_float(r[g * 8 + 2 * i + 1]) + bf16_hi(bw[i]));
+          }
+          if (EPI == FGB_EPI_BIAS_GELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = gelu_tanh_f(y[i]);
+          }
+          if (EPI == FGB_EPI_GATED_RESIDUAL || EPI == FGB_EPI_RESIDUAL) {
+            if (row_ok) {
+              const uint4 xv = *reinterpret_cast<const uint4*>(crow + col);
+              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+              if (EPI == FGB_EPI_GATED_RESIDUAL) {
+                const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate + col));
+                const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  y[2 * i] = bf16_lo(xw[i]) + round_bf16(bf16_lo(gw[i]) * y[2 * i]);
+                  y[2 * i + 1] = bf16_hi(xw[i]) + round_bf16(bf16_hi(gw[i]) * y[2 * i + 1]);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  y[2 * i] = bf16_lo(xw[i]) + y[2 * i];
+                  y[2 * i + 1] = bf16_hi(xw[i]) + y[2 * i + 1];
+                }
+              }
+            }
+          }
+          if (row_ok) {
+            uint4 o;
+            o.x = pack_bf16(y[0], y[1]);
+            o.y = pack_bf16(y[2], y[3]);
+            o.z = pack_bf16(y[4], y[5]);
+            o.w = pack_bf16(y[6], y[7]);
+            *reinterpret_cast<uint4*>(crow + col) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int EPI>
+static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t stream) {
+  auto kfn = gemm_bf16_kernel<EPI>;
+  static bool configured = false;  // per template instance; attribute is sticky per function
+  if (!configured) {
+    FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    configured = true;
+  }
+  const int grid = p.tiles < ctx->sm_count ? p.tiles : ctx->sm_count;
+  kfn<<<grid, kGemmThreads, kGemmSmem, stream>>>(ta, tb, p);
+  FGB_LAUNCH_CHECK("gemm_bf16_kernel");
+  return FGB_OK;
+}
+
+}  // namespace fgb
+
+extern "C" int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias,
+                             void* c, int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue,
+                             const void* gate0, const void* gate1, int32_t rows_gate0, void* stream) {
+  using namespace fgb;
+  FGB_CHECK_ARG(ctx, "fgb_gemm_bf16: ctx is NULL");
+  FGB_CHECK_ARG(a && w && c, "fgb_gemm_bf16: NULL matrix pointer");
+  FGB_CHECK_ARG(m > 0 && n > 0 && k > 0, "fgb_gemm_bf16: empty problem m=%d n=%d k=%d", m, n, k);
+  FGB_CHECK_ARG(n % 8 == 0 && k % 8 == 0, "fgb_gemm_bf16: n=%d and k=%d must be multiples of 8", n, k);
+  FGB_CHECK_ARG(lda >= k && ldw >= k && ldc >= n, "fgb_gemm_bf16: leading dimension too small");
+  FGB_CHECK_ARG(ldc % 8 == 0 && aligned16(c), "fgb_gemm_bf16: C must be 16-byte aligned with ldc %% 8 == 0");
+  FGB_CHECK_ARG(!bias || aligned16(bias), "fgb_gemm_bf16: bias must be 16-byte aligned");
+  FGB_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "fgb_gemm_bf16: unknown epilogue %d", epilogue);
+  if (epilogue == FGB_EPI_GATED_RESIDUAL)
+    FGB_CHECK_ARG(gate0 && gate1 && aligned16(gate0) && aligned16(gate1),
+                  "fgb_gemm_bf16: gated residual needs 16-byte aligned gate0/gate1");
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(ctx, &tb, w, n, k, ldw, kBN);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.c = static_cast<__nv_bfloat16*>(c);
+  p.gate0 = static_cast<const __nv_bfloat16*>(gate0);
+  p.gate1 = static_cast<const __nv_bfloat16*>(gate1);
+  p.ldc = ldc;
+  p.m = m;
+  p.n = n;
+  p.k = k;
+  p.rows_gate0 = rows_gate0;
+  p.m_blocks = (m + kBM - 1) / kBM;
+  p.n_blocks = (n + kBN - 1) / kBN;
+  p.tiles = p.m_blocks * p.n_blocks;
+  p.k_blocks = (k + kBK - 1) / kBK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (epilogue) {
+    case FGB_EPI_BIAS: return launch_gemm<FGB_EPI_BIAS>(ctx, ta, tb, p, s);
+    case FGB_EPI_BIAS_GELU_TANH: return launch_gemm<FGB_EPI_BIAS_GELU_TANH>(ctx, ta, tb, p, s);
+    case FGB_EPI_GATED_RESIDUAL: return launch_gemm<FGB_EPI_GATED_RESIDUAL>(ctx, ta, tb, p, s);
+    default: return launch_gemm<FGB_EPI_RESIDUAL>(ctx, ta, tb, p, s);
+  }
+}

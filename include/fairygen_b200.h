@@ -1,0 +1,145 @@
+/* fairygen_b200 — C ABI of the B200-native Wan2.2-TI2V-5B DiT denoise hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one group of library-kernel call sites
+ * of the reference (CloudEngineHub/FairyGen, animation/diffsynth). The reference has no native
+ * code and no FFI of its own — its "operator API" for this path is the set of torch calls made by
+ * diffsynth/models/wan_video_dit.py (DIT), diffsynth/pipelines/wan_video.py (PIPE) and
+ * diffsynth/diffusion/flow_match.py (FM); each declaration below cites the lines it replaces.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (PyTorch); the library never allocates
+ *    or frees device memory. Matrices are row-major with the last dimension contiguous; `ld*` are
+ *    leading dimensions in ELEMENTS. bf16 unless stated. Pointers and leading dimensions of
+ *    matrices that feed tensor-core kernels must be 16-byte aligned.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). Every call only
+ *    enqueues work; nothing synchronises except fgb_sync_check.
+ *  - Every function returns 0 on success, a non-zero fgb_status otherwise; fgb_last_error() gives
+ *    the message for the calling thread. No exit()/abort() inside the library.
+ *  - There is NO CPU fallback: without a CUDA device fgb_create fails.
+ */
+#ifndef FAIRYGEN_B200_H_
+#define FAIRYGEN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGB_ABI_VERSION 1
+#define FGB_HEAD_DIM 128 /* Wan2.2-TI2V-5B: dim 3072 / 24 heads (model_configs.py:294) */
+
+typedef enum fgb_status {
+  FGB_OK = 0,
+  FGB_ERR_INVALID = 1,     /* bad argument (shape, alignment, null pointer) */
+  FGB_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed            */
+  FGB_ERR_UNSUPPORTED = 3, /* not an sm_100 device, or unsupported shape     */
+} fgb_status;
+
+/* Epilogues of fgb_gemm_bf16. acc = A·Wᵀ in fp32; y = bf16(acc + bias). */
+typedef enum fgb_epilogue {
+  FGB_EPI_BIAS = 0,           /* C = y                                   nn.Linear, DIT:140-142,176-178 */
+  FGB_EPI_BIAS_GELU_TANH = 1, /* C = gelu_tanh(y)                        ffn[0]+ffn[1], DIT:208-209     */
+  FGB_EPI_GATED_RESIDUAL = 2, /* C = C + gate[row] * y                   GateModule, DIT:192-193,225,228 */
+  FGB_EPI_RESIDUAL = 3,       /* C = C + y                               cross-attn residual, DIT:226   */
+} fgb_epilogue;
+
+typedef struct fgb_ctx fgb_ctx;
+
+int fgb_abi_version(void);
+const char* fgb_last_error(void);
+
+/* One context per process/GPU (the reference is one process per GPU, xdit_context_parallel.py:21). */
+int fgb_create(int device, fgb_ctx** out);
+int fgb_destroy(fgb_ctx* ctx);
+/* cudaStreamSynchronize + sticky-error check (asynchronous kernel faults surface here). */
+int fgb_sync_check(fgb_ctx* ctx, void* stream);
+int fgb_sm_count(fgb_ctx* ctx);
+
+/* ---- tensor-core kernels (tcgen05 + TMEM + TMA) ------------------------------------------- */
+
+/* C[m,n] = epilogue(A[m,k] · W[n,k]ᵀ + bias[n]).  W is an nn.Linear weight as stored ([out,in]).
+ * Replaces every nn.Linear on the path: q/k/v/o (DIT:140-146, 176-185), ffn (DIT:208-209),
+ * head (DIT:258,264), patch_embedding as a GEMM (DIT:305), time/text embeddings (DIT:307-318).
+ * GATED_RESIDUAL: row r uses gate0 when r < rows_gate0, else gate1 (the TI2V per-token timestep
+ * of PIPE:1218-1228 has only two distinct modulation rows); gate0/gate1 are [n] bf16.
+ * bias may be NULL. k*2 bytes and all leading dimensions*2 bytes must be multiples of 16. */
+int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias,
+                  void* c, int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue,
+                  const void* gate0, const void* gate1, int32_t rows_gate0, void* stream);
+
+/* o = softmax(q kᵀ · scale) v per head, no mask, non-causal; head_dim = 128.
+ * q,o: [s_q, heads*128]; k,v: [s_kv, heads*128] (row strides ldq/ldk/ldv/ldo elements).
+ * Replaces flash_attention()/AttentionModule for self- and cross-attention (DIT:27-60, 113-120,
+ * 145, 179). Keys at index >= s_kv do not exist (no padding attends). */
+int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                 int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
+                 void* stream);
+
+/* ---- fused memory-bound kernels ------------------------------------------------------------ */
+
+/* y = LayerNorm(x; eps, no affine) * (1 + scale[row]) + shift[row]; rows < rows_mod0 use
+ * (shift0, scale0), the rest (shift1, scale1); each [dim] bf16.
+ * Replaces norm1/norm2 + modulate (DIT:205-206, 63-64, 224, 227) and Head's norm+modulate
+ * (DIT:257, 262-267) without materialising the (1,S,6,D) t_mod of PIPE:1228 / DIT:217-223. */
+int fgb_ln_modulate(fgb_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t dim,
+                    float eps, const void* shift0, const void* scale0, const void* shift1, const void* scale1,
+                    int32_t rows_mod0, void* stream);
+
+/* y = LayerNorm(x; eps) * weight + bias   (norm3, DIT:207, 226). */
+int fgb_ln_affine(fgb_ctx* ctx, const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t dim,
+                  float eps, const void* weight, const void* bias, void* stream);
+
+/* In place: x = RMSNorm(x over the full row of `dim`; eps) * weight, then (if rope_tab != NULL) the
+ * 3-D RoPE of rope_apply on adjacent pairs within each 128-wide head.
+ * rope_tab: float2 [1024][64] (cos, sin) — lanes [0,22) rotate with the frame index, [22,43) with the
+ * row index, [43,64) with the column index (precompute_freqs_cis_3d, DIT:74-88, 325); token t of
+ * this call is global token (token_offset + t) in (f h w) order; tokens >= gf*gh*gw are left
+ * un-rotated (the ones-padding of xdit_context_parallel.py:30-55).
+ * Replaces RMSNorm (DIT:99-110, 140-141, 176-177) + rope_apply (DIT:91-96, 143-144). */
+int fgb_rmsnorm_rope(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows, int32_t dim, float eps, const void* weight,
+                     const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, int32_t token_offset, void* stream);
+
+/* rows[t, c*4 + y*2 + z] = latents[c, f, 2h+y, 2w+z] for token t = (f h w): the im2row side of the
+ * Conv3d(k=s=(1,2,2)) patch embedding (DIT:305, 338-344; PIPE:1253, 1260-1261). latents is
+ * [channels, gf, 2*gh, 2*gw] contiguous; writes tokens [token_offset, token_offset+rows). */
+int fgb_patchify_rows(fgb_ctx* ctx, const void* latents, void* rows_out, int64_t ld_rows, int32_t channels,
+                      int32_t gf, int32_t gh, int32_t gw, int32_t token_offset, int32_t rows, void* stream);
+
+/* out[c, f, 2h+y, 2w+z] = head_rows[t, y*2*channels + z*channels + c]  (unpatchify, DIT:346-351). */
+int fgb_unpatchify(fgb_ctx* ctx, const void* head_rows, int64_t ld_rows, void* out, int32_t channels, int32_t gf,
+                   int32_t gh, int32_t gw, void* stream);
+
+/* One fused denoising update on the latent [channels, frames, hw] (bf16, in place):
+ *   n   = noise_neg + cfg_scale * (noise_pos - noise_neg)     (PIPE:302; noise_neg NULL -> n = noise_pos)
+ *   x   = x + n * sigma_delta                                  (FlowMatchScheduler.step, FM:144-154)
+ *   x[:, 0] = first_frame                                      (PIPE:308-309; first_frame NULL -> skip)
+ * with the reference's bf16 rounding after every tensor op. */
+int fgb_cfg_fm_step(fgb_ctx* ctx, void* latents, const void* noise_pos, const void* noise_neg,
+                    const void* first_frame, float cfg_scale, float sigma_delta, int32_t channels, int32_t frames,
+                    int32_t hw, void* stream);
+
+/* out[r, :] = [cos(t_r * w_i), sin(t_r * w_i)], w_i = 10000^(-i/(dim/2)), computed in fp64 and
+ * rounded to bf16 (sinusoidal_embedding_1d, DIT:67-71). timesteps: fp32 [rows]. */
+int fgb_sinusoidal_embedding(fgb_ctx* ctx, const void* timesteps_f32, void* out, int32_t rows, int32_t dim,
+                             void* stream);
+
+/* y = silu(x) elementwise, bf16 (nn.SiLU in time_embedding/time_projection, DIT:312-318). */
+int fgb_silu(fgb_ctx* ctx, const void* x, void* y, int64_t n, void* stream);
+
+/* out[r, j] = bf16(a[r, j] + b[j % period])  — `modulation + t_mod` (DIT:217-218, 263, 266). */
+int fgb_add_bcast(fgb_ctx* ctx, const void* a, const void* b, void* out, int64_t rows, int64_t cols,
+                  int64_t period, void* stream);
+
+/* ---- Ulysses sequence-parallel re-partition (xdit_context_parallel.py:125-146) --------------
+ * Pack/unpack between token-sharded [s_local, heads*128] and the peer-major exchange buffer
+ * [world][s_local][heads/world * 128] that an all-to-all (NCCL or peer stores) moves. */
+int fgb_sp_pack_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* send, int32_t s_local, int32_t heads,
+                      int32_t world, void* stream);
+int fgb_sp_unpack_heads(fgb_ctx* ctx, const void* recv, void* x, int64_t ldx, int32_t s_local, int32_t heads,
+                        int32_t world, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAIRYGEN_B200_H_ */
