@@ -1,0 +1,101 @@
+"""ctypes binding of the C ABI declared in ``include/fairygen_b200.h``.
+
+The shared library is built in-tree (``fairygen_b200/libfairygen_b200.so``) by
+``fairygen_b200/csrc/Makefile``.  There is no fallback: if the library is missing, or a call
+returns non-zero, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfairygen_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+# name -> (restype, argtypes); must list every symbol of include/fairygen_b200.h
+_P, _I32, _I64, _F = c_void_p, c_int32, c_int64, c_float
+SIGNATURES = {
+    "fgb_abi_version": (ctypes.c_int, []),
+    "fgb_last_error": (c_char_p, []),
+    "fgb_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_void_p)]),
+    "fgb_destroy": (ctypes.c_int, [_P]),
+    "fgb_sync_check": (ctypes.c_int, [_P, _P]),
+    "fgb_sm_count": (ctypes.c_int, [_P]),
+    "fgb_gemm_bf16": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
+    "fgb_attn_fwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P]),
+    "fgb_ln_modulate": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _I32, _P]),
+    "fgb_ln_affine": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
+    "fgb_rmsnorm_rope": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _F, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "fgb_patchify_rows": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "fgb_unpatchify": (ctypes.c_int, [_P, _P, _I64, _P, _I32, _I32, _I32, _I32, _P]),
+    "fgb_cfg_fm_step": (ctypes.c_int, [_P, _P, _P, _P, _P, _F, _F, _I32, _I32, _I32, _P]),
+    "fgb_sinusoidal_embedding": (ctypes.c_int, [_P, _P, _P, _I32, _I32, _P]),
+    "fgb_silu": (ctypes.c_int, [_P, _P, _P, _I64, _P]),
+    "fgb_add_bcast": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P]),
+    "fgb_sp_pack_heads": (ctypes.c_int, [_P, _P, _I64, _P, _I32, _I32, _I32, _I32, _P]),
+    "fgb_sp_unpack_heads": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P]),
+}
+
+EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_GATED_RESIDUAL, EPI_RESIDUAL = 0, 1, 2, 3
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the shared library for sm_100a with nvcc (cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libfairygen_b200.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    if verbose:
+        print(res.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load the C-ABI library (once).  Raises if it has not been built — there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `make -C {CSRC_DIR}` or `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "fairygen_b200 has no CPU / PyTorch fallback."
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().fgb_last_error()
+        raise RuntimeError(f"fairygen_b200 {what} failed (status {rc}): {msg.decode() if msg else '?'}")
+
+
+class Context:
+    """Owns one ``fgb_ctx`` (one per process/GPU)."""
+
+    def __init__(self, device_index: int = 0):
+        self._lib = lib()
+        handle = c_void_p()
+        check(self._lib.fgb_create(device_index, ctypes.byref(handle)), "fgb_create")
+        self.handle = handle
+        self.device_index = device_index
+        self.sm_count = self._lib.fgb_sm_count(handle)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.fgb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

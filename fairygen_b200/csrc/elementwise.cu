@@ -282,18 +282,22 @@ __global__ void add_bcast_kernel(const __nv_bfloat16* __restrict__ a, const __nv
 // ---------------------------------------------------------------------------------------------
 template <bool PACK>
 __global__ void sp_heads_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ buf,
-                                int s_local, int heads, int world) {
-  // buf is [world][s_local][heads/world * 128]; 16 vectors of 16 B per head row
+                                int s_local, int heads, int groups, int world) {
+  // x is [s_local][groups][heads][128] (e.g. groups = 3 for a fused q|k|v row);
+  // buf is [world][s_local][groups][heads/world][128]; 16 vectors of 16 B per head row.
   const int hpr = heads / world;
-  const int64_t total = static_cast<int64_t>(s_local) * heads * 16;
+  const int gh = groups * heads;
+  const int64_t total = static_cast<int64_t>(s_local) * gh * 16;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int vec = static_cast<int>(idx & 15);
-    const int head = static_cast<int>((idx >> 4) % heads);
-    const int64_t s = (idx >> 4) / heads;
+    const int g_head = static_cast<int>((idx >> 4) % gh);
+    const int64_t s = (idx >> 4) / gh;
+    const int grp = g_head / heads, head = g_head % heads;
     const int peer = head / hpr, hh = head % hpr;
-    uint4* xp = reinterpret_cast<uint4*>(x + s * ldx + head * 128) + vec;
-    uint4* bp = reinterpret_cast<uint4*>(buf + ((static_cast<int64_t>(peer) * s_local + s) * hpr + hh) * 128) + vec;
+    uint4* xp = reinterpret_cast<uint4*>(x + s * ldx + static_cast<int64_t>(g_head) * 128) + vec;
+    uint4* bp = reinterpret_cast<uint4*>(
+                    buf + (((static_cast<int64_t>(peer) * s_local + s) * groups + grp) * hpr + hh) * 128) + vec;
     if (PACK) *bp = *xp; else *xp = *bp;
   }
 }
@@ -456,29 +460,30 @@ extern "C" int fgb_add_bcast(fgb_ctx* ctx, const void* a, const void* b, void* o
 }
 
 static int sp_heads(fgb_ctx* ctx, bool pack, void* x, int64_t ldx, void* buf, int32_t s_local, int32_t heads,
-                    int32_t world, void* stream) {
+                    int32_t groups, int32_t world, void* stream) {
   FGB_CHECK_ARG(ctx && x && buf, "fgb_sp_(un)pack_heads: NULL argument");
-  FGB_CHECK_ARG(s_local > 0 && heads > 0 && world > 0 && heads % world == 0,
+  FGB_CHECK_ARG(s_local > 0 && heads > 0 && groups > 0 && world > 0 && heads % world == 0,
                 "fgb_sp_(un)pack_heads: heads=%d must divide by world=%d", heads, world);
-  FGB_CHECK_ARG(ldx % 8 == 0 && aligned16(x) && aligned16(buf), "fgb_sp_(un)pack_heads: alignment");
-  const int64_t total = static_cast<int64_t>(s_local) * heads * 16;
+  FGB_CHECK_ARG(ldx % 8 == 0 && ldx >= static_cast<int64_t>(groups) * heads * 128 && aligned16(x) && aligned16(buf),
+                "fgb_sp_(un)pack_heads: alignment / leading dimension");
+  const int64_t total = static_cast<int64_t>(s_local) * groups * heads * 16;
   int grid = grid_1d(total, 256);
   if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (pack)
-    sp_heads_kernel<true><<<grid, 256, 0, s>>>(static_cast<bf16*>(x), ldx, static_cast<bf16*>(buf), s_local, heads, world);
+    sp_heads_kernel<true><<<grid, 256, 0, s>>>(static_cast<bf16*>(x), ldx, static_cast<bf16*>(buf), s_local, heads, groups, world);
   else
-    sp_heads_kernel<false><<<grid, 256, 0, s>>>(static_cast<bf16*>(x), ldx, static_cast<bf16*>(buf), s_local, heads, world);
+    sp_heads_kernel<false><<<grid, 256, 0, s>>>(static_cast<bf16*>(x), ldx, static_cast<bf16*>(buf), s_local, heads, groups, world);
   FGB_LAUNCH_CHECK("sp_heads_kernel");
   return FGB_OK;
 }
 
 extern "C" int fgb_sp_pack_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* send, int32_t s_local, int32_t heads,
-                                 int32_t world, void* stream) {
-  return sp_heads(ctx, true, const_cast<void*>(x), ldx, send, s_local, heads, world, stream);
+                                 int32_t groups, int32_t world, void* stream) {
+  return sp_heads(ctx, true, const_cast<void*>(x), ldx, send, s_local, heads, groups, world, stream);
 }
 
 extern "C" int fgb_sp_unpack_heads(fgb_ctx* ctx, const void* recv, void* x, int64_t ldx, int32_t s_local, int32_t heads,
-                                   int32_t world, void* stream) {
-  return sp_heads(ctx, false, x, ldx, const_cast<void*>(recv), s_local, heads, world, stream);
+                                   int32_t groups, int32_t world, void* stream) {
+  return sp_heads(ctx, false, x, ldx, const_cast<void*>(recv), s_local, heads, groups, world, stream);
 }

@@ -1,0 +1,140 @@
+"""Drop-in for ``pipe.model_fn`` = ``model_fn_wan_video`` (reference animation/diffsynth/pipelines/
+wan_video.py:1122-1388), TI2V-5B branches, backed by the sm_100a kernels.
+
+Boundary: the reference calls ``self.model_fn(**models, **inputs_shared,
+**inputs_posi, timestep=timestep)`` (wan_video.py:296, 301; diffusion/loss.py:17).  This function
+honours that keyword signature, swallows the ~40 unrelated keys in ``**kwargs`` and returns the
+velocity prediction with the shape/dtype/device of ``latents``.  The reference ``WanModel`` stays
+the weight container (so ``pipe.load_lora(pipe.dit, ...)`` keeps working); the engine re-packs from
+it whenever a parameter's version counter changes.
+
+    import fairygen_b200
+    fairygen_b200.install(pipe)        # pipe.model_fn -> this file; pipe.scheduler -> fused step
+    video = pipe(prompt=..., input_image=..., ...)   # unchanged reference call
+
+Anything outside the TI2V-5B inference path (VACE, S2V audio, Animate, VAP, LongCat, camera/motion
+controllers, reference latents, TeaCache, sliding windows, CLIP/VAE-concat image inputs) raises
+``NotImplementedError`` instead of silently falling back.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .config import WanDiTConfig
+from .engine import WanDiTEngine
+
+_ENGINE_ATTR = "_fairygen_b200_engine"
+_VERSION_ATTR = "_fairygen_b200_weight_version"
+
+
+def _weights_version(dit) -> int:
+    return sum(p._version for p in dit.parameters()) + sum(id(p) & 0xFFFF for p in dit.parameters())
+
+
+def engine_for(dit, sp=None) -> WanDiTEngine:
+    """Engine attached to a reference ``WanModel``; packs (or re-packs after ``load_lora``) lazily."""
+    eng: Optional[WanDiTEngine] = getattr(dit, _ENGINE_ATTR, None)
+    version = _weights_version(dit)
+    if eng is None or (sp is not None and eng.sp is not sp):
+        device = next(dit.parameters()).device
+        eng = WanDiTEngine(WanDiTConfig.from_module(dit), device=device, sp=sp)
+        object.__setattr__(dit, _ENGINE_ATTR, eng)
+        object.__setattr__(dit, _VERSION_ATTR, None)
+    if getattr(dit, _VERSION_ATTR, None) != version:
+        eng.load_state_dict(dit.state_dict())
+        object.__setattr__(dit, _VERSION_ATTR, version)
+    return eng
+
+
+def _reject(name: str, value) -> None:
+    if value is not None:
+        raise NotImplementedError(f"fairygen_b200 model_fn: `{name}` is outside the Wan2.2-TI2V-5B hot path (SURVEY.md §2, out of scope)")
+
+
+def model_fn_wan_video(
+    dit=None,
+    motion_controller=None,
+    vace=None,
+    vap=None,
+    animate_adapter=None,
+    latents: torch.Tensor = None,
+    timestep: torch.Tensor = None,
+    context: torch.Tensor = None,
+    clip_feature=None,
+    y=None,
+    reference_latents=None,
+    vace_context=None,
+    vace_scale=1.0,
+    audio_embeds=None,
+    motion_latents=None,
+    s2v_pose_latents=None,
+    vap_hidden_state=None,
+    vap_clip_feature=None,
+    context_vap=None,
+    drop_motion_frames: bool = True,
+    tea_cache=None,
+    use_unified_sequence_parallel: bool = False,
+    motion_bucket_id=None,
+    pose_latents=None,
+    face_pixel_values=None,
+    longcat_latents=None,
+    sliding_window_size=None,
+    sliding_window_stride=None,
+    cfg_merge: bool = False,
+    use_gradient_checkpointing: bool = False,
+    use_gradient_checkpointing_offload: bool = False,
+    control_camera_latents_input=None,
+    fuse_vae_embedding_in_latents: bool = False,
+    **kwargs,
+):
+    for name, value in (("vace_context", vace_context), ("audio_embeds", audio_embeds), ("reference_latents", reference_latents),
+                        ("tea_cache", tea_cache), ("pose_latents", pose_latents), ("face_pixel_values", face_pixel_values),
+                        ("longcat_latents", longcat_latents), ("sliding_window_size", sliding_window_size),
+                        ("control_camera_latents_input", control_camera_latents_input), ("vap_hidden_state", vap_hidden_state)):
+        _reject(name, value)
+    if motion_bucket_id is not None and motion_controller is not None:
+        _reject("motion_controller", motion_controller)
+    if y is not None and getattr(dit, "require_vae_embedding", False):
+        _reject("y (VAE-concat image conditioning)", y)
+    if clip_feature is not None and getattr(dit, "require_clip_embedding", False):
+        _reject("clip_feature", clip_feature)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in dit.parameters()):
+        raise NotImplementedError("fairygen_b200 model_fn is forward-only (inference path); training backward is §8 'next'")
+    if latents is None or timestep is None or context is None or dit is None:
+        raise ValueError("model_fn_wan_video needs dit, latents, timestep and context")
+
+    sp = None
+    if use_unified_sequence_parallel:
+        import torch.distributed as dist
+
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            from .sp import SequenceParallel
+
+            sp = getattr(dit, "_fairygen_b200_sp", None)
+            if sp is None:
+                sp = SequenceParallel()
+                object.__setattr__(dit, "_fairygen_b200_sp", sp)
+    eng = engine_for(dit, sp)
+
+    # merged CFG (PIPE:785-803, 1240-1243): one latent, a batch of contexts -> one forward per context
+    outs = []
+    for b in range(context.shape[0]):
+        lat_b = latents[b:b + 1] if latents.shape[0] == context.shape[0] else latents[0:1]
+        outs.append(eng.forward(lat_b, timestep, context[b:b + 1], fuse_vae_embedding_in_latents))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+
+def install(pipe, fused_scheduler: bool = True):
+    """Point a reference ``WanVideoPipeline`` at the B200 path.  ``pipe.model_fn`` is the attribute the
+    reference itself swaps behaviour through (wan_video.py:81); ``pipe.scheduler`` gets the fused
+    flow-match step with identical ``set_timesteps`` / ``step`` semantics (flow_match.py:29-39, 132-154)."""
+    pipe.model_fn = model_fn_wan_video
+    if fused_scheduler:
+        from .scheduler import FlowMatchScheduler
+
+        pipe.scheduler = FlowMatchScheduler("Wan")
+    if getattr(pipe, "dit", None) is not None:
+        engine_for(pipe.dit)
+    return pipe

@@ -1,0 +1,228 @@
+"""Torch-tensor front end of the C ABI (``include/fairygen_b200.h``).
+
+PyTorch is used for device memory and streams only; every function here forwards raw device
+pointers to a hand-written sm_100a kernel and raises on any non-zero status.  No function has a
+PyTorch / CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from ctypes import c_void_p
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_GATED_RESIDUAL, EPI_RESIDUAL  # noqa: F401
+
+BF16 = torch.bfloat16
+_ctx_by_device = {}
+
+
+def context(device: torch.device) -> _lib.Context:
+    """One fgb_ctx per CUDA device of this process."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"fairygen_b200 runs on CUDA (sm_100a) only, got device {device}; there is no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _ctx_by_device:
+        _ctx_by_device[idx] = _lib.Context(idx)
+    return _ctx_by_device[idx]
+
+
+def _h(t: torch.Tensor) -> _lib.Context:
+    return context(t.device)
+
+
+def _p(t: Optional[torch.Tensor]) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _rowmajor(t: torch.Tensor, what: str) -> int:
+    """Leading dimension (elements) of a 2-D bf16 view whose last dim is contiguous."""
+    if t.dtype != BF16 or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{what}: expected a 2-D bf16 tensor with contiguous last dim, got {t.dtype} {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _vec(t: Optional[torch.Tensor], n: int, what: str) -> None:
+    if t is not None and (t.dtype != BF16 or t.numel() != n or not t.is_contiguous()):
+        raise ValueError(f"{what}: expected a contiguous bf16 vector of {n} elements")
+
+
+def gemm(a, w, bias, out, epilogue=EPI_BIAS, gate0=None, gate1=None, rows_gate0=0):
+    """out[m,n] = epilogue(a[m,k] @ w[n,k].T + bias); see fgb_gemm_bf16."""
+    lda, ldw, ldc = _rowmajor(a, "a"), _rowmajor(w, "w"), _rowmajor(out, "out")
+    m, k = a.shape
+    n = w.shape[0]
+    if w.shape[1] != k or tuple(out.shape) != (m, n):
+        raise ValueError(f"gemm shape mismatch: a {tuple(a.shape)} w {tuple(w.shape)} out {tuple(out.shape)}")
+    _vec(bias, n, "bias"), _vec(gate0, n, "gate0"), _vec(gate1, n, "gate1")
+    c = _h(a)
+    _lib.check(_lib.lib().fgb_gemm_bf16(c.handle, _p(a), lda, _p(w), ldw, _p(bias), _p(out), ldc, m, n, k, epilogue,
+                                        _p(gate0), _p(gate1), rows_gate0, _stream()), "fgb_gemm_bf16")
+    return out
+
+
+def attention(q, k, v, out, heads: int, scale: Optional[float] = None):
+    """out = softmax(q k^T scale) v per 128-wide head; q/out [s_q, heads*128], k/v [s_kv, heads*128]."""
+    ldq, ldk, ldv, ldo = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v"), _rowmajor(out, "out")
+    s_q, s_kv = q.shape[0], k.shape[0]
+    width = heads * 128
+    if q.shape[1] != width or k.shape[1] != width or v.shape != k.shape or out.shape != q.shape:
+        raise ValueError(f"attention shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} heads {heads}")
+    scale = 1.0 / math.sqrt(128.0) if scale is None else scale
+    c = _h(q)
+    _lib.check(_lib.lib().fgb_attn_fwd(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), ldo, s_q, s_kv, heads,
+                                       scale, _stream()), "fgb_attn_fwd")
+    return out
+
+
+def ln_modulate(x, out, eps, shift0, scale0, shift1, scale1, rows_mod0):
+    ldx, ldy = _rowmajor(x, "x"), _rowmajor(out, "out")
+    rows, dim = x.shape
+    for t in (shift0, scale0, shift1, scale1):
+        _vec(t, dim, "modulation row")
+    c = _h(x)
+    _lib.check(_lib.lib().fgb_ln_modulate(c.handle, _p(x), ldx, _p(out), ldy, rows, dim, eps, _p(shift0), _p(scale0),
+                                          _p(shift1), _p(scale1), rows_mod0, _stream()), "fgb_ln_modulate")
+    return out
+
+
+def ln_affine(x, out, eps, weight, bias):
+    ldx, ldy = _rowmajor(x, "x"), _rowmajor(out, "out")
+    rows, dim = x.shape
+    _vec(weight, dim, "weight"), _vec(bias, dim, "bias")
+    c = _h(x)
+    _lib.check(_lib.lib().fgb_ln_affine(c.handle, _p(x), ldx, _p(out), ldy, rows, dim, eps, _p(weight), _p(bias),
+                                        _stream()), "fgb_ln_affine")
+    return out
+
+
+def rmsnorm_rope(x, eps, weight, rope_tab=None, grid=(1, 1, 1), token_offset=0):
+    """In place on x [rows, dim] (may be a strided column slice of a wider buffer)."""
+    ldx = _rowmajor(x, "x")
+    rows, dim = x.shape
+    _vec(weight, dim, "weight")
+    if rope_tab is not None and (rope_tab.dtype != torch.float32 or tuple(rope_tab.shape) != (1024, 64, 2) or not rope_tab.is_contiguous()):
+        raise ValueError("rope_tab must be a contiguous float32 [1024, 64, 2] table")
+    c = _h(x)
+    _lib.check(_lib.lib().fgb_rmsnorm_rope(c.handle, _p(x), ldx, rows, dim, eps, _p(weight), _p(rope_tab), grid[0], grid[1],
+                                           grid[2], token_offset, _stream()), "fgb_rmsnorm_rope")
+    return x
+
+
+def patchify_rows(latents, rows_out, grid, token_offset=0):
+    """latents [C, f, 2h, 2w] bf16 contiguous -> rows_out [rows, >= 4C] (tokens token_offset..)."""
+    if latents.dtype != BF16 or not latents.is_contiguous() or latents.dim() != 4:
+        raise ValueError("latents must be a contiguous bf16 [C, F, H, W] tensor")
+    ch = latents.shape[0]
+    f, h, w = grid
+    if tuple(latents.shape[1:]) != (f, 2 * h, 2 * w):
+        raise ValueError(f"latents {tuple(latents.shape)} do not match grid {grid}")
+    ld = _rowmajor(rows_out, "rows_out")
+    c = _h(latents)
+    _lib.check(_lib.lib().fgb_patchify_rows(c.handle, _p(latents), _p(rows_out), ld, ch, f, h, w, token_offset,
+                                            rows_out.shape[0], _stream()), "fgb_patchify_rows")
+    return rows_out
+
+
+def unpatchify(head_rows, out, grid):
+    """head_rows [f*h*w, 4C] -> out [C, f, 2h, 2w]."""
+    ld = _rowmajor(head_rows, "head_rows")
+    f, h, w = grid
+    ch = out.shape[0]
+    if out.dtype != BF16 or not out.is_contiguous() or tuple(out.shape) != (ch, f, 2 * h, 2 * w) or head_rows.shape[0] < f * h * w:
+        raise ValueError("unpatchify shape mismatch")
+    c = _h(out)
+    _lib.check(_lib.lib().fgb_unpatchify(c.handle, _p(head_rows), ld, _p(out), ch, f, h, w, _stream()), "fgb_unpatchify")
+    return out
+
+
+def cfg_fm_step(latents, noise_pos, noise_neg, first_frame, cfg_scale: float, sigma_delta: float):
+    """In place on latents [..., C, F, H, W] (batch 1): CFG + Euler step + first-frame restore."""
+    lat = latents
+    if lat.dtype != BF16 or not lat.is_contiguous():
+        raise ValueError("latents must be contiguous bf16")
+    ch, fr, hh, ww = lat.shape[-4:]
+    for t in (noise_pos, noise_neg):
+        if t is not None and (t.dtype != BF16 or not t.is_contiguous() or t.numel() != lat.numel()):
+            raise ValueError("noise predictions must be contiguous bf16 tensors shaped like latents")
+    if first_frame is not None and (first_frame.dtype != BF16 or not first_frame.is_contiguous() or first_frame.numel() != ch * hh * ww):
+        raise ValueError("first_frame must be contiguous bf16 [C,1,H,W]")
+    c = _h(lat)
+    _lib.check(_lib.lib().fgb_cfg_fm_step(c.handle, _p(lat), _p(noise_pos), _p(noise_neg), _p(first_frame), cfg_scale,
+                                          sigma_delta, ch, fr, hh * ww, _stream()), "fgb_cfg_fm_step")
+    return latents
+
+
+def sinusoidal_embedding(timesteps_f32, out):
+    rows, dim = out.shape
+    if timesteps_f32.dtype != torch.float32 or timesteps_f32.numel() != rows or out.dtype != BF16 or not out.is_contiguous():
+        raise ValueError("sinusoidal_embedding: timesteps fp32 [rows], out bf16 [rows, dim]")
+    c = _h(out)
+    _lib.check(_lib.lib().fgb_sinusoidal_embedding(c.handle, _p(timesteps_f32), _p(out), rows, dim, _stream()),
+               "fgb_sinusoidal_embedding")
+    return out
+
+
+def silu(x, out):
+    if x.dtype != BF16 or out.dtype != BF16 or not x.is_contiguous() or not out.is_contiguous() or x.numel() != out.numel():
+        raise ValueError("silu: contiguous bf16 tensors of equal size")
+    c = _h(x)
+    _lib.check(_lib.lib().fgb_silu(c.handle, _p(x), _p(out), x.numel(), _stream()), "fgb_silu")
+    return out
+
+
+def add_bcast(a, b, out, period: Optional[int] = None):
+    """out[r, j] = a[r, j] + b[j % period]; a/out [rows, cols] contiguous bf16."""
+    rows, cols = a.shape
+    period = cols if period is None else period
+    if a.dtype != BF16 or not a.is_contiguous() or out.shape != a.shape or not out.is_contiguous() or b.numel() < period or b.dtype != BF16:
+        raise ValueError("add_bcast shape mismatch")
+    c = _h(a)
+    _lib.check(_lib.lib().fgb_add_bcast(c.handle, _p(a), _p(b), _p(out), rows, cols, period, _stream()), "fgb_add_bcast")
+    return out
+
+
+def sp_pack_heads(x, send, heads: int, groups: int, world: int):
+    ldx = _rowmajor(x, "x")
+    c = _h(x)
+    _lib.check(_lib.lib().fgb_sp_pack_heads(c.handle, _p(x), ldx, _p(send), x.shape[0], heads, groups, world, _stream()),
+               "fgb_sp_pack_heads")
+    return send
+
+
+def sp_unpack_heads(recv, x, heads: int, groups: int, world: int):
+    ldx = _rowmajor(x, "x")
+    c = _h(x)
+    _lib.check(_lib.lib().fgb_sp_unpack_heads(c.handle, _p(recv), _p(x), ldx, x.shape[0], heads, groups, world, _stream()),
+               "fgb_sp_unpack_heads")
+    return x
+
+
+def rope_table(head_dim: int = 128, positions: int = 1024, theta: float = 10000.0) -> np.ndarray:
+    """Host-side float32 [positions, head_dim/2, 2] (cos, sin) table for fgb_rmsnorm_rope.
+
+    Same construction as the reference's precompute_freqs_cis_3d (DIT:74-88): the head's complex
+    lanes are split frame/row/column = dim-2*(dim//3), dim//3, dim//3 real dims, each axis with its
+    own theta^(-2i/axis_dim) ladder, evaluated in float64 and rounded once to float32.
+    """
+    axis_dims = (head_dim - 2 * (head_dim // 3), head_dim // 3, head_dim // 3)
+    cols = []
+    pos = np.arange(positions, dtype=np.float64)[:, None]
+    for ad in axis_dims:
+        inv = 1.0 / (theta ** (np.arange(0, ad, 2, dtype=np.float64)[: ad // 2] / ad))
+        cols.append(pos * inv[None, :])
+    ang = np.concatenate(cols, axis=1)  # [positions, head_dim/2]
+    return np.stack([np.cos(ang), np.sin(ang)], axis=-1).astype(np.float32)
+
+
+def sync_check(device=None):
+    c = context(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    _lib.check(_lib.lib().fgb_sync_check(c.handle, _stream()), "fgb_sync_check")

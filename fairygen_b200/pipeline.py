@@ -1,0 +1,59 @@
+"""The denoising hot loop of ``WanVideoPipeline.__call__`` (reference animation/diffsynth/pipelines/
+wan_video.py:282-309) as a standalone object: 2 DiT forwards per step (classifier-free guidance),
+CFG combine, flow-match Euler update and first-frame restore — the last three in one fused kernel.
+
+This is the public entry point ``bench.py`` times end to end; a reference pipeline object gets the
+same behaviour through ``fairygen_b200.install(pipe)``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .engine import WanDiTEngine
+from .scheduler import FlowMatchScheduler
+
+
+class WanDenoiser:
+    def __init__(self, engine: WanDiTEngine, num_inference_steps: int = 50, cfg_scale: float = 5.0,
+                 sigma_shift: float = 5.0, denoising_strength: float = 1.0, cfg_group=None):
+        self.engine = engine
+        self.cfg_scale = float(cfg_scale)
+        self.scheduler = FlowMatchScheduler("Wan")
+        self.scheduler.set_timesteps(num_inference_steps, denoising_strength=denoising_strength, shift=sigma_shift)
+        self.cfg_group = cfg_group  # fairygen_b200.cfg_parallel.CfgParallel or None
+        # timesteps as the model sees them: rounded to the pipeline dtype (bf16) at PIPE:293
+        self.model_timesteps = self.scheduler.timesteps.to(torch.bfloat16).to(torch.float32)
+
+    @property
+    def num_steps(self) -> int:
+        return len(self.scheduler.timesteps)
+
+    @torch.no_grad()
+    def step(self, index: int, latents: torch.Tensor, context_pos: torch.Tensor, context_neg: Optional[torch.Tensor],
+             first_frame_latents: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One denoising step, in place on ``latents`` (1,C,F,H,W) bf16 on the engine's device."""
+        ts = self.model_timesteps[index:index + 1]
+        fuse = first_frame_latents is not None
+        if self.cfg_group is not None and self.cfg_scale != 1.0:
+            npos, nneg = self.cfg_group.forward_pair(self.engine, latents, ts, context_pos, context_neg, fuse)
+        else:
+            npos = self.engine.forward(latents, ts, context_pos, fuse)
+            nneg = self.engine.forward(latents, ts, context_neg, fuse) if self.cfg_scale != 1.0 else None
+        self.scheduler.step_fused(latents, npos, nneg, self.cfg_scale, index, first_frame_latents)
+        return latents
+
+    @torch.no_grad()
+    def __call__(self, latents: torch.Tensor, context_pos: torch.Tensor, context_neg: Optional[torch.Tensor],
+                 first_frame_latents: Optional[torch.Tensor] = None, steps: Optional[range] = None) -> torch.Tensor:
+        dev = self.engine.device
+        lat = latents.to(device=dev, dtype=torch.bfloat16, non_blocking=True).contiguous().clone()
+        cp = context_pos.to(device=dev, dtype=torch.bfloat16, non_blocking=True)
+        cn = None if context_neg is None else context_neg.to(device=dev, dtype=torch.bfloat16, non_blocking=True)
+        z0 = None if first_frame_latents is None else first_frame_latents.to(device=dev, dtype=torch.bfloat16, non_blocking=True).contiguous()
+        if z0 is not None:
+            lat[:, :, 0:1] = z0  # ImageEmbedderFused plants the clean first frame (PIPE:496)
+        for i in (steps if steps is not None else range(self.num_steps)):
+            self.step(i, lat, cp, cn, z0)
+        return lat

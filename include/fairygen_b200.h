@@ -132,12 +132,15 @@ int fgb_add_bcast(fgb_ctx* ctx, const void* a, const void* b, void* out, int64_t
                   int64_t period, void* stream);
 
 /* ---- Ulysses sequence-parallel re-partition (xdit_context_parallel.py:125-146) --------------
- * Pack/unpack between token-sharded [s_local, heads*128] and the peer-major exchange buffer
- * [world][s_local][heads/world * 128] that an all-to-all (NCCL or peer stores) moves. */
+ * Pack/unpack between the token-sharded layout x[s_local][groups][heads][128] (groups = 3 for a fused
+ * q|k|v row, 1 for the attention output) and the peer-major exchange buffer
+ * [world][s_local][groups][heads/world][128] that an all-to-all (NCCL or NVLink peer stores) moves.
+ * After the exchange the receive buffer reads as [world*s_local tokens][groups][heads/world][128]:
+ * the full (padded) sequence for this rank's heads, directly consumable by fgb_attn_fwd. */
 int fgb_sp_pack_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* send, int32_t s_local, int32_t heads,
-                      int32_t world, void* stream);
+                      int32_t groups, int32_t world, void* stream);
 int fgb_sp_unpack_heads(fgb_ctx* ctx, const void* recv, void* x, int64_t ldx, int32_t s_local, int32_t heads,
-                        int32_t world, void* stream);
+                        int32_t groups, int32_t world, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,288 @@
+"""Per-kernel parity on the B200: every C-ABI entry point against the oracle's torch restatement of the
+same reference op (fp32 math on the same bf16 inputs), plus bit-exact checks where the op is pure
+rounding arithmetic (scheduler step, layout kernels) against the golden vectors from the real reference."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def env():
+    from fairygen_b200 import ops
+    from oracle import wan_dit_oracle as o
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    ops.context(torch.device("cuda", 0))  # raises if the CUDA extension is missing / not sm_100
+    return ops, o
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(BF)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (2, 768, 256), (200, 192, 192), (1000, 3072, 3072), (513, 1536, 256),
+                                   (300, 512, 4096), (2049, 14336, 3072)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_epilogues(env, m, n, k, epi):
+    ops, o = env
+    if epi != 0 and m * n * k > 3e10:
+        pytest.skip("large shape checked with the plain epilogue only")
+    a, w, bias = rnd(m, k, seed=1), rnd(n, k, seed=2, scale=1 / math.sqrt(k)), rnd(n, seed=3, scale=0.5)
+    g0, g1, c0 = rnd(n, seed=4), rnd(n, seed=5), rnd(m, n, seed=6)
+    rows0 = m // 3
+    out = c0.clone()
+    ops.gemm(a, w, bias, out, epi, g0, g1, rows0)
+    ops.sync_check()
+    y = (a.float() @ w.float().T + bias.float()).to(BF).float()     # nn.Linear output in bf16
+    if epi == 0:
+        ref = y
+    elif epi == 1:
+        ref = F.gelu(y, approximate="tanh")
+    elif epi == 2:
+        gate = torch.where((torch.arange(m, device="cuda") < rows0)[:, None], g0.float()[None], g1.float()[None])
+        ref = c0.float() + (gate * y).to(BF).float()
+    else:
+        ref = c0.float() + y
+    assert rel_l2(out, ref.to(BF)) < 2e-3
+
+
+def test_gemm_no_bias_and_strided_views(env):
+    ops, o = env
+    a_wide = rnd(300, 1024, seed=1)
+    a = a_wide[:, 256:768]                       # lda = 1024
+    w = rnd(384, 512, seed=2, scale=0.05)
+    out_wide = torch.zeros(300, 1024, dtype=BF, device="cuda")
+    out = out_wide[:, 128:512]                   # ldc = 1024
+    ops.gemm(a, w, None, out)
+    ops.sync_check()
+    assert rel_l2(out, (a.float() @ w.float().T).to(BF)) < 2e-3
+    assert out_wide[:, :128].abs().max() == 0 and out_wide[:, 512:].abs().max() == 0   # nothing written outside
+
+
+def test_gemm_rejects_bad_arguments(env):
+    ops, o = env
+    with pytest.raises(ValueError):
+        ops.gemm(rnd(8, 64), rnd(16, 32), None, torch.empty(8, 16, dtype=BF, device="cuda"))
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        ops.gemm(rnd(8, 64), rnd(12, 64), None, torch.empty(8, 12, dtype=BF, device="cuda"))
+
+
+@pytest.mark.parametrize("s_q,s_kv,heads", [(256, 128, 1), (128, 512, 2), (300, 200, 2), (48, 32, 2), (1000, 1000, 3),
+                                            (30, 24, 2), (1025, 77, 4), (2304, 2304, 3)])
+def test_attention_matches_sdpa(env, s_q, s_kv, heads):
+    ops, o = env
+    q, k, v = rnd(s_q, heads * 128, seed=1), rnd(s_kv, heads * 128, seed=2), rnd(s_kv, heads * 128, seed=3)
+    out = torch.full((s_q, heads * 128), float("nan"), dtype=BF, device="cuda")
+    ops.attention(q, k, v, out, heads)
+    ops.sync_check()
+    ref = o.attention(q[None].float(), k[None].float(), v[None].float(), heads)[0]
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 6e-3
+
+
+def test_attention_strided_qkv_and_large_scores(env):
+    """q|k|v as column slices of one fused buffer (the engine's layout); large-magnitude scores exercise the
+    lazy running-max rescale of the accumulator."""
+    ops, o = env
+    heads, s = 2, 700
+    qkv = rnd(s, 3 * heads * 128, seed=9)
+    d = heads * 128
+    qkv[:, :d] *= 6.0
+    # make late keys dominate so the running max keeps growing
+    qkv[:, d:2 * d] *= torch.linspace(0.2, 4.0, s, device="cuda")[:, None].to(BF)
+    out = torch.empty(s, d, dtype=BF, device="cuda")
+    ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, heads)
+    ops.sync_check()
+    ref = o.attention(qkv[None, :, :d].float(), qkv[None, :, d:2 * d].float(), qkv[None, :, 2 * d:].float(), heads)[0]
+    assert rel_l2(out, ref) < 8e-3
+
+
+def test_attention_properties_at_headline_size(env):
+    """S = 27 280, 24 heads (BASELINE config 2): size-independent properties instead of an O(S^2) oracle.
+    (1) rows of softmax sum to one: with V == 1 the output is exactly 1; (2) linearity in V;
+    (3) a sample of query rows against the exact fp32 formula."""
+    ops, o = env
+    s, heads = 27280, 24
+    d = heads * 128
+    q, k = rnd(s, d, seed=1), rnd(s, d, seed=2)
+    ones = torch.ones(s, d, dtype=BF, device="cuda")
+    out = torch.empty(s, d, dtype=BF, device="cuda")
+    ops.attention(q, k, ones, out, heads)
+    ops.sync_check()
+    assert (out.float() - 1).abs().max() < 1e-2
+    v1, v2 = rnd(s, d, seed=3), rnd(s, d, seed=4)
+    o1, o2, o12 = torch.empty_like(out), torch.empty_like(out), torch.empty_like(out)
+    ops.attention(q, k, v1, o1, heads)
+    ops.attention(q, k, v2, o2, heads)
+    ops.attention(q, k, (v1.float() + v2.float()).to(BF), o12, heads)
+    ops.sync_check()
+    assert rel_l2(o12, o1.float() + o2.float()) < 2e-2
+    rows = torch.tensor([0, 1, 127, 128, 255, 256, 13640, 27151, 27152, 27279], device="cuda")
+    for h in (0, 11, 23):
+        sl = slice(h * 128, (h + 1) * 128)
+        sc = (q[rows, sl].float() @ k[:, sl].float().T) / math.sqrt(128)
+        ref = torch.softmax(sc, dim=-1) @ v1[:, sl].float()
+        assert rel_l2(o1[rows, sl], ref) < 1e-2
+
+
+@pytest.mark.parametrize("rows,dim", [(30, 256), (1000, 3072), (129, 1024)])
+def test_ln_modulate_and_affine(env, rows, dim):
+    ops, o = env
+    x = rnd(rows, dim, seed=1, scale=2.0) + 0.5
+    sh0, sc0, sh1, sc1 = (rnd(dim, seed=s, scale=0.3) for s in (2, 3, 4, 5))
+    n0 = rows // 4
+    out = torch.empty_like(x)
+    ops.ln_modulate(x, out, 1e-6, sh0, sc0, sh1, sc1, n0)
+    ops.sync_check()
+    first = (torch.arange(rows, device="cuda") < n0)[:, None]
+    shift, scale = torch.where(first, sh0[None], sh1[None]), torch.where(first, sc0[None], sc1[None])
+    ref_bf16 = o.modulate(o.layer_norm(x, 1e-6), shift, scale)                       # the reference's bf16 op chain
+    ref_f32 = o.modulate(o.layer_norm(x.float(), 1e-6), shift.float(), scale.float())
+    assert rel_l2(out, ref_f32) < 6e-3
+    assert (out.float() - ref_bf16.float()).abs().max() <= 2 * ref_bf16.float().abs().max() * 2 ** -8
+    assert (out == ref_bf16).float().mean() > 0.98   # same rounding points -> almost always bit-identical
+    w, b = rnd(dim, seed=6, scale=0.2) + 1, rnd(dim, seed=7, scale=0.2)
+    ops.ln_affine(x, out, 1e-6, w, b)
+    ops.sync_check()
+    assert rel_l2(out, o.layer_norm(x.float(), 1e-6, w.float(), b.float())) < 4e-3
+
+
+def test_rmsnorm_rope_matches_reference_math(env, golden):
+    ops, o = env
+    cfg = o.TINY
+    f, h, w = 2, 3, 5
+    s = f * h * w
+    tab = torch.from_numpy(ops.rope_table(128)).cuda()
+    x = rnd(s, cfg.dim, seed=1, scale=1.5)
+    wt = rnd(cfg.dim, seed=2, scale=0.1) + 1
+    freqs = o.rope_freqs(o.rope_tables_3d(128), f, h, w)
+    ref = o.rope_apply(o.rms_norm(x[None].cpu(), wt.cpu(), 1e-6), freqs, cfg.num_heads)[0]   # bf16 chain, fp64 rope
+    got = x.clone()
+    ops.rmsnorm_rope(got, 1e-6, wt, tab, (f, h, w), 0)
+    ops.sync_check()
+    assert rel_l2(got, ref.float()) < 3e-3
+    assert (got.cpu() == ref).float().mean() > 0.97
+    # no rope (cross-attention q/k) and a strided column slice of a wider buffer
+    wide = rnd(s, 3 * cfg.dim, seed=3)
+    ref2 = o.rms_norm(wide[:, cfg.dim:2 * cfg.dim].float(), wt.float(), 1e-6)
+    keep = wide.clone()
+    ops.rmsnorm_rope(wide[:, cfg.dim:2 * cfg.dim], 1e-6, wt)
+    ops.sync_check()
+    assert rel_l2(wide[:, cfg.dim:2 * cfg.dim], ref2) < 6e-3
+    assert torch.equal(wide[:, :cfg.dim], keep[:, :cfg.dim]) and torch.equal(wide[:, 2 * cfg.dim:], keep[:, 2 * cfg.dim:])
+    # sequence-parallel offsets: rank slices with ones-padding beyond the last token (USP:30-55)
+    g = golden("usp")
+    xs = torch.from_numpy(g["x"]).cuda().to(BF)
+    ones = torch.ones(cfg.dim, dtype=BF, device="cuda")
+    for rank in range(4):
+        chunk = torch.from_numpy(g[f"chunk_rank{rank}"])[0].cuda().to(BF).contiguous()
+        refr = o.sp_rope_apply(chunk[None].cpu(), freqs, cfg.num_heads, rank, 4)[0]
+        # isolate the rotation: weight 1 and undo the RMS scale afterwards is awkward -> compare full op instead
+        want = o.rope_apply(o.rms_norm(chunk[None].cpu(), ones.cpu(), 1e-6),
+                            torch.cat([freqs, torch.ones(2, 1, 64, dtype=freqs.dtype)])[rank * 8:(rank + 1) * 8], cfg.num_heads)[0]
+        ops.rmsnorm_rope(chunk, 1e-6, ones, tab, (f, h, w), rank * 8)
+        ops.sync_check()
+        assert rel_l2(chunk, want.float()) < 3e-3
+        assert refr.shape == want.shape
+
+
+def test_patchify_unpatchify_exact(env, golden):
+    ops, o = env
+    g = golden("ops")
+    cfg = o.TINY
+    lat = torch.from_numpy(g["lat"]).cuda().to(BF)[0].contiguous()          # [48, 2, 6, 10]
+    grid = (2, 3, 5)
+    rows = torch.full((30, 192), float("nan"), dtype=BF, device="cuda")
+    ops.patchify_rows(lat, rows, grid, 0)
+    ops.sync_check()
+    ref = lat.view(48, 2, 3, 2, 5, 2).permute(1, 2, 4, 0, 3, 5).reshape(30, 192)   # (f h w) (c y z)
+    assert torch.equal(rows, ref)
+    # with a rank offset and zero padding past the last token
+    part = torch.full((16, 192), float("nan"), dtype=BF, device="cuda")
+    ops.patchify_rows(lat, part, grid, 16)
+    ops.sync_check()
+    assert torch.equal(part[:14], ref[16:]) and part[14:].abs().max() == 0
+    # as a GEMM it equals the reference Conv3d patch embedding (golden from the real reference)
+    w = o.make_weights(cfg, seed=0)
+    out = torch.empty(30, cfg.dim, dtype=BF, device="cuda")
+    ops.gemm(rows, w["patch_embedding.weight"].reshape(cfg.dim, -1).cuda().to(BF).contiguous(),
+             w["patch_embedding.bias"].cuda().to(BF), out)
+    ops.sync_check()
+    want = torch.from_numpy(g["patchify"]).flatten(2).transpose(1, 2)[0]
+    assert rel_l2(out, want) < 6e-3
+    head_rows = rnd(30, 192, seed=5)
+    got = torch.empty(48, 2, 6, 10, dtype=BF, device="cuda")
+    ops.unpatchify(head_rows, got, grid)
+    ops.sync_check()
+    assert torch.equal(got, o.unpatchify(head_rows[None], grid, cfg)[0])
+
+
+def test_cfg_fm_step_bit_exact_vs_reference(env, golden):
+    ops, o = env
+    from fairygen_b200.scheduler import FlowMatchScheduler
+    g = golden("scheduler")
+    s = FlowMatchScheduler("Wan")
+    s.set_timesteps(50, shift=5.0)
+    sample, npos, nneg, z0 = (torch.from_numpy(g[k]).cuda().to(BF) for k in ("sample", "npos", "nneg", "z0"))
+    for i in (0, 17, 49):
+        lat = sample.clone()
+        s.step_fused(lat, npos, nneg, 5.0, i, z0)
+        ops.sync_check()
+        assert torch.equal(lat.float().cpu(), torch.from_numpy(g[f"step_{i}"])), f"step {i} differs from the reference"
+    # reference-style API: step() returns a new tensor and leaves its inputs alone (FM:144-154)
+    npred = (nneg + 5.0 * (npos - nneg))
+    nxt = s.step(npred, s.timesteps[17], sample)
+    nxt[:, :, 0:1] = z0
+    assert torch.equal(nxt.float().cpu(), torch.from_numpy(g["step_17"]))
+    assert torch.equal(sample.float().cpu(), torch.from_numpy(g["sample"]))
+    # odd innermost size takes the scalar path
+    lat = rnd(1, 3, 2, 5, 7, seed=1)
+    a, b = rnd(1, 3, 2, 5, 7, seed=2), rnd(1, 3, 2, 5, 7, seed=3)
+    want = lat + (b + 2.0 * (a - b)) * torch.tensor(s.sigma_delta(3))
+    s.step_fused(lat, a, b, 2.0, 3, None)
+    ops.sync_check()
+    assert torch.equal(lat, want.to(BF))
+
+
+def test_small_embedding_kernels(env, golden):
+    ops, o = env
+    g = golden("ops")
+    t = torch.tensor([0.0, 996.0, 1000.0], device="cuda")
+    out = torch.empty(3, 256, dtype=BF, device="cuda")
+    ops.sinusoidal_embedding(t, out)
+    ops.sync_check()
+    assert (out.float().cpu() - torch.from_numpy(g["sinusoid_bf16"])).abs().max() <= 2 ** -8
+    assert (out.float().cpu() == torch.from_numpy(g["sinusoid_bf16"])).float().mean() > 0.99
+    x = rnd(7, 300, seed=1, scale=3)
+    y = torch.empty_like(x)
+    ops.silu(x, y)
+    ops.sync_check()
+    assert (y.float() - F.silu(x).float()).abs().max() <= 2 ** -7 * F.silu(x).float().abs().max()
+    a, b = rnd(5, 600, seed=2), rnd(300, seed=3)
+    outp = torch.empty_like(a)
+    ops.add_bcast(a, b, outp, period=300)
+    ops.sync_check()
+    assert torch.equal(outp, a + torch.cat([b, b])[None])
+
+
+def test_sp_pack_unpack_roundtrip(env):
+    ops, o = env
+    rows, heads, world = 37, 4, 2
+    x = rnd(rows, 3 * heads * 128, seed=1)
+    send = torch.empty(world * rows, 3 * heads * 128 // world, dtype=BF, device="cuda")
+    ops.sp_pack_heads(x, send, heads, 3, world)
+    ops.sync_check()
+    ref = x.view(rows, 3, world, heads // world, 128).permute(2, 0, 1, 3, 4).reshape(world * rows, -1)
+    assert torch.equal(send, ref)
+    back = torch.zeros_like(x)
+    ops.sp_unpack_heads(send, back, heads, 3, world)
+    ops.sync_check()
+    assert torch.equal(back, x)
