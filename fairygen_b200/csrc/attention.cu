@@ -8,14 +8,18 @@
 //
 // Design: one CTA per (256 query rows, head); 320 threads.
 //   warps 0-3 / 4-7  softmax warpgroup for query tile 0 / 1 (one query row per thread): tcgen05.ld
-//                    the 128x128 fp32 score tile S from TMEM, online softmax with exp2 and a LAZY
-//                    running-max (O is only rescaled when the max grows by more than 2^8), write
-//                    P as packed bf16 back into TMEM over S (tcgen05.st), normalise O at the end.
+//                    the 128x128 fp32 score tile S from TMEM 32 columns at a time, online softmax with
+//                    exp2 against a LAZY running max: the exponentials are computed speculatively against
+//                    the stale max while the tile max is found on the side; only if the max grew by more
+//                    than 2^8 is O rescaled and the tile redone. P goes back into TMEM over S as packed
+//                    bf16 (tcgen05.st); O is normalised at the end.
 //   warp 8           MMA issuer (one thread): S_i = Q_i·K_jᵀ (SS, both K-major) and
 //                    O_i += P_i·V_j (A = P from TMEM, B = V from smem, MN-major), the two query
 //                    tiles ping-pong so tensor cores work on one tile while the other is in softmax.
 //   warp 9           TMA producer: Q once, then a 2-stage ring of K and V tiles (128 keys each).
 // TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P_i aliases the first 64 columns of S_i.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -41,6 +45,56 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): halves the issue slots of the softmax ----
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// 2^x for a pair on the FMA/ALU pipes instead of the MUFU (which is as busy as the tensor pipe in this
+// kernel): round-to-nearest split x = n + f via the 1.5*2^23 trick, degree-3 minimax polynomial for 2^f
+// on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), exponent add in integer.
+__device__ __forceinline__ void exp2_emulated(uint64_t x2, float& r0, float& r1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t kMagic = pack2(12582912.0f, 12582912.0f);
+  const uint64_t kNegMagic = pack2(-12582912.0f, -12582912.0f);
+  const uint64_t kMinusOne = pack2(-1.0f, -1.0f);
+  const uint64_t c0 = pack2(0.9999280572f, 0.9999280572f), c1 = pack2(0.6932609677f, 0.6932609677f);
+  const uint64_t c2 = pack2(0.2426111251f, 0.2426111251f), c3 = pack2(0.0551716685f, 0.0551716685f);
+  const uint64_t t = add2(x2, kMagic);            // integer part lands in the low mantissa bits
+  const uint64_t n = add2(t, kNegMagic);          // round(x) as float
+  const uint64_t f = fma2(n, kMinusOne, x2);      // x - round(x)
+  uint64_t p = fma2(f, c3, c2);
+  p = fma2(p, f, c1);
+  p = fma2(p, f, c0);
+  float p0, p1, t0, t1;
+  unpack2(p, p0, p1);
+  unpack2(t, t0, t1);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+struct TagTrue { static constexpr bool value = true; };
+struct TagFalse { static constexpr bool value = false; };
+
+// EMU: of every 8 score pairs, EMU are exponentiated by exp2_emulated, the rest by MUFU.EX2.
+template <int EMU>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -89,7 +143,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 9) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------- TMA producer -------------------------------
       mbar_expect_tx(q_full, 2 * kTileBytes);
       for (int i = 0; i < 2; ++i)
@@ -112,27 +166,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else if (warp == 8) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------- MMA issuer ---------------------------------
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // P (TMEM)   x V (MN-major)
+      // Descriptors are built once; per MMA only a compile-time offset is added to the 14-bit address field.
+      const uint64_t q_desc = make_sdesc_sw128(smem_u32(smem_q), 16, 1024);
+      const uint64_t k_desc = make_sdesc_sw128(smem_u32(smem_k), 16, 1024);
+      const uint64_t v_desc = make_sdesc_sw128(smem_u32(smem_v), kBoxBytes, 1024);
       auto issue_s = [&](int i, int st) {
-        const uint32_t qa = smem_u32(smem_q + i * kTileBytes);
-        const uint32_t ka = smem_u32(smem_k + st * kTileBytes);
+        const uint64_t qd = q_desc + static_cast<uint64_t>((i * kTileBytes) >> 4);
+        const uint64_t kd = k_desc + static_cast<uint64_t>((st * kTileBytes) >> 4);
+        const uint32_t d_tmem = tmem_base + i * 128;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // 16 head-dim elements per MMA
-          const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-          umma_ss(tmem_base + i * 128, make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(ka + off, 16, 1024),
-                  idesc_s, kk != 0);
+          const uint64_t off = static_cast<uint64_t>(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          umma_ss(d_tmem, qd + off, kd + off, idesc_s, kk != 0);
         }
         tc_commit(&s_full[i]);
       };
       auto issue_pv = [&](int i, int st, int j) {
-        const uint32_t va = smem_u32(smem_v + st * kTileBytes);
+        const uint64_t vd = v_desc + static_cast<uint64_t>((st * kTileBytes) >> 4);
+        const uint32_t d_tmem = tmem_base + 256 + i * 128;
+        const uint32_t p_tmem = tmem_base + i * 128;
+        mbar_wait(&p_ready[i], j & 1);
+        tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA: 16 rows of 128 B in each d-half box
-          umma_ts(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8,
-                  make_sdesc_sw128(va + kk * 2048, kBoxBytes, 1024), idesc_pv, (j | kk) != 0);
+          umma_ts(d_tmem, p_tmem + kk * 8, vd + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv, (j | kk) != 0);
         }
         tc_commit(&pv_done[i]);
       };
@@ -147,8 +208,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int st1 = (j + 1) & 1;
         mbar_wait(&v_full[st], (j >> 1) & 1);
         for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_ready[i], j & 1);
-          tc_fence_after();
           issue_pv(i, st, j);
           if (i == 1) tc_commit(&v_empty[st]);
           if (j + 1 < n_kv) {
@@ -171,33 +230,83 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t t_s = tmem_base + lane_bits + i * 128;
     const uint32_t t_o = tmem_base + lane_bits + 256 + i * 128;
     float m = -INFINITY, l = 0.f;
+
+    // One pass over the 128 scores of this row, 32 at a time (the next TMEM load is in flight while a chunk is
+    // processed): tracks the row maximum and, if EXPS, writes P = 2^(s*scale - m_used) as packed bf16 into pk
+    // and returns the row sum.
+    auto sweep = [&](auto exps_tag, float m_used, float& row_max, uint32_t (&pk)[64]) -> float {
+      constexpr bool EXPS = decltype(exps_tag)::value;
+      uint32_t buf[2][32];
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+      const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
+      const uint64_t negm2 = pack2(-m_used, -m_used);
+      tmem_ld32(t_s, buf[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t (&cur)[32] = buf[c & 1];
+        tmem_ld_wait();
+        if (c < 3) tmem_ld32(t_s + (c + 1) * 32, buf[(c + 1) & 1]);
+#pragma unroll
+        for (int e = 0; e < 32; e += 2)
+          mx[(e >> 1) & 3] = fmaxf(mx[(e >> 1) & 3], fmaxf(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])));
+        if (EXPS) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const uint64_t x2 = fma2(pack2(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1])), scale2, negm2);
+            float p0, p1;
+            if ((e & 7) < EMU) {
+              exp2_emulated(x2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack2(x2, x0, x1);
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            acc[e & 3] = add2(acc[e & 3], pack2(p0, p1));
+            pk[c * 16 + e] = pack_bf16(p0, p1);
+          }
+        }
+      }
+      row_max = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      float a0, a1, b0, b1;
+      unpack2(add2(acc[0], acc[1]), a0, a1);
+      unpack2(add2(acc[2], acc[3]), b0, b1);
+      return (a0 + a1) + (b0 + b1);
+    };
+
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
-      uint32_t sr[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, sr[c]);
-      tmem_ld_wait();
       const int valid = p.s_kv - j * kTile;  // keys of this tile that exist
       if (valid < kTile) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
+        // last, partial KV tile (rare path, kept out of line): overwrite the scores of keys that do not exist with -inf
+#pragma unroll 1
+        for (int c = valid >> 5; c < 4; ++c) {
+          uint32_t fix[32];
+          tmem_ld32(t_s + c * 32, fix);
+          tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (c * 32 + e >= valid) sr[c][e] = 0xff800000u;  // -inf
+            if (c * 32 + e >= valid) fix[e] = 0xff800000u;
+          tmem_st32(t_s + c * 32, fix);
+        }
+        tmem_st_wait();
       }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sr[c][e]));
-      const float m_tile = mx * p.scale_log2;
+      uint32_t pk[64];
+      float row_max, sum;
+      bool redo = false;
       if (j == 0) {
-        m = m_tile;
+        sweep(TagFalse{}, 0.f, row_max, pk);  // exact maximum of the first tile
+        m = row_max * p.scale_log2;
+        redo = true;
       } else {
-        const float m_new = fmaxf(m, m_tile);
+        // Speculate that the running maximum has not grown by more than 2^8: exponentiate against the stale
+        // maximum while the true tile maximum is computed on the side (MUFU and ALU pipes in parallel).
+        sum = sweep(TagTrue{}, m, row_max, pk);
+        const float m_new = fmaxf(m, row_max * p.scale_log2);
         if (__any_sync(0xffffffffu, m_new - m > 8.0f)) {
-          // rescale the running sum and the O accumulator of this row by 2^(m - m_new)
+          // rare: rescale the running sum and the O accumulator of this row by 2^(m - m_new), then redo the tile
           const float alpha = fast_exp2(m - m_new);
           l *= alpha;
           m = m_new;
@@ -212,23 +321,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int e = 0; e < 32; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
             tmem_st32(t_o + c * 32, orr);
           }
+          redo = true;
         }
       }
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {  // 64 keys -> 32 packed columns per store
-        uint32_t pk[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int src = c * 64 + 2 * e;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[src >> 5][src & 31]), p.scale_log2, -m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[(src + 1) >> 5][(src + 1) & 31]), p.scale_log2, -m));
-          sum += p0 + p1;
-          pk[e] = pack_bf16(p0, p1);
-        }
-        tmem_st32(t_s + c * 32, pk);
-      }
+      if (redo) sum = sweep(TagTrue{}, m, row_max, pk);  // S is still intact in TMEM: P has not been stored yet
       l += sum;
+      {
+        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
+        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
+        tmem_st32(t_s, lo);
+        tmem_st32(t_s + 32, hi);
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[i]);
@@ -265,6 +368,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
+constexpr int kDefaultEmu = 0;
+
+template <int EMU>
+static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p) {
+  auto kfn = attn_fwd_kernel<EMU>;
+  static bool configured = false;
+  if (!configured) {
+    FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    configured = true;
+  }
+  kfn<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
+  FGB_LAUNCH_CHECK("attn_fwd_kernel");
+  return FGB_OK;
+}
+
 }  // namespace fgb
 
 extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -294,13 +413,22 @@ extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void
   p.s_kv = s_kv;
   p.scale_log2 = scale * 1.4426950408889634f;
 
-  static bool configured = false;
-  if (!configured) {
-    FGB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    configured = true;
+  // fraction of exponentials moved off the MUFU (EMU of every 8 pairs); FGB_ATTN_EMU overrides for tuning
+  static int emu = -1;
+  if (emu < 0) {
+    const char* env = getenv("FGB_ATTN_EMU");
+    emu = env ? atoi(env) : kDefaultEmu;
+    if (emu < 0 || emu > 6) emu = kDefaultEmu;
   }
   dim3 grid((s_q + 2 * kTile - 1) / (2 * kTile), heads);
-  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
-  FGB_LAUNCH_CHECK("attn_fwd_kernel");
-  return FGB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (emu) {
+    case 0: return launch_attn<0>(grid, st, tq, tk, tv, p);
+    case 1: return launch_attn<1>(grid, st, tq, tk, tv, p);
+    case 2: return launch_attn<2>(grid, st, tq, tk, tv, p);
+    case 3: return launch_attn<3>(grid, st, tq, tk, tv, p);
+    case 4: return launch_attn<4>(grid, st, tq, tk, tv, p);
+    case 5: return launch_attn<5>(grid, st, tq, tk, tv, p);
+    default: return launch_attn<6>(grid, st, tq, tk, tv, p);
+  }
 }

@@ -22,6 +22,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// One lane of a converged warp. Guarding a single-thread role with elect.sync (rather than lane == 0) lets
+// the compiler treat everything inside as uniform, so tcgen05/TMA operands go to uniform registers without
+// per-instruction "waterfall" loops.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Global "a wait timed out" flag: kernels trap instead of hanging the GPU box.
 // (A hung kernel on a leased box is a strike; a trap is just an error code.)
 #ifndef FGB_SPIN_LIMIT

@@ -100,7 +100,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------- TMA producer -------------------------------
       int stage = 0;
       uint32_t phase = 0;
@@ -117,9 +117,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------- MMA issuer ---------------------------------
       constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, 0, 0);
+      // descriptors are built once; per MMA only an offset is added to the 14-bit address field
+      const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(smem_a), 16, 1024);
+      const uint64_t b_desc0 = make_sdesc_sw128(smem_u32(smem_b), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -132,14 +135,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+          const uint64_t adesc = a_desc0 + static_cast<uint64_t>((stage * kABytes) >> 4);
+          const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * kBBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t adesc = make_sdesc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = make_sdesc_sw128(b_addr + k * 32, 16, 1024);
-            umma_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_ss(tmem_d, adesc + static_cast<uint64_t>((k * 32) >> 4), bdesc + static_cast<uint64_t>((k * 32) >> 4), idesc,
+                    (kb | k) != 0);
           tc_commit(&empty[stage]);  // ring slot reusable once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }

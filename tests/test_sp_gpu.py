@@ -1,0 +1,57 @@
+"""Ulysses sequence parallelism on real GPUs (NCCL over NVLink): 2 ranks must reproduce the single-GPU
+forward (our SP masks padded keys, so equality holds for ragged S too).  Skipped with fewer than 2 GPUs."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BF = torch.bfloat16
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, shape, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+
+    import fairygen_b200 as fg
+    from fairygen_b200 import synthetic
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", rank))
+    cfg = fg.WanDiTConfig(dim=1024, ffn_dim=2048, text_dim=256, num_heads=8, num_layers=2)
+    sd = synthetic.random_state_dict(cfg, seed=0, device=f"cuda:{rank}", dtype=BF)
+    lat, z0, cp, cn = synthetic.synthetic_inputs(cfg, shape, text_len=64, live_text=16, pin=False)
+    ts = torch.tensor([996.0])
+    single = fg.WanDiTEngine(cfg, f"cuda:{rank}")
+    single.load_state_dict(sd)
+    ref = single.forward(lat.cuda(), ts, cp.cuda(), True)
+    par = fg.WanDiTEngine(cfg, f"cuda:{rank}", sp=fg.SequenceParallel())
+    par.load_state_dict(sd)
+    out = par.forward(lat.cuda(), ts, cp.cuda(), True)
+    fg.ops.sync_check()
+    err = float((out.float() - ref.float()).norm() / ref.float().norm())
+    torch.save({"err": err, "finite": bool(torch.isfinite(out.float()).all())}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(1, 48, 4, 16, 16), (1, 48, 3, 10, 14)])   # S = 256 (even split) and S = 105 (ragged)
+def test_sp2_equals_single_gpu(tmp_path, shape):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert res["finite"] and res["err"] < 2e-3, res   # same kernels, same rounding; only the attention tiling differs
