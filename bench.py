@@ -110,11 +110,11 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, layout=None):
     return {
         "workload": "Wan2.2-TI2V-5B denoise step, 704x1280x121 (latent 1x48x31x44x80, S=27280 video tokens, 512 text tokens), "
                     "bf16, CFG on (2 DiT forwards/step, cfg_scale 5), merged rank-32 motion LoRA, 50-step flow-match schedule (shift 5)",
-        "tokens": 27280, "text_tokens": TEXT_LEN, "layers": 30, "parallelism": f"ulysses_sp{n_gpus}" if n_gpus > 1 else "single_gpu",
+        "tokens": 27280, "text_tokens": TEXT_LEN, "layers": 30, "parallelism": layout or ("single_gpu" if n_gpus == 1 else f"{n_gpus}_gpus"),
         "l2_policy": "working set per step (10 GB weights + 2 GB activations) >> 126 MB L2; no explicit flush needed",
     }
 
@@ -139,9 +139,20 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     sp = None
+    par = None
+    sp_ways = 1
+    layout_name = "single_gpu"
     if world > 1:
+        from fairygen_b200.cfg_parallel import Layout, ParallelContext
+
         dist.init_process_group("nccl", init_method="env://", device_id=dev)
-        sp = fg.SequenceParallel()
+        # one video: CFG pair (positive / negative prompt on disjoint halves of the box) x Ulysses inside each half,
+        # or pure Ulysses over all ranks with --layout sp
+        layout = Layout(world, 1, 1, world) if args.layout == "sp" else Layout.auto(world, 1, True, fg.TI2V_5B.num_heads)
+        par = ParallelContext(layout)
+        sp = par.sequence_parallel()
+        sp_ways = layout.sp
+        layout_name = f"cfg{layout.cfg}_x_ulysses_sp{layout.sp}"
 
     cfg = fg.TI2V_5B
     shape = synthetic.latent_shape(cfg, HEIGHT, WIDTH, FRAMES)
@@ -151,7 +162,8 @@ def run_ours(args):
     engine.load_state_dict(sd)
     del sd
     lat_h, z0_h, cp_h, cn_h = synthetic.synthetic_inputs(cfg, shape, text_len=TEXT_LEN)
-    den = fg.WanDenoiser(engine, NUM_INFERENCE_STEPS, CFG_SCALE, SIGMA_SHIFT)
+    den = fg.WanDenoiser(engine, NUM_INFERENCE_STEPS, CFG_SCALE, SIGMA_SHIFT,
+                         cfg_group=par if (par is not None and par.layout.cfg > 1) else None)
     lat = lat_h.to(dev).contiguous()
     z0, cp, cn = z0_h.to(dev).contiguous(), cp_h.to(dev), cn_h.to(dev)
     lat[:, :, 0:1] = z0
@@ -220,7 +232,7 @@ def run_ours(args):
     achieved_tflops = 2 * flops_fwd * steps_per_s / 1e12
     # dominant kernel: self-attention (53 % of the counted FLOPs). Algorithmic FLOPs per launch = 4 * S^2 * (heads*128) / world
     attn = kernels.get("attn_self")
-    attn_flops = 4.0 * tokens * tokens * cfg.dim / world
+    attn_flops = 4.0 * tokens * tokens * cfg.dim / sp_ways
     roofline = None
     if attn:
         a = attn_flops / (attn["avg_ms"] * 1e-3) / 1e12
@@ -229,7 +241,8 @@ def run_ours(args):
                     "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "flops_per_launch": attn_flops, "avg_launch_ms": attn["avg_ms"], "launches": attn["launches"]}
     gemm_ms = sum(v["total_ms"] for k, v in kernels.items() if k.startswith("gemm"))
-    gemm_flops = 30 * (12 * tokens * cfg.dim ** 2 + 4 * tokens * cfg.dim * cfg.ffn_dim) / world * 2 * args.steps
+    fwd_per_rank = 2 * sp_ways / world   # DiT forwards each rank takes part in per step (1 under CFG-parallel)
+    gemm_flops = 30 * (12 * tokens * cfg.dim ** 2 + 4 * tokens * cfg.dim * cfg.ffn_dim) / sp_ways * fwd_per_rank * args.steps
     breakdown = {k: round(v["total_ms"] / args.steps, 3) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["total_ms"])}
 
     cpu_base = None
@@ -239,7 +252,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": workload_config(world),
+        "data": "synthetic", "config": workload_config(world, layout_name),
         "video_tokens_per_s": 2 * tokens * steps_per_s, "dit_forwards_per_s": 2 * steps_per_s,
         "achieved_tflops": achieved_tflops, "frac_of_bf16_peak_burst": achieved_tflops / (world * peaks["bf16_burst"]),
         "frac_of_bf16_peak_sustained": achieved_tflops / (world * peaks["bf16_sustained"]),
@@ -263,6 +276,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--layout", choices=["auto", "sp"], default="auto",
+                    help="N>1: auto = CFG pair x Ulysses SP (N/2 ways); sp = pure Ulysses SP over all N ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -37,6 +37,13 @@ struct AttnParams {
   int64_t ldo;
   int32_t s_q, s_kv;
   float scale_log2;
+  // Work list: CTA b < n_full handles unit b over all KV tiles; the remaining CTAs handle the LAST units of
+  // the list, each split `split` ways along the keys (wave-quantisation fix, see fgb_attn_fwd_ex). A unit is
+  // (head, pair of query tiles): unit = head * n_pairs + pair.
+  int32_t n_pairs, n_full, split;
+  float* part_o;    // [split CTA][256 rows][128] un-normalised fp32 partial outputs
+  float2* part_ml;  // [split CTA][256 rows] (running max in log2 units, row sum)
+  float* lse;       // optional [heads][s_q]: log2-domain log-sum-exp of the scaled scores (for the backward pass)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -116,9 +123,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * (2 * kTile);
-  const int n_kv = (p.s_kv + kTile - 1) / kTile;
+  const int n_kv_all = (p.s_kv + kTile - 1) / kTile;
+  int unit = blockIdx.x, kv_lo = 0, kv_hi = n_kv_all, part = -1;
+  if (unit >= p.n_full) {
+    part = unit - p.n_full;
+    const int chunk = part % p.split;
+    unit = p.n_full + part / p.split;
+    kv_lo = static_cast<int>(static_cast<int64_t>(chunk) * n_kv_all / p.split);
+    kv_hi = static_cast<int>(static_cast<int64_t>(chunk + 1) * n_kv_all / p.split);
+  }
+  const int head = unit / p.n_pairs;
+  const int q0 = (unit % p.n_pairs) * (2 * kTile);
+  const int n_kv = kv_hi - kv_lo;   // KV tiles of this CTA; local tile jj is global tile kv_lo + jj
 
   if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -157,12 +173,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_expect_tx(&k_full[st], kTileBytes);
         for (int b = 0; b < 2; ++b)
           tma_load_2d(smem_k + st * kTileBytes + b * kBoxBytes, &tmap_k, &k_full[st], head * 128 + b * 64,
-                      j * kTile, kEvictLast);
+                      (kv_lo + j) * kTile, kEvictLast);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], kTileBytes);
         for (int b = 0; b < 2; ++b)
           tma_load_2d(smem_v + st * kTileBytes + b * kBoxBytes, &tmap_v, &v_full[st], head * 128 + b * 64,
-                      j * kTile, kEvictLast);
+                      (kv_lo + j) * kTile, kEvictLast);
       }
     }
   } else if (warp == 8) {
@@ -278,7 +294,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
-      const int valid = p.s_kv - j * kTile;  // keys of this tile that exist
+      const int valid = p.s_kv - (kv_lo + j) * kTile;  // keys of this tile that exist
       if (valid < kTile) {
         // last, partial KV tile (rare path, kept out of line): overwrite the scores of keys that do not exist with -inf
 #pragma unroll 1
@@ -336,25 +352,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before();
       mbar_arrive(&p_ready[i]);
     }
-    // final normalisation: O / l -> bf16 -> global
     mbar_wait(&pv_done[i], (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * 128;
+    if (part >= 0) {
+      // split-KV CTA: un-normalised O and (m, l) go to the workspace; attn_combine_kernel merges the chunks
+      const int r_local = i * kTile + quarter * 32 + lane;
+      float* prow = p.part_o + (static_cast<int64_t>(part) * (2 * kTile) + r_local) * 128;
+      p.part_ml[static_cast<int64_t>(part) * (2 * kTile) + r_local] = make_float2(m, l);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t orr[32];
-      tmem_ld32(t_o + c * 32, orr);
-      tmem_ld_wait();
-      if (row < p.s_q) {
+      for (int c = 0; c < 4; ++c) {
+        uint32_t orr[32];
+        tmem_ld32(t_o + c * 32, orr);
+        tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(orr[g * 8 + 0]) * inv_l, __uint_as_float(orr[g * 8 + 1]) * inv_l);
-          o.y = pack_bf16(__uint_as_float(orr[g * 8 + 2]) * inv_l, __uint_as_float(orr[g * 8 + 3]) * inv_l);
-          o.z = pack_bf16(__uint_as_float(orr[g * 8 + 4]) * inv_l, __uint_as_float(orr[g * 8 + 5]) * inv_l);
-          o.w = pack_bf16(__uint_as_float(orr[g * 8 + 6]) * inv_l, __uint_as_float(orr[g * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(prow + c * 32 + g * 4) = make_uint4(orr[g * 4], orr[g * 4 + 1], orr[g * 4 + 2], orr[g * 4 + 3]);
+      }
+    } else {
+      // final normalisation: O / l -> bf16 -> global
+      const float inv_l = 1.0f / l;
+      if (p.lse != nullptr && row < p.s_q) p.lse[static_cast<int64_t>(head) * p.s_q + row] = m + __log2f(l);
+      __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t orr[32];
+        tmem_ld32(t_o + c * 32, orr);
+        tmem_ld_wait();
+        if (row < p.s_q) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(orr[g * 8 + 0]) * inv_l, __uint_as_float(orr[g * 8 + 1]) * inv_l);
+            o.y = pack_bf16(__uint_as_float(orr[g * 8 + 2]) * inv_l, __uint_as_float(orr[g * 8 + 3]) * inv_l);
+            o.z = pack_bf16(__uint_as_float(orr[g * 8 + 4]) * inv_l, __uint_as_float(orr[g * 8 + 5]) * inv_l);
+            o.w = pack_bf16(__uint_as_float(orr[g * 8 + 6]) * inv_l, __uint_as_float(orr[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+          }
         }
       }
     }
@@ -370,8 +403,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
 constexpr int kDefaultEmu = 0;
 
+// Merge the `split` key-chunk partials of the split units: one warp per query row.
+//   M = max_c m_c;  w_c = 2^(m_c - M);  o = sum_c w_c O_c / sum_c w_c l_c
+__global__ void __launch_bounds__(256)
+attn_combine_kernel(const AttnParams p, int n_split_units) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int u = gw / (2 * kTile);
+  const int r_local = gw % (2 * kTile);
+  if (u >= n_split_units) return;
+  const int unit = p.n_full + u;
+  const int head = unit / p.n_pairs;
+  const int row = (unit % p.n_pairs) * (2 * kTile) + r_local;
+  if (row >= p.s_q) return;
+  float mmax = -INFINITY;
+  for (int c = 0; c < p.split; ++c)
+    mmax = fmaxf(mmax, p.part_ml[(static_cast<int64_t>(u) * p.split + c) * (2 * kTile) + r_local].x);
+  float lsum = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < p.split; ++c) {
+    const int64_t pr = (static_cast<int64_t>(u) * p.split + c) * (2 * kTile) + r_local;
+    const float2 ml = p.part_ml[pr];
+    const float w = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - mmax);
+    lsum += w * ml.y;
+    const float4 o = *reinterpret_cast<const float4*>(p.part_o + pr * 128 + lane * 4);
+    acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
+  }
+  const float inv = 1.0f / lsum;
+  uint2 out;
+  out.x = pack_bf16(acc.x * inv, acc.y * inv);
+  out.y = pack_bf16(acc.z * inv, acc.w * inv);
+  *reinterpret_cast<uint2*>(p.o + static_cast<int64_t>(row) * p.ldo + head * 128 + lane * 4) = out;
+  if (p.lse != nullptr && lane == 0) p.lse[static_cast<int64_t>(head) * p.s_q + row] = mmax + log2f(lsum);
+}
+
 template <int EMU>
-static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+static int launch_attn(int grid, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p) {
   auto kfn = attn_fwd_kernel<EMU>;
   static bool configured = false;
@@ -384,11 +451,45 @@ static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tq, co
   return FGB_OK;
 }
 
+// How the last, partly filled wave of CTAs is cut along the keys: returns the split factor g (1 = no split) and the
+// number of units that are split. With U units on n_sm SMs (one CTA per SM), the last U mod n_sm units would occupy a
+// whole wave on their own; cutting each into g key chunks makes the tail ceil(rem*g/n_sm)/g of a wave instead.
+static void plan_split(int units, int n_kv, int n_sm, int* split, int* n_split_units) {
+  *split = 1;
+  *n_split_units = 0;
+  const int rem = units % n_sm;
+  if (rem == 0 || n_kv < 16) return;
+  double best = 1.0;   // tail length in waves without a split
+  int best_g = 1;
+  const int g_max = n_kv / 8 < 16 ? n_kv / 8 : 16;
+  for (int g = 2; g <= g_max; ++g) {
+    const int waves = (rem * g + n_sm - 1) / n_sm;
+    const double tail = static_cast<double>(waves) / g + 0.01 * g;   // + prologue/epilogue/combine cost per chunk
+    if (tail < best - 0.05) {
+      best = tail;
+      best_g = g;
+    }
+  }
+  if (best_g > 1) {
+    *split = best_g;
+    *n_split_units = rem;
+  }
+}
+
 }  // namespace fgb
 
-extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                            int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
-                            void* stream) {
+extern "C" int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s_kv, int32_t heads) {
+  using namespace fgb;
+  if (!ctx || s_q <= 0 || s_kv <= 0 || heads <= 0) return 0;
+  const int n_pairs = (s_q + 2 * kTile - 1) / (2 * kTile);
+  int split, n_split;
+  plan_split(n_pairs * heads, (s_kv + kTile - 1) / kTile, ctx->sm_count, &split, &n_split);
+  return static_cast<int64_t>(n_split) * split * (2 * kTile) * (128 * 4 + 8);
+}
+
+extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                               int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
+                               void* lse, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace fgb;
   FGB_CHECK_ARG(ctx, "fgb_attn_fwd: ctx is NULL");
   FGB_CHECK_ARG(q && k && v && o, "fgb_attn_fwd: NULL tensor pointer");
@@ -397,6 +498,7 @@ extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void
   const int64_t width = static_cast<int64_t>(heads) * FGB_HEAD_DIM;
   FGB_CHECK_ARG(ldq >= width && ldk >= width && ldv >= width && ldo >= width, "fgb_attn_fwd: leading dimension < heads*128");
   FGB_CHECK_ARG(aligned16(o) && ldo % 8 == 0, "fgb_attn_fwd: o must be 16-byte aligned with ldo %% 8 == 0");
+  FGB_CHECK_ARG(workspace == nullptr || aligned16(workspace), "fgb_attn_fwd: workspace must be 16-byte aligned");
 
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_bf16_2d(ctx, &tq, q, s_q, width, ldq, kTile);
@@ -412,6 +514,23 @@ extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void
   p.s_q = s_q;
   p.s_kv = s_kv;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = static_cast<float*>(lse);
+  p.n_pairs = (s_q + 2 * kTile - 1) / (2 * kTile);
+  const int64_t units64 = static_cast<int64_t>(p.n_pairs) * heads;
+  FGB_CHECK_ARG(units64 < (1ll << 30), "fgb_attn_fwd: problem too large");
+  const int units = static_cast<int>(units64);
+  int split = 1, n_split = 0;
+  // the key split needs the caller's scratch (the library never allocates); without it every unit runs whole
+  if (workspace != nullptr) plan_split(units, (s_kv + kTile - 1) / kTile, ctx->sm_count, &split, &n_split);
+  const int64_t need = static_cast<int64_t>(n_split) * split * (2 * kTile) * (128 * 4 + 8);
+  if (need > workspace_bytes) {
+    split = 1;
+    n_split = 0;
+  }
+  p.split = split;
+  p.n_full = units - n_split;
+  p.part_o = static_cast<float*>(workspace);
+  p.part_ml = reinterpret_cast<float2*>(static_cast<char*>(workspace) + static_cast<int64_t>(n_split) * split * (2 * kTile) * 128 * 4);
 
   // fraction of exponentials moved off the MUFU (EMU of every 8 pairs); FGB_ATTN_EMU overrides for tuning
   static int emu = -1;
@@ -420,15 +539,28 @@ extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void
     emu = env ? atoi(env) : kDefaultEmu;
     if (emu < 0 || emu > 6) emu = kDefaultEmu;
   }
-  dim3 grid((s_q + 2 * kTile - 1) / (2 * kTile), heads);
+  const int grid = p.n_full + n_split * split;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (emu) {
-    case 0: return launch_attn<0>(grid, st, tq, tk, tv, p);
-    case 1: return launch_attn<1>(grid, st, tq, tk, tv, p);
-    case 2: return launch_attn<2>(grid, st, tq, tk, tv, p);
-    case 3: return launch_attn<3>(grid, st, tq, tk, tv, p);
-    case 4: return launch_attn<4>(grid, st, tq, tk, tv, p);
-    case 5: return launch_attn<5>(grid, st, tq, tk, tv, p);
-    default: return launch_attn<6>(grid, st, tq, tk, tv, p);
+    case 0: rc = launch_attn<0>(grid, st, tq, tk, tv, p); break;
+    case 1: rc = launch_attn<1>(grid, st, tq, tk, tv, p); break;
+    case 2: rc = launch_attn<2>(grid, st, tq, tk, tv, p); break;
+    case 3: rc = launch_attn<3>(grid, st, tq, tk, tv, p); break;
+    case 4: rc = launch_attn<4>(grid, st, tq, tk, tv, p); break;
+    case 5: rc = launch_attn<5>(grid, st, tq, tk, tv, p); break;
+    default: rc = launch_attn<6>(grid, st, tq, tk, tv, p); break;
   }
+  if (rc) return rc;
+  if (n_split > 0) {
+    const int warps = n_split * 2 * kTile;
+    attn_combine_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(p, n_split);
+    FGB_LAUNCH_CHECK("attn_combine_kernel");
+  }
+  return FGB_OK;
+}
+
+extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                            int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
+                            void* stream) {
+  return fgb_attn_fwd_ex(ctx, q, ldq, k, ldk, v, ldv, o, ldo, s_q, s_kv, heads, scale, nullptr, nullptr, 0, stream);
 }

@@ -69,17 +69,38 @@ def gemm(a, w, bias, out, epilogue=EPI_BIAS, gate0=None, gate1=None, rows_gate0=
     return out
 
 
-def attention(q, k, v, out, heads: int, scale: Optional[float] = None):
-    """out = softmax(q k^T scale) v per 128-wide head; q/out [s_q, heads*128], k/v [s_kv, heads*128]."""
+_attn_ws = {}
+
+
+def attention_workspace(q_rows: int, kv_rows: int, heads: int, device) -> Optional[torch.Tensor]:
+    """Caller-owned scratch for the key-split tail of fgb_attn_fwd_ex (None when the grid needs no split)."""
+    c = context(device)
+    need = _lib.lib().fgb_attn_workspace_bytes(c.handle, q_rows, kv_rows, heads)
+    if need <= 0:
+        return None
+    key = (c.device_index, torch.cuda.current_stream().cuda_stream)
+    ws = _attn_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=torch.device("cuda", c.device_index))
+        _attn_ws[key] = ws
+    return ws
+
+
+def attention(q, k, v, out, heads: int, scale: Optional[float] = None, lse: Optional[torch.Tensor] = None):
+    """out = softmax(q k^T scale) v per 128-wide head; q/out [s_q, heads*128], k/v [s_kv, heads*128].
+    lse (optional, fp32 [heads, s_q]) receives the log2-domain log-sum-exp rows for the backward pass."""
     ldq, ldk, ldv, ldo = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v"), _rowmajor(out, "out")
     s_q, s_kv = q.shape[0], k.shape[0]
     width = heads * 128
     if q.shape[1] != width or k.shape[1] != width or v.shape != k.shape or out.shape != q.shape:
         raise ValueError(f"attention shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} heads {heads}")
     scale = 1.0 / math.sqrt(128.0) if scale is None else scale
+    if lse is not None and (lse.dtype != torch.float32 or tuple(lse.shape) != (heads, s_q) or not lse.is_contiguous()):
+        raise ValueError("lse must be a contiguous float32 [heads, s_q] tensor")
     c = _h(q)
-    _lib.check(_lib.lib().fgb_attn_fwd(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), ldo, s_q, s_kv, heads,
-                                       scale, _stream()), "fgb_attn_fwd")
+    ws = attention_workspace(s_q, s_kv, heads, q.device)
+    _lib.check(_lib.lib().fgb_attn_fwd_ex(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), ldo, s_q, s_kv, heads,
+                                          scale, _p(lse), _p(ws), 0 if ws is None else ws.numel(), _stream()), "fgb_attn_fwd_ex")
     return out
 
 

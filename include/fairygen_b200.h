@@ -76,6 +76,17 @@ int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_
                  int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
                  void* stream);
 
+/* Same, with the two extras the multi-GPU and training paths need:
+ *  - workspace (optional, caller-owned, 16-byte aligned, fgb_attn_workspace_bytes() bytes): lets the kernel cut the
+ *    units of the last, partly filled wave of CTAs into key chunks whose partial (max, sum, O) results are merged by a
+ *    small combine kernel. With heads/P heads per rank under Ulysses SP the grid is only 2.2 waves of the 148 SMs at
+ *    P = 8, so without the split a third of the machine idles for a whole wave. NULL = no split.
+ *  - lse (optional): fp32 [heads][s_q], log2-domain log-sum-exp of the scaled scores, saved for fgb_attn_bwd. */
+int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                    int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
+                    void* lse, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s_kv, int32_t heads);
+
 /* ---- fused memory-bound kernels ------------------------------------------------------------ */
 
 /* y = LayerNorm(x; eps, no affine) * (1 + scale[row]) + shift[row]; rows < rows_mod0 use

@@ -65,7 +65,7 @@ __global__ void gemm_ref_kernel(const bf16* A, const bf16* W, const bf16* bias, 
 
 // one warp per (query row, head): exact two-pass softmax in fp32
 __global__ void attn_ref_kernel(const bf16* q, const bf16* k, const bf16* v, float* o, int s_q, int s_kv, int heads,
-                                float scale) {
+                                float scale, float* lse_ref) {
   int row = blockIdx.x, h = blockIdx.y, lane = threadIdx.x;
   int64_t W = (int64_t)heads * 128;
   float qv[4];
@@ -89,6 +89,7 @@ __global__ void attn_ref_kernel(const bf16* q, const bf16* k, const bf16* v, flo
     for (int i = 0; i < 4; ++i) acc[i] += pb * __bfloat162float(v[j * W + h * 128 + lane * 4 + i]);
   }
   for (int i = 0; i < 4; ++i) o[row * W + h * 128 + lane * 4 + i] = acc[i] / l;
+  if (lane == 0) lse_ref[(int64_t)h * s_q + row] = (mx + logf(l)) * 1.4426950408889634f;
 }
 
 static void compare(const std::vector<bf16>& got, const std::vector<float>& ref, const char* what) {
@@ -179,13 +180,33 @@ int main(int argc, char** argv) {
     fill(k, SKV * W, 12, 2.0f);
     fill(v, SKV * W, 13, 1.0f);
     float scale = 1.0f / sqrtf(128.f);
-    FK(fgb_attn_fwd(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, nullptr));
+    // key-split workspace (KCHECK_NOSPLIT=1 runs every unit whole) and the saved log-sum-exp rows
+    int64_t ws_bytes = getenv("KCHECK_NOSPLIT") ? 0 : fgb_attn_workspace_bytes(ctx, SQ, SKV, H);
+    void* ws = nullptr;
+    float* lse = nullptr;
+    if (ws_bytes > 0) CK(cudaMalloc(&ws, ws_bytes));
+    CK(cudaMalloc(&lse, (size_t)SQ * H * 4));
+    printf("attn workspace %lld bytes\n", (long long)ws_bytes);
+    auto run = [&]() { return fgb_attn_fwd_ex(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, lse, ws, ws_bytes, nullptr); };
+    FK(run());
     FK(fgb_sync_check(ctx, nullptr));
     if (check) {
       CK(cudaMalloc(&oref, (size_t)SQ * W * 4));
       dim3 g(SQ, H);
-      attn_ref_kernel<<<g, 32, SKV * 4>>>(q, k, v, oref, SQ, SKV, H, scale);
+      float* lse_ref;
+      CK(cudaMalloc(&lse_ref, (size_t)SQ * H * 4));
+      CK(cudaFuncSetAttribute(attn_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKV * 4));
+      attn_ref_kernel<<<g, 32, SKV * 4>>>(q, k, v, oref, SQ, SKV, H, scale, lse_ref);
+      CK(cudaGetLastError());
       CK(cudaDeviceSynchronize());
+      {
+        std::vector<float> a((size_t)SQ * H), b((size_t)SQ * H);
+        CK(cudaMemcpy(a.data(), lse, a.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b.data(), lse_ref, b.size() * 4, cudaMemcpyDeviceToHost));
+        double mx = 0;
+        for (size_t i = 0; i < a.size(); ++i) mx = fmax(mx, fabs((double)a[i] - b[i]));
+        printf("lse max_abs_err=%.3e %s\n", mx, mx < 2e-3 ? "PASS" : "FAIL");
+      }
       std::vector<bf16> got((size_t)SQ * W);
       std::vector<float> ref((size_t)SQ * W);
       CK(cudaMemcpy(got.data(), o, got.size() * 2, cudaMemcpyDeviceToHost));
@@ -195,9 +216,9 @@ int main(int argc, char** argv) {
       compare(got, ref, name);
     }
     if (iters > 0) {
-      for (int i = 0; i < 2; ++i) FK(fgb_attn_fwd(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, nullptr));
+      for (int i = 0; i < 2; ++i) FK(run());
       CK(cudaEventRecord(e0));
-      for (int i = 0; i < iters; ++i) FK(fgb_attn_fwd(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, nullptr));
+      for (int i = 0; i < iters; ++i) FK(run());
       CK(cudaEventRecord(e1));
       CK(cudaEventSynchronize(e1));
       float ms;
