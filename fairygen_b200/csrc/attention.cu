@@ -43,7 +43,8 @@ struct AttnParams {
   int32_t n_pairs, n_full, split;
   float* part_o;    // [split CTA][256 rows][128] un-normalised fp32 partial outputs
   float2* part_ml;  // [split CTA][256 rows] (running max in log2 units, row sum)
-  float* lse;       // optional [heads][s_q]: log2-domain log-sum-exp of the scaled scores (for the backward pass)
+  float* lse;       // optional [heads][ld_lse]: log2-domain log-sum-exp of the scaled scores (for the backward pass);
+  int64_t ld_lse;   // rows in [s_q, ld_lse) get the value of an all-zero query row, so the backward needs no masks
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -371,7 +372,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     } else {
       // final normalisation: O / l -> bf16 -> global
       const float inv_l = 1.0f / l;
-      if (p.lse != nullptr && row < p.s_q) p.lse[static_cast<int64_t>(head) * p.s_q + row] = m + __log2f(l);
+      if (p.lse != nullptr && row < p.ld_lse) p.lse[static_cast<int64_t>(head) * p.ld_lse + row] = m + __log2f(l);
       __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * 128;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -415,7 +416,7 @@ attn_combine_kernel(const AttnParams p, int n_split_units) {
   const int unit = p.n_full + u;
   const int head = unit / p.n_pairs;
   const int row = (unit % p.n_pairs) * (2 * kTile) + r_local;
-  if (row >= p.s_q) return;
+  if (row >= p.s_q && (p.lse == nullptr || row >= p.ld_lse)) return;
   float mmax = -INFINITY;
   for (int c = 0; c < p.split; ++c)
     mmax = fmaxf(mmax, p.part_ml[(static_cast<int64_t>(u) * p.split + c) * (2 * kTile) + r_local].x);
@@ -433,8 +434,8 @@ attn_combine_kernel(const AttnParams p, int n_split_units) {
   uint2 out;
   out.x = pack_bf16(acc.x * inv, acc.y * inv);
   out.y = pack_bf16(acc.z * inv, acc.w * inv);
-  *reinterpret_cast<uint2*>(p.o + static_cast<int64_t>(row) * p.ldo + head * 128 + lane * 4) = out;
-  if (p.lse != nullptr && lane == 0) p.lse[static_cast<int64_t>(head) * p.s_q + row] = mmax + log2f(lsum);
+  if (row < p.s_q) *reinterpret_cast<uint2*>(p.o + static_cast<int64_t>(row) * p.ldo + head * 128 + lane * 4) = out;
+  if (p.lse != nullptr && lane == 0 && row < p.ld_lse) p.lse[static_cast<int64_t>(head) * p.ld_lse + row] = mmax + log2f(lsum);
 }
 
 template <int EMU>
@@ -489,7 +490,7 @@ extern "C" int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s
 
 extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
-                               void* lse, void* workspace, int64_t workspace_bytes, void* stream) {
+                               void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace fgb;
   FGB_CHECK_ARG(ctx, "fgb_attn_fwd: ctx is NULL");
   FGB_CHECK_ARG(q && k && v && o, "fgb_attn_fwd: NULL tensor pointer");
@@ -515,6 +516,8 @@ extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const v
   p.s_kv = s_kv;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = static_cast<float*>(lse);
+  p.ld_lse = ld_lse;
+  FGB_CHECK_ARG(lse == nullptr || ld_lse >= s_q, "fgb_attn_fwd: ld_lse=%lld < s_q", (long long)ld_lse);
   p.n_pairs = (s_q + 2 * kTile - 1) / (2 * kTile);
   const int64_t units64 = static_cast<int64_t>(p.n_pairs) * heads;
   FGB_CHECK_ARG(units64 < (1ll << 30), "fgb_attn_fwd: problem too large");
@@ -562,5 +565,5 @@ extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const v
 extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
                             void* stream) {
-  return fgb_attn_fwd_ex(ctx, q, ldq, k, ldk, v, ldv, o, ldo, s_q, s_kv, heads, scale, nullptr, nullptr, 0, stream);
+  return fgb_attn_fwd_ex(ctx, q, ldq, k, ldk, v, ldv, o, ldo, s_q, s_kv, heads, scale, nullptr, 0, nullptr, 0, stream);
 }

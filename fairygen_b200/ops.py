@@ -88,20 +88,47 @@ def attention_workspace(q_rows: int, kv_rows: int, heads: int, device) -> Option
 
 def attention(q, k, v, out, heads: int, scale: Optional[float] = None, lse: Optional[torch.Tensor] = None):
     """out = softmax(q k^T scale) v per 128-wide head; q/out [s_q, heads*128], k/v [s_kv, heads*128].
-    lse (optional, fp32 [heads, s_q]) receives the log2-domain log-sum-exp rows for the backward pass."""
+    lse (optional, fp32 [heads, ld] with ld >= s_q, ld % 64 == 0) receives the log2-domain log-sum-exp rows
+    for the backward pass."""
     ldq, ldk, ldv, ldo = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v"), _rowmajor(out, "out")
     s_q, s_kv = q.shape[0], k.shape[0]
     width = heads * 128
     if q.shape[1] != width or k.shape[1] != width or v.shape != k.shape or out.shape != q.shape:
         raise ValueError(f"attention shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} heads {heads}")
     scale = 1.0 / math.sqrt(128.0) if scale is None else scale
-    if lse is not None and (lse.dtype != torch.float32 or tuple(lse.shape) != (heads, s_q) or not lse.is_contiguous()):
-        raise ValueError("lse must be a contiguous float32 [heads, s_q] tensor")
+    if lse is not None and (lse.dtype != torch.float32 or lse.dim() != 2 or lse.shape[0] != heads or lse.shape[1] < s_q
+                            or lse.shape[1] % 64 or not lse.is_contiguous()):
+        raise ValueError("lse must be a contiguous float32 [heads, ld] tensor with ld >= s_q and ld % 64 == 0")
     c = _h(q)
     ws = attention_workspace(s_q, s_kv, heads, q.device)
     _lib.check(_lib.lib().fgb_attn_fwd_ex(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), ldo, s_q, s_kv, heads,
-                                          scale, _p(lse), _p(ws), 0 if ws is None else ws.numel(), _stream()), "fgb_attn_fwd_ex")
+                                          scale, _p(lse), 0 if lse is None else lse.shape[1], _p(ws),
+                                          0 if ws is None else ws.numel(), _stream()), "fgb_attn_fwd_ex")
     return out
+
+
+def stat_rows(s_q: int) -> int:
+    """Row stride of the lse / delta buffers: s_q rounded up to the 64-row sub-tile of fgb_attn_bwd."""
+    return -(-s_q // 64) * 64
+
+
+def attention_bwd(q, k, v, out, dout, lse, dq, dk, dv, heads: int, scale: Optional[float] = None, delta=None):
+    """Backward of :func:`attention`; writes dq, dk, dv (bf16, same layouts as q, k, v)."""
+    s_q, s_kv = q.shape[0], k.shape[0]
+    ld = [_rowmajor(t, n) for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv"))]
+    width = heads * 128
+    if any(t.shape[1] != width for t in (q, k, v, out, dout, dq, dk, dv)) or dq.shape != q.shape or dk.shape != k.shape or dv.shape != v.shape:
+        raise ValueError("attention_bwd shape mismatch")
+    if lse.dtype != torch.float32 or lse.dim() != 2 or lse.shape[0] != heads or lse.shape[1] % 64 or lse.shape[1] < s_q:
+        raise ValueError("lse must be the float32 [heads, ld] tensor written by attention(..., lse=)")
+    if delta is None:
+        delta = torch.empty_like(lse)
+    scale = 1.0 / math.sqrt(128.0) if scale is None else scale
+    c = _h(q)
+    _lib.check(_lib.lib().fgb_attn_bwd(c.handle, _p(q), ld[0], _p(k), ld[1], _p(v), ld[2], _p(out), ld[3], _p(dout), ld[4], _p(lse),
+                                       _p(delta), lse.shape[1], _p(dq), ld[5], _p(dk), ld[6], _p(dv), ld[7], s_q, s_kv, heads,
+                                       scale, _stream()), "fgb_attn_bwd")
+    return dq, dk, dv
 
 
 def ln_modulate(x, out, eps, shift0, scale0, shift1, scale1, rows_mod0):

@@ -81,11 +81,23 @@ int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_
  *    units of the last, partly filled wave of CTAs into key chunks whose partial (max, sum, O) results are merged by a
  *    small combine kernel. With heads/P heads per rank under Ulysses SP the grid is only 2.2 waves of the 148 SMs at
  *    P = 8, so without the split a third of the machine idles for a whole wave. NULL = no split.
- *  - lse (optional): fp32 [heads][s_q], log2-domain log-sum-exp of the scaled scores, saved for fgb_attn_bwd. */
+ *  - lse (optional): fp32 [heads][ld_lse], log2-domain log-sum-exp of the scaled scores, saved for fgb_attn_bwd
+ *    (ld_lse >= s_q; rows in [s_q, ld_lse) receive the value of an all-zero query row). */
 int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                     int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
-                    void* lse, void* workspace, int64_t workspace_bytes, void* stream);
+                    void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s_kv, int32_t heads);
+
+/* Backward of fgb_attn_fwd(_ex): given dout = dL/do, writes dq [s_q, heads*128], dk and dv [s_kv, heads*128] (bf16).
+ * The reference obtains this from torch autograd through flash_attention (DIT:27-60) during the stage-2 LoRA
+ * fine-tune (config 5; diffusion/loss.py:17-20 -> model_fn -> DiTBlock, PIPE:1348-1360 re-computes each block).
+ * o and lse are the forward's outputs; lse and the scratch `delta` are fp32 [heads][ld_stat] with ld_stat a multiple
+ * of 64 and >= s_q (delta = rowsum(dout*o) is computed here). Deterministic: two tensor-core kernels (dK|dV with the
+ * keys resident, dQ with the queries resident), no atomics. */
+int fgb_attn_bwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                 const void* o, int64_t ldo, const void* dout, int64_t ld_do, const void* lse, void* delta,
+                 int64_t ld_stat, void* dq, int64_t ld_dq, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv,
+                 int32_t s_q, int32_t s_kv, int32_t heads, float scale, void* stream);
 
 /* ---- fused memory-bound kernels ------------------------------------------------------------ */
 

@@ -133,6 +133,50 @@ def test_attention_properties_at_headline_size(env):
         assert rel_l2(o1[rows, sl], ref) < 1e-2
 
 
+@pytest.mark.parametrize("s_q,s_kv,heads", [(128, 128, 1), (256, 64, 1), (300, 200, 2), (1000, 1000, 3), (70, 515, 2),
+                                            (2304, 2304, 2), (5070, 512, 2)])
+def test_attention_backward_matches_autograd(env, s_q, s_kv, heads):
+    """fgb_attn_bwd vs torch autograd through the oracle's fp32 attention on the same bf16 inputs (config 5:
+    the reference back-propagates through flash_attention, DIT:27-60)."""
+    ops, o = env
+    d = heads * 128
+    q, k, v = rnd(s_q, d, seed=1), rnd(s_kv, d, seed=2), rnd(s_kv, d, seed=3)
+    dout = rnd(s_q, d, seed=4)
+    out = torch.empty(s_q, d, dtype=BF, device="cuda")
+    lse = torch.full((heads, ops.stat_rows(s_q)), float("nan"), dtype=torch.float32, device="cuda")
+    ops.attention(q, k, v, out, heads, lse=lse)
+    dq, dk, dv = (torch.full_like(t, float("nan")) for t in (q, k, v))
+    ops.attention_bwd(q, k, v, out, dout, lse, dq, dk, dv, heads)
+    ops.sync_check()
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = o.attention(qf[None], kf[None], vf[None], heads)[0]
+    ref.backward(dout.float())
+    # lse is in log2 units: log2(sum_j exp(s_ij))
+    sc = torch.einsum("qhd,khd->hqk", q.float().view(s_q, heads, 128), k.float().view(s_kv, heads, 128)) / math.sqrt(128)
+    assert (lse[:, :s_q] - torch.logsumexp(sc, dim=-1) * math.log2(math.e)).abs().max() < 2e-3
+    assert torch.isfinite(lse).all()
+    for got, want, name in ((dq, qf.grad, "dq"), (dk, kf.grad, "dk"), (dv, vf.grad, "dv")):
+        assert torch.isfinite(got.float()).all(), name
+        assert rel_l2(got, want) < 1e-2, (name, rel_l2(got, want))
+
+
+def test_attention_backward_strided_fused_qkv(env):
+    """q|k|v and dq|dk|dv as column slices of fused [S, 3*H*128] buffers (the training engine's layout)."""
+    ops, o = env
+    heads, s = 2, 450
+    d = heads * 128
+    qkv, dqkv = rnd(s, 3 * d, seed=5), torch.zeros(s, 3 * d, dtype=BF, device="cuda")
+    dout, out = rnd(s, d, seed=6), torch.empty(s, d, dtype=BF, device="cuda")
+    lse = torch.empty(heads, ops.stat_rows(s), dtype=torch.float32, device="cuda")
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    ops.attention(q, k, v, out, heads, lse=lse)
+    ops.attention_bwd(q, k, v, out, dout, lse, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], heads)
+    ops.sync_check()
+    leaf = qkv.float().requires_grad_(True)
+    o.attention(leaf[None, :, :d], leaf[None, :, d:2 * d], leaf[None, :, 2 * d:], heads)[0].backward(dout.float())
+    assert rel_l2(dqkv, leaf.grad) < 1e-2
+
+
 @pytest.mark.parametrize("rows,dim", [(30, 256), (1000, 3072), (129, 1024)])
 def test_ln_modulate_and_affine(env, rows, dim):
     ops, o = env

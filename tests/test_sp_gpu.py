@@ -55,3 +55,45 @@ def test_sp2_equals_single_gpu(tmp_path, shape):
     for r in range(world):
         res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         assert res["finite"] and res["err"] < 2e-3, res   # same kernels, same rounding; only the attention tiling differs
+
+
+def _cfg_worker(rank, world, port, shape, sp_ways, out_dir):
+    """CFG-parallel pair (x Ulysses inside each half): a 3-step denoise must equal the single-GPU sequential loop."""
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+
+    import fairygen_b200 as fg
+    from fairygen_b200 import synthetic
+    from fairygen_b200.cfg_parallel import Layout, ParallelContext
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    cfg = fg.WanDiTConfig(dim=1024, ffn_dim=2048, text_dim=256, num_heads=8, num_layers=2)
+    sd = synthetic.random_state_dict(cfg, seed=0, device=dev, dtype=BF)
+    lat, z0, cp, cn = synthetic.synthetic_inputs(cfg, shape, text_len=64, live_text=16, pin=False)
+    single = fg.WanDiTEngine(cfg, dev)
+    single.load_state_dict(sd)
+    ref = fg.WanDenoiser(single, 4)(lat, cp, cn, z0, steps=range(3))
+    par = ParallelContext(Layout(world, 1, 2, sp_ways))
+    eng = fg.WanDiTEngine(cfg, dev, sp=par.sequence_parallel())
+    eng.load_state_dict(sd)
+    out = fg.WanDenoiser(eng, 4, cfg_group=par)(lat, cp, cn, z0, steps=range(3))
+    fg.ops.sync_check()
+    err = float((out.float() - ref.float()).norm() / ref.float().norm())
+    torch.save({"err": err, "finite": bool(torch.isfinite(out.float()).all())}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,sp_ways", [(2, 1), (4, 2)])
+def test_cfg_parallel_equals_sequential(tmp_path, world, sp_ways):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+
+    mp.spawn(_cfg_worker, args=(world, _free_port(), (1, 48, 3, 10, 14), sp_ways, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        # sp_ways == 1: bit-identical kernels on both sides, only the exchange differs
+        assert res["finite"] and res["err"] < (1e-6 if sp_ways == 1 else 2e-3), res

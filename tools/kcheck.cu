@@ -89,7 +89,7 @@ __global__ void attn_ref_kernel(const bf16* q, const bf16* k, const bf16* v, flo
     for (int i = 0; i < 4; ++i) acc[i] += pb * __bfloat162float(v[j * W + h * 128 + lane * 4 + i]);
   }
   for (int i = 0; i < 4; ++i) o[row * W + h * 128 + lane * 4 + i] = acc[i] / l;
-  if (lane == 0) lse_ref[(int64_t)h * s_q + row] = (mx + logf(l)) * 1.4426950408889634f;
+  if (lane == 0) lse_ref[(int64_t)h * ((s_q + 63) / 64 * 64) + row] = (mx + logf(l)) * 1.4426950408889634f;
 }
 
 static void compare(const std::vector<bf16>& got, const std::vector<float>& ref, const char* what) {
@@ -185,26 +185,28 @@ int main(int argc, char** argv) {
     void* ws = nullptr;
     float* lse = nullptr;
     if (ws_bytes > 0) CK(cudaMalloc(&ws, ws_bytes));
-    CK(cudaMalloc(&lse, (size_t)SQ * H * 4));
+    const int64_t LDS = (SQ + 63) / 64 * 64;
+    CK(cudaMalloc(&lse, (size_t)LDS * H * 4));
     printf("attn workspace %lld bytes\n", (long long)ws_bytes);
-    auto run = [&]() { return fgb_attn_fwd_ex(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, lse, ws, ws_bytes, nullptr); };
+    auto run = [&]() { return fgb_attn_fwd_ex(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, lse, LDS, ws, ws_bytes, nullptr); };
     FK(run());
     FK(fgb_sync_check(ctx, nullptr));
     if (check) {
       CK(cudaMalloc(&oref, (size_t)SQ * W * 4));
       dim3 g(SQ, H);
       float* lse_ref;
-      CK(cudaMalloc(&lse_ref, (size_t)SQ * H * 4));
+      CK(cudaMalloc(&lse_ref, (size_t)LDS * H * 4));
       CK(cudaFuncSetAttribute(attn_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKV * 4));
       attn_ref_kernel<<<g, 32, SKV * 4>>>(q, k, v, oref, SQ, SKV, H, scale, lse_ref);
       CK(cudaGetLastError());
       CK(cudaDeviceSynchronize());
       {
-        std::vector<float> a((size_t)SQ * H), b((size_t)SQ * H);
+        std::vector<float> a((size_t)LDS * H), b((size_t)LDS * H);
         CK(cudaMemcpy(a.data(), lse, a.size() * 4, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(b.data(), lse_ref, b.size() * 4, cudaMemcpyDeviceToHost));
         double mx = 0;
-        for (size_t i = 0; i < a.size(); ++i) mx = fmax(mx, fabs((double)a[i] - b[i]));
+        for (int h = 0; h < H; ++h)
+          for (int r = 0; r < SQ; ++r) mx = fmax(mx, fabs((double)a[h * LDS + r] - b[h * LDS + r]));
         printf("lse max_abs_err=%.3e %s\n", mx, mx < 2e-3 ? "PASS" : "FAIL");
       }
       std::vector<bf16> got((size_t)SQ * W);
@@ -227,6 +229,40 @@ int main(int argc, char** argv) {
       printf("attn s_q=%d s_kv=%d heads=%d: %.3f ms  %.1f TFLOP/s\n", SQ, SKV, H, ms,
              4.0 * SQ * SKV * (double)W / ms * 1e-9);
     }
+  } else if (!strcmp(argv[1], "attnbwd") && argc >= 5) {
+    // timing only (parity lives in tests/test_kernels_gpu.py against torch autograd)
+    int SQ = atoi(argv[2]), SKV = atoi(argv[3]), H = atoi(argv[4]);
+    int iters = argc > 5 ? atoi(argv[5]) : 3;
+    int64_t W = (int64_t)H * 128;
+    const int64_t LDS = (SQ + 63) / 64 * 64;
+    bf16 *q, *k, *v, *o, *dout, *dq, *dk, *dv;
+    float *lse, *delta;
+    for (bf16** p : {&q, &o, &dout, &dq}) CK(cudaMalloc(p, (size_t)SQ * W * 2));
+    for (bf16** p : {&k, &v, &dk, &dv}) CK(cudaMalloc(p, (size_t)SKV * W * 2));
+    CK(cudaMalloc(&lse, (size_t)LDS * H * 4));
+    CK(cudaMalloc(&delta, (size_t)LDS * H * 4));
+    auto fill = [&](bf16* p, int64_t n, uint32_t seed, float s) { fill_kernel<<<(n + 255) / 256, 256>>>(p, n, seed, s); };
+    fill(q, SQ * W, 11, 2.0f);
+    fill(k, SKV * W, 12, 2.0f);
+    fill(v, SKV * W, 13, 1.0f);
+    fill(dout, SQ * W, 14, 1.0f);
+    float scale = 1.0f / sqrtf(128.f);
+    FK(fgb_attn_fwd_ex(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, lse, LDS, nullptr, 0, nullptr));
+    auto run = [&]() {
+      return fgb_attn_bwd(ctx, q, W, k, W, v, W, o, W, dout, W, lse, delta, LDS, dq, W, dk, W, dv, W, SQ, SKV, H, scale, nullptr);
+    };
+    FK(run());
+    FK(fgb_sync_check(ctx, nullptr));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) FK(run());
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+    // counted FLOPs: 2.5 x forward (5 S x S x 128 products: S, dP, dV, dK, dQ); the two-kernel scheme executes 7
+    printf("attnbwd s_q=%d s_kv=%d heads=%d: %.3f ms  %.1f TFLOP/s counted (2.5x fwd), %.1f executed (3.5x fwd)\n", SQ, SKV, H, ms,
+           10.0 * SQ * SKV * (double)W / ms * 1e-9, 14.0 * SQ * SKV * (double)W / ms * 1e-9);
   } else {
     printf("bad arguments\n");
     return 1;
