@@ -30,6 +30,19 @@ SIGNATURES = {
     "fgb_attn_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64,
                                     _I32, _I32, _I32, _F, _P]),
     "fgb_attn_workspace_bytes": (c_int64, [_P, _I32, _I32, _I32]),
+    "fgb_gemm_dgrad": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P]),
+    "fgb_ln_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P, _I32, _I32, _P]),
+    "fgb_rmsnorm_rope_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "fgb_gelu_tanh": (ctypes.c_int, [_P, _P, _P, _I64, _P]),
+    "fgb_gelu_tanh_bwd": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P]),
+    "fgb_mul_gate": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _P, _P, _I32, _P]),
+    "fgb_lora_merge": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _P, _F, _F, _P, _I64, _I32, _I32, _I32, _P]),
+    "fgb_lora_wgrad": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _F, _I32, _I32, _I32, _P]),
+    "fgb_bernoulli_mask": (ctypes.c_int, [_P, _P, _I64, _F, ctypes.c_uint64, _P]),
+    "fgb_fm_noise_target": (ctypes.c_int, [_P, _P, _P, _F, _P, _P, _I64, _P]),
+    "fgb_mse_loss_grad": (ctypes.c_int, [_P, _P, _P, _F, _P, _P, _I64, _P]),
+    "fgb_unpatchify_bwd": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P]),
+    "fgb_adamw_step": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P]),
     "fgb_ln_modulate": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _I32, _P]),
     "fgb_ln_affine": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
     "fgb_rmsnorm_rope": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _F, _P, _P, _I32, _I32, _I32, _I32, _P]),

@@ -12,21 +12,6 @@ namespace fgb {
 
 constexpr int kRowWarps = 4;  // rows per CTA (one warp per row)
 
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
-  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
-  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
-  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  uint4 v;
-  v.x = pack_bf16(f[0], f[1]);
-  v.y = pack_bf16(f[2], f[3]);
-  v.z = pack_bf16(f[4], f[5]);
-  v.w = pack_bf16(f[6], f[7]);
-  return v;
-}
-
 // ---------------------------------------------------------------------------------------------
 // LayerNorm (no affine) + adaLN modulate, or LayerNorm with affine.      DIT:205-207, 63-64, 224-227
 // NV = dim / 256 16-byte vectors per lane.

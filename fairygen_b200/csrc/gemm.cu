@@ -62,7 +62,10 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
-template <int EPI>
+// B_MN = false: W is [n, k] (nn.Linear weight, K-major B operand)            C = A · Wᵀ   (forward)
+// B_MN = true : W is [k, n] (the same nn.Linear weight read as [out=k, in=n])  C = A · W    (dgrad: dX = dY · W)
+//               B tile = 4 TMA boxes of [64 k-rows][64 n-cols], fed to the tensor core as an MN-major operand.
+template <int EPI, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -111,7 +114,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], kABytes + kBBytes);
           tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full[stage], kb * kBK, m_blk * kBM, kEvictNormal);
-          tma_load_2d(smem_b + stage * kBBytes, &tmap_b, &full[stage], kb * kBK, n_blk * kBN, kEvictLast);
+          if (B_MN) {
+#pragma unroll
+            for (int b = 0; b < kBN / 64; ++b)
+              tma_load_2d(smem_b + stage * kBBytes + b * (kBK * 128), &tmap_b, &full[stage], n_blk * kBN + b * 64, kb * kBK,
+                          kEvictLast);
+          } else {
+            tma_load_2d(smem_b + stage * kBBytes, &tmap_b, &full[stage], kb * kBK, n_blk * kBN, kEvictLast);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -119,10 +129,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     if (elect_one()) {
       // ------------------------------- MMA issuer ---------------------------------
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, 0, B_MN ? 1 : 0);
       // descriptors are built once; per MMA only an offset is added to the 14-bit address field
       const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(smem_a), 16, 1024);
-      const uint64_t b_desc0 = make_sdesc_sw128(smem_u32(smem_b), 16, 1024);
+      // MN-major B: rows are k (128 B = 64 n each), the next 64 n-columns live kBK*128 bytes further (LBO)
+      const uint64_t b_desc0 = B_MN ? make_sdesc_sw128(smem_u32(smem_b), kBK * 128, 1024) : make_sdesc_sw128(smem_u32(smem_b), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -139,8 +150,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * kBBytes) >> 4);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            umma_ss(tmem_d, adesc + static_cast<uint64_t>((k * 32) >> 4), bdesc + static_cast<uint64_t>((k * 32) >> 4), idesc,
-                    (kb | k) != 0);
+            umma_ss(tmem_d, adesc + static_cast<uint64_t>((k * 32) >> 4),
+                    bdesc + static_cast<uint64_t>((B_MN ? k * 2048 : k * 32) >> 4), idesc, (kb | k) != 0);
           tc_commit(&empty[stage]);  // ring slot reusable once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -232,10 +243,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int EPI>
+template <int EPI, bool B_MN = false>
 static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t stream) {
-  auto kfn = gemm_bf16_kernel<EPI>;
+  auto kfn = gemm_bf16_kernel<EPI, B_MN>;
   static bool configured = false;  // per template instance; attribute is sticky per function
   if (!configured) {
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
@@ -292,4 +303,34 @@ extern "C" int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const voi
     case FGB_EPI_GATED_RESIDUAL: return launch_gemm<FGB_EPI_GATED_RESIDUAL>(ctx, ta, tb, p, s);
     default: return launch_gemm<FGB_EPI_RESIDUAL>(ctx, ta, tb, p, s);
   }
+}
+
+extern "C" int fgb_gemm_dgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* w, int64_t ldw, void* dx, int64_t ld_dx,
+                              int32_t m, int32_t n_in, int32_t k_out, void* stream) {
+  using namespace fgb;
+  FGB_CHECK_ARG(ctx, "fgb_gemm_dgrad: ctx is NULL");
+  FGB_CHECK_ARG(dy && w && dx, "fgb_gemm_dgrad: NULL matrix pointer");
+  FGB_CHECK_ARG(m > 0 && n_in > 0 && k_out > 0, "fgb_gemm_dgrad: empty problem m=%d n_in=%d k_out=%d", m, n_in, k_out);
+  FGB_CHECK_ARG(n_in % 8 == 0 && k_out % 8 == 0, "fgb_gemm_dgrad: n_in=%d and k_out=%d must be multiples of 8", n_in, k_out);
+  FGB_CHECK_ARG(ld_dy >= k_out && ldw >= n_in && ld_dx >= n_in, "fgb_gemm_dgrad: leading dimension too small");
+  FGB_CHECK_ARG(ld_dx % 8 == 0 && aligned16(dx), "fgb_gemm_dgrad: dx must be 16-byte aligned with ld_dx %% 8 == 0");
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(ctx, &ta, dy, m, k_out, ld_dy, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(ctx, &tb, w, k_out, n_in, ldw, kBK);   // box = [64 k-rows][64 n-cols]
+  if (rc) return rc;
+  GemmParams p;
+  p.bias = nullptr;
+  p.c = static_cast<__nv_bfloat16*>(dx);
+  p.gate0 = p.gate1 = nullptr;
+  p.ldc = ld_dx;
+  p.m = m;
+  p.n = n_in;
+  p.k = k_out;
+  p.rows_gate0 = 0;
+  p.m_blocks = (m + kBM - 1) / kBM;
+  p.n_blocks = (n_in + kBN - 1) / kBN;
+  p.tiles = p.m_blocks * p.n_blocks;
+  p.k_blocks = (k_out + kBK - 1) / kBK;
+  return launch_gemm<FGB_EPI_BIAS, true>(ctx, ta, tb, p, static_cast<cudaStream_t>(stream));
 }

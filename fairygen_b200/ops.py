@@ -274,3 +274,140 @@ def rope_table(head_dim: int = 128, positions: int = 1024, theta: float = 10000.
 def sync_check(device=None):
     c = context(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
     _lib.check(_lib.lib().fgb_sync_check(c.handle, _stream()), "fgb_sync_check")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training kernels (BASELINE config 5; see include/fairygen_b200.h "training")
+# ---------------------------------------------------------------------------------------------------------
+def gemm_dgrad(dy, w, dx):
+    """dx[m, in] = dy[m, out] @ w[out, in]  (input gradient of nn.Linear, W as stored)."""
+    ld_dy, ldw, ld_dx = _rowmajor(dy, "dy"), _rowmajor(w, "w"), _rowmajor(dx, "dx")
+    m, k_out = dy.shape
+    n_in = w.shape[1]
+    if w.shape[0] != k_out or tuple(dx.shape) != (m, n_in):
+        raise ValueError(f"gemm_dgrad shape mismatch: dy {tuple(dy.shape)} w {tuple(w.shape)} dx {tuple(dx.shape)}")
+    c = _h(dy)
+    _lib.check(_lib.lib().fgb_gemm_dgrad(c.handle, _p(dy), ld_dy, _p(w), ldw, _p(dx), ld_dx, m, n_in, k_out, _stream()), "fgb_gemm_dgrad")
+    return dx
+
+
+def ln_bwd(x, dy, out, eps, g0, g1=None, rows_mod0=0, affine=False, dres=None):
+    rows, dim = x.shape
+    _vec(g0, dim, "g0"), _vec(g1, dim, "g1")
+    c = _h(x)
+    _lib.check(_lib.lib().fgb_ln_bwd(c.handle, _p(x), _rowmajor(x, "x"), _p(dy), _rowmajor(dy, "dy"), _p(dres),
+                                     0 if dres is None else _rowmajor(dres, "dres"), _p(out), _rowmajor(out, "out"), rows, dim, eps,
+                                     _p(g0), _p(g1), rows_mod0, 1 if affine else 0, _stream()), "fgb_ln_bwd")
+    return out
+
+
+def rmsnorm_rope_bwd(x_pre, dy, eps, weight, rope_tab=None, grid=(1, 1, 1), token_offset=0):
+    """In place on dy [rows, dim]: gradient w.r.t. the rotated, normalised output -> gradient w.r.t. x_pre."""
+    rows, dim = x_pre.shape
+    _vec(weight, dim, "weight")
+    c = _h(dy)
+    _lib.check(_lib.lib().fgb_rmsnorm_rope_bwd(c.handle, _p(x_pre), _rowmajor(x_pre, "x_pre"), _p(dy), _rowmajor(dy, "dy"), rows, dim, eps,
+                                               _p(weight), _p(rope_tab), grid[0], grid[1], grid[2], token_offset, _stream()),
+               "fgb_rmsnorm_rope_bwd")
+    return dy
+
+
+def _flat_bf16(*ts):
+    n = ts[0].numel()
+    for t in ts:
+        if t.dtype != BF16 or not t.is_contiguous() or t.numel() != n:
+            raise ValueError("expected contiguous bf16 tensors of equal size")
+    return n
+
+
+def gelu_tanh(z, h):
+    n = _flat_bf16(z, h)
+    _lib.check(_lib.lib().fgb_gelu_tanh(_h(z).handle, _p(z), _p(h), n, _stream()), "fgb_gelu_tanh")
+    return h
+
+
+def gelu_tanh_bwd(z, dh, dz):
+    n = _flat_bf16(z, dh, dz)
+    _lib.check(_lib.lib().fgb_gelu_tanh_bwd(_h(z).handle, _p(z), _p(dh), _p(dz), n, _stream()), "fgb_gelu_tanh_bwd")
+    return dz
+
+
+def mul_gate(dx, out, gate0, gate1, rows_gate0):
+    rows, dim = dx.shape
+    _vec(gate0, dim, "gate0"), _vec(gate1, dim, "gate1")
+    _lib.check(_lib.lib().fgb_mul_gate(_h(dx).handle, _p(dx), _rowmajor(dx, "dx"), _p(out), _rowmajor(out, "out"), rows, dim,
+                                       _p(gate0), _p(gate1), rows_gate0, _stream()), "fgb_mul_gate")
+    return out
+
+
+def lora_merge(w, a1, b1, b2, mask, w_eff, mask_mul=2.0, scaling=1.0):
+    """w_eff = w + scaling * (b1 + bf16(bf16(b2*mask)*mask_mul)) @ a1;  w [n,k], a1 [r,k], b1/b2 [n,r], mask uint8 [n,r]."""
+    n, k = w.shape
+    r = a1.shape[0]
+    for t, shp in ((a1, (r, k)), (b1, (n, r)), (b2, (n, r)), (w_eff, (n, k))):
+        if t is not None and (tuple(t.shape) != shp or t.dtype != BF16):
+            raise ValueError(f"lora_merge: expected bf16 {shp}, got {t.dtype} {tuple(t.shape)}")
+    for t in (a1, b1, b2, mask):
+        if t is not None and not t.is_contiguous():
+            raise ValueError("lora_merge: a1, b1, b2 and mask must be contiguous")
+    if mask is not None and (mask.dtype != torch.uint8 or tuple(mask.shape) != (n, r)):
+        raise ValueError("lora_merge: mask must be uint8 [n, r]")
+    _lib.check(_lib.lib().fgb_lora_merge(_h(w).handle, _p(w), _rowmajor(w, "w"), _p(a1), _rowmajor(a1, "a1"), _p(b1), _p(b2), _p(mask),
+                                         mask_mul, scaling, _p(w_eff), _rowmajor(w_eff, "w_eff"), n, k, r, _stream()), "fgb_lora_merge")
+    return w_eff
+
+
+def lora_wgrad(dy, t, db, mask=None, mul=1.0):
+    """db[n, r] (fp32) += mul * mask * dy[s, n]^T @ t[s, r]."""
+    rows, n = dy.shape
+    r = t.shape[1]
+    if t.shape[0] != rows or db.dtype != torch.float32 or tuple(db.shape) != (n, r) or not db.is_contiguous():
+        raise ValueError("lora_wgrad shape mismatch")
+    if mask is not None and (mask.dtype != torch.uint8 or tuple(mask.shape) != (n, r) or not mask.is_contiguous()):
+        raise ValueError("lora_wgrad: mask must be contiguous uint8 [n, r]")
+    _lib.check(_lib.lib().fgb_lora_wgrad(_h(dy).handle, _p(dy), _rowmajor(dy, "dy"), _p(t), _rowmajor(t, "t"), _p(db), _p(mask), mul,
+                                         rows, n, r, _stream()), "fgb_lora_wgrad")
+    return db
+
+
+def bernoulli_mask(out_u8, drop_prob: float, seed: int):
+    if out_u8.dtype != torch.uint8 or not out_u8.is_contiguous():
+        raise ValueError("bernoulli_mask: contiguous uint8 output")
+    _lib.check(_lib.lib().fgb_bernoulli_mask(_h(out_u8).handle, _p(out_u8), out_u8.numel(), drop_prob, seed & (2 ** 64 - 1), _stream()),
+               "fgb_bernoulli_mask")
+    return out_u8
+
+
+def fm_noise_target(x0, noise, sigma: float, latents, target):
+    n = _flat_bf16(x0, noise, latents, target)
+    _lib.check(_lib.lib().fgb_fm_noise_target(_h(x0).handle, _p(x0), _p(noise), sigma, _p(latents), _p(target), n, _stream()),
+               "fgb_fm_noise_target")
+    return latents, target
+
+
+def mse_loss_grad(pred, target, weight: float, loss_f32, dpred=None):
+    n = _flat_bf16(pred, target) if dpred is None else _flat_bf16(pred, target, dpred)
+    if loss_f32.dtype != torch.float32 or loss_f32.numel() != 1:
+        raise ValueError("mse_loss_grad: loss must be a float32 scalar tensor")
+    _lib.check(_lib.lib().fgb_mse_loss_grad(_h(pred).handle, _p(pred), _p(target), weight, _p(loss_f32), _p(dpred), n, _stream()),
+               "fgb_mse_loss_grad")
+    return loss_f32
+
+
+def unpatchify_bwd(dpred, d_rows, grid):
+    f, h, w = grid
+    ch = dpred.shape[0]
+    if dpred.dtype != BF16 or not dpred.is_contiguous() or tuple(dpred.shape) != (ch, f, 2 * h, 2 * w) or d_rows.shape[0] < f * h * w:
+        raise ValueError("unpatchify_bwd shape mismatch")
+    _lib.check(_lib.lib().fgb_unpatchify_bwd(_h(dpred).handle, _p(dpred), _p(d_rows), _rowmajor(d_rows, "d_rows"), ch, f, h, w, _stream()),
+               "fgb_unpatchify_bwd")
+    return d_rows
+
+
+def adamw_step(param, grad, m, v, lr, beta1, beta2, eps, weight_decay, step: int):
+    n = param.numel()
+    if param.dtype != BF16 or any(t.dtype != torch.float32 or t.numel() != n or not t.is_contiguous() for t in (grad, m, v)) or not param.is_contiguous():
+        raise ValueError("adamw_step: bf16 param, fp32 grad/m/v of equal size")
+    _lib.check(_lib.lib().fgb_adamw_step(_h(param).handle, _p(param), _p(grad), _p(m), _p(v), n, lr, beta1, beta2, eps, weight_decay, step,
+                                         _stream()), "fgb_adamw_step")
+    return param

@@ -165,6 +165,65 @@ int fgb_sp_pack_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* send, int3
 int fgb_sp_unpack_heads(fgb_ctx* ctx, const void* recv, void* x, int64_t ldx, int32_t s_local, int32_t heads,
                         int32_t groups, int32_t world, void* stream);
 
+/* ---- training (BASELINE config 5: stage-2 motion-LoRA fine-tune step) -------------------------------------------
+ * The reference trains the `lora_B2` matrices of the 300 adapted Linears (diffusion/training_module.py:266-352, TMOD)
+ * under the flow-matching SFT loss (diffusion/loss.py:5-21, LOSS); every gradient below is what torch autograd
+ * computes there. Activation gradients are bf16 (as autograd's), reductions / B2 gradients fp32. */
+
+/* dx[m, n_in] = dy[m, k_out] · W[k_out, n_in] — input gradient of nn.Linear with W as stored ([out, in]); same tcgen05
+ * kernel as fgb_gemm_bf16 with W fed as an MN-major operand (no transposed weight copy). W is frozen, so there is no
+ * full-rank wgrad on this path (TMOD:279-307). */
+int fgb_gemm_dgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* w, int64_t ldw, void* dx, int64_t ld_dx,
+                   int32_t m, int32_t n_in, int32_t k_out, void* stream);
+
+/* Backward of fgb_ln_modulate (affine = 0: g = 1 + scale row, rows < rows_mod0 use g0 else g1) or fgb_ln_affine
+ * (affine = 1: g0 = weight): out = dres + LN'(x)ᵀ(dy * g). dres may be NULL, and may alias out. */
+int fgb_ln_bwd(fgb_ctx* ctx, const void* x, int64_t ldx, const void* dy, int64_t ld_dy, const void* dres, int64_t ld_dres,
+               void* out, int64_t ld_out, int32_t rows, int32_t dim, float eps, const void* g0, const void* g1,
+               int32_t rows_mod0, int32_t affine, void* stream);
+
+/* Backward of fgb_rmsnorm_rope, in place on dy: x is the PRE-norm input saved by the forward. */
+int fgb_rmsnorm_rope_bwd(fgb_ctx* ctx, const void* x, int64_t ldx, void* dy, int64_t ld_dy, int32_t rows, int32_t dim,
+                         float eps, const void* weight, const void* rope_tab, int32_t gf, int32_t gh, int32_t gw,
+                         int32_t token_offset, void* stream);
+
+/* h = gelu_tanh(z) and dz = dh * gelu_tanh'(z) (the training forward keeps z, so FFN-1 uses FGB_EPI_BIAS). DIT:208 */
+int fgb_gelu_tanh(fgb_ctx* ctx, const void* z, void* h, int64_t n, void* stream);
+int fgb_gelu_tanh_bwd(fgb_ctx* ctx, const void* z, const void* dh, void* dz, int64_t n, void* stream);
+
+/* out[r, :] = dx[r, :] * gate[r < rows_gate0 ? 0 : 1][:]  — gradient through GateModule (DIT:192-193). */
+int fgb_mul_gate(fgb_ctx* ctx, const void* dx, int64_t ld_dx, void* out, int64_t ld_out, int32_t rows, int32_t dim,
+                 const void* gate0, const void* gate1, int32_t rows_gate0, void* stream);
+
+/* W_eff[n,k] = W[n,k] + scaling * sum_r (B1[n,r] + bf16(bf16(B2[n,r]*mask[n,r]) * mask_mul)) * A1[r,k]
+ * — the stage-2 forward of TMOD:317-352 folded into one weight per step (b1 or b2 may be NULL; mask uint8 or NULL). */
+int fgb_lora_merge(fgb_ctx* ctx, const void* w, int64_t ldw, const void* a1, int64_t lda, const void* b1, const void* b2,
+                   const void* mask, float mask_mul, float scaling, void* w_eff, int64_t ld_eff, int32_t n, int32_t k,
+                   int32_t rank, void* stream);
+
+/* db[n, r] += mul * mask[n, r] * sum_s dy[s, n] * t[s, r]   (fp32 accumulate; t = A1·x, [rows, rank] bf16). */
+int fgb_lora_wgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* t, int64_t ld_t, void* db_f32, const void* mask,
+                   float mul, int32_t rows, int32_t n, int32_t rank, void* stream);
+
+/* keep-mask of the weight dropout on B2 (`torch.rand_like(B2) > p`, TMOD:338-346): counter-based, reproducible per seed. */
+int fgb_bernoulli_mask(fgb_ctx* ctx, void* out_u8, int64_t n, float drop_prob, uint64_t seed, void* stream);
+
+/* latents = (1 - sigma) * x0 + sigma * noise;  target = noise - x0   (flow_match.py:164-175), bf16 roundings as torch's. */
+int fgb_fm_noise_target(fgb_ctx* ctx, const void* x0, const void* noise, float sigma, void* latents, void* target, int64_t n,
+                        void* stream);
+
+/* loss = weight * mean((pred - target)^2) in fp32 (LOSS:19-20) and dpred = dloss/dpred (bf16; NULL to skip). */
+int fgb_mse_loss_grad(fgb_ctx* ctx, const void* pred, const void* target, float weight, void* loss_f32, void* dpred, int64_t n,
+                      void* stream);
+
+/* Adjoint of fgb_unpatchify: d_rows[t, y*2C + z*C + c] = dpred[c, f, 2h+y, 2w+z]. */
+int fgb_unpatchify_bwd(fgb_ctx* ctx, const void* dpred, void* d_rows, int64_t ld_rows, int32_t channels, int32_t gf, int32_t gh,
+                       int32_t gw, void* stream);
+
+/* AdamW on bf16 parameters with fp32 gradient and moments (the reference's optimizer for lora_B2, train.py). */
+int fgb_adamw_step(fgb_ctx* ctx, void* param_bf16, const void* grad_f32, void* m_f32, void* v_f32, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,6 +245,9 @@ def attention(q, k, v, num_heads: int) -> torch.Tensor:
 
 
 def linear(w: Weights, name: str, x: torch.Tensor) -> torch.Tensor:
+    hook = w.get("__linear__")  # oracle/wan_train_oracle.py installs the stage-2 LoRA forward here
+    if hook is not None:
+        return hook(w, name, x)
     return F.linear(x, w[name + ".weight"], w[name + ".bias"])
 
 

@@ -1,0 +1,39 @@
+"""The training oracle (oracle/wan_train_oracle.py) against tests/golden/train.npz — loss, prediction and every
+lora_B2 gradient of one stage-2 fine-tune step computed by the REAL reference DiT under autograd
+(oracle/make_golden_train.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import wan_dit_oracle as o
+from oracle import wan_train_oracle as t
+
+
+@pytest.mark.parametrize("tag,shape,text_len,timestep_id", [("a", (1, 48, 3, 8, 8), 32, 500), ("b", (1, 48, 2, 6, 10), 24, 37)])
+def test_training_step_matches_reference(golden, tag, shape, text_len, timestep_id):
+    g = golden("train")
+    cfg = o.TINY
+    w, lora = o.make_weights(cfg, seed=0), o.make_lora(cfg, rank=32, seed=2)
+    b2, masks = t.make_b2(cfg), t.make_masks(cfg)
+    x0, _, ctx, _ = o.make_inputs(cfg, shape, text_len=text_len, live_text=8)
+    noise = torch.randn(shape, generator=torch.Generator().manual_seed(9))
+    loss, pred, grads = t.loss_and_grads(w, cfg, lora, b2, masks, x0, noise, timestep_id, ctx)
+    assert abs(float(loss) - float(g[f"{tag}_loss"])) <= 1e-6 * max(1.0, abs(float(g[f"{tag}_loss"])))
+    np.testing.assert_allclose(pred.numpy(), g[f"{tag}_pred"], rtol=1e-5, atol=1e-6)
+    assert len(grads) == 20
+    for name, gr in grads.items():
+        ref = g[f"{tag}_grad.{name}"]
+        assert np.abs(ref).max() > 0, name            # every adapted Linear (incl. cross-attention k/v) gets a gradient
+        np.testing.assert_allclose(gr.numpy(), ref, rtol=2e-4, atol=1e-8 + 2e-5 * np.abs(ref).max(), err_msg=name)
+        # the weight-dropout mask zeroes exactly the dropped entries
+        assert np.all(ref[masks[name].numpy() == 0] == 0)
+
+
+def test_training_schedule_and_targets():
+    sig, ts, wts = t.training_schedule()
+    assert len(sig) == 1000 and float(ts[0]) == 1000.0 and abs(float(wts.sum()) - 1000.0) < 1e-2
+    cfg = o.TINY
+    assert len(list(t.lora_targets(cfg))) == 10 * cfg.num_layers
+    m = t.make_masks(cfg)
+    frac = np.mean([float(v.float().mean()) for v in m.values()])
+    assert 0.45 < frac < 0.55
