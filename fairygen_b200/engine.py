@@ -132,6 +132,38 @@ class WanDiTEngine:
             return self.timer.call(name, fn, *args, **kwargs)
         return fn(*args, **kwargs)
 
+    def _time_tables(self, ws, timestep: torch.Tensor, R: int):
+        """Modulation tables for the R distinct timestep rows (row 0 = t=0 first-frame tokens when R == 2):
+        mod_tab [R][L][6D] = block modulation + time_projection(t) (DIT:217-218), head_tab [R][2D] (DIT:263)."""
+        dev, d = self.device, self.cfg.dim
+        ts = ws["ts"]
+        ts.zero_()
+        ts[R - 1:R].copy_(timestep.reshape(-1)[:1].to(device=dev, dtype=torch.float32))
+        emb, t0, t0s, t, tss, tmod = (ws[k][:R] for k in ("emb", "t0", "t0s", "t", "ts_silu", "tmod"))
+        ops.sinusoidal_embedding(ts[:R], emb)
+        ops.gemm(emb, self.w_time0, self.b_time0, t0)
+        ops.silu(t0, t0s)
+        ops.gemm(t0s, self.w_time2, self.b_time2, t)
+        ops.silu(t, tss)
+        ops.gemm(tss, self.w_tproj, self.b_tproj, tmod)
+        mod_tab, head_tab = ws["mod_tab"], ws["head_tab"]
+        for r in range(R):
+            ops.add_bcast(self.mods_all, tmod[r], mod_tab[r])                 # modulation + t_mod   (DIT:217-218)
+            ops.add_bcast(self.head_mod, t[r], head_tab[r:r + 1], period=d)   # head.modulation + t  (DIT:263)
+        self._launched(6 + 2 * R)
+        return mod_tab, head_tab
+
+    def text_embedding(self, context: torch.Tensor) -> torch.Tensor:
+        """text_embedding MLP on [n, text_dim] -> [n, dim] (DIT:307-311, PIPE:1236)."""
+        cfg, dev = self.cfg, self.device
+        c = context.reshape(-1, cfg.text_dim).to(device=dev, dtype=BF16).contiguous()
+        hid = torch.empty(c.shape[0], cfg.dim, dtype=BF16, device=dev)
+        emb = torch.empty(c.shape[0], cfg.dim, dtype=BF16, device=dev)
+        ops.gemm(c, self.w_text0, self.b_text0, hid, EPI_BIAS_GELU_TANH)
+        ops.gemm(hid, self.w_text2, self.b_text2, emb, EPI_BIAS)
+        self._launched(2)
+        return emb
+
     def _context_kv(self, context: torch.Tensor):
         """text_embedding + per-block cross-attention K (RMS-normed) | V; cached per context tensor."""
         key = (context.data_ptr(), tuple(context.shape), context._version, context.dtype)
@@ -140,17 +172,13 @@ class WanDiTEngine:
             return hit
         cfg, dev = self.cfg, self.device
         d = cfg.dim
-        c = context.reshape(-1, cfg.text_dim).to(device=dev, dtype=BF16).contiguous()
-        n = c.shape[0]
-        hid = torch.empty(n, d, dtype=BF16, device=dev)
-        emb = torch.empty(n, d, dtype=BF16, device=dev)
-        ops.gemm(c, self.w_text0, self.b_text0, hid, EPI_BIAS_GELU_TANH)
-        ops.gemm(hid, self.w_text2, self.b_text2, emb, EPI_BIAS)
+        emb = self.text_embedding(context)
+        n = emb.shape[0]
         kv = torch.empty(cfg.num_layers, n, 2 * d, dtype=BF16, device=dev)
         for i, b in enumerate(self.blocks):
             ops.gemm(emb, b.cwkv, b.cbkv, kv[i], EPI_BIAS)
             ops.rmsnorm_rope(kv[i][:, :d], cfg.eps, b.cnk)
-        self._launched(2 + 2 * cfg.num_layers)
+        self._launched(2 * cfg.num_layers)
         val = (kv, n, context)  # keep `context` alive so its data_ptr cannot be recycled under the key
         self._ctx_cache[key] = val
         self._ctx_cache_order.append(key)
@@ -187,21 +215,7 @@ class WanDiTEngine:
         # ---- time embedding on the distinct timestep rows only (PIPE:1218-1231, DIT:67-71, 312-318)
         per_token = bool(cfg.seperated_timestep and fuse_vae_embedding_in_latents)
         R = 2 if per_token else 1
-        ts = ws["ts"]
-        ts.zero_()
-        ts[R - 1:R].copy_(timestep.reshape(-1)[:1].to(device=dev, dtype=torch.float32))
-        emb, t0, t0s, t, tss, tmod = (ws[k][:R] for k in ("emb", "t0", "t0s", "t", "ts_silu", "tmod"))
-        ops.sinusoidal_embedding(ts[:R], emb)
-        ops.gemm(emb, self.w_time0, self.b_time0, t0)
-        ops.silu(t0, t0s)
-        ops.gemm(t0s, self.w_time2, self.b_time2, t)
-        ops.silu(t, tss)
-        ops.gemm(tss, self.w_tproj, self.b_tproj, tmod)
-        mod_tab, head_tab = ws["mod_tab"], ws["head_tab"]
-        for r in range(R):
-            ops.add_bcast(self.mods_all, tmod[r], mod_tab[r])                 # modulation + t_mod   (DIT:217-218)
-            ops.add_bcast(self.head_mod, t[r], head_tab[r:r + 1], period=d)   # head.modulation + t  (DIT:263)
-        self._launched(6 + 2 * R)
+        mod_tab, head_tab = self._time_tables(ws, timestep, R)
         r_main = R - 1                                   # row used by tokens after the first frame
         n_first = max(0, min(rows, h * w - tok0)) if per_token else 0   # tokens of this rank at t = 0
 

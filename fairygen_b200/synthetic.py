@@ -87,6 +87,18 @@ def random_state_dict(cfg: WanDiTConfig, seed: int = 0, device="cuda", dtype=tor
     return out
 
 
+def random_lora(cfg: WanDiTConfig, rank: int = 32, seed: int = 2, device="cuda", dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """Unmerged synthetic motion LoRA (stage-1 A1, B1) in the on-disk key format the reference loads
+    (``<module>.lora_{A,B}.default.weight``, utils/lora/general.py:10-41) — the same tensors random_state_dict merges."""
+    shapes = param_shapes(cfg)
+    out: Dict[str, torch.Tensor] = {}
+    for t in lora_targets(cfg):
+        n, k = shapes[t + ".weight"]
+        out[f"{t}.lora_A.default.weight"] = (torch.randn((rank, k), generator=_gen(t + ".A", seed, device), device=device) / math.sqrt(k)).to(dtype)
+        out[f"{t}.lora_B.default.weight"] = (torch.randn((n, rank), generator=_gen(t + ".B", seed, device), device=device) * 0.02).to(dtype)
+    return out
+
+
 def latent_shape(cfg: WanDiTConfig, height: int, width: int, num_frames: int):
     """(1, C, (frames-1)/4+1, H/16, W/16) — Wan2.2 VAE38 compression (wan_video_vae.py:1354-1382)."""
     return (1, cfg.in_dim, (num_frames - 1) // 4 + 1, height // 16, width // 16)

@@ -1,0 +1,406 @@
+"""Stage-2 motion-LoRA fine-tune step of the DiT (BASELINE config 5) on the sm_100a kernels.
+
+What the reference does (animation/diffsynth): ``DiffusionTrainingModule`` injects rank-32 LoRA adapters into the
+300 Linears "q,k,v,o,ffn.0,ffn.2", loads the stage-1 (A1, B1), adds a zero-initialised trainable ``lora_B2`` per
+Linear and monkey-patches the stage-2 forward (diffusion/training_module.py:266-352, TMOD); ``FlowMatchSFTLoss``
+(diffusion/loss.py:5-21, LOSS) noises the latents, calls ``pipe.model_fn`` under autograd and back-propagates the
+weighted MSE; each DiTBlock is re-computed in backward (pipelines/wan_video.py:1348-1360).
+
+Here, per step:
+  * ``fgb_lora_merge`` folds the step's LoRA (B1 + B2*mask*2)A1 into one effective bf16 weight per Linear, so the
+    forward GEMMs and the dgrad GEMMs are the SAME tcgen05 kernels as inference (``fgb_gemm_bf16`` /
+    ``fgb_gemm_dgrad``) — the adapters cost a rank-32 side GEMM ``t = A1 x`` that the B2 gradient needs anyway;
+  * the forward keeps every block's activations (23 GB at 480x832x49; B200 has 180 GB), so nothing is re-computed
+    unless ``recompute=True`` asks for the reference's checkpointing schedule;
+  * the backward is hand-written: ``fgb_attn_bwd`` (tensor cores), ``fgb_gemm_dgrad``, fused LN / RMSNorm+RoPE /
+    GELU / gate backward kernels, and ``fgb_lora_wgrad`` for dB2 = (dyᵀ A1x) * mask * 2 in fp32.
+Only ``lora_B2`` receives gradients (TMOD:279-307); base weights, A1, B1, norms and modulations are frozen.
+
+``Stage2Trainer.model_fn`` wraps forward/backward in a ``torch.autograd.Function`` so the reference's own
+``FlowMatchSFTLoss`` / ``loss.backward()`` drive it unchanged; ``Stage2Trainer.step`` runs the whole step (noise,
+forward, loss, backward) without autograd.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+
+from . import ops
+from .engine import WanDiTEngine
+from .ops import BF16, EPI_BIAS, EPI_GATED_RESIDUAL, EPI_RESIDUAL
+from .scheduler import FlowMatchScheduler
+
+
+def lora_targets(num_layers: int) -> Iterable[str]:
+    """Module names adapted by --lora_target_modules "q,k,v,o,ffn.0,ffn.2" (peft suffix match, TMOD:35-42)."""
+    for i in range(num_layers):
+        for a in ("self_attn", "cross_attn"):
+            for p in "qkvo":
+                yield f"blocks.{i}.{a}.{p}"
+        yield f"blocks.{i}.ffn.0"
+        yield f"blocks.{i}.ffn.2"
+
+
+class _Saved:
+    """Activations of one block kept for its backward."""
+    __slots__ = ("x_in", "a1", "qk_pre", "qkv", "o", "lse", "x1", "a2", "cq_pre", "cq", "ck_pre", "ckv", "co", "lse_c", "x2", "a3",
+                 "z1", "h", "t_qkv", "t_o", "t_cq", "t_ckv", "t_co", "t_1", "t_2")
+
+
+class Stage2Trainer:
+    def __init__(self, engine: WanDiTEngine, lora: Dict[str, torch.Tensor], rank: int = 32, lora_alpha: Optional[float] = None,
+                 dropout_prob: float = 0.5, recompute: bool = False, dp_group=None):
+        if not engine.loaded:
+            raise RuntimeError("Stage2Trainer needs an engine with loaded (frozen) base weights")
+        if engine.sp is not None:
+            raise NotImplementedError("training runs data-parallel (one video per GPU); sequence-parallel backward is not built")
+        self.engine = engine
+        self.cfg = engine.cfg
+        self.rank = rank
+        self.scaling = float((lora_alpha if lora_alpha is not None else rank) / rank)   # peft: alpha / r (TMOD:33-34)
+        self.dropout_prob = float(dropout_prob)
+        self.mask_mul = 1.0 / (1.0 - self.dropout_prob)                                 # TMOD:343
+        self.recompute = recompute
+        self.dp_group = dp_group
+        dev, cfg = engine.device, engine.cfg
+        d, f = cfg.dim, cfg.ffn_dim
+        self.targets: List[str] = list(lora_targets(cfg.num_layers))
+        out_dim = lambda t: f if t.endswith("ffn.0") else d  # noqa: E731
+        # ---- frozen stage-1 adapters, packed per fused GEMM ------------------------------------------------------
+        g = lambda k: lora[k].detach().to(device=dev, dtype=BF16).contiguous()  # noqa: E731
+        self.a1: Dict[str, torch.Tensor] = {}
+        self.b1: Dict[str, torch.Tensor] = {}
+        for t in self.targets:
+            self.a1[t] = g(f"{t}.lora_A.default.weight")
+            self.b1[t] = g(f"{t}.lora_B.default.weight")
+            if self.a1[t].shape[0] != rank:
+                raise ValueError(f"{t}: LoRA rank {self.a1[t].shape[0]} != {rank}")
+        self.a1_qkv = [torch.cat([self.a1[f"blocks.{i}.self_attn.{p}"] for p in "qkv"], 0).contiguous() for i in range(cfg.num_layers)]
+        self.a1_ckv = [torch.cat([self.a1[f"blocks.{i}.cross_attn.{p}"] for p in "kv"], 0).contiguous() for i in range(cfg.num_layers)]
+        # ---- trainable B2: one flat bf16 parameter buffer, fp32 gradient / Adam moments ---------------------------
+        sizes = [out_dim(t) * rank for t in self.targets]
+        total = sum(sizes)
+        self.b2_flat = torch.zeros(total, dtype=BF16, device=dev)                       # zero init (TMOD:296-298)
+        self.grad_flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.adam_m = self.adam_v = None
+        self.adam_step = 0
+        self.b2: Dict[str, torch.Tensor] = {}
+        self.grad: Dict[str, torch.Tensor] = {}
+        self.mask: Dict[str, torch.Tensor] = {}
+        self._mask_flat = torch.ones(total, dtype=torch.uint8, device=dev)
+        off = 0
+        for t, n in zip(self.targets, sizes):
+            self.b2[t] = self.b2_flat[off:off + n].view(-1, rank)
+            self.grad[t] = self.grad_flat[off:off + n].view(-1, rank)
+            self.mask[t] = self._mask_flat[off:off + n].view(-1, rank)
+            off += n
+        # ---- per-step effective weights (same layouts as the engine's packed base weights) ------------------------
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
+        self.eff = [dict(wqkv=e(3 * d, d), wo=e(d, d), cwq=e(d, d), cwkv=e(2 * d, d), cwo=e(d, d), w1=e(f, d), w2=e(d, f))
+                    for _ in range(cfg.num_layers)]
+        self.scheduler = FlowMatchScheduler("Wan")
+        self.scheduler.set_timesteps(1000, training=True)                               # train.py / LOSS:6-9
+        self._saved: List[Optional[_Saved]] = []
+        self._shape_key = None
+        self._fwd_state = None
+        self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.kernel_launches = 0
+        self._mask_calls = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    # parameters
+    # ------------------------------------------------------------------------------------------------------------
+    def load_b2(self, b2: Dict[str, torch.Tensor]) -> None:
+        for t in self.targets:
+            self.b2[t].copy_(b2[t].to(device=self.engine.device, dtype=BF16))
+
+    def set_masks(self, masks: Optional[Dict[str, torch.Tensor]] = None, seed: Optional[int] = None) -> None:
+        """Weight-dropout keep-masks of this step: injected (parity tests) or drawn on the device from `seed`."""
+        if masks is not None:
+            for t in self.targets:
+                self.mask[t].copy_(masks[t].to(device=self.engine.device, dtype=torch.uint8))
+        else:
+            if seed is None:   # a fresh mask per call, as torch.rand_like gives the reference (TMOD:338-342)
+                self._mask_calls += 1
+                seed = 0x5EED + 7919 * self._mask_calls
+            ops.bernoulli_mask(self._mask_flat, self.dropout_prob, seed)
+            self.kernel_launches += 1
+
+    def zero_grad(self) -> None:
+        self.grad_flat.zero_()
+
+    def merge(self) -> None:
+        """W_eff = W + s (B1 + B2*mask*2) A1 for all 300 Linears (row slices of the fused QKV / cross-KV weights)."""
+        d = self.cfg.dim
+        for i, (b, eff) in enumerate(zip(self.engine.blocks, self.eff)):
+            p = f"blocks.{i}."
+            for j, proj in enumerate("qkv"):
+                self._merge_one(b.wqkv[j * d:(j + 1) * d], eff["wqkv"][j * d:(j + 1) * d], p + "self_attn." + proj)
+            self._merge_one(b.wo, eff["wo"], p + "self_attn.o")
+            self._merge_one(b.cwq, eff["cwq"], p + "cross_attn.q")
+            for j, proj in enumerate("kv"):
+                self._merge_one(b.cwkv[j * d:(j + 1) * d], eff["cwkv"][j * d:(j + 1) * d], p + "cross_attn." + proj)
+            self._merge_one(b.cwo, eff["cwo"], p + "cross_attn.o")
+            self._merge_one(b.w1, eff["w1"], p + "ffn.0")
+            self._merge_one(b.w2, eff["w2"], p + "ffn.2")
+
+    def _merge_one(self, w, w_eff, name) -> None:
+        ops.lora_merge(w, self.a1[name], self.b1[name], self.b2[name], self.mask[name], w_eff, self.mask_mul, self.scaling)
+        self.kernel_launches += 1
+
+    # ------------------------------------------------------------------------------------------------------------
+    # buffers
+    # ------------------------------------------------------------------------------------------------------------
+    def _alloc_saved(self, rows: int, n_ctx: int) -> _Saved:
+        cfg, dev = self.cfg, self.engine.device
+        d, f, r, H = cfg.dim, cfg.ffn_dim, self.rank, cfg.num_heads
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
+        s = _Saved()
+        s.x_in, s.a1, s.o, s.x1, s.a2, s.cq_pre, s.cq, s.co, s.x2, s.a3 = (e(rows, d) for _ in range(10))
+        s.qk_pre, s.qkv = e(rows, 2 * d), e(rows, 3 * d)
+        s.ck_pre, s.ckv = e(n_ctx, d), e(n_ctx, 2 * d)
+        s.z1, s.h = e(rows, f), e(rows, f)
+        s.t_qkv, s.t_o, s.t_cq, s.t_ckv, s.t_co, s.t_1, s.t_2 = e(rows, 3 * r), e(rows, r), e(rows, r), e(n_ctx, 2 * r), e(rows, r), e(rows, r), e(rows, r)
+        ld = ops.stat_rows(rows)
+        s.lse = torch.zeros(H, ld, dtype=torch.float32, device=dev)
+        s.lse_c = torch.zeros(H, ld, dtype=torch.float32, device=dev)
+        return s
+
+    def _buffers(self, rows: int, n_ctx: int):
+        key = (rows, n_ctx)
+        if self._shape_key != key:
+            cfg, dev = self.cfg, self.engine.device
+            d, f, H = cfg.dim, cfg.ffn_dim, cfg.num_heads
+            e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
+            n_sets = 1 if self.recompute else cfg.num_layers
+            self._saved = [self._alloc_saved(rows, n_ctx) for _ in range(n_sets)]
+            self._x_ckpt = [e(rows, d) for _ in range(cfg.num_layers)] if self.recompute else None
+            self._scratch = dict(dx=e(rows, d), t1=e(rows, d), t2=e(rows, d), dqkv=e(rows, 3 * d), dh=e(rows, f), dckv=e(n_ctx, 2 * d),
+                                 delta=torch.empty(H, ops.stat_rows(rows), dtype=torch.float32, device=dev), x=e(rows, d),
+                                 x_final=e(rows, d), a_head=e(rows, d), d_hrow=e(rows, cfg.out_dim * 4))
+            self._shape_key = key
+        return self._scratch
+
+    def _saved_for(self, i: int) -> _Saved:
+        return self._saved[0 if self.recompute else i]
+
+    # ------------------------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------------------------
+    def _block_forward(self, i: int, x: torch.Tensor, s: _Saved, st) -> None:
+        """DiTBlock.forward (DIT:213-229) with the stage-2 LoRA folded into `eff`; x is updated in place."""
+        eng, cfg = self.engine, self.cfg
+        d, H = cfg.dim, cfg.num_heads
+        b, w = eng.blocks[i], self.eff[i]
+        m0, m1, n_first, grid, ctx_emb = st["m0"][i], st["m1"][i], st["n_first"], st["grid"], st["ctx_emb"]
+        s.x_in.copy_(x)
+        ops.ln_modulate(x, s.a1, cfg.eps, m0[0], m0[1], m1[0], m1[1], n_first)
+        ops.gemm(s.a1, w["wqkv"], b.bqkv, s.qkv)
+        ops.gemm(s.a1, self.a1_qkv[i], None, s.t_qkv)
+        s.qk_pre.copy_(s.qkv[:, :2 * d])
+        ops.rmsnorm_rope(s.qkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, 0)
+        ops.rmsnorm_rope(s.qkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, 0)
+        ops.attention(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, H, lse=s.lse)
+        ops.gemm(s.o, self.a1[f"blocks.{i}.self_attn.o"], None, s.t_o)
+        ops.gemm(s.o, w["wo"], b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first)
+        s.x1.copy_(x)
+        ops.ln_affine(x, s.a2, cfg.eps, b.n3w, b.n3b)
+        ops.gemm(s.a2, w["cwq"], b.cbq, s.cq)
+        ops.gemm(s.a2, self.a1[f"blocks.{i}.cross_attn.q"], None, s.t_cq)
+        s.cq_pre.copy_(s.cq)
+        ops.rmsnorm_rope(s.cq, cfg.eps, b.cnq)
+        ops.gemm(ctx_emb, w["cwkv"], b.cbkv, s.ckv)
+        ops.gemm(ctx_emb, self.a1_ckv[i], None, s.t_ckv)
+        s.ck_pre.copy_(s.ckv[:, :d])
+        ops.rmsnorm_rope(s.ckv[:, :d], cfg.eps, b.cnk)
+        ops.attention(s.cq, s.ckv[:, :d], s.ckv[:, d:], s.co, H, lse=s.lse_c)
+        ops.gemm(s.co, self.a1[f"blocks.{i}.cross_attn.o"], None, s.t_co)
+        ops.gemm(s.co, w["cwo"], b.cbo, x, EPI_RESIDUAL)
+        s.x2.copy_(x)
+        ops.ln_modulate(x, s.a3, cfg.eps, m0[3], m0[4], m1[3], m1[4], n_first)
+        ops.gemm(s.a3, w["w1"], b.b1, s.z1, EPI_BIAS)
+        ops.gemm(s.a3, self.a1[f"blocks.{i}.ffn.0"], None, s.t_1)
+        ops.gelu_tanh(s.z1, s.h)
+        ops.gemm(s.h, self.a1[f"blocks.{i}.ffn.2"], None, s.t_2)
+        ops.gemm(s.h, w["w2"], b.b2, x, EPI_GATED_RESIDUAL, m0[5], m1[5], n_first)
+        self.kernel_launches += 25
+
+    def forward_train(self, latents: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor,
+                      fuse_vae_embedding_in_latents: bool = True) -> torch.Tensor:
+        """model_fn_wan_video (PIPE:1217-1388) with saved activations; call set_masks() + merge() first."""
+        eng, cfg = self.engine, self.cfg
+        dev, d = eng.device, cfg.dim
+        if latents.dim() != 5 or latents.shape[0] != 1 or latents.shape[1] != cfg.in_dim:
+            raise ValueError(f"latents must be (1,{cfg.in_dim},F,H,W), got {tuple(latents.shape)}")
+        f, h, w = latents.shape[2], latents.shape[3] // 2, latents.shape[4] // 2
+        grid, S = (f, h, w), f * h * w
+        ws = eng._workspace(S, S)
+        per_token = bool(cfg.seperated_timestep and fuse_vae_embedding_in_latents)
+        R = 2 if per_token else 1
+        mod_tab, head_tab = eng._time_tables(ws, timestep, R)
+        r_main = R - 1
+        n_first = min(S, h * w) if per_token else 0
+        ctx_emb = eng.text_embedding(context)
+        sc = self._buffers(S, ctx_emb.shape[0])
+        L = cfg.num_layers
+        st = dict(grid=grid, S=S, n_first=n_first, ctx_emb=ctx_emb,
+                  m0=[mod_tab[0, i].view(6, d) for i in range(L)], m1=[mod_tab[r_main, i].view(6, d) for i in range(L)],
+                  h0=head_tab[0].view(2, d), h1=head_tab[r_main].view(2, d), lat_dtype=latents.dtype)
+        x = sc["x"]
+        lat = latents[0].to(device=dev, dtype=BF16).contiguous()
+        ops.patchify_rows(lat, ws["prow"], grid, 0)
+        ops.gemm(ws["prow"], eng.w_patch, eng.b_patch, x)
+        for i in range(L):
+            if self.recompute:
+                self._x_ckpt[i].copy_(x)
+            self._block_forward(i, x, self._saved_for(i), st)
+        sc["x_final"].copy_(x)
+        ops.ln_modulate(x, sc["a_head"], cfg.eps, st["h0"][0], st["h0"][1], st["h1"][0], st["h1"][1], n_first)
+        ops.gemm(sc["a_head"], eng.w_head, eng.b_head, ws["hrow"])
+        out = torch.empty(cfg.out_dim, f, 2 * h, 2 * w, dtype=BF16, device=dev)
+        ops.unpatchify(ws["hrow"], out, grid)
+        self.kernel_launches += 5
+        self._fwd_state = st
+        return out.unsqueeze(0)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------------------------
+    def _wgrad(self, dy, t, name) -> None:
+        ops.lora_wgrad(dy, t, self.grad[name], self.mask[name], self.mask_mul * self.scaling)
+        self.kernel_launches += 1
+
+    def _block_backward(self, i: int, s: _Saved, st) -> None:
+        """dx (grad w.r.t. the block output) -> dx (grad w.r.t. the block input), accumulating dB2 of its 10 Linears."""
+        eng, cfg, sc = self.engine, self.cfg, self._scratch
+        d, H, r = cfg.dim, cfg.num_heads, self.rank
+        b, w = eng.blocks[i], self.eff[i]
+        m0, m1, n_first, grid = st["m0"][i], st["m1"][i], st["n_first"], st["grid"]
+        dx, t1, t2, dqkv, dh, dckv, delta = sc["dx"], sc["t1"], sc["t2"], sc["dqkv"], sc["dh"], sc["dckv"], sc["delta"]
+        p = f"blocks.{i}."
+        # ---- feed-forward branch: x3 = x2 + gate_mlp * ffn2(gelu(ffn0(a3)))                       (DIT:227-228)
+        ops.mul_gate(dx, t1, m0[5], m1[5], n_first)
+        self._wgrad(t1, s.t_2, p + "ffn.2")
+        ops.gemm_dgrad(t1, w["w2"], dh)
+        ops.gelu_tanh_bwd(s.z1, dh, dh)
+        self._wgrad(dh, s.t_1, p + "ffn.0")
+        ops.gemm_dgrad(dh, w["w1"], t1)
+        ops.ln_bwd(s.x2, t1, dx, cfg.eps, m0[4], m1[4], n_first, affine=False, dres=dx)
+        # ---- cross-attention branch: x2 = x1 + o(attn(norm_q(q(a2)), norm_k(k(ctx)), v(ctx)))      (DIT:226)
+        self._wgrad(dx, s.t_co, p + "cross_attn.o")
+        ops.gemm_dgrad(dx, w["cwo"], t1)
+        ops.attention_bwd(s.cq, s.ckv[:, :d], s.ckv[:, d:], s.co, t1, s.lse_c, t2, dckv[:, :d], dckv[:, d:], H, delta=delta)
+        ops.rmsnorm_rope_bwd(s.cq_pre, t2, cfg.eps, b.cnq)
+        ops.rmsnorm_rope_bwd(s.ck_pre, dckv[:, :d], cfg.eps, b.cnk)
+        self._wgrad(t2, s.t_cq, p + "cross_attn.q")
+        self._wgrad(dckv[:, :d], s.t_ckv[:, :r], p + "cross_attn.k")
+        self._wgrad(dckv[:, d:], s.t_ckv[:, r:], p + "cross_attn.v")
+        ops.gemm_dgrad(t2, w["cwq"], t1)
+        ops.ln_bwd(s.x1, t1, dx, cfg.eps, b.n3w, None, 0, affine=True, dres=dx)
+        # ---- self-attention branch: x1 = x0 + gate_msa * o(attn(rope(norm_q(q(a1))), ...))        (DIT:224-225)
+        ops.mul_gate(dx, t1, m0[2], m1[2], n_first)
+        self._wgrad(t1, s.t_o, p + "self_attn.o")
+        ops.gemm_dgrad(t1, w["wo"], t2)
+        ops.attention_bwd(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, t2, s.lse, dqkv[:, :d], dqkv[:, d:2 * d],
+                          dqkv[:, 2 * d:], H, delta=delta)
+        ops.rmsnorm_rope_bwd(s.qk_pre[:, :d], dqkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, 0)
+        ops.rmsnorm_rope_bwd(s.qk_pre[:, d:], dqkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, 0)
+        for j, proj in enumerate("qkv"):
+            self._wgrad(dqkv[:, j * d:(j + 1) * d], s.t_qkv[:, j * r:(j + 1) * r], p + "self_attn." + proj)
+        ops.gemm_dgrad(dqkv, w["wqkv"], t1)
+        ops.ln_bwd(s.x_in, t1, dx, cfg.eps, m0[1], m1[1], n_first, affine=False, dres=dx)
+        self.kernel_launches += 20
+
+    def backward_train(self, dpred: torch.Tensor) -> None:
+        """Back-propagate dL/dprediction (1,C,F,H,W) through head and blocks; adds into ``self.grad`` (fp32)."""
+        st = self._fwd_state
+        if st is None:
+            raise RuntimeError("backward_train called before forward_train")
+        eng, cfg, sc = self.engine, self.cfg, self._scratch
+        grid, n_first = st["grid"], st["n_first"]
+        dp = dpred.reshape(cfg.out_dim, grid[0], 2 * grid[1], 2 * grid[2]).to(dtype=BF16).contiguous()
+        ops.unpatchify_bwd(dp, sc["d_hrow"], grid)
+        ops.gemm_dgrad(sc["d_hrow"], eng.w_head, sc["t1"])
+        ops.ln_bwd(sc["x_final"], sc["t1"], sc["dx"], cfg.eps, st["h0"][1], st["h1"][1], n_first, affine=False, dres=None)
+        self.kernel_launches += 3
+        for i in reversed(range(cfg.num_layers)):
+            s = self._saved_for(i)
+            if self.recompute:   # the reference's per-block checkpointing (PIPE:1348-1360): rebuild the activations
+                sc["x"].copy_(self._x_ckpt[i])
+                self._block_forward(i, sc["x"], s, st)
+            self._block_backward(i, s, st)
+        self._fwd_state = None
+        if self.dp_group is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.grad_flat, group=self.dp_group)
+            self.grad_flat.div_(dist.get_world_size(self.dp_group))   # DDP averages (accelerate, train.py)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # whole step without autograd (LOSS:5-21)
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, input_latents: torch.Tensor, noise: torch.Tensor, timestep_id: int, context: torch.Tensor,
+             masks: Optional[Dict[str, torch.Tensor]] = None, seed: Optional[int] = None,
+             fuse_vae_embedding_in_latents: bool = True, return_pred: bool = False):
+        """One forward + backward of FlowMatchSFTLoss with the random draws (timestep id, noise, masks) given."""
+        dev = self.engine.device
+        x0 = input_latents.to(device=dev, dtype=BF16).contiguous()
+        nz = noise.to(device=dev, dtype=BF16).contiguous()
+        sched = self.scheduler
+        # LOSS:9 casts the sampled timestep to the pipeline dtype (bf16); add_noise / training_weight then look the
+        # schedule index up again by argmin (FM:164-179), which can land on a neighbouring entry — reproduced as is
+        t_bf16 = sched.timesteps[timestep_id:timestep_id + 1].to(BF16)
+        timestep = t_bf16.to(torch.float32)
+        index = sched._index(t_bf16)
+        sigma = float(sched.sigmas[index])
+        weight = float(sched.linear_timesteps_weights[index])
+        latents, target = torch.empty_like(x0), torch.empty_like(x0)
+        ops.fm_noise_target(x0, nz, sigma, latents, target)
+        self.set_masks(masks, seed)
+        self.merge()
+        pred = self.forward_train(latents, timestep, context, fuse_vae_embedding_in_latents)
+        dpred = torch.empty_like(pred)
+        ops.mse_loss_grad(pred, target, weight, self.loss_buf, dpred)
+        self.kernel_launches += 2
+        self.backward_train(dpred)
+        return (self.loss_buf, pred) if return_pred else self.loss_buf
+
+    def optimizer_step(self, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2) -> None:
+        if self.adam_m is None:
+            self.adam_m, self.adam_v = torch.zeros_like(self.grad_flat), torch.zeros_like(self.grad_flat)
+        self.adam_step += 1
+        ops.adamw_step(self.b2_flat, self.grad_flat, self.adam_m, self.adam_v, lr, betas[0], betas[1], eps, weight_decay, self.adam_step)
+        self.kernel_launches += 1
+
+    # ------------------------------------------------------------------------------------------------------------
+    # autograd bridge: pipe.model_fn under torch.enable_grad (LOSS:17)
+    # ------------------------------------------------------------------------------------------------------------
+    def model_fn(self, b2_params: List[torch.nn.Parameter], latents, timestep, context, fuse_vae_embedding_in_latents=True,
+                 masks=None, seed=None):
+        """Prediction with a grad_fn: ``loss.backward()`` fills ``p.grad`` of the given B2 parameters (ordered as
+        ``self.targets``), so the reference's FlowMatchSFTLoss + optimizer loop runs unchanged."""
+        return _Stage2Function.apply(self, latents, timestep, context, fuse_vae_embedding_in_latents, masks, seed, *b2_params)
+
+
+class _Stage2Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, trainer: Stage2Trainer, latents, timestep, context, fuse, masks, seed, *b2_params):
+        for t, p in zip(trainer.targets, b2_params):
+            trainer.b2[t].copy_(p.detach().to(BF16))
+        trainer.set_masks(masks, seed)
+        trainer.merge()
+        ctx.trainer = trainer
+        ctx.n = len(b2_params)
+        ctx.dtypes = [p.dtype for p in b2_params]
+        return trainer.forward_train(latents, timestep.to(torch.float32), context, fuse).to(latents.dtype)
+
+    @staticmethod
+    def backward(ctx, dpred):
+        tr = ctx.trainer
+        tr.zero_grad()
+        with torch.no_grad():
+            tr.backward_train(dpred)
+        grads = tuple(tr.grad[t].to(dt) for t, dt in zip(tr.targets, ctx.dtypes))
+        return (None, None, None, None, None, None, None) + grads

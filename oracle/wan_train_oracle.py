@@ -95,26 +95,31 @@ def training_schedule(num_steps: int = 1000, shift: float = 5.0):
 
 def sft_loss(w: Weights, cfg: o.DiTConfig, lora: Weights, b2: Weights, masks, x0: torch.Tensor, noise: torch.Tensor,
              timestep_id: int, context: torch.Tensor, fuse_vae_embedding_in_latents: bool = True,
-             schedule=None, return_pred: bool = False):
+             schedule=None, return_pred: bool = False, timestep_dtype=None):
     """LOSS:5-21 with the random draws (timestep id, noise) injected.  x0/noise (1,C,F,H,W) in the compute dtype."""
     sigmas, timesteps, weights = schedule if schedule is not None else training_schedule()
     dtype = x0.dtype
-    timestep = timesteps[timestep_id:timestep_id + 1].to(dtype)                             # LOSS:9
-    sigma = sigmas[timestep_id]
+    # LOSS:9 casts the timestep to the PIPELINE dtype (bf16 in training) BEFORE add_noise / training_weight look
+    # their index up again by argmin (FM:164-179) — so with bf16 the sigma and the loss weight can belong to a
+    # neighbouring schedule entry.  timestep_dtype reproduces that when the oracle itself computes in fp32.
+    t_cast = timesteps[timestep_id:timestep_id + 1].to(timestep_dtype or dtype)
+    timestep = t_cast.to(dtype).to(x0.device)
+    index = int(torch.argmin((timesteps - t_cast.cpu()).abs()))
+    sigma = float(sigmas[index])
     latents = (1 - sigma) * x0 + sigma * noise                                              # add_noise, FM:164-170
     target = noise - x0                                                                     # training_target, FM:172-175
     ww = dict(w)
     ww["__linear__"] = stage2_linear_fn(lora, b2, masks)
     pred = o.dit_forward(ww, cfg, latents.to(dtype), timestep, context, fuse_vae_embedding_in_latents)  # LOSS:17
-    loss = F.mse_loss(pred.float(), target.float()) * weights[timestep_id]                   # LOSS:19-20
+    loss = F.mse_loss(pred.float(), target.float()) * float(weights[index])                   # LOSS:19-20
     return (loss, pred) if return_pred else loss
 
 
 def loss_and_grads(w: Weights, cfg: o.DiTConfig, lora: Weights, b2: Weights, masks, x0, noise, timestep_id, context,
-                   fuse_vae_embedding_in_latents: bool = True):
+                   fuse_vae_embedding_in_latents: bool = True, timestep_dtype=None):
     """(loss, prediction, {module: dloss/dB2}) by autograd — the quantities of one reference training step."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in b2.items()}
     loss, pred = sft_loss(w, cfg, lora, leaves, masks, x0, noise, timestep_id, context, fuse_vae_embedding_in_latents,
-                          return_pred=True)
+                          return_pred=True, timestep_dtype=timestep_dtype)
     loss.backward()
     return loss.detach(), pred.detach(), {k: v.grad.detach() for k, v in leaves.items()}
