@@ -149,10 +149,10 @@ def run_ours(args):
         # one video: CFG pair (positive / negative prompt on disjoint halves of the box) x Ulysses inside each half,
         # or pure Ulysses over all ranks with --layout sp
         layout = Layout(world, 1, 1, world) if args.layout == "sp" else Layout.auto(world, 1, True, fg.TI2V_5B.num_heads)
-        par = ParallelContext(layout)
+        par = ParallelContext(layout, exchange=args.exchange)
         sp = par.sequence_parallel()
         sp_ways = layout.sp
-        layout_name = f"cfg{layout.cfg}_x_ulysses_sp{layout.sp}"
+        layout_name = f"cfg{layout.cfg}_x_ulysses_sp{layout.sp}_{args.exchange}"
 
     cfg = fg.TI2V_5B
     shape = synthetic.latent_shape(cfg, HEIGHT, WIDTH, FRAMES)
@@ -278,6 +278,9 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--layout", choices=["auto", "sp"], default="auto",
                     help="N>1: auto = CFG pair x Ulysses SP (N/2 ways); sp = pure Ulysses SP over all N ranks")
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
+                    help="Ulysses exchange: p2p = NVLink peer stores from our own kernels (attention epilogue writes the owner's "
+                         "buffer); nccl = pack / all-to-all / unpack")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -78,12 +78,13 @@ class ParallelContext:
     """Creates the SP and CFG-pair process groups of a :class:`Layout` (every rank must construct it:
     ``dist.new_group`` is collective) and offers the two operations the denoise loop needs."""
 
-    def __init__(self, layout: Layout, rank: Optional[int] = None):
+    def __init__(self, layout: Layout, rank: Optional[int] = None, exchange: str = "p2p"):
         if not dist.is_initialized():
             raise RuntimeError("ParallelContext needs an initialised torch.distributed process group")
         if dist.get_world_size() != layout.world:
             raise ValueError(f"layout is for world {layout.world}, process group has {dist.get_world_size()}")
         self.layout = layout
+        self.exchange = exchange
         self.rank = dist.get_rank() if rank is None else rank
         self.shot_group, self.cfg_rank, self.sp_rank = layout.coords(self.rank)
         self.sp_group = None
@@ -116,7 +117,7 @@ class ParallelContext:
             return None
         from .sp import SequenceParallel
 
-        return SequenceParallel(self.sp_group)
+        return SequenceParallel(self.sp_group, exchange=self.exchange)
 
     # ---- CFG pair ---------------------------------------------------------------------------------
     def forward_pair(self, engine, latents, timestep, context_pos, context_neg, fuse: bool):

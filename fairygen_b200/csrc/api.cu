@@ -75,6 +75,12 @@ int fgb_create(int device, fgb_ctx** out) {
     return fgb::set_error(FGB_ERR_CUDA, "fgb_create: cuTensorMapEncodeTiled not available from the driver");
   }
   ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres);
+  if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn)
+    ctx->mem_get_address_range = reinterpret_cast<decltype(ctx->mem_get_address_range)>(fn);
+  else
+    cudaGetLastError();
   *out = ctx;
   return FGB_OK;
 }
@@ -92,5 +98,37 @@ int fgb_sync_check(fgb_ctx* ctx, void* stream) {
 }
 
 int fgb_sm_count(fgb_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+// ---- peer memory over NVLink: CUDA IPC handles for caller-owned buffers (one process per GPU) ----------------------
+int fgb_ipc_export(fgb_ctx* ctx, const void* dev_ptr, void* handle_out, int64_t* offset_out) {
+  if (!ctx || !dev_ptr || !handle_out || !offset_out) return fgb::set_error(FGB_ERR_INVALID, "fgb_ipc_export: NULL argument");
+  if (!ctx->mem_get_address_range) return fgb::set_error(FGB_ERR_UNSUPPORTED, "fgb_ipc_export: cuMemGetAddressRange unavailable");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  CUresult r = ctx->mem_get_address_range(&base, &size, reinterpret_cast<CUdeviceptr>(dev_ptr));
+  if (r != CUDA_SUCCESS) return fgb::set_error(FGB_ERR_CUDA, "fgb_ipc_export: cuMemGetAddressRange failed (%d)", (int)r);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  cudaIpcMemHandle_t h;
+  FGB_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  memcpy(handle_out, &h, sizeof(h));
+  *offset_out = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(dev_ptr) - base);
+  return FGB_OK;
+}
+
+int fgb_ipc_open(fgb_ctx* ctx, const void* handle, int64_t offset, void** peer_ptr) {
+  if (!ctx || !handle || !peer_ptr || offset < 0) return fgb::set_error(FGB_ERR_INVALID, "fgb_ipc_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* base = nullptr;
+  FGB_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *peer_ptr = static_cast<char*>(base) + offset;
+  return FGB_OK;
+}
+
+int fgb_ipc_close(fgb_ctx* ctx, void* peer_ptr, int64_t offset) {
+  if (!ctx || !peer_ptr) return fgb::set_error(FGB_ERR_INVALID, "fgb_ipc_close: bad argument");
+  FGB_CUDA(cudaIpcCloseMemHandle(static_cast<char*>(peer_ptr) - offset));
+  return FGB_OK;
+}
 
 }  // extern "C"

@@ -45,7 +45,20 @@ struct AttnParams {
   float2* part_ml;  // [split CTA][256 rows] (running max in log2 units, row sum)
   float* lse;       // optional [heads][ld_lse]: log2-domain log-sum-exp of the scaled scores (for the backward pass);
   int64_t ld_lse;   // rows in [s_q, ld_lse) get the value of an all-zero query row, so the backward needs no masks
+  // Fused Ulysses return exchange: when rows_per_peer > 0 the output row of global token t goes straight into the
+  // token-major buffer of the rank that owns t (peer memory over NVLink): o_peers[t / rows_per_peer] + (t %
+  // rows_per_peer) * ldo + (col_offset + head*128); `o` is unused.
+  __nv_bfloat16* o_peers[FGB_MAX_PEERS];
+  int32_t rows_per_peer, col_offset;
 };
+
+__device__ __forceinline__ __nv_bfloat16* out_row(const AttnParams& p, int row, int head) {
+  if (p.rows_per_peer > 0) {
+    const int peer = row / p.rows_per_peer;
+    return p.o_peers[peer] + static_cast<int64_t>(row - peer * p.rows_per_peer) * p.ldo + p.col_offset + head * 128;
+  }
+  return p.o + static_cast<int64_t>(row) * p.ldo + head * 128;
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -373,7 +386,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // final normalisation: O / l -> bf16 -> global
       const float inv_l = 1.0f / l;
       if (p.lse != nullptr && row < p.ld_lse) p.lse[static_cast<int64_t>(head) * p.ld_lse + row] = m + __log2f(l);
-      __nv_bfloat16* orow = p.o + static_cast<int64_t>(row) * p.ldo + head * 128;
+      __nv_bfloat16* orow = row < p.s_q ? out_row(p, row, head) : nullptr;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t orr[32];
@@ -434,7 +447,7 @@ attn_combine_kernel(const AttnParams p, int n_split_units) {
   uint2 out;
   out.x = pack_bf16(acc.x * inv, acc.y * inv);
   out.y = pack_bf16(acc.z * inv, acc.w * inv);
-  if (row < p.s_q) *reinterpret_cast<uint2*>(p.o + static_cast<int64_t>(row) * p.ldo + head * 128 + lane * 4) = out;
+  if (row < p.s_q) *reinterpret_cast<uint2*>(out_row(p, row, head) + lane * 4) = out;
   if (p.lse != nullptr && lane == 0 && row < p.ld_lse) p.lse[static_cast<int64_t>(head) * p.ld_lse + row] = mmax + log2f(lsum);
 }
 
@@ -488,18 +501,25 @@ extern "C" int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s
   return static_cast<int64_t>(n_split) * split * (2 * kTile) * (128 * 4 + 8);
 }
 
-extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                               int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
-                               void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* stream) {
+static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                         int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
+                         void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* const* o_peers,
+                         int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, void* stream) {
   using namespace fgb;
   FGB_CHECK_ARG(ctx, "fgb_attn_fwd: ctx is NULL");
-  FGB_CHECK_ARG(q && k && v && o, "fgb_attn_fwd: NULL tensor pointer");
+  FGB_CHECK_ARG(q && k && v && (o || o_peers), "fgb_attn_fwd: NULL tensor pointer");
   FGB_CHECK_ARG(s_q > 0 && s_kv > 0 && heads > 0, "fgb_attn_fwd: empty problem s_q=%d s_kv=%d heads=%d", s_q, s_kv, heads);
   FGB_CHECK_ARG(heads <= 65535, "fgb_attn_fwd: too many heads");
   const int64_t width = static_cast<int64_t>(heads) * FGB_HEAD_DIM;
   FGB_CHECK_ARG(ldq >= width && ldk >= width && ldv >= width && ldo >= width, "fgb_attn_fwd: leading dimension < heads*128");
-  FGB_CHECK_ARG(aligned16(o) && ldo % 8 == 0, "fgb_attn_fwd: o must be 16-byte aligned with ldo %% 8 == 0");
+  FGB_CHECK_ARG(ldo % 8 == 0 && (o_peers || aligned16(o)), "fgb_attn_fwd: o must be 16-byte aligned with ldo %% 8 == 0");
   FGB_CHECK_ARG(workspace == nullptr || aligned16(workspace), "fgb_attn_fwd: workspace must be 16-byte aligned");
+  if (o_peers) {
+    FGB_CHECK_ARG(n_peers > 0 && n_peers <= FGB_MAX_PEERS && rows_per_peer > 0 && static_cast<int64_t>(rows_per_peer) * n_peers >= s_q &&
+                      col_offset >= 0 && col_offset % 8 == 0 && ldo >= col_offset + width,
+                  "fgb_attn_fwd_scatter: peers=%d rows_per_peer=%d col_offset=%d", n_peers, rows_per_peer, col_offset);
+    for (int i = 0; i < n_peers; ++i) FGB_CHECK_ARG(o_peers[i] && aligned16(o_peers[i]), "fgb_attn_fwd_scatter: peer output %d", i);
+  }
 
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_bf16_2d(ctx, &tq, q, s_q, width, ldq, kTile);
@@ -517,6 +537,9 @@ extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const v
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = static_cast<float*>(lse);
   p.ld_lse = ld_lse;
+  p.rows_per_peer = o_peers ? rows_per_peer : 0;
+  p.col_offset = col_offset;
+  for (int i = 0; i < FGB_MAX_PEERS; ++i) p.o_peers[i] = (o_peers && i < n_peers) ? static_cast<__nv_bfloat16*>(o_peers[i]) : nullptr;
   FGB_CHECK_ARG(lse == nullptr || ld_lse >= s_q, "fgb_attn_fwd: ld_lse=%lld < s_q", (long long)ld_lse);
   p.n_pairs = (s_q + 2 * kTile - 1) / (2 * kTile);
   const int64_t units64 = static_cast<int64_t>(p.n_pairs) * heads;
@@ -560,6 +583,22 @@ extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const v
     FGB_LAUNCH_CHECK("attn_combine_kernel");
   }
   return FGB_OK;
+}
+
+extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                               int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
+                               void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* stream) {
+  return attn_fwd_impl(ctx, q, ldq, k, ldk, v, ldv, o, ldo, s_q, s_kv, heads, scale, lse, ld_lse, workspace, workspace_bytes, nullptr, 0,
+                       0, 0, stream);
+}
+
+extern "C" int fgb_attn_fwd_scatter(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                    int64_t ldv, void* const* o_peers, int32_t n_peers, int64_t ldo, int32_t rows_per_peer,
+                                    int32_t col_offset, int32_t s_q, int32_t s_kv, int32_t heads, float scale, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  if (!o_peers) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_fwd_scatter: o_peers is NULL");
+  return attn_fwd_impl(ctx, q, ldq, k, ldk, v, ldv, nullptr, ldo, s_q, s_kv, heads, scale, nullptr, 0, workspace, workspace_bytes, o_peers,
+                       n_peers, rows_per_peer, col_offset, stream);
 }
 
 extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,

@@ -287,6 +287,55 @@ __global__ void sp_heads_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, __nv
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ulysses exchange over NVLink peer memory (no NCCL on the data path)
+// ---------------------------------------------------------------------------------------------
+struct PeerPtrs {
+  void* p[FGB_MAX_PEERS];
+};
+
+// x [s_local][groups][heads][128] of THIS rank -> recv buffer of every peer, laid out [world*s_local tokens][groups]
+// [heads/world][128]: the head slice owned by peer `q` goes to rows [rank*s_local, (rank+1)*s_local) of q's buffer.
+// 16-byte stores; consecutive threads write consecutive 16 B of one 256-byte head row (full NVLink packets).
+__global__ void sp_scatter_heads_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, PeerPtrs peers, int s_local,
+                                        int heads, int groups, int world, int rank) {
+  const int hpr = heads / world;
+  const int gh = groups * heads;
+  const int64_t total = static_cast<int64_t>(s_local) * gh * 16;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(idx & 15);
+    const int g_head = static_cast<int>((idx >> 4) % gh);
+    const int64_t s = (idx >> 4) / gh;
+    const int grp = g_head / heads, head = g_head % heads;
+    const int peer = head / hpr, hh = head % hpr;
+    const uint4 v = ldg_nc_v4(reinterpret_cast<const uint4*>(x + s * ldx + static_cast<int64_t>(g_head) * 128) + vec);
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(peers.p[peer]) +
+                         ((static_cast<int64_t>(rank) * s_local + s) * groups + grp) * hpr * 128 + hh * 128;
+    reinterpret_cast<uint4*>(dst)[vec] = v;
+  }
+}
+
+// Cross-GPU barrier for the exchange: thread q publishes `epoch` in peer q's flag slot [rank] (release, system scope)
+// and then waits until peer q has published `epoch` in ours (acquire). All earlier peer stores of this stream are
+// complete (kernel boundary) and made visible by the fence. Bounded: traps after ~4 s instead of hanging the box.
+__global__ void sp_barrier_kernel(PeerPtrs flags, int world, int rank, int epoch) {
+  const int q = threadIdx.x;
+  if (q >= world) return;
+  __threadfence_system();
+  int* remote = static_cast<int*>(flags.p[q]) + rank;
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const int* mine = static_cast<const int*>(flags.p[rank]) + q;
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (v - epoch >= 0) break;
+    if (clock64() - t0 > 8000000000ll) __trap();
+  }
+  __threadfence_system();
+}
+
 static inline int grid_1d(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
 
 template <bool AFFINE>
@@ -471,4 +520,32 @@ extern "C" int fgb_sp_pack_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void*
 extern "C" int fgb_sp_unpack_heads(fgb_ctx* ctx, const void* recv, void* x, int64_t ldx, int32_t s_local, int32_t heads,
                                    int32_t groups, int32_t world, void* stream) {
   return sp_heads(ctx, false, x, ldx, const_cast<void*>(recv), s_local, heads, groups, world, stream);
+}
+
+extern "C" int fgb_sp_scatter_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* const* peer_bufs, int32_t s_local,
+                                    int32_t heads, int32_t groups, int32_t world, int32_t rank, void* stream) {
+  FGB_CHECK_ARG(ctx && x && peer_bufs, "fgb_sp_scatter_heads: NULL argument");
+  FGB_CHECK_ARG(s_local > 0 && heads > 0 && groups > 0 && world > 0 && world <= FGB_MAX_PEERS && heads % world == 0 && rank >= 0 &&
+                    rank < world, "fgb_sp_scatter_heads: heads=%d world=%d rank=%d", heads, world, rank);
+  FGB_CHECK_ARG(ldx % 8 == 0 && ldx >= static_cast<int64_t>(groups) * heads * 128 && aligned16(x), "fgb_sp_scatter_heads: alignment");
+  PeerPtrs pp;
+  for (int i = 0; i < FGB_MAX_PEERS; ++i) pp.p[i] = i < world ? peer_bufs[i] : nullptr;
+  for (int i = 0; i < world; ++i) FGB_CHECK_ARG(pp.p[i] && aligned16(pp.p[i]), "fgb_sp_scatter_heads: peer buffer %d", i);
+  const int64_t total = static_cast<int64_t>(s_local) * groups * heads * 16;
+  int grid = grid_1d(total, 256);
+  if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+  sp_scatter_heads_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x), ldx, pp, s_local, heads,
+                                                                             groups, world, rank);
+  FGB_LAUNCH_CHECK("sp_scatter_heads_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* stream) {
+  FGB_CHECK_ARG(ctx && peer_flags && world > 0 && world <= FGB_MAX_PEERS && rank >= 0 && rank < world, "fgb_sp_barrier: bad argument");
+  PeerPtrs pp;
+  for (int i = 0; i < FGB_MAX_PEERS; ++i) pp.p[i] = i < world ? peer_flags[i] : nullptr;
+  for (int i = 0; i < world; ++i) FGB_CHECK_ARG(pp.p[i], "fgb_sp_barrier: peer flag array %d is NULL", i);
+  sp_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pp, world, rank, epoch);
+  FGB_LAUNCH_CHECK("sp_barrier_kernel");
+  return FGB_OK;
 }

@@ -19,7 +19,10 @@ struct fgb_ctx {
   CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                            const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+  CUresult (*mem_get_address_range)(CUdeviceptr* base, size_t* size, CUdeviceptr ptr) = nullptr;
 };
+
+#define FGB_MAX_PEERS 8  // one NVSwitch box
 
 namespace fgb {
 

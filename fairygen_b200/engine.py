@@ -117,8 +117,13 @@ class WanDiTEngine:
             )
             if self.sp is not None:
                 hpr_w = 3 * d // self.sp.world
-                ws.update(send=e(s_pad, hpr_w), recv=e(s_pad, hpr_w), o_full=e(s_pad, d // self.sp.world),
-                          o_recv=e(s_pad, d // self.sp.world), hgather=e(s_pad, cfg.out_dim * 4))
+                ws.update(hgather=e(s_pad, cfg.out_dim * 4))
+                if getattr(self.sp, "exchange", "nccl") == "p2p":
+                    ar = self.sp.peer_arena(rows, cfg.num_heads, dev)   # peers store straight into recv / o
+                    ws.update(recv=ar.recv, o=ar.o)
+                else:
+                    ws.update(send=e(s_pad, hpr_w), recv=e(s_pad, hpr_w), o_full=e(s_pad, d // self.sp.world),
+                              o_recv=e(s_pad, d // self.sp.world))
             self._ws = {key: ws}  # keep one shape resident (a video has one shape for all 100 forwards)
         return ws
 

@@ -254,6 +254,58 @@ def sp_unpack_heads(recv, x, heads: int, groups: int, world: int):
     return x
 
 
+def _ptr_array(ptrs):
+    arr = (c_void_p * len(ptrs))(*[c_void_p(int(p)) for p in ptrs])
+    return arr
+
+
+def ipc_export(t: torch.Tensor):
+    """(64-byte CUDA IPC handle, byte offset of t inside its allocation) for a caller-owned device tensor."""
+    import ctypes
+    handle = ctypes.create_string_buffer(64)
+    off = ctypes.c_int64(0)
+    _lib.check(_lib.lib().fgb_ipc_export(_h(t).handle, _p(t), handle, ctypes.byref(off)), "fgb_ipc_export")
+    return bytes(handle.raw), int(off.value)
+
+
+def ipc_open(device, handle: bytes, offset: int) -> int:
+    import ctypes
+    out = c_void_p()
+    buf = ctypes.create_string_buffer(handle, 64)
+    _lib.check(_lib.lib().fgb_ipc_open(context(device).handle, buf, offset, ctypes.byref(out)), "fgb_ipc_open")
+    return int(out.value)
+
+
+def ipc_close(device, peer_ptr: int, offset: int) -> None:
+    _lib.check(_lib.lib().fgb_ipc_close(context(device).handle, c_void_p(peer_ptr), offset), "fgb_ipc_close")
+
+
+def sp_scatter_heads(x, peer_ptrs, heads: int, groups: int, world: int, rank: int):
+    """Store this rank's [s_local, groups*heads*128] rows into every peer's receive matrix (NVLink peer stores)."""
+    ldx = _rowmajor(x, "x")
+    c = _h(x)
+    _lib.check(_lib.lib().fgb_sp_scatter_heads(c.handle, _p(x), ldx, _ptr_array(peer_ptrs), x.shape[0], heads, groups, world, rank,
+                                               _stream()), "fgb_sp_scatter_heads")
+
+
+def sp_barrier(device, flag_ptrs, world: int, rank: int, epoch: int):
+    _lib.check(_lib.lib().fgb_sp_barrier(context(device).handle, _ptr_array(flag_ptrs), world, rank, epoch, _stream()), "fgb_sp_barrier")
+
+
+def attention_scatter(q, k, v, o_peer_ptrs, ldo: int, rows_per_peer: int, col_offset: int, heads: int, scale: Optional[float] = None):
+    """attention() whose output rows go straight into the token-major o buffers of the ranks that own the tokens."""
+    ldq, ldk, ldv = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v")
+    s_q, s_kv = q.shape[0], k.shape[0]
+    if q.shape[1] != heads * 128 or k.shape[1] != heads * 128 or v.shape != k.shape:
+        raise ValueError("attention_scatter shape mismatch")
+    scale = 1.0 / math.sqrt(128.0) if scale is None else scale
+    c = _h(q)
+    ws = attention_workspace(s_q, s_kv, heads, q.device)
+    _lib.check(_lib.lib().fgb_attn_fwd_scatter(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _ptr_array(o_peer_ptrs), len(o_peer_ptrs), ldo,
+                                               rows_per_peer, col_offset, s_q, s_kv, heads, scale, _p(ws), 0 if ws is None else ws.numel(),
+                                               _stream()), "fgb_attn_fwd_scatter")
+
+
 def rope_table(head_dim: int = 128, positions: int = 1024, theta: float = 10000.0) -> np.ndarray:
     """Host-side float32 [positions, head_dim/2, 2] (cos, sin) table for fgb_rmsnorm_rope.
 

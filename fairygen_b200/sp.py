@@ -45,13 +45,72 @@ def init_process_group_from_env(device_type: str = "cuda"):
     return dist.group.WORLD
 
 
+class PeerArena:
+    """Caller-owned exchange arena of one rank, mapped into every peer of the Ulysses group through CUDA IPC:
+
+        [ recv : s_pad x 3*(H/P)*128 bf16 | o : rows x H*128 bf16 | flags : 2 x 64 int32 ]
+
+    ``recv`` is where the peers' fgb_sp_scatter_heads stores land (it is directly the q|k|v matrix the attention
+    kernel reads), ``o`` is where the peers' attention epilogues store this rank's token rows, ``flags`` carries the
+    epochs of fgb_sp_barrier.  torch.distributed is used once, to swap the 64-byte IPC handles."""
+
+    def __init__(self, group, world: int, rank: int, rows: int, heads: int, device):
+        self.group, self.world, self.rank, self.rows, self.device = group, world, rank, rows, device
+        s_pad = rows * world
+        wloc = 3 * (heads // world) * 128
+        d = heads * 128
+        self.off_recv = 0
+        self.off_o = (s_pad * wloc * 2 + 255) // 256 * 256
+        self.off_flags = self.off_o + (rows * d * 2 + 255) // 256 * 256
+        total = self.off_flags + 2 * 64 * 4
+        self.buf = torch.zeros(total, dtype=torch.uint8, device=device)
+        self.recv = self.buf[self.off_recv:self.off_recv + s_pad * wloc * 2].view(torch.bfloat16).view(s_pad, wloc)
+        self.o = self.buf[self.off_o:self.off_o + rows * d * 2].view(torch.bfloat16).view(rows, d)
+        handle, offset = ops.ipc_export(self.buf)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, (handle, offset), group=group)
+        self._opened = []
+        bases = []
+        for q, (h, off) in enumerate(everyone):
+            if q == rank:
+                bases.append(self.buf.data_ptr())
+            else:
+                ptr = ops.ipc_open(device, h, off)
+                self._opened.append((ptr, off))
+                bases.append(ptr)
+        self.recv_ptrs = [b + self.off_recv for b in bases]
+        self.o_ptrs = [b + self.off_o for b in bases]
+        self.flag_ptrs = [[b + self.off_flags + which * 64 * 4 for b in bases] for which in (0, 1)]
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)   # every arena is zeroed and mapped before the first peer store
+
+    def close(self):
+        for ptr, off in self._opened:
+            ops.ipc_close(self.device, ptr, off)
+        self._opened = []
+
+
 class SequenceParallel:
-    def __init__(self, group=None):
+    def __init__(self, group=None, exchange: str = "p2p"):
+        """exchange = "p2p": NVLink peer stores issued by our own kernels (scatter + fused attention epilogue);
+        "nccl": pack / all-to-all / unpack (the plain-library variant, kept for comparison and for the CPU tests)."""
         if not dist.is_initialized():
             raise RuntimeError("SequenceParallel needs an initialised torch.distributed process group")
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError(f"exchange must be 'p2p' or 'nccl', got {exchange!r}")
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
+        self.exchange = exchange
+        self.arena = None
+
+    def peer_arena(self, rows: int, heads: int, device) -> PeerArena:
+        if self.arena is None or self.arena.rows != rows:
+            if self.arena is not None:
+                self.arena.close()
+            self.arena = PeerArena(self.group, self.world, self.rank, rows, heads, device)
+        return self.arena
 
     # ---- collectives (thin: NCCL on device tensors, gloo in the CPU tests) ----------------------
     def all_to_all(self, recv: torch.Tensor, send: torch.Tensor) -> torch.Tensor:
@@ -69,6 +128,17 @@ class SequenceParallel:
         hpr = heads // self.world
         wloc = hpr * 128
         k = engine._k
+        if self.exchange == "p2p":
+            ar = self.arena            # created by the engine's workspace; ws["recv"] / ws["o"] are views of it
+            rows = qkv.shape[0]
+            k("sp_scatter", ops.sp_scatter_heads, qkv, ar.recv_ptrs, heads, 3, self.world, self.rank)
+            ar.epoch += 1
+            k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[0], self.world, self.rank, ar.epoch)
+            recv = ar.recv
+            k("attn_self", ops.attention_scatter, recv[:, :wloc], recv[:tokens, wloc:2 * wloc], recv[:tokens, 2 * wloc:], ar.o_ptrs,
+              heads * 128, rows, self.rank * wloc, hpr)
+            k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[1], self.world, self.rank, ar.epoch)
+            return
         k("sp_pack", ops.sp_pack_heads, qkv, ws["send"], heads, 3, self.world)
         recv = k("sp_all_to_all", self.all_to_all, ws["recv"], ws["send"])     # [s_pad tokens, (q|k|v) x hpr x 128]
         k("attn_self", ops.attention, recv[:, :wloc], recv[:tokens, wloc:2 * wloc], recv[:tokens, 2 * wloc:], ws["o_full"], hpr)

@@ -165,6 +165,29 @@ int fgb_sp_pack_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* send, int3
 int fgb_sp_unpack_heads(fgb_ctx* ctx, const void* recv, void* x, int64_t ldx, int32_t s_local, int32_t heads,
                         int32_t groups, int32_t world, void* stream);
 
+/* ---- Ulysses exchange over NVLink peer memory (no NCCL on the data path) --------------------------------------------
+ * One process per GPU; each rank exports the CUDA IPC handle of a caller-owned arena and opens its peers' (the 64-byte
+ * handles travel over the torch.distributed control plane once). Afterwards the exchange of
+ * xdit_context_parallel.py:125-146 is done by the producing kernels themselves:
+ *   forward:  fgb_sp_scatter_heads stores every head slice of this rank's q|k|v rows into the owning peer's receive
+ *             matrix (the layout fgb_sp_pack_heads + all-to-all would produce);
+ *   return:   fgb_attn_fwd_scatter — the attention epilogue stores each output row straight into the token-major `o`
+ *             buffer of the rank that owns the token (compute and collective in ONE kernel);
+ *   fgb_sp_barrier orders the two (system-scope release/acquire flags in the arenas; monotonically increasing epoch). */
+int fgb_ipc_export(fgb_ctx* ctx, const void* dev_ptr, void* handle_out_64B, int64_t* offset_out);
+int fgb_ipc_open(fgb_ctx* ctx, const void* handle_64B, int64_t offset, void** peer_ptr);
+int fgb_ipc_close(fgb_ctx* ctx, void* peer_ptr, int64_t offset);
+/* peer_bufs / peer_flags / o_peers: HOST arrays of `world` device pointers (index = rank in the SP group, own rank included). */
+int fgb_sp_scatter_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* const* peer_bufs, int32_t s_local, int32_t heads,
+                         int32_t groups, int32_t world, int32_t rank, void* stream);
+int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* stream);
+/* fgb_attn_fwd_ex whose output row of global token t goes to o_peers[t / rows_per_peer][(t % rows_per_peer) * ldo +
+ * col_offset + head*128 ...] (col_offset = rank * heads * 128 for Ulysses). */
+int fgb_attn_fwd_scatter(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                         void* const* o_peers, int32_t n_peers, int64_t ldo, int32_t rows_per_peer, int32_t col_offset,
+                         int32_t s_q, int32_t s_kv, int32_t heads, float scale, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+
 /* ---- training (BASELINE config 5: stage-2 motion-LoRA fine-tune step) -------------------------------------------
  * The reference trains the `lora_B2` matrices of the 300 adapted Linears (diffusion/training_module.py:266-352, TMOD)
  * under the flow-matching SFT loss (diffusion/loss.py:5-21, LOSS); every gradient below is what torch autograd

@@ -67,7 +67,7 @@ def _worker(rank, world, port, shots, cfg, sp, out_dir):
     from fairygen_b200.cfg_parallel import Layout, ParallelContext, denoise_shots
 
     lay = Layout(world, shots, cfg, sp)
-    ctx = ParallelContext(lay)
+    ctx = ParallelContext(lay, exchange="nccl")
     eng = _FakeEngine(ctx.sequence_parallel())
     n_shots = 3
     data = []

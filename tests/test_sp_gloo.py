@@ -73,7 +73,7 @@ def _worker(rank, world, port, tokens, heads, result_dir):
         def _k(name, fn, *a, **kw):
             return fn(*a, **kw)
 
-    par = spmod.SequenceParallel()
+    par = spmod.SequenceParallel(exchange="nccl")   # the collective variant (gloo here); the NVLink peer-store variant needs GPUs
     assert (par.world, par.rank) == (world, rank)
     out = torch.empty(rows, d)
     par.attention(Eng, ws, qkv, out, tokens)

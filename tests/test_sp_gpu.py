@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, shape, out_dir):
+def _worker(rank, world, port, shape, exchange, out_dir):
     sys.path.insert(0, REPO)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch.distributed as dist
@@ -35,7 +35,7 @@ def _worker(rank, world, port, shape, out_dir):
     single = fg.WanDiTEngine(cfg, f"cuda:{rank}")
     single.load_state_dict(sd)
     ref = single.forward(lat.cuda(), ts, cp.cuda(), True)
-    par = fg.WanDiTEngine(cfg, f"cuda:{rank}", sp=fg.SequenceParallel())
+    par = fg.WanDiTEngine(cfg, f"cuda:{rank}", sp=fg.SequenceParallel(exchange=exchange))
     par.load_state_dict(sd)
     out = par.forward(lat.cuda(), ts, cp.cuda(), True)
     fg.ops.sync_check()
@@ -44,14 +44,15 @@ def _worker(rank, world, port, shape, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])   # NVLink peer stores from our kernels / NCCL all-to-all
 @pytest.mark.parametrize("shape", [(1, 48, 4, 16, 16), (1, 48, 3, 10, 14)])   # S = 256 (even split) and S = 105 (ragged)
-def test_sp2_equals_single_gpu(tmp_path, shape):
+def test_sp2_equals_single_gpu(tmp_path, shape, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
 
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, exchange, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         assert res["finite"] and res["err"] < 2e-3, res   # same kernels, same rounding; only the attention tiling differs
