@@ -12,7 +12,7 @@ import subprocess
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfairygen_b200.so")
+LIB_PATH = os.environ.get("FGB_LIB_PATH") or os.path.join(_HERE, "libfairygen_b200.so")   # override: A/B builds of one kernel
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 # name -> (restype, argtypes); must list every symbol of include/fairygen_b200.h
