@@ -25,6 +25,25 @@ NUM_INFERENCE_STEPS, CFG_SCALE, SIGMA_SHIFT, TEXT_LEN, LORA_RANK = 50, 5.0, 5.0,
 METRIC, UNIT = "dit_denoise_steps_per_s", "steps/s"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (self-attention at S = 27 280, 24 heads)
+    from the committed `ncu --set full` summary; None if the summary is missing.  Only meaningful for the 1-GPU shape."""
+    path = os.path.join(REPO, "profiles", "r01_ncu_attn_summary.csv")
+    try:
+        tot = 0.0
+        with open(path) as f:
+            for line in f:
+                parts = line.strip().split(",")
+                if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(parts[1], None)
+                    if scale is None:
+                        return None
+                    tot += float(parts[2]) * scale
+        return tot or None
+    except OSError:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -237,7 +256,9 @@ def run_ours(args):
     if attn:
         a = attn_flops / (attn["avg_ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "attn_fwd_kernel (self-attention)", "achieved": a, "peak": peaks["bf16_sustained"],
-                    "unit": "TFLOP/s", "frac": a / peaks["bf16_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": a / peaks["bf16_sustained"], "traffic": ncu_traffic_bytes() if world == 1 else None,
+                    "traffic_note": "DRAM bytes of one launch (ncu --set full, profiles/r01_ncu_attn_summary.csv); algorithmic bytes = q,k,v,o "
+                                    "once = 4*S*D*2 = 670 MB",
                     "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "flops_per_launch": attn_flops, "avg_launch_ms": attn["avg_ms"], "launches": attn["launches"]}
     gemm_ms = sum(v["total_ms"] for k, v in kernels.items() if k.startswith("gemm"))

@@ -12,6 +12,17 @@ namespace fgb {
 
 constexpr int kRowWarps = 4;  // rows per CTA (one warp per row)
 
+struct PeerPtrs {
+  void* p[FGB_MAX_PEERS];
+};
+// Where the Ulysses exchange wants a row: peers.p == all NULL -> in place. Otherwise the 128-wide head `h` of local
+// row r goes to peer h / (heads/world), row (rank*s_local + r), group `grp` of that peer's receive matrix
+// [world*s_local][groups][heads/world][128] (see sp_scatter_heads_kernel).
+struct ScatterSpec {
+  PeerPtrs peers;
+  int s_local, heads, world, rank, grp, groups;
+};
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm (no affine) + adaLN modulate, or LayerNorm with affine.      DIT:205-207, 63-64, 224-227
 // NV = dim / 256 16-byte vectors per lane.
@@ -80,11 +91,11 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __res
 // ---------------------------------------------------------------------------------------------
 // RMSNorm over the full row (all heads) + optional 3-D RoPE, in place.      DIT:91-110, 140-144
 // ---------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool SCATTER>
 __global__ void __launch_bounds__(kRowWarps * 32)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float eps,
                     const __nv_bfloat16* __restrict__ weight, const float2* __restrict__ rope_tab, int gf, int gh,
-                    int gw, int token_offset) {
+                    int gw, int token_offset, const ScatterSpec sc) {
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -141,7 +152,19 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
         f[2 * j + 1] = a * sn[j] + b * cs[j];
       }
     }
-    xr[i * 32 + lane] = pack8(f);
+    if (SCATTER) {
+      // fused Ulysses exchange: the normalised, rotated head slice goes straight to the peer that owns the head
+      const int col = (i * 32 + lane) * 8;
+      const int head = col >> 7;
+      const int hpr = sc.heads / sc.world;
+      const int peer = head / hpr;
+      __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(sc.peers.p[peer]) +
+                           ((static_cast<int64_t>(sc.rank) * sc.s_local + row) * sc.groups + sc.grp) * hpr * 128 +
+                           (head - peer * hpr) * 128 + (col & 127);
+      *reinterpret_cast<uint4*>(dst) = pack8(f);
+    } else {
+      xr[i * 32 + lane] = pack8(f);
+    }
   }
 }
 
@@ -290,15 +313,11 @@ __global__ void sp_heads_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, __nv
 // ---------------------------------------------------------------------------------------------
 // Ulysses exchange over NVLink peer memory (no NCCL on the data path)
 // ---------------------------------------------------------------------------------------------
-struct PeerPtrs {
-  void* p[FGB_MAX_PEERS];
-};
-
 // x [s_local][groups][heads][128] of THIS rank -> recv buffer of every peer, laid out [world*s_local tokens][groups]
 // [heads/world][128]: the head slice owned by peer `q` goes to rows [rank*s_local, (rank+1)*s_local) of q's buffer.
 // 16-byte stores; consecutive threads write consecutive 16 B of one 256-byte head row (full NVLink packets).
 __global__ void sp_scatter_heads_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, PeerPtrs peers, int s_local,
-                                        int heads, int groups, int world, int rank) {
+                                        int heads, int groups, int world, int rank, int grp0, int groups_total) {
   const int hpr = heads / world;
   const int gh = groups * heads;
   const int64_t total = static_cast<int64_t>(s_local) * gh * 16;
@@ -311,7 +330,7 @@ __global__ void sp_scatter_heads_kernel(const __nv_bfloat16* __restrict__ x, int
     const int peer = head / hpr, hh = head % hpr;
     const uint4 v = ldg_nc_v4(reinterpret_cast<const uint4*>(x + s * ldx + static_cast<int64_t>(g_head) * 128) + vec);
     __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(peers.p[peer]) +
-                         ((static_cast<int64_t>(rank) * s_local + s) * groups + grp) * hpr * 128 + hh * 128;
+                         ((static_cast<int64_t>(rank) * s_local + s) * groups_total + grp0 + grp) * hpr * 128 + hh * 128;
     reinterpret_cast<uint4*>(dst)[vec] = v;
   }
 }
@@ -406,9 +425,10 @@ extern "C" int fgb_rmsnorm_rope(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows
   bf16* xp = static_cast<bf16*>(x);
   const bf16* wp = static_cast<const bf16*>(weight);
   const float2* tab = static_cast<const float2*>(rope_tab);
+  ScatterSpec none{};
 #define FGB_RMS_CASE(NV)                                                                                         \
   case NV:                                                                                                       \
-    rmsnorm_rope_kernel<NV><<<grid, kRowWarps * 32, 0, s>>>(xp, ldx, rows, eps, wp, tab, gf, gh, gw, token_offset); \
+    rmsnorm_rope_kernel<NV, false><<<grid, kRowWarps * 32, 0, s>>>(xp, ldx, rows, eps, wp, tab, gf, gh, gw, token_offset, none); \
     break;
   switch (dim / 256) {
     FGB_RMS_CASE(1) FGB_RMS_CASE(2) FGB_RMS_CASE(4) FGB_RMS_CASE(6) FGB_RMS_CASE(8) FGB_RMS_CASE(12) FGB_RMS_CASE(16)
@@ -523,8 +543,11 @@ extern "C" int fgb_sp_unpack_heads(fgb_ctx* ctx, const void* recv, void* x, int6
 }
 
 extern "C" int fgb_sp_scatter_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* const* peer_bufs, int32_t s_local,
-                                    int32_t heads, int32_t groups, int32_t world, int32_t rank, void* stream) {
+                                    int32_t heads, int32_t groups, int32_t group_first, int32_t groups_total, int32_t world,
+                                    int32_t rank, void* stream) {
   FGB_CHECK_ARG(ctx && x && peer_bufs, "fgb_sp_scatter_heads: NULL argument");
+  FGB_CHECK_ARG(group_first >= 0 && group_first + groups <= groups_total, "fgb_sp_scatter_heads: groups [%d,%d) of %d", group_first,
+                group_first + groups, groups_total);
   FGB_CHECK_ARG(s_local > 0 && heads > 0 && groups > 0 && world > 0 && world <= FGB_MAX_PEERS && heads % world == 0 && rank >= 0 &&
                     rank < world, "fgb_sp_scatter_heads: heads=%d world=%d rank=%d", heads, world, rank);
   FGB_CHECK_ARG(ldx % 8 == 0 && ldx >= static_cast<int64_t>(groups) * heads * 128 && aligned16(x), "fgb_sp_scatter_heads: alignment");
@@ -535,7 +558,7 @@ extern "C" int fgb_sp_scatter_heads(fgb_ctx* ctx, const void* x, int64_t ldx, vo
   int grid = grid_1d(total, 256);
   if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
   sp_scatter_heads_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x), ldx, pp, s_local, heads,
-                                                                             groups, world, rank);
+                                                                             groups, world, rank, group_first, groups_total);
   FGB_LAUNCH_CHECK("sp_scatter_heads_kernel");
   return FGB_OK;
 }
@@ -547,5 +570,49 @@ extern "C" int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t wor
   for (int i = 0; i < world; ++i) FGB_CHECK_ARG(pp.p[i], "fgb_sp_barrier: peer flag array %d is NULL", i);
   sp_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pp, world, rank, epoch);
   FGB_LAUNCH_CHECK("sp_barrier_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_rmsnorm_rope_scatter(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t rows, int32_t dim, float eps,
+                                        const void* weight, const void* rope_tab, int32_t gf, int32_t gh, int32_t gw,
+                                        int32_t token_offset, void* const* peer_bufs, int32_t world, int32_t rank, int32_t group,
+                                        int32_t groups_total, void* stream) {
+  FGB_CHECK_ARG(ctx && x && weight && peer_bufs, "fgb_rmsnorm_rope_scatter: NULL argument");
+  FGB_CHECK_ARG(rows > 0 && dim > 0 && dim % 256 == 0, "fgb_rmsnorm_rope_scatter: rows=%d dim=%d", rows, dim);
+  FGB_CHECK_ARG(ldx % 8 == 0 && aligned16(x) && aligned16(weight), "fgb_rmsnorm_rope_scatter: operands must be 16-byte aligned");
+  const int heads = dim / 128;
+  FGB_CHECK_ARG(world > 0 && world <= FGB_MAX_PEERS && heads % world == 0 && rank >= 0 && rank < world && group >= 0 && group < groups_total,
+                "fgb_rmsnorm_rope_scatter: heads=%d world=%d rank=%d group=%d/%d", heads, world, rank, group, groups_total);
+  if (rope_tab)
+    FGB_CHECK_ARG(gf > 0 && gh > 0 && gw > 0 && gf <= 1024 && gh <= 1024 && gw <= 1024 && token_offset >= 0,
+                  "fgb_rmsnorm_rope_scatter: grid (%d,%d,%d) outside the RoPE table", gf, gh, gw);
+  ScatterSpec sc{};
+  for (int i = 0; i < world; ++i) {
+    FGB_CHECK_ARG(peer_bufs[i] && aligned16(peer_bufs[i]), "fgb_rmsnorm_rope_scatter: peer buffer %d", i);
+    sc.peers.p[i] = peer_bufs[i];
+  }
+  sc.s_local = rows;
+  sc.heads = heads;
+  sc.world = world;
+  sc.rank = rank;
+  sc.grp = group;
+  sc.groups = groups_total;
+  dim3 grid((rows + kRowWarps - 1) / kRowWarps);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bf16* xp = const_cast<bf16*>(static_cast<const bf16*>(x));
+  const bf16* wp = static_cast<const bf16*>(weight);
+  const float2* tab = static_cast<const float2*>(rope_tab);
+#define FGB_RMS_CASE(NV)                                                                                                    \
+  case NV:                                                                                                                  \
+    rmsnorm_rope_kernel<NV, true><<<grid, kRowWarps * 32, 0, s>>>(xp, ldx, rows, eps, wp, tab, gf, gh, gw, token_offset, sc); \
+    break;
+  switch (dim / 256) {
+    FGB_RMS_CASE(1) FGB_RMS_CASE(2) FGB_RMS_CASE(4) FGB_RMS_CASE(6) FGB_RMS_CASE(8) FGB_RMS_CASE(12) FGB_RMS_CASE(16)
+    FGB_RMS_CASE(20)
+    default:
+      return set_error(FGB_ERR_UNSUPPORTED, "rmsnorm: dim %d is not one of 256*{1,2,4,6,8,12,16,20}", dim);
+  }
+#undef FGB_RMS_CASE
+  FGB_LAUNCH_CHECK("rmsnorm_rope_kernel<scatter>");
   return FGB_OK;
 }

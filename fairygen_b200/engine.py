@@ -238,12 +238,15 @@ class WanDiTEngine:
             # self-attention branch (DIT:224-225)
             k("ln_modulate", ops.ln_modulate, x, a, cfg.eps, m0[0], m0[1], m1[0], m1[1], n_first)
             k("gemm_qkv", ops.gemm, a, b.wqkv, b.bqkv, qkv)
-            k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)
-            k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, d:2 * d], cfg.eps, b.nk, self.rope_tab, grid, tok0)
-            if sp is None:
-                k("attn_self", ops.attention, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, H)
+            if sp is not None and getattr(sp, "exchange", "nccl") == "p2p":
+                sp.attention(self, ws, qkv, o, S, norm=(cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0))
             else:
-                sp.attention(self, ws, qkv, o, S)
+                k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)
+                k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, d:2 * d], cfg.eps, b.nk, self.rope_tab, grid, tok0)
+                if sp is None:
+                    k("attn_self", ops.attention, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, H)
+                else:
+                    sp.attention(self, ws, qkv, o, S)
             k("gemm_o", ops.gemm, o, b.wo, b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first)
             # cross-attention branch (DIT:226)
             k("ln_affine", ops.ln_affine, x, a, cfg.eps, b.n3w, b.n3b)

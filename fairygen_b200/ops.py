@@ -280,12 +280,25 @@ def ipc_close(device, peer_ptr: int, offset: int) -> None:
     _lib.check(_lib.lib().fgb_ipc_close(context(device).handle, c_void_p(peer_ptr), offset), "fgb_ipc_close")
 
 
-def sp_scatter_heads(x, peer_ptrs, heads: int, groups: int, world: int, rank: int):
-    """Store this rank's [s_local, groups*heads*128] rows into every peer's receive matrix (NVLink peer stores)."""
+def sp_scatter_heads(x, peer_ptrs, heads: int, groups: int, world: int, rank: int, group_first: int = 0, groups_total: Optional[int] = None):
+    """Store this rank's [s_local, groups*heads*128] rows into groups [group_first, group_first+groups) of every peer's
+    receive matrix (NVLink peer stores)."""
     ldx = _rowmajor(x, "x")
     c = _h(x)
-    _lib.check(_lib.lib().fgb_sp_scatter_heads(c.handle, _p(x), ldx, _ptr_array(peer_ptrs), x.shape[0], heads, groups, world, rank,
-                                               _stream()), "fgb_sp_scatter_heads")
+    _lib.check(_lib.lib().fgb_sp_scatter_heads(c.handle, _p(x), ldx, _ptr_array(peer_ptrs), x.shape[0], heads, groups, group_first,
+                                               groups if groups_total is None else groups_total, world, rank, _stream()),
+               "fgb_sp_scatter_heads")
+
+
+def rmsnorm_rope_scatter(x, eps, weight, rope_tab, grid, token_offset, peer_ptrs, world: int, rank: int, group: int, groups_total: int):
+    """rmsnorm_rope(x) stored head by head into group `group` of the owning peers' receive matrices (x is not modified)."""
+    ldx = _rowmajor(x, "x")
+    rows, dim = x.shape
+    _vec(weight, dim, "weight")
+    c = _h(x)
+    _lib.check(_lib.lib().fgb_rmsnorm_rope_scatter(c.handle, _p(x), ldx, rows, dim, eps, _p(weight), _p(rope_tab), grid[0], grid[1], grid[2],
+                                                   token_offset, _ptr_array(peer_ptrs), world, rank, group, groups_total, _stream()),
+               "fgb_rmsnorm_rope_scatter")
 
 
 def sp_barrier(device, flag_ptrs, world: int, rank: int, epoch: int):

@@ -122,8 +122,10 @@ class SequenceParallel:
         return out
 
     # ---- the self-attention exchange ---------------------------------------------------------------
-    def attention(self, engine, ws, qkv: torch.Tensor, o: torch.Tensor, tokens: int) -> None:
-        """qkv [rows, 3*H*128] (q,k already RMS-normed + rotated) -> o [rows, H*128]."""
+    def attention(self, engine, ws, qkv: torch.Tensor, o: torch.Tensor, tokens: int, norm=None) -> None:
+        """qkv [rows, 3*H*128] -> o [rows, H*128].  norm = None: q, k are already RMS-normed + rotated.
+        norm = (eps, weight_q, weight_k, rope_tab, grid, token_offset) (p2p only): the pre-norm q, k are normalised,
+        rotated and sent by one fused kernel each."""
         heads = engine.cfg.num_heads
         hpr = heads // self.world
         wloc = hpr * 128
@@ -131,7 +133,15 @@ class SequenceParallel:
         if self.exchange == "p2p":
             ar = self.arena            # created by the engine's workspace; ws["recv"] / ws["o"] are views of it
             rows = qkv.shape[0]
-            k("sp_scatter", ops.sp_scatter_heads, qkv, ar.recv_ptrs, heads, 3, self.world, self.rank)
+            d = heads * 128
+            if norm is None:
+                k("sp_scatter", ops.sp_scatter_heads, qkv, ar.recv_ptrs, heads, 3, self.world, self.rank)
+            else:
+                # q and k leave for their owners straight from the RMSNorm+RoPE registers; v needs a plain scatter
+                eps, wq, wk, rope_tab, grid, tok0 = norm
+                k("rmsnorm_rope", ops.rmsnorm_rope_scatter, qkv[:, :d], eps, wq, rope_tab, grid, tok0, ar.recv_ptrs, self.world, self.rank, 0, 3)
+                k("rmsnorm_rope", ops.rmsnorm_rope_scatter, qkv[:, d:2 * d], eps, wk, rope_tab, grid, tok0, ar.recv_ptrs, self.world, self.rank, 1, 3)
+                k("sp_scatter", ops.sp_scatter_heads, qkv[:, 2 * d:], ar.recv_ptrs, heads, 1, self.world, self.rank, 2, 3)
             ar.epoch += 1
             k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[0], self.world, self.rank, ar.epoch)
             recv = ar.recv

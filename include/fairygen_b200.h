@@ -178,8 +178,15 @@ int fgb_ipc_export(fgb_ctx* ctx, const void* dev_ptr, void* handle_out_64B, int6
 int fgb_ipc_open(fgb_ctx* ctx, const void* handle_64B, int64_t offset, void** peer_ptr);
 int fgb_ipc_close(fgb_ctx* ctx, void* peer_ptr, int64_t offset);
 /* peer_bufs / peer_flags / o_peers: HOST arrays of `world` device pointers (index = rank in the SP group, own rank included). */
+/* x holds `groups` consecutive groups (group_first .. group_first+groups-1 of the receive matrix's groups_total). */
 int fgb_sp_scatter_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* const* peer_bufs, int32_t s_local, int32_t heads,
-                         int32_t groups, int32_t world, int32_t rank, void* stream);
+                         int32_t groups, int32_t group_first, int32_t groups_total, int32_t world, int32_t rank, void* stream);
+/* fgb_rmsnorm_rope whose normalised / rotated rows are not written back but stored head by head into group `group` of
+ * the owning peers' receive matrices: q and k of DIT:140-144 leave for the Ulysses exchange straight from registers. */
+int fgb_rmsnorm_rope_scatter(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t rows, int32_t dim, float eps, const void* weight,
+                             const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, int32_t token_offset,
+                             void* const* peer_bufs, int32_t world, int32_t rank, int32_t group, int32_t groups_total,
+                             void* stream);
 int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* stream);
 /* fgb_attn_fwd_ex whose output row of global token t goes to o_peers[t / rows_per_peer][(t % rows_per_peer) * ldo +
  * col_offset + head*128 ...] (col_offset = rank * heads * 128 for Ulysses). */
