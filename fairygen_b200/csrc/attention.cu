@@ -26,100 +26,9 @@
 // TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P_i aliases columns [0,32) and [64,96) of S_i.
 #include <cstdlib>
 
-#include "common.cuh"
-#include "host.h"
+#include "attention_common.cuh"
 
 namespace fgb {
-
-constexpr int kAttnThreads = 320;
-constexpr int kTile = 128;                  // query rows per tile == keys per KV tile == head_dim
-constexpr int kBoxBytes = kTile * 64 * 2;   // one TMA box: 128 rows x 64 bf16 = 16 KB
-constexpr int kTileBytes = 2 * kBoxBytes;   // 128 x 128 bf16 = 32 KB (two 64-column boxes)
-constexpr int kKVStages = 2;
-constexpr int kAttnSmem = 2 * kTileBytes /*Q*/ + 2 * kKVStages * kTileBytes /*K,V*/ + 1024 /*align*/ + 256 /*barriers*/ +
-                          2 * 2 * kTile * 4 /*row-max exchange*/;
-
-struct AttnParams {
-  __nv_bfloat16* o;
-  int64_t ldo;
-  int32_t s_q, s_kv;
-  float scale_log2;
-  // Work list: CTA b < n_full handles unit b over all KV tiles; the remaining CTAs handle the LAST units of
-  // the list, each split `split` ways along the keys (wave-quantisation fix, see fgb_attn_fwd_ex). A unit is
-  // (head, pair of query tiles): unit = head * n_pairs + pair.
-  int32_t n_pairs, n_full, split;
-  float* part_o;    // [split CTA][256 rows][128] un-normalised fp32 partial outputs
-  float2* part_ml;  // [split CTA][256 rows] (running max in log2 units, row sum)
-  float* lse;       // optional [heads][ld_lse]: log2-domain log-sum-exp of the scaled scores (for the backward pass);
-  int64_t ld_lse;   // rows in [s_q, ld_lse) get the value of an all-zero query row, so the backward needs no masks
-  // Fused Ulysses return exchange: when rows_per_peer > 0 the output row of global token t goes straight into the
-  // token-major buffer of the rank that owns t (peer memory over NVLink): o_peers[t / rows_per_peer] + (t %
-  // rows_per_peer) * ldo + (col_offset + head*128); `o` is unused.
-  __nv_bfloat16* o_peers[FGB_MAX_PEERS];
-  int32_t rows_per_peer, col_offset;
-};
-
-__device__ __forceinline__ __nv_bfloat16* out_row(const AttnParams& p, int row, int head) {
-  if (p.rows_per_peer > 0) {
-    const int peer = row / p.rows_per_peer;
-    return p.o_peers[peer] + static_cast<int64_t>(row - peer * p.rows_per_peer) * p.ldo + p.col_offset + head * 128;
-  }
-  return p.o + static_cast<int64_t>(row) * p.ldo + head * 128;
-}
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): halves the issue slots of the softmax ----
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// 2^x for a pair on the FMA/ALU pipes instead of the MUFU (which is as busy as the tensor pipe in this
-// kernel): round-to-nearest split x = n + f via the 1.5*2^23 trick, degree-3 minimax polynomial for 2^f
-// on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), exponent add in integer.
-__device__ __forceinline__ void exp2_emulated(uint64_t x2, float& r0, float& r1) {
-  float x0, x1;
-  unpack2(x2, x0, x1);
-  x2 = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
-  const uint64_t kMagic = pack2(12582912.0f, 12582912.0f);
-  const uint64_t kNegMagic = pack2(-12582912.0f, -12582912.0f);
-  const uint64_t kMinusOne = pack2(-1.0f, -1.0f);
-  const uint64_t c0 = pack2(0.9999280572f, 0.9999280572f), c1 = pack2(0.6932609677f, 0.6932609677f);
-  const uint64_t c2 = pack2(0.2426111251f, 0.2426111251f), c3 = pack2(0.0551716685f, 0.0551716685f);
-  const uint64_t t = add2(x2, kMagic);            // integer part lands in the low mantissa bits
-  const uint64_t n = add2(t, kNegMagic);          // round(x) as float
-  const uint64_t f = fma2(n, kMinusOne, x2);      // x - round(x)
-  uint64_t p = fma2(f, c3, c2);
-  p = fma2(p, f, c1);
-  p = fma2(p, f, c0);
-  float p0, p1, t0, t1;
-  unpack2(p, p0, p1);
-  unpack2(t, t0, t1);
-  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-}
-
-struct TagTrue { static constexpr bool value = true; };
-struct TagFalse { static constexpr bool value = false; };
 
 // EMU: of every 8 score pairs, EMU are exponentiated by exp2_emulated, the rest by MUFU.EX2.
 template <int EMU>
@@ -501,6 +410,16 @@ static int launch_attn(int grid, cudaStream_t stream, const CUtensorMap& tq, con
   return FGB_OK;
 }
 
+// FGB_ATTN_CLUSTER=1 selects attention_cluster.cu (one query tile per CTA, double-buffered S, K/V multicast in a 2-CTA cluster)
+static bool attn_cluster_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* env = getenv("FGB_ATTN_CLUSTER");
+    mode = env ? (atoi(env) != 0) : 0;
+  }
+  return mode != 0;
+}
+
 // How the last, partly filled wave of CTAs is cut along the keys: returns the split factor g (1 = no split) and the
 // number of units that are split. With U units on n_sm SMs (one CTA per SM), the last U mod n_sm units would occupy a
 // whole wave on their own; cutting each into g key chunks makes the tail ceil(rem*g/n_sm)/g of a wave instead.
@@ -533,7 +452,7 @@ extern "C" int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s
   if (!ctx || s_q <= 0 || s_kv <= 0 || heads <= 0) return 0;
   const int n_pairs = (s_q + 2 * kTile - 1) / (2 * kTile);
   int split, n_split;
-  plan_split(n_pairs * heads, (s_kv + kTile - 1) / kTile, ctx->sm_count, &split, &n_split);
+  plan_split(n_pairs * heads, (s_kv + kTile - 1) / kTile, attn_cluster_mode() ? ctx->sm_count / 2 : ctx->sm_count, &split, &n_split);
   return static_cast<int64_t>(n_split) * split * (2 * kTile) * (128 * 4 + 8);
 }
 
@@ -557,12 +476,14 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
     for (int i = 0; i < n_peers; ++i) FGB_CHECK_ARG(o_peers[i] && aligned16(o_peers[i]), "fgb_attn_fwd_scatter: peer output %d", i);
   }
 
+  const bool cluster = attn_cluster_mode();
+  const int kv_box = cluster ? 64 : kTile;   // the cluster kernel loads half tiles and multicasts them
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_bf16_2d(ctx, &tq, q, s_q, width, ldq, kTile);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(ctx, &tk, k, s_kv, width, ldk, kTile);
+  rc = make_tmap_bf16_2d(ctx, &tk, k, s_kv, width, ldk, kv_box);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(ctx, &tv, v, s_kv, width, ldv, kTile);
+  rc = make_tmap_bf16_2d(ctx, &tv, v, s_kv, width, ldv, kv_box);
   if (rc) return rc;
 
   AttnParams p;
@@ -583,7 +504,7 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   const int units = static_cast<int>(units64);
   int split = 1, n_split = 0;
   // the key split needs the caller's scratch (the library never allocates); without it every unit runs whole
-  if (workspace != nullptr) plan_split(units, (s_kv + kTile - 1) / kTile, ctx->sm_count, &split, &n_split);
+  if (workspace != nullptr) plan_split(units, (s_kv + kTile - 1) / kTile, cluster ? ctx->sm_count / 2 : ctx->sm_count, &split, &n_split);
   const int64_t need = static_cast<int64_t>(n_split) * split * (2 * kTile) * (128 * 4 + 8);
   if (need > workspace_bytes) {
     split = 1;
@@ -603,7 +524,14 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   }
   const int grid = p.n_full + n_split * split;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (emu) {
+  int emu_sel = emu;
+  if (cluster) {
+    rc = launch_attn_cluster(emu, grid, st, tq, tk, tv, p);
+    if (rc) return rc;
+    emu_sel = -2;   // skip the switch below
+  }
+  switch (emu_sel) {
+    case -2: break;
     case 0: rc = launch_attn<0>(grid, st, tq, tk, tv, p); break;
     case 1: rc = launch_attn<1>(grid, st, tq, tk, tv, p); break;
     case 2: rc = launch_attn<2>(grid, st, tq, tk, tv, p); break;

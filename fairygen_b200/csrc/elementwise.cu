@@ -337,7 +337,8 @@ __global__ void sp_scatter_heads_kernel(const __nv_bfloat16* __restrict__ x, int
 
 // Cross-GPU barrier for the exchange: thread q publishes `epoch` in peer q's flag slot [rank] (release, system scope)
 // and then waits until peer q has published `epoch` in ours (acquire). All earlier peer stores of this stream are
-// complete (kernel boundary) and made visible by the fence. Bounded: traps after ~4 s instead of hanging the box.
+// complete (kernel boundary) and made visible by the fence. Bounded: traps after ~30 s (ranks can be seconds apart at
+// start-up) instead of hanging the box.
 __global__ void sp_barrier_kernel(PeerPtrs flags, int world, int rank, int epoch) {
   const int q = threadIdx.x;
   if (q >= world) return;
@@ -350,7 +351,7 @@ __global__ void sp_barrier_kernel(PeerPtrs flags, int world, int rank, int epoch
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
     if (v - epoch >= 0) break;
-    if (clock64() - t0 > 8000000000ll) __trap();
+    if (clock64() - t0 > 50000000000ll) __trap();
   }
   __threadfence_system();
 }
