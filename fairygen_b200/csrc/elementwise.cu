@@ -28,7 +28,7 @@ struct ScatterSpec {
 // NV = dim / 256 16-byte vectors per lane.
 // ---------------------------------------------------------------------------------------------
 template <int NV, bool AFFINE>
-__global__ void __launch_bounds__(kRowWarps * 32)
+__global__ void __launch_bounds__(kRowWarps * 32, 3)   // <= 168 registers (the unrolled scale/shift loads would otherwise take 255): 12 warps/SM
 ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy, int rows,
           float eps, const __nv_bfloat16* __restrict__ shift0, const __nv_bfloat16* __restrict__ scale0,
           const __nv_bfloat16* __restrict__ shift1, const __nv_bfloat16* __restrict__ scale1, int rows_mod0) {

@@ -143,12 +143,10 @@ rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_b
     }
   }
   const uint4* wr = reinterpret_cast<const uint4*>(weight);
-  float s2 = 0.f;
-  float dn[NV][8];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float f[8], d[8], w[8];
-    unpack8(v[i], f);
+  // dn = rot^-1(dy) * w is formed twice (once for the reduction, once for the result) instead of being kept:
+  // the row and its gradient already occupy 96 registers at D = 3072
+  auto grad_n = [&](int i, float (&d)[8]) {
+    float w[8];
     unpack8(dv[i], d);
     unpack8(__ldg(wr + i * 32 + lane), w);
     if (rotate) {
@@ -160,18 +158,25 @@ rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_b
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      dn[i][e] = d[e] * w[e];
-      s2 += dn[i][e] * f[e] * rs;
-    }
+    for (int e = 0; e < 8; ++e) d[e] *= w[e];
+  };
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8], d[8];
+    unpack8(v[i], f);
+    grad_n(i, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s2 += d[e] * f[e] * rs;
   }
   s2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    float f[8];
+    float f[8], d[8];
     unpack8(v[i], f);
+    grad_n(i, d);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = rs * (dn[i][e] - f[e] * rs * s2);
+    for (int e = 0; e < 8; ++e) f[e] = rs * (d[e] - f[e] * rs * s2);
     dr[i * 32 + lane] = pack8(f);
   }
 }
