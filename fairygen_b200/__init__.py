@@ -23,6 +23,12 @@ def __getattr__(name):  # lazy: importing the package must not require CUDA or t
     if name == "WanDenoiser":
         from .pipeline import WanDenoiser
         return WanDenoiser
+    if name == "Stage2Trainer":
+        from .training import Stage2Trainer
+        return Stage2Trainer
+    if name in ("lora_io", "cfg_parallel", "training"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
     if name == "SequenceParallel":
         from .sp import SequenceParallel
         return SequenceParallel

@@ -153,3 +153,22 @@ def test_headline_shape_full_model_vs_oracle_bf16(env):
     err = rel_l2(out, ref16)
     print(f"30 layers S=27280: ours-vs-ref_bf16 {err:.3e}")
     assert err < PER_STEP_TOL
+
+
+def test_on_gpu_lora_fuse_matches_reference_fuse(env):
+    """lora_io.fuse_into_engine (one fgb_lora_merge per adapted Linear on the packed weights) vs the reference's
+    GeneralLoRALoader.fuse_lora_to_base_model as restated by the oracle (pinned by tests/golden/lora.npz)."""
+    fg, o = env
+    from fairygen_b200 import lora_io
+    w = o.make_weights(o.TINY, seed=0)
+    lora = o.make_lora(o.TINY, rank=32, seed=2)
+    ref_eng = tiny_engine(fg, o, o.fuse_lora({k: v.to(BF) for k, v in w.items()}, {k: v.to(BF) for k, v in lora.items()}, alpha=1.0))
+    eng = tiny_engine(fg, o, w)
+    assert lora_io.fuse_into_engine(eng, lora, alpha=1.0) == 20
+    fg.ops.sync_check()
+    for b, rb in zip(eng.blocks, ref_eng.blocks):
+        for name in ("wqkv", "wo", "cwq", "cwkv", "cwo", "w1", "w2"):
+            assert rel_l2(getattr(b, name), getattr(rb, name)) < 3e-3, name   # fp32-accumulated vs bf16 mm + bf16 add
+    lat, z0, cp, cn = o.make_inputs(o.TINY, (1, 48, 3, 8, 8), text_len=32, live_text=8)
+    ts = torch.tensor([900.0])
+    assert rel_l2(eng.forward(lat.cuda(), ts, cp.cuda(), True), ref_eng.forward(lat.cuda(), ts, cp.cuda(), True)) < 5e-3
