@@ -265,6 +265,16 @@ def run_ours(args):
     fwd_per_rank = 2 * sp_ways / world   # DiT forwards each rank takes part in per step (1 under CFG-parallel)
     gemm_flops = 30 * (12 * tokens * cfg.dim ** 2 + 4 * tokens * cfg.dim * cfg.ffn_dim) / sp_ways * fwd_per_rank * args.steps
     breakdown = {k: round(v["total_ms"] / args.steps, 3) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["total_ms"])}
+    # memory-bound kernels: algorithmic bytes per launch (one read + one write of the [rows, D] bf16 matrix = 2X/P)
+    # over the live CUDA-event time of the launch, against the measured HBM copy bandwidth
+    x_bytes = 2.0 * (-(-tokens // sp_ways)) * cfg.dim * 2
+    hbm = {}
+    for name in ("ln_modulate", "ln_affine", "rmsnorm_rope", "rmsnorm"):
+        kt = kernels.get(name)
+        if kt and kt["avg_ms"] > 0:
+            gbs = x_bytes / (kt["avg_ms"] * 1e-3) / 1e9
+            hbm[name] = {"achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3), "bytes_per_launch": x_bytes,
+                         "avg_launch_us": round(kt["avg_ms"] * 1e3, 2)}
 
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
@@ -281,7 +291,7 @@ def run_ours(args):
                 "api": "fairygen_b200.WanDenoiser.step on pinned host latents/contexts, result copied back to host"},
         "gpu_launches": launches, "roofline": roofline,
         "gemm": {"tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "ms_per_step": gemm_ms / args.steps},
-        "kernel_ms_per_step": breakdown, "clocks": clocks.summary(), "output_finite": finite,
+        "kernel_ms_per_step": breakdown, "memory_bound_kernels": hbm, "clocks": clocks.summary(), "output_finite": finite,
     }
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
