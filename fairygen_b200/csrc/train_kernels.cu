@@ -245,15 +245,28 @@ lora_merge_kernel(const __nv_bfloat16* __restrict__ w, int64_t ldw, const __nv_b
                   const uint8_t* __restrict__ mask, float mask_mul, float scaling, __nv_bfloat16* __restrict__ w_eff,
                   int64_t ld_eff, int n, int k) {
   constexpr int R = 16 * NR;
-  __shared__ __align__(32) __nv_bfloat16 s_b[64 * R];
-  __shared__ __align__(32) float s_acc[64 * 136];
+  // operands and the fp32 result tile share one buffer (the result overwrites the operands after the last MMA)
+  constexpr int kOperandBytes = (64 * R + R * 128) * 2, kAccBytes = 64 * 136 * 4;
+  __shared__ __align__(32) unsigned char s_raw[kOperandBytes > kAccBytes ? kOperandBytes : kAccBytes];
+  __nv_bfloat16* s_b = reinterpret_cast<__nv_bfloat16*>(s_raw);              // (B1 + B2*mask*2) * scaling, rows n0..n0+63
+  __nv_bfloat16* s_a = s_b + 64 * R;                                         // A1[:, k0..k0+127]
+  float* s_acc = reinterpret_cast<float*>(s_raw);
   const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 128;
+  // every global read of this tile is issued up front (one round trip): the W tile into registers, A1 and B into smem
+  uint4 wv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x + j * 256;
+    wv[j] = ldg_nc_v4(w + static_cast<int64_t>(n0 + (i >> 4)) * ldw + k0 + (i & 15) * 8);
+  }
+  for (int i = threadIdx.x; i < R * 16; i += 256)
+    *reinterpret_cast<uint4*>(s_a + (i >> 4) * 128 + (i & 15) * 8) = ldg_nc_v4(a1 + static_cast<int64_t>(i >> 4) * lda + k0 + (i & 15) * 8);
   for (int i = threadIdx.x; i < 64 * R; i += 256) {
     const int64_t g = static_cast<int64_t>(n0 + i / R) * R + (i % R);
     float v = b1 ? __bfloat162float(b1[g]) : 0.f;
     if (b2) {
       // B2 * mask -> bf16, * scale_factor -> bf16 (TMOD:343-346), summed with B1 in fp32
-      float m = mask ? static_cast<float>(mask[g]) : 1.0f;
+      const float m = mask ? static_cast<float>(mask[g]) : 1.0f;
       v += round_bf16(round_bf16(__bfloat162float(b2[g]) * m) * mask_mul);
     }
     s_b[i] = __float2bfloat16_rn(v * scaling);
@@ -271,17 +284,20 @@ lora_merge_kernel(const __nv_bfloat16* __restrict__ w, int64_t ldw, const __nv_b
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
-      wmma::load_matrix_sync(fb, a1 + static_cast<int64_t>(r * 16) * lda + k0 + wk + j * 16, static_cast<unsigned>(lda));
+      wmma::load_matrix_sync(fb, s_a + r * 16 * 128 + wk + j * 16, 128);
       wmma::mma_sync(acc[j], fa, fb, acc[j]);
     }
   }
+  __syncthreads();   // every warp is done reading the operands
 #pragma unroll
   for (int j = 0; j < 4; ++j) wmma::store_matrix_sync(s_acc + wn * 136 + wk + j * 16, acc[j], 136, wmma::mem_row_major);
   __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x + j * 256;
     const int r = i >> 4, c = (i & 15) * 8;
     float f[8];
-    unpack8(ldg_nc_v4(w + static_cast<int64_t>(n0 + r) * ldw + k0 + c), f);
+    unpack8(wv[j], f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] += s_acc[r * 136 + c + e];
     *reinterpret_cast<uint4*>(w_eff + static_cast<int64_t>(n0 + r) * ld_eff + k0 + c) = pack8(f);
@@ -293,8 +309,10 @@ __global__ void __launch_bounds__(128)
 lora_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const __nv_bfloat16* __restrict__ t, int64_t ld_t,
                   float* __restrict__ db, const uint8_t* __restrict__ mask, float mul, int rows, int n, int rows_per_cta) {
   constexpr int R = 16 * NR;
-  __shared__ __align__(32) __nv_bfloat16 s_dy[32 * 64];
-  __shared__ __align__(32) __nv_bfloat16 s_t[32 * R];
+  constexpr int kChunk = 64;                       // tokens per step
+  constexpr int kTV = kChunk * R / 8 / 128;        // 16-byte vectors of t per thread per chunk (R = 16/32/64 -> 1/2/4)
+  __shared__ __align__(32) __nv_bfloat16 s_dy[kChunk * 64];
+  __shared__ __align__(32) __nv_bfloat16 s_t[kChunk * R];
   __shared__ __align__(32) float s_out[64 * R];
   const int n0 = blockIdx.x * 64;
   const int s_begin = blockIdx.y * rows_per_cta;
@@ -303,23 +321,39 @@ lora_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const __n
   wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[NR];
 #pragma unroll
   for (int j = 0; j < NR; ++j) wmma::fill_fragment(acc[j], 0.f);
-  for (int s0 = s_begin; s0 < s_end; s0 += 32) {
-    // stage [32 tokens][64 outputs] of dy and [32 tokens][R] of t; rows past the end and columns past n are zeros
-    for (int i = threadIdx.x; i < 32 * 8; i += 128) {
+  // register double buffer: the loads of chunk c+1 are in flight while chunk c is multiplied out of shared memory;
+  // rows past the end and columns past n are zeros
+  uint4 rdy[4], rt[kTV];
+  auto fetch = [&](int s0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + j * 128;
       const int r = i >> 3, c = (i & 7) * 8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (s0 + r < s_end && n0 + c < n) v = ldg_nc_v4(dy + static_cast<int64_t>(s0 + r) * ld_dy + n0 + c);
-      *reinterpret_cast<uint4*>(s_dy + r * 64 + c) = v;
+      rdy[j] = (s0 + r < s_end && n0 + c < n) ? ldg_nc_v4(dy + static_cast<int64_t>(s0 + r) * ld_dy + n0 + c) : make_uint4(0, 0, 0, 0);
     }
-    for (int i = threadIdx.x; i < 32 * (R / 8); i += 128) {
+#pragma unroll
+    for (int j = 0; j < kTV; ++j) {
+      const int i = threadIdx.x + j * 128;
       const int r = i / (R / 8), c = (i % (R / 8)) * 8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (s0 + r < s_end) v = ldg_nc_v4(t + static_cast<int64_t>(s0 + r) * ld_t + c);
-      *reinterpret_cast<uint4*>(s_t + r * R + c) = v;
+      rt[j] = (s0 + r < s_end) ? ldg_nc_v4(t + static_cast<int64_t>(s0 + r) * ld_t + c) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  fetch(s_begin);
+  for (int s0 = s_begin; s0 < s_end; s0 += kChunk) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + j * 128;
+      *reinterpret_cast<uint4*>(s_dy + (i >> 3) * 64 + (i & 7) * 8) = rdy[j];
+    }
+#pragma unroll
+    for (int j = 0; j < kTV; ++j) {
+      const int i = threadIdx.x + j * 128;
+      *reinterpret_cast<uint4*>(s_t + (i / (R / 8)) * R + (i % (R / 8)) * 8) = rt[j];
     }
     __syncthreads();
+    if (s0 + kChunk < s_end) fetch(s0 + kChunk);
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
+    for (int ks = 0; ks < kChunk / 16; ++ks) {
       wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa;  // A[n_i, s_k] = dy[s_k, n_i]
       wmma::load_matrix_sync(fa, s_dy + ks * 16 * 64 + warp * 16, 64);
 #pragma unroll
@@ -556,7 +590,8 @@ extern "C" int fgb_lora_wgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const
   // enough token chunks to fill the machine ~4x over; each chunk a multiple of 32 rows
   int splits = (4 * ctx->sm_count + n_tiles - 1) / n_tiles;
   int rows_per_cta = ((rows + splits - 1) / splits + 31) / 32 * 32;
-  if (rows_per_cta < 128) rows_per_cta = 128;
+  rows_per_cta = (rows_per_cta + 63) / 64 * 64;
+  if (rows_per_cta < 256) rows_per_cta = 256;
   splits = (rows + rows_per_cta - 1) / rows_per_cta;
   dim3 grid(n_tiles, splits);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--recompute", action="store_true", help="the reference's per-block checkpointing schedule")
+    ap.add_argument("--profile", action="store_true", help="print the per-kernel CUDA time of one step (torch.profiler / CUPTI)")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=832)
     ap.add_argument("--frames", type=int, default=49)
@@ -58,6 +59,12 @@ def main():
     for i in range(args.warmup):
         one(i)
     torch.cuda.synchronize()
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            one(99)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70), file=sys.stderr)
     if world > 1:
         dist.barrier()
     tr.kernel_launches = 0
