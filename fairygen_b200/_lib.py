@@ -25,6 +25,8 @@ SIGNATURES = {
     "fgb_sync_check": (ctypes.c_int, [_P, _P]),
     "fgb_sm_count": (ctypes.c_int, [_P]),
     "fgb_gemm_bf16": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
+    "fgb_gemm_bf16_ex": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _I64, _P, _I64, _I32, _P]),
+    "fgb_gemm_dgrad_ex": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _I64, _I32, _P]),
     "fgb_attn_fwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P]),
     "fgb_attn_fwd_ex": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _I64, _P, _I64, _P]),
     "fgb_attn_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64,

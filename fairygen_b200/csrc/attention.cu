@@ -203,7 +203,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t (&cur)[32] = buf[c];
-        if (c == 0) tmem_ld_wait_1(); else tmem_ld_wait();
+        if (c == 0) tmem_ld_wait();   // waits for both loads (tcgen05.wait::ld has no partial form)
 #pragma unroll
         for (int e = 0; e < 32; e += 2)
           mx[(e >> 1) & 3] = fmaxf(mx[(e >> 1) & 3], fmaxf(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])));

@@ -317,8 +317,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// tcgen05.wait::ld waits for ALL prior loads of the thread; there is no partial wait, the alias documents intent.
-__device__ __forceinline__ void tmem_ld_wait_1() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------

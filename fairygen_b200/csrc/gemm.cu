@@ -41,6 +41,7 @@ struct GemmParams {
   int32_t m, n, k;
   int32_t rows_gate0;
   int32_t m_blocks, n_blocks, tiles, k_blocks;
+  int32_t k2_blocks;   // extra K-blocks taken from the second operand pair (tmap_a2, tmap_b2): acc += A2 · W2ᵀ (or A2 · W2)
 };
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
@@ -68,7 +69,7 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 template <int EPI, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -86,6 +87,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.k2_blocks > 0) {
+      tma_prefetch_desc(&tmap_a2);
+      tma_prefetch_desc(&tmap_b2);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -110,17 +115,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(p, tile, m_blk, n_blk);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        const int k_total = p.k_blocks + p.k2_blocks;
+        for (int kb = 0; kb < k_total; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], kABytes + kBBytes);
-          tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full[stage], kb * kBK, m_blk * kBM, kEvictNormal);
+          // the last k2_blocks K-blocks come from the second operand pair (a rank-r LoRA term folded into the GEMM)
+          const bool second = kb >= p.k_blocks;
+          const CUtensorMap* ma = second ? &tmap_a2 : &tmap_a;
+          const CUtensorMap* mb = second ? &tmap_b2 : &tmap_b;
+          const int kc = (second ? kb - p.k_blocks : kb) * kBK;
+          tma_load_2d(smem_a + stage * kABytes, ma, &full[stage], kc, m_blk * kBM, kEvictNormal);
           if (B_MN) {
 #pragma unroll
             for (int b = 0; b < kBN / 64; ++b)
-              tma_load_2d(smem_b + stage * kBBytes + b * (kBK * 128), &tmap_b, &full[stage], n_blk * kBN + b * 64, kb * kBK,
-                          kEvictLast);
+              tma_load_2d(smem_b + stage * kBBytes + b * (kBK * 128), mb, &full[stage], n_blk * kBN + b * 64, kc, kEvictLast);
           } else {
-            tma_load_2d(smem_b + stage * kBBytes, &tmap_b, &full[stage], kb * kBK, n_blk * kBN, kEvictLast);
+            tma_load_2d(smem_b + stage * kBBytes, mb, &full[stage], kc, n_blk * kBN, kEvictLast);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -143,7 +153,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kBN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        const int k_total = p.k_blocks + p.k2_blocks;
+        for (int kb = 0; kb < k_total; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t adesc = a_desc0 + static_cast<uint64_t>((stage * kABytes) >> 4);
@@ -245,7 +256,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 template <int EPI, bool B_MN = false>
 static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const CUtensorMap* ta2 = nullptr, const CUtensorMap* tb2 = nullptr) {
   auto kfn = gemm_bf16_kernel<EPI, B_MN>;
   static bool configured = false;  // per template instance; attribute is sticky per function
   if (!configured) {
@@ -253,7 +264,7 @@ static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
     configured = true;
   }
   const int grid = p.tiles < ctx->sm_count ? p.tiles : ctx->sm_count;
-  kfn<<<grid, kGemmThreads, kGemmSmem, stream>>>(ta, tb, p);
+  kfn<<<grid, kGemmThreads, kGemmSmem, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, p);
   FGB_LAUNCH_CHECK("gemm_bf16_kernel");
   return FGB_OK;
 }
@@ -263,6 +274,14 @@ static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
 extern "C" int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias,
                              void* c, int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue,
                              const void* gate0, const void* gate1, int32_t rows_gate0, void* stream) {
+  return fgb_gemm_bf16_ex(ctx, a, lda, w, ldw, bias, c, ldc, m, n, k, epilogue, gate0, gate1, rows_gate0, nullptr, 0, nullptr, 0, 0,
+                          stream);
+}
+
+extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias,
+                                void* c, int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue, const void* gate0,
+                                const void* gate1, int32_t rows_gate0, const void* a2, int64_t lda2, const void* w2,
+                                int64_t ldw2, int32_t k2, void* stream) {
   using namespace fgb;
   FGB_CHECK_ARG(ctx, "fgb_gemm_bf16: ctx is NULL");
   FGB_CHECK_ARG(a && w && c, "fgb_gemm_bf16: NULL matrix pointer");
@@ -276,13 +295,19 @@ extern "C" int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const voi
     FGB_CHECK_ARG(gate0 && gate1 && aligned16(gate0) && aligned16(gate1),
                   "fgb_gemm_bf16: gated residual needs 16-byte aligned gate0/gate1");
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta2, tb2;
   int rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kBM);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(ctx, &tb, w, n, k, ldw, kBN);
   if (rc) return rc;
+  if (k2 > 0) {
+    FGB_CHECK_ARG(a2 && w2 && k2 % 8 == 0 && lda2 >= k2 && ldw2 >= k2, "fgb_gemm_bf16_ex: bad second operand pair (k2=%d)", k2);
+    if ((rc = make_tmap_bf16_2d(ctx, &ta2, a2, m, k2, lda2, kBM))) return rc;
+    if ((rc = make_tmap_bf16_2d(ctx, &tb2, w2, n, k2, ldw2, kBN))) return rc;
+  }
 
   GemmParams p;
+  p.k2_blocks = k2 > 0 ? (k2 + kBK - 1) / kBK : 0;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.c = static_cast<__nv_bfloat16*>(c);
   p.gate0 = static_cast<const __nv_bfloat16*>(gate0);
@@ -297,16 +322,24 @@ extern "C" int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const voi
   p.tiles = p.m_blocks * p.n_blocks;
   p.k_blocks = (k + kBK - 1) / kBK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const CUtensorMap* pa2 = k2 > 0 ? &ta2 : nullptr;
+  const CUtensorMap* pb2 = k2 > 0 ? &tb2 : nullptr;
   switch (epilogue) {
-    case FGB_EPI_BIAS: return launch_gemm<FGB_EPI_BIAS>(ctx, ta, tb, p, s);
-    case FGB_EPI_BIAS_GELU_TANH: return launch_gemm<FGB_EPI_BIAS_GELU_TANH>(ctx, ta, tb, p, s);
-    case FGB_EPI_GATED_RESIDUAL: return launch_gemm<FGB_EPI_GATED_RESIDUAL>(ctx, ta, tb, p, s);
-    default: return launch_gemm<FGB_EPI_RESIDUAL>(ctx, ta, tb, p, s);
+    case FGB_EPI_BIAS: return launch_gemm<FGB_EPI_BIAS>(ctx, ta, tb, p, s, pa2, pb2);
+    case FGB_EPI_BIAS_GELU_TANH: return launch_gemm<FGB_EPI_BIAS_GELU_TANH>(ctx, ta, tb, p, s, pa2, pb2);
+    case FGB_EPI_GATED_RESIDUAL: return launch_gemm<FGB_EPI_GATED_RESIDUAL>(ctx, ta, tb, p, s, pa2, pb2);
+    default: return launch_gemm<FGB_EPI_RESIDUAL>(ctx, ta, tb, p, s, pa2, pb2);
   }
 }
 
 extern "C" int fgb_gemm_dgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* w, int64_t ldw, void* dx, int64_t ld_dx,
                               int32_t m, int32_t n_in, int32_t k_out, void* stream) {
+  return fgb_gemm_dgrad_ex(ctx, dy, ld_dy, w, ldw, dx, ld_dx, m, n_in, k_out, nullptr, 0, nullptr, 0, 0, stream);
+}
+
+extern "C" int fgb_gemm_dgrad_ex(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* w, int64_t ldw, void* dx, int64_t ld_dx,
+                                 int32_t m, int32_t n_in, int32_t k_out, const void* u, int64_t ld_u, const void* a1, int64_t ld_a1,
+                                 int32_t k2, void* stream) {
   using namespace fgb;
   FGB_CHECK_ARG(ctx, "fgb_gemm_dgrad: ctx is NULL");
   FGB_CHECK_ARG(dy && w && dx, "fgb_gemm_dgrad: NULL matrix pointer");
@@ -314,12 +347,18 @@ extern "C" int fgb_gemm_dgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const
   FGB_CHECK_ARG(n_in % 8 == 0 && k_out % 8 == 0, "fgb_gemm_dgrad: n_in=%d and k_out=%d must be multiples of 8", n_in, k_out);
   FGB_CHECK_ARG(ld_dy >= k_out && ldw >= n_in && ld_dx >= n_in, "fgb_gemm_dgrad: leading dimension too small");
   FGB_CHECK_ARG(ld_dx % 8 == 0 && aligned16(dx), "fgb_gemm_dgrad: dx must be 16-byte aligned with ld_dx %% 8 == 0");
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta2, tb2;
   int rc = make_tmap_bf16_2d(ctx, &ta, dy, m, k_out, ld_dy, kBM);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(ctx, &tb, w, k_out, n_in, ldw, kBK);   // box = [64 k-rows][64 n-cols]
   if (rc) return rc;
+  if (k2 > 0) {
+    FGB_CHECK_ARG(u && a1 && k2 % 8 == 0 && ld_u >= k2 && ld_a1 >= n_in, "fgb_gemm_dgrad_ex: bad second operand pair (k2=%d)", k2);
+    if ((rc = make_tmap_bf16_2d(ctx, &ta2, u, m, k2, ld_u, kBM))) return rc;
+    if ((rc = make_tmap_bf16_2d(ctx, &tb2, a1, k2, n_in, ld_a1, kBK))) return rc;
+  }
   GemmParams p;
+  p.k2_blocks = k2 > 0 ? (k2 + kBK - 1) / kBK : 0;
   p.bias = nullptr;
   p.c = static_cast<__nv_bfloat16*>(dx);
   p.gate0 = p.gate1 = nullptr;
@@ -332,5 +371,6 @@ extern "C" int fgb_gemm_dgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const
   p.n_blocks = (n_in + kBN - 1) / kBN;
   p.tiles = p.m_blocks * p.n_blocks;
   p.k_blocks = (k_out + kBK - 1) / kBK;
-  return launch_gemm<FGB_EPI_BIAS, true>(ctx, ta, tb, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm<FGB_EPI_BIAS, true>(ctx, ta, tb, p, static_cast<cudaStream_t>(stream), k2 > 0 ? &ta2 : nullptr,
+                                         k2 > 0 ? &tb2 : nullptr);
 }

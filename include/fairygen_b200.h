@@ -68,6 +68,13 @@ int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64
                   void* c, int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue,
                   const void* gate0, const void* gate1, int32_t rows_gate0, void* stream);
 
+/* Same with a second operand pair folded in as extra K-blocks:  acc = A·Wᵀ + A2·W2ᵀ  (a2 [m, k2], w2 [n, k2], k2 % 8 == 0).
+ * Used by the stage-2 LoRA forward (training_module.py:317-352): y = W₁x + b + (B2*mask*2)(A1 x) without re-merging the
+ * weight every step — A2 = A1·x (rank r), W2 = the masked B2. */
+int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c,
+                     int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue, const void* gate0, const void* gate1,
+                     int32_t rows_gate0, const void* a2, int64_t lda2, const void* w2, int64_t ldw2, int32_t k2, void* stream);
+
 /* o = softmax(q kᵀ · scale) v per head, no mask, non-causal; head_dim = 128.
  * q,o: [s_q, heads*128]; k,v: [s_kv, heads*128] (row strides ldq/ldk/ldv/ldo elements).
  * Replaces flash_attention()/AttentionModule for self- and cross-attention (DIT:27-60, 113-120,
@@ -205,6 +212,11 @@ int fgb_attn_fwd_scatter(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
  * full-rank wgrad on this path (TMOD:279-307). */
 int fgb_gemm_dgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* w, int64_t ldw, void* dx, int64_t ld_dx,
                    int32_t m, int32_t n_in, int32_t k_out, void* stream);
+
+/* Same plus a rank-r term as extra K-blocks: dx = dy·W + u·A1  (u [m, k2] = dy·B2eff, a1 [k2, n_in] row-major). */
+int fgb_gemm_dgrad_ex(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* w, int64_t ldw, void* dx, int64_t ld_dx,
+                      int32_t m, int32_t n_in, int32_t k_out, const void* u, int64_t ld_u, const void* a1, int64_t ld_a1,
+                      int32_t k2, void* stream);
 
 /* Backward of fgb_ln_modulate (affine = 0: g = 1 + scale row, rows < rows_mod0 use g0 else g1) or fgb_ln_affine
  * (affine = 1: g0 = weight): out = dres + LN'(x)ᵀ(dy * g). dres may be NULL, and may alias out. */

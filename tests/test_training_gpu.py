@@ -286,3 +286,28 @@ def test_real_dims_training_step(env):
     worst = max(rel_l2(tr.grad[n], grads_ref[n]) for n in tr.targets)
     print(f"real dims: pred {rel_l2(pred, pred_ref):.3e} loss {float(loss):.6f} vs {float(loss_ref):.6f} worst grad rel-L2 {worst:.3e}")
     assert worst < 5e-2
+
+
+def test_training_entry_points_reject_bad_arguments(env):
+    """Error convention of the C ABI (status code + fgb_last_error -> RuntimeError / ValueError in the shim), no crashes."""
+    _, ops, _, _ = env
+    q = rnd(100, 128, seed=1)
+    out, dq = torch.empty_like(q), torch.empty_like(q)
+    lse_bad = torch.zeros(1, 100, dtype=torch.float32, device="cuda")          # stride not a multiple of 64
+    with pytest.raises(ValueError):
+        ops.attention(q, q, q, out, 1, lse=lse_bad)
+    with pytest.raises(ValueError):
+        ops.attention_bwd(q, q, q, out, out, lse_bad, dq, dq.clone(), dq.clone(), 1)
+    with pytest.raises(ValueError):
+        ops.gemm_dgrad(rnd(8, 64), rnd(32, 64), torch.empty(8, 64, dtype=BF, device="cuda"))     # dy cols != w rows
+    with pytest.raises(RuntimeError, match="must divide by 64"):
+        ops.lora_merge(rnd(100, 256), rnd(32, 256), rnd(100, 32), None, None, torch.empty(100, 256, dtype=BF, device="cuda"))
+    with pytest.raises(RuntimeError, match="rank"):
+        ops.lora_merge(rnd(128, 256), rnd(24, 256), rnd(128, 24), None, None, torch.empty(128, 256, dtype=BF, device="cuda"))
+    with pytest.raises(ValueError):
+        ops.lora_wgrad(rnd(64, 128), rnd(32, 32), torch.zeros(128, 32, device="cuda"))            # token counts differ
+    with pytest.raises(RuntimeError, match="multiple of 256"):
+        ops.ln_bwd(rnd(8, 100), rnd(8, 100), torch.empty(8, 100, dtype=BF, device="cuda"), 1e-6, rnd(100))
+    with pytest.raises(ValueError):
+        ops.gelu_tanh(rnd(8, 16), torch.empty(8, 8, dtype=BF, device="cuda"))
+    ops.sync_check()   # none of the rejected calls launched anything
