@@ -378,6 +378,16 @@ lora_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const __n
   }
 }
 
+// B2eff[n, r] = bf16(bf16(bf16(B2 * mask) * mask_mul) * scaling) into a (possibly strided, e.g. block-diagonal) view
+__global__ void lora_b2_eff_kernel(const __nv_bfloat16* __restrict__ b2, const uint8_t* __restrict__ mask, float mask_mul,
+                                   float scaling, __nv_bfloat16* __restrict__ out, int64_t ld_out, int64_t n_rows, int rank) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_rows * rank) return;
+  const float m = mask ? static_cast<float>(mask[i]) : 1.0f;
+  const float v = round_bf16(round_bf16(__bfloat162float(b2[i]) * m) * mask_mul);
+  out[(i / rank) * ld_out + (i % rank)] = __float2bfloat16_rn(v * scaling);
+}
+
 // counter-based Bernoulli mask: keep[i] = hash(seed, i) / 2^32 > drop_prob   (torch.rand_like(...) > p, TMOD:342)
 __global__ void bernoulli_mask_kernel(uint8_t* __restrict__ out, int64_t n, float drop_prob, uint64_t seed) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -652,5 +662,14 @@ extern "C" int fgb_adamw_step(fgb_ctx* ctx, void* param_bf16, const void* grad_f
       static_cast<bf16*>(param_bf16), static_cast<const float*>(grad_f32), static_cast<float*>(m_f32), static_cast<float*>(v_f32), n, lr,
       beta1, beta2, eps, weight_decay, bc1, bc2);
   FGB_LAUNCH_CHECK("adamw_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_lora_b2_eff(fgb_ctx* ctx, const void* b2, const void* mask, float mask_mul, float scaling, void* out,
+                               int64_t ld_out, int64_t n_rows, int32_t rank, void* stream) {
+  FGB_CHECK_ARG(ctx && b2 && out && n_rows > 0 && rank > 0 && ld_out >= rank, "fgb_lora_b2_eff: bad argument");
+  lora_b2_eff_kernel<<<static_cast<unsigned>((n_rows * rank + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(b2), static_cast<const uint8_t*>(mask), mask_mul, scaling, static_cast<bf16*>(out), ld_out, n_rows, rank);
+  FGB_LAUNCH_CHECK("lora_b2_eff_kernel");
   return FGB_OK;
 }

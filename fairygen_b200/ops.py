@@ -55,8 +55,8 @@ def _vec(t: Optional[torch.Tensor], n: int, what: str) -> None:
         raise ValueError(f"{what}: expected a contiguous bf16 vector of {n} elements")
 
 
-def gemm(a, w, bias, out, epilogue=EPI_BIAS, gate0=None, gate1=None, rows_gate0=0):
-    """out[m,n] = epilogue(a[m,k] @ w[n,k].T + bias); see fgb_gemm_bf16."""
+def gemm(a, w, bias, out, epilogue=EPI_BIAS, gate0=None, gate1=None, rows_gate0=0, a2=None, w2=None):
+    """out[m,n] = epilogue(a[m,k] @ w[n,k].T (+ a2[m,k2] @ w2[n,k2].T) + bias); see fgb_gemm_bf16 / fgb_gemm_bf16_ex."""
     lda, ldw, ldc = _rowmajor(a, "a"), _rowmajor(w, "w"), _rowmajor(out, "out")
     m, k = a.shape
     n = w.shape[0]
@@ -64,8 +64,15 @@ def gemm(a, w, bias, out, epilogue=EPI_BIAS, gate0=None, gate1=None, rows_gate0=
         raise ValueError(f"gemm shape mismatch: a {tuple(a.shape)} w {tuple(w.shape)} out {tuple(out.shape)}")
     _vec(bias, n, "bias"), _vec(gate0, n, "gate0"), _vec(gate1, n, "gate1")
     c = _h(a)
-    _lib.check(_lib.lib().fgb_gemm_bf16(c.handle, _p(a), lda, _p(w), ldw, _p(bias), _p(out), ldc, m, n, k, epilogue,
-                                        _p(gate0), _p(gate1), rows_gate0, _stream()), "fgb_gemm_bf16")
+    if a2 is None and w2 is None:
+        _lib.check(_lib.lib().fgb_gemm_bf16(c.handle, _p(a), lda, _p(w), ldw, _p(bias), _p(out), ldc, m, n, k, epilogue,
+                                            _p(gate0), _p(gate1), rows_gate0, _stream()), "fgb_gemm_bf16")
+        return out
+    if a2 is None or w2 is None or a2.shape[0] != m or w2.shape[0] != n or a2.shape[1] != w2.shape[1]:
+        raise ValueError("gemm: the second operand pair must be a2 [m, k2] and w2 [n, k2]")
+    _lib.check(_lib.lib().fgb_gemm_bf16_ex(c.handle, _p(a), lda, _p(w), ldw, _p(bias), _p(out), ldc, m, n, k, epilogue, _p(gate0), _p(gate1),
+                                           rows_gate0, _p(a2), _rowmajor(a2, "a2"), _p(w2), _rowmajor(w2, "w2"), a2.shape[1], _stream()),
+               "fgb_gemm_bf16_ex")
     return out
 
 
@@ -344,15 +351,21 @@ def sync_check(device=None):
 # ---------------------------------------------------------------------------------------------------------
 # training kernels (BASELINE config 5; see include/fairygen_b200.h "training")
 # ---------------------------------------------------------------------------------------------------------
-def gemm_dgrad(dy, w, dx):
-    """dx[m, in] = dy[m, out] @ w[out, in]  (input gradient of nn.Linear, W as stored)."""
+def gemm_dgrad(dy, w, dx, u=None, a1=None):
+    """dx[m, in] = dy[m, out] @ w[out, in] (+ u[m, r] @ a1[r, in])  — input gradient of nn.Linear, W as stored."""
     ld_dy, ldw, ld_dx = _rowmajor(dy, "dy"), _rowmajor(w, "w"), _rowmajor(dx, "dx")
     m, k_out = dy.shape
     n_in = w.shape[1]
     if w.shape[0] != k_out or tuple(dx.shape) != (m, n_in):
         raise ValueError(f"gemm_dgrad shape mismatch: dy {tuple(dy.shape)} w {tuple(w.shape)} dx {tuple(dx.shape)}")
     c = _h(dy)
-    _lib.check(_lib.lib().fgb_gemm_dgrad(c.handle, _p(dy), ld_dy, _p(w), ldw, _p(dx), ld_dx, m, n_in, k_out, _stream()), "fgb_gemm_dgrad")
+    if u is None and a1 is None:
+        _lib.check(_lib.lib().fgb_gemm_dgrad(c.handle, _p(dy), ld_dy, _p(w), ldw, _p(dx), ld_dx, m, n_in, k_out, _stream()), "fgb_gemm_dgrad")
+        return dx
+    if u is None or a1 is None or u.shape[0] != m or a1.shape[1] != n_in or u.shape[1] != a1.shape[0]:
+        raise ValueError("gemm_dgrad: the low-rank term must be u [m, r] and a1 [r, in]")
+    _lib.check(_lib.lib().fgb_gemm_dgrad_ex(c.handle, _p(dy), ld_dy, _p(w), ldw, _p(dx), ld_dx, m, n_in, k_out, _p(u), _rowmajor(u, "u"),
+                                            _p(a1), _rowmajor(a1, "a1"), u.shape[1], _stream()), "fgb_gemm_dgrad_ex")
     return dx
 
 
@@ -420,6 +433,18 @@ def lora_merge(w, a1, b1, b2, mask, w_eff, mask_mul=2.0, scaling=1.0):
     _lib.check(_lib.lib().fgb_lora_merge(_h(w).handle, _p(w), _rowmajor(w, "w"), _p(a1), _rowmajor(a1, "a1"), _p(b1), _p(b2), _p(mask),
                                          mask_mul, scaling, _p(w_eff), _rowmajor(w_eff, "w_eff"), n, k, r, _stream()), "fgb_lora_merge")
     return w_eff
+
+
+def lora_b2_eff(b2, mask, out, mask_mul=2.0, scaling=1.0):
+    """out (view with contiguous last dim, e.g. a diagonal block) = scaling * bf16(bf16(b2 * mask) * mask_mul)."""
+    n, r = b2.shape
+    if b2.dtype != BF16 or not b2.is_contiguous() or tuple(out.shape) != (n, r) or out.dtype != BF16 or out.stride(1) != 1:
+        raise ValueError("lora_b2_eff: b2 contiguous bf16 [n, r], out a bf16 [n, r] view")
+    if mask is not None and (mask.dtype != torch.uint8 or tuple(mask.shape) != (n, r) or not mask.is_contiguous()):
+        raise ValueError("lora_b2_eff: mask must be contiguous uint8 [n, r]")
+    _lib.check(_lib.lib().fgb_lora_b2_eff(_h(b2).handle, _p(b2), _p(mask), mask_mul, scaling, _p(out), out.stride(0), n, r, _stream()),
+               "fgb_lora_b2_eff")
+    return out
 
 
 def lora_wgrad(dy, t, db, mask=None, mul=1.0):

@@ -6,10 +6,12 @@ Linear and monkey-patches the stage-2 forward (diffusion/training_module.py:266-
 (diffusion/loss.py:5-21, LOSS) noises the latents, calls ``pipe.model_fn`` under autograd and back-propagates the
 weighted MSE; each DiTBlock is re-computed in backward (pipelines/wan_video.py:1348-1360).
 
-Here, per step:
-  * ``fgb_lora_merge`` folds the step's LoRA (B1 + B2*mask*2)A1 into one effective bf16 weight per Linear, so the
-    forward GEMMs and the dgrad GEMMs are the SAME tcgen05 kernels as inference (``fgb_gemm_bf16`` /
-    ``fgb_gemm_dgrad``) — the adapters cost a rank-32 side GEMM ``t = A1 x`` that the B2 gradient needs anyway;
+Here:
+  * the frozen stage-1 adapter is folded once into W₁ = W + s·B1·A1 (``fgb_lora_merge``); the trainable term
+    s·(B2*mask*2)(A1 x) rides along as ONE extra 64-wide K-block of the same tcgen05 GEMM (``fgb_gemm_bf16_ex``:
+    second operand pair A2 = t = A1 x, W2 = masked B2), and in the backward as dX = dY·W₁ + (dY·B2eff)·A1
+    (``fgb_gemm_dgrad_ex``) — no 10 GB weight re-merge per step, and the rank-32 side GEMM ``t = A1 x`` is the
+    activation the B2 gradient needs anyway;
   * the forward keeps every block's activations (23 GB at 480x832x49; B200 has 180 GB), so nothing is re-computed
     unless ``recompute=True`` asks for the reference's checkpointing schedule;
   * the backward is hand-written: ``fgb_attn_bwd`` (tensor cores), ``fgb_gemm_dgrad``, fused LN / RMSNorm+RoPE /
@@ -95,10 +97,16 @@ class Stage2Trainer:
             self.grad[t] = self.grad_flat[off:off + n].view(-1, rank)
             self.mask[t] = self._mask_flat[off:off + n].view(-1, rank)
             off += n
-        # ---- per-step effective weights (same layouts as the engine's packed base weights) ------------------------
+        # ---- W1 = W + s*B1*A1 (static; same layouts as the engine's packed base weights) and the per-step masked B2
+        #      operands of the GEMM K-extension (block-diagonal for the fused q|k|v and cross k|v GEMMs)
         e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
+        z = lambda *s: torch.zeros(*s, dtype=BF16, device=dev)  # noqa: E731
+        r = rank
         self.eff = [dict(wqkv=e(3 * d, d), wo=e(d, d), cwq=e(d, d), cwkv=e(2 * d, d), cwo=e(d, d), w1=e(f, d), w2=e(d, f))
                     for _ in range(cfg.num_layers)]
+        self.b2e = [dict(qkv=z(3 * d, 3 * r), o=z(d, r), cq=z(d, r), ckv=z(2 * d, 2 * r), co=z(d, r), f1=z(f, r), f2=z(d, r))
+                    for _ in range(cfg.num_layers)]
+        self._merge_static()
         self.scheduler = FlowMatchScheduler("Wan")
         self.scheduler.set_timesteps(1000, training=True)                               # train.py / LOSS:6-9
         self._saved: List[Optional[_Saved]] = []
@@ -130,8 +138,8 @@ class Stage2Trainer:
     def zero_grad(self) -> None:
         self.grad_flat.zero_()
 
-    def merge(self) -> None:
-        """W_eff = W + s (B1 + B2*mask*2) A1 for all 300 Linears (row slices of the fused QKV / cross-KV weights)."""
+    def _merge_static(self) -> None:
+        """W1 = W + s * B1 * A1 for all 300 Linears (row slices of the fused QKV / cross-KV weights) — once."""
         d = self.cfg.dim
         for i, (b, eff) in enumerate(zip(self.engine.blocks, self.eff)):
             p = f"blocks.{i}."
@@ -146,7 +154,25 @@ class Stage2Trainer:
             self._merge_one(b.w2, eff["w2"], p + "ffn.2")
 
     def _merge_one(self, w, w_eff, name) -> None:
-        ops.lora_merge(w, self.a1[name], self.b1[name], self.b2[name], self.mask[name], w_eff, self.mask_mul, self.scaling)
+        ops.lora_merge(w, self.a1[name], self.b1[name], None, None, w_eff, 1.0, self.scaling)
+
+    def merge(self) -> None:
+        """Per step: B2eff = s * bf16(bf16(B2 * mask) * 2) (TMOD:343-346) into the K-extension operands."""
+        d, r = self.cfg.dim, self.rank
+        for i, be in enumerate(self.b2e):
+            p = f"blocks.{i}."
+            for j, proj in enumerate("qkv"):
+                self._b2_eff(p + "self_attn." + proj, be["qkv"][j * d:(j + 1) * d, j * r:(j + 1) * r])
+            self._b2_eff(p + "self_attn.o", be["o"])
+            self._b2_eff(p + "cross_attn.q", be["cq"])
+            for j, proj in enumerate("kv"):
+                self._b2_eff(p + "cross_attn." + proj, be["ckv"][j * d:(j + 1) * d, j * r:(j + 1) * r])
+            self._b2_eff(p + "cross_attn.o", be["co"])
+            self._b2_eff(p + "ffn.0", be["f1"])
+            self._b2_eff(p + "ffn.2", be["f2"])
+
+    def _b2_eff(self, name, out) -> None:
+        ops.lora_b2_eff(self.b2[name], self.mask[name], out, self.mask_mul, self.scaling)
         self.kernel_launches += 1
 
     # ------------------------------------------------------------------------------------------------------------
@@ -178,7 +204,7 @@ class Stage2Trainer:
             self._x_ckpt = [e(rows, d) for _ in range(cfg.num_layers)] if self.recompute else None
             self._scratch = dict(dx=e(rows, d), t1=e(rows, d), t2=e(rows, d), dqkv=e(rows, 3 * d), dh=e(rows, f), dckv=e(n_ctx, 2 * d),
                                  delta=torch.empty(H, ops.stat_rows(rows), dtype=torch.float32, device=dev), x=e(rows, d),
-                                 x_final=e(rows, d), a_head=e(rows, d), d_hrow=e(rows, cfg.out_dim * 4))
+                                 x_final=e(rows, d), a_head=e(rows, d), d_hrow=e(rows, cfg.out_dim * 4), u=e(rows, 3 * self.rank))
             self._shape_key = key
         return self._scratch
 
@@ -194,36 +220,37 @@ class Stage2Trainer:
         d, H = cfg.dim, cfg.num_heads
         b, w = eng.blocks[i], self.eff[i]
         m0, m1, n_first, grid, ctx_emb = st["m0"][i], st["m1"][i], st["n_first"], st["grid"], st["ctx_emb"]
+        be = self.b2e[i]
         s.x_in.copy_(x)
         ops.ln_modulate(x, s.a1, cfg.eps, m0[0], m0[1], m1[0], m1[1], n_first)
-        ops.gemm(s.a1, w["wqkv"], b.bqkv, s.qkv)
         ops.gemm(s.a1, self.a1_qkv[i], None, s.t_qkv)
+        ops.gemm(s.a1, w["wqkv"], b.bqkv, s.qkv, a2=s.t_qkv, w2=be["qkv"])
         s.qk_pre.copy_(s.qkv[:, :2 * d])
         ops.rmsnorm_rope(s.qkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, 0)
         ops.rmsnorm_rope(s.qkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, 0)
         ops.attention(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, H, lse=s.lse)
         ops.gemm(s.o, self.a1[f"blocks.{i}.self_attn.o"], None, s.t_o)
-        ops.gemm(s.o, w["wo"], b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first)
+        ops.gemm(s.o, w["wo"], b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first, a2=s.t_o, w2=be["o"])
         s.x1.copy_(x)
         ops.ln_affine(x, s.a2, cfg.eps, b.n3w, b.n3b)
-        ops.gemm(s.a2, w["cwq"], b.cbq, s.cq)
         ops.gemm(s.a2, self.a1[f"blocks.{i}.cross_attn.q"], None, s.t_cq)
+        ops.gemm(s.a2, w["cwq"], b.cbq, s.cq, a2=s.t_cq, w2=be["cq"])
         s.cq_pre.copy_(s.cq)
         ops.rmsnorm_rope(s.cq, cfg.eps, b.cnq)
-        ops.gemm(ctx_emb, w["cwkv"], b.cbkv, s.ckv)
         ops.gemm(ctx_emb, self.a1_ckv[i], None, s.t_ckv)
+        ops.gemm(ctx_emb, w["cwkv"], b.cbkv, s.ckv, a2=s.t_ckv, w2=be["ckv"])
         s.ck_pre.copy_(s.ckv[:, :d])
         ops.rmsnorm_rope(s.ckv[:, :d], cfg.eps, b.cnk)
         ops.attention(s.cq, s.ckv[:, :d], s.ckv[:, d:], s.co, H, lse=s.lse_c)
         ops.gemm(s.co, self.a1[f"blocks.{i}.cross_attn.o"], None, s.t_co)
-        ops.gemm(s.co, w["cwo"], b.cbo, x, EPI_RESIDUAL)
+        ops.gemm(s.co, w["cwo"], b.cbo, x, EPI_RESIDUAL, a2=s.t_co, w2=be["co"])
         s.x2.copy_(x)
         ops.ln_modulate(x, s.a3, cfg.eps, m0[3], m0[4], m1[3], m1[4], n_first)
-        ops.gemm(s.a3, w["w1"], b.b1, s.z1, EPI_BIAS)
         ops.gemm(s.a3, self.a1[f"blocks.{i}.ffn.0"], None, s.t_1)
+        ops.gemm(s.a3, w["w1"], b.b1, s.z1, EPI_BIAS, a2=s.t_1, w2=be["f1"])
         ops.gelu_tanh(s.z1, s.h)
         ops.gemm(s.h, self.a1[f"blocks.{i}.ffn.2"], None, s.t_2)
-        ops.gemm(s.h, w["w2"], b.b2, x, EPI_GATED_RESIDUAL, m0[5], m1[5], n_first)
+        ops.gemm(s.h, w["w2"], b.b2, x, EPI_GATED_RESIDUAL, m0[5], m1[5], n_first, a2=s.t_2, w2=be["f2"])
         self.kernel_launches += 25
 
     def forward_train(self, latents: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor,
@@ -267,6 +294,14 @@ class Stage2Trainer:
     # ------------------------------------------------------------------------------------------------------------
     # backward
     # ------------------------------------------------------------------------------------------------------------
+    def _dgrad(self, dy, w1, b2e, a1, dx) -> None:
+        """dX = dY·W1 + (dY·B2eff)·A1: the rank-r factor u = dY·B2eff first (one narrow dgrad), then the main dgrad with u·A1
+        folded in as an extra K-block."""
+        u = self._scratch["u"][:, :b2e.shape[1]]
+        ops.gemm_dgrad(dy, b2e, u)
+        ops.gemm_dgrad(dy, w1, dx, u=u, a1=a1)
+        self.kernel_launches += 1
+
     def _wgrad(self, dy, t, name) -> None:
         ops.lora_wgrad(dy, t, self.grad[name], self.mask[name], self.mask_mul * self.scaling)
         self.kernel_launches += 1
@@ -279,36 +314,37 @@ class Stage2Trainer:
         m0, m1, n_first, grid = st["m0"][i], st["m1"][i], st["n_first"], st["grid"]
         dx, t1, t2, dqkv, dh, dckv, delta = sc["dx"], sc["t1"], sc["t2"], sc["dqkv"], sc["dh"], sc["dckv"], sc["delta"]
         p = f"blocks.{i}."
+        be = self.b2e[i]
         # ---- feed-forward branch: x3 = x2 + gate_mlp * ffn2(gelu(ffn0(a3)))                       (DIT:227-228)
         ops.mul_gate(dx, t1, m0[5], m1[5], n_first)
         self._wgrad(t1, s.t_2, p + "ffn.2")
-        ops.gemm_dgrad(t1, w["w2"], dh)
+        self._dgrad(t1, w["w2"], be["f2"], self.a1[p + "ffn.2"], dh)
         ops.gelu_tanh_bwd(s.z1, dh, dh)
         self._wgrad(dh, s.t_1, p + "ffn.0")
-        ops.gemm_dgrad(dh, w["w1"], t1)
+        self._dgrad(dh, w["w1"], be["f1"], self.a1[p + "ffn.0"], t1)
         ops.ln_bwd(s.x2, t1, dx, cfg.eps, m0[4], m1[4], n_first, affine=False, dres=dx)
         # ---- cross-attention branch: x2 = x1 + o(attn(norm_q(q(a2)), norm_k(k(ctx)), v(ctx)))      (DIT:226)
         self._wgrad(dx, s.t_co, p + "cross_attn.o")
-        ops.gemm_dgrad(dx, w["cwo"], t1)
+        self._dgrad(dx, w["cwo"], be["co"], self.a1[p + "cross_attn.o"], t1)
         ops.attention_bwd(s.cq, s.ckv[:, :d], s.ckv[:, d:], s.co, t1, s.lse_c, t2, dckv[:, :d], dckv[:, d:], H, delta=delta)
         ops.rmsnorm_rope_bwd(s.cq_pre, t2, cfg.eps, b.cnq)
         ops.rmsnorm_rope_bwd(s.ck_pre, dckv[:, :d], cfg.eps, b.cnk)
         self._wgrad(t2, s.t_cq, p + "cross_attn.q")
         self._wgrad(dckv[:, :d], s.t_ckv[:, :r], p + "cross_attn.k")
         self._wgrad(dckv[:, d:], s.t_ckv[:, r:], p + "cross_attn.v")
-        ops.gemm_dgrad(t2, w["cwq"], t1)
+        self._dgrad(t2, w["cwq"], be["cq"], self.a1[p + "cross_attn.q"], t1)
         ops.ln_bwd(s.x1, t1, dx, cfg.eps, b.n3w, None, 0, affine=True, dres=dx)
         # ---- self-attention branch: x1 = x0 + gate_msa * o(attn(rope(norm_q(q(a1))), ...))        (DIT:224-225)
         ops.mul_gate(dx, t1, m0[2], m1[2], n_first)
         self._wgrad(t1, s.t_o, p + "self_attn.o")
-        ops.gemm_dgrad(t1, w["wo"], t2)
+        self._dgrad(t1, w["wo"], be["o"], self.a1[p + "self_attn.o"], t2)
         ops.attention_bwd(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, t2, s.lse, dqkv[:, :d], dqkv[:, d:2 * d],
                           dqkv[:, 2 * d:], H, delta=delta)
         ops.rmsnorm_rope_bwd(s.qk_pre[:, :d], dqkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, 0)
         ops.rmsnorm_rope_bwd(s.qk_pre[:, d:], dqkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, 0)
         for j, proj in enumerate("qkv"):
             self._wgrad(dqkv[:, j * d:(j + 1) * d], s.t_qkv[:, j * r:(j + 1) * r], p + "self_attn." + proj)
-        ops.gemm_dgrad(dqkv, w["wqkv"], t1)
+        self._dgrad(dqkv, w["wqkv"], be["qkv"], self.a1_qkv[i], t1)
         ops.ln_bwd(s.x_in, t1, dx, cfg.eps, m0[1], m1[1], n_first, affine=False, dres=dx)
         self.kernel_launches += 20
 

@@ -243,6 +243,11 @@ int fgb_lora_merge(fgb_ctx* ctx, const void* w, int64_t ldw, const void* a1, int
                    const void* mask, float mask_mul, float scaling, void* w_eff, int64_t ld_eff, int32_t n, int32_t k,
                    int32_t rank, void* stream);
 
+/* out[n, r] = scaling * bf16(bf16(B2[n,r]*mask[n,r]) * mask_mul) (TMOD:343-346) into a view with row stride ld_out — the W2
+ * operand of fgb_gemm_bf16_ex / the k_out x r matrix of the `u = dy·B2eff` dgrad (block-diagonal for the fused q|k|v GEMM). */
+int fgb_lora_b2_eff(fgb_ctx* ctx, const void* b2, const void* mask, float mask_mul, float scaling, void* out, int64_t ld_out,
+                    int64_t n_rows, int32_t rank, void* stream);
+
 /* db[n, r] += mul * mask[n, r] * sum_s dy[s, n] * t[s, r]   (fp32 accumulate; t = A1·x, [rows, rank] bf16). */
 int fgb_lora_wgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* t, int64_t ld_t, void* db_f32, const void* mask,
                    float mul, int32_t rows, int32_t n, int32_t rank, void* stream);
