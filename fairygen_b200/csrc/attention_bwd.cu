@@ -16,7 +16,9 @@
 //                 dV += Pᵀ·dO and dK += dSᵀ·Q (B = the same dO / Q smem tiles read MN-major). No smem round trip.
 //   kDKV = false  CTA = (128 queries, head): Q and dO resident, K/V streamed 64 keys at a time; S = Q·Kᵀ,
 //                 dP = dO·Vᵀ, dS (TMEM, bf16) is the A operand of dQ += dS·K. L and Δ are per-thread scalars.
-// Warp roles (192 threads): warps 0-3 softmax/epilogue (TMEM lane quarter = warp), warp 4 MMA issuer, warp 5 TMA.
+// Warp roles (320 threads): warps 0-3 / 4-7 softmax + epilogue for score columns [0,32) / [32,64) of every streamed
+// sub-tile (TMEM lane quarter = warp % 4; two warps per SM sub-partition hide each other's MUFU / TMEM latencies — no
+// row statistics are exchanged in the backward, L and Δ come from the forward), warp 8 MMA issuer, warp 9 TMA.
 // The two score blocks are double-buffered in TMEM, so the MMAs of sub-tile i+1 run under the softmax of i.
 // TMEM: [S|dP] x 2 buffers (256 columns), accumulators dV (128) and dK or dQ (128).
 // Out-of-range rows need no masks: TMA zero-fills them, so they contribute exact zeros to every product.
@@ -25,7 +27,8 @@
 
 namespace fgb {
 
-constexpr int kBwdThreads = 192;
+constexpr int kBwdThreads = 320;   // warps 0-7 softmax / epilogue, warp 8 MMA issuer, warp 9 TMA producer
+constexpr int kBwdMmaWarp = 8, kBwdTmaWarp = 9;
 constexpr int kRes = 128;                       // resident rows per CTA
 constexpr int kSub = 64;                        // streamed rows per step
 constexpr int kResBox = kRes * 64 * 2;          // 16 KB: [128 rows][64 cols] box
@@ -88,7 +91,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_consta
   const int r0 = blockIdx.x * kRes;
   const int n_sub = (p.rows_str + kSub - 1) / kSub;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == kBwdTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_r1);
     tma_prefetch_desc(&tmap_r2);
     tma_prefetch_desc(&tmap_t1);
@@ -100,19 +103,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
+      mbar_init(&p_ready[i], 256);
     }
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<512>(tmem_slot);
+  if (warp == kBwdMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // TMEM columns: buffer b: scores at b*128 + [0,64), dP at b*128 + [64,128); acc0 (dV) at 256; acc1 (dK / dQ) at 384.
 
-  if (warp == 5) {
+  if (warp == kBwdTmaWarp) {
     if (elect_one()) {
       // ------------------------------- TMA producer -------------------------------
       mbar_expect_tx(res_full, 2 * kResBytes);
@@ -137,7 +140,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_consta
         if (++st == kBwdStages) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kBwdMmaWarp) {
     if (elect_one()) {
       // ------------------------------- MMA issuer ---------------------------------
       constexpr uint32_t idesc_s = make_idesc_bf16(128, kSub, 0, 0);    // resident (K-major) x streamed (K-major), N = 64
@@ -197,6 +200,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_consta
   } else {
     // ------------------------------ softmax / epilogue warps ------------------------------
     const int quarter = warp & 3;
+    const int wg = warp >> 2;        // 32-column half of every 64-column sub-tile handled by this warpgroup
     const int r_local = quarter * 32 + lane;
     const int row = r0 + r_local;
     const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
@@ -216,8 +220,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_consta
       mbar_wait(&s_full[buf], (i >> 1) & 1);
       tc_fence_after();
       const float* stat = smem_stat + st * 2 * kSub;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {  // 32 score columns at a time
+      {
+        const int c = wg;              // this warpgroup's 32 score columns
         uint32_t s[32], dp[32], pk[16], dk[16];
         tmem_ld32(t_s + c * 32, s);
         tmem_ld32(t_s + 64 + c * 32, dp);
@@ -270,7 +274,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_consta
     auto store_acc = [&](uint32_t tcol, __nv_bfloat16* out, int64_t ld, float mul) {
       __nv_bfloat16* orow = out + static_cast<int64_t>(row) * ld + head * 128;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * wg; c < 2 * wg + 2; ++c) {   // each warpgroup stores 64 of the 128 output columns
         uint32_t a[32];
         tmem_ld32(tmem_base + lane_bits + tcol + c * 32, a);
         tmem_ld_wait();
@@ -293,7 +297,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kBwdMmaWarp) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
