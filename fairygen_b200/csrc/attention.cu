@@ -35,6 +35,8 @@ template <int EMU>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  constexpr int kEmu = EMU;
+  constexpr int kFrac = (EMU == 9) ? 3 : EMU;   // pairs of every 8 that take the FMA-pipe exp2
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                                   // [2 tiles][2 boxes][128][64]
@@ -192,8 +194,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // One pass over this thread's 64 scores, 32 at a time (the second TMEM load is in flight while the first chunk is
     // processed): tracks the maximum and, if EXPS, writes P = 2^(s*scale - m_used) as packed bf16 into pk and
     // returns the sum.
-    auto sweep = [&](auto exps_tag, uint32_t t_s, float m_used, float& row_max, uint32_t (&pk)[32]) -> float {
+    auto sweep = [&](auto exps_tag, auto max_tag, uint32_t t_s, float m_used, float& row_max, uint32_t (&pk)[32]) -> float {
       constexpr bool EXPS = decltype(exps_tag)::value;
+      constexpr bool MAXV = decltype(max_tag)::value;
       uint32_t buf[2][32];
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
@@ -204,9 +207,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int c = 0; c < 2; ++c) {
         uint32_t (&cur)[32] = buf[c];
         if (c == 0) tmem_ld_wait();   // waits for both loads (tcgen05.wait::ld has no partial form)
+        if (MAXV && !(kEmu == 9 && EXPS)) {   // DEBUG (FGB_ATTN_EMU=9): no running-max work after the first tile (timing only)
 #pragma unroll
-        for (int e = 0; e < 32; e += 2)
-          mx[(e >> 1) & 3] = fmaxf(mx[(e >> 1) & 3], fmaxf(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])));
+          for (int e = 0; e < 32; e += 2)
+            mx[(e >> 1) & 3] = fmaxf(mx[(e >> 1) & 3], fmaxf(__uint_as_float(cur[e]), __uint_as_float(cur[e + 1])));
+        }
         if (EXPS) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
@@ -214,7 +219,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             float p0, p1;
             if (EMU == 7) {          // DEBUG (FGB_ATTN_EMU=7): no exponential at all — isolates the MUFU cost
               unpack2(x2, p0, p1);
-            } else if ((e & 7) < EMU) {
+            } else if ((e & 7) < kFrac) {
               exp2_emulated(x2, p0, p1);
             } else {
               float x0, x1;
@@ -233,6 +238,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       unpack2(add2(acc[2], acc[3]), b0, b1);
       return (a0 + a1) + (b0 + b1);
     };
+
+    // ---- bounded-score mode: fixed per-row reference B_i = ||q_i||·kmax·scale·log2e instead of a running maximum
+    bool bounded = false;
+    if (p.kmax != nullptr) {
+      mbar_wait(q_full, 0);
+      const float kmax2 = __ldg(p.kmax + head);   // max_j ||k_j||^2 of this head (fgb_head_norm_max)
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        // this thread's query row: 2 boxes x 128 B (the 128-byte swizzle only permutes 16-byte chunks inside the row)
+        float ss = 0.f;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const uint4* qr = reinterpret_cast<const uint4*>(smem_q + i * kTileBytes + b * kBoxBytes + r_local * 128);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 v = qr[(ch + r_local) & 7];   // staggered chunk order: neighbouring rows hit different banks
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ss += bf16_lo(w[e]) * bf16_lo(w[e]) + bf16_hi(w[e]) * bf16_hi(w[e]);
+          }
+        }
+        const float bound = sqrtf(ss * kmax2) * p.scale_log2 * 1.0001f;
+        ok = ok && (bound <= 60.0f);
+        m[i] = bound;
+      }
+      // one decision per CTA (the two warpgroups of a row must agree; per-CTA keeps it simple): vote through smem
+      if (threadIdx.x == 0) xchg[0] = 1.0f;
+      asm volatile("bar.sync 9, 256;" ::: "memory");
+      if (!ok) xchg[0] = 0.0f;
+      asm volatile("bar.sync 9, 256;" ::: "memory");
+      bounded = xchg[0] != 0.0f;
+      asm volatile("bar.sync 9, 256;" ::: "memory");   // xchg is reused by swap_rows
+      if (!bounded) m[0] = m[1] = -INFINITY;
+    }
 
     for (int j = 0; j < n_kv; ++j) {
 #pragma unroll
@@ -259,22 +299,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         uint32_t pk[32];
         float row_max, sum;
         bool redo = false;
+        if (bounded) {             // no maximum, no exchange, no rescale: one pass of exponentials
+          l[i] += sweep(TagTrue{}, TagFalse{}, t_s, m[i], row_max, pk);
+          tmem_st32(t_s, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_ready[i]);
+          continue;
+        }
         if (EMU == 8) {            // DEBUG (FGB_ATTN_EMU=8): no softmax work at all — the tensor / barrier skeleton alone
           tc_fence_before();
           mbar_arrive(&p_ready[i]);
           continue;
         }
         if (j == 0) {
-          sweep(TagFalse{}, t_s, 0.f, row_max, pk);  // exact maximum of the first tile
+          sweep(TagFalse{}, TagTrue{}, t_s, 0.f, row_max, pk);  // exact maximum of the first tile
           row_max = fmaxf(row_max, swap_rows(row_max));
           m[i] = row_max * p.scale_log2;
           redo = true;
         } else {
           // Speculate that the running maximum has not grown by more than 2^8: exponentiate against the stale
           // maximum while the true maximum is computed on the side (MUFU and ALU pipes in parallel).
-          sum = sweep(TagTrue{}, t_s, m[i], row_max, pk);
-          row_max = fmaxf(row_max, swap_rows(row_max));   // maximum of the whole 128-key row
-          const float m_new = fmaxf(m[i], row_max * p.scale_log2);
+          sum = sweep(TagTrue{}, TagTrue{}, t_s, m[i], row_max, pk);
+          if (kEmu != 9) row_max = fmaxf(row_max, swap_rows(row_max));   // maximum of the whole 128-key row
+          const float m_new = kEmu == 9 ? m[i] : fmaxf(m[i], row_max * p.scale_log2);
           // both threads of a row see the same m_new, so both warps of the pair take the same branch
           if (__any_sync(0xffffffffu, m_new - m[i] > 8.0f)) {
             // rare: rescale the running sum and this warpgroup's half of the O accumulator by 2^(m - m_new), redo the tile
@@ -295,7 +343,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             redo = true;
           }
         }
-        if (redo) sum = sweep(TagTrue{}, t_s, m[i], row_max, pk);  // S is still intact in TMEM: P has not been stored yet
+        if (redo) sum = sweep(TagTrue{}, TagTrue{}, t_s, m[i], row_max, pk);  // S is still intact in TMEM: P has not been stored yet
         l[i] += sum;
         tmem_st32(t_s, pk);   // P over this thread's own first 32 (consumed) score columns
         tmem_st_wait();
@@ -459,7 +507,7 @@ extern "C" int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s
 static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                          int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
                          void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* const* o_peers,
-                         int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, void* stream) {
+                         int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, const void* kmax, void* stream) {
   using namespace fgb;
   FGB_CHECK_ARG(ctx, "fgb_attn_fwd: ctx is NULL");
   FGB_CHECK_ARG(q && k && v && (o || o_peers), "fgb_attn_fwd: NULL tensor pointer");
@@ -494,6 +542,7 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = static_cast<float*>(lse);
   p.ld_lse = ld_lse;
+  p.kmax = static_cast<const float*>(kmax);
   p.rows_per_peer = o_peers ? rows_per_peer : 0;
   p.col_offset = col_offset;
   for (int i = 0; i < FGB_MAX_PEERS; ++i) p.o_peers[i] = (o_peers && i < n_peers) ? static_cast<__nv_bfloat16*>(o_peers[i]) : nullptr;
@@ -520,7 +569,7 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   if (emu < 0) {
     const char* env = getenv("FGB_ATTN_EMU");
     emu = env ? atoi(env) : kDefaultEmu;
-    if (emu < 0 || emu > 8) emu = kDefaultEmu;
+    if (emu < 0 || emu > 9) emu = kDefaultEmu;
   }
   const int grid = p.n_full + n_split * split;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -540,7 +589,8 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
     case 5: rc = launch_attn<5>(grid, st, tq, tk, tv, p); break;
     case 6: rc = launch_attn<6>(grid, st, tq, tk, tv, p); break;
     case 7: rc = launch_attn<7>(grid, st, tq, tk, tv, p); break;
-    default: rc = launch_attn<8>(grid, st, tq, tk, tv, p); break;
+    case 8: rc = launch_attn<8>(grid, st, tq, tk, tv, p); break;
+    default: rc = launch_attn<9>(grid, st, tq, tk, tv, p); break;
   }
   if (rc) return rc;
   if (n_split > 0) {
@@ -555,7 +605,16 @@ extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const v
                                int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
                                void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* stream) {
   return attn_fwd_impl(ctx, q, ldq, k, ldk, v, ldv, o, ldo, s_q, s_kv, heads, scale, lse, ld_lse, workspace, workspace_bytes, nullptr, 0,
-                       0, 0, stream);
+                       0, 0, nullptr, stream);
+}
+
+extern "C" int fgb_attn_fwd_bounded(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                    int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
+                                    const void* kmax, void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes,
+                                    void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, void* stream) {
+  if (!kmax) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_fwd_bounded: kmax is NULL");
+  return attn_fwd_impl(ctx, q, ldq, k, ldk, v, ldv, o, ldo, s_q, s_kv, heads, scale, lse, ld_lse, workspace, workspace_bytes, o_peers,
+                       n_peers, rows_per_peer, col_offset, kmax, stream);
 }
 
 extern "C" int fgb_attn_fwd_scatter(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -564,7 +623,7 @@ extern "C" int fgb_attn_fwd_scatter(fgb_ctx* ctx, const void* q, int64_t ldq, co
                                     int64_t workspace_bytes, void* stream) {
   if (!o_peers) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_fwd_scatter: o_peers is NULL");
   return attn_fwd_impl(ctx, q, ldq, k, ldk, v, ldv, nullptr, ldo, s_q, s_kv, heads, scale, nullptr, 0, workspace, workspace_bytes, o_peers,
-                       n_peers, rows_per_peer, col_offset, stream);
+                       n_peers, rows_per_peer, col_offset, nullptr, stream);
 }
 
 extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,

@@ -32,6 +32,11 @@ struct AttnParams {
   // rows_per_peer) * ldo + (col_offset + head*128); `o` is unused.
   __nv_bfloat16* o_peers[FGB_MAX_PEERS];
   int32_t rows_per_peer, col_offset;
+  // Bounded-score softmax: kmax[head] = max_j ||k_j||^2 over all keys of the head (fp32, NULL = running-max softmax).
+  // |s_ij| <= ||q_i||·kmax (Cauchy-Schwarz), so B_i = ||q_i||·kmax·scale·log2e is a valid FIXED reference for the row:
+  // P = 2^(s - B_i) needs no running max, no rescale and no exchange. Used when every B_i of the CTA is <= 60
+  // (s - B_i >= -120: bf16 / fp32 have the exponent range for it, precision is scale-free); otherwise the CTA falls back.
+  const float* kmax;
 };
 
 __device__ __forceinline__ __nv_bfloat16* out_row(const AttnParams& p, int row, int head) {

@@ -175,6 +175,50 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
 }
 
 // ---------------------------------------------------------------------------------------------
+// out[h] = max over rows of ||x[row, h*128 : (h+1)*128]||^2  — the key-norm bound of the bounded-score softmax
+// (fgb_attn_fwd_bounded). One warp per row (grid-stride); a head is 16 consecutive lanes of one 16-byte vector index.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+head_norm_max_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int rows, int heads, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  float best[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) best[i] = 0.f;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      float ss = 0.f;
+      if (i * 32 + lane < heads * 16) {   // an odd head count (3 heads per rank at SP8) leaves the last half-warp idle
+        unpack8(ldg_nc_v4(xr + i * 32 + lane), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);   // stays inside the 16-lane half
+      best[i] = fmaxf(best[i], ss);
+    }
+  }
+  // block-level maximum first (8 warps), then one atomic per head and CTA: a few hundred contended atomics per head
+  // instead of one per warp
+  __shared__ float red[8][2 * NV];
+  if ((lane & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[threadIdx.x >> 5][2 * i + (lane >> 4)] = best[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * NV && static_cast<int>(threadIdx.x) < heads) {
+    float m = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w][threadIdx.x]);
+    atomicMax(reinterpret_cast<unsigned int*>(out) + threadIdx.x, __float_as_uint(m));   // non-negative floats order like their bits
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // CFG combine + flow-match Euler update + first-frame restore.          PIPE:302, 307-309; FM:144-154
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float cfg_fm_one(float x, float np, float nn, bool has_neg, float cfg, float dsig) {
@@ -621,5 +665,29 @@ extern "C" int fgb_rmsnorm_rope_scatter(fgb_ctx* ctx, const void* x, int64_t ldx
   }
 #undef FGB_RMS_CASE
   FGB_LAUNCH_CHECK("rmsnorm_rope_kernel<scatter>");
+  return FGB_OK;
+}
+
+extern "C" int fgb_head_norm_max(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t rows, int32_t heads, void* out_f32, void* stream) {
+  FGB_CHECK_ARG(ctx && x && out_f32 && rows > 0 && heads > 0, "fgb_head_norm_max: bad argument");
+  FGB_CHECK_ARG(ldx % 8 == 0 && ldx >= static_cast<int64_t>(heads) * 128 && aligned16(x), "fgb_head_norm_max: x must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FGB_CUDA(cudaMemsetAsync(out_f32, 0, sizeof(float) * heads, s));
+  int grid = (rows + 7) / 8;
+  if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+  const bf16* xp = static_cast<const bf16*>(x);
+  float* op = static_cast<float*>(out_f32);
+#define FGB_HNM_CASE(NV)                                                     \
+  case NV:                                                                   \
+    head_norm_max_kernel<NV><<<grid, 256, 0, s>>>(xp, ldx, rows, heads, op); \
+    break;
+  switch ((heads + 1) / 2) {
+    FGB_HNM_CASE(1) FGB_HNM_CASE(2) FGB_HNM_CASE(3) FGB_HNM_CASE(4) FGB_HNM_CASE(6) FGB_HNM_CASE(8) FGB_HNM_CASE(12) FGB_HNM_CASE(16)
+    FGB_HNM_CASE(20)
+    default:
+      return set_error(FGB_ERR_UNSUPPORTED, "fgb_head_norm_max: unsupported head count %d", heads);
+  }
+#undef FGB_HNM_CASE
+  FGB_LAUNCH_CHECK("head_norm_max_kernel");
   return FGB_OK;
 }

@@ -114,6 +114,7 @@ class WanDiTEngine:
                 prow=e(rows, io), hrow=e(rows, cfg.out_dim * 4),
                 ts=torch.zeros(2, dtype=torch.float32, device=dev), emb=e(2, cfg.freq_dim), t0=e(2, d), t0s=e(2, d),
                 t=e(2, d), ts_silu=e(2, d), tmod=e(2, 6 * d), mod_tab=e(2, L, 6 * d), head_tab=e(2, 2 * d),
+                kmax2=torch.zeros(cfg.num_heads, dtype=torch.float32, device=dev),
             )
             if self.sp is not None:
                 hpr_w = 3 * d // self.sp.world
@@ -180,11 +181,13 @@ class WanDiTEngine:
         emb = self.text_embedding(context)
         n = emb.shape[0]
         kv = torch.empty(cfg.num_layers, n, 2 * d, dtype=BF16, device=dev)
+        kmax = torch.empty(cfg.num_layers, cfg.num_heads, dtype=torch.float32, device=dev)   # key bounds of the bounded softmax
         for i, b in enumerate(self.blocks):
             ops.gemm(emb, b.cwkv, b.cbkv, kv[i], EPI_BIAS)
             ops.rmsnorm_rope(kv[i][:, :d], cfg.eps, b.cnk)
-        self._launched(2 * cfg.num_layers)
-        val = (kv, n, context)  # keep `context` alive so its data_ptr cannot be recycled under the key
+            ops.head_norm_max(kv[i][:, :d], kmax[i], cfg.num_heads)
+        self._launched(3 * cfg.num_layers)
+        val = (kv, n, context, kmax)  # keep `context` alive so its data_ptr cannot be recycled under the key
         self._ctx_cache[key] = val
         self._ctx_cache_order.append(key)
         while len(self._ctx_cache_order) > 4:
@@ -224,7 +227,7 @@ class WanDiTEngine:
         r_main = R - 1                                   # row used by tokens after the first frame
         n_first = max(0, min(rows, h * w - tok0)) if per_token else 0   # tokens of this rank at t = 0
 
-        kv_all, n_ctx, _ = self._context_kv(context)
+        kv_all, n_ctx, _, kmax_all = self._context_kv(context)
 
         # ---- patch embedding: im2row + GEMM (DIT:305, PIPE:1253-1261)
         x, a, qkv, o, cq, hbuf = ws["x"], ws["a"], ws["qkv"], ws["o"], ws["cq"], ws["h"]
@@ -244,7 +247,8 @@ class WanDiTEngine:
                 k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)
                 k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, d:2 * d], cfg.eps, b.nk, self.rope_tab, grid, tok0)
                 if sp is None:
-                    k("attn_self", ops.attention, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, H)
+                    k("head_norm_max", ops.head_norm_max, qkv[:, d:2 * d], ws["kmax2"], H)
+                    k("attn_self", ops.attention, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, H, kmax2=ws["kmax2"])
                 else:
                     sp.attention(self, ws, qkv, o, S)
             k("gemm_o", ops.gemm, o, b.wo, b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first)
@@ -252,7 +256,7 @@ class WanDiTEngine:
             k("ln_affine", ops.ln_affine, x, a, cfg.eps, b.n3w, b.n3b)
             k("gemm_cross_q", ops.gemm, a, b.cwq, b.cbq, cq)
             k("rmsnorm", ops.rmsnorm_rope, cq, cfg.eps, b.cnq)
-            k("attn_cross", ops.attention, cq, kv_all[i][:, :d], kv_all[i][:, d:], o, H)
+            k("attn_cross", ops.attention, cq, kv_all[i][:, :d], kv_all[i][:, d:], o, H, kmax2=kmax_all[i])
             k("gemm_cross_o", ops.gemm, o, b.cwo, b.cbo, x, EPI_RESIDUAL)
             # feed-forward branch (DIT:227-228)
             k("ln_modulate", ops.ln_modulate, x, a, cfg.eps, m0[3], m0[4], m1[3], m1[4], n_first)

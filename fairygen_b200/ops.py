@@ -93,7 +93,17 @@ def attention_workspace(q_rows: int, kv_rows: int, heads: int, device) -> Option
     return ws
 
 
-def attention(q, k, v, out, heads: int, scale: Optional[float] = None, lse: Optional[torch.Tensor] = None):
+def head_norm_max(k, out_f32, heads: int):
+    """out_f32[h] = max over rows of ||k[row, h*128:(h+1)*128]||^2 — the key bound of the bounded-score softmax."""
+    ldk = _rowmajor(k, "k")
+    if k.shape[1] != heads * 128 or out_f32.dtype != torch.float32 or out_f32.numel() != heads or not out_f32.is_contiguous():
+        raise ValueError("head_norm_max: k [rows, heads*128] bf16, out float32 [heads]")
+    _lib.check(_lib.lib().fgb_head_norm_max(_h(k).handle, _p(k), ldk, k.shape[0], heads, _p(out_f32), _stream()), "fgb_head_norm_max")
+    return out_f32
+
+
+def attention(q, k, v, out, heads: int, scale: Optional[float] = None, lse: Optional[torch.Tensor] = None,
+              kmax2: Optional[torch.Tensor] = None):
     """out = softmax(q k^T scale) v per 128-wide head; q/out [s_q, heads*128], k/v [s_kv, heads*128].
     lse (optional, fp32 [heads, ld] with ld >= s_q, ld % 64 == 0) receives the log2-domain log-sum-exp rows
     for the backward pass."""
@@ -108,6 +118,13 @@ def attention(q, k, v, out, heads: int, scale: Optional[float] = None, lse: Opti
         raise ValueError("lse must be a contiguous float32 [heads, ld] tensor with ld >= s_q and ld % 64 == 0")
     c = _h(q)
     ws = attention_workspace(s_q, s_kv, heads, q.device)
+    if kmax2 is not None:   # bounded-score softmax: fixed per-row reference from ||q_i||·max_j||k_j||, no running maximum
+        if kmax2.dtype != torch.float32 or kmax2.numel() != heads or not kmax2.is_contiguous():
+            raise ValueError("kmax2 must be a contiguous float32 [heads] tensor (head_norm_max of k)")
+        _lib.check(_lib.lib().fgb_attn_fwd_bounded(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), ldo, s_q, s_kv, heads, scale,
+                                                   _p(kmax2), _p(lse), 0 if lse is None else lse.shape[1], _p(ws),
+                                                   0 if ws is None else ws.numel(), None, 0, 0, 0, _stream()), "fgb_attn_fwd_bounded")
+        return out
     _lib.check(_lib.lib().fgb_attn_fwd_ex(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), ldo, s_q, s_kv, heads,
                                           scale, _p(lse), 0 if lse is None else lse.shape[1], _p(ws),
                                           0 if ws is None else ws.numel(), _stream()), "fgb_attn_fwd_ex")
@@ -312,7 +329,8 @@ def sp_barrier(device, flag_ptrs, world: int, rank: int, epoch: int):
     _lib.check(_lib.lib().fgb_sp_barrier(context(device).handle, _ptr_array(flag_ptrs), world, rank, epoch, _stream()), "fgb_sp_barrier")
 
 
-def attention_scatter(q, k, v, o_peer_ptrs, ldo: int, rows_per_peer: int, col_offset: int, heads: int, scale: Optional[float] = None):
+def attention_scatter(q, k, v, o_peer_ptrs, ldo: int, rows_per_peer: int, col_offset: int, heads: int, scale: Optional[float] = None,
+                      kmax2: Optional[torch.Tensor] = None):
     """attention() whose output rows go straight into the token-major o buffers of the ranks that own the tokens."""
     ldq, ldk, ldv = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v")
     s_q, s_kv = q.shape[0], k.shape[0]
@@ -321,6 +339,11 @@ def attention_scatter(q, k, v, o_peer_ptrs, ldo: int, rows_per_peer: int, col_of
     scale = 1.0 / math.sqrt(128.0) if scale is None else scale
     c = _h(q)
     ws = attention_workspace(s_q, s_kv, heads, q.device)
+    if kmax2 is not None:
+        _lib.check(_lib.lib().fgb_attn_fwd_bounded(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, None, ldo, s_q, s_kv, heads, scale,
+                                                   _p(kmax2), None, 0, _p(ws), 0 if ws is None else ws.numel(), _ptr_array(o_peer_ptrs),
+                                                   len(o_peer_ptrs), rows_per_peer, col_offset, _stream()), "fgb_attn_fwd_bounded")
+        return
     _lib.check(_lib.lib().fgb_attn_fwd_scatter(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _ptr_array(o_peer_ptrs), len(o_peer_ptrs), ldo,
                                                rows_per_peer, col_offset, s_q, s_kv, heads, scale, _p(ws), 0 if ws is None else ws.numel(),
                                                _stream()), "fgb_attn_fwd_scatter")

@@ -145,8 +145,10 @@ class SequenceParallel:
             ar.epoch += 1
             k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[0], self.world, self.rank, ar.epoch)
             recv = ar.recv
+            kmax2 = ws["kmax2"][:hpr]
+            k("head_norm_max", ops.head_norm_max, recv[:tokens, wloc:2 * wloc], kmax2, hpr)
             k("attn_self", ops.attention_scatter, recv[:, :wloc], recv[:tokens, wloc:2 * wloc], recv[:tokens, 2 * wloc:], ar.o_ptrs,
-              heads * 128, rows, self.rank * wloc, hpr)
+              heads * 128, rows, self.rank * wloc, hpr, kmax2=kmax2)
             k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[1], self.world, self.rank, ar.epoch)
             return
         k("sp_pack", ops.sp_pack_heads, qkv, ws["send"], heads, 3, self.world)

@@ -95,6 +95,16 @@ int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int
                     void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s_kv, int32_t heads);
 
+/* Bounded-score softmax. kmax2[head] = max_j ||k[j, head]||^2 (fgb_head_norm_max) gives |q_i·k_j| <= ||q_i||·sqrt(kmax2), a
+ * FIXED per-row reference for the exponentials: no running maximum, no rescale of O, no per-tile exchange between the
+ * threads that share a row. A CTA uses it when all its bounds are <= 60 in log2 units (no underflow possible), else it
+ * falls back to the running-max path; results are the same softmax either way. o_peers may be NULL (then `o` is used). */
+int fgb_head_norm_max(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t rows, int32_t heads, void* out_f32, void* stream);
+int fgb_attn_fwd_bounded(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                         void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale, const void* kmax2,
+                         void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* const* o_peers,
+                         int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, void* stream);
+
 /* Backward of fgb_attn_fwd(_ex): given dout = dL/do, writes dq [s_q, heads*128], dk and dv [s_kv, heads*128] (bf16).
  * The reference obtains this from torch autograd through flash_attention (DIT:27-60) during the stage-2 LoRA
  * fine-tune (config 5; diffusion/loss.py:17-20 -> model_fn -> DiTBlock, PIPE:1348-1360 re-computes each block).

@@ -346,3 +346,32 @@ def test_attention_cluster_variant_kcheck():
     for shape in (("300", "200", "2"), ("1000", "3000", "3"), ("1025", "77", "4"), ("515", "4100", "5")):
         out = subprocess.run([kcheck, "attn", *shape], env=env, capture_output=True, text=True, timeout=120).stdout
         assert out.count("PASS") == 2 and "FAIL" not in out, out
+
+
+@pytest.mark.parametrize("s_q,s_kv,heads,scale_q", [(300, 200, 2, 1.0), (1000, 1000, 3, 1.0), (2304, 2304, 2, 1.0), (515, 4100, 5, 1.0),
+                                                    (700, 700, 2, 12.0)])
+def test_bounded_score_attention(env, s_q, s_kv, heads, scale_q):
+    """fgb_attn_fwd_bounded: softmax against the fixed Cauchy-Schwarz reference ||q_i||·max_j||k_j|| instead of a running
+    maximum. scale_q = 12 pushes the bound past 60 (log2 units), which must fall back to the running-max path."""
+    ops, o = env
+    d = heads * 128
+    q, k, v = rnd(s_q, d, seed=1, scale=scale_q), rnd(s_kv, d, seed=2), rnd(s_kv, d, seed=3)
+    kmax2 = torch.empty(heads, dtype=torch.float32, device="cuda")
+    ops.head_norm_max(k, kmax2, heads)
+    ops.sync_check()
+    want = (k.float().view(s_kv, heads, 128) ** 2).sum(-1).max(0).values
+    assert torch.allclose(kmax2, want, rtol=1e-5)
+    out = torch.full((s_q, d), float("nan"), dtype=BF, device="cuda")
+    lse = torch.empty(heads, ops.stat_rows(s_q), dtype=torch.float32, device="cuda")
+    ops.attention(q, k, v, out, heads, lse=lse, kmax2=kmax2)
+    ops.sync_check()
+    ref = o.attention(q[None].float(), k[None].float(), v[None].float(), heads)[0]
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 6e-3
+    sc = torch.einsum("qhd,khd->hqk", q.float().view(s_q, heads, 128), k.float().view(s_kv, heads, 128)) / math.sqrt(128)
+    assert (lse[:, :s_q] - torch.logsumexp(sc, dim=-1) * math.log2(math.e)).abs().max() < 5e-3 * max(1.0, scale_q)
+    # odd head count (3 heads per rank under Ulysses SP8) and a strided k view
+    kk = rnd(257, 3 * 128 + 64, seed=5)[:, 64:]
+    km = torch.empty(3, dtype=torch.float32, device="cuda")
+    ops.head_norm_max(kk, km, 3)
+    assert torch.allclose(km, (kk.float().reshape(257, 3, 128) ** 2).sum(-1).max(0).values, rtol=1e-5)
