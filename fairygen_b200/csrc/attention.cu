@@ -458,16 +458,6 @@ static int launch_attn(int grid, cudaStream_t stream, const CUtensorMap& tq, con
   return FGB_OK;
 }
 
-// FGB_ATTN_CLUSTER=1 selects attention_cluster.cu (one query tile per CTA, double-buffered S, K/V multicast in a 2-CTA cluster)
-static bool attn_cluster_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* env = getenv("FGB_ATTN_CLUSTER");
-    mode = env ? (atoi(env) != 0) : 0;
-  }
-  return mode != 0;
-}
-
 // How the last, partly filled wave of CTAs is cut along the keys: returns the split factor g (1 = no split) and the
 // number of units that are split. With U units on n_sm SMs (one CTA per SM), the last U mod n_sm units would occupy a
 // whole wave on their own; cutting each into g key chunks makes the tail ceil(rem*g/n_sm)/g of a wave instead.
@@ -500,7 +490,7 @@ extern "C" int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s
   if (!ctx || s_q <= 0 || s_kv <= 0 || heads <= 0) return 0;
   const int n_pairs = (s_q + 2 * kTile - 1) / (2 * kTile);
   int split, n_split;
-  plan_split(n_pairs * heads, (s_kv + kTile - 1) / kTile, attn_cluster_mode() ? ctx->sm_count / 2 : ctx->sm_count, &split, &n_split);
+  plan_split(n_pairs * heads, (s_kv + kTile - 1) / kTile, ctx->sm_count, &split, &n_split);
   return static_cast<int64_t>(n_split) * split * (2 * kTile) * (128 * 4 + 8);
 }
 
@@ -524,14 +514,12 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
     for (int i = 0; i < n_peers; ++i) FGB_CHECK_ARG(o_peers[i] && aligned16(o_peers[i]), "fgb_attn_fwd_scatter: peer output %d", i);
   }
 
-  const bool cluster = attn_cluster_mode();
-  const int kv_box = cluster ? 64 : kTile;   // the cluster kernel loads half tiles and multicasts them
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_bf16_2d(ctx, &tq, q, s_q, width, ldq, kTile);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(ctx, &tk, k, s_kv, width, ldk, kv_box);
+  rc = make_tmap_bf16_2d(ctx, &tk, k, s_kv, width, ldk, kTile);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(ctx, &tv, v, s_kv, width, ldv, kv_box);
+  rc = make_tmap_bf16_2d(ctx, &tv, v, s_kv, width, ldv, kTile);
   if (rc) return rc;
 
   AttnParams p;
@@ -553,7 +541,7 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   const int units = static_cast<int>(units64);
   int split = 1, n_split = 0;
   // the key split needs the caller's scratch (the library never allocates); without it every unit runs whole
-  if (workspace != nullptr) plan_split(units, (s_kv + kTile - 1) / kTile, cluster ? ctx->sm_count / 2 : ctx->sm_count, &split, &n_split);
+  if (workspace != nullptr) plan_split(units, (s_kv + kTile - 1) / kTile, ctx->sm_count, &split, &n_split);
   const int64_t need = static_cast<int64_t>(n_split) * split * (2 * kTile) * (128 * 4 + 8);
   if (need > workspace_bytes) {
     split = 1;
@@ -573,14 +561,7 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   }
   const int grid = p.n_full + n_split * split;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int emu_sel = emu;
-  if (cluster) {
-    rc = launch_attn_cluster(emu, grid, st, tq, tk, tv, p);
-    if (rc) return rc;
-    emu_sel = -2;   // skip the switch below
-  }
-  switch (emu_sel) {
-    case -2: break;
+  switch (emu) {
     case 0: rc = launch_attn<0>(grid, st, tq, tk, tv, p); break;
     case 1: rc = launch_attn<1>(grid, st, tq, tk, tv, p); break;
     case 2: rc = launch_attn<2>(grid, st, tq, tk, tv, p); break;

@@ -1,4 +1,5 @@
-// fairygen_b200 — pieces shared by the attention-forward kernels (attention.cu, attention_cluster.cu).
+// fairygen_b200 — parameters and arithmetic helpers of the attention-forward kernel (attention.cu; also used by the
+// experimental variants kept under experiments/).
 #pragma once
 
 #include "common.cuh"
@@ -101,9 +102,5 @@ __device__ __forceinline__ void exp2_emulated(uint64_t x2, float& r0, float& r1)
 struct TagTrue { static constexpr bool value = true; };
 struct TagFalse { static constexpr bool value = false; };
 
-
-// attention_cluster.cu: one query tile per CTA, S double-buffered in TMEM, K/V multicast across a 2-CTA cluster
-int launch_attn_cluster(int emu, int units, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMap& tv64,
-                        const AttnParams& p);
 
 }  // namespace fgb

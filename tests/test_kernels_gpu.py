@@ -332,22 +332,6 @@ def test_sp_pack_unpack_roundtrip(env):
     assert torch.equal(back, x)
 
 
-def test_attention_cluster_variant_kcheck():
-    """FGB_ATTN_CLUSTER=1 selects attention_cluster.cu (one query tile per CTA, double-buffered S, K/V multicast across a
-    2-CTA cluster). The mode is latched per process, so it is exercised through the stand-alone harness tools/kcheck,
-    which compares with a naive fp32 CUDA-core reference (outputs and log-sum-exp rows)."""
-    import os
-    import subprocess
-    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    kcheck = os.path.join(repo, "tools", "kcheck")
-    if not os.path.exists(kcheck):
-        pytest.skip("tools/kcheck not built")
-    env = dict(os.environ, FGB_ATTN_CLUSTER="1")
-    for shape in (("300", "200", "2"), ("1000", "3000", "3"), ("1025", "77", "4"), ("515", "4100", "5")):
-        out = subprocess.run([kcheck, "attn", *shape], env=env, capture_output=True, text=True, timeout=120).stdout
-        assert out.count("PASS") == 2 and "FAIL" not in out, out
-
-
 @pytest.mark.parametrize("s_q,s_kv,heads,scale_q", [(300, 200, 2, 1.0), (1000, 1000, 3, 1.0), (2304, 2304, 2, 1.0), (515, 4100, 5, 1.0),
                                                     (700, 700, 2, 12.0)])
 def test_bounded_score_attention(env, s_q, s_kv, heads, scale_q):
