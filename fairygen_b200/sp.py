@@ -153,6 +153,9 @@ class SequenceParallel:
             return
         k("sp_pack", ops.sp_pack_heads, qkv, ws["send"], heads, 3, self.world)
         recv = k("sp_all_to_all", self.all_to_all, ws["recv"], ws["send"])     # [s_pad tokens, (q|k|v) x hpr x 128]
-        k("attn_self", ops.attention, recv[:, :wloc], recv[:tokens, wloc:2 * wloc], recv[:tokens, 2 * wloc:], ws["o_full"], hpr)
+        kmax2 = ws["kmax2"][:hpr] if "kmax2" in ws else None   # bounded-score softmax, as on the single-GPU and p2p paths
+        if kmax2 is not None:
+            k("head_norm_max", ops.head_norm_max, recv[:tokens, wloc:2 * wloc], kmax2, hpr)
+        k("attn_self", ops.attention, recv[:, :wloc], recv[:tokens, wloc:2 * wloc], recv[:tokens, 2 * wloc:], ws["o_full"], hpr, kmax2=kmax2)
         o_recv = k("sp_all_to_all", self.all_to_all, ws["o_recv"], ws["o_full"])  # [world][rows][hpr*128]
         k("sp_unpack", ops.sp_unpack_heads, o_recv, o, heads, 1, self.world)

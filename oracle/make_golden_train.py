@@ -62,6 +62,86 @@ class Stage2Linear(torch.nn.Module):
         return result + update * self.scaling
 
 
+class Stage1Linear(torch.nn.Module):
+    """TMOD:200-264 (`new_forward` of stage-1) on a plain nn.Linear base layer; A and B trainable."""
+
+    def __init__(self, base, a, b, mask):
+        super().__init__()
+        self.base_layer = base
+        self.lora_A = torch.nn.Parameter(a.clone())
+        self.lora_B = torch.nn.Parameter(b.clone())
+        self.mask = mask
+        self.scaling = 1.0
+
+    def forward(self, x):
+        result = self.base_layer(x)
+        dropout_prob = 0.8
+        mask = self.mask.to(self.lora_B.dtype)
+        scale_factor = 1.0 / (1 - dropout_prob)
+        b_dropped = self.lora_B * mask * scale_factor
+        intermediate = F.linear(x, self.lora_A)
+        update = F.linear(intermediate, b_dropped, None)
+        return result + update * self.scaling
+
+
+def build_ref(cfg, w):
+    dit = wd.WanModel(dim=cfg.dim, in_dim=cfg.in_dim, ffn_dim=cfg.ffn_dim, out_dim=cfg.out_dim, text_dim=cfg.text_dim,
+                      freq_dim=cfg.freq_dim, eps=cfg.eps, patch_size=cfg.patch_size, num_heads=cfg.num_heads,
+                      num_layers=cfg.num_layers, has_image_input=False, seperated_timestep=True,
+                      require_clip_embedding=False, require_vae_embedding=False, fuse_vae_embedding_in_latents=True).eval()
+    dit.load_state_dict(w, strict=True)
+    for p in dit.parameters():
+        p.requires_grad_(False)
+    return dit
+
+
+def wrap(dit, cfg, factory):
+    wrapped = {}
+    for name in t.lora_targets(cfg):
+        parent_name, child = name.rsplit(".", 1)
+        parent = dit.get_submodule(parent_name)
+        base = getattr(parent, child) if not child.isdigit() else parent[int(child)]
+        mod = factory(name, base)
+        if child.isdigit():
+            parent[int(child)] = mod
+        else:
+            setattr(parent, child, mod)
+        wrapped[name] = mod
+    return wrapped
+
+
+STAGE1_STORED = ("blocks.0.self_attn.q", "blocks.0.cross_attn.k", "blocks.0.ffn.0", "blocks.1.self_attn.o", "blocks.1.cross_attn.v",
+                 "blocks.1.ffn.2")
+
+
+def golden_stage1(out):
+    """Stage-1 (identity) LoRA step: A and B trainable, weight dropout 0.8 (TMOD:200-264)."""
+    cfg = o.TINY
+    w = o.make_weights(cfg, seed=0)
+    lora = o.make_lora(cfg, rank=32, seed=2)
+    masks = t.make_masks_stage1(cfg, rank=32)
+    dit = build_ref(cfg, w)
+    wrapped = wrap(dit, cfg, lambda name, base: Stage1Linear(base, lora[f"{name}.lora_A.default.weight"],
+                                                            lora[f"{name}.lora_B.default.weight"], masks[name]))
+    sched = FlowMatchScheduler("Wan")
+    sched.set_timesteps(1000, training=True)
+    shape, text_len, timestep_id = (1, cfg.in_dim, 3, 8, 8), 32, 500
+    x0, _, ctx, _ = o.make_inputs(cfg, shape, text_len=text_len, live_text=8)
+    noise = torch.randn(shape, generator=torch.Generator().manual_seed(9))
+    timestep = sched.timesteps[torch.tensor([timestep_id])]
+    latents = sched.add_noise(x0, noise, timestep)
+    target = sched.training_target(x0, noise, timestep)
+    pred = wv.model_fn_wan_video(dit=dit, latents=latents, timestep=timestep, context=ctx, fuse_vae_embedding_in_latents=True)
+    loss = F.mse_loss(pred.float(), target.float()) * sched.training_weight(timestep)
+    loss.backward()
+    out["s1_loss"] = np.array(float(loss.detach()), dtype=np.float64)
+    out["s1_pred"] = pred.detach().numpy()
+    for name in STAGE1_STORED:
+        out[f"s1_gradA.{name}"] = wrapped[name].lora_A.grad.detach().numpy().astype(np.float32)
+        out[f"s1_gradB.{name}"] = wrapped[name].lora_B.grad.detach().numpy().astype(np.float32)
+    print("stage1 loss", float(loss.detach()))
+
+
 def main():
     cfg = o.TINY
     rank = 32
@@ -111,6 +191,7 @@ def main():
         print(tag, "loss", float(loss), "timestep", float(timestep))
     sig, ts, wts = t.training_schedule()
     assert torch.equal(sig, sched.sigmas) and torch.equal(ts, sched.timesteps) and torch.allclose(wts, sched.linear_timesteps_weights)
+    golden_stage1(out)
     np.savez_compressed(os.path.join(OUT, "train.npz"), **out)
     print("train.npz:", len(out), "arrays", os.path.getsize(os.path.join(OUT, "train.npz")), "bytes")
 

@@ -77,6 +77,32 @@ def stage2_linear_fn(lora: Weights, b2: Weights, masks: Dict[str, torch.Tensor],
     return hook
 
 
+def stage1_linear_fn(lora: Weights, masks: Dict[str, torch.Tensor], scaling: float = 1.0, dropout_prob: float = 0.8):
+    """The stage-1 ``new_forward`` (TMOD:200-264): y = W x + b + s * F.linear(A x, B * mask * 5), A and B trainable,
+    mask ~ Bernoulli(0.2) keep (``rand_like(B) > 0.8``) drawn per layer per call — injected here."""
+    def hook(w: Weights, name: str, x: torch.Tensor) -> torch.Tensor:
+        result = F.linear(x, w[name + ".weight"], w[name + ".bias"])                       # TMOD:218
+        ka, kb = f"{name}.lora_A.default.weight", f"{name}.lora_B.default.weight"
+        if kb not in lora:
+            return result
+        a, b = lora[ka], lora[kb]
+        mask = masks[name].to(dtype=b.dtype, device=b.device)                             # TMOD:234-236 (injected)
+        b_dropped = b * mask * (1.0 / (1 - dropout_prob))                                 # TMOD:237-238
+        update = F.linear(F.linear(x, a), b_dropped)                                      # TMOD:240-241
+        return result + update * scaling                                                  # TMOD:242
+    return hook
+
+
+def make_masks_stage1(cfg: o.DiTConfig, rank: int = 32, seed: int = 8) -> Dict[str, torch.Tensor]:
+    """Fixed keep-masks `rand > 0.8` (uint8), one per adapted Linear."""
+    shapes = o.param_shapes(cfg)
+    out = {}
+    for t in lora_targets(cfg):
+        g = torch.Generator().manual_seed(o._seed_for(t + ".mask1", seed))
+        out[t] = (torch.rand((shapes[t + ".weight"][0], rank), generator=g) > 0.8).to(torch.uint8)
+    return out
+
+
 def training_schedule(num_steps: int = 1000, shift: float = 5.0):
     """FlowMatchScheduler('Wan').set_timesteps(1000, training=True) (flow_match.py:29-39, 132-142): sigmas,
     timesteps and the bell-shaped per-timestep loss weights."""
@@ -93,7 +119,7 @@ def training_schedule(num_steps: int = 1000, shift: float = 5.0):
     return sigmas, timesteps, weights
 
 
-def sft_loss(w: Weights, cfg: o.DiTConfig, lora: Weights, b2: Weights, masks, x0: torch.Tensor, noise: torch.Tensor,
+def sft_loss(w: Weights, cfg: o.DiTConfig, lora: Weights, b2: Optional[Weights], masks, x0: torch.Tensor, noise: torch.Tensor,
              timestep_id: int, context: torch.Tensor, fuse_vae_embedding_in_latents: bool = True,
              schedule=None, return_pred: bool = False, timestep_dtype=None):
     """LOSS:5-21 with the random draws (timestep id, noise) injected.  x0/noise (1,C,F,H,W) in the compute dtype."""
@@ -109,7 +135,7 @@ def sft_loss(w: Weights, cfg: o.DiTConfig, lora: Weights, b2: Weights, masks, x0
     latents = (1 - sigma) * x0 + sigma * noise                                              # add_noise, FM:164-170
     target = noise - x0                                                                     # training_target, FM:172-175
     ww = dict(w)
-    ww["__linear__"] = stage2_linear_fn(lora, b2, masks)
+    ww["__linear__"] = stage2_linear_fn(lora, b2, masks) if b2 is not None else stage1_linear_fn(lora, masks)   # b2 None: stage 1
     pred = o.dit_forward(ww, cfg, latents.to(dtype), timestep, context, fuse_vae_embedding_in_latents)  # LOSS:17
     loss = F.mse_loss(pred.float(), target.float()) * float(weights[index])                   # LOSS:19-20
     return (loss, pred) if return_pred else loss
@@ -120,6 +146,16 @@ def loss_and_grads(w: Weights, cfg: o.DiTConfig, lora: Weights, b2: Weights, mas
     """(loss, prediction, {module: dloss/dB2}) by autograd — the quantities of one reference training step."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in b2.items()}
     loss, pred = sft_loss(w, cfg, lora, leaves, masks, x0, noise, timestep_id, context, fuse_vae_embedding_in_latents,
+                          return_pred=True, timestep_dtype=timestep_dtype)
+    loss.backward()
+    return loss.detach(), pred.detach(), {k: v.grad.detach() for k, v in leaves.items()}
+
+
+def loss_and_grads_stage1(w: Weights, cfg: o.DiTConfig, lora: Weights, masks, x0, noise, timestep_id, context,
+                          fuse_vae_embedding_in_latents: bool = True, timestep_dtype=None):
+    """Stage 1 (identity LoRA): (loss, prediction, {lora key: dloss/d(A or B)}) by autograd."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in lora.items()}
+    loss, pred = sft_loss(w, cfg, leaves, None, masks, x0, noise, timestep_id, context, fuse_vae_embedding_in_latents,
                           return_pred=True, timestep_dtype=timestep_dtype)
     loss.backward()
     return loss.detach(), pred.detach(), {k: v.grad.detach() for k, v in leaves.items()}

@@ -37,7 +37,7 @@ def _emulated_unpack(recv, x, heads, groups, world):
     return x
 
 
-def _emulated_attention(q, k, v, out, heads, scale=None):
+def _emulated_attention(q, k, v, out, heads, scale=None, lse=None, kmax2=None):
     from oracle import wan_dit_oracle as o
     out.copy_(o.attention(q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0), heads)[0])
     return out

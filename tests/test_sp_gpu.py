@@ -55,7 +55,7 @@ def test_sp2_equals_single_gpu(tmp_path, shape, exchange):
     mp.spawn(_worker, args=(world, _free_port(), shape, exchange, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
-        assert res["finite"] and res["err"] < 2e-3, res   # same kernels, same rounding; only the attention tiling differs
+        assert res["finite"] and res["err"] < 3e-3, res   # same kernels; only the attention work split / key-split tail differs
 
 
 def _cfg_worker(rank, world, port, shape, sp_ways, out_dir):
