@@ -307,7 +307,8 @@ lora_merge_kernel(const __nv_bfloat16* __restrict__ w, int64_t ldw, const __nv_b
 template <int NR>
 __global__ void __launch_bounds__(128)
 lora_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const __nv_bfloat16* __restrict__ t, int64_t ld_t,
-                  float* __restrict__ db, const uint8_t* __restrict__ mask, float mul, int rows, int n, int rows_per_cta) {
+                  float* __restrict__ db, const uint8_t* __restrict__ mask, float mul, int rows, int n, int rows_per_cta,
+                  int transpose_out) {
   constexpr int R = 16 * NR;
   constexpr int kChunk = 64;                       // tokens per step
   constexpr int kTV = kChunk * R / 8 / 128;        // 16-byte vectors of t per thread per chunk (R = 16/32/64 -> 1/2/4)
@@ -374,7 +375,8 @@ lora_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const __n
     const int64_t g = static_cast<int64_t>(n0 + r) * R + c;
     const float m = mask ? static_cast<float>(mask[g]) : 1.0f;
     const float v = s_out[i] * m * mul;
-    if (v != 0.f) atomicAdd(db + g, v);
+    // transpose_out: db is [R, n] (the layout of lora_A: dA = uᵀ·X computed as (Xᵀ·u)ᵀ)
+    if (v != 0.f) atomicAdd(db + (transpose_out ? static_cast<int64_t>(c) * n + (n0 + r) : g), v);
   }
 }
 
@@ -591,10 +593,11 @@ extern "C" int fgb_lora_merge(fgb_ctx* ctx, const void* w, int64_t ldw, const vo
 }
 
 extern "C" int fgb_lora_wgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* t, int64_t ld_t, void* db_f32,
-                              const void* mask, float mul, int32_t rows, int32_t n, int32_t rank, void* stream) {
+                              const void* mask, float mul, int32_t rows, int32_t n, int32_t rank, int32_t transpose_out, void* stream) {
   FGB_CHECK_ARG(ctx && dy && t && db_f32, "fgb_lora_wgrad: NULL argument");
   FGB_CHECK_ARG(rows > 0 && n > 0 && n % 8 == 0, "fgb_lora_wgrad: rows=%d n=%d (n %% 8)", rows, n);
   FGB_CHECK_ARG(rank == 16 || rank == 32 || rank == 64, "fgb_lora_wgrad: rank %d not in {16, 32, 64}", rank);
+  FGB_CHECK_ARG(!(transpose_out && mask), "fgb_lora_wgrad: a mask applies to the [n, rank] layout only");
   FGB_CHECK_ARG(ld_dy % 8 == 0 && ld_t % 8 == 0 && aligned16(dy) && aligned16(t), "fgb_lora_wgrad: operands must be 16-byte aligned");
   const int n_tiles = (n + 63) / 64;
   // enough token chunks to fill the machine ~4x over; each chunk a multiple of 32 rows
@@ -607,7 +610,7 @@ extern "C" int fgb_lora_wgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define LAUNCH(NR)                                                                                                  \
   lora_wgrad_kernel<NR><<<grid, 128, 0, s>>>((const bf16*)dy, ld_dy, (const bf16*)t, ld_t, (float*)db_f32,          \
-                                             (const uint8_t*)mask, mul, rows, n, rows_per_cta)
+                                             (const uint8_t*)mask, mul, rows, n, rows_per_cta, transpose_out)
   if (rank == 16) LAUNCH(1); else if (rank == 32) LAUNCH(2); else LAUNCH(4);
 #undef LAUNCH
   FGB_LAUNCH_CHECK("lora_wgrad_kernel");

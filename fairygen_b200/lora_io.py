@@ -93,6 +93,16 @@ def stage2_state_dict(b2: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return out
 
 
+def stage1_state_dict(trainer) -> Dict[str, torch.Tensor]:
+    """A stage-1 trainer's adapters in the stage-1 checkpoint layout (``<module>.lora_{A,B}.default.weight``, bf16, CPU) —
+    what ``export_trainable_state_dict(remove_prefix="pipe.dit.")`` writes (training_module.py:62-72, logger.py:41)."""
+    out: Dict[str, torch.Tensor] = {}
+    for module in trainer.targets:
+        out[module + A_SUFFIX] = trainer.a1[module].detach().to("cpu").to(torch.bfloat16).contiguous()
+        out[module + B_SUFFIX] = trainer.b2[module].detach().to("cpu").to(torch.bfloat16).contiguous()
+    return out
+
+
 def save_stage2_checkpoint(trainer, path: str) -> None:
     """What ModelLogger.save_model writes during stage-2 training, from a fairygen_b200 Stage2Trainer."""
     import os

@@ -470,16 +470,17 @@ def lora_b2_eff(b2, mask, out, mask_mul=2.0, scaling=1.0):
     return out
 
 
-def lora_wgrad(dy, t, db, mask=None, mul=1.0):
-    """db[n, r] (fp32) += mul * mask * dy[s, n]^T @ t[s, r]."""
+def lora_wgrad(dy, t, db, mask=None, mul=1.0, transpose=False):
+    """db[n, r] (fp32) += mul * mask * dy[s, n]^T @ t[s, r];  transpose=True: db is [r, n] (no mask)."""
     rows, n = dy.shape
     r = t.shape[1]
-    if t.shape[0] != rows or db.dtype != torch.float32 or tuple(db.shape) != (n, r) or not db.is_contiguous():
+    want = (r, n) if transpose else (n, r)
+    if t.shape[0] != rows or db.dtype != torch.float32 or tuple(db.shape) != want or not db.is_contiguous():
         raise ValueError("lora_wgrad shape mismatch")
     if mask is not None and (mask.dtype != torch.uint8 or tuple(mask.shape) != (n, r) or not mask.is_contiguous()):
         raise ValueError("lora_wgrad: mask must be contiguous uint8 [n, r]")
     _lib.check(_lib.lib().fgb_lora_wgrad(_h(dy).handle, _p(dy), _rowmajor(dy, "dy"), _p(t), _rowmajor(t, "t"), _p(db), _p(mask), mul,
-                                         rows, n, r, _stream()), "fgb_lora_wgrad")
+                                         rows, n, r, 1 if transpose else 0, _stream()), "fgb_lora_wgrad")
     return db
 
 

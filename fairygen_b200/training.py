@@ -51,8 +51,17 @@ class _Saved:
 
 
 class Stage2Trainer:
+    """stage = 2 (default): FairyGen's motion stage — A1, B1 frozen, ``lora_B2`` trainable, weight dropout 0.5 (TMOD:266-352).
+    stage = 1: the identity stage — ``lora_A`` and ``lora_B`` trainable, weight dropout 0.8 on B (TMOD:200-264); the same
+    kernels, with ``self.b2`` holding B, no frozen adapter to merge, and dA = (dY·Beff)ᵀ·X from the factor u that the
+    dgrad K-extension computes anyway."""
+
     def __init__(self, engine: WanDiTEngine, lora: Dict[str, torch.Tensor], rank: int = 32, lora_alpha: Optional[float] = None,
-                 dropout_prob: float = 0.5, recompute: bool = False, dp_group=None):
+                 dropout_prob: Optional[float] = None, recompute: bool = False, dp_group=None, stage: int = 2):
+        if stage not in (1, 2):
+            raise ValueError(f"stage must be 1 or 2, got {stage}")
+        self.stage = stage
+        dropout_prob = (0.5 if stage == 2 else 0.8) if dropout_prob is None else dropout_prob
         if not engine.loaded:
             raise RuntimeError("Stage2Trainer needs an engine with loaded (frozen) base weights")
         if engine.sp is not None:
@@ -69,17 +78,35 @@ class Stage2Trainer:
         d, f = cfg.dim, cfg.ffn_dim
         self.targets: List[str] = list(lora_targets(cfg.num_layers))
         out_dim = lambda t: f if t.endswith("ffn.0") else d  # noqa: E731
-        # ---- frozen stage-1 adapters, packed per fused GEMM ------------------------------------------------------
+        # ---- A (frozen in stage 2, trainable in stage 1): one flat bf16 buffer laid out per fused GEMM, so that the
+        #      [3r, D] / [2r, D] operands of the fused q|k|v and cross k|v side GEMMs are views, not copies
         g = lambda k: lora[k].detach().to(device=dev, dtype=BF16).contiguous()  # noqa: E731
+        in_dim = lambda t: f if t.endswith("ffn.2") else d  # noqa: E731
+        self.a_flat = torch.empty(sum(rank * in_dim(t) for t in self.targets), dtype=BF16, device=dev)
+        self.grad_a_flat = torch.zeros(self.a_flat.numel(), dtype=torch.float32, device=dev) if stage == 1 else None
         self.a1: Dict[str, torch.Tensor] = {}
+        self.grad_a: Dict[str, torch.Tensor] = {}
         self.b1: Dict[str, torch.Tensor] = {}
+        self.a1_qkv, self.a1_ckv = [], []
+        off = 0
+        for i in range(cfg.num_layers):      # lora_targets() order: self q,k,v,o, cross q,k,v,o, ffn.0, ffn.2
+            p = f"blocks.{i}."
+            block_start = off
+            for t in [p + "self_attn." + c for c in "qkvo"] + [p + "cross_attn." + c for c in "qkvo"] + [p + "ffn.0", p + "ffn.2"]:
+                n = rank * in_dim(t)
+                self.a1[t] = self.a_flat[off:off + n].view(rank, in_dim(t))
+                if stage == 1:
+                    self.grad_a[t] = self.grad_a_flat[off:off + n].view(rank, in_dim(t))
+                off += n
+            self.a1_qkv.append(self.a_flat[block_start:block_start + 3 * rank * d].view(3 * rank, d))
+            ck = block_start + 5 * rank * d   # after self q,k,v,o and cross q
+            self.a1_ckv.append(self.a_flat[ck:ck + 2 * rank * d].view(2 * rank, d))
         for t in self.targets:
-            self.a1[t] = g(f"{t}.lora_A.default.weight")
+            a = g(f"{t}.lora_A.default.weight")
+            if a.shape[0] != rank:
+                raise ValueError(f"{t}: LoRA rank {a.shape[0]} != {rank}")
+            self.a1[t].copy_(a)
             self.b1[t] = g(f"{t}.lora_B.default.weight")
-            if self.a1[t].shape[0] != rank:
-                raise ValueError(f"{t}: LoRA rank {self.a1[t].shape[0]} != {rank}")
-        self.a1_qkv = [torch.cat([self.a1[f"blocks.{i}.self_attn.{p}"] for p in "qkv"], 0).contiguous() for i in range(cfg.num_layers)]
-        self.a1_ckv = [torch.cat([self.a1[f"blocks.{i}.cross_attn.{p}"] for p in "kv"], 0).contiguous() for i in range(cfg.num_layers)]
         # ---- trainable B2: one flat bf16 parameter buffer, fp32 gradient / Adam moments ---------------------------
         sizes = [out_dim(t) * rank for t in self.targets]
         total = sum(sizes)
@@ -102,11 +129,17 @@ class Stage2Trainer:
         e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
         z = lambda *s: torch.zeros(*s, dtype=BF16, device=dev)  # noqa: E731
         r = rank
-        self.eff = [dict(wqkv=e(3 * d, d), wo=e(d, d), cwq=e(d, d), cwkv=e(2 * d, d), cwo=e(d, d), w1=e(f, d), w2=e(d, f))
-                    for _ in range(cfg.num_layers)]
+        if stage == 2:
+            self.eff = [dict(wqkv=e(3 * d, d), wo=e(d, d), cwq=e(d, d), cwkv=e(2 * d, d), cwo=e(d, d), w1=e(f, d), w2=e(d, f))
+                        for _ in range(cfg.num_layers)]
+        else:   # stage 1: no frozen adapter — the GEMMs read the engine's base weights directly
+            self.eff = [dict(wqkv=b.wqkv, wo=b.wo, cwq=b.cwq, cwkv=b.cwkv, cwo=b.cwo, w1=b.w1, w2=b.w2) for b in engine.blocks]
         self.b2e = [dict(qkv=z(3 * d, 3 * r), o=z(d, r), cq=z(d, r), ckv=z(2 * d, 2 * r), co=z(d, r), f1=z(f, r), f2=z(d, r))
                     for _ in range(cfg.num_layers)]
-        self._merge_static()
+        if stage == 2:
+            self._merge_static()
+        else:
+            self.load_b2({t: self.b1[t] for t in self.targets})   # stage 1 trains B itself (self.b2 is the trainable matrix)
         self.scheduler = FlowMatchScheduler("Wan")
         self.scheduler.set_timesteps(1000, training=True)                               # train.py / LOSS:6-9
         self._saved: List[Optional[_Saved]] = []
@@ -137,6 +170,8 @@ class Stage2Trainer:
 
     def zero_grad(self) -> None:
         self.grad_flat.zero_()
+        if self.grad_a_flat is not None:
+            self.grad_a_flat.zero_()
 
     def _merge_static(self) -> None:
         """W1 = W + s * B1 * A1 for all 300 Linears (row slices of the fused QKV / cross-KV weights) — once."""
@@ -204,7 +239,7 @@ class Stage2Trainer:
             self._x_ckpt = [e(rows, d) for _ in range(cfg.num_layers)] if self.recompute else None
             self._scratch = dict(dx=e(rows, d), t1=e(rows, d), t2=e(rows, d), dqkv=e(rows, 3 * d), dh=e(rows, f), dckv=e(n_ctx, 2 * d),
                                  delta=torch.empty(H, ops.stat_rows(rows), dtype=torch.float32, device=dev), x=e(rows, d),
-                                 x_final=e(rows, d), a_head=e(rows, d), d_hrow=e(rows, cfg.out_dim * 4), u=e(rows, 3 * self.rank))
+                                 x_final=e(rows, d), a_head=e(rows, d), d_hrow=e(rows, cfg.out_dim * 4), u=e(max(rows, n_ctx), 3 * self.rank))
             self._shape_key = key
         return self._scratch
 
@@ -294,13 +329,19 @@ class Stage2Trainer:
     # ------------------------------------------------------------------------------------------------------------
     # backward
     # ------------------------------------------------------------------------------------------------------------
-    def _dgrad(self, dy, w1, b2e, a1, dx) -> None:
+    def _dgrad(self, dy, w1, b2e, a1, dx, x_in=None, names=()) -> None:
         """dX = dY·W1 + (dY·B2eff)·A1: the rank-r factor u = dY·B2eff first (one narrow dgrad), then the main dgrad with u·A1
-        folded in as an extra K-block."""
-        u = self._scratch["u"][:, :b2e.shape[1]]
+        folded in as an extra K-block (dx = None: only u is needed). Stage 1: dA_j += u_jᵀ·X for the Linears in `names`."""
+        u = self._scratch["u"][:dy.shape[0], :b2e.shape[1]]
         ops.gemm_dgrad(dy, b2e, u)
-        ops.gemm_dgrad(dy, w1, dx, u=u, a1=a1)
-        self.kernel_launches += 1
+        if dx is not None:
+            ops.gemm_dgrad(dy, w1, dx, u=u, a1=a1)
+        self.kernel_launches += 2
+        if self.stage == 1:
+            r = self.rank
+            for j, name in enumerate(names):
+                ops.lora_wgrad(x_in, u[:, j * r:(j + 1) * r], self.grad_a[name], None, 1.0, transpose=True)
+                self.kernel_launches += 1
 
     def _wgrad(self, dy, t, name) -> None:
         ops.lora_wgrad(dy, t, self.grad[name], self.mask[name], self.mask_mul * self.scaling)
@@ -318,33 +359,35 @@ class Stage2Trainer:
         # ---- feed-forward branch: x3 = x2 + gate_mlp * ffn2(gelu(ffn0(a3)))                       (DIT:227-228)
         ops.mul_gate(dx, t1, m0[5], m1[5], n_first)
         self._wgrad(t1, s.t_2, p + "ffn.2")
-        self._dgrad(t1, w["w2"], be["f2"], self.a1[p + "ffn.2"], dh)
+        self._dgrad(t1, w["w2"], be["f2"], self.a1[p + "ffn.2"], dh, s.h, (p + "ffn.2",))
         ops.gelu_tanh_bwd(s.z1, dh, dh)
         self._wgrad(dh, s.t_1, p + "ffn.0")
-        self._dgrad(dh, w["w1"], be["f1"], self.a1[p + "ffn.0"], t1)
+        self._dgrad(dh, w["w1"], be["f1"], self.a1[p + "ffn.0"], t1, s.a3, (p + "ffn.0",))
         ops.ln_bwd(s.x2, t1, dx, cfg.eps, m0[4], m1[4], n_first, affine=False, dres=dx)
         # ---- cross-attention branch: x2 = x1 + o(attn(norm_q(q(a2)), norm_k(k(ctx)), v(ctx)))      (DIT:226)
         self._wgrad(dx, s.t_co, p + "cross_attn.o")
-        self._dgrad(dx, w["cwo"], be["co"], self.a1[p + "cross_attn.o"], t1)
+        self._dgrad(dx, w["cwo"], be["co"], self.a1[p + "cross_attn.o"], t1, s.co, (p + "cross_attn.o",))
         ops.attention_bwd(s.cq, s.ckv[:, :d], s.ckv[:, d:], s.co, t1, s.lse_c, t2, dckv[:, :d], dckv[:, d:], H, delta=delta)
         ops.rmsnorm_rope_bwd(s.cq_pre, t2, cfg.eps, b.cnq)
         ops.rmsnorm_rope_bwd(s.ck_pre, dckv[:, :d], cfg.eps, b.cnk)
         self._wgrad(t2, s.t_cq, p + "cross_attn.q")
         self._wgrad(dckv[:, :d], s.t_ckv[:, :r], p + "cross_attn.k")
         self._wgrad(dckv[:, d:], s.t_ckv[:, r:], p + "cross_attn.v")
-        self._dgrad(t2, w["cwq"], be["cq"], self.a1[p + "cross_attn.q"], t1)
+        if self.stage == 1:   # the context has no gradient, but A of cross k / v does: only the factor u is needed
+            self._dgrad(dckv, None, be["ckv"], None, None, st["ctx_emb"], (p + "cross_attn.k", p + "cross_attn.v"))
+        self._dgrad(t2, w["cwq"], be["cq"], self.a1[p + "cross_attn.q"], t1, s.a2, (p + "cross_attn.q",))
         ops.ln_bwd(s.x1, t1, dx, cfg.eps, b.n3w, None, 0, affine=True, dres=dx)
         # ---- self-attention branch: x1 = x0 + gate_msa * o(attn(rope(norm_q(q(a1))), ...))        (DIT:224-225)
         ops.mul_gate(dx, t1, m0[2], m1[2], n_first)
         self._wgrad(t1, s.t_o, p + "self_attn.o")
-        self._dgrad(t1, w["wo"], be["o"], self.a1[p + "self_attn.o"], t2)
+        self._dgrad(t1, w["wo"], be["o"], self.a1[p + "self_attn.o"], t2, s.o, (p + "self_attn.o",))
         ops.attention_bwd(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, t2, s.lse, dqkv[:, :d], dqkv[:, d:2 * d],
                           dqkv[:, 2 * d:], H, delta=delta)
         ops.rmsnorm_rope_bwd(s.qk_pre[:, :d], dqkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, 0)
         ops.rmsnorm_rope_bwd(s.qk_pre[:, d:], dqkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, 0)
         for j, proj in enumerate("qkv"):
             self._wgrad(dqkv[:, j * d:(j + 1) * d], s.t_qkv[:, j * r:(j + 1) * r], p + "self_attn." + proj)
-        self._dgrad(dqkv, w["wqkv"], be["qkv"], self.a1_qkv[i], t1)
+        self._dgrad(dqkv, w["wqkv"], be["qkv"], self.a1_qkv[i], t1, s.a1, tuple(p + "self_attn." + c for c in "qkv"))
         ops.ln_bwd(s.x_in, t1, dx, cfg.eps, m0[1], m1[1], n_first, affine=False, dres=dx)
         self.kernel_launches += 20
 
@@ -370,8 +413,10 @@ class Stage2Trainer:
         if self.dp_group is not None:
             import torch.distributed as dist
 
-            dist.all_reduce(self.grad_flat, group=self.dp_group)
-            self.grad_flat.div_(dist.get_world_size(self.dp_group))   # DDP averages (accelerate, train.py)
+            for gflat in (self.grad_flat, self.grad_a_flat):
+                if gflat is not None:
+                    dist.all_reduce(gflat, group=self.dp_group)
+                    gflat.div_(dist.get_world_size(self.dp_group))   # DDP averages (accelerate, train.py)
 
     # ------------------------------------------------------------------------------------------------------------
     # whole step without autograd (LOSS:5-21)
@@ -409,6 +454,12 @@ class Stage2Trainer:
         self.adam_step += 1
         ops.adamw_step(self.b2_flat, self.grad_flat, self.adam_m, self.adam_v, lr, betas[0], betas[1], eps, weight_decay, self.adam_step)
         self.kernel_launches += 1
+        if self.stage == 1:
+            if getattr(self, "adam_ma", None) is None:
+                self.adam_ma, self.adam_va = torch.zeros_like(self.grad_a_flat), torch.zeros_like(self.grad_a_flat)
+            ops.adamw_step(self.a_flat, self.grad_a_flat, self.adam_ma, self.adam_va, lr, betas[0], betas[1], eps, weight_decay,
+                           self.adam_step)
+            self.kernel_launches += 1
 
     # ------------------------------------------------------------------------------------------------------------
     # autograd bridge: pipe.model_fn under torch.enable_grad (LOSS:17)

@@ -258,9 +258,11 @@ int fgb_lora_merge(fgb_ctx* ctx, const void* w, int64_t ldw, const void* a1, int
 int fgb_lora_b2_eff(fgb_ctx* ctx, const void* b2, const void* mask, float mask_mul, float scaling, void* out, int64_t ld_out,
                     int64_t n_rows, int32_t rank, void* stream);
 
-/* db[n, r] += mul * mask[n, r] * sum_s dy[s, n] * t[s, r]   (fp32 accumulate; t = A1·x, [rows, rank] bf16). */
+/* db[n, r] += mul * mask[n, r] * sum_s dy[s, n] * t[s, r]   (fp32 accumulate; t = A1·x, [rows, rank] bf16).
+ * transpose_out = 1 writes db as [rank, n] instead (mask must be NULL): dA = uᵀ·X of the stage-1 LoRA, called with dy := X,
+ * t := u = dY·Beff (training_module.py:200-264). */
 int fgb_lora_wgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* t, int64_t ld_t, void* db_f32, const void* mask,
-                   float mul, int32_t rows, int32_t n, int32_t rank, void* stream);
+                   float mul, int32_t rows, int32_t n, int32_t rank, int32_t transpose_out, void* stream);
 
 /* keep-mask of the weight dropout on B2 (`torch.rand_like(B2) > p`, TMOD:338-346): counter-based, reproducible per seed. */
 int fgb_bernoulli_mask(fgb_ctx* ctx, void* out_u8, int64_t n, float drop_prob, uint64_t seed, void* stream);

@@ -37,3 +37,27 @@ def test_training_schedule_and_targets():
     m = t.make_masks(cfg)
     frac = np.mean([float(v.float().mean()) for v in m.values()])
     assert 0.45 < frac < 0.55
+
+
+def test_stage1_training_step_matches_reference(golden):
+    """Stage-1 (identity) LoRA: A and B trainable, weight dropout 0.8 (training_module.py:200-264) — loss, prediction and
+    the stored A / B gradients of the REAL reference DiT under autograd."""
+    g = golden("train")
+    cfg = o.TINY
+    w, lora = o.make_weights(cfg, seed=0), o.make_lora(cfg, rank=32, seed=2)
+    masks = t.make_masks_stage1(cfg)
+    shape = (1, 48, 3, 8, 8)
+    x0, _, ctx, _ = o.make_inputs(cfg, shape, text_len=32, live_text=8)
+    noise = torch.randn(shape, generator=torch.Generator().manual_seed(9))
+    loss, pred, grads = t.loss_and_grads_stage1(w, cfg, lora, masks, x0, noise, 500, ctx)
+    assert abs(float(loss) - float(g["s1_loss"])) <= 1e-6 * abs(float(g["s1_loss"]))
+    np.testing.assert_allclose(pred.numpy(), g["s1_pred"], rtol=1e-5, atol=1e-6)
+    stored = [k[len("s1_gradA."):] for k in g if k.startswith("s1_gradA.")]
+    assert len(stored) == 6
+    for name in stored:
+        for tag, key in (("A", f"{name}.lora_A.default.weight"), ("B", f"{name}.lora_B.default.weight")):
+            ref = g[f"s1_grad{tag}.{name}"]
+            assert np.abs(ref).max() > 0, (name, tag)
+            np.testing.assert_allclose(grads[key].numpy(), ref, rtol=2e-4, atol=1e-8 + 2e-5 * np.abs(ref).max(), err_msg=f"{name} {tag}")
+    frac = np.mean([float(v.float().mean()) for v in masks.values()])
+    assert 0.17 < frac < 0.23          # keep probability 0.2

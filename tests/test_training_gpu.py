@@ -311,3 +311,43 @@ def test_training_entry_points_reject_bad_arguments(env):
     with pytest.raises(ValueError):
         ops.gelu_tanh(rnd(8, 16), torch.empty(8, 8, dtype=BF, device="cuda"))
     ops.sync_check()   # none of the rejected calls launched anything
+
+
+def test_stage1_training_step_vs_oracle(env):
+    """Stage 1 (identity LoRA, training_module.py:200-264): A and B trainable, weight dropout 0.8 on B. Same kernels; dA comes
+    from the rank-r factor u = dY·Beff of the dgrad K-extension (fgb_lora_wgrad with transposed output)."""
+    fg, ops, o, t = env
+    from fairygen_b200 import lora_io
+    from fairygen_b200.training import Stage2Trainer
+    ocfg = o.TINY
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    w, lora = o.make_weights(ocfg, seed=0), o.make_lora(ocfg, rank=32, seed=2)
+    masks = t.make_masks_stage1(ocfg)
+    eng = fg.WanDiTEngine(cfg, "cuda")
+    eng.load_state_dict(w)
+    shape = (1, 48, 3, 8, 8)
+    x0, _, ctx, _ = o.make_inputs(ocfg, shape, text_len=32, live_text=8)
+    noise = torch.randn(shape, generator=torch.Generator().manual_seed(9))
+    tr = Stage2Trainer(eng, lora, rank=32, stage=1)
+    assert tr.mask_mul == pytest.approx(5.0)
+    tr.zero_grad()
+    loss, pred = tr.step(x0, noise, 500, ctx.cuda(), masks=masks, return_pred=True)
+    ops.sync_check()
+    r = lambda v: v.to(BF).float().cuda()  # noqa: E731
+    loss_ref, pred_ref, grads_ref = t.loss_and_grads_stage1({k: r(v) for k, v in w.items()}, ocfg, {k: r(v) for k, v in lora.items()},
+                                                            {k: v.cuda() for k, v in masks.items()}, r(x0), r(noise), 500, r(ctx),
+                                                            timestep_dtype=BF)
+    assert rel_l2(pred, pred_ref) < 1e-2
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
+    worst_a = max(rel_l2(tr.grad_a[n], grads_ref[f"{n}.lora_A.default.weight"]) for n in tr.targets)
+    worst_b = max(rel_l2(tr.grad[n], grads_ref[f"{n}.lora_B.default.weight"]) for n in tr.targets)
+    print(f"stage 1: pred {rel_l2(pred, pred_ref):.3e} loss {float(loss):.6f} vs {float(loss_ref):.6f} worst dA {worst_a:.3e} dB {worst_b:.3e}")
+    assert worst_a < 5e-2 and worst_b < 5e-2
+    for n in tr.targets:
+        assert torch.all(tr.grad[n][masks[n].cuda() == 0] == 0), n
+    before_a, before_b = tr.a_flat.clone(), tr.b2_flat.clone()
+    tr.optimizer_step(lr=1e-3, weight_decay=0.0)
+    ops.sync_check()
+    assert (tr.a_flat != before_a).any() and (tr.b2_flat != before_b).any()
+    sd = lora_io.stage1_state_dict(tr)
+    assert set(sd) == set(lora) and all(v.dtype == BF for v in sd.values())
