@@ -188,7 +188,16 @@ int main(int argc, char** argv) {
     const int64_t LDS = (SQ + 63) / 64 * 64;
     CK(cudaMalloc(&lse, (size_t)LDS * H * 4));
     printf("attn workspace %lld bytes\n", (long long)ws_bytes);
-    auto run = [&]() { return fgb_attn_fwd_ex(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, lse, LDS, ws, ws_bytes, nullptr); };
+    // KCHECK_BOUNDED=1: bounded-score softmax (the engine's default): key-norm bound first, then fgb_attn_fwd_bounded
+    float* kmax2 = nullptr;
+    if (getenv("KCHECK_BOUNDED")) {
+      CK(cudaMalloc(&kmax2, H * 4));
+      FK(fgb_head_norm_max(ctx, k, W, SKV, H, kmax2, nullptr));
+    }
+    auto run = [&]() {
+      if (kmax2) return fgb_attn_fwd_bounded(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, kmax2, lse, LDS, ws, ws_bytes, nullptr, 0, 0, 0, nullptr);
+      return fgb_attn_fwd_ex(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, lse, LDS, ws, ws_bytes, nullptr);
+    };
     FK(run());
     FK(fgb_sync_check(ctx, nullptr));
     if (check) {
