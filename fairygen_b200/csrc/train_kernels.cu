@@ -600,11 +600,11 @@ extern "C" int fgb_lora_wgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const
   FGB_CHECK_ARG(!(transpose_out && mask), "fgb_lora_wgrad: a mask applies to the [n, rank] layout only");
   FGB_CHECK_ARG(ld_dy % 8 == 0 && ld_t % 8 == 0 && aligned16(dy) && aligned16(t), "fgb_lora_wgrad: operands must be 16-byte aligned");
   const int n_tiles = (n + 63) / 64;
-  // enough token chunks to fill the machine ~4x over; each chunk a multiple of 32 rows
-  int splits = (4 * ctx->sm_count + n_tiles - 1) / n_tiles;
+  // enough token chunks to fill the machine ~10x over (each CTA keeps only one 12 KB chunk in flight); multiples of 64 rows
+  int splits = (10 * ctx->sm_count + n_tiles - 1) / n_tiles;
   int rows_per_cta = ((rows + splits - 1) / splits + 31) / 32 * 32;
   rows_per_cta = (rows_per_cta + 63) / 64 * 64;
-  if (rows_per_cta < 256) rows_per_cta = 256;
+  if (rows_per_cta < 128) rows_per_cta = 128;
   splits = (rows + rows_per_cta - 1) / rows_per_cta;
   dim3 grid(n_tiles, splits);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

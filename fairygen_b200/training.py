@@ -263,7 +263,8 @@ class Stage2Trainer:
         s.qk_pre.copy_(s.qkv[:, :2 * d])
         ops.rmsnorm_rope(s.qkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, 0)
         ops.rmsnorm_rope(s.qkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, 0)
-        ops.attention(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, H, lse=s.lse)
+        ops.head_norm_max(s.qkv[:, d:2 * d], st["kmax2"], H)
+        ops.attention(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, H, lse=s.lse, kmax2=st["kmax2"])
         ops.gemm(s.o, self.a1[f"blocks.{i}.self_attn.o"], None, s.t_o)
         ops.gemm(s.o, w["wo"], b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first, a2=s.t_o, w2=be["o"])
         s.x1.copy_(x)
@@ -276,7 +277,8 @@ class Stage2Trainer:
         ops.gemm(ctx_emb, w["cwkv"], b.cbkv, s.ckv, a2=s.t_ckv, w2=be["ckv"])
         s.ck_pre.copy_(s.ckv[:, :d])
         ops.rmsnorm_rope(s.ckv[:, :d], cfg.eps, b.cnk)
-        ops.attention(s.cq, s.ckv[:, :d], s.ckv[:, d:], s.co, H, lse=s.lse_c)
+        ops.head_norm_max(s.ckv[:, :d], st["kmax2"], H)
+        ops.attention(s.cq, s.ckv[:, :d], s.ckv[:, d:], s.co, H, lse=s.lse_c, kmax2=st["kmax2"])
         ops.gemm(s.co, self.a1[f"blocks.{i}.cross_attn.o"], None, s.t_co)
         ops.gemm(s.co, w["cwo"], b.cbo, x, EPI_RESIDUAL, a2=s.t_co, w2=be["co"])
         s.x2.copy_(x)
@@ -286,7 +288,7 @@ class Stage2Trainer:
         ops.gelu_tanh(s.z1, s.h)
         ops.gemm(s.h, self.a1[f"blocks.{i}.ffn.2"], None, s.t_2)
         ops.gemm(s.h, w["w2"], b.b2, x, EPI_GATED_RESIDUAL, m0[5], m1[5], n_first, a2=s.t_2, w2=be["f2"])
-        self.kernel_launches += 25
+        self.kernel_launches += 34
 
     def forward_train(self, latents: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor,
                       fuse_vae_embedding_in_latents: bool = True) -> torch.Tensor:
@@ -306,7 +308,7 @@ class Stage2Trainer:
         ctx_emb = eng.text_embedding(context)
         sc = self._buffers(S, ctx_emb.shape[0])
         L = cfg.num_layers
-        st = dict(grid=grid, S=S, n_first=n_first, ctx_emb=ctx_emb,
+        st = dict(grid=grid, S=S, n_first=n_first, ctx_emb=ctx_emb, kmax2=ws["kmax2"],
                   m0=[mod_tab[0, i].view(6, d) for i in range(L)], m1=[mod_tab[r_main, i].view(6, d) for i in range(L)],
                   h0=head_tab[0].view(2, d), h1=head_tab[r_main].view(2, d), lat_dtype=latents.dtype)
         x = sc["x"]
