@@ -312,8 +312,9 @@ lora_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const __n
   constexpr int R = 16 * NR;
   constexpr int kChunk = 64;                       // tokens per step
   constexpr int kTV = kChunk * R / 8 / 128;        // 16-byte vectors of t per thread per chunk (R = 16/32/64 -> 1/2/4)
-  __shared__ __align__(32) __nv_bfloat16 s_dy[kChunk * 64];
-  __shared__ __align__(32) __nv_bfloat16 s_t[kChunk * R];
+  constexpr int kLdDy = 64 + 8, kLdT = R + 8;     // 16 bytes of padding per row: the transposed (col-major) A fragments
+  __shared__ __align__(32) __nv_bfloat16 s_dy[kChunk * kLdDy];   // of wmma would otherwise hit the same banks 16 ways
+  __shared__ __align__(32) __nv_bfloat16 s_t[kChunk * kLdT];
   __shared__ __align__(32) float s_out[64 * R];
   const int n0 = blockIdx.x * 64;
   const int s_begin = blockIdx.y * rows_per_cta;
@@ -344,23 +345,23 @@ lora_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int64_t ld_dy, const __n
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = threadIdx.x + j * 128;
-      *reinterpret_cast<uint4*>(s_dy + (i >> 3) * 64 + (i & 7) * 8) = rdy[j];
+      *reinterpret_cast<uint4*>(s_dy + (i >> 3) * kLdDy + (i & 7) * 8) = rdy[j];
     }
 #pragma unroll
     for (int j = 0; j < kTV; ++j) {
       const int i = threadIdx.x + j * 128;
-      *reinterpret_cast<uint4*>(s_t + (i / (R / 8)) * R + (i % (R / 8)) * 8) = rt[j];
+      *reinterpret_cast<uint4*>(s_t + (i / (R / 8)) * kLdT + (i % (R / 8)) * 8) = rt[j];
     }
     __syncthreads();
     if (s0 + kChunk < s_end) fetch(s0 + kChunk);
 #pragma unroll
     for (int ks = 0; ks < kChunk / 16; ++ks) {
       wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa;  // A[n_i, s_k] = dy[s_k, n_i]
-      wmma::load_matrix_sync(fa, s_dy + ks * 16 * 64 + warp * 16, 64);
+      wmma::load_matrix_sync(fa, s_dy + ks * 16 * kLdDy + warp * 16, kLdDy);
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
-        wmma::load_matrix_sync(fb, s_t + ks * 16 * R + j * 16, R);
+        wmma::load_matrix_sync(fb, s_t + ks * 16 * kLdT + j * 16, kLdT);
         wmma::mma_sync(acc[j], fa, fb, acc[j]);
       }
     }
