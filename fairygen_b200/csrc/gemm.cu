@@ -186,12 +186,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const __nv_bfloat16* gate = nullptr;
       if (EPI == FGB_EPI_GATED_RESIDUAL) gate = (row < p.rows_gate0) ? p.gate0 : p.gate1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kBN;
+      // residual epilogues read C: the 64 bytes of the NEXT 32-column chunk are requested before the current chunk is
+      // processed, so their latency hides under the TMEM load and the math (with K = 3072 the epilogue of a tile is as
+      // long as its main loop, and a serial load -> use chain per chunk cost 15 %)
+      constexpr bool kReadsC = (EPI == FGB_EPI_GATED_RESIDUAL || EPI == FGB_EPI_RESIDUAL);
+      uint4 xcur[4], xnext[4];
+      auto load_c = [&](int c, uint4 (&dst)[4]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = n_blk * kBN + c * 32 + g * 8;
+          dst[g] = (row_ok && col < p.n) ? *reinterpret_cast<const uint4*>(crow + col) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (kReadsC) load_c(0, xcur);
 #pragma unroll 1
       for (int c = 0; c < kBN / 32; ++c) {
         const int col0 = n_blk * kBN + c * 32;
         if (col0 >= p.n) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
+        if (kReadsC && c + 1 < kBN / 32) load_c(c + 1, xnext);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -210,9 +224,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = gelu_tanh_f(y[i]);
           }
-          if (EPI == FGB_EPI_GATED_RESIDUAL || EPI == FGB_EPI_RESIDUAL) {
+          if (kReadsC) {
             if (row_ok) {
-              const uint4 xv = *reinterpret_cast<const uint4*>(crow + col);
+              const uint4 xv = xcur[g];
               const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
               if (EPI == FGB_EPI_GATED_RESIDUAL) {
                 const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gate + col));
@@ -239,6 +253,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             o.w = pack_bf16(y[6], y[7]);
             *reinterpret_cast<uint4*>(crow + col) = o;
           }
+        }
+        if (kReadsC) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) xcur[g] = xnext[g];
         }
       }
       tc_fence_before();
