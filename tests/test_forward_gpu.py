@@ -172,3 +172,41 @@ def test_on_gpu_lora_fuse_matches_reference_fuse(env):
     lat, z0, cp, cn = o.make_inputs(o.TINY, (1, 48, 3, 8, 8), text_len=32, live_text=8)
     ts = torch.tensor([900.0])
     assert rel_l2(eng.forward(lat.cuda(), ts, cp.cuda(), True), ref_eng.forward(lat.cuda(), ts, cp.cuda(), True)) < 5e-3
+
+
+@pytest.mark.parametrize("real_dims", [False, True])
+def test_full_50_step_schedule_vs_reference_bf16_chain(env, real_dims):
+    """North star: latent relative L2 <= 3e-2 after the FULL 50-step CFG schedule (wan_video.py:282-309) against the reference's
+    bf16 path — the oracle's restatement run in bf16 on the same GPU (cuBLAS / SDPA) — and both against the fp32 oracle, to show
+    that our accumulated error is of the size of the reference's own bf16 error. Tiny model (S = 48) and TI2V-5B block shapes
+    (D = 3072, 24 heads, F = 14336, merged rank-32 LoRA; 2 layers, S = 320)."""
+    fg, o = env
+    if real_dims:
+        cfg, ocfg, sd, eng, lat, cp = _real_dim_case(fg, o, 2, (1, 48, 5, 16, 16))
+        from fairygen_b200 import synthetic
+        _, z0, _, cn = synthetic.synthetic_inputs(cfg, (1, 48, 5, 16, 16), text_len=512, pin=False)
+        z0, cn = z0.cuda(), cn.cuda()
+        w = sd
+    else:
+        ocfg = o.TINY
+        w = {k: v.cuda() for k, v in o.make_weights(ocfg, seed=0).items()}
+        eng = tiny_engine(fg, o)
+        lat, z0, cp, cn = (t.cuda() for t in o.make_inputs(ocfg, (1, 48, 3, 8, 8), text_len=32, live_text=8))
+    den = fg.WanDenoiser(eng, num_inference_steps=50, cfg_scale=5.0, sigma_shift=5.0)
+    ours = den(lat, cp, cn, z0)
+    fg.ops.sync_check()
+    with torch.no_grad():
+        w16 = {k: v.to(BF) for k, v in w.items()}
+        start16 = lat.to(BF).clone()
+        start16[:, :, 0:1] = z0.to(BF)
+        ref16 = o.denoise(w16, ocfg, start16, cp.to(BF), cn.to(BF), z0.to(BF), 50, 5.0, 5.0)
+        w32 = {k: v.to(BF).float() for k, v in w.items()}
+        start32 = lat.to(BF).float().clone()
+        start32[:, :, 0:1] = z0.to(BF).float()
+        ref32 = o.denoise(w32, ocfg, start32, cp.to(BF).float(), cn.to(BF).float(), z0.to(BF).float(), 50, 5.0, 5.0)
+    e_ours16, e_ours32, e_ref = rel_l2(ours, ref16), rel_l2(ours, ref32), rel_l2(ref16, ref32)
+    print(f"50-step schedule ({'real dims' if real_dims else 'tiny'}): ours-vs-ref_bf16 {e_ours16:.3e}  ours-vs-fp32 {e_ours32:.3e}  "
+          f"ref_bf16-vs-fp32 {e_ref:.3e}")
+    assert torch.isfinite(ours.float()).all()
+    assert e_ours16 < SCHEDULE_TOL
+    assert e_ours32 < max(SCHEDULE_TOL, 2.0 * e_ref)
