@@ -54,26 +54,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): halves the issue slots of the softmax ----
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 // 2^x for a pair on the FMA/ALU pipes instead of the MUFU (which is as busy as the tensor pipe in this
 // kernel): round-to-nearest split x = n + f via the 1.5*2^23 trick, degree-3 minimax polynomial for 2^f
 // on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), exponent add in integer.

@@ -54,6 +54,20 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
   n_blk = in_group / gsz;
 }
 
+// two elements per instruction on the FMA pipe (fp32x2); tanh stays on the MUFU
+__device__ __forceinline__ void gelu_tanh_2(float& x0, float& x1) {
+  const float kAlpha = 0.7978845608028654f, kAB = 0.7978845608028654f * 0.044715f;
+  const uint64_t x2 = pack2(x0, x1);
+  const uint64_t t = fma2(mul2(x2, x2), pack2(kAB, kAB), pack2(kAlpha, kAlpha));   // alpha * (1 + beta x^2)
+  float i0, i1;
+  unpack2(mul2(t, x2), i0, i1);
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(i0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(i1));
+  const uint64_t h = mul2(x2, pack2(0.5f, 0.5f));
+  unpack2(fma2(h, pack2(t0, t1), h), x0, x1);
+}
+
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  — nn.GELU(approximate='tanh')
   const float kAlpha = 0.7978845608028654f, kBeta = 0.044715f;
@@ -222,7 +236,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (EPI == FGB_EPI_BIAS_GELU_TANH) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = gelu_tanh_f(y[i]);
+            for (int i = 0; i < 8; i += 2) gelu_tanh_2(y[i], y[i + 1]);
           }
           if (kReadsC) {
             if (row_ok) {
