@@ -2,8 +2,10 @@
 Wan2.2-TI2V-5B DiT denoising step behind the reference's ``pipe.model_fn`` surface.
 
 Only what the path needs lives here: ``csrc/`` (CUDA kernels + C ABI), the ctypes binding, the
-engine that mirrors ``model_fn_wan_video``, the fused flow-match scheduler, the denoise loop and
-the Ulysses sequence-parallel exchange.  There is no CPU or PyTorch fallback.
+engine that mirrors ``model_fn_wan_video``, the fused flow-match scheduler, the denoise loop, the
+Ulysses / CFG / shot parallel layout (NVLink peer-store exchange), the stage-1/2 LoRA trainer
+(hand-written backward), LoRA checkpoint formats and checkpoint detection / loading.  There is no CPU
+or PyTorch fallback.
 """
 from .config import TI2V_5B, WanDiTConfig, counted_flops  # noqa: F401
 

@@ -14,7 +14,8 @@ it whenever a parameter's version counter changes.
 
 Anything outside the TI2V-5B inference path (VACE, S2V audio, Animate, VAP, LongCat, camera/motion
 controllers, reference latents, TeaCache, sliding windows, CLIP/VAE-concat image inputs) raises
-``NotImplementedError`` instead of silently falling back.
+``NotImplementedError`` instead of silently falling back; so does a call under autograd with trainable
+parameters — LoRA training goes through ``fairygen_b200.training.Stage2Trainer`` (same kernels + hand-written backward).
 """
 from __future__ import annotations
 
@@ -101,7 +102,8 @@ def model_fn_wan_video(
     if clip_feature is not None and getattr(dit, "require_clip_embedding", False):
         _reject("clip_feature", clip_feature)
     if torch.is_grad_enabled() and any(p.requires_grad for p in dit.parameters()):
-        raise NotImplementedError("fairygen_b200 model_fn is forward-only (inference path); training backward is §8 'next'")
+        raise NotImplementedError("fairygen_b200.model_fn_wan_video is the inference path (no autograd graph); for LoRA training use "
+                                  "fairygen_b200.training.Stage2Trainer.model_fn, which back-propagates through the same kernels")
     if latents is None or timestep is None or context is None or dit is None:
         raise ValueError("model_fn_wan_video needs dit, latents, timestep and context")
 
