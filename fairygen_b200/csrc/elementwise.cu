@@ -385,6 +385,27 @@ __global__ void sp_scatter_heads_kernel(const __nv_bfloat16* __restrict__ x, int
   }
 }
 
+// Reverse direction (backward of the Ulysses exchange): x [s_pad][groups][heads/world][128] — this rank's heads, ALL tokens
+// (e.g. dq|dk|dv from fgb_attn_bwd) -> the token-major matrix [rows][groups][heads][128] of the rank that owns each token.
+__global__ void sp_return_heads_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, PeerPtrs peers, int64_t ld_dst, int rows,
+                                       int s_pad, int heads, int groups, int world, int rank) {
+  const int hpr = heads / world;
+  const int gh = groups * hpr;
+  const int64_t total = static_cast<int64_t>(s_pad) * gh * 16;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(idx & 15);
+    const int g_head = static_cast<int>((idx >> 4) % gh);
+    const int64_t s = (idx >> 4) / gh;
+    const int grp = g_head / hpr, hh = g_head % hpr;
+    const int peer = static_cast<int>(s / rows);
+    const uint4 v = ldg_nc_v4(reinterpret_cast<const uint4*>(x + s * ldx + static_cast<int64_t>(g_head) * 128) + vec);
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(peers.p[peer]) + (s - static_cast<int64_t>(peer) * rows) * ld_dst +
+                         static_cast<int64_t>(grp) * heads * 128 + (rank * hpr + hh) * 128;
+    reinterpret_cast<uint4*>(dst)[vec] = v;
+  }
+}
+
 // Cross-GPU barrier for the exchange: thread q publishes `epoch` in peer q's flag slot [rank] (release, system scope)
 // and then waits until peer q has published `epoch` in ours (acquire). All earlier peer stores of this stream are
 // complete (kernel boundary) and made visible by the fence. Bounded: traps after ~30 s (ranks can be seconds apart at
@@ -689,5 +710,24 @@ extern "C" int fgb_head_norm_max(fgb_ctx* ctx, const void* x, int64_t ldx, int32
   }
 #undef FGB_HNM_CASE
   FGB_LAUNCH_CHECK("head_norm_max_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_sp_return_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* const* peer_bufs, int64_t ld_dst, int32_t rows,
+                                   int32_t s_pad, int32_t heads, int32_t groups, int32_t world, int32_t rank, void* stream) {
+  FGB_CHECK_ARG(ctx && x && peer_bufs, "fgb_sp_return_heads: NULL argument");
+  FGB_CHECK_ARG(rows > 0 && s_pad == rows * world && heads > 0 && groups > 0 && world > 0 && world <= FGB_MAX_PEERS && heads % world == 0 &&
+                    rank >= 0 && rank < world, "fgb_sp_return_heads: rows=%d s_pad=%d heads=%d world=%d rank=%d", rows, s_pad, heads, world, rank);
+  FGB_CHECK_ARG(ldx % 8 == 0 && ldx >= static_cast<int64_t>(groups) * (heads / world) * 128 && aligned16(x) && ld_dst % 8 == 0 &&
+                    ld_dst >= static_cast<int64_t>(groups) * heads * 128, "fgb_sp_return_heads: alignment / leading dimensions");
+  PeerPtrs pp;
+  for (int i = 0; i < FGB_MAX_PEERS; ++i) pp.p[i] = i < world ? peer_bufs[i] : nullptr;
+  for (int i = 0; i < world; ++i) FGB_CHECK_ARG(pp.p[i] && aligned16(pp.p[i]), "fgb_sp_return_heads: peer buffer %d", i);
+  const int64_t total = static_cast<int64_t>(s_pad) * groups * (heads / world) * 16;
+  int grid = grid_1d(total, 256);
+  if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+  sp_return_heads_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x), ldx, pp, ld_dst, rows, s_pad,
+                                                                            heads, groups, world, rank);
+  FGB_LAUNCH_CHECK("sp_return_heads_kernel");
   return FGB_OK;
 }

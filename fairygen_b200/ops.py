@@ -325,12 +325,19 @@ def rmsnorm_rope_scatter(x, eps, weight, rope_tab, grid, token_offset, peer_ptrs
                "fgb_rmsnorm_rope_scatter")
 
 
+def sp_return_heads(x, peer_ptrs, ld_dst: int, rows: int, heads: int, groups: int, world: int, rank: int):
+    """x [rows*world, groups*(heads/world)*128] (this rank's heads, all tokens) -> the token owners' [rows, groups*heads*128]."""
+    ldx = _rowmajor(x, "x")
+    _lib.check(_lib.lib().fgb_sp_return_heads(_h(x).handle, _p(x), ldx, _ptr_array(peer_ptrs), ld_dst, rows, x.shape[0], heads, groups,
+                                              world, rank, _stream()), "fgb_sp_return_heads")
+
+
 def sp_barrier(device, flag_ptrs, world: int, rank: int, epoch: int):
     _lib.check(_lib.lib().fgb_sp_barrier(context(device).handle, _ptr_array(flag_ptrs), world, rank, epoch, _stream()), "fgb_sp_barrier")
 
 
 def attention_scatter(q, k, v, o_peer_ptrs, ldo: int, rows_per_peer: int, col_offset: int, heads: int, scale: Optional[float] = None,
-                      kmax2: Optional[torch.Tensor] = None):
+                      kmax2: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None):
     """attention() whose output rows go straight into the token-major o buffers of the ranks that own the tokens."""
     ldq, ldk, ldv = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v")
     s_q, s_kv = q.shape[0], k.shape[0]
@@ -341,9 +348,12 @@ def attention_scatter(q, k, v, o_peer_ptrs, ldo: int, rows_per_peer: int, col_of
     ws = attention_workspace(s_q, s_kv, heads, q.device)
     if kmax2 is not None:
         _lib.check(_lib.lib().fgb_attn_fwd_bounded(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, None, ldo, s_q, s_kv, heads, scale,
-                                                   _p(kmax2), None, 0, _p(ws), 0 if ws is None else ws.numel(), _ptr_array(o_peer_ptrs),
+                                                   _p(kmax2), _p(lse), 0 if lse is None else lse.shape[1], _p(ws),
+                                                   0 if ws is None else ws.numel(), _ptr_array(o_peer_ptrs),
                                                    len(o_peer_ptrs), rows_per_peer, col_offset, _stream()), "fgb_attn_fwd_bounded")
         return
+    if lse is not None:
+        raise ValueError("attention_scatter: lse needs the bounded form (pass kmax2)")
     _lib.check(_lib.lib().fgb_attn_fwd_scatter(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _ptr_array(o_peer_ptrs), len(o_peer_ptrs), ldo,
                                                rows_per_peer, col_offset, s_q, s_kv, heads, scale, _p(ws), 0 if ws is None else ws.numel(),
                                                _stream()), "fgb_attn_fwd_scatter")

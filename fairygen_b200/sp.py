@@ -54,18 +54,21 @@ class PeerArena:
     kernel reads), ``o`` is where the peers' attention epilogues store this rank's token rows, ``flags`` carries the
     epochs of fgb_sp_barrier.  torch.distributed is used once, to swap the 64-byte IPC handles."""
 
-    def __init__(self, group, world: int, rank: int, rows: int, heads: int, device):
+    def __init__(self, group, world: int, rank: int, rows: int, heads: int, device, backward: bool = False):
         self.group, self.world, self.rank, self.rows, self.device = group, world, rank, rows, device
+        self.backward = backward
         s_pad = rows * world
         wloc = 3 * (heads // world) * 128
         d = heads * 128
         self.off_recv = 0
         self.off_o = (s_pad * wloc * 2 + 255) // 256 * 256
-        self.off_flags = self.off_o + (rows * d * 2 + 255) // 256 * 256
+        self.off_dqkv = self.off_o + (rows * d * 2 + 255) // 256 * 256      # training only: [rows, 3*H*128] gradient matrix
+        self.off_flags = self.off_dqkv + ((rows * 3 * d * 2 + 255) // 256 * 256 if backward else 0)
         total = self.off_flags + 2 * 64 * 4
         self.buf = torch.zeros(total, dtype=torch.uint8, device=device)
         self.recv = self.buf[self.off_recv:self.off_recv + s_pad * wloc * 2].view(torch.bfloat16).view(s_pad, wloc)
         self.o = self.buf[self.off_o:self.off_o + rows * d * 2].view(torch.bfloat16).view(rows, d)
+        self.dqkv = self.buf[self.off_dqkv:self.off_dqkv + rows * 3 * d * 2].view(torch.bfloat16).view(rows, 3 * d) if backward else None
         handle, offset = ops.ipc_export(self.buf)
         everyone = [None] * world
         dist.all_gather_object(everyone, (handle, offset), group=group)
@@ -80,6 +83,7 @@ class PeerArena:
                 bases.append(ptr)
         self.recv_ptrs = [b + self.off_recv for b in bases]
         self.o_ptrs = [b + self.off_o for b in bases]
+        self.dqkv_ptrs = [b + self.off_dqkv for b in bases]
         self.flag_ptrs = [[b + self.off_flags + which * 64 * 4 for b in bases] for which in (0, 1)]
         self.epoch = 0
         torch.cuda.synchronize(device)
@@ -105,12 +109,19 @@ class SequenceParallel:
         self.exchange = exchange
         self.arena = None
 
-    def peer_arena(self, rows: int, heads: int, device) -> PeerArena:
-        if self.arena is None or self.arena.rows != rows:
+    def peer_arena(self, rows: int, heads: int, device, backward: bool = False) -> PeerArena:
+        if self.arena is None or self.arena.rows != rows or (backward and not self.arena.backward):
             if self.arena is not None:
                 self.arena.close()
-            self.arena = PeerArena(self.group, self.world, self.rank, rows, heads, device)
+            self.arena = PeerArena(self.group, self.world, self.rank, rows, heads, device, backward=backward)
         return self.arena
+
+    def barrier(self, which: int, device) -> None:
+        """System-scope barrier of the exchange (which = 0 / 1: the two alternating flag sets)."""
+        ar = self.arena
+        if which == 0:
+            ar.epoch += 1
+        ops.sp_barrier(device, ar.flag_ptrs[which], self.world, self.rank, ar.epoch)
 
     # ---- collectives (thin: NCCL on device tensors, gloo in the CPU tests) ----------------------
     def all_to_all(self, recv: torch.Tensor, send: torch.Tensor) -> torch.Tensor:

@@ -18,6 +18,11 @@ Here:
     GELU / gate backward kernels, and ``fgb_lora_wgrad`` for dB2 = (dyᵀ A1x) * mask * 2 in fp32.
 Only ``lora_B2`` receives gradients (TMOD:279-307); base weights, A1, B1, norms and modulations are frozen.
 
+With an engine built on a ``SequenceParallel(exchange="p2p")`` group the trainer splits the tokens of one video over the
+group ("SP ... reuses the same exchange in backward"): the forward exchange of the inference path, and in the
+backward O, dO -> head owners, ``fgb_attn_bwd`` on the local heads, dq|dk|dv -> token owners (``fgb_sp_return_heads``), all
+as NVLink peer stores from our kernels, then one sum all-reduce of this backward's LoRA gradients.
+
 ``Stage2Trainer.model_fn`` wraps forward/backward in a ``torch.autograd.Function`` so the reference's own
 ``FlowMatchSFTLoss`` / ``loss.backward()`` drive it unchanged; ``Stage2Trainer.step`` runs the whole step (noise,
 forward, loss, backward) without autograd.
@@ -64,8 +69,9 @@ class Stage2Trainer:
         dropout_prob = (0.5 if stage == 2 else 0.8) if dropout_prob is None else dropout_prob
         if not engine.loaded:
             raise RuntimeError("Stage2Trainer needs an engine with loaded (frozen) base weights")
-        if engine.sp is not None:
-            raise NotImplementedError("training runs data-parallel (one video per GPU); sequence-parallel backward is not built")
+        self.sp = engine.sp   # Ulysses group: tokens of ONE video split over its ranks, forward and backward (see _sp_*)
+        if self.sp is not None and getattr(self.sp, "exchange", "nccl") != "p2p":
+            raise NotImplementedError("sequence-parallel training uses the peer-memory exchange: SequenceParallel(exchange='p2p')")
         self.engine = engine
         self.cfg = engine.cfg
         self.rank = rank
@@ -216,16 +222,17 @@ class Stage2Trainer:
     def _alloc_saved(self, rows: int, n_ctx: int) -> _Saved:
         cfg, dev = self.cfg, self.engine.device
         d, f, r, H = cfg.dim, cfg.ffn_dim, self.rank, cfg.num_heads
+        P = self.sp.world if self.sp is not None else 1
         e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
         s = _Saved()
         s.x_in, s.a1, s.o, s.x1, s.a2, s.cq_pre, s.cq, s.co, s.x2, s.a3 = (e(rows, d) for _ in range(10))
-        s.qk_pre, s.qkv = e(rows, 2 * d), e(rows, 3 * d)
+        # q|k|v after norm + RoPE: [rows, 3*H*128], or under SP the exchanged matrix [rows*P tokens, 3*(H/P)*128]
+        s.qk_pre, s.qkv = e(rows, 2 * d), e(rows * P, 3 * d // P)
         s.ck_pre, s.ckv = e(n_ctx, d), e(n_ctx, 2 * d)
         s.z1, s.h = e(rows, f), e(rows, f)
         s.t_qkv, s.t_o, s.t_cq, s.t_ckv, s.t_co, s.t_1, s.t_2 = e(rows, 3 * r), e(rows, r), e(rows, r), e(n_ctx, 2 * r), e(rows, r), e(rows, r), e(rows, r)
-        ld = ops.stat_rows(rows)
-        s.lse = torch.zeros(H, ld, dtype=torch.float32, device=dev)
-        s.lse_c = torch.zeros(H, ld, dtype=torch.float32, device=dev)
+        s.lse = torch.zeros(H // P, ops.stat_rows(rows * P), dtype=torch.float32, device=dev)
+        s.lse_c = torch.zeros(H, ops.stat_rows(rows), dtype=torch.float32, device=dev)
         return s
 
     def _buffers(self, rows: int, n_ctx: int):
@@ -240,6 +247,12 @@ class Stage2Trainer:
             self._scratch = dict(dx=e(rows, d), t1=e(rows, d), t2=e(rows, d), dqkv=e(rows, 3 * d), dh=e(rows, f), dckv=e(n_ctx, 2 * d),
                                  delta=torch.empty(H, ops.stat_rows(rows), dtype=torch.float32, device=dev), x=e(rows, d),
                                  x_final=e(rows, d), a_head=e(rows, d), d_hrow=e(rows, cfg.out_dim * 4), u=e(max(rows, n_ctx), 3 * self.rank))
+            if self.sp is not None:
+                P = self.sp.world
+                z = lambda *s: torch.zeros(*s, dtype=BF16, device=dev)  # noqa: E731
+                # dloc: dq|dk|dv of this rank's heads for all tokens; its padded key rows are never written and stay zero
+                self._scratch.update(qkv_tok=e(rows, 3 * d), dloc=z(rows * P, 3 * d // P), d_hrow_full=z(rows * P, cfg.out_dim * 4),
+                                     delta_sp=torch.empty(H // P, ops.stat_rows(rows * P), dtype=torch.float32, device=dev))
             self._shape_key = key
         return self._scratch
 
@@ -259,12 +272,15 @@ class Stage2Trainer:
         s.x_in.copy_(x)
         ops.ln_modulate(x, s.a1, cfg.eps, m0[0], m0[1], m1[0], m1[1], n_first)
         ops.gemm(s.a1, self.a1_qkv[i], None, s.t_qkv)
-        ops.gemm(s.a1, w["wqkv"], b.bqkv, s.qkv, a2=s.t_qkv, w2=be["qkv"])
-        s.qk_pre.copy_(s.qkv[:, :2 * d])
-        ops.rmsnorm_rope(s.qkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, 0)
-        ops.rmsnorm_rope(s.qkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, 0)
-        ops.head_norm_max(s.qkv[:, d:2 * d], st["kmax2"], H)
-        ops.attention(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, H, lse=s.lse, kmax2=st["kmax2"])
+        if self.sp is None:
+            ops.gemm(s.a1, w["wqkv"], b.bqkv, s.qkv, a2=s.t_qkv, w2=be["qkv"])
+            s.qk_pre.copy_(s.qkv[:, :2 * d])
+            ops.rmsnorm_rope(s.qkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, 0)
+            ops.rmsnorm_rope(s.qkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, 0)
+            ops.head_norm_max(s.qkv[:, d:2 * d], st["kmax2"], H)
+            ops.attention(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, H, lse=s.lse, kmax2=st["kmax2"])
+        else:
+            self._sp_attention_forward(i, s, st)
         ops.gemm(s.o, self.a1[f"blocks.{i}.self_attn.o"], None, s.t_o)
         ops.gemm(s.o, w["wo"], b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first, a2=s.t_o, w2=be["o"])
         s.x1.copy_(x)
@@ -290,6 +306,50 @@ class Stage2Trainer:
         ops.gemm(s.h, w["w2"], b.b2, x, EPI_GATED_RESIDUAL, m0[5], m1[5], n_first, a2=s.t_2, w2=be["f2"])
         self.kernel_launches += 34
 
+    def _sp_attention_forward(self, i: int, s: _Saved, st) -> None:
+        """Self-attention of block i under Ulysses SP (xdit_context_parallel.py:125-146): q, k leave for the rank that owns
+        their head straight from the RMSNorm+RoPE kernel, v by a plain scatter; attention runs on H/P heads x all tokens and
+        its epilogue stores each token row back to its owner.  Kept for the backward: the pre-norm q|k (token-major), the
+        exchanged q|k|v (head-major), the log-sum-exp of the local heads and the gathered output."""
+        eng, cfg, sp, sc = self.engine, self.cfg, self.sp, self._scratch
+        d, H, P, rk = cfg.dim, cfg.num_heads, self.sp.world, self.sp.rank
+        b, w, be = eng.blocks[i], self.eff[i], self.b2e[i]
+        hpr, wloc, S, rows = H // P, d // P, st["S"], s.a1.shape[0]
+        ar, qkv, dev = sp.arena, sc["qkv_tok"], eng.device
+        ops.gemm(s.a1, w["wqkv"], b.bqkv, qkv, a2=s.t_qkv, w2=be["qkv"])
+        s.qk_pre.copy_(qkv[:, :2 * d])
+        ops.rmsnorm_rope_scatter(qkv[:, :d], cfg.eps, b.nq, eng.rope_tab, st["grid"], st["tok0"], ar.recv_ptrs, P, rk, 0, 3)
+        ops.rmsnorm_rope_scatter(qkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, st["grid"], st["tok0"], ar.recv_ptrs, P, rk, 1, 3)
+        ops.sp_scatter_heads(qkv[:, 2 * d:], ar.recv_ptrs, H, 1, P, rk, 2, 3)
+        sp.barrier(0, dev)
+        recv, kmax2 = ar.recv, st["kmax2"][:hpr]
+        ops.head_norm_max(recv[:S, wloc:2 * wloc], kmax2, hpr)
+        ops.attention_scatter(recv[:, :wloc], recv[:S, wloc:2 * wloc], recv[:S, 2 * wloc:], ar.o_ptrs, d, rows, rk * wloc, hpr,
+                              kmax2=kmax2, lse=s.lse)
+        s.qkv.copy_(recv)          # before the barrier: the peers' next scatter may overwrite recv right after it
+        sp.barrier(1, dev)
+        s.o.copy_(ar.o)            # complete once every peer's attention epilogue has passed the barrier
+        self.kernel_launches += 2
+
+    def _sp_attention_backward(self, i: int, s: _Saved, d_o: torch.Tensor, st) -> torch.Tensor:
+        """Reverse exchange: O and dO go to the head owners (same scatter as v in the forward), fgb_attn_bwd runs on the local
+        heads over all tokens, and dq|dk|dv return token-major into the owners' arena (fgb_sp_return_heads).  Returns the
+        [rows, 3*D] gradient matrix of this rank's tokens (a view of the arena)."""
+        cfg, sp, sc = self.cfg, self.sp, self._scratch
+        d, H, P, rk = cfg.dim, cfg.num_heads, self.sp.world, self.sp.rank
+        hpr, wloc, S, rows = H // P, d // P, st["S"], s.a1.shape[0]
+        ar, dloc, dev = sp.arena, sc["dloc"], self.engine.device
+        ops.sp_scatter_heads(s.o, ar.recv_ptrs, H, 1, P, rk, 0, 3)
+        ops.sp_scatter_heads(d_o, ar.recv_ptrs, H, 1, P, rk, 1, 3)
+        sp.barrier(0, dev)
+        recv = ar.recv
+        ops.attention_bwd(s.qkv[:, :wloc], s.qkv[:S, wloc:2 * wloc], s.qkv[:S, 2 * wloc:], recv[:, :wloc], recv[:, wloc:2 * wloc], s.lse,
+                          dloc[:, :wloc], dloc[:S, wloc:2 * wloc], dloc[:S, 2 * wloc:], hpr, delta=sc["delta_sp"])
+        ops.sp_return_heads(dloc, ar.dqkv_ptrs, 3 * d, rows, H, 3, P, rk)
+        sp.barrier(1, dev)
+        self.kernel_launches += 4
+        return ar.dqkv
+
     def forward_train(self, latents: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor,
                       fuse_vae_embedding_in_latents: bool = True) -> torch.Tensor:
         """model_fn_wan_video (PIPE:1217-1388) with saved activations; call set_masks() + merge() first."""
@@ -299,21 +359,29 @@ class Stage2Trainer:
             raise ValueError(f"latents must be (1,{cfg.in_dim},F,H,W), got {tuple(latents.shape)}")
         f, h, w = latents.shape[2], latents.shape[3] // 2, latents.shape[4] // 2
         grid, S = (f, h, w), f * h * w
-        ws = eng._workspace(S, S)
+        sp = self.sp
+        P, rk = (sp.world, sp.rank) if sp is not None else (1, 0)
+        rows = -(-S // P)              # tokens of this rank (contiguous split, zero-padded tail: PIPE:1312-1315)
+        tok0 = rk * rows
+        if sp is not None:             # the arena with the backward region must exist before the engine maps its workspace
+            old = sp.arena
+            if sp.peer_arena(rows, cfg.num_heads, dev, backward=True) is not old:
+                eng._ws = {}
+        ws = eng._workspace(rows, rows * P)
         per_token = bool(cfg.seperated_timestep and fuse_vae_embedding_in_latents)
         R = 2 if per_token else 1
         mod_tab, head_tab = eng._time_tables(ws, timestep, R)
         r_main = R - 1
-        n_first = min(S, h * w) if per_token else 0
+        n_first = max(0, min(rows, h * w - tok0)) if per_token else 0
         ctx_emb = eng.text_embedding(context)
-        sc = self._buffers(S, ctx_emb.shape[0])
+        sc = self._buffers(rows, ctx_emb.shape[0])
         L = cfg.num_layers
-        st = dict(grid=grid, S=S, n_first=n_first, ctx_emb=ctx_emb, kmax2=ws["kmax2"],
+        st = dict(grid=grid, S=S, tok0=tok0, n_first=n_first, ctx_emb=ctx_emb, kmax2=ws["kmax2"],
                   m0=[mod_tab[0, i].view(6, d) for i in range(L)], m1=[mod_tab[r_main, i].view(6, d) for i in range(L)],
                   h0=head_tab[0].view(2, d), h1=head_tab[r_main].view(2, d), lat_dtype=latents.dtype)
         x = sc["x"]
         lat = latents[0].to(device=dev, dtype=BF16).contiguous()
-        ops.patchify_rows(lat, ws["prow"], grid, 0)
+        ops.patchify_rows(lat, ws["prow"], grid, tok0)
         ops.gemm(ws["prow"], eng.w_patch, eng.b_patch, x)
         for i in range(L):
             if self.recompute:
@@ -322,8 +390,9 @@ class Stage2Trainer:
         sc["x_final"].copy_(x)
         ops.ln_modulate(x, sc["a_head"], cfg.eps, st["h0"][0], st["h0"][1], st["h1"][0], st["h1"][1], n_first)
         ops.gemm(sc["a_head"], eng.w_head, eng.b_head, ws["hrow"])
+        hrow = ws["hrow"] if sp is None else sp.all_gather_rows(ws["hrow"], ws["hgather"])   # PIPE:1379-1382
         out = torch.empty(cfg.out_dim, f, 2 * h, 2 * w, dtype=BF16, device=dev)
-        ops.unpatchify(ws["hrow"], out, grid)
+        ops.unpatchify(hrow, out, grid)
         self.kernel_launches += 5
         self._fwd_state = st
         return out.unsqueeze(0)
@@ -383,10 +452,13 @@ class Stage2Trainer:
         ops.mul_gate(dx, t1, m0[2], m1[2], n_first)
         self._wgrad(t1, s.t_o, p + "self_attn.o")
         self._dgrad(t1, w["wo"], be["o"], self.a1[p + "self_attn.o"], t2, s.o, (p + "self_attn.o",))
-        ops.attention_bwd(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, t2, s.lse, dqkv[:, :d], dqkv[:, d:2 * d],
-                          dqkv[:, 2 * d:], H, delta=delta)
-        ops.rmsnorm_rope_bwd(s.qk_pre[:, :d], dqkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, 0)
-        ops.rmsnorm_rope_bwd(s.qk_pre[:, d:], dqkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, 0)
+        if self.sp is None:
+            ops.attention_bwd(s.qkv[:, :d], s.qkv[:, d:2 * d], s.qkv[:, 2 * d:], s.o, t2, s.lse, dqkv[:, :d], dqkv[:, d:2 * d],
+                              dqkv[:, 2 * d:], H, delta=delta)
+        else:
+            dqkv = self._sp_attention_backward(i, s, t2, st)
+        ops.rmsnorm_rope_bwd(s.qk_pre[:, :d], dqkv[:, :d], cfg.eps, b.nq, eng.rope_tab, grid, st["tok0"])
+        ops.rmsnorm_rope_bwd(s.qk_pre[:, d:], dqkv[:, d:2 * d], cfg.eps, b.nk, eng.rope_tab, grid, st["tok0"])
         for j, proj in enumerate("qkv"):
             self._wgrad(dqkv[:, j * d:(j + 1) * d], s.t_qkv[:, j * r:(j + 1) * r], p + "self_attn." + proj)
         self._dgrad(dqkv, w["wqkv"], be["qkv"], self.a1_qkv[i], t1, s.a1, tuple(p + "self_attn." + c for c in "qkv"))
@@ -401,10 +473,21 @@ class Stage2Trainer:
         eng, cfg, sc = self.engine, self.cfg, self._scratch
         grid, n_first = st["grid"], st["n_first"]
         dp = dpred.reshape(cfg.out_dim, grid[0], 2 * grid[1], 2 * grid[2]).to(dtype=BF16).contiguous()
-        ops.unpatchify_bwd(dp, sc["d_hrow"], grid)
-        ops.gemm_dgrad(sc["d_hrow"], eng.w_head, sc["t1"])
+        if self.sp is None:
+            d_hrow = ops.unpatchify_bwd(dp, sc["d_hrow"], grid)
+        else:   # every rank holds the whole prediction gradient; it keeps the rows of its own tokens (padded rows stay zero)
+            rows = sc["d_hrow"].shape[0]
+            d_hrow = ops.unpatchify_bwd(dp, sc["d_hrow_full"], grid)[st["tok0"]:st["tok0"] + rows]
+        ops.gemm_dgrad(d_hrow, eng.w_head, sc["t1"])
         ops.ln_bwd(sc["x_final"], sc["t1"], sc["dx"], cfg.eps, st["h0"][1], st["h1"][1], n_first, affine=False, dres=None)
         self.kernel_launches += 3
+        # group reductions act on THIS backward's gradients only: what earlier micro-steps accumulated is set aside
+        reduce_groups = self.sp is not None or self.dp_group is not None
+        flats = [g for g in (self.grad_flat, self.grad_a_flat) if g is not None]
+        held = [g.clone() for g in flats] if reduce_groups else []
+        if reduce_groups:
+            for g in flats:
+                g.zero_()
         for i in reversed(range(cfg.num_layers)):
             s = self._saved_for(i)
             if self.recompute:   # the reference's per-block checkpointing (PIPE:1348-1360): rebuild the activations
@@ -412,13 +495,16 @@ class Stage2Trainer:
                 self._block_forward(i, sc["x"], s, st)
             self._block_backward(i, s, st)
         self._fwd_state = None
-        if self.dp_group is not None:
+        if reduce_groups:
             import torch.distributed as dist
 
-            for gflat in (self.grad_flat, self.grad_a_flat):
-                if gflat is not None:
+            for gflat, prev in zip(flats, held):
+                if self.sp is not None:   # each rank saw only its tokens (and, for cross k / v, its queries): the gradients add up
+                    dist.all_reduce(gflat, group=self.sp.group)
+                if self.dp_group is not None:
                     dist.all_reduce(gflat, group=self.dp_group)
                     gflat.div_(dist.get_world_size(self.dp_group))   # DDP averages (accelerate, train.py)
+                gflat.add_(prev)
 
     # ------------------------------------------------------------------------------------------------------------
     # whole step without autograd (LOSS:5-21)

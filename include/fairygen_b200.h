@@ -204,6 +204,10 @@ int fgb_rmsnorm_rope_scatter(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t r
                              const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, int32_t token_offset,
                              void* const* peer_bufs, int32_t world, int32_t rank, int32_t group, int32_t groups_total,
                              void* stream);
+/* Backward of the exchange: x [s_pad, groups*(heads/world)*128] (this rank's heads, all tokens, e.g. dq|dk|dv) -> rows
+ * [rank*..] of every token owner's [rows, groups*heads*128] matrix (peer_bufs, row stride ld_dst). */
+int fgb_sp_return_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* const* peer_bufs, int64_t ld_dst, int32_t rows,
+                        int32_t s_pad, int32_t heads, int32_t groups, int32_t world, int32_t rank, void* stream);
 int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* stream);
 /* fgb_attn_fwd_ex whose output row of global token t goes to o_peers[t / rows_per_peer][(t % rows_per_peer) * ldo +
  * col_offset + head*128 ...] (col_offset = rank * heads * 128 for Ulysses). */

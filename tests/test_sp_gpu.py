@@ -98,3 +98,74 @@ def test_cfg_parallel_equals_sequential(tmp_path, world, sp_ways):
         res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         # sp_ways == 1: bit-identical kernels on both sides, only the exchange differs
         assert res["finite"] and res["err"] < (1e-6 if sp_ways == 1 else 2e-3), res
+
+
+def _train_worker(rank, world, port, shape, stage, recompute, out_dir):
+    """Sequence-parallel LoRA training step (tokens of one video over 2 GPUs, forward AND backward exchange through peer
+    memory) against the single-GPU trainer on the same weights, adapters, dropout masks, noise and timestep."""
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+
+    import fairygen_b200 as fg
+    from fairygen_b200 import synthetic
+    from fairygen_b200.training import Stage2Trainer
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    cfg = fg.WanDiTConfig(dim=512, ffn_dim=1024, text_dim=256, num_heads=4, num_layers=2)
+    sd = synthetic.random_state_dict(cfg, seed=0, device=dev, dtype=BF)
+    lora = synthetic.random_lora(cfg, rank=32, seed=2, device=dev)
+    x0, _, ctx, _ = synthetic.synthetic_inputs(cfg, shape, text_len=32, live_text=8, pin=False)
+    noise = torch.randn(shape, generator=torch.Generator().manual_seed(9))
+    gen = torch.Generator().manual_seed(11)
+    res = {}
+    trainers = []
+    for sp in (None, fg.SequenceParallel(exchange="p2p")):
+        eng = fg.WanDiTEngine(cfg, dev, sp=sp)
+        eng.load_state_dict(sd)
+        tr = Stage2Trainer(eng, lora, rank=32, stage=stage, recompute=recompute and sp is not None)
+        trainers.append(tr)
+    single, par = trainers
+    b2 = {t: torch.randn(single.b2[t].shape, generator=gen) * 0.05 for t in single.targets}
+    masks = {t: (torch.rand(single.b2[t].shape, generator=gen) > single.dropout_prob).to(torch.uint8) for t in single.targets}
+    out = []
+    for tr in trainers:
+        tr.load_b2(b2)
+        tr.zero_grad()
+        loss, pred = tr.step(x0, noise, 400, ctx.to(dev), masks=masks, return_pred=True)
+        fg.ops.sync_check()
+        out.append((float(loss), pred.float().clone(), tr.grad_flat.clone(), None if tr.grad_a_flat is None else tr.grad_a_flat.clone()))
+    rel = lambda a, b: float((a - b).norm() / b.norm())  # noqa: E731
+    res["loss"] = (out[1][0], out[0][0])
+    res["pred"] = rel(out[1][1], out[0][1])
+    res["grad"] = rel(out[1][2], out[0][2])
+    res["grad_a"] = 0.0 if out[0][3] is None else rel(out[1][3], out[0][3])
+    res["worst"] = max(rel(par.grad[t], single.grad[t]) for t in single.targets)
+    res["nonzero"] = bool(out[0][2].abs().max() > 0)
+    # a second micro-step accumulates on top of the reduced gradients (the reduction covers one backward only)
+    par.step(x0, noise, 400, ctx.to(dev), masks=masks)
+    fg.ops.sync_check()
+    res["accum"] = rel(par.grad_flat, 2 * out[1][2])
+    torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,stage,recompute", [((1, 48, 3, 10, 14), 2, False),    # S = 105: ragged split, one padded row
+                                                   ((1, 48, 4, 8, 8), 1, True)])      # S = 64, stage 1 (dA and dB), checkpointing
+def test_sp2_training_step_equals_single_gpu(tmp_path, shape, stage, recompute):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    world = 2
+    mp.spawn(_train_worker, args=(world, _free_port(), shape, stage, recompute, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        print(res)
+        assert res["nonzero"]
+        assert res["pred"] < 3e-3, res
+        assert abs(res["loss"][0] - res["loss"][1]) < 5e-3 * abs(res["loss"][1]), res
+        assert res["grad"] < 1e-2 and res["grad_a"] < 1e-2 and res["worst"] < 3e-2, res
+        assert res["accum"] < 1e-3, res
