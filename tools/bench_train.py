@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--recompute", action="store_true", help="the reference's per-block checkpointing schedule")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel CUDA time of one step (torch.profiler / CUPTI)")
+    ap.add_argument("--sp", action="store_true", help="sequence-parallel: the N ranks split the tokens of ONE video (strong scaling) "
+                                                     "instead of running N data-parallel replicas")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=832)
     ap.add_argument("--frames", type=int, default=49)
@@ -42,13 +44,14 @@ def main():
     cfg = fg.TI2V_5B
     shape = synthetic.latent_shape(cfg, args.height, args.width, args.frames)
     tokens = shape[2] * (shape[3] // 2) * (shape[4] // 2)
-    eng = fg.WanDiTEngine(cfg, dev)
+    sp = fg.SequenceParallel(group, exchange="p2p") if args.sp and world > 1 else None
+    eng = fg.WanDiTEngine(cfg, dev, sp=sp)
     eng.load_state_dict(synthetic.random_state_dict(cfg, seed=0, device=dev, dtype=torch.bfloat16))
     lora = synthetic.random_lora(cfg, rank=32, seed=2, device=dev)
-    tr = Stage2Trainer(eng, lora, rank=32, recompute=args.recompute, dp_group=group)
+    tr = Stage2Trainer(eng, lora, rank=32, recompute=args.recompute, dp_group=None if sp is not None else group)
     tr.b2_flat.normal_(0, 0.02, generator=torch.Generator(device=dev).manual_seed(6))
     x0, _, ctx, _ = synthetic.synthetic_inputs(cfg, shape, text_len=512, pin=False)
-    noise = torch.randn(shape, generator=torch.Generator().manual_seed(9 + rank)).to(torch.bfloat16)
+    noise = torch.randn(shape, generator=torch.Generator().manual_seed(9 + (0 if sp is not None else rank))).to(torch.bfloat16)
     x0, ctx, noise = x0.to(dev), ctx.to(dev), noise.to(dev)
 
     def one(i):
@@ -59,7 +62,7 @@ def main():
     for i in range(args.warmup):
         one(i)
     torch.cuda.synchronize()
-    if args.profile and rank == 0:
+    if args.profile and world == 1:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             one(99)
@@ -87,12 +90,12 @@ def main():
         bwd = gemm + 2.5 * attn
         total = fwd + bwd + (fwd if args.recompute else 0)
         print(json.dumps({
-            "metric": "stage2_lora_train_steps_per_s", "value": world * 1e3 / ms, "unit": "steps/s", "n_gpus": world, "ms_per_step": ms,
-            "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+            "metric": "stage2_lora_train_steps_per_s", "value": (1 if sp is not None else world) * 1e3 / ms, "unit": "steps/s", "n_gpus": world, "ms_per_step": ms,
+            "scaling": "strong" if sp is not None else "weak", "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"Wan2.2-TI2V-5B stage-2 motion-LoRA fine-tune step, {args.height}x{args.width}x{args.frames} "
                                    f"(S={tokens}), rank 32 unmerged adapters, only lora_B2 trainable, AdamW", "recompute": args.recompute,
-                       "parallelism": f"dp{world}"},
-            "counted_flops_per_step": total, "achieved_tflops_per_gpu": total / (ms * 1e-3) / 1e12,
+                       "parallelism": f"sp{world}" if sp is not None else f"dp{world}"},
+            "counted_flops_per_step": total, "achieved_tflops_per_gpu": total / (ms * 1e-3) / 1e12 / (world if sp is not None else 1),
             "gpu_launches": tr.kernel_launches, "loss": float(tr.loss_buf), "grad_norm": float(tr.grad_flat.norm()),
             "finite": bool(torch.isfinite(tr.grad_flat).all()),
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
