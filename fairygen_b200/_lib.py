@@ -59,6 +59,11 @@ SIGNATURES = {
     "fgb_mse_loss_grad": (ctypes.c_int, [_P, _P, _P, _F, _P, _P, _I64, _P]),
     "fgb_unpatchify_bwd": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P]),
     "fgb_adamw_step": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P]),
+    "fgb_embedding_rows": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _I64, _P]),
+    "fgb_t5_layer_norm": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P]),
+    "fgb_geglu": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _P]),
+    "fgb_t5_bias_table": (ctypes.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P]),
+    "fgb_t5_attention": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "fgb_ln_modulate": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P, _I32, _P]),
     "fgb_ln_affine": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
     "fgb_rmsnorm_rope": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _F, _P, _P, _I32, _I32, _I32, _I32, _P]),

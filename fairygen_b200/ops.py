@@ -535,3 +535,66 @@ def adamw_step(param, grad, m, v, lr, beta1, beta2, eps, weight_decay, step: int
     _lib.check(_lib.lib().fgb_adamw_step(_h(param).handle, _p(param), _p(grad), _p(m), _p(v), n, lr, beta1, beta2, eps, weight_decay, step,
                                          _stream()), "fgb_adamw_step")
     return param
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# umT5 text encoder (fgb_embedding_rows, fgb_t5_layer_norm, fgb_geglu, fgb_t5_bias_table, fgb_t5_attention)
+# ---------------------------------------------------------------------------------------------------------------
+def embedding_rows(table, ids, out):
+    """out[r] = table[ids[r]]; ids: int64 device vector."""
+    if ids.dtype != torch.int64 or ids.dim() != 1 or not ids.is_contiguous() or ids.device != table.device:
+        raise ValueError("embedding_rows: ids must be a contiguous int64 vector on the table's device")
+    if out.shape[0] != ids.numel() or out.shape[1] != table.shape[1]:
+        raise ValueError(f"embedding_rows shape mismatch: table {tuple(table.shape)} ids {tuple(ids.shape)} out {tuple(out.shape)}")
+    _lib.check(_lib.lib().fgb_embedding_rows(_h(table).handle, _p(table), _rowmajor(table, "table"), table.shape[0], _p(ids), ids.numel(),
+                                             table.shape[1], _p(out), _rowmajor(out, "out"), _stream()), "fgb_embedding_rows")
+    return out
+
+
+def t5_layer_norm(x, out, eps, weight):
+    rows, dim = x.shape
+    _vec(weight, dim, "weight")
+    if weight is None or tuple(out.shape) != (rows, dim):
+        raise ValueError("t5_layer_norm: weight is required and out must match x")
+    _lib.check(_lib.lib().fgb_t5_layer_norm(_h(x).handle, _p(x), _rowmajor(x, "x"), _p(out), _rowmajor(out, "out"), rows, dim, eps,
+                                            _p(weight), _stream()), "fgb_t5_layer_norm")
+    return out
+
+
+def geglu(gate_fc1, out):
+    """out = gate_fc1[:, F:] * gelu_tanh(gate_fc1[:, :F])."""
+    rows, two_f = gate_fc1.shape
+    if two_f % 2 or tuple(out.shape) != (rows, two_f // 2):
+        raise ValueError(f"geglu shape mismatch: gate_fc1 {tuple(gate_fc1.shape)} out {tuple(out.shape)}")
+    _lib.check(_lib.lib().fgb_geglu(_h(out).handle, _p(gate_fc1), _rowmajor(gate_fc1, "gate_fc1"), _p(out), _rowmajor(out, "out"), rows,
+                                    two_f // 2, _stream()), "fgb_geglu")
+    return out
+
+
+def t5_bias_table(emb, bucket_of_rel, out):
+    """out [heads, n_rel] fp32 = emb[bucket_of_rel].T; emb [buckets, heads] bf16, bucket_of_rel int32 [n_rel]."""
+    buckets, heads = emb.shape
+    n_rel = bucket_of_rel.numel()
+    if (emb.dtype != BF16 or not emb.is_contiguous() or bucket_of_rel.dtype != torch.int32 or not bucket_of_rel.is_contiguous() or
+            out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (heads, n_rel)):
+        raise ValueError("t5_bias_table: emb bf16 [buckets, heads], bucket_of_rel int32 [n_rel], out fp32 [heads, n_rel]")
+    _lib.check(_lib.lib().fgb_t5_bias_table(_h(emb).handle, _p(emb), _p(bucket_of_rel), n_rel, heads, buckets, _p(out), _stream()),
+               "fgb_t5_bias_table")
+    return out
+
+
+def t5_attention(q, k, v, out, batch: int, heads: int, bias=None, key_mask=None):
+    """T5 attention core on [batch*s, heads*64] matrices (no score scaling); bias fp32 [heads, s_q+s_kv-1], key_mask uint8 [batch, s_kv]."""
+    if q.shape[0] % batch or k.shape[0] % batch or k.shape[0] != v.shape[0] or out.shape[0] != q.shape[0]:
+        raise ValueError("t5_attention: row counts must be batch * sequence length")
+    s_q, s_kv = q.shape[0] // batch, k.shape[0] // batch
+    if any(t.shape[1] != heads * 64 for t in (q, k, v, out)):
+        raise ValueError("t5_attention: head_dim is 64 — every matrix must be heads*64 wide")
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous() or tuple(bias.shape) != (heads, s_q + s_kv - 1)):
+        raise ValueError(f"t5_attention: bias must be fp32 [heads, s_q+s_kv-1] = [{heads}, {s_q + s_kv - 1}]")
+    if key_mask is not None and (key_mask.dtype != torch.uint8 or not key_mask.is_contiguous() or tuple(key_mask.shape) != (batch, s_kv)):
+        raise ValueError(f"t5_attention: key_mask must be uint8 [batch, s_kv] = [{batch}, {s_kv}]")
+    _lib.check(_lib.lib().fgb_t5_attention(_h(q).handle, _p(q), _rowmajor(q, "q"), _p(k), _rowmajor(k, "k"), _p(v), _rowmajor(v, "v"),
+                                           _p(out), _rowmajor(out, "out"), batch, s_q, s_kv, heads, _p(bias), _p(key_mask), _stream()),
+               "fgb_t5_attention")
+    return out

@@ -287,6 +287,37 @@ int fgb_unpatchify_bwd(fgb_ctx* ctx, const void* dpred, void* d_rows, int64_t ld
 int fgb_adamw_step(fgb_ctx* ctx, void* param_bf16, const void* grad_f32, void* m_f32, void* v_f32, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * umT5 text encoder: animation/diffsynth/models/wan_video_text_encoder.py ("TENC"), called at
+ * pipelines/wan_video.py:404-412. The Linears (bias-free) run on fgb_gemm_bf16; these are the ops around them.
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* out[r, :] = table[ids[r], :] (ids: int64 on the device).  nn.Embedding token_embedding, TENC:233-234, 246. */
+int fgb_embedding_rows(fgb_ctx* ctx, const void* table, int64_t ld_table, int32_t vocab, const void* ids, int32_t n, int32_t dim,
+                       void* out, int64_t ldo, void* stream);
+
+/* out = weight * bf16(x * rsqrt(mean(x^2) + eps)).  T5LayerNorm.forward, TENC:33-38. */
+int fgb_t5_layer_norm(fgb_ctx* ctx, const void* x, int64_t ldx, void* out, int64_t ldo, int32_t rows, int32_t dim, float eps,
+                      const void* weight, void* stream);
+
+/* out[r, j] = gate_fc1[r, F + j] * gelu_tanh(gate_fc1[r, j]): the product of T5FeedForward.forward (TENC:18-22, 109) on the
+ * output of ONE GEMM against the row-concatenated [gate.0.weight; fc1.weight]. */
+int fgb_geglu(fgb_ctx* ctx, const void* gate_fc1, int64_t ld, void* out, int64_t ldo, int32_t rows, int32_t ffn_dim, void* stream);
+
+/* out[h, i] = emb[bucket_of_rel[i], h] (fp32 [heads, n_rel]): T5RelativeEmbedding.forward (TENC:159-169) stored by
+ * relative position i = (key - query) + (s_q - 1) instead of as a dense [heads, s_q, s_kv] tensor; bucket_of_rel (int32 on
+ * the device) is the host-side restatement of _relative_position_bucket (TENC:171-193). */
+int fgb_t5_bias_table(fgb_ctx* ctx, const void* emb, const void* bucket_of_rel, int32_t n_rel, int32_t heads, int32_t buckets,
+                      void* out, void* stream);
+
+/* T5Attention.forward core (TENC:74-88), head_dim 64, no score scaling: for every sample b and head h
+ *   o[b*s_q + i, h*64:(h+1)*64] = softmax_j(q_i·k_j + bias[h, j - i + s_q - 1], keys with key_mask[b, j] == 0 excluded) · v.
+ * q rows b*s_q.., k / v rows b*s_kv..; bias (fp32, from fgb_t5_bias_table) and key_mask (uint8 [batch, s_kv]) may be NULL.
+ * A sample whose keys are all masked yields zeros (the host mirror rejects such masks). */
+int fgb_t5_attention(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                     int64_t ldo, int32_t batch, int32_t s_q, int32_t s_kv, int32_t heads, const void* bias, const void* key_mask,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif
