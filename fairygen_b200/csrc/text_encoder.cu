@@ -105,24 +105,28 @@ __global__ void t5_bias_table_kernel(const __nv_bfloat16* __restrict__ emb, cons
 // T5 self-attention, head_dim 64: o = softmax(q·kᵀ + bias[key - query] (+ -inf on masked keys))·v       TENC:59-95
 //
 // CTA = (32 query rows, one head, one sample), 8 warps x 4 rows; keys in chunks of 128 staged in shared memory as bf16
-// with a 33-word row stride (lane j reads row j: conflict-free), online softmax over chunks in fp32. QK: each lane owns
-// 4 keys of the chunk and holds the query row in registers. PV: probabilities go through a per-warp shared strip and are
-// read back 4 at a time as broadcasts; each lane owns 2 of the 64 output dims. Plain FMA pipe on purpose: 512 x 512 x 64
-// heads is ~4 GFLOP per layer against ~200 GFLOP of Linears (see DESIGN §8 for the measured share).
+// with a 34-word row stride (lane j reads row j with 8-byte loads: conflict-free per half-warp), online softmax over chunks
+// in fp32. A warp works on its 4 rows together so that every K / V word fetched from shared memory feeds 4 rows: QK — each
+// lane owns 4 keys of the chunk, the query rows arrive as 16-byte broadcasts; PV — probabilities go through a per-warp
+// shared strip and come back 4 at a time as broadcasts, each lane owns 2 of the 64 output dims. Chunks without a live key
+// (the padded tail of a prompt) are skipped before they are staged. Plain FMA pipe on purpose: 512 x 512 x 64 heads is
+// ~4 GFLOP per layer against ~200 GFLOP of Linears.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTeRows = 32;    // query rows per CTA
 constexpr int kTeKeys = 128;   // keys per staged chunk
-constexpr int kTeStride = 33;  // 32-bit words per staged K / V row (64 bf16 + 1 pad word)
+constexpr int kTeStride = 34;  // 32-bit words per staged K / V row (64 bf16 + 2 pad words; even: rows stay 8-byte aligned)
+constexpr int kTeSmemBytes = (2 * kTeKeys * kTeStride + kTeRows * 64 + 8 * 4 * kTeKeys) * 4;
 
 __global__ void __launch_bounds__(256) t5_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
                                                            const __nv_bfloat16* __restrict__ k, int64_t ldk,
                                                            const __nv_bfloat16* __restrict__ v, int64_t ldv, __nv_bfloat16* o,
                                                            int64_t ldo, int s_q, int s_kv, const float* __restrict__ bias,
                                                            const uint8_t* __restrict__ key_mask) {
-  __shared__ uint32_t sk[kTeKeys * kTeStride];
-  __shared__ uint32_t sv[kTeKeys * kTeStride];
-  __shared__ __align__(16) float sq[kTeRows][64];
-  __shared__ __align__(16) float sp[8][kTeKeys];
+  extern __shared__ __align__(16) uint32_t te_smem[];
+  uint32_t* sk = te_smem;                                                   // [128][34]
+  uint32_t* sv = sk + kTeKeys * kTeStride;                                  // [128][34]
+  float* sq = reinterpret_cast<float*>(sv + kTeKeys * kTeStride);           // [32][64]
+  float* sp = sq + kTeRows * 64;                                            // [8 warps][4 rows][128]
   const int head = blockIdx.y, sample = blockIdx.z;
   const int row0 = blockIdx.x * kTeRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,13 +137,13 @@ __global__ void __launch_bounds__(256) t5_attention_kernel(const __nv_bfloat16* 
   const __nv_bfloat16* kb = k + static_cast<int64_t>(sample) * s_kv * ldk + head * 64;
   const __nv_bfloat16* vb = v + static_cast<int64_t>(sample) * s_kv * ldv + head * 64;
 
-  // query tile -> fp32 shared (8 threads per row, 8 values each)
+  // query tile -> fp32 shared (8 threads per row, 8 values each); rows past s_q are zeros and never stored
   {
     const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
     float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (row0 + r < s_q) unpack8(ldg_nc_v4(reinterpret_cast<const uint4*>(qb + static_cast<int64_t>(row0 + r) * ldq) + c), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sq[r][c * 8 + j] = f[j];
+    for (int j = 0; j < 8; ++j) sq[r * 64 + c * 8 + j] = f[j];
   }
 
   float m[4], l[4], acc0[4], acc1[4];
@@ -149,10 +153,15 @@ __global__ void __launch_bounds__(256) t5_attention_kernel(const __nv_bfloat16* 
     l[i] = 0.f;
     acc0[i] = acc1[i] = 0.f;
   }
+  const int rl0 = warp * 4;                 // first of this warp's rows inside the tile
+  float* spw = sp + warp * 4 * kTeKeys;
 
   for (int key0 = 0; key0 < s_kv; key0 += kTeKeys) {
-    __syncthreads();  // previous chunk fully consumed (and, first time round, the query tile written)
-    // stage K and V rows [key0, key0+128): 8 threads per row, one 16-byte load each, stored as 4 words at stride 33
+    // barrier (previous chunk consumed; first time round: query tile written) + "does this chunk hold a live key?"
+    const int probe = key0 + static_cast<int>(threadIdx.x);
+    const int any_live = __syncthreads_or(threadIdx.x < kTeKeys && probe < s_kv && (mask == nullptr || mask[probe] != 0));
+    if (!any_live) continue;                // block-uniform
+    // stage K and V rows [key0, key0+128): 8 threads per row, one 16-byte load each, stored as 4 words at stride 34
     for (int t = threadIdx.x; t < kTeKeys * 8; t += 256) {
       const int r = t >> 3, c = t & 7;
       uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = make_uint4(0, 0, 0, 0);
@@ -160,14 +169,13 @@ __global__ void __launch_bounds__(256) t5_attention_kernel(const __nv_bfloat16* 
         kv4 = ldg_nc_v4(reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(key0 + r) * ldk) + c);
         vv4 = ldg_nc_v4(reinterpret_cast<const uint4*>(vb + static_cast<int64_t>(key0 + r) * ldv) + c);
       }
-      uint32_t* dk = sk + r * kTeStride + c * 4;
-      uint32_t* dv = sv + r * kTeStride + c * 4;
-      dk[0] = kv4.x; dk[1] = kv4.y; dk[2] = kv4.z; dk[3] = kv4.w;
-      dv[0] = vv4.x; dv[1] = vv4.y; dv[2] = vv4.z; dv[3] = vv4.w;
+      uint2* dk = reinterpret_cast<uint2*>(sk + r * kTeStride + c * 4);
+      uint2* dv = reinterpret_cast<uint2*>(sv + r * kTeStride + c * 4);
+      dk[0] = make_uint2(kv4.x, kv4.y); dk[1] = make_uint2(kv4.z, kv4.w);
+      dv[0] = make_uint2(vv4.x, vv4.y); dv[1] = make_uint2(vv4.z, vv4.w);
     }
     __syncthreads();
 
-    // which of this lane's 4 keys exist and are unmasked
     bool live[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -175,74 +183,85 @@ __global__ void __launch_bounds__(256) t5_attention_kernel(const __nv_bfloat16* 
       live[t] = key < s_kv && (mask == nullptr || mask[key] != 0);
     }
 
+    // ---- scores of 4 rows x (4 keys per lane)
+    float s[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {           // unrolled: the per-row softmax state stays in registers
-      const int rl = warp * 4 + i;          // row inside the tile
-      const int row = row0 + rl;
-      if (row >= s_q) break;                // warp-uniform
-      float s[4] = {0.f, 0.f, 0.f, 0.f};
-      const float4* q4 = reinterpret_cast<const float4*>(sq[rl]);
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {        // 4 dims (2 words of K) per step
-        const float4 qq = q4[c];
+      for (int t = 0; t < 4; ++t) s[i][t] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 16; ++c) {          // 4 of the 64 dims per step
+      float4 qq[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint32_t* kr = sk + (t * 32 + lane) * kTeStride + c * 2;
-          const uint32_t w0 = kr[0], w1 = kr[1];
-          s[t] = fmaf(qq.x, bf16_lo(w0), s[t]);
-          s[t] = fmaf(qq.y, bf16_hi(w0), s[t]);
-          s[t] = fmaf(qq.z, bf16_lo(w1), s[t]);
-          s[t] = fmaf(qq.w, bf16_hi(w1), s[t]);
+      for (int i = 0; i < 4; ++i) qq[i] = reinterpret_cast<const float4*>(sq + (rl0 + i) * 64)[c];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint2 kw = *reinterpret_cast<const uint2*>(sk + (t * 32 + lane) * kTeStride + c * 2);
+        const float k0 = bf16_lo(kw.x), k1 = bf16_hi(kw.x), k2 = bf16_lo(kw.y), k3 = bf16_hi(kw.y);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          s[i][t] = fmaf(qq[i].x, k0, s[i][t]);
+          s[i][t] = fmaf(qq[i].y, k1, s[i][t]);
+          s[i][t] = fmaf(qq[i].z, k2, s[i][t]);
+          s[i][t] = fmaf(qq[i].w, k3, s[i][t]);
         }
       }
+    }
+
+    // ---- bias, mask, online softmax; probabilities to the warp's strip
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = row0 + rl0 + i;
       float cmax = -INFINITY;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int key = key0 + t * 32 + lane;
         if (live[t]) {
-          if (bias_h) s[t] += __ldg(bias_h + (key - row));
-          cmax = fmaxf(cmax, s[t]);
-        } else {
-          s[t] = -INFINITY;
+          if (bias_h && row < s_q) s[i][t] += __ldg(bias_h + (key - row));
+          cmax = fmaxf(cmax, s[i][t]);
         }
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, off));
-      if (cmax == -INFINITY) continue;      // the whole chunk is masked for this row (warp-uniform)
-      const float m_new = fmaxf(m[i], cmax);
-      const float rescale = __expf(m[i] - m_new);   // m = -inf on the first live chunk: exp(-inf) = 0
+      const float m_new = fmaxf(m[i], cmax);        // finite: the chunk holds a live key
+      const float rescale = __expf(m[i] - m_new);   // m = -inf before the first live chunk: exp(-inf) = 0
       float psum = 0.f;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float p = live[t] ? __expf(s[t] - m_new) : 0.f;
+        const float p = live[t] ? __expf(s[i][t] - m_new) : 0.f;
         psum += p;
-        sp[warp][t * 32 + lane] = p;
+        spw[i * kTeKeys + t * 32 + lane] = p;
       }
       psum = warp_sum(psum);
       l[i] = l[i] * rescale + psum;
       m[i] = m_new;
-      __syncwarp();
-      float a0 = acc0[i] * rescale, a1 = acc1[i] * rescale;
-      const float4* p4 = reinterpret_cast<const float4*>(sp[warp]);
-      const int kmax = min(kTeKeys, s_kv - key0);
-      for (int j = 0; j < kmax; j += 4) {   // rows past s_kv hold zeros in sv and p = 0 in sp
-        const float4 pp = p4[j >> 2];
-        const uint32_t v0 = sv[(j + 0) * kTeStride + lane], v1 = sv[(j + 1) * kTeStride + lane];
-        const uint32_t v2 = sv[(j + 2) * kTeStride + lane], v3 = sv[(j + 3) * kTeStride + lane];
-        a0 = fmaf(pp.x, bf16_lo(v0), a0); a1 = fmaf(pp.x, bf16_hi(v0), a1);
-        a0 = fmaf(pp.y, bf16_lo(v1), a0); a1 = fmaf(pp.y, bf16_hi(v1), a1);
-        a0 = fmaf(pp.z, bf16_lo(v2), a0); a1 = fmaf(pp.z, bf16_hi(v2), a1);
-        a0 = fmaf(pp.w, bf16_lo(v3), a0); a1 = fmaf(pp.w, bf16_hi(v3), a1);
-      }
-      acc0[i] = a0;
-      acc1[i] = a1;
-      __syncwarp();                          // sp[warp] is rewritten by the next row
+      acc0[i] *= rescale;
+      acc1[i] *= rescale;
     }
+    __syncwarp();
+
+    // ---- o += P·V for the 4 rows (keys past s_kv: V staged as zeros, p = 0)
+    const int kmax = min(kTeKeys, s_kv - key0);
+    for (int j = 0; j < kmax; j += 4) {
+      const uint32_t v0 = sv[(j + 0) * kTeStride + lane], v1 = sv[(j + 1) * kTeStride + lane];
+      const uint32_t v2 = sv[(j + 2) * kTeStride + lane], v3 = sv[(j + 3) * kTeStride + lane];
+      const float a0 = bf16_lo(v0), b0 = bf16_hi(v0), a1 = bf16_lo(v1), b1 = bf16_hi(v1);
+      const float a2 = bf16_lo(v2), b2 = bf16_hi(v2), a3 = bf16_lo(v3), b3 = bf16_hi(v3);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 pp = reinterpret_cast<const float4*>(spw + i * kTeKeys)[j >> 2];
+        acc0[i] = fmaf(pp.x, a0, acc0[i]); acc1[i] = fmaf(pp.x, b0, acc1[i]);
+        acc0[i] = fmaf(pp.y, a1, acc0[i]); acc1[i] = fmaf(pp.y, b1, acc1[i]);
+        acc0[i] = fmaf(pp.z, a2, acc0[i]); acc1[i] = fmaf(pp.z, b2, acc1[i]);
+        acc0[i] = fmaf(pp.w, a3, acc0[i]); acc1[i] = fmaf(pp.w, b3, acc1[i]);
+      }
+    }
+    __syncwarp();                            // the strip is rewritten in the next chunk
   }
 
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int row = row0 + warp * 4 + i;
+    const int row = row0 + rl0 + i;
     if (row >= s_q) break;
     const float inv = l[i] > 0.f ? 1.f / l[i] : 0.f;
     uint32_t* orow = reinterpret_cast<uint32_t*>(o + (static_cast<int64_t>(sample) * s_q + row) * ldo + head * 64);
@@ -314,8 +333,10 @@ extern "C" int fgb_t5_attention(fgb_ctx* ctx, const void* q, int64_t ldq, const 
   FGB_CHECK_ARG(ldq >= width && ldk >= width && ldv >= width && ldo >= width && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 &&
                     aligned16(q) && aligned16(k) && aligned16(v) && (reinterpret_cast<uintptr_t>(o) & 3u) == 0,
                 "fgb_t5_attention: head_dim is 64; rows must be 16-byte aligned (ld %% 8) and at least heads*64 wide");
+  // > 48 KB of dynamic shared memory needs the opt-in (per device; a few hundred ns, so not cached)
+  FGB_CUDA(cudaFuncSetAttribute(t5_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeSmemBytes));
   dim3 grid((s_q + kTeRows - 1) / kTeRows, heads, batch);
-  t5_attention_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  t5_attention_kernel<<<grid, 256, kTeSmemBytes, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, static_cast<const bf16*>(v), ldv, static_cast<bf16*>(o), ldo, s_q,
       s_kv, static_cast<const float*>(bias), static_cast<const uint8_t*>(key_mask));
   FGB_LAUNCH_CHECK("t5_attention_kernel");

@@ -128,7 +128,9 @@ class UMT5Encoder:
             for i, b in enumerate(self.blocks):
                 ops.t5_bias_table(b.pos, buckets, tab[i])
             self.kernel_launches += cfg.num_layers
-            self._bias_cache = {L: tab}
+            if len(self._bias_cache) >= 8:        # prompts come in many lengths (encode_prompt trims to the live tokens)
+                self._bias_cache.pop(next(iter(self._bias_cache)))
+            self._bias_cache[L] = tab
         return tab
 
     def _workspace(self, rows: int) -> Dict[str, torch.Tensor]:
@@ -183,11 +185,58 @@ class UMT5Encoder:
 
     __call__ = forward
 
+    def _encode_live(self, ids: torch.Tensor, mask: torch.Tensor):
+        """Encoder output for the first max(live) positions only, placed in a zeroed [B, L, dim] tensor.  Rows of live tokens
+        never see the padded positions (masked as keys), so trimming the padded tail changes none of them."""
+        if ids.dim() != 2 or tuple(mask.shape) != tuple(ids.shape):
+            raise ValueError(f"ids and mask must both be [batch, seq_len], got {tuple(ids.shape)} and {tuple(mask.shape)}")
+        lens = (mask != 0).sum(dim=1).tolist()
+        B, L = ids.shape
+        n = max(int(v) for v in lens)
+        if n == 0 or bool((mask[:, :n] != 0).sum(dim=1).ne(torch.tensor(lens, device=mask.device)).any()):
+            n = L          # not the tokenizer's prefix mask: no trimming
+        emb = torch.zeros(B, L, self.cfg.dim, dtype=BF16, device=self.device)
+        emb[:, :n] = self.forward(ids[:, :n], mask[:, :n])
+        return emb, lens
+
     @torch.no_grad()
     def encode_prompt(self, ids: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         """encode_prompt after tokenisation (PIPE:404-412): the encoder output with the rows from each sample's length on set
-        to zero — in every sample of the batch, as the reference's ``prompt_emb[:, v:] = 0`` loop does."""
-        emb = self.forward(ids, mask)
-        for v in (mask != 0).sum(dim=1).tolist():
+        to zero — in every sample of the batch, as the reference's ``prompt_emb[:, v:] = 0`` loop does (the reference calls
+        it with one prompt at a time).  Only the live prefix is computed."""
+        emb, lens = self._encode_live(ids, mask)
+        for v in lens:
             emb[:, int(v):] = 0
         return emb
+
+    @torch.no_grad()
+    def encode_prompts(self, ids: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """Several prompts (e.g. positive + negative of one call) as ONE batch, each treated as its own reference
+        ``encode_prompt`` call: sample b is zeroed from ITS length on.  The weights are read once for all of them."""
+        emb, lens = self._encode_live(ids, mask)
+        for b, v in enumerate(lens):
+            emb[b, int(v):] = 0
+        return emb
+
+
+def config_of(module) -> UMT5Config:
+    """UMT5Config of a reference ``WanTextEncoder`` instance (its constructor arguments, TENC:225-243)."""
+    return UMT5Config(vocab=module.token_embedding.num_embeddings, dim=module.dim, dim_attn=module.dim_attn, dim_ffn=module.dim_ffn,
+                      num_heads=module.num_heads, num_layers=module.num_layers, num_buckets=module.num_buckets)
+
+
+def install(pipe) -> UMT5Encoder:
+    """Replace ``pipe.text_encoder`` (a loaded reference WanTextEncoder, PIPE:133) by a UMT5Encoder holding the same weights.
+    ``pipe.text_encoder(ids, mask)`` (PIPE:409) then runs on the kernels; the reference module is dropped from the pipeline's
+    children, so its offload / onload bookkeeping (base_pipeline.py:146-168) no longer touches the encoder."""
+    ref = getattr(pipe, "text_encoder", None)
+    if ref is None or getattr(ref, "shared_pos", False):
+        raise ValueError("pipe.text_encoder must be a loaded WanTextEncoder with per-layer position embeddings (shared_pos=False)")
+    enc = UMT5Encoder(config_of(ref), getattr(pipe, "device", "cuda"))
+    enc.load_state_dict(ref.state_dict())
+    if isinstance(pipe, torch.nn.Module):
+        delattr(pipe, "text_encoder")               # unregister the child module before storing a plain object
+        object.__setattr__(pipe, "text_encoder", enc)
+    else:
+        pipe.text_encoder = enc
+    return enc

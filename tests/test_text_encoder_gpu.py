@@ -111,6 +111,28 @@ def test_tiny_encoder_vs_oracle_and_reference_golden(env, name):
     print(f"umT5 tiny {name}: vs oracle {rel_l2(out, want):.3e}, vs reference golden {rel_l2(out, gold):.3e}")
 
 
+def test_encode_prompts_equals_one_reference_call_per_prompt(env):
+    """Positive + negative prompt as one batch == two encode_prompt calls (each zeroed from its own length on)."""
+    ops, te, u = env
+    ocfg, w, enc = _tiny(env)
+    ids, mask = u.make_ids(ocfg, 2, 64, (50, 9), seed=6)
+    both = enc.encode_prompts(ids, mask)
+    ops.sync_check()
+    w16 = {k: v.to(BF).float().cuda() for k, v in w.items()}
+    for b in range(2):
+        want = u.encode_prompt(w16, ocfg, ids[b:b + 1].cuda(), mask[b:b + 1].cuda())
+        alone = enc.encode_prompt(ids[b:b + 1], mask[b:b + 1])
+        assert rel_l2(both[b:b + 1], want) < 1e-2
+        assert rel_l2(both[b:b + 1], alone) < 2e-3       # batch of 2 vs batch of 1: same kernels, other GEMM tile fill
+        assert not both[b, int(mask[b].sum()):].float().abs().max() > 0
+    # a mask that is not a prefix (never produced by the tokenizer) is computed untrimmed
+    odd = mask.clone()
+    odd[0, 60] = 1
+    full = enc.encode_prompts(ids, odd)
+    want = u.encoder_forward(w16, ocfg, ids.cuda(), odd.cuda())
+    assert rel_l2(full[1, :9], want[1, :9]) < 1e-2 and rel_l2(full[0, :51], want[0, :51]) < 1e-2
+
+
 def test_encoder_without_mask_and_cached_bias(env):
     ops, te, u = env
     ocfg, w, enc = _tiny(env)
@@ -137,6 +159,41 @@ def test_one_layer_at_umt5_xxl_dimensions(env):
     want = u.encoder_forward(w16, ocfg, ids.cuda(), mask.cuda())
     assert torch.isfinite(out.float()).all()
     assert rel_l2(out, want) < 1e-2, rel_l2(out, want)
+
+
+def test_install_replaces_the_pipeline_text_encoder(env):
+    """text_encoder.install(pipe): the reference module (a stand-in with its attributes and state dict) is swapped for the
+    kernel encoder, called exactly as PIPE:409 calls it."""
+    ops, te, u = env
+    ocfg = u.TINY
+    w = u.make_weights(ocfg, seed=0)
+
+    class RefEncoder(torch.nn.Module):          # what install() reads off a WanTextEncoder (TENC:225-243)
+        def __init__(self):
+            super().__init__()
+            self.dim, self.dim_attn, self.dim_ffn = ocfg.dim, ocfg.dim_attn, ocfg.dim_ffn
+            self.num_heads, self.num_layers, self.num_buckets, self.shared_pos = ocfg.num_heads, ocfg.num_layers, ocfg.num_buckets, False
+            self.token_embedding = torch.nn.Embedding(ocfg.vocab, ocfg.dim)
+
+        def state_dict(self, *a, **k):
+            return dict(w)
+
+    class Pipe(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.text_encoder = RefEncoder()
+            self.device = "cuda"
+
+    pipe = Pipe()
+    enc = te.install(pipe)
+    assert pipe.text_encoder is enc and "text_encoder" not in dict(pipe.named_children())
+    ids, mask = u.make_ids(ocfg, 1, 40, (13,), seed=3)
+    out = pipe.text_encoder(ids.cuda(), mask.cuda())
+    ops.sync_check()
+    assert rel_l2(out, torch.from_numpy(np.load(GOLD)["short"]).cuda()) < 1.5e-2
+    pipe.text_encoder = None
+    with pytest.raises(ValueError):
+        te.install(pipe)
 
 
 def test_text_encoder_rejects_bad_arguments(env):
