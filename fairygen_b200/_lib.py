@@ -52,6 +52,7 @@ SIGNATURES = {
     "fgb_gelu_tanh_bwd": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P]),
     "fgb_mul_gate": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _P, _P, _I32, _P]),
     "fgb_lora_merge": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _P, _F, _F, _P, _I64, _I32, _I32, _I32, _P]),
+    "fgb_lora_b2_eff_batched": (ctypes.c_int, [_P, _P, _P, _P, _I32, _I32, _F, _F, _P]),
     "fgb_lora_b2_eff": (ctypes.c_int, [_P, _P, _P, _F, _F, _P, _I64, _I64, _I32, _P]),
     "fgb_lora_wgrad": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _F, _I32, _I32, _I32, _I32, _P]),
     "fgb_bernoulli_mask": (ctypes.c_int, [_P, _P, _I64, _F, ctypes.c_uint64, _P]),

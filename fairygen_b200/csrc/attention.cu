@@ -448,10 +448,9 @@ template <int EMU>
 static int launch_attn(int grid, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p) {
   auto kfn = attn_fwd_kernel<EMU>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;  // per template instance and device
+  if (first_use_on_device(configured)) {
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    configured = true;
   }
   kfn<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
   FGB_LAUNCH_CHECK("attn_fwd_kernel");

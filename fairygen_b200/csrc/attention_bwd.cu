@@ -326,10 +326,9 @@ template <bool kDKV>
 static int launch_bwd(dim3 grid, cudaStream_t stream, const CUtensorMap& r1, const CUtensorMap& r2, const CUtensorMap& t1,
                       const CUtensorMap& t2, const AttnBwdParams& p) {
   auto kfn = attn_bwd_kernel<kDKV>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;  // per template instance and device
+  if (first_use_on_device(configured)) {
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-    configured = true;
   }
   kfn<<<grid, kBwdThreads, kBwdSmem, stream>>>(r1, r2, t1, t2, p);
   FGB_LAUNCH_CHECK("attn_bwd_kernel");

@@ -290,10 +290,9 @@ template <int EPI, bool B_MN = false>
 static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t stream, const CUtensorMap* ta2 = nullptr, const CUtensorMap* tb2 = nullptr) {
   auto kfn = gemm_bf16_kernel<EPI, B_MN>;
-  static bool configured = false;  // per template instance; attribute is sticky per function
-  if (!configured) {
+  static unsigned long long configured = 0;  // per template instance and device
+  if (first_use_on_device(configured)) {
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-    configured = true;
   }
   const int grid = p.tiles < ctx->sm_count ? p.tiles : ctx->sm_count;
   kfn<<<grid, kGemmThreads, kGemmSmem, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, p);

@@ -53,6 +53,17 @@ int set_error(int code, const char* fmt, ...);
 int make_tmap_bf16_2d(const fgb_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
                       int64_t ld, int32_t box_rows, int32_t box_cols = 64);
 
+// cudaFuncSetAttribute applies to the current device only: remember per kernel which device ordinals of this process have
+// been configured (one bit each), so that a process driving several GPUs configures every one of them.
+inline bool first_use_on_device(unsigned long long& seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (seen & bit) return false;
+  seen |= bit;
+  return true;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace fgb

@@ -391,6 +391,20 @@ __global__ void lora_b2_eff_kernel(const __nv_bfloat16* __restrict__ b2, const u
   out[(i / rank) * ld_out + (i % rank)] = __float2bfloat16_rn(v * scaling);
 }
 
+// All adapted Linears of the model in one launch: entry e = {offset into the flat B2 / mask buffers, rows, destination pointer,
+// destination row stride}; blockIdx.y = entry, grid-stride over its elements.
+__global__ void lora_b2_eff_batched_kernel(const __nv_bfloat16* __restrict__ b2, const uint8_t* __restrict__ mask,
+                                           const int64_t* __restrict__ table, float mask_mul, float scaling, int rank) {
+  const int64_t* e = table + 4 * static_cast<int64_t>(blockIdx.y);
+  const int64_t off = e[0], total = e[1] * rank, ld_out = e[3];
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(static_cast<uintptr_t>(e[2]));
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float m = mask ? static_cast<float>(mask[off + i]) : 1.0f;
+    const float v = round_bf16(round_bf16(__bfloat162float(b2[off + i]) * m) * mask_mul);
+    out[(i / rank) * ld_out + (i % rank)] = __float2bfloat16_rn(v * scaling);
+  }
+}
+
 // counter-based Bernoulli mask: keep[i] = hash(seed, i) / 2^32 > drop_prob   (torch.rand_like(...) > p, TMOD:342)
 __global__ void bernoulli_mask_kernel(uint8_t* __restrict__ out, int64_t n, float drop_prob, uint64_t seed) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -666,6 +680,15 @@ extern "C" int fgb_adamw_step(fgb_ctx* ctx, void* param_bf16, const void* grad_f
       static_cast<bf16*>(param_bf16), static_cast<const float*>(grad_f32), static_cast<float*>(m_f32), static_cast<float*>(v_f32), n, lr,
       beta1, beta2, eps, weight_decay, bc1, bc2);
   FGB_LAUNCH_CHECK("adamw_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_lora_b2_eff_batched(fgb_ctx* ctx, const void* b2_flat, const void* mask_flat, const void* table, int32_t n_entries,
+                                       int32_t rank, float mask_mul, float scaling, void* stream) {
+  FGB_CHECK_ARG(ctx && b2_flat && table && n_entries > 0 && n_entries <= 65535 && rank > 0, "fgb_lora_b2_eff_batched: bad argument");
+  lora_b2_eff_batched_kernel<<<dim3(48, n_entries), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(b2_flat), static_cast<const uint8_t*>(mask_flat), static_cast<const int64_t*>(table), mask_mul, scaling, rank);
+  FGB_LAUNCH_CHECK("lora_b2_eff_batched_kernel");
   return FGB_OK;
 }
 

@@ -468,6 +468,17 @@ def lora_merge(w, a1, b1, b2, mask, w_eff, mask_mul=2.0, scaling=1.0):
     return w_eff
 
 
+def lora_b2_eff_batched(b2_flat, mask_flat, table, rank: int, mask_mul=2.0, scaling=1.0):
+    """lora_b2_eff for every Linear in one launch; table int64 [n, 4] on the device = (offset, rows, destination pointer, stride)."""
+    if (b2_flat.dtype != BF16 or not b2_flat.is_contiguous() or table.dtype != torch.int64 or table.dim() != 2 or table.shape[1] != 4 or
+            not table.is_contiguous() or table.device != b2_flat.device):
+        raise ValueError("lora_b2_eff_batched: b2_flat contiguous bf16, table int64 [n, 4] on the same device")
+    if mask_flat is not None and (mask_flat.dtype != torch.uint8 or mask_flat.numel() != b2_flat.numel() or not mask_flat.is_contiguous()):
+        raise ValueError("lora_b2_eff_batched: mask_flat must be contiguous uint8 with one entry per B2 element")
+    _lib.check(_lib.lib().fgb_lora_b2_eff_batched(_h(b2_flat).handle, _p(b2_flat), _p(mask_flat), _p(table), table.shape[0], rank, mask_mul,
+                                                  scaling, _stream()), "fgb_lora_b2_eff_batched")
+
+
 def lora_b2_eff(b2, mask, out, mask_mul=2.0, scaling=1.0):
     """out (view with contiguous last dim, e.g. a diagonal block) = scaling * bf16(bf16(b2 * mask) * mask_mul)."""
     n, r = b2.shape

@@ -154,6 +154,7 @@ class Stage2Trainer:
         self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
         self.kernel_launches = 0
         self._mask_calls = 0
+        self._b2_table = None
 
     # ------------------------------------------------------------------------------------------------------------
     # parameters
@@ -197,23 +198,36 @@ class Stage2Trainer:
     def _merge_one(self, w, w_eff, name) -> None:
         ops.lora_merge(w, self.a1[name], self.b1[name], None, None, w_eff, 1.0, self.scaling)
 
-    def merge(self) -> None:
-        """Per step: B2eff = s * bf16(bf16(B2 * mask) * 2) (TMOD:343-346) into the K-extension operands."""
+    def _b2_eff_table(self) -> torch.Tensor:
+        """(offset into b2_flat, rows, destination pointer, destination stride) of every adapted Linear: where its masked,
+        scaled B2 goes inside the K-extension operands (diagonal blocks for the fused q|k|v and cross k|v GEMMs)."""
         d, r = self.cfg.dim, self.rank
+        base = self.b2_flat.data_ptr()
+        rows = []
+
+        def add(name, out):
+            src = self.b2[name]
+            rows.append(((src.data_ptr() - base) // 2, src.shape[0], out.data_ptr(), out.stride(0)))
+
         for i, be in enumerate(self.b2e):
             p = f"blocks.{i}."
             for j, proj in enumerate("qkv"):
-                self._b2_eff(p + "self_attn." + proj, be["qkv"][j * d:(j + 1) * d, j * r:(j + 1) * r])
-            self._b2_eff(p + "self_attn.o", be["o"])
-            self._b2_eff(p + "cross_attn.q", be["cq"])
+                add(p + "self_attn." + proj, be["qkv"][j * d:(j + 1) * d, j * r:(j + 1) * r])
+            add(p + "self_attn.o", be["o"])
+            add(p + "cross_attn.q", be["cq"])
             for j, proj in enumerate("kv"):
-                self._b2_eff(p + "cross_attn." + proj, be["ckv"][j * d:(j + 1) * d, j * r:(j + 1) * r])
-            self._b2_eff(p + "cross_attn.o", be["co"])
-            self._b2_eff(p + "ffn.0", be["f1"])
-            self._b2_eff(p + "ffn.2", be["f2"])
+                add(p + "cross_attn." + proj, be["ckv"][j * d:(j + 1) * d, j * r:(j + 1) * r])
+            add(p + "cross_attn.o", be["co"])
+            add(p + "ffn.0", be["f1"])
+            add(p + "ffn.2", be["f2"])
+        return torch.tensor(rows, dtype=torch.int64, device=self.engine.device)
 
-    def _b2_eff(self, name, out) -> None:
-        ops.lora_b2_eff(self.b2[name], self.mask[name], out, self.mask_mul, self.scaling)
+    def merge(self) -> None:
+        """Per step: B2eff = s * bf16(bf16(B2 * mask) * 2) (TMOD:343-346) into the K-extension operands — one launch for
+        all 10 x num_layers Linears."""
+        if self._b2_table is None:
+            self._b2_table = self._b2_eff_table()
+        ops.lora_b2_eff_batched(self.b2_flat, self._mask_flat, self._b2_table, self.rank, self.mask_mul, self.scaling)
         self.kernel_launches += 1
 
     # ------------------------------------------------------------------------------------------------------------

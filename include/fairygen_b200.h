@@ -262,6 +262,11 @@ int fgb_lora_merge(fgb_ctx* ctx, const void* w, int64_t ldw, const void* a1, int
 int fgb_lora_b2_eff(fgb_ctx* ctx, const void* b2, const void* mask, float mask_mul, float scaling, void* out, int64_t ld_out,
                     int64_t n_rows, int32_t rank, void* stream);
 
+/* The same for every adapted Linear of the model in ONE launch. table: int64 [n_entries][4] on the device, entry =
+ * {element offset into b2_flat / mask_flat, rows, destination pointer, destination row stride (elements)}. */
+int fgb_lora_b2_eff_batched(fgb_ctx* ctx, const void* b2_flat, const void* mask_flat, const void* table, int32_t n_entries,
+                            int32_t rank, float mask_mul, float scaling, void* stream);
+
 /* db[n, r] += mul * mask[n, r] * sum_s dy[s, n] * t[s, r]   (fp32 accumulate; t = A1·x, [rows, rank] bf16).
  * transpose_out = 1 writes db as [rank, n] instead (mask must be NULL): dA = uᵀ·X of the stage-1 LoRA, called with dy := X,
  * t := u = dY·Beff (training_module.py:200-264). */
