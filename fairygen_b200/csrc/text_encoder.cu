@@ -333,8 +333,9 @@ extern "C" int fgb_t5_attention(fgb_ctx* ctx, const void* q, int64_t ldq, const 
   FGB_CHECK_ARG(ldq >= width && ldk >= width && ldv >= width && ldo >= width && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 &&
                     aligned16(q) && aligned16(k) && aligned16(v) && (reinterpret_cast<uintptr_t>(o) & 3u) == 0,
                 "fgb_t5_attention: head_dim is 64; rows must be 16-byte aligned (ld %% 8) and at least heads*64 wide");
-  // > 48 KB of dynamic shared memory needs the opt-in (per device; a few hundred ns, so not cached)
-  FGB_CUDA(cudaFuncSetAttribute(t5_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeSmemBytes));
+  static unsigned long long configured = 0;   // > 48 KB of dynamic shared memory needs the opt-in, once per device
+  if (first_use_on_device(configured))
+    FGB_CUDA(cudaFuncSetAttribute(t5_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeSmemBytes));
   dim3 grid((s_q + kTeRows - 1) / kTeRows, heads, batch);
   t5_attention_kernel<<<grid, 256, kTeSmemBytes, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, static_cast<const bf16*>(v), ldv, static_cast<bf16*>(o), ldo, s_q,

@@ -77,9 +77,18 @@ class _Block:
     __slots__ = ("norm1", "wqkv", "wo", "norm2", "wgf", "w2", "pos")
 
 
+class _Captured:
+    """One captured forward: the CUDA graph plus every buffer its kernels were recorded with."""
+    __slots__ = ("graph", "ids", "mask", "out", "ws", "bias")
+
+
 class UMT5Encoder:
-    def __init__(self, cfg: UMT5Config = UMT5_XXL, device="cuda"):
+    def __init__(self, cfg: UMT5Config = UMT5_XXL, device="cuda", use_graph: bool = True):
+        """use_graph: the ~200 launches of a forward are a few microseconds of GPU work each at prompt sizes, so the forward
+        is captured once per (batch, length, masked?) into a CUDA graph and replayed (the launch-bound inner loop)."""
         self.cfg = cfg
+        self.use_graph = use_graph
+        self._graphs: Dict[tuple, _Captured] = {}
         self.device = torch.device(device)
         ops.context(self.device)       # raises off-GPU: there is no CPU path
         self.loaded = False
@@ -116,6 +125,7 @@ class UMT5Encoder:
             b.pos = g(p + "pos_embedding.embedding.weight")
             self.blocks.append(b)
         self._bias_cache.clear()
+        self._graphs.clear()           # captured graphs hold pointers to the previous weights
         self.loaded = True
 
     def _bias_tables(self, L: int) -> torch.Tensor:
@@ -144,6 +154,45 @@ class UMT5Encoder:
         return ws
 
     # ------------------------------------------------------------------------------------------------------------
+    def _launch(self, ids_dev, key_mask, B: int, ws, bias, out) -> None:
+        """The kernels of one forward, in order, on the current stream; allocates nothing (capturable)."""
+        cfg = self.cfg
+        x, n, qkv, o, gf, h = (ws[k] for k in ("x", "n", "qkv", "o", "gf", "h"))
+        da, H = cfg.dim_attn, cfg.num_heads
+        ops.embedding_rows(self.token_embedding, ids_dev, x)
+        for i, b in enumerate(self.blocks):
+            ops.t5_layer_norm(x, n, cfg.eps, b.norm1)
+            ops.gemm(n, b.wqkv, None, qkv, EPI_BIAS)
+            ops.t5_attention(qkv[:, :da], qkv[:, da:2 * da], qkv[:, 2 * da:], o, B, H, bias=bias[i], key_mask=key_mask)
+            ops.gemm(o, b.wo, None, x, EPI_RESIDUAL)                     # x += o(attn)            TENC:144
+            ops.t5_layer_norm(x, n, cfg.eps, b.norm2)
+            ops.gemm(n, b.wgf, None, gf, EPI_BIAS)
+            ops.geglu(gf, h)
+            ops.gemm(h, b.w2, None, x, EPI_RESIDUAL)                     # x += fc2(fc1 * gelu(gate))  TENC:145
+        ops.t5_layer_norm(x, out, cfg.eps, self.norm)
+        self.kernel_launches += 2 + 8 * cfg.num_layers
+
+    def _capture(self, key, ids_dev, key_mask, B: int, L: int) -> _Captured:
+        cfg, dev = self.cfg, self.device
+        c = _Captured()
+        c.ids = ids_dev.clone()
+        c.mask = None if key_mask is None else key_mask.clone()
+        c.out = torch.empty(B * L, cfg.dim, dtype=BF16, device=dev)
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
+        rows = B * L
+        c.ws = dict(x=e(rows, cfg.dim), n=e(rows, cfg.dim), qkv=e(rows, 3 * cfg.dim_attn), o=e(rows, cfg.dim_attn),
+                    gf=e(rows, 2 * cfg.dim_ffn), h=e(rows, cfg.dim_ffn))
+        c.bias = self._bias_tables(L)
+        self._launch(c.ids, c.mask, B, c.ws, c.bias, c.out)        # eager once: one-time kernel attributes are set outside capture
+        torch.cuda.synchronize(dev)
+        c.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(c.graph):
+            self._launch(c.ids, c.mask, B, c.ws, c.bias, c.out)
+        if len(self._graphs) >= 16:
+            self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[key] = c
+        return c
+
     @torch.no_grad()
     def forward(self, ids: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """WanTextEncoder.forward (TENC:245-254): ids [B, L] int, mask [B, L] (0 = padded key) or None -> [B, L, dim] bf16."""
@@ -163,24 +212,19 @@ class UMT5Encoder:
                 raise ValueError("mask leaves a sample without any key (the tokenizer always emits </s>)")
             key_mask = (mask != 0).to(device=dev, dtype=torch.uint8).contiguous()
         ids_dev = ids.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
-        rows = B * L
-        ws = self._workspace(rows)
-        x, n, qkv, o, gf, h = (ws[k] for k in ("x", "n", "qkv", "o", "gf", "h"))
-        bias = self._bias_tables(L)
-        da, H = cfg.dim_attn, cfg.num_heads
-        ops.embedding_rows(self.token_embedding, ids_dev, x)
-        for i, b in enumerate(self.blocks):
-            ops.t5_layer_norm(x, n, cfg.eps, b.norm1)
-            ops.gemm(n, b.wqkv, None, qkv, EPI_BIAS)
-            ops.t5_attention(qkv[:, :da], qkv[:, da:2 * da], qkv[:, 2 * da:], o, B, H, bias=bias[i], key_mask=key_mask)
-            ops.gemm(o, b.wo, None, x, EPI_RESIDUAL)                     # x += o(attn)            TENC:144
-            ops.t5_layer_norm(x, n, cfg.eps, b.norm2)
-            ops.gemm(n, b.wgf, None, gf, EPI_BIAS)
-            ops.geglu(gf, h)
-            ops.gemm(h, b.w2, None, x, EPI_RESIDUAL)                     # x += fc2(fc1 * gelu(gate))  TENC:145
-        out = torch.empty(rows, cfg.dim, dtype=BF16, device=dev)
-        ops.t5_layer_norm(x, out, cfg.eps, self.norm)
-        self.kernel_launches += 2 + 8 * cfg.num_layers
+        if self.use_graph and not torch.cuda.is_current_stream_capturing():
+            key = (B, L, key_mask is not None)
+            c = self._graphs.get(key)
+            if c is None:
+                c = self._capture(key, ids_dev, key_mask, B, L)
+            c.ids.copy_(ids_dev)
+            if key_mask is not None:
+                c.mask.copy_(key_mask)
+            c.graph.replay()
+            self.kernel_launches += 2 + 8 * cfg.num_layers
+            return c.out.clone().view(B, L, cfg.dim)      # the graph's output buffer is overwritten by the next call
+        out = torch.empty(B * L, cfg.dim, dtype=BF16, device=dev)
+        self._launch(ids_dev, key_mask, B, self._workspace(B * L), self._bias_tables(L), out)
         return out.view(B, L, cfg.dim)
 
     __call__ = forward
@@ -195,6 +239,7 @@ class UMT5Encoder:
         n = max(int(v) for v in lens)
         if n == 0 or bool((mask[:, :n] != 0).sum(dim=1).ne(torch.tensor(lens, device=mask.device)).any()):
             n = L          # not the tokenizer's prefix mask: no trimming
+        n = min(L, -(-n // 32) * 32)   # a few extra masked positions; prompt lengths then share workspaces / captured graphs
         emb = torch.zeros(B, L, self.cfg.dim, dtype=BF16, device=self.device)
         emb[:, :n] = self.forward(ids[:, :n], mask[:, :n])
         return emb, lens

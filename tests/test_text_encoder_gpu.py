@@ -161,6 +161,21 @@ def test_one_layer_at_umt5_xxl_dimensions(env):
     assert rel_l2(out, want) < 1e-2, rel_l2(out, want)
 
 
+def test_captured_graph_equals_eager_launches(env):
+    """The CUDA-graph replay (default) and the plain launch sequence give the same bits, call after call, for new ids / masks
+    of a captured shape and for a new shape."""
+    ops, te, u = env
+    ocfg, w, enc = _tiny(env)
+    eager = te.UMT5Encoder(enc.cfg, "cuda", use_graph=False)
+    eager.load_state_dict(w)
+    for seed, (b, L, live) in enumerate([(2, 64, (40, 64)), (2, 64, (64, 3)), (1, 40, (13,)), (2, 64, (5, 6))]):
+        ids, mask = u.make_ids(ocfg, b, L, live, seed=20 + seed)
+        got, want = enc(ids, mask), eager(ids, mask)
+        ops.sync_check()
+        assert torch.equal(got, want), (seed, rel_l2(got, want))
+    assert len(enc._graphs) == 2 and not eager._graphs
+
+
 def test_install_replaces_the_pipeline_text_encoder(env):
     """text_encoder.install(pipe): the reference module (a stand-in with its attributes and state dict) is swapped for the
     kernel encoder, called exactly as PIPE:409 calls it."""

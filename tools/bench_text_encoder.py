@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--live", type=int, nargs=2, default=[96, 160], help="live tokens of the positive / negative prompt")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="plain launch sequence instead of the captured CUDA graph")
     args = ap.parse_args()
     from fairygen_b200 import ops, text_encoder as te
 
@@ -40,7 +41,7 @@ def main():
         else:
             t = torch.randn(shape, generator=g, device=dev, dtype=torch.bfloat16) * (shape[1] ** -0.5) * (0.35 if ".attn.q." in name or ".attn.k." in name else 1.0)
         sd[name] = t.to(torch.bfloat16)
-    enc = te.UMT5Encoder(cfg, dev)
+    enc = te.UMT5Encoder(cfg, dev, use_graph=not args.no_graph)
     enc.load_state_dict(sd)
     del sd
     B, L = 2, 512
@@ -76,7 +77,8 @@ def main():
     ms_e2e = timed(e2e, args.steps)
     # the attention kernel alone, on the buffers of the last layer (24 launches = one forward's worth)
     Le = max(args.live)
-    ws = enc._workspace(B * Le)
+    ws = {"qkv": (torch.randn(B * Le, 3 * cfg.dim_attn, device=dev) * 0.3).to(torch.bfloat16),
+          "o": torch.empty(B * Le, cfg.dim_attn, device=dev, dtype=torch.bfloat16)}
     bias = enc._bias_tables(Le)
     km = (mask_dev[:, :Le] != 0).to(torch.uint8).contiguous()
     da = cfg.dim_attn
@@ -96,7 +98,7 @@ def main():
         "config": {"workload": f"umT5-xxl encoder, 24 layers, 2 prompts x 512 tokens in one batch (live {args.live}; padded tail not computed), random-init weights"},
         "e2e": {"value": B * 1e3 / ms_e2e, "unit": "prompts/s", "h2d_bytes_per_step": ids.numel() * 8 + mask.numel() * 8,
                 "d2h_bytes_per_step": out_host.numel() * 2},
-        "gpu_launches": launches, "attention_ms_per_step": ms_attn, "attention_share": ms_attn / ms,
+        "gpu_launches": launches, "cuda_graph": not args.no_graph, "attention_ms_per_step": ms_attn, "attention_share": ms_attn / ms,
         "gemm_tflops": gemm_flops / (ms * 1e-3) / 1e12, "weight_stream_gbps_lower_bound": weight_bytes / (ms * 1e-3) / 1e9,
     }
     if not args.no_cpu_baseline:
