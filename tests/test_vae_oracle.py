@@ -1,0 +1,74 @@
+"""oracle/vae38_oracle.py against the REAL reference VAE38's outputs (tests/golden/vae38.npz, written by
+oracle/make_golden_vae.py in the build container): chunked causal decode with the feature cache, single frame, tiled decode
+with blending (even and ragged tilings), and the primitives (DupUp3D, unpatchify, attention block, temporal up-sampling
+across chunks, residual block across chunks)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vae38_oracle as o
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "vae38.npz"))
+
+
+def latents(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return o.make_weights(o.TINY, seed=0)
+
+
+def close(a, b, tol=2e-5):
+    np.testing.assert_allclose(a.numpy() if isinstance(a, torch.Tensor) else a, b, rtol=tol, atol=tol)
+
+
+def test_plan_matches_the_full_size_decoder():
+    assert o.VAE38.dims == [1024, 1024, 1024, 512, 256] and o.VAE38.upsampling_factor == 16
+    assert [(up, t) for _, _, _, up, t in o.stage_plan(o.VAE38)] == [(True, True), (True, True), (True, False), (False, False)]
+    assert o.count_cache_slots(o.VAE38) == o.count_cache_slots(o.TINY)
+
+
+def test_model_decode_chunked(weights):
+    with torch.no_grad():
+        got = o.model_decode(weights, o.TINY, latents((1, 8, 3, 3, 4), 1))
+    assert got.shape == (1, 3, 9, 48, 64)
+    close(got, GOLD["model_decode"])
+
+
+def test_single_frame_is_clamped(weights):
+    with torch.no_grad():
+        got = o.decode(weights, o.TINY, latents((1, 8, 1, 2, 2), 2) * 3)
+    close(got, GOLD["single_frame"])
+    assert got.min() >= -1 and got.max() <= 1 and (got.abs() == 1).any()
+
+
+def test_tiled_decode(weights):
+    with torch.no_grad():
+        close(o.decode(weights, o.TINY, latents((1, 8, 2, 5, 5), 3), tiled=True, tile_size=(3, 3), tile_stride=(2, 2)), GOLD["tiled"])
+        close(o.decode(weights, o.TINY, latents((1, 8, 1, 4, 7), 4), tiled=True, tile_size=(3, 4), tile_stride=(2, 3)), GOLD["tiled_ragged"])
+    assert o.tile_tasks(44, 80, (30, 52), (15, 26)) == [(0, 30, 0, 52), (0, 30, 26, 78), (0, 30, 52, 104), (15, 45, 0, 52), (15, 45, 26, 78),
+                                                        (15, 45, 52, 104)]          # 704x1280 with the pipeline's defaults
+
+
+def test_primitives(weights):
+    cfg = o.TINY
+    x = latents((1, 32, 1, 3, 4), 5)
+    assert np.array_equal(o.dup_up3d(x, 16, 2, 2, True).numpy(), GOLD["dup_t2_first"])
+    assert np.array_equal(o.dup_up3d(x, 16, 2, 2, False).numpy(), GOLD["dup_t2"])
+    assert np.array_equal(o.dup_up3d(x, 32, 1, 2, True).numpy(), GOLD["dup_t1"])
+    assert np.array_equal(o.unpatchify(latents((1, 12, 2, 3, 5), 6)).numpy(), GOLD["unpatchify"])
+    with torch.no_grad():
+        close(o.attention_block(weights, "decoder.middle.1.", latents((1, cfg.dims[0], 2, 3, 4), 7)), GOLD["attention"])
+        cache = [None]
+        for i in range(3):          # chunk 0 skips the temporal doubling, chunk 1 sees zeros, chunk 2 the cached frame
+            got = o.resample_up(weights, "decoder.upsamples.0.upsamples.3.", latents((1, cfg.dims[1], 1, 2, 3), 10 + i), True, cache, [0])
+            close(got, GOLD[f"resample3d_c{i}"])
+        cache = [None, None]
+        for i in range(3):
+            got = o.residual_block(weights, "decoder.upsamples.2.upsamples.0.", latents((1, cfg.dims[2], 1 if i < 2 else 2, 3, 3), 20 + i),
+                                   cache, [0])
+            close(got, GOLD[f"resblock_c{i}"])
