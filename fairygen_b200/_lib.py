@@ -60,6 +60,15 @@ SIGNATURES = {
     "fgb_mse_loss_grad": (ctypes.c_int, [_P, _P, _P, _F, _P, _P, _I64, _P]),
     "fgb_unpatchify_bwd": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P]),
     "fgb_adamw_step": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P]),
+    "fgb_conv_taps_bf16": (ctypes.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32,
+                                          ctypes.POINTER(ctypes.c_int32), _I32, _I32, _I32, _P]),
+    "fgb_vae_latent_rows": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "fgb_vae_norm_silu": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _I32, _P]),
+    "fgb_vae_upsample2x": (ctypes.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "fgb_vae_dup_up_add": (ctypes.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "fgb_vae_attn_softmax": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _F, _P]),
+    "fgb_vae_unpatchify": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "fgb_vae_blend_finish": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "fgb_embedding_rows": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _I64, _P]),
     "fgb_t5_layer_norm": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P]),
     "fgb_geglu": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _P]),

@@ -42,6 +42,12 @@ struct GemmParams {
   int32_t rows_gate0;
   int32_t m_blocks, n_blocks, tiles, k_blocks;
   int32_t k2_blocks;   // extra K-blocks taken from the second operand pair (tmap_a2, tmap_b2): acc += A2 · W2ᵀ (or A2 · W2)
+  // Convolution as a GEMM over shifted rows (fgb_conv_taps_bf16): K-block kb belongs to tap kb / tap_kblocks and reads the A
+  // rows [m_blk*128 + a_row0 + tap_off[tap], +128) — TMA zero-fills rows outside the tensor. tap_kblocks = 0: plain GEMM.
+  int32_t tap_kblocks;
+  int32_t a_row0;
+  int32_t grid_h, grid_w;   // > 0: C rows are positions of a [.., grid_h, grid_w] grid whose 1-wide border is written as zero
+  int32_t tap_off[27];
 };
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
@@ -138,7 +144,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const CUtensorMap* ma = second ? &tmap_a2 : &tmap_a;
           const CUtensorMap* mb = second ? &tmap_b2 : &tmap_b;
           const int kc = (second ? kb - p.k_blocks : kb) * kBK;
-          tma_load_2d(smem_a + stage * kABytes, ma, &full[stage], kc, m_blk * kBM, kEvictNormal);
+          if (p.tap_kblocks > 0) {
+            const int tap = kb / p.tap_kblocks;
+            tma_load_2d(smem_a + stage * kABytes, ma, &full[stage], (kb - tap * p.tap_kblocks) * kBK,
+                        m_blk * kBM + p.a_row0 + p.tap_off[tap], kEvictNormal);
+          } else {
+            tma_load_2d(smem_a + stage * kABytes, ma, &full[stage], kc, m_blk * kBM, kEvictNormal);
+          }
           if (B_MN) {
 #pragma unroll
             for (int b = 0; b < kBN / 64; ++b)
@@ -196,6 +208,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int row = m_blk * kBM + quarter * 32 + lane;
       const bool row_ok = row < p.m;
+      bool border = false;
+      if (p.grid_w > 0) {
+        const int pos = row % (p.grid_h * p.grid_w), gy = pos / p.grid_w, gx = pos - gy * p.grid_w;
+        border = gy == 0 || gy == p.grid_h - 1 || gx == 0 || gx == p.grid_w - 1;
+      }
       __nv_bfloat16* crow = p.c + static_cast<int64_t>(row) * p.ldc;
       const __nv_bfloat16* gate = nullptr;
       if (EPI == FGB_EPI_GATED_RESIDUAL) gate = (row < p.rows_gate0) ? p.gate0 : p.gate1;
@@ -261,6 +278,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (row_ok) {
             uint4 o;
+            if (border) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = 0.f;
+            }
             o.x = pack_bf16(y[0], y[1]);
             o.y = pack_bf16(y[2], y[3]);
             o.z = pack_bf16(y[4], y[5]);
@@ -338,6 +359,9 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
   }
 
   GemmParams p;
+  p.tap_kblocks = 0;
+  p.a_row0 = 0;
+  p.grid_h = p.grid_w = 0;
   p.k2_blocks = k2 > 0 ? (k2 + kBK - 1) / kBK : 0;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.c = static_cast<__nv_bfloat16*>(c);
@@ -389,6 +413,9 @@ extern "C" int fgb_gemm_dgrad_ex(fgb_ctx* ctx, const void* dy, int64_t ld_dy, co
     if ((rc = make_tmap_bf16_2d(ctx, &tb2, a1, k2, n_in, ld_a1, kBK))) return rc;
   }
   GemmParams p;
+  p.tap_kblocks = 0;
+  p.a_row0 = 0;
+  p.grid_h = p.grid_w = 0;
   p.k2_blocks = k2 > 0 ? (k2 + kBK - 1) / kBK : 0;
   p.bias = nullptr;
   p.c = static_cast<__nv_bfloat16*>(dx);
@@ -404,4 +431,44 @@ extern "C" int fgb_gemm_dgrad_ex(fgb_ctx* ctx, const void* dy, int64_t ld_dy, co
   p.k_blocks = (k_out + kBK - 1) / kBK;
   return launch_gemm<FGB_EPI_BIAS, true>(ctx, ta, tb, p, static_cast<cudaStream_t>(stream), k2 > 0 ? &ta2 : nullptr,
                                          k2 > 0 ? &tb2 : nullptr);
+}
+
+extern "C" int fgb_conv_taps_bf16(fgb_ctx* ctx, const void* x, int64_t ldx, int64_t x_rows, int64_t a_row0, const void* w, int64_t ldw,
+                                  const void* bias, void* out, int64_t ldo, int32_t m, int32_t n, int32_t cin, int32_t taps,
+                                  const int32_t* tap_offsets, int32_t grid_h, int32_t grid_w, int32_t epilogue, void* stream) {
+  using namespace fgb;
+  FGB_CHECK_ARG(ctx && x && w && out && tap_offsets, "fgb_conv_taps_bf16: NULL argument");
+  FGB_CHECK_ARG(m > 0 && n > 0 && n % 8 == 0 && cin > 0 && cin % kBK == 0 && taps >= 1 && taps <= 27,
+                "fgb_conv_taps_bf16: m=%d n=%d cin=%d taps=%d (n %% 8, cin %% 64, 1 <= taps <= 27)", m, n, cin, taps);
+  FGB_CHECK_ARG(x_rows > 0 && ldx >= cin && ldw >= static_cast<int64_t>(taps) * cin && ldo >= n && ldo % 8 == 0 && aligned16(out) &&
+                    (!bias || aligned16(bias)), "fgb_conv_taps_bf16: leading dimensions / alignment");
+  FGB_CHECK_ARG(epilogue == FGB_EPI_BIAS || epilogue == FGB_EPI_RESIDUAL, "fgb_conv_taps_bf16: epilogue must be BIAS or RESIDUAL");
+  FGB_CHECK_ARG((grid_h == 0 && grid_w == 0) || (grid_h >= 3 && grid_w >= 3), "fgb_conv_taps_bf16: grid %d x %d", grid_h, grid_w);
+  FGB_CHECK_ARG(a_row0 > -(1ll << 30) && a_row0 < (1ll << 30) && x_rows < (1ll << 31), "fgb_conv_taps_bf16: row range");
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(ctx, &ta, x, x_rows, cin, ldx, kBM);
+  if (rc) return rc;
+  if ((rc = make_tmap_bf16_2d(ctx, &tb, w, n, static_cast<int64_t>(taps) * cin, ldw, kBN))) return rc;
+  GemmParams p;
+  p.tap_kblocks = cin / kBK;
+  p.a_row0 = static_cast<int32_t>(a_row0);
+  p.grid_h = grid_h;
+  p.grid_w = grid_w;
+  for (int i = 0; i < 27; ++i) p.tap_off[i] = i < taps ? tap_offsets[i] : 0;
+  p.k2_blocks = 0;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.c = static_cast<__nv_bfloat16*>(out);
+  p.gate0 = p.gate1 = nullptr;
+  p.ldc = ldo;
+  p.m = m;
+  p.n = n;
+  p.k = taps * cin;
+  p.rows_gate0 = 0;
+  p.m_blocks = (m + kBM - 1) / kBM;
+  p.n_blocks = (n + kBN - 1) / kBN;
+  p.tiles = p.m_blocks * p.n_blocks;
+  p.k_blocks = taps * p.tap_kblocks;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (epilogue == FGB_EPI_RESIDUAL) return launch_gemm<FGB_EPI_RESIDUAL>(ctx, ta, tb, p, s);
+  return launch_gemm<FGB_EPI_BIAS>(ctx, ta, tb, p, s);
 }

@@ -1,0 +1,296 @@
+// fairygen_b200 — kernels of the Wan2.2 VAE38 decoder around its convolutions (sm_100a).            SURVEY §8(f) row 1
+//
+// Reference: animation/diffsynth/models/wan_video_vae.py ("VAE"). Feature maps live channels-last on a zero-bordered grid,
+//   G[t][y][x][c],  y in [0, H+2), x in [0, W+2), c in [0, Cp)   (Cp = channels rounded up to 64, padding channels zero),
+// so that a causal 3x3x3 convolution is a GEMM over shifted rows of the flattened grid (fgb_conv_taps_bf16 in gemm.cu: one
+// K-block group per tap, the tap's row offset added to the TMA coordinate, border rows written as zero by the epilogue) and
+// the two cached frames of CausalConv3d (VAE:44-52, 288-301) are simply the two frames stored in front of the new ones.
+// This file holds the memory-bound rest: latent de-normalisation into the grid, RMS_norm + SiLU, nearest-exact 2x
+// up-sampling (with the frame interleave of the temporal up-sampling), the DupUp3D shortcut, the softmax of the single-head
+// attention block, and un-patchify + tile blending + clamp. One pass each, 16-byte accesses along the channels, fp32 math.
+#include "common.cuh"
+#include "host.h"
+
+namespace fgb {
+
+static inline int vae_grid(int64_t n, int block, int cap) {
+  const int64_t g = (n + block - 1) / block;
+  return static_cast<int>(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// z / (1/std) + mean (VAE:1328-1331), [C][T][H][W] -> grid interior (border and padding channels are left as they are: zero)
+// ---------------------------------------------------------------------------------------------
+__global__ void vae_latent_rows_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                       __nv_bfloat16* __restrict__ out, int C, int T, int H, int W, int Cp) {
+  const int64_t total = static_cast<int64_t>(T) * H * W * C;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    int64_t r = idx / C;
+    const int x = static_cast<int>(r % W);
+    r /= W;
+    const int y = static_cast<int>(r % H), t = static_cast<int>(r / H);
+    const float v = round_bf16(__bfloat162float(z[((static_cast<int64_t>(c) * T + t) * H + y) * W + x]) / inv_std[c]) + mean[c];
+    out[((static_cast<int64_t>(t) * (H + 2) + y + 1) * (W + 2) + x + 1) * Cp + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMS_norm (VAE:67-70: x / max(|x|_2, 1e-12) * sqrt(C) * gamma) followed by SiLU (VAE:274-277). One warp per grid row.
+// Zero rows (the border) stay zero, so the output is again a zero-bordered grid.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) vae_norm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                            int64_t rows, int Cp, float sqrt_c, const __nv_bfloat16* __restrict__ gamma,
+                                                            int silu) {
+  const int64_t row = blockIdx.x * 4ll + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * Cp);
+  const int nvec = Cp / 8;
+  float ss = 0.f;
+  for (int i = lane; i < nvec; i += 32) {
+    float f[8];
+    unpack8(xr[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
+  uint4* orow = reinterpret_cast<uint4*>(out + row * Cp);
+  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
+  for (int i = lane; i < nvec; i += 32) {
+    float f[8], g[8];
+    unpack8(xr[i], f);
+    unpack8(ldg_nc_v4(gr + i), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = round_bf16(f[j] * inv * g[j]);
+      if (silu) y = y / (1.f + __expf(-y));
+      f[j] = y;
+    }
+    orow[i] = pack8(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Upsample(scale 2, nearest-exact) per frame (VAE:73-79, 98-100) into the interior of a grid of twice the size. With halves = 2
+// the source is the output of the temporal up-sampling conv (VAE:147-156): frame t' of the result is the channel half t' % 2 of
+// source frame t' / 2.
+// ---------------------------------------------------------------------------------------------
+__global__ void vae_upsample2x_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cp, int T_dst, int H,
+                                      int W, int halves) {
+  const int vec = Cp / 8;
+  const int64_t total = static_cast<int64_t>(T_dst) * (2 * H) * (2 * W) * vec;
+  const int64_t ld_src = static_cast<int64_t>(halves) * Cp;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % vec);
+    int64_t r = idx / vec;
+    const int x = static_cast<int>(r % (2 * W));
+    r /= 2 * W;
+    const int y = static_cast<int>(r % (2 * H)), t = static_cast<int>(r / (2 * H));
+    const int64_t srow = (static_cast<int64_t>(t / halves) * (H + 2) + (y >> 1) + 1) * (W + 2) + (x >> 1) + 1;
+    const uint4 v = ldg_nc_v4(reinterpret_cast<const uint4*>(src + srow * ld_src + static_cast<int64_t>(t % halves) * Cp) + c);
+    const int64_t drow = (static_cast<int64_t>(t) * (2 * H + 2) + y + 1) * (2 * W + 2) + x + 1;
+    reinterpret_cast<uint4*>(dst + drow * Cp)[c] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main += DupUp3D(x) (VAE:417-439, 511-512): channel j = ((c_out*ft + a)*2 + b)*2 + d of repeat_interleave(x, repeats) lands at
+// (t*ft + a, 2y + b, 2x + d); on the first chunk the first ft-1 frames are dropped.
+// ---------------------------------------------------------------------------------------------
+__global__ void vae_dup_up_add_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ main, int Cin_p, int Cout, int Cout_p,
+                                      int repeats, int ft, int skip, int T_out, int H, int W) {
+  const int64_t total = static_cast<int64_t>(T_out) * (2 * H) * (2 * W) * Cout;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % Cout);
+    int64_t r = idx / Cout;
+    const int xo = static_cast<int>(r % (2 * W));
+    r /= 2 * W;
+    const int yo = static_cast<int>(r % (2 * H)), to = static_cast<int>(r / (2 * H));
+    const int tt = to + skip, a = tt % ft, t = tt / ft;
+    const int j = ((c * ft + a) * 2 + (yo & 1)) * 2 + (xo & 1);
+    const int64_t srow = (static_cast<int64_t>(t) * (H + 2) + (yo >> 1) + 1) * (W + 2) + (xo >> 1) + 1;
+    const int64_t drow = (static_cast<int64_t>(to) * (2 * H + 2) + yo + 1) * (2 * W + 2) + xo + 1;
+    __nv_bfloat16* d = main + drow * Cout_p + c;
+    *d = __float2bfloat16_rn(__bfloat162float(*d) + __bfloat162float(x[srow * Cin_p + j / repeats]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row softmax of the attention block's scores (VAE:331-337, scale 1/sqrt(C)), in place on bf16 [rows][ld]; keys are grid
+// positions of one frame: the border positions and the columns past the frame are excluded.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) vae_attn_softmax_kernel(__nv_bfloat16* __restrict__ s, int64_t ld, int rows, int n_cols, int gh, int gw,
+                                                               float scale) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  __nv_bfloat16* sr = s + static_cast<int64_t>(row) * ld;
+  const int tokens = gh * gw;
+  auto live = [&](int col) {
+    if (col >= tokens) return false;
+    const int y = col / gw, x = col - y * gw;
+    return y > 0 && y < gh - 1 && x > 0 && x < gw - 1;
+  };
+  float mx = -INFINITY;
+  for (int c = lane; c < n_cols; c += 32)
+    if (live(c)) mx = fmaxf(mx, __bfloat162float(sr[c]) * scale);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float sum = 0.f;
+  for (int c = lane; c < n_cols; c += 32)
+    if (live(c)) sum += __expf(__bfloat162float(sr[c]) * scale - mx);
+  sum = warp_sum(sum);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  for (int c = lane; c < n_cols; c += 32)
+    sr[c] = __float2bfloat16_rn(live(c) ? __expf(__bfloat162float(sr[c]) * scale - mx) * inv : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Un-patchify 'b (c r q) f h w -> b c f (h q) (w r)' (VAE:214-224) of the head output (12 of Cp channels) into the video, either
+// clamped to [-1, 1] directly (single_decode, VAE:1212-1215) or accumulated with the blending ramps of tiled_decode
+// (VAE:1081-1100, 1128-1150): values += v * mask, weight += mask, mask = min(ramp_y, ramp_x).
+// ---------------------------------------------------------------------------------------------
+struct VaeOutParams {
+  int T, H, W, Cp;            // head grid: T frames of H x W positions (interior), Cp channels per row
+  int t0, y0, x0;             // where the tile starts in the video (frames, pixels)
+  int VT, VH, VW;             // video size
+  int top_bound, bottom_bound, left_bound, right_bound, border_y, border_x;
+};
+
+__device__ __forceinline__ float vae_ramp(int i, int n, int first_is_bound, int last_is_bound, int border) {
+  float m = 1.f;
+  if (!first_is_bound && i < border) m = static_cast<float>(i + 1) / border;
+  if (!last_is_bound && i >= n - border) m = static_cast<float>(n - i) / border;   // flip((arange+1)/border)
+  return m;
+}
+
+template <bool BLEND>
+__global__ void vae_unpatchify_kernel(const __nv_bfloat16* __restrict__ head, float* __restrict__ values, float* __restrict__ weight,
+                                      VaeOutParams p) {
+  const int PH = 2 * p.H, PW = 2 * p.W;
+  const int64_t total = static_cast<int64_t>(p.T) * PH * PW;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % PW);
+    int64_t r = idx / PW;
+    const int Y = static_cast<int>(r % PH), t = static_cast<int>(r / PH);
+    const int q = Y & 1, rr = X & 1;
+    const __nv_bfloat16* hrow = head + ((static_cast<int64_t>(t) * (p.H + 2) + (Y >> 1) + 1) * (p.W + 2) + (X >> 1) + 1) * p.Cp;
+    const int vy = p.y0 + Y, vx = p.x0 + X, vt = p.t0 + t;
+    if (vy >= p.VH || vx >= p.VW || vt >= p.VT) continue;
+    float m = 1.f;
+    if (BLEND) m = fminf(vae_ramp(Y, PH, p.top_bound, p.bottom_bound, p.border_y), vae_ramp(X, PW, p.left_bound, p.right_bound, p.border_x));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __bfloat162float(hrow[(c * 2 + rr) * 2 + q]);
+      const int64_t o = ((static_cast<int64_t>(c) * p.VT + vt) * p.VH + vy) * p.VW + vx;
+      if (BLEND) values[o] += v * m;
+      else values[o] = fminf(fmaxf(v, -1.f), 1.f);
+    }
+    if (BLEND) weight[(static_cast<int64_t>(vt) * p.VH + vy) * p.VW + vx] += m;
+  }
+}
+
+__global__ void vae_blend_finish_kernel(float* __restrict__ values, const float* __restrict__ weight, int64_t plane, int channels) {
+  const int64_t total = plane * channels;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    values[idx] = fminf(fmaxf(values[idx] / weight[idx % plane], -1.f), 1.f);
+}
+
+}  // namespace fgb
+
+using namespace fgb;
+using bf16 = __nv_bfloat16;
+
+extern "C" int fgb_vae_latent_rows(fgb_ctx* ctx, const void* z, const void* mean_f32, const void* inv_std_f32, void* grid, int32_t channels,
+                                   int32_t frames, int32_t h, int32_t w, int32_t cp, void* stream) {
+  FGB_CHECK_ARG(ctx && z && mean_f32 && inv_std_f32 && grid, "fgb_vae_latent_rows: NULL argument");
+  FGB_CHECK_ARG(channels > 0 && frames > 0 && h > 0 && w > 0 && cp >= channels && cp % 8 == 0, "fgb_vae_latent_rows: C=%d T=%d H=%d W=%d Cp=%d",
+                channels, frames, h, w, cp);
+  const int64_t total = static_cast<int64_t>(frames) * h * w * channels;
+  vae_latent_rows_kernel<<<vae_grid(total, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(z), static_cast<const float*>(mean_f32), static_cast<const float*>(inv_std_f32), static_cast<bf16*>(grid),
+      channels, frames, h, w, cp);
+  FGB_LAUNCH_CHECK("vae_latent_rows_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_norm_silu(fgb_ctx* ctx, const void* x, void* out, int64_t rows, int32_t channels, int32_t cp, const void* gamma,
+                                 int32_t silu, void* stream) {
+  FGB_CHECK_ARG(ctx && x && out && gamma, "fgb_vae_norm_silu: NULL argument");
+  FGB_CHECK_ARG(rows > 0 && channels > 0 && cp >= channels && cp % 8 == 0 && aligned16(x) && aligned16(out) && aligned16(gamma),
+                "fgb_vae_norm_silu: rows=%lld C=%d Cp=%d (Cp %% 8, 16-byte alignment)", (long long)rows, channels, cp);
+  vae_norm_silu_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(out), rows, cp, sqrtf(static_cast<float>(channels)), static_cast<const bf16*>(gamma), silu);
+  FGB_LAUNCH_CHECK("vae_norm_silu_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_upsample2x(fgb_ctx* ctx, const void* src, void* dst, int32_t cp, int32_t frames_dst, int32_t h, int32_t w,
+                                  int32_t halves, void* stream) {
+  FGB_CHECK_ARG(ctx && src && dst, "fgb_vae_upsample2x: NULL argument");
+  FGB_CHECK_ARG(cp > 0 && cp % 8 == 0 && frames_dst > 0 && h > 0 && w > 0 && (halves == 1 || halves == 2) && frames_dst % halves == 0 &&
+                    aligned16(src) && aligned16(dst), "fgb_vae_upsample2x: Cp=%d T=%d H=%d W=%d halves=%d", cp, frames_dst, h, w, halves);
+  const int64_t total = static_cast<int64_t>(frames_dst) * 4 * h * w * (cp / 8);
+  vae_upsample2x_kernel<<<vae_grid(total, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(src), static_cast<bf16*>(dst), cp, frames_dst, h, w, halves);
+  FGB_LAUNCH_CHECK("vae_upsample2x_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_dup_up_add(fgb_ctx* ctx, const void* x, void* main, int32_t cin, int32_t cin_p, int32_t cout, int32_t cout_p,
+                                  int32_t factor_t, int32_t first_chunk, int32_t frames_out, int32_t h, int32_t w, void* stream) {
+  FGB_CHECK_ARG(ctx && x && main, "fgb_vae_dup_up_add: NULL argument");
+  FGB_CHECK_ARG(cin > 0 && cout > 0 && cin_p >= cin && cout_p >= cout && (factor_t == 1 || factor_t == 2) && frames_out > 0 && h > 0 && w > 0 &&
+                    (cout * factor_t * 4) % cin == 0, "fgb_vae_dup_up_add: Cin=%d Cout=%d factor_t=%d", cin, cout, factor_t);
+  const int64_t total = static_cast<int64_t>(frames_out) * 4 * h * w * cout;
+  vae_dup_up_add_kernel<<<vae_grid(total, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(main), cin_p, cout, cout_p, cout * factor_t * 4 / cin, factor_t,
+      first_chunk ? factor_t - 1 : 0, frames_out, h, w);
+  FGB_LAUNCH_CHECK("vae_dup_up_add_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_attn_softmax(fgb_ctx* ctx, void* scores, int64_t ld, int32_t rows, int32_t n_cols, int32_t grid_h, int32_t grid_w,
+                                    float scale, void* stream) {
+  FGB_CHECK_ARG(ctx && scores && rows > 0 && n_cols > 0 && ld >= n_cols && grid_h >= 3 && grid_w >= 3, "fgb_vae_attn_softmax: bad argument");
+  vae_attn_softmax_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16*>(scores), ld, rows, n_cols, grid_h,
+                                                                                        grid_w, scale);
+  FGB_LAUNCH_CHECK("vae_attn_softmax_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_unpatchify(fgb_ctx* ctx, const void* head, int32_t frames, int32_t h, int32_t w, int32_t cp, void* values_f32,
+                                  void* weight_f32, int32_t t0, int32_t y0, int32_t x0, int32_t video_frames, int32_t video_h,
+                                  int32_t video_w, int32_t bounds_tblr, int32_t border_y, int32_t border_x, void* stream) {
+  FGB_CHECK_ARG(ctx && head && values_f32, "fgb_vae_unpatchify: NULL argument");
+  FGB_CHECK_ARG(frames > 0 && h > 0 && w > 0 && cp >= 12 && t0 >= 0 && y0 >= 0 && x0 >= 0 && video_frames > 0 && video_h > 0 && video_w > 0,
+                "fgb_vae_unpatchify: bad geometry");
+  FGB_CHECK_ARG(!weight_f32 || (border_y > 0 && border_x > 0), "fgb_vae_unpatchify: blending needs positive border widths");
+  VaeOutParams p{frames, h, w, cp, t0, y0, x0, video_frames, video_h, video_w, (bounds_tblr >> 3) & 1, (bounds_tblr >> 2) & 1,
+                 (bounds_tblr >> 1) & 1, bounds_tblr & 1, border_y, border_x};
+  const int64_t total = static_cast<int64_t>(frames) * 4 * h * w;
+  const int grid = vae_grid(total, 256, ctx->sm_count * 16);
+  if (weight_f32)
+    vae_unpatchify_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(head), static_cast<float*>(values_f32),
+                                                                                     static_cast<float*>(weight_f32), p);
+  else
+    vae_unpatchify_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(head),
+                                                                                      static_cast<float*>(values_f32), nullptr, p);
+  FGB_LAUNCH_CHECK("vae_unpatchify_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_blend_finish(fgb_ctx* ctx, void* values_f32, const void* weight_f32, int64_t plane, int32_t channels, void* stream) {
+  FGB_CHECK_ARG(ctx && values_f32 && weight_f32 && plane > 0 && channels > 0, "fgb_vae_blend_finish: bad argument");
+  vae_blend_finish_kernel<<<vae_grid(plane * channels, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<float*>(values_f32), static_cast<const float*>(weight_f32), plane, channels);
+  FGB_LAUNCH_CHECK("vae_blend_finish_kernel");
+  return FGB_OK;
+}

@@ -609,3 +609,86 @@ def t5_attention(q, k, v, out, batch: int, heads: int, bias=None, key_mask=None)
                                            _p(out), _rowmajor(out, "out"), batch, s_q, s_kv, heads, _p(bias), _p(key_mask), _stream()),
                "fgb_t5_attention")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VAE38 decoder (fgb_conv_taps_bf16, fgb_vae_*): feature maps are 2-D row views [T*(H+2)*(W+2), Cp] of zero-bordered grids
+# ---------------------------------------------------------------------------------------------------------------
+def conv_taps(x, a_row0: int, w, bias, out, tap_offsets, grid_hw=(0, 0), epilogue=EPI_BIAS):
+    """out[r] = epilogue(sum_tap x[a_row0 + r + tap_offsets[tap]] @ w[:, tap*cin:(tap+1)*cin].T + bias) for r < out.shape[0]."""
+    import ctypes
+
+    ldx, ldw, ldo = _rowmajor(x, "x"), _rowmajor(w, "w"), _rowmajor(out, "out")
+    cin, taps = x.shape[1], len(tap_offsets)
+    m, n = out.shape
+    if w.shape[0] != n or w.shape[1] != taps * cin:
+        raise ValueError(f"conv_taps shape mismatch: x {tuple(x.shape)} w {tuple(w.shape)} out {tuple(out.shape)} taps {taps}")
+    _vec(bias, n, "bias")
+    offs = (ctypes.c_int32 * taps)(*[int(v) for v in tap_offsets])
+    _lib.check(_lib.lib().fgb_conv_taps_bf16(_h(x).handle, _p(x), ldx, x.shape[0], a_row0, _p(w), ldw, _p(bias), _p(out), ldo, m, n, cin, taps,
+                                             offs, grid_hw[0], grid_hw[1], epilogue, _stream()), "fgb_conv_taps_bf16")
+    return out
+
+
+def vae_latent_rows(z, mean, inv_std, grid, cp: int):
+    """z bf16 [C, T, H, W] -> interior of grid (rows view of [T, H+2, W+2, cp]) = z / inv_std + mean."""
+    C, T, H, W = z.shape
+    if z.dtype != BF16 or not z.is_contiguous() or grid.shape[0] != T * (H + 2) * (W + 2) or grid.shape[1] != cp or not grid.is_contiguous():
+        raise ValueError("vae_latent_rows: z contiguous bf16 [C, T, H, W], grid contiguous rows [T*(H+2)*(W+2), cp]")
+    if any(t.dtype != torch.float32 or t.numel() != C or not t.is_contiguous() for t in (mean, inv_std)):
+        raise ValueError("vae_latent_rows: mean / inv_std must be contiguous fp32 [C]")
+    _lib.check(_lib.lib().fgb_vae_latent_rows(_h(z).handle, _p(z), _p(mean), _p(inv_std), _p(grid), C, T, H, W, cp, _stream()),
+               "fgb_vae_latent_rows")
+
+
+def vae_norm_silu(x, out, channels: int, gamma, silu: bool = True):
+    rows, cp = x.shape
+    if not x.is_contiguous() or not out.is_contiguous() or tuple(out.shape) != (rows, cp) or x.dtype != BF16 or out.dtype != BF16:
+        raise ValueError("vae_norm_silu: x and out must be contiguous bf16 row matrices of one shape")
+    _vec(gamma, cp, "gamma")
+    _lib.check(_lib.lib().fgb_vae_norm_silu(_h(x).handle, _p(x), _p(out), rows, channels, cp, _p(gamma), 1 if silu else 0, _stream()),
+               "fgb_vae_norm_silu")
+
+
+def vae_upsample2x(src, dst, cp: int, frames_dst: int, h: int, w: int, halves: int = 1):
+    if src.dtype != BF16 or dst.dtype != BF16 or not src.is_contiguous() or not dst.is_contiguous():
+        raise ValueError("vae_upsample2x: contiguous bf16 grids")
+    if src.numel() < (frames_dst // halves) * (h + 2) * (w + 2) * halves * cp or dst.numel() < frames_dst * (2 * h + 2) * (2 * w + 2) * cp:
+        raise ValueError("vae_upsample2x: grid too small")
+    _lib.check(_lib.lib().fgb_vae_upsample2x(_h(src).handle, _p(src), _p(dst), cp, frames_dst, h, w, halves, _stream()), "fgb_vae_upsample2x")
+
+
+def vae_dup_up_add(x, main, cin: int, cout: int, factor_t: int, first_chunk: bool, frames_out: int, h: int, w: int):
+    if x.dtype != BF16 or main.dtype != BF16 or not x.is_contiguous() or not main.is_contiguous():
+        raise ValueError("vae_dup_up_add: contiguous bf16 grids")
+    frames_in = (frames_out + (factor_t - 1 if first_chunk else 0)) // factor_t
+    if x.shape[0] < frames_in * (h + 2) * (w + 2) or main.shape[0] < frames_out * (2 * h + 2) * (2 * w + 2):
+        raise ValueError("vae_dup_up_add: grid too small")
+    _lib.check(_lib.lib().fgb_vae_dup_up_add(_h(x).handle, _p(x), _p(main), cin, x.shape[1], cout, main.shape[1], factor_t,
+                                             1 if first_chunk else 0, frames_out, h, w, _stream()), "fgb_vae_dup_up_add")
+
+
+def vae_attn_softmax(scores, n_cols: int, grid_h: int, grid_w: int, scale: float):
+    ld = _rowmajor(scores, "scores")
+    _lib.check(_lib.lib().fgb_vae_attn_softmax(_h(scores).handle, _p(scores), ld, scores.shape[0], n_cols, grid_h, grid_w, scale, _stream()),
+               "fgb_vae_attn_softmax")
+
+
+def vae_unpatchify(head, frames: int, h: int, w: int, values, weight, t0: int, y0: int, x0: int, bounds=(True, True, True, True),
+                   border=(1, 1)):
+    """head rows [frames*(h+2)*(w+2), cp] -> values fp32 [3, VT, VH, VW] (+ weight fp32 [VT, VH, VW] when blending tiles)."""
+    if head.dtype != BF16 or not head.is_contiguous() or head.shape[0] < frames * (h + 2) * (w + 2):
+        raise ValueError("vae_unpatchify: head must be the contiguous bf16 rows of the head grid")
+    if values.dtype != torch.float32 or values.dim() != 4 or values.shape[0] != 3 or not values.is_contiguous():
+        raise ValueError("vae_unpatchify: values must be contiguous fp32 [3, T, H, W]")
+    if weight is not None and (weight.dtype != torch.float32 or tuple(weight.shape) != tuple(values.shape[1:]) or not weight.is_contiguous()):
+        raise ValueError("vae_unpatchify: weight must be contiguous fp32 [T, H, W]")
+    b = (int(bounds[0]) << 3) | (int(bounds[1]) << 2) | (int(bounds[2]) << 1) | int(bounds[3])
+    _lib.check(_lib.lib().fgb_vae_unpatchify(_h(head).handle, _p(head), frames, h, w, head.shape[1], _p(values), _p(weight), t0, y0, x0,
+                                             values.shape[1], values.shape[2], values.shape[3], b, border[0], border[1], _stream()),
+               "fgb_vae_unpatchify")
+
+
+def vae_blend_finish(values, weight):
+    _lib.check(_lib.lib().fgb_vae_blend_finish(_h(values).handle, _p(values), _p(weight), weight.numel(), values.shape[0], _stream()),
+               "fgb_vae_blend_finish")

@@ -323,6 +323,56 @@ int fgb_t5_attention(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, in
                      int64_t ldo, int32_t batch, int32_t s_q, int32_t s_kv, int32_t heads, const void* bias, const void* key_mask,
                      void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Wan2.2 VAE38 decoder: animation/diffsynth/models/wan_video_vae.py ("VAE"), called at
+ * pipelines/wan_video.py:322-323. Feature maps are channels-last zero-bordered grids G[t][H+2][W+2][Cp] (Cp = channels rounded
+ * up to 64, padding channels zero), flattened to rows.
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* Convolution as a GEMM over shifted rows: out[r, :] = epilogue(sum_tap x[a_row0 + r + tap_offsets[tap], :] · w[:, tap*cin:(tap+1)*cin]ᵀ
+ * + bias), r in [0, m). x: [x_rows, cin] rows (rows outside [0, x_rows) read as zero), w: [n, taps*cin], cin % 64 == 0.
+ * grid_h, grid_w > 0: output rows are positions of [.., grid_h, grid_w] grids and the 1-wide border positions are written as
+ * zero (the zero padding of the next convolution). epilogue: FGB_EPI_BIAS or FGB_EPI_RESIDUAL (out += ...).
+ * Replaces CausalConv3d / nn.Conv2d / 1x1 convs of the decoder (VAE:33-52, 98-105, 274-281, 315-316): a causal 3x3x3 conv has 27
+ * taps with offsets (dt*grid_h + dy)*grid_w + dx, dt in {-2,-1,0}, the cached frames (VAE:288-301) stored in front of x. */
+int fgb_conv_taps_bf16(fgb_ctx* ctx, const void* x, int64_t ldx, int64_t x_rows, int64_t a_row0, const void* w, int64_t ldw,
+                       const void* bias, void* out, int64_t ldo, int32_t m, int32_t n, int32_t cin, int32_t taps,
+                       const int32_t* tap_offsets, int32_t grid_h, int32_t grid_w, int32_t epilogue, void* stream);
+
+/* grid interior <- z[c, t, y, x] / inv_std[c] + mean[c]  (latents bf16 [C, T, H, W]; VideoVAE38_.decode, VAE:1328-1331). */
+int fgb_vae_latent_rows(fgb_ctx* ctx, const void* z, const void* mean_f32, const void* inv_std_f32, void* grid, int32_t channels,
+                        int32_t frames, int32_t h, int32_t w, int32_t cp, void* stream);
+
+/* out = silu?(x / max(|x|_2, 1e-12) * sqrt(channels) * gamma) per row: RMS_norm (VAE:67-70) + nn.SiLU (VAE:274-277, 886). */
+int fgb_vae_norm_silu(fgb_ctx* ctx, const void* x, void* out, int64_t rows, int32_t channels, int32_t cp, const void* gamma,
+                      int32_t silu, void* stream);
+
+/* nearest-exact x2 in h, w into the interior of a grid of twice the size (Upsample, VAE:73-79). halves = 2: src rows hold
+ * 2*cp channels and frame t' of dst is channel half t' % 2 of src frame t' / 2 (temporal up-sampling, VAE:147-156). */
+int fgb_vae_upsample2x(fgb_ctx* ctx, const void* src, void* dst, int32_t cp, int32_t frames_dst, int32_t h, int32_t w, int32_t halves,
+                       void* stream);
+
+/* main += DupUp3D(x): the parameter-free shortcut of Up_ResidualBlock (VAE:417-439, 506-514). x grid [T, h, w, cin_p], main grid
+ * [frames_out, 2h, 2w, cout_p]; first_chunk drops the first factor_t - 1 frames. */
+int fgb_vae_dup_up_add(fgb_ctx* ctx, const void* x, void* main, int32_t cin, int32_t cin_p, int32_t cout, int32_t cout_p,
+                       int32_t factor_t, int32_t first_chunk, int32_t frames_out, int32_t h, int32_t w, void* stream);
+
+/* In place on bf16 scores [rows, ld]: softmax(scale * s) over the interior positions of one [grid_h, grid_w] frame (columns that
+ * are border positions or >= grid_h*grid_w get probability 0).  AttentionBlock.forward, VAE:331-337. */
+int fgb_vae_attn_softmax(fgb_ctx* ctx, void* scores, int64_t ld, int32_t rows, int32_t n_cols, int32_t grid_h, int32_t grid_w, float scale,
+                         void* stream);
+
+/* Un-patchify (VAE:214-224) of the head grid [frames, h, w, cp] (12 channels used) into the fp32 video [3, video_frames, video_h,
+ * video_w] at (t0, y0, x0). weight_f32 == NULL: values = clamp(v, -1, 1) (single_decode, VAE:1212-1215). Otherwise the blending
+ * of tiled_decode (VAE:1081-1100, 1128-1150): values += v * mask, weight += mask; bounds_tblr bit 3/2/1/0 = the tile touches the
+ * top / bottom / left / right edge of the video (no ramp there); border_y / border_x = ramp widths in pixels. */
+int fgb_vae_unpatchify(fgb_ctx* ctx, const void* head, int32_t frames, int32_t h, int32_t w, int32_t cp, void* values_f32,
+                       void* weight_f32, int32_t t0, int32_t y0, int32_t x0, int32_t video_frames, int32_t video_h, int32_t video_w,
+                       int32_t bounds_tblr, int32_t border_y, int32_t border_x, void* stream);
+
+/* values = clamp(values / weight, -1, 1) (VAE:1151-1152); weight has one plane, values `channels` planes. */
+int fgb_vae_blend_finish(fgb_ctx* ctx, void* values_f32, const void* weight_f32, int64_t plane, int32_t channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -211,24 +211,32 @@ def dup_up3d(x, out_channels: int, factor_t: int, factor_s: int, first_chunk: bo
     return x[:, :, factor_t - 1:] if first_chunk else x
 
 
-def decoder_chunk(w: Weights, cfg: VAE38Config, x, cache: List, first_chunk: bool):
-    """Decoder3d_38.forward on one latent frame, VAE:889-940."""
+def decoder_chunk(w: Weights, cfg: VAE38Config, x, cache: List, first_chunk: bool, trace=None):
+    """Decoder3d_38.forward on one latent frame, VAE:889-940.  trace(name, tensor): intermediate results for the tests."""
+    tr = trace if trace is not None else (lambda name, t: None)
     idx = [0]
     tail = _cache_tail(x, cache[0])
     x = causal_conv3d(x, w["decoder.conv1.weight"], w["decoder.conv1.bias"], cache[0])
     cache[0] = tail
     idx[0] = 1
+    tr("conv1", x)
     x = residual_block(w, "decoder.middle.0.", x, cache, idx)
+    tr("mid0", x)
     x = attention_block(w, "decoder.middle.1.", x)
+    tr("attn", x)
     x = residual_block(w, "decoder.middle.2.", x, cache, idx)
+    tr("mid2", x)
     for i, (cin, cout, n, up, t_up) in enumerate(stage_plan(cfg)):                    # Up_ResidualBlock.forward, VAE:506-514
         p = f"decoder.upsamples.{i}.upsamples."
         main = x
         for j in range(n):
             main = residual_block(w, f"{p}{j}.", main, cache, idx)
+            tr(f"s{i}.b{j}", main)
         if up:
             main = resample_up(w, f"{p}{n}.", main, t_up, cache, idx)
+            tr(f"s{i}.resample", main)
             x = main + dup_up3d(x, cout, 2 if t_up else 1, 2, first_chunk)
+            tr(f"s{i}.out", x)
         else:
             x = main
     x = F.silu(rms_norm(x, w["decoder.head.0.gamma"]))
@@ -236,6 +244,7 @@ def decoder_chunk(w: Weights, cfg: VAE38Config, x, cache: List, first_chunk: boo
     tail = _cache_tail(x, cache[i])
     x = causal_conv3d(x, w["decoder.head.2.weight"], w["decoder.head.2.bias"], cache[i])
     cache[i] = tail
+    tr("head", x)
     return x
 
 
@@ -252,14 +261,14 @@ def unpatchify(x, patch: int = 2):
     return x.permute(0, 1, 4, 5, 3, 6, 2).reshape(b, c, f, hh * patch, ww * patch)
 
 
-def model_decode(w: Weights, cfg: VAE38Config, z: torch.Tensor) -> torch.Tensor:
+def model_decode(w: Weights, cfg: VAE38Config, z: torch.Tensor, trace=None) -> torch.Tensor:
     """VideoVAE38_.decode, VAE:1326-1351: z [1, z_dim, T, h, w] -> [1, 3, 4T-3, 16h, 16w] (not clamped)."""
     mean, inv_std = latent_scale(cfg)
     mean, inv_std = mean.to(z), inv_std.to(z)
     z = z / inv_std.view(1, -1, 1, 1, 1) + mean.view(1, -1, 1, 1, 1)
     x = causal_conv3d(z, w["conv2.weight"], w["conv2.bias"])
     cache: List = [None] * count_cache_slots(cfg)
-    outs = [decoder_chunk(w, cfg, x[:, :, i:i + 1], cache, first_chunk=(i == 0)) for i in range(z.shape[2])]
+    outs = [decoder_chunk(w, cfg, x[:, :, i:i + 1], cache, first_chunk=(i == 0), trace=trace) for i in range(z.shape[2])]
     return unpatchify(torch.cat(outs, dim=2))
 
 
