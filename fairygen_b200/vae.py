@@ -51,6 +51,37 @@ class VAE38Config:
 VAE38 = VAE38Config()
 
 
+def param_shapes(cfg: VAE38Config) -> Dict[str, tuple]:
+    """State-dict keys / shapes of ``VideoVAE38_`` that decode reads: ``conv2`` and ``decoder`` (VAE:1294-1296, 842-887)."""
+    def res(p, cin, cout):
+        s = {p + "residual.0.gamma": (cin, 1, 1, 1), p + "residual.2.weight": (cout, cin, 3, 3, 3), p + "residual.2.bias": (cout,),
+             p + "residual.3.gamma": (cout, 1, 1, 1), p + "residual.6.weight": (cout, cout, 3, 3, 3), p + "residual.6.bias": (cout,)}
+        if cin != cout:
+            s.update({p + "shortcut.weight": (cout, cin, 1, 1, 1), p + "shortcut.bias": (cout,)})
+        return s
+
+    dims, z = cfg.dims, cfg.z_dim
+    d0 = dims[0]
+    out = {"conv2.weight": (z, z, 1, 1, 1), "conv2.bias": (z,), "decoder.conv1.weight": (d0, z, 3, 3, 3), "decoder.conv1.bias": (d0,)}
+    out.update(res("decoder.middle.0.", d0, d0))
+    out.update({"decoder.middle.1.norm.gamma": (d0, 1, 1), "decoder.middle.1.to_qkv.weight": (3 * d0, d0, 1, 1),
+                "decoder.middle.1.to_qkv.bias": (3 * d0,), "decoder.middle.1.proj.weight": (d0, d0, 1, 1), "decoder.middle.1.proj.bias": (d0,)})
+    out.update(res("decoder.middle.2.", d0, d0))
+    n = cfg.num_res_blocks + 1
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        p = f"decoder.upsamples.{i}.upsamples."
+        c = cin
+        for j in range(n):
+            out.update(res(f"{p}{j}.", c, cout))
+            c = cout
+        if i != len(cfg.dim_mult) - 1:
+            out.update({f"{p}{n}.resample.1.weight": (cout, cout, 3, 3), f"{p}{n}.resample.1.bias": (cout,)})
+            if i < len(cfg.temperal_upsample) and cfg.temperal_upsample[i]:
+                out.update({f"{p}{n}.time_conv.weight": (2 * cout, cout, 3, 1, 1), f"{p}{n}.time_conv.bias": (2 * cout,)})
+    out.update({"decoder.head.0.gamma": (dims[-1], 1, 1, 1), "decoder.head.2.weight": (12, dims[-1], 3, 3, 3), "decoder.head.2.bias": (12,)})
+    return out
+
+
 def _c64(c: int) -> int:
     return -(-c // 64) * 64
 
@@ -133,10 +164,13 @@ class VAE38Decoder:
         if any(k.startswith("model.") for k in sd):
             sd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
         dev = self.device
-
-        def need(k):
+        for k, shape in param_shapes(self.cfg).items():
             if k not in sd:
                 raise KeyError(f"VAE38 state dict has no '{k}'")
+            if tuple(sd[k].shape) != shape:
+                raise ValueError(f"{k}: shape {tuple(sd[k].shape)} != {shape} of the configuration")
+
+        def need(k):
             return sd[k]
 
         def conv(p, parts=1):

@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""VAE38 decode at the headline size: 31 latent frames of 44 x 80 (704x1280x121 video), tiled with the
+pipeline's defaults (tile 30 x 52, stride 15 x 26: 6 windows), random-init weights of the full-width decoder.  One JSON line:
+seconds per video with the latents resident, through the public call with host latents and the video read back (`e2e`),
+convolution FLOPs actually issued (grid borders and channel padding included) and the rate they ran at."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=31, help="latent frames (31 = 121 video frames)")
+    ap.add_argument("--height", type=int, default=44)
+    ap.add_argument("--width", type=int, default=80)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--torch-chain", action="store_true",
+                    help="also time the reference's own bf16 op chain (torch / cuDNN kernels, the oracle functions run in bf16) on the "
+                         "same windows on this GPU — the baseline leg; blending and the reference's per-tile CPU round trip excluded")
+    args = ap.parse_args()
+    from fairygen_b200 import ops, vae
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    cfg = vae.VAE38
+    g = torch.Generator(device=dev).manual_seed(0)
+    sd = {}
+    for name, shape in vae.param_shapes(cfg).items():
+        if name.endswith("gamma"):
+            t = 1 + 0.1 * torch.randn(shape, generator=g, device=dev)
+        elif name.endswith("bias"):
+            t = 0.05 * torch.randn(shape, generator=g, device=dev)
+        else:
+            fan = 1
+            for v in shape[1:]:
+                fan *= v
+            t = torch.randn(shape, generator=g, device=dev) * fan ** -0.5
+        sd[name] = t
+    dec = vae.VAE38Decoder(cfg, dev)
+    dec.load_state_dict(sd)
+    chain_w = {k: v.to(torch.bfloat16) for k, v in sd.items()} if args.torch_chain else None
+    del sd
+    z_host = torch.randn(1, 48, args.frames, args.height, args.width, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).pin_memory()
+    z_dev = z_host.to(dev)
+    tile, stride = (30, 52), (15, 26)
+    flops = [0]
+    orig = ops.conv_taps
+
+    def counted(x, a_row0, w, bias, out, taps, grid_hw=(0, 0), epilogue=0):
+        flops[0] += 2 * out.shape[0] * w.shape[0] * w.shape[1]
+        return orig(x, a_row0, w, bias, out, taps, grid_hw, epilogue)
+
+    ops.conv_taps = counted
+
+    def run(z):
+        return dec.decode(z, tiled=True, tile_size=tile, tile_stride=stride)
+
+    for _ in range(args.warmup):
+        run(z_dev)
+    torch.cuda.synchronize()
+    flops[0] = 0
+    dec.kernel_launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = run(z_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    conv_flops = flops[0] / args.steps
+    launches = dec.kernel_launches // args.steps
+    host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    e0.record()
+    for _ in range(args.steps):
+        host_out.copy_(run(z_host), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    chain = None
+    if args.torch_chain:
+        from oracle import vae38_oracle as o    # baseline leg only: the reference's op chain, timed, never part of the product path
+        wins = vae.tile_tasks(args.height, args.width, tile, stride)
+        with torch.no_grad():
+            o.model_decode(chain_w, o.VAE38, z_dev[:, :, :2, :8, :8])       # warm cuDNN up
+            torch.cuda.synchronize()
+            e0.record()
+            for h0, h1, w0, w1 in wins:
+                o.model_decode(chain_w, o.VAE38, z_dev[:, :, :, h0:h1, w0:w1])
+            e1.record()
+            torch.cuda.synchronize()
+        chain = {"ms_per_video": e0.elapsed_time(e1), "what": "reference op chain in bf16 via torch / cuDNN on the same 6 windows, same GPU; "
+                 "no blending, no per-tile CPU round trip"}
+    print(json.dumps({
+        "metric": "vae38_decode_videos_per_s", "value": 1e3 / ms, "unit": "videos/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"Wan2.2 VAE38 tiled decode, latents 48x{args.frames}x{args.height}x{args.width} -> "
+                               f"{4 * args.frames - 3} frames of {16 * args.height}x{16 * args.width}, tile {tile} stride {stride}, "
+                               "full-width decoder (1024/512/256 channels), random-init weights"},
+        "e2e": {"value": 1e3 / ms_e2e, "unit": "videos/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": z_host.numel() * 2,
+                "d2h_bytes_per_step": host_out.numel() * host_out.element_size()},
+        "gpu_launches": launches, "conv_flops_issued": conv_flops, "conv_tflops": conv_flops / (ms * 1e-3) / 1e12,
+        "torch_bf16_chain": chain,
+        "output_finite": bool(torch.isfinite(out.float()).all()), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+    }))
+
+
+if __name__ == "__main__":
+    main()
