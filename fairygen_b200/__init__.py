@@ -4,7 +4,7 @@ Wan2.2-TI2V-5B DiT denoising step behind the reference's ``pipe.model_fn`` surfa
 Only what the path needs lives here: ``csrc/`` (CUDA kernels + C ABI), the ctypes binding, the
 engine that mirrors ``model_fn_wan_video``, the fused flow-match scheduler, the denoise loop, the
 Ulysses / CFG / shot parallel layout (NVLink peer-store exchange), the stage-1/2 LoRA trainer
-(hand-written backward), LoRA checkpoint formats, checkpoint detection / loading and the umT5 text encoder.  There is no CPU
+(hand-written backward), LoRA checkpoint formats, checkpoint detection / loading the umT5 text encoder and the VAE38 decoder.  There is no CPU
 or PyTorch fallback.
 """
 from .config import TI2V_5B, WanDiTConfig, counted_flops  # noqa: F401
@@ -31,7 +31,10 @@ def __getattr__(name):  # lazy: importing the package must not require CUDA or t
     if name in ("UMT5Encoder", "UMT5Config", "UMT5_XXL"):
         from . import text_encoder
         return getattr(text_encoder, name)
-    if name in ("lora_io", "cfg_parallel", "training", "text_encoder"):
+    if name in ("VAE38Decoder", "VAE38Config", "VAE38"):
+        from . import vae
+        return getattr(vae, name)
+    if name in ("lora_io", "cfg_parallel", "training", "text_encoder", "vae"):
         import importlib
         return importlib.import_module("." + name, __name__)
     if name == "SequenceParallel":

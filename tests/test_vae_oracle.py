@@ -72,3 +72,13 @@ def test_primitives(weights):
             got = o.residual_block(weights, "decoder.upsamples.2.upsamples.0.", latents((1, cfg.dims[2], 1 if i < 2 else 2, 3, 3), 20 + i),
                                    cache, [0])
             close(got, GOLD[f"resblock_c{i}"])
+
+
+def test_host_mirror_agrees_with_the_oracle_on_keys_shapes_and_tiling():
+    """fairygen_b200.vae (product, CUDA only) and the oracle list the same state-dict keys / shapes and the same tile windows."""
+    from fairygen_b200 import vae
+    assert vae.param_shapes(vae.VAE38) == o.param_shapes(o.VAE38)
+    assert vae.param_shapes(vae.VAE38Config(z_dim=8, dec_dim=16)) == o.param_shapes(o.TINY)
+    for args in [(44, 80, (30, 52), (15, 26)), (5, 5, (3, 3), (2, 2)), (4, 7, (3, 4), (2, 3)), (30, 52, (34, 34), (18, 16))]:
+        assert vae.tile_tasks(*args) == o.tile_tasks(*args)
+    assert vae.MEAN38 == o.MEAN38 and vae.STD38 == o.STD38
