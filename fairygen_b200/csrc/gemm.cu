@@ -86,7 +86,9 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 // B_MN = false: W is [n, k] (nn.Linear weight, K-major B operand)            C = A · Wᵀ   (forward)
 // B_MN = true : W is [k, n] (the same nn.Linear weight read as [out=k, in=n])  C = A · W    (dgrad: dX = dY · W)
 //               B tile = 4 TMA boxes of [64 k-rows][64 n-cols], fed to the tensor core as an MN-major operand.
-template <int EPI, bool B_MN>
+// TAPS = true: convolution mode (fgb_conv_taps_bf16): per-tap row offsets in the producer, grid-border masking in the epilogue.
+// A compile-time switch so that the DiT instantiations carry none of it.
+template <int EPI, bool B_MN, bool TAPS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2, const GemmParams p) {
@@ -144,7 +146,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const CUtensorMap* ma = second ? &tmap_a2 : &tmap_a;
           const CUtensorMap* mb = second ? &tmap_b2 : &tmap_b;
           const int kc = (second ? kb - p.k_blocks : kb) * kBK;
-          if (p.tap_kblocks > 0) {
+          if constexpr (TAPS) {
             const int tap = kb / p.tap_kblocks;
             tma_load_2d(smem_a + stage * kABytes, ma, &full[stage], (kb - tap * p.tap_kblocks) * kBK,
                         m_blk * kBM + p.a_row0 + p.tap_off[tap], kEvictNormal);
@@ -209,7 +211,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row = m_blk * kBM + quarter * 32 + lane;
       const bool row_ok = row < p.m;
       bool border = false;
-      if (p.grid_w > 0) {
+      if (TAPS && p.grid_w > 0) {
         const int pos = row % (p.grid_h * p.grid_w), gy = pos / p.grid_w, gx = pos - gy * p.grid_w;
         border = gy == 0 || gy == p.grid_h - 1 || gx == 0 || gx == p.grid_w - 1;
       }
@@ -278,7 +280,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (row_ok) {
             uint4 o;
-            if (border) {
+            if (TAPS && border) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) y[i] = 0.f;
             }
@@ -307,10 +309,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int EPI, bool B_MN = false>
+template <int EPI, bool B_MN = false, bool TAPS = false>
 static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t stream, const CUtensorMap* ta2 = nullptr, const CUtensorMap* tb2 = nullptr) {
-  auto kfn = gemm_bf16_kernel<EPI, B_MN>;
+  auto kfn = gemm_bf16_kernel<EPI, B_MN, TAPS>;
   static unsigned long long configured = 0;  // per template instance and device
   if (first_use_on_device(configured)) {
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
@@ -469,6 +471,6 @@ extern "C" int fgb_conv_taps_bf16(fgb_ctx* ctx, const void* x, int64_t ldx, int6
   p.tiles = p.m_blocks * p.n_blocks;
   p.k_blocks = taps * p.tap_kblocks;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (epilogue == FGB_EPI_RESIDUAL) return launch_gemm<FGB_EPI_RESIDUAL>(ctx, ta, tb, p, s);
-  return launch_gemm<FGB_EPI_BIAS>(ctx, ta, tb, p, s);
+  if (epilogue == FGB_EPI_RESIDUAL) return launch_gemm<FGB_EPI_RESIDUAL, false, true>(ctx, ta, tb, p, s);
+  return launch_gemm<FGB_EPI_BIAS, false, true>(ctx, ta, tb, p, s);
 }

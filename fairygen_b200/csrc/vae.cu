@@ -48,20 +48,35 @@ __global__ void __launch_bounds__(128) vae_norm_silu_kernel(const __nv_bfloat16*
   const int lane = threadIdx.x & 31;
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * Cp);
   const int nvec = Cp / 8;
+  // rows of up to 1024 channels (every decoder width) are held in registers between the two passes: 4 x 16 bytes per lane
+  uint4 held[4];
+  const bool fits = nvec <= 128;
   float ss = 0.f;
-  for (int i = lane; i < nvec; i += 32) {
-    float f[8];
-    unpack8(xr[i], f);
+  if (fits) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+    for (int k = 0; k < 4; ++k) {
+      const int i = lane + 32 * k;
+      held[k] = i < nvec ? ldg_nc_v4(xr + i) : make_uint4(0, 0, 0, 0);
+      float f[8];
+      unpack8(held[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+    }
+  } else {
+    for (int i = lane; i < nvec; i += 32) {
+      float f[8];
+      unpack8(xr[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+    }
   }
   ss = warp_sum(ss);
   const float inv = sqrt_c / fmaxf(sqrtf(ss), 1e-12f);
   uint4* orow = reinterpret_cast<uint4*>(out + row * Cp);
   const uint4* gr = reinterpret_cast<const uint4*>(gamma);
-  for (int i = lane; i < nvec; i += 32) {
+  auto finish = [&](int i, const uint4& xv) {
     float f[8], g[8];
-    unpack8(xr[i], f);
+    unpack8(xv, f);
     unpack8(ldg_nc_v4(gr + i), g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -70,6 +85,13 @@ __global__ void __launch_bounds__(128) vae_norm_silu_kernel(const __nv_bfloat16*
       f[j] = y;
     }
     orow[i] = pack8(f);
+  };
+  if (fits) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane + 32 * k < nvec) finish(lane + 32 * k, held[k]);
+  } else {
+    for (int i = lane; i < nvec; i += 32) finish(i, xr[i]);
   }
 }
 
@@ -103,20 +125,28 @@ __global__ void vae_upsample2x_kernel(const __nv_bfloat16* __restrict__ src, __n
 // ---------------------------------------------------------------------------------------------
 __global__ void vae_dup_up_add_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ main, int Cin_p, int Cout, int Cout_p,
                                       int repeats, int ft, int skip, int T_out, int H, int W) {
-  const int64_t total = static_cast<int64_t>(T_out) * (2 * H) * (2 * W) * Cout;
+  // one thread = 8 consecutive output channels of one position: one 16-byte read-modify-write of `main`, 8 gathered x values
+  const int groups = (Cout + 7) / 8;
+  const int64_t total = static_cast<int64_t>(T_out) * (2 * H) * (2 * W) * groups;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(idx % Cout);
-    int64_t r = idx / Cout;
+    const int c0 = static_cast<int>(idx % groups) * 8;
+    int64_t r = idx / groups;
     const int xo = static_cast<int>(r % (2 * W));
     r /= 2 * W;
     const int yo = static_cast<int>(r % (2 * H)), to = static_cast<int>(r / (2 * H));
     const int tt = to + skip, a = tt % ft, t = tt / ft;
-    const int j = ((c * ft + a) * 2 + (yo & 1)) * 2 + (xo & 1);
+    const int sub = (a * 2 + (yo & 1)) * 2 + (xo & 1);          // j = c * (4 ft) + sub
     const int64_t srow = (static_cast<int64_t>(t) * (H + 2) + (yo >> 1) + 1) * (W + 2) + (xo >> 1) + 1;
     const int64_t drow = (static_cast<int64_t>(to) * (2 * H + 2) + yo + 1) * (2 * W + 2) + xo + 1;
-    __nv_bfloat16* d = main + drow * Cout_p + c;
-    *d = __float2bfloat16_rn(__bfloat162float(*d) + __bfloat162float(x[srow * Cin_p + j / repeats]));
+    const __nv_bfloat16* xs = x + srow * Cin_p;
+    uint4* d = reinterpret_cast<uint4*>(main + drow * Cout_p + c0);
+    float f[8];
+    unpack8(*d, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c0 + i < Cout) f[i] = round_bf16(f[i] + __bfloat162float(xs[((c0 + i) * 4 * ft + sub) / repeats]));
+    *d = pack8(f);
   }
 }
 
@@ -249,7 +279,8 @@ extern "C" int fgb_vae_dup_up_add(fgb_ctx* ctx, const void* x, void* main, int32
   FGB_CHECK_ARG(ctx && x && main, "fgb_vae_dup_up_add: NULL argument");
   FGB_CHECK_ARG(cin > 0 && cout > 0 && cin_p >= cin && cout_p >= cout && (factor_t == 1 || factor_t == 2) && frames_out > 0 && h > 0 && w > 0 &&
                     (cout * factor_t * 4) % cin == 0, "fgb_vae_dup_up_add: Cin=%d Cout=%d factor_t=%d", cin, cout, factor_t);
-  const int64_t total = static_cast<int64_t>(frames_out) * 4 * h * w * cout;
+  FGB_CHECK_ARG(cout_p % 8 == 0 && aligned16(main), "fgb_vae_dup_up_add: main rows must be 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(frames_out) * 4 * h * w * ((cout + 7) / 8);
   vae_dup_up_add_kernel<<<vae_grid(total, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(x), static_cast<bf16*>(main), cin_p, cout, cout_p, cout * factor_t * 4 / cin, factor_t,
       first_chunk ? factor_t - 1 : 0, frames_out, h, w);

@@ -271,15 +271,18 @@ class VAE38Decoder:
     # ------------------------------------------------------------------------------------------------------------
     # blocks
     # ------------------------------------------------------------------------------------------------------------
-    def _res(self, r: _Res, x: torch.Tensor, T: int, h: int, w: int, tag: str) -> torch.Tensor:
-        """ResidualBlock.forward (VAE:283-301)."""
+    def _res(self, r: _Res, x: torch.Tensor, T: int, h: int, w: int, tag: str, keep_input: bool = True) -> torch.Tensor:
+        """ResidualBlock.forward (VAE:283-301). keep_input = False: nobody reads `x` afterwards, so an identity shortcut
+        accumulates the second convolution straight into it instead of into a copy."""
         P = (h + 2) * (w + 2)
         rows = T * P
-        out = self._empty(rows, r.c2.cout_p)
         if r.short is not None:
+            out = self._empty(rows, r.c2.cout_p)
             self._conv(r.short, T, h, w, out, EPI_BIAS, src=x)
+        elif keep_input:
+            out = x[:rows].clone()
         else:
-            out.copy_(x[:rows])
+            out = x[:rows]
         ops.vae_norm_silu(x[:rows], self._input(r.c1, T, h, w), r.cin, r.g1)
         tmp = self._empty(rows, r.c1.cout_p)
         self._conv(r.c1, T, h, w, tmp)
@@ -320,8 +323,8 @@ class VAE38Decoder:
     def _stage(self, i: int, st, x: torch.Tensor, T: int, h: int, w: int, first_chunk: bool):
         """Up_ResidualBlock.forward (VAE:506-514) with Resample38 'upsample2d' / 'upsample3d' (VAE:120-160)."""
         main = x
-        for j, r in enumerate(st["blocks"]):
-            main = self._res(r, main, T, h, w, f"s{i}.b{j}")
+        for j, r in enumerate(st["blocks"]):   # the stage input `x` feeds the DupUp3D shortcut later: block 0 must not overwrite it
+            main = self._res(r, main, T, h, w, f"s{i}.b{j}", keep_input=(j == 0 and st["up"]))
         if not st["up"]:
             return main, T, h, w
         cout, cp = st["cout"], _c64(st["cout"])
@@ -379,9 +382,9 @@ class VAE38Decoder:
             x = self._empty(P, self.conv1.cout_p)
             self._conv(self.conv1, 1, h, w, x)
             self._tr("conv1", x, 1, h, w, cfg.dims[0])
-            x = self._res(self.mid0, x, 1, h, w, "mid0")
+            x = self._res(self.mid0, x, 1, h, w, "mid0", keep_input=False)
             x = self._attention(x, 1, h, w)
-            x = self._res(self.mid2, x, 1, h, w, "mid2")
+            x = self._res(self.mid2, x, 1, h, w, "mid2", keep_input=False)
             tc, hc, wc = 1, h, w
             for si, st in enumerate(self.stages):
                 x, tc, hc, wc = self._stage(si, st, x, tc, hc, wc, first)

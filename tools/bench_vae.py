@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--width", type=int, default=80)
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--profile", action="store_true", help="print the per-kernel CUDA time of one decode (torch.profiler / CUPTI) to stderr")
     ap.add_argument("--torch-chain", action="store_true",
                     help="also time the reference's own bf16 op chain (torch / cuDNN kernels, the oracle functions run in bf16) on the "
                          "same windows on this GPU — the baseline leg; blending and the reference's per-tile CPU round trip excluded")
@@ -65,6 +66,12 @@ def main():
     for _ in range(args.warmup):
         run(z_dev)
     torch.cuda.synchronize()
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run(z_dev)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=16, max_name_column_width=60), file=sys.stderr)
     flops[0] = 0
     dec.kernel_launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
