@@ -100,6 +100,19 @@ def tile_tasks(H: int, W: int, tile_size, tile_stride):
     return tasks
 
 
+def assign_windows(tasks, H: int, W: int, world: int):
+    """Windows of one video spread over `world` ranks: largest (clipped) area first, each to the least loaded rank — the
+    windows are independent until the blend, so this is the multi-GPU split of the decode (no exchange but the final sum)."""
+    area = lambda t: (min(t[1], H) - t[0]) * (min(t[3], W) - t[2])  # noqa: E731
+    order = sorted(range(len(tasks)), key=lambda i: (-area(tasks[i]), i))
+    load, mine = [0] * world, [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        load[r] += area(tasks[i])
+        mine[r].append(tasks[i])
+    return mine
+
+
 class _Conv:
     """One convolution as a tap GEMM: weight repacked to [parts*Cout_p, taps*Cin_p] (tap-major K), bias to [parts*Cout_p]."""
 
@@ -401,11 +414,17 @@ class VAE38Decoder:
     # public: WanVideoVAE.decode (VAE:1235-1248)
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def decode(self, hidden_states, device=None, tiled: bool = False, tile_size=(34, 34), tile_stride=(18, 16)) -> torch.Tensor:
+    def decode(self, hidden_states, device=None, tiled: bool = False, tile_size=(34, 34), tile_stride=(18, 16), group=None) -> torch.Tensor:
         """latents [B, z_dim, T, h, w] (tensor or list of [z_dim, T, h, w]) -> videos [B, 3, 4T-3, 16h, 16w] in [-1, 1], on the
-        GPU in the latents' dtype.  `device` is accepted for signature compatibility (the decoder lives on its own device)."""
+        GPU in the latents' dtype.  `device` is accepted for signature compatibility (the decoder lives on its own device).
+        group (a torch.distributed process group, tiled only): every rank holds the same latents and decodes its share of the
+        windows (assign_windows); one sum all-reduce of the blended video and its weights gives every rank the full result."""
         if not self.loaded:
             raise RuntimeError("VAE38Decoder.decode called before load_state_dict")
+        world, rank = 1, 0
+        if group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
         vids = []
         f = self.upsampling_factor
         for lat in hidden_states:
@@ -421,9 +440,13 @@ class VAE38Decoder:
                     raise ValueError("tile_size must exceed tile_stride in both directions (the overlap carries the blending ramp)")
                 weight = torch.zeros(out_t, H * f, W * f, dtype=torch.float32, device=self.device)
                 border = ((tile_size[0] - tile_stride[0]) * f, (tile_size[1] - tile_stride[1]) * f)
-                for h0, h1, w0, w1 in tile_tasks(H, W, tile_size, tile_stride):
+                tasks = tile_tasks(H, W, tile_size, tile_stride)
+                for h0, h1, w0, w1 in (assign_windows(tasks, H, W, world)[rank] if world > 1 else tasks):
                     win = z[:, :, h0:h1, w0:w1].contiguous()
                     self._decode_window(win, values, weight, h0 * f, w0 * f, (h0 == 0, h1 >= H, w0 == 0, w1 >= W), border)
+                if world > 1:
+                    dist.all_reduce(values, group=group)
+                    dist.all_reduce(weight, group=group)
                 ops.vae_blend_finish(values, weight)
                 self.kernel_launches += 1
             else:

@@ -82,3 +82,15 @@ def test_host_mirror_agrees_with_the_oracle_on_keys_shapes_and_tiling():
     for args in [(44, 80, (30, 52), (15, 26)), (5, 5, (3, 3), (2, 2)), (4, 7, (3, 4), (2, 3)), (30, 52, (34, 34), (18, 16))]:
         assert vae.tile_tasks(*args) == o.tile_tasks(*args)
     assert vae.MEAN38 == o.MEAN38 and vae.STD38 == o.STD38
+
+
+def test_window_assignment_covers_every_window_once_and_balances():
+    from fairygen_b200 import vae
+    tasks = vae.tile_tasks(44, 80, (30, 52), (15, 26))                      # the 6 windows of the 704x1280 decode
+    for world in (1, 2, 4, 6, 8):
+        parts = vae.assign_windows(tasks, 44, 80, world)
+        assert len(parts) == world and sorted(t for p in parts for t in p) == sorted(tasks)
+        area = lambda t: (min(t[1], 44) - t[0]) * (min(t[3], 80) - t[2])  # noqa: E731
+        loads = [sum(area(t) for t in p) for p in parts]
+        assert max(loads) <= {1: 7788, 2: 3908, 4: 2348, 6: 1560, 8: 1560}[world]
+    assert vae.assign_windows(tasks, 44, 80, 2) == vae.assign_windows(tasks, 44, 80, 2)      # deterministic: every rank agrees
