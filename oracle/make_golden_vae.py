@@ -35,13 +35,17 @@ def latents(shape, seed):
 def main():
     cfg = o.TINY
     w = o.make_weights(cfg, seed=0)
-    model = rv.VideoVAE38_(dim=16, z_dim=cfg.z_dim, dec_dim=cfg.dec_dim).eval()
+    model = rv.VideoVAE38_(dim=cfg.enc_dim, z_dim=cfg.z_dim, dec_dim=cfg.dec_dim).eval()
     ref_sd = model.state_dict()
     dec_keys = {k: tuple(v.shape) for k, v in ref_sd.items() if k.startswith("decoder.") or k.startswith("conv2.")}
     assert dec_keys == o.param_shapes(cfg), set(dec_keys) ^ set(o.param_shapes(cfg))
     assert o.count_cache_slots(cfg) == rv.count_conv3d(model.decoder)
-    sd = dict(ref_sd)
-    sd.update(w)
+    enc_keys = {k: tuple(v.shape) for k, v in ref_sd.items() if k.startswith("encoder.") or k.startswith("conv1.")}
+    assert enc_keys == o.enc_param_shapes(cfg), set(enc_keys) ^ set(o.enc_param_shapes(cfg))
+    assert o.count_enc_cache_slots(cfg) == rv.count_conv3d(model.encoder)
+    sd = dict(w)
+    sd.update(o.make_enc_weights(cfg, seed=0))
+    assert set(sd) == set(ref_sd)                      # decoder + conv2 + encoder + conv1 = the whole module
     model.load_state_dict(sd, strict=True)
     vae = object.__new__(rv.WanVideoVAE38)          # the wrapper's methods without building the full-width default model
     torch.nn.Module.__init__(vae)
@@ -56,6 +60,17 @@ def main():
     out["tiled"] = vae.decode(zt, device="cpu", tiled=True, tile_size=(3, 3), tile_stride=(2, 2)).float().numpy()
     out["tiled_ragged"] = vae.decode(latents((1, cfg.z_dim, 1, 4, 7), 4), device="cpu", tiled=True, tile_size=(3, 4),
                                      tile_stride=(2, 3)).float().numpy()
+    # encoder (first-frame conditioning and a 9-frame clip: chunks of 1, 4, 4 frames)
+    img = torch.tanh(latents((3, 1, 32, 48), 30))
+    out["encode_image"] = vae.encode([img], device="cpu").numpy()                                   # [1, 8, 1, 2, 3]
+    clip = torch.tanh(latents((3, 9, 32, 32), 31))
+    out["encode_clip"] = vae.encode([clip], device="cpu").numpy()                                   # [1, 8, 3, 2, 2]
+    out["encode_tiled"] = vae.encode([torch.tanh(latents((3, 1, 80, 96), 32))], device="cpu", tiled=True, tile_size=(3, 4),
+                                     tile_stride=(2, 2)).numpy()                                    # [1, 8, 1, 5, 6]
+    xa = latents((1, 16, 3, 4, 6), 33)
+    out["avg_down_t2"] = rv.AvgDown3D(16, 32, factor_t=2, factor_s=2)(xa).numpy()
+    out["avg_down_t1"] = rv.AvgDown3D(16, 16, factor_t=1, factor_s=2)(xa).numpy()
+    out["patchify"] = rv.patchify(latents((1, 3, 2, 6, 10), 34), 2).numpy()
     # primitives
     x = latents((1, 32, 1, 3, 4), 5)
     up = rv.DupUp3D(32, 16, factor_t=2, factor_s=2)

@@ -1,9 +1,11 @@
-"""CPU/PyTorch ORACLE for the Wan2.2 VAE38 decoder.  TEST INFRASTRUCTURE ONLY.
+"""CPU/PyTorch ORACLE for the Wan2.2 VAE38 decoder and encoder.  TEST INFRASTRUCTURE ONLY.
 
 A functional restatement (plain torch ops over a flat ``{name: tensor}`` weight dict, explicit feature-cache list) of what
 the reference's ``WanVideoVAE38.decode`` computes: latent de-normalisation, ``conv2``, the chunk-by-chunk causal decoder
-with its two-frame feature cache, ``unpatchify``, the tiled variant with linear-ramp blending, and the final clamp.  Not
-part of the product: only ``tests/`` and bench CPU-baseline legs may import it.
+with its two-frame feature cache, ``unpatchify``, the tiled variant with linear-ramp blending, and the final clamp; and of
+``WanVideoVAE38.encode`` (patchify, chunked causal encoder with AvgDown3D shortcuts, ``conv1``, latent normalisation, tiled
+variant) — the encoder has no CUDA path yet, its oracle is the groundwork for it.  Not part of the product: only ``tests/``
+and bench CPU-baseline legs may import it.
 
 Parity status: PINNED.  ``oracle/make_golden_vae.py`` runs the real ``WanVideoVAE38`` (imported from
 ``/root/reference/animation`` in the build container) at reduced widths on seeded weights / latents and stores its outputs
@@ -41,10 +43,16 @@ class VAE38Config:                                       # VideoVAE38_.__init__ 
     num_res_blocks: int = 2
     temperal_upsample: Tuple[bool, ...] = (True, True, False)   # temperal_downsample[::-1], VAE:1288 (sic)
     out_channels: int = 12                               # 3 x 2 x 2, un-patchified to RGB at twice the size (VAE:887, 1350)
+    enc_dim: int = 160                                   # `dim` of VideoVAE38_ / WanVideoVAE38 (VAE:1272, 1356)
+    temperal_downsample: Tuple[bool, ...] = (False, True, True)   # VAE:1278
 
     @property
     def dims(self) -> List[int]:                         # VAE:859
         return [self.dec_dim * u for u in [self.dim_mult[-1]] + list(self.dim_mult[::-1])]
+
+    @property
+    def enc_dims(self) -> List[int]:                     # VAE:638
+        return [self.enc_dim * u for u in [1] + list(self.dim_mult)]
 
     @property
     def upsampling_factor(self) -> int:                  # 2^(stages with up_flag) x patch 2  (= 16, VAE:1380)
@@ -52,7 +60,7 @@ class VAE38Config:                                       # VideoVAE38_.__init__ 
 
 
 VAE38 = VAE38Config()
-TINY = VAE38Config(z_dim=8, dec_dim=16)
+TINY = VAE38Config(z_dim=8, dec_dim=16, enc_dim=16)
 
 
 def stage_plan(cfg: VAE38Config):
@@ -327,3 +335,174 @@ def decode(w: Weights, cfg: VAE38Config, latents: torch.Tensor, tiled: bool = Fa
         lat = lat.unsqueeze(0)
         vids.append((tiled_decode(w, cfg, lat, tile_size, tile_stride) if tiled else single_decode(w, cfg, lat)).squeeze(0))
     return torch.stack(vids)
+
+
+# ============================================================================================
+# encoder (first-frame conditioning: pipelines/wan_video.py:490-497 -> WanVideoVAE.encode, VAE:1218-1232)
+# ============================================================================================
+def enc_stage_plan(cfg: VAE38Config):
+    """(in_dim, out_dim, n residual blocks, down_flag, temporal down) of the Down_ResidualBlocks, VAE:644-661."""
+    dims = cfg.enc_dims
+    plan = []
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        t_down = cfg.temperal_downsample[i] if i < len(cfg.temperal_downsample) else False
+        plan.append((a, b, cfg.num_res_blocks, i != len(cfg.dim_mult) - 1, t_down))
+    return plan
+
+
+def enc_param_shapes(cfg: VAE38Config) -> Dict[str, tuple]:
+    """State-dict keys / shapes of ``VideoVAE38_`` that encode touches: ``encoder`` and ``conv1`` (VAE:1291-1294, 620-676)."""
+    d0, dl = cfg.enc_dims[0], cfg.enc_dims[-1]
+    s = {"conv1.weight": (2 * cfg.z_dim, 2 * cfg.z_dim, 1, 1, 1), "conv1.bias": (2 * cfg.z_dim,),
+         "encoder.conv1.weight": (d0, 12, 3, 3, 3), "encoder.conv1.bias": (d0,)}
+    for i, (cin, cout, n, down, t_down) in enumerate(enc_stage_plan(cfg)):
+        p = f"encoder.downsamples.{i}.downsamples."
+        c = cin
+        for j in range(n):
+            s.update(_res_shapes(f"{p}{j}.", c, cout))
+            c = cout
+        if down:
+            s[f"{p}{n}.resample.1.weight"] = (cout, cout, 3, 3)
+            s[f"{p}{n}.resample.1.bias"] = (cout,)
+            if t_down:
+                s[f"{p}{n}.time_conv.weight"] = (cout, cout, 3, 1, 1)
+                s[f"{p}{n}.time_conv.bias"] = (cout,)
+    s.update(_res_shapes("encoder.middle.0.", dl, dl))
+    s.update({"encoder.middle.1.norm.gamma": (dl, 1, 1), "encoder.middle.1.to_qkv.weight": (3 * dl, dl, 1, 1),
+              "encoder.middle.1.to_qkv.bias": (3 * dl,), "encoder.middle.1.proj.weight": (dl, dl, 1, 1), "encoder.middle.1.proj.bias": (dl,)})
+    s.update(_res_shapes("encoder.middle.2.", dl, dl))
+    s.update({"encoder.head.0.gamma": (dl, 1, 1, 1), "encoder.head.2.weight": (2 * cfg.z_dim, dl, 3, 3, 3), "encoder.head.2.bias": (2 * cfg.z_dim,)})
+    return s
+
+
+def make_enc_weights(cfg: VAE38Config, seed: int = 0) -> Weights:
+    out = {}
+    for name, shape in enc_param_shapes(cfg).items():
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+        if name.endswith("gamma"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("bias"):
+            t = 0.05 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for v in shape[1:]:
+                fan_in *= v
+            t = torch.randn(shape, generator=g) * (fan_in ** -0.5)
+        out[name] = t
+    return out
+
+
+def patchify(x, patch: int = 2):
+    """'b c f (h q) (w r) -> b (c r q) f h w', VAE:199-211."""
+    b, c, f, H, W = x.shape
+    x = x.view(b, c, f, H // patch, patch, W // patch, patch)          # (h, q, w, r)
+    return x.permute(0, 1, 6, 4, 2, 3, 5).reshape(b, c * patch * patch, f, H // patch, W // patch)
+
+
+def avg_down3d(x, out_channels: int, factor_t: int, factor_s: int):
+    """AvgDown3D.forward, VAE:363-395: (t, h, w) sub-positions fold into channels, groups of channels are averaged."""
+    pad_t = (factor_t - x.shape[2] % factor_t) % factor_t
+    x = F.pad(x, (0, 0, 0, 0, pad_t, 0))
+    B, C, T, H, W = x.shape
+    factor = factor_t * factor_s * factor_s
+    x = x.view(B, C, T // factor_t, factor_t, H // factor_s, factor_s, W // factor_s, factor_s).permute(0, 1, 3, 5, 7, 2, 4, 6).contiguous()
+    x = x.view(B, out_channels, C * factor // out_channels, T // factor_t, H // factor_s, W // factor_s)
+    return x.mean(dim=2)
+
+
+def resample_down(w: Weights, p: str, x, temporal: bool, cache: List, idx: List[int]):
+    """Resample38.forward for 'downsample2d' / 'downsample3d', VAE:157-173: ZeroPad2d((0,1,0,1)) + 3x3 stride-2 Conv2d per
+    frame; then, temporal: the first chunk only stores its frame, later chunks run the stride-2 time_conv on
+    (last cached frame | x)."""
+    b, c, t, hh, ww = x.shape
+    y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, hh, ww)
+    y = F.conv2d(F.pad(y, (0, 1, 0, 1)), w[p + "resample.1.weight"], w[p + "resample.1.bias"], stride=2)
+    x = y.reshape(b, t, y.shape[1], y.shape[2], y.shape[3]).permute(0, 2, 1, 3, 4)
+    if temporal:
+        i = idx[0]
+        if cache[i] is None:
+            cache[i] = x.clone()
+        else:
+            tail = x[:, :, -1:].clone()
+            x = F.conv3d(torch.cat([cache[i][:, :, -1:], x], 2), w[p + "time_conv.weight"], w[p + "time_conv.bias"], stride=(2, 1, 1))
+            cache[i] = tail
+        idx[0] += 1
+    return x
+
+
+def encoder_chunk(w: Weights, cfg: VAE38Config, x, cache: List):
+    """Encoder3d_38.forward on one chunk of frames, VAE:679-733."""
+    idx = [0]
+    tail = _cache_tail(x, cache[0])
+    x = causal_conv3d(x, w["encoder.conv1.weight"], w["encoder.conv1.bias"], cache[0])
+    cache[0] = tail
+    idx[0] = 1
+    for i, (cin, cout, n, down, t_down) in enumerate(enc_stage_plan(cfg)):            # Down_ResidualBlock.forward, VAE:469-474
+        p = f"encoder.downsamples.{i}.downsamples."
+        main = x
+        for j in range(n):
+            main = residual_block(w, f"{p}{j}.", main, cache, idx)
+        if down:
+            main = resample_down(w, f"{p}{n}.", main, t_down, cache, idx)
+        x = main + avg_down3d(x, cout, 2 if t_down else 1, 2 if down else 1)
+    x = residual_block(w, "encoder.middle.0.", x, cache, idx)
+    x = attention_block(w, "encoder.middle.1.", x)
+    x = residual_block(w, "encoder.middle.2.", x, cache, idx)
+    x = F.silu(rms_norm(x, w["encoder.head.0.gamma"]))
+    i = idx[0]
+    tail = _cache_tail(x, cache[i])
+    x = causal_conv3d(x, w["encoder.head.2.weight"], w["encoder.head.2.bias"], cache[i])
+    cache[i] = tail
+    return x
+
+
+def count_enc_cache_slots(cfg: VAE38Config) -> int:
+    """count_conv3d(encoder), VAE:943-948."""
+    return sum(1 for k, s in enc_param_shapes(cfg).items() if k.startswith("encoder.") and k.endswith("weight") and len(s) == 5)
+
+
+def model_encode(w: Weights, cfg: VAE38Config, video: torch.Tensor) -> torch.Tensor:
+    """VideoVAE38_.encode, VAE:1298-1323: video [1, 3, 1+4k, H, W] in [-1, 1] -> normalised latent mean [1, z_dim, 1+k, H/16, W/16];
+    the first frame alone, then chunks of 4 frames."""
+    x = patchify(video)
+    cache: List = [None] * count_enc_cache_slots(cfg)
+    t = x.shape[2]
+    outs = []
+    for i in range(1 + (t - 1) // 4):
+        chunk = x[:, :, :1] if i == 0 else x[:, :, 1 + 4 * (i - 1):1 + 4 * i]
+        outs.append(encoder_chunk(w, cfg, chunk, cache))
+    mu = causal_conv3d(torch.cat(outs, 2), w["conv1.weight"], w["conv1.bias"]).chunk(2, dim=1)[0]
+    mean, inv_std = latent_scale(cfg)
+    return (mu - mean.to(mu).view(1, -1, 1, 1, 1)) * inv_std.to(mu).view(1, -1, 1, 1, 1)
+
+
+def tiled_encode(w: Weights, cfg: VAE38Config, video: torch.Tensor, tile_size, tile_stride) -> torch.Tensor:
+    """WanVideoVAE.tiled_encode, VAE:1155-1203; tile_size / tile_stride in PIXELS (encode() multiplies the latent-unit arguments
+    by 16 first, VAE:1224-1226)."""
+    _, _, T, H, W = video.shape
+    f = cfg.upsampling_factor
+    out_t = (T + 3) // 4
+    weight = torch.zeros(1, 1, out_t, H // f, W // f, dtype=video.dtype)
+    values = torch.zeros(1, cfg.z_dim, out_t, H // f, W // f, dtype=video.dtype)
+    for h, h_, ww, w_ in tile_tasks(H, W, tile_size, tile_stride):
+        part = model_encode(w, cfg, video[:, :, :, h:h_, ww:w_])
+        ph, pw = part.shape[3], part.shape[4]
+        mh = build_1d_mask(ph, h == 0, h_ >= H, (tile_size[0] - tile_stride[0]) // f)
+        mw = build_1d_mask(pw, ww == 0, w_ >= W, (tile_size[1] - tile_stride[1]) // f)
+        mask = torch.minimum(mh[:, None].expand(ph, pw), mw[None, :].expand(ph, pw)).view(1, 1, 1, ph, pw).to(video.dtype)
+        values[:, :, :, h // f:h // f + ph, ww // f:ww // f + pw] += part * mask
+        weight[:, :, :, h // f:h // f + ph, ww // f:ww // f + pw] += mask
+    return values / weight
+
+
+def encode(w: Weights, cfg: VAE38Config, videos, tiled: bool = False, tile_size=(34, 34), tile_stride=(18, 16)) -> torch.Tensor:
+    """WanVideoVAE.encode, VAE:1218-1232: list of videos [3, T, H, W] -> latents [B, z_dim, (T+3)//4, H/16, W/16]."""
+    f = cfg.upsampling_factor
+    outs = []
+    for v in videos:
+        v = v.unsqueeze(0)
+        if tiled:
+            outs.append(tiled_encode(w, cfg, v, (tile_size[0] * f, tile_size[1] * f), (tile_stride[0] * f, tile_stride[1] * f)).squeeze(0))
+        else:
+            outs.append(model_encode(w, cfg, v).squeeze(0))
+    return torch.stack(outs)

@@ -94,3 +94,31 @@ def test_window_assignment_covers_every_window_once_and_balances():
         loads = [sum(area(t) for t in p) for p in parts]
         assert max(loads) <= {1: 7788, 2: 3908, 4: 2348, 6: 1560, 8: 1560}[world]
     assert vae.assign_windows(tasks, 44, 80, 2) == vae.assign_windows(tasks, 44, 80, 2)      # deterministic: every rank agrees
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# encoder (first-frame conditioning)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def enc_weights():
+    return o.make_enc_weights(o.TINY, seed=0)
+
+
+def test_encoder_plan_and_primitives():
+    assert o.VAE38.enc_dims == [160, 160, 320, 640, 640]
+    assert [(d, t) for _, _, _, d, t in o.enc_stage_plan(o.VAE38)] == [(True, False), (True, True), (True, True), (False, False)]
+    xa = latents((1, 16, 3, 4, 6), 33)
+    assert np.array_equal(o.avg_down3d(xa, 32, 2, 2).numpy(), GOLD["avg_down_t2"])
+    assert np.array_equal(o.avg_down3d(xa, 16, 1, 2).numpy(), GOLD["avg_down_t1"])
+    x = latents((1, 3, 2, 6, 10), 34)
+    assert np.array_equal(o.patchify(x).numpy(), GOLD["patchify"])
+    assert torch.equal(o.unpatchify(o.patchify(x)), x)
+
+
+def test_encode_image_clip_and_tiled(enc_weights):
+    cfg = o.TINY
+    with torch.no_grad():
+        close(o.encode(enc_weights, cfg, [torch.tanh(latents((3, 1, 32, 48), 30))]), GOLD["encode_image"])
+        close(o.encode(enc_weights, cfg, [torch.tanh(latents((3, 9, 32, 32), 31))]), GOLD["encode_clip"])      # chunks of 1, 4, 4 frames
+        close(o.encode(enc_weights, cfg, [torch.tanh(latents((3, 1, 80, 96), 32))], tiled=True, tile_size=(3, 4), tile_stride=(2, 2)),
+              GOLD["encode_tiled"])
