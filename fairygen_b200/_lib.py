@@ -69,6 +69,12 @@ SIGNATURES = {
     "fgb_vae_attn_softmax": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _F, _P]),
     "fgb_vae_unpatchify": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "fgb_vae_blend_finish": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "fgb_vae_patchify_rows": (ctypes.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "fgb_vae_space_to_depth": (ctypes.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "fgb_vae_avg_down_add": (ctypes.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "fgb_vae_latent_out": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                          _I32, _I32, _P]),
+    "fgb_vae_blend_divide": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "fgb_embedding_rows": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _I64, _P]),
     "fgb_t5_layer_norm": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _F, _P, _P]),
     "fgb_geglu": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _P]),

@@ -233,6 +233,110 @@ __global__ void vae_blend_finish_kernel(float* __restrict__ values, const float*
     values[idx] = fminf(fmaxf(values[idx] / weight[idx % plane], -1.f), 1.f);
 }
 
+// =============================================================================================
+// Encoder side (VideoVAE38_.encode, VAE:1298-1323; Encoder3d_38, VAE:620-733) — kernels written against the pinned oracle
+// (oracle/vae38_oracle.py::encode); see DESIGN §7c for their verification status.
+// =============================================================================================
+
+// patchify 'b c f (h q) (w r) -> b (c r q) f h w' (VAE:199-211): video bf16 [3][T][H][W] -> grid [T][H/2+2][W/2+2][Cp], channel
+// (c*2 + r)*2 + q holds pixel (2y + q, 2x + r) of colour c.
+__global__ void vae_patchify_rows_kernel(const __nv_bfloat16* __restrict__ video, __nv_bfloat16* __restrict__ out, int T, int H, int W,
+                                         int Cp) {
+  const int64_t total = static_cast<int64_t>(T) * H * W * 3;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % W);
+    int64_t r = idx / W;
+    const int Y = static_cast<int>(r % H);
+    r /= H;
+    const int t = static_cast<int>(r % T), c = static_cast<int>(r / T);
+    const int ch = (c * 2 + (X & 1)) * 2 + (Y & 1);
+    const int64_t row = (static_cast<int64_t>(t) * (H / 2 + 2) + (Y >> 1) + 1) * (W / 2 + 2) + (X >> 1) + 1;
+    out[row * Cp + ch] = video[idx];
+  }
+}
+
+// space-to-depth by 2 in h, w: dst[t][y+1][x+1][(py*2 + px)*Cp + c] = src[t][2y+py+1][2x+px+1][c]. A stride-2 3x3 convolution
+// with ZeroPad2d((0,1,0,1)) (Resample 'downsample2d/3d', VAE:106-117, 240-249) is then a stride-1 convolution with 2x2 taps
+// over 4*Cp channels of this grid (kernel rows / columns 2t + p, the fourth one zero), i.e. one fgb_conv_taps_bf16 launch.
+__global__ void vae_space_to_depth_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cp, int T, int H, int W) {
+  const int vec = Cp / 8;
+  const int h2 = H / 2, w2 = W / 2;
+  const int64_t total = static_cast<int64_t>(T) * H * W * vec;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % vec);
+    int64_t r = idx / vec;
+    const int X = static_cast<int>(r % W);
+    r /= W;
+    const int Y = static_cast<int>(r % H), t = static_cast<int>(r / H);
+    const uint4 v = ldg_nc_v4(reinterpret_cast<const uint4*>(src + ((static_cast<int64_t>(t) * (H + 2) + Y + 1) * (W + 2) + X + 1) * Cp) + c);
+    const int64_t drow = (static_cast<int64_t>(t) * (h2 + 2) + (Y >> 1) + 1) * (w2 + 2) + (X >> 1) + 1;
+    reinterpret_cast<uint4*>(dst + drow * (4ll * Cp) + ((Y & 1) * 2 + (X & 1)) * Cp)[c] = v;
+  }
+}
+
+// main += AvgDown3D(x) (VAE:363-395, 469-474): the (ft, fs, fs) sub-positions of x fold into channels k = ((c*ft + a)*fs + b)*fs + d,
+// consecutive groups of `group` such channels are averaged into one output channel. pad_front zero frames precede x when its
+// frame count is not a multiple of ft (the single-frame first chunk).
+__global__ void vae_avg_down_add_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ main, int Cin_p, int Cout, int Cout_p,
+                                        int group, int ft, int fs, int pad_front, int T_out, int H_out, int W_out) {
+  const int64_t total = static_cast<int64_t>(T_out) * H_out * W_out * Cout;
+  const int Hin = H_out * fs, Win = W_out * fs;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(idx % Cout);
+    int64_t r = idx / Cout;
+    const int xo = static_cast<int>(r % W_out);
+    r /= W_out;
+    const int yo = static_cast<int>(r % H_out), to = static_cast<int>(r / H_out);
+    float sum = 0.f;
+    for (int g = 0; g < group; ++g) {
+      const int k = co * group + g;
+      const int c = k / (ft * fs * fs), rem = k % (ft * fs * fs);
+      const int a = rem / (fs * fs), b = (rem / fs) % fs, d = rem % fs;
+      const int ti = to * ft + a - pad_front;
+      if (ti < 0) continue;
+      sum += __bfloat162float(x[((static_cast<int64_t>(ti) * (Hin + 2) + yo * fs + b + 1) * (Win + 2) + xo * fs + d + 1) * Cin_p + c]);
+    }
+    __nv_bfloat16* dptr = main + ((static_cast<int64_t>(to) * (H_out + 2) + yo + 1) * (W_out + 2) + xo + 1) * Cout_p + co;
+    *dptr = __float2bfloat16_rn(__bfloat162float(*dptr) + round_bf16(sum / group));
+  }
+}
+
+// Latent mean out of the 1x1x1 `conv1` grid (first z of its 2z channels), normalised (mu - mean) * inv_std (VAE:1313-1320), into
+// fp32 [z][VT][Vh][Vw] at (t0, y0, x0): directly, or blended like tiled_encode (VAE:1181-1203).
+template <bool BLEND>
+__global__ void vae_latent_out_kernel(const __nv_bfloat16* __restrict__ grid, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                      float* __restrict__ values, float* __restrict__ weight, int Z, VaeOutParams p) {
+  const int64_t total = static_cast<int64_t>(p.T) * p.H * p.W;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % p.W);
+    int64_t r = idx / p.W;
+    const int Y = static_cast<int>(r % p.H), t = static_cast<int>(r / p.H);
+    const int vy = p.y0 + Y, vx = p.x0 + X, vt = p.t0 + t;
+    if (vy >= p.VH || vx >= p.VW || vt >= p.VT) continue;
+    const __nv_bfloat16* row = grid + ((static_cast<int64_t>(t) * (p.H + 2) + Y + 1) * (p.W + 2) + X + 1) * p.Cp;
+    float m = 1.f;
+    if (BLEND) m = fminf(vae_ramp(Y, p.H, p.top_bound, p.bottom_bound, p.border_y), vae_ramp(X, p.W, p.left_bound, p.right_bound, p.border_x));
+    for (int c = 0; c < Z; ++c) {
+      const float v = (__bfloat162float(row[c]) - mean[c]) * inv_std[c];
+      const int64_t o = ((static_cast<int64_t>(c) * p.VT + vt) * p.VH + vy) * p.VW + vx;
+      if (BLEND) values[o] += round_bf16(v) * m;
+      else values[o] = v;
+    }
+    if (BLEND) weight[(static_cast<int64_t>(vt) * p.VH + vy) * p.VW + vx] += m;
+  }
+}
+
+__global__ void vae_blend_divide_kernel(float* __restrict__ values, const float* __restrict__ weight, int64_t plane, int channels) {
+  const int64_t total = plane * channels;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    values[idx] = values[idx] / weight[idx % plane];
+}
+
 }  // namespace fgb
 
 using namespace fgb;
@@ -323,5 +427,76 @@ extern "C" int fgb_vae_blend_finish(fgb_ctx* ctx, void* values_f32, const void* 
   vae_blend_finish_kernel<<<vae_grid(plane * channels, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<float*>(values_f32), static_cast<const float*>(weight_f32), plane, channels);
   FGB_LAUNCH_CHECK("vae_blend_finish_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_patchify_rows(fgb_ctx* ctx, const void* video, void* grid, int32_t frames, int32_t h, int32_t w, int32_t cp,
+                                     void* stream) {
+  FGB_CHECK_ARG(ctx && video && grid, "fgb_vae_patchify_rows: NULL argument");
+  FGB_CHECK_ARG(frames > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && cp >= 12, "fgb_vae_patchify_rows: T=%d H=%d W=%d Cp=%d (even H, W)",
+                frames, h, w, cp);
+  const int64_t total = static_cast<int64_t>(frames) * h * w * 3;
+  vae_patchify_rows_kernel<<<vae_grid(total, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(video), static_cast<bf16*>(grid), frames, h, w, cp);
+  FGB_LAUNCH_CHECK("vae_patchify_rows_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_space_to_depth(fgb_ctx* ctx, const void* src, void* dst, int32_t cp, int32_t frames, int32_t h, int32_t w, void* stream) {
+  FGB_CHECK_ARG(ctx && src && dst, "fgb_vae_space_to_depth: NULL argument");
+  FGB_CHECK_ARG(cp > 0 && cp % 8 == 0 && frames > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && aligned16(src) && aligned16(dst),
+                "fgb_vae_space_to_depth: Cp=%d T=%d H=%d W=%d (even H, W)", cp, frames, h, w);
+  const int64_t total = static_cast<int64_t>(frames) * h * w * (cp / 8);
+  vae_space_to_depth_kernel<<<vae_grid(total, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(src), static_cast<bf16*>(dst), cp, frames, h, w);
+  FGB_LAUNCH_CHECK("vae_space_to_depth_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_avg_down_add(fgb_ctx* ctx, const void* x, void* main, int32_t cin, int32_t cin_p, int32_t cout, int32_t cout_p,
+                                    int32_t factor_t, int32_t factor_s, int32_t pad_front, int32_t frames_out, int32_t h_out, int32_t w_out,
+                                    void* stream) {
+  FGB_CHECK_ARG(ctx && x && main, "fgb_vae_avg_down_add: NULL argument");
+  FGB_CHECK_ARG(cin > 0 && cout > 0 && cin_p >= cin && cout_p >= cout && (factor_t == 1 || factor_t == 2) && (factor_s == 1 || factor_s == 2) &&
+                    pad_front >= 0 && pad_front < factor_t && frames_out > 0 && h_out > 0 && w_out > 0 &&
+                    (cin * factor_t * factor_s * factor_s) % cout == 0,
+                "fgb_vae_avg_down_add: Cin=%d Cout=%d factor_t=%d factor_s=%d pad_front=%d", cin, cout, factor_t, factor_s, pad_front);
+  const int64_t total = static_cast<int64_t>(frames_out) * h_out * w_out * cout;
+  vae_avg_down_add_kernel<<<vae_grid(total, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(main), cin_p, cout, cout_p, cin * factor_t * factor_s * factor_s / cout, factor_t, factor_s,
+      pad_front, frames_out, h_out, w_out);
+  FGB_LAUNCH_CHECK("vae_avg_down_add_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_latent_out(fgb_ctx* ctx, const void* grid, int32_t frames, int32_t h, int32_t w, int32_t cp, const void* mean_f32,
+                                  const void* inv_std_f32, int32_t z_dim, void* values_f32, void* weight_f32, int32_t t0, int32_t y0, int32_t x0,
+                                  int32_t out_frames, int32_t out_h, int32_t out_w, int32_t bounds_tblr, int32_t border_y, int32_t border_x,
+                                  void* stream) {
+  FGB_CHECK_ARG(ctx && grid && mean_f32 && inv_std_f32 && values_f32, "fgb_vae_latent_out: NULL argument");
+  FGB_CHECK_ARG(frames > 0 && h > 0 && w > 0 && z_dim > 0 && cp >= z_dim && t0 >= 0 && y0 >= 0 && x0 >= 0 && out_frames > 0 && out_h > 0 && out_w > 0,
+                "fgb_vae_latent_out: bad geometry");
+  FGB_CHECK_ARG(!weight_f32 || (border_y > 0 && border_x > 0), "fgb_vae_latent_out: blending needs positive border widths");
+  VaeOutParams p{frames, h, w, cp, t0, y0, x0, out_frames, out_h, out_w, (bounds_tblr >> 3) & 1, (bounds_tblr >> 2) & 1,
+                 (bounds_tblr >> 1) & 1, bounds_tblr & 1, border_y, border_x};
+  const int64_t total = static_cast<int64_t>(frames) * h * w;
+  const int blocks = vae_grid(total, 128, ctx->sm_count * 16);
+  if (weight_f32)
+    vae_latent_out_kernel<true><<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(grid), static_cast<const float*>(mean_f32), static_cast<const float*>(inv_std_f32),
+        static_cast<float*>(values_f32), static_cast<float*>(weight_f32), z_dim, p);
+  else
+    vae_latent_out_kernel<false><<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(grid), static_cast<const float*>(mean_f32), static_cast<const float*>(inv_std_f32),
+        static_cast<float*>(values_f32), nullptr, z_dim, p);
+  FGB_LAUNCH_CHECK("vae_latent_out_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_vae_blend_divide(fgb_ctx* ctx, void* values_f32, const void* weight_f32, int64_t plane, int32_t channels, void* stream) {
+  FGB_CHECK_ARG(ctx && values_f32 && weight_f32 && plane > 0 && channels > 0, "fgb_vae_blend_divide: bad argument");
+  vae_blend_divide_kernel<<<vae_grid(plane * channels, 256, ctx->sm_count * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<float*>(values_f32), static_cast<const float*>(weight_f32), plane, channels);
+  FGB_LAUNCH_CHECK("vae_blend_divide_kernel");
   return FGB_OK;
 }

@@ -692,3 +692,55 @@ def vae_unpatchify(head, frames: int, h: int, w: int, values, weight, t0: int, y
 def vae_blend_finish(values, weight):
     _lib.check(_lib.lib().fgb_vae_blend_finish(_h(values).handle, _p(values), _p(weight), weight.numel(), values.shape[0], _stream()),
                "fgb_vae_blend_finish")
+
+
+# ---- VAE38 encoder side (not yet run on a GPU at the end of round 1) ----
+def vae_patchify_rows(video, grid, cp: int):
+    """video bf16 [3, T, H, W] -> interior of grid rows [T*(H/2+2)*(W/2+2), cp]."""
+    C, T, H, W = video.shape
+    if video.dtype != BF16 or not video.is_contiguous() or C != 3 or H % 2 or W % 2:
+        raise ValueError("vae_patchify_rows: video must be contiguous bf16 [3, T, H, W] with even H, W")
+    if grid.dtype != BF16 or not grid.is_contiguous() or tuple(grid.shape) != (T * (H // 2 + 2) * (W // 2 + 2), cp):
+        raise ValueError("vae_patchify_rows: grid must be contiguous bf16 rows [T*(H/2+2)*(W/2+2), cp]")
+    _lib.check(_lib.lib().fgb_vae_patchify_rows(_h(video).handle, _p(video), _p(grid), T, H, W, cp, _stream()), "fgb_vae_patchify_rows")
+
+
+def vae_space_to_depth(src, dst, cp: int, frames: int, h: int, w: int):
+    if src.dtype != BF16 or dst.dtype != BF16 or not src.is_contiguous() or not dst.is_contiguous() or h % 2 or w % 2:
+        raise ValueError("vae_space_to_depth: contiguous bf16 grids, even h and w")
+    if src.numel() < frames * (h + 2) * (w + 2) * cp or dst.numel() < frames * (h // 2 + 2) * (w // 2 + 2) * 4 * cp:
+        raise ValueError("vae_space_to_depth: grid too small")
+    _lib.check(_lib.lib().fgb_vae_space_to_depth(_h(src).handle, _p(src), _p(dst), cp, frames, h, w, _stream()), "fgb_vae_space_to_depth")
+
+
+def vae_avg_down_add(x, main, cin: int, cout: int, factor_t: int, factor_s: int, pad_front: int, frames_out: int, h_out: int, w_out: int):
+    if x.dtype != BF16 or main.dtype != BF16 or not x.is_contiguous() or not main.is_contiguous():
+        raise ValueError("vae_avg_down_add: contiguous bf16 grids")
+    frames_in = frames_out * factor_t - pad_front
+    if x.shape[0] < frames_in * (h_out * factor_s + 2) * (w_out * factor_s + 2) or main.shape[0] < frames_out * (h_out + 2) * (w_out + 2):
+        raise ValueError("vae_avg_down_add: grid too small")
+    _lib.check(_lib.lib().fgb_vae_avg_down_add(_h(x).handle, _p(x), _p(main), cin, x.shape[1], cout, main.shape[1], factor_t, factor_s,
+                                               pad_front, frames_out, h_out, w_out, _stream()), "fgb_vae_avg_down_add")
+
+
+def vae_latent_out(grid, frames: int, h: int, w: int, mean, inv_std, values, weight, t0: int, y0: int, x0: int,
+                   bounds=(True, True, True, True), border=(1, 1)):
+    """conv1 grid rows [frames*(h+2)*(w+2), cp] -> normalised latent mean into values fp32 [z, T, H, W] (+ weight when blending)."""
+    z = values.shape[0]
+    if grid.dtype != BF16 or not grid.is_contiguous() or grid.shape[0] < frames * (h + 2) * (w + 2) or grid.shape[1] < z:
+        raise ValueError("vae_latent_out: grid must be the contiguous bf16 rows of the conv1 grid")
+    if values.dtype != torch.float32 or values.dim() != 4 or not values.is_contiguous():
+        raise ValueError("vae_latent_out: values must be contiguous fp32 [z, T, H, W]")
+    if weight is not None and (weight.dtype != torch.float32 or tuple(weight.shape) != tuple(values.shape[1:]) or not weight.is_contiguous()):
+        raise ValueError("vae_latent_out: weight must be contiguous fp32 [T, H, W]")
+    if any(t.dtype != torch.float32 or t.numel() != z or not t.is_contiguous() for t in (mean, inv_std)):
+        raise ValueError("vae_latent_out: mean / inv_std must be contiguous fp32 [z]")
+    b = (int(bounds[0]) << 3) | (int(bounds[1]) << 2) | (int(bounds[2]) << 1) | int(bounds[3])
+    _lib.check(_lib.lib().fgb_vae_latent_out(_h(grid).handle, _p(grid), frames, h, w, grid.shape[1], _p(mean), _p(inv_std), z, _p(values),
+                                             _p(weight), t0, y0, x0, values.shape[1], values.shape[2], values.shape[3], b, border[0], border[1],
+                                             _stream()), "fgb_vae_latent_out")
+
+
+def vae_blend_divide(values, weight):
+    _lib.check(_lib.lib().fgb_vae_blend_divide(_h(values).handle, _p(values), _p(weight), weight.numel(), values.shape[0], _stream()),
+               "fgb_vae_blend_divide")

@@ -308,7 +308,7 @@ class VAE38Decoder:
     def _attention(self, x: torch.Tensor, T: int, h: int, w: int) -> torch.Tensor:
         """AttentionBlock.forward (VAE:321-342): one head of width C over the positions of each frame; the grid border is
         excluded as keys and re-zeroed in the output."""
-        C = self.cfg.dims[0]
+        C = getattr(self, "_attn_dim", self.cfg.dims[0])      # the encoder (vae_encode.py) runs the same block at its own width
         cp = _c64(C)
         hp, wp = h + 2, w + 2
         P = hp * wp

@@ -373,6 +373,31 @@ int fgb_vae_unpatchify(fgb_ctx* ctx, const void* head, int32_t frames, int32_t h
 /* values = clamp(values / weight, -1, 1) (VAE:1151-1152); weight has one plane, values `channels` planes. */
 int fgb_vae_blend_finish(fgb_ctx* ctx, void* values_f32, const void* weight_f32, int64_t plane, int32_t channels, void* stream);
 
+/* --- VAE38 encoder side (VideoVAE38_.encode, VAE:1298-1323; Encoder3d_38, VAE:620-733). Written against the pinned oracle; not yet
+ * run on a GPU at the end of round 1 — the GPU tests are gated behind FGB_UNVERIFIED=1 until they have been. --- */
+
+/* patchify 'b c f (h q) (w r) -> b (c r q) f h w' (VAE:199-211): video bf16 [3, frames, h, w] -> grid [frames, h/2, w/2, cp]. */
+int fgb_vae_patchify_rows(fgb_ctx* ctx, const void* video, void* grid, int32_t frames, int32_t h, int32_t w, int32_t cp, void* stream);
+
+/* dst[t, y, x, (py*2+px)*cp + c] = src[t, 2y+py, 2x+px, c] (grids [frames, h, w, cp] -> [frames, h/2, w/2, 4cp]): turns the stride-2
+ * 3x3 convolution with ZeroPad2d((0,1,0,1)) of Resample 'downsample2d/3d' (VAE:106-117, 240-249) into a 2x2-tap stride-1 tap GEMM. */
+int fgb_vae_space_to_depth(fgb_ctx* ctx, const void* src, void* dst, int32_t cp, int32_t frames, int32_t h, int32_t w, void* stream);
+
+/* main += AvgDown3D(x): the parameter-free shortcut of Down_ResidualBlock (VAE:363-395, 469-474). x grid [T_in, h_out*fs, w_out*fs,
+ * cin_p], main grid [frames_out, h_out, w_out, cout_p]; pad_front zero frames precede x (frame count not a multiple of factor_t). */
+int fgb_vae_avg_down_add(fgb_ctx* ctx, const void* x, void* main, int32_t cin, int32_t cin_p, int32_t cout, int32_t cout_p,
+                         int32_t factor_t, int32_t factor_s, int32_t pad_front, int32_t frames_out, int32_t h_out, int32_t w_out,
+                         void* stream);
+
+/* Latent mean (first z_dim channels of the conv1 grid), normalised (mu - mean) * inv_std (VAE:1313-1320), into fp32
+ * [z_dim, out_frames, out_h, out_w] at (t0, y0, x0); weight_f32 != NULL: blended like tiled_encode (VAE:1181-1203), arguments as in
+ * fgb_vae_unpatchify. fgb_vae_blend_divide then forms values / weight (no clamp). */
+int fgb_vae_latent_out(fgb_ctx* ctx, const void* grid, int32_t frames, int32_t h, int32_t w, int32_t cp, const void* mean_f32,
+                       const void* inv_std_f32, int32_t z_dim, void* values_f32, void* weight_f32, int32_t t0, int32_t y0, int32_t x0,
+                       int32_t out_frames, int32_t out_h, int32_t out_w, int32_t bounds_tblr, int32_t border_y, int32_t border_x,
+                       void* stream);
+int fgb_vae_blend_divide(fgb_ctx* ctx, void* values_f32, const void* weight_f32, int64_t plane, int32_t channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,214 @@
+"""Host logic of the VAE38 encoder (fairygen_b200/vae_encode.py) and decoder (vae.py) on the CPU: the kernels are replaced by plain-torch statements of
+what each C entry point computes (the same contracts include/fairygen_b200.h states), and the orchestration — chunking, feature
+cache, tap offsets, space-to-depth stride-2 convolution, per-frame temporal convolution, AvgDown3D arguments, tiling — must then
+reproduce the pinned oracle.  The kernels themselves are covered by tests/test_vae_encode_gpu.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vae38_oracle as o
+
+BF = torch.bfloat16
+
+
+def _emulated_ops(monkeypatch):
+    from fairygen_b200 import ops
+
+    def conv_taps(x, a_row0, w, bias, out, tap_offsets, grid_hw=(0, 0), epilogue=ops.EPI_BIAS):
+        m, n = out.shape
+        cin = x.shape[1]
+        acc = torch.zeros(m, n)
+        base = torch.arange(m) + a_row0
+        for t, off in enumerate(tap_offsets):
+            idx = base + off
+            ok = (idx >= 0) & (idx < x.shape[0])
+            rows = torch.zeros(m, cin)
+            rows[ok] = x[idx[ok]].float()
+            acc += rows @ w[:, t * cin:(t + 1) * cin].float().T
+        y = (acc + (0 if bias is None else bias.float())).to(BF).float()
+        if epilogue == ops.EPI_RESIDUAL:
+            y = out.float() + y
+        if grid_hw[1] > 0:
+            pos = torch.arange(m) % (grid_hw[0] * grid_hw[1])
+            gy, gx = pos // grid_hw[1], pos % grid_hw[1]
+            y[(gy == 0) | (gy == grid_hw[0] - 1) | (gx == 0) | (gx == grid_hw[1] - 1)] = 0
+        out.copy_(y.to(BF))
+        return out
+
+    def vae_norm_silu(x, out, channels, gamma, silu=True):
+        xf = x.float()
+        y = (xf / xf.norm(dim=1, keepdim=True).clamp_min(1e-12) * channels ** 0.5 * gamma.float()).to(BF).float()
+        out.copy_((torch.nn.functional.silu(y) if silu else y).to(BF))
+
+    def vae_patchify_rows(video, grid, cp):
+        _, T, H, W = video.shape
+        g = grid.view(T, H // 2 + 2, W // 2 + 2, cp)
+        for c in range(3):
+            for r in range(2):
+                for q in range(2):
+                    g[:, 1:-1, 1:-1, (c * 2 + r) * 2 + q] = video[c, :, q::2, r::2]
+
+    def vae_space_to_depth(src, dst, cp, frames, h, w):
+        s = src[:frames * (h + 2) * (w + 2)].view(frames, h + 2, w + 2, cp)
+        d = dst[:frames * (h // 2 + 2) * (w // 2 + 2)].view(frames, h // 2 + 2, w // 2 + 2, 4 * cp)
+        for py in range(2):
+            for px in range(2):
+                d[:, 1:-1, 1:-1, (py * 2 + px) * cp:(py * 2 + px + 1) * cp] = s[:, 1 + py:1 + h:2, 1 + px:1 + w:2]
+
+    def vae_avg_down_add(x, main, cin, cout, factor_t, factor_s, pad_front, frames_out, h_out, w_out):
+        hin, win = h_out * factor_s, w_out * factor_s
+        t_in = frames_out * factor_t - pad_front
+        xv = x[:t_in * (hin + 2) * (win + 2)].view(t_in, hin + 2, win + 2, -1)[:, 1:-1, 1:-1, :cin].float().permute(3, 0, 1, 2)[None]
+        add = o.avg_down3d(xv, cout, factor_t, factor_s)[0]                      # [cout, frames_out, h_out, w_out]
+        m = main[:frames_out * (h_out + 2) * (w_out + 2)].view(frames_out, h_out + 2, w_out + 2, -1)
+        m[:, 1:-1, 1:-1, :cout] = (m[:, 1:-1, 1:-1, :cout].float() + add.to(BF).float().permute(1, 2, 3, 0)).to(BF)
+
+    def gemm(a, w, bias, out, *args, **kw):
+        out.copy_((a.float() @ w.float().T).to(BF))
+        return out
+
+    def gemm_dgrad(dy, w, dx, *args, **kw):
+        dx.copy_((dy.float() @ w.float()).to(BF))
+        return dx
+
+    def vae_attn_softmax(scores, n_cols, gh, gw, scale):
+        col = torch.arange(n_cols)
+        gy, gx = col // gw, col % gw
+        live = (col < gh * gw) & (gy > 0) & (gy < gh - 1) & (gx > 0) & (gx < gw - 1)
+        s = (scores[:, :n_cols].float() * scale).masked_fill(~live, float("-inf"))
+        scores[:, :n_cols] = torch.softmax(s, dim=1).to(BF)
+
+    def ramp(n, first, last, border):
+        return o.build_1d_mask(n, first, last, border)
+
+    def vae_latent_out(grid, frames, h, w, mean, inv_std, values, weight, t0, y0, x0, bounds=(True,) * 4, border=(1, 1)):
+        z = values.shape[0]
+        g = grid[:frames * (h + 2) * (w + 2)].view(frames, h + 2, w + 2, -1)[:, 1:-1, 1:-1, :z].float()
+        v = ((g - mean) * inv_std).permute(3, 0, 1, 2)
+        if weight is None:
+            values[:, t0:t0 + frames, y0:y0 + h, x0:x0 + w] = v
+        else:
+            m = torch.minimum(ramp(h, bounds[0], bounds[1], border[0])[:, None], ramp(w, bounds[2], bounds[3], border[1])[None, :])
+            values[:, t0:t0 + frames, y0:y0 + h, x0:x0 + w] += v.to(BF).float() * m
+            weight[t0:t0 + frames, y0:y0 + h, x0:x0 + w] += m
+
+    def vae_blend_divide(values, weight):
+        values /= weight
+
+    # ---- decoder side
+    def vae_latent_rows(z, mean, inv_std, grid, cp):
+        C, T, H, W = z.shape
+        g = grid.view(T, H + 2, W + 2, cp)
+        v = (z.float() / inv_std.view(-1, 1, 1, 1)).to(BF).float() + mean.view(-1, 1, 1, 1)
+        g[:, 1:-1, 1:-1, :C] = v.permute(1, 2, 3, 0).to(BF)
+
+    def vae_upsample2x(src, dst, cp, frames_dst, h, w, halves=1):
+        s = src[:(frames_dst // halves) * (h + 2) * (w + 2)].view(frames_dst // halves, h + 2, w + 2, halves, cp)[:, 1:-1, 1:-1]
+        s = s.permute(0, 3, 1, 2, 4).reshape(frames_dst, h, w, cp)                # frame t' = half t' % halves of source frame t' // halves
+        d = dst[:frames_dst * (2 * h + 2) * (2 * w + 2)].view(frames_dst, 2 * h + 2, 2 * w + 2, cp)
+        d[:, 1:-1, 1:-1] = s.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+
+    def vae_dup_up_add(x, main, cin, cout, factor_t, first_chunk, frames_out, h, w):
+        t_in = (frames_out + (factor_t - 1 if first_chunk else 0)) // factor_t
+        xv = x[:t_in * (h + 2) * (w + 2)].view(t_in, h + 2, w + 2, -1)[:, 1:-1, 1:-1, :cin].float().permute(3, 0, 1, 2)[None]
+        add = o.dup_up3d(xv, cout, factor_t, 2, first_chunk)[0]
+        m = main[:frames_out * (2 * h + 2) * (2 * w + 2)].view(frames_out, 2 * h + 2, 2 * w + 2, -1)
+        m[:, 1:-1, 1:-1, :cout] = (m[:, 1:-1, 1:-1, :cout].float() + add.permute(1, 2, 3, 0)).to(BF)
+
+    def vae_unpatchify(head, frames, h, w, values, weight, t0, y0, x0, bounds=(True,) * 4, border=(1, 1)):
+        g = head[:frames * (h + 2) * (w + 2)].view(frames, h + 2, w + 2, -1)[:, 1:-1, 1:-1, :12].float().permute(3, 0, 1, 2)[None]
+        v = o.unpatchify(g)[0]                                                    # [3, frames, 2h, 2w]
+        vt = min(frames, values.shape[1] - t0)
+        if weight is None:
+            values[:, t0:t0 + vt, y0:y0 + 2 * h, x0:x0 + 2 * w] = v[:, :vt].clamp(-1, 1)
+        else:
+            m = torch.minimum(ramp(2 * h, bounds[0], bounds[1], border[0])[:, None], ramp(2 * w, bounds[2], bounds[3], border[1])[None, :])
+            values[:, t0:t0 + vt, y0:y0 + 2 * h, x0:x0 + 2 * w] += v[:, :vt] * m
+            weight[t0:t0 + vt, y0:y0 + 2 * h, x0:x0 + 2 * w] += m
+
+    def vae_blend_finish(values, weight):
+        values.copy_((values / weight).clamp(-1, 1))
+
+    for name, fn in list(locals().items()):
+        if callable(fn) and name not in ("ramp",) and hasattr(ops, name):
+            monkeypatch.setattr(ops, name, fn)
+    monkeypatch.setattr(ops, "context", lambda device: None)
+
+
+def latents(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+@pytest.fixture()
+def encoder(monkeypatch):
+    _emulated_ops(monkeypatch)
+    from fairygen_b200 import vae, vae_encode
+    cfg = vae.VAE38Config(z_dim=o.TINY.z_dim, dec_dim=o.TINY.dec_dim)
+    enc = vae_encode.VAE38Encoder(cfg, "cpu", enc_dim=o.TINY.enc_dim)
+    w = o.make_enc_weights(o.TINY, seed=0)
+    enc.load_state_dict({"model." + k: v for k, v in w.items()})
+    return enc, {k: v.to(BF).float() for k, v in w.items()}
+
+
+def test_host_mirror_lists_the_reference_keys():
+    from fairygen_b200 import vae, vae_encode
+    assert vae_encode.enc_param_shapes(vae.VAE38) == o.enc_param_shapes(o.VAE38)
+    assert vae_encode.enc_param_shapes(vae.VAE38Config(z_dim=8, dec_dim=16), 16) == o.enc_param_shapes(o.TINY)
+
+
+@pytest.mark.parametrize("shape,seed", [((3, 1, 32, 48), 30), ((3, 9, 32, 32), 31), ((3, 5, 48, 32), 35)])
+def test_encoder_orchestration_matches_the_oracle(encoder, shape, seed):
+    """Image (one chunk), 9 frames (chunks of 1, 4, 4: both temporal down-samplings with their caches), 5 frames."""
+    enc, w16 = encoder
+    video = torch.tanh(latents(shape, seed)).to(BF)
+    got = enc.encode([video])
+    with torch.no_grad():
+        want = o.encode(w16, o.TINY, [video.float()])
+    assert got.shape == want.shape and got.dtype == BF
+    print("encode", shape, rel(got.float(), want))
+    assert rel(got.float(), want) < 2e-2, rel(got.float(), want)
+
+
+def test_tiled_encode_matches_the_oracle_and_the_reference_golden(encoder):
+    import os
+    enc, w16 = encoder
+    video = torch.tanh(latents((3, 1, 80, 96), 32)).to(BF)
+    got = enc.encode([video], tiled=True, tile_size=(3, 4), tile_stride=(2, 2))
+    with torch.no_grad():
+        want = o.encode(w16, o.TINY, [video.float()], tiled=True, tile_size=(3, 4), tile_stride=(2, 2))
+    assert rel(got.float(), want) < 2e-2
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "vae38.npz"))["encode_tiled"]
+    assert rel(got.float(), torch.from_numpy(gold)) < 3e-2
+
+
+@pytest.mark.parametrize("tiled", [False, True])
+def test_decoder_orchestration_matches_the_oracle(monkeypatch, tiled):
+    """The same emulated kernels under the decoder (whose real kernels are verified on the GPU): chunked decode of 3 latent
+    frames and a tiled decode — the emulations state the kernels' contracts, the host logic around them is what is tested."""
+    _emulated_ops(monkeypatch)
+    from fairygen_b200 import vae
+    dec = vae.VAE38Decoder(vae.VAE38Config(z_dim=o.TINY.z_dim, dec_dim=o.TINY.dec_dim), "cpu")
+    w = o.make_weights(o.TINY, seed=0)
+    dec.load_state_dict(w)
+    w16 = {k: v.to(BF).float() for k, v in w.items()}
+    z = (latents((1, 8, 2, 5, 5), 3) if tiled else latents((1, 8, 3, 3, 4), 1)).to(BF)
+    kw = dict(tiled=True, tile_size=(3, 3), tile_stride=(2, 2)) if tiled else {}
+    got = dec.decode(z, **kw)
+    with torch.no_grad():
+        want = o.decode(w16, o.TINY, z.float(), **kw)
+    assert got.shape == want.shape
+    assert rel(got.float(), want) < 2.5e-2, rel(got.float(), want)
+
+
+def test_encoder_rejects_bad_input(encoder):
+    enc, _ = encoder
+    with pytest.raises(ValueError):
+        enc.encode([torch.zeros(3, 2, 32, 32)])          # 2 frames: not 1 + 4k
+    with pytest.raises(ValueError):
+        enc.encode([torch.zeros(3, 1, 24, 32)])          # height not a multiple of 16
+    with pytest.raises(ValueError):
+        enc.encode([torch.zeros(4, 1, 32, 32)])
