@@ -234,8 +234,7 @@ __global__ void vae_blend_finish_kernel(float* __restrict__ values, const float*
 }
 
 // =============================================================================================
-// Encoder side (VideoVAE38_.encode, VAE:1298-1323; Encoder3d_38, VAE:620-733) — kernels written against the pinned oracle
-// (oracle/vae38_oracle.py::encode); see DESIGN §7c for their verification status.
+// Encoder side (VideoVAE38_.encode, VAE:1298-1323; Encoder3d_38, VAE:620-733).
 // =============================================================================================
 
 // patchify 'b c f (h q) (w r) -> b (c r q) f h w' (VAE:199-211): video bf16 [3][T][H][W] -> grid [T][H/2+2][W/2+2][Cp], channel

@@ -694,7 +694,7 @@ def vae_blend_finish(values, weight):
                "fgb_vae_blend_finish")
 
 
-# ---- VAE38 encoder side (not yet run on a GPU at the end of round 1) ----
+# ---- VAE38 encoder side ----
 def vae_patchify_rows(video, grid, cp: int):
     """video bf16 [3, T, H, W] -> interior of grid rows [T*(H/2+2)*(W/2+2), cp]."""
     C, T, H, W = video.shape

@@ -1,9 +1,5 @@
 """Wan2.2 VAE38 encoder on the sm_100a kernels — the encode half of ``pipe.vae``.
 
-STATUS: written against the pinned oracle (``oracle/vae38_oracle.py::encode``) at the end of round 1, when the round's GPU
-budget was spent: it compiles and its host logic is covered on the CPU, but it has NOT been run on a GPU yet.  Its GPU tests
-(``tests/test_vae_encode_gpu.py``) are skipped unless ``FGB_UNVERIFIED=1``; nothing else in the package imports this module.
-
 Reference: ``WanVideoVAE38.encode`` (models/wan_video_vae.py:1218-1232, VAE) -> ``VideoVAE38_.encode`` (VAE:1298-1323) ->
 ``Encoder3d_38`` (VAE:620-733): patchify, the first frame alone and then chunks of 4 frames through the causal encoder with
 its feature cache, the 1x1x1 ``conv1``, the mean half of the channels, latent normalisation; used for the first-frame

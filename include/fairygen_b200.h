@@ -373,8 +373,7 @@ int fgb_vae_unpatchify(fgb_ctx* ctx, const void* head, int32_t frames, int32_t h
 /* values = clamp(values / weight, -1, 1) (VAE:1151-1152); weight has one plane, values `channels` planes. */
 int fgb_vae_blend_finish(fgb_ctx* ctx, void* values_f32, const void* weight_f32, int64_t plane, int32_t channels, void* stream);
 
-/* --- VAE38 encoder side (VideoVAE38_.encode, VAE:1298-1323; Encoder3d_38, VAE:620-733). Written against the pinned oracle; not yet
- * run on a GPU at the end of round 1 — the GPU tests are gated behind FGB_UNVERIFIED=1 until they have been. --- */
+/* --- VAE38 encoder side (VideoVAE38_.encode, VAE:1298-1323; Encoder3d_38, VAE:620-733) --- */
 
 /* patchify 'b c f (h q) (w r) -> b (c r q) f h w' (VAE:199-211): video bf16 [3, frames, h, w] -> grid [frames, h/2, w/2, cp]. */
 int fgb_vae_patchify_rows(fgb_ctx* ctx, const void* video, void* grid, int32_t frames, int32_t h, int32_t w, int32_t cp, void* stream);

@@ -1,8 +1,5 @@
-"""VAE38 encoder on the B200: the encoder-side kernels against plain torch, and the encoder against the pinned oracle.
-
-GATED: this file was written at the end of round 1 after the round's GPU budget was spent — the code under test
-(fairygen_b200/vae_encode.py and the fgb_vae_{patchify_rows, space_to_depth, avg_down_add, latent_out, blend_divide} kernels)
-has not been run on a GPU yet. Set FGB_UNVERIFIED=1 to run it; remove the gate once it has passed."""
+"""VAE38 encoder on the B200: the encoder-side kernels (patchify, space-to-depth stride-2 convolution, AvgDown3D, latent output)
+against plain torch, and the encoder (image, 9-frame clip, tiled) against the pinned oracle and the reference's stored outputs."""
 import os
 
 import numpy as np
@@ -12,8 +9,7 @@ import torch.nn.functional as F
 
 from conftest import rel_l2
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("FGB_UNVERIFIED") != "1",
-                                                  reason="encoder path not yet verified on a GPU (set FGB_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "vae38.npz")
 
