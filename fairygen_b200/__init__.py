@@ -4,7 +4,7 @@ Wan2.2-TI2V-5B DiT denoising step behind the reference's ``pipe.model_fn`` surfa
 Only what the path needs lives here: ``csrc/`` (CUDA kernels + C ABI), the ctypes binding, the
 engine that mirrors ``model_fn_wan_video``, the fused flow-match scheduler, the denoise loop, the
 Ulysses / CFG / shot parallel layout (NVLink peer-store exchange), the stage-1/2 LoRA trainer
-(hand-written backward), LoRA checkpoint formats, checkpoint detection / loading the umT5 text encoder and the VAE38 decoder.  There is no CPU
+(hand-written backward), LoRA checkpoint formats, checkpoint detection / loading the umT5 text encoder and the VAE38 decoder / encoder.  There is no CPU
 or PyTorch fallback.
 """
 from .config import TI2V_5B, WanDiTConfig, counted_flops  # noqa: F401
@@ -34,7 +34,10 @@ def __getattr__(name):  # lazy: importing the package must not require CUDA or t
     if name in ("VAE38Decoder", "VAE38Config", "VAE38"):
         from . import vae
         return getattr(vae, name)
-    if name in ("lora_io", "cfg_parallel", "training", "text_encoder", "vae"):
+    if name == "VAE38Encoder":
+        from .vae_encode import VAE38Encoder
+        return VAE38Encoder
+    if name in ("lora_io", "cfg_parallel", "training", "text_encoder", "vae", "vae_encode"):
         import importlib
         return importlib.import_module("." + name, __name__)
     if name == "SequenceParallel":

@@ -283,3 +283,15 @@ class VAE38Encoder(VAE38Decoder):
                 self._encode_window(v, values, None, 0, 0, (True, True, True, True), (1, 1))
             outs.append(values.to(dtype))
         return torch.stack(outs)
+
+
+def install(pipe) -> VAE38Encoder:
+    """Route ``pipe.vae.encode`` (first-frame conditioning PIPE:490-497, training videos PIPE:374-379) through a VAE38Encoder
+    holding the weights of the loaded reference VAE (``vae.install`` does the same for ``decode``)."""
+    ref = getattr(pipe, "vae", None)
+    if ref is None or not hasattr(ref, "model") or getattr(ref, "z_dim", None) != 48:
+        raise ValueError("pipe.vae must be a loaded WanVideoVAE38")
+    enc = VAE38Encoder(VAE38, getattr(pipe, "device", "cuda"), enc_dim=ref.model.dim)
+    enc.load_state_dict(ref.state_dict())
+    ref.encode = enc.encode
+    return enc

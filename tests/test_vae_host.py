@@ -204,6 +204,47 @@ def test_decoder_orchestration_matches_the_oracle(monkeypatch, tiled):
     assert rel(got.float(), want) < 2.5e-2, rel(got.float(), want)
 
 
+def test_install_routes_pipe_vae_encode_and_decode(monkeypatch):
+    """vae.install / vae_encode.install on a stand-in for the loaded reference VAE (its `model`, `z_dim`, `state_dict()`)."""
+    _emulated_ops(monkeypatch)
+    from fairygen_b200 import vae, vae_encode
+    small = vae.VAE38Config(z_dim=48, dec_dim=16)
+    monkeypatch.setattr(vae, "VAE38", small)
+    monkeypatch.setattr(vae_encode, "VAE38", small)
+    ocfg = o.VAE38Config(z_dim=48, dec_dim=16, enc_dim=16)
+    sd = {"model." + k: v for k, v in {**o.make_weights(ocfg, seed=0), **o.make_enc_weights(ocfg, seed=0)}.items()}
+
+    class Model:
+        dim = 16
+
+    class RefVAE(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model, self.z_dim = Model(), 48
+
+        def state_dict(self, *a, **k):
+            return dict(sd)
+
+    class Pipe:
+        device = "cpu"
+        vae = RefVAE()
+
+    pipe = Pipe()
+    dec, enc = vae.install(pipe), vae_encode.install(pipe)
+    assert pipe.vae.decode == dec.decode and pipe.vae.encode == enc.encode
+    image = torch.tanh(latents((3, 1, 32, 32), 40)).to(BF)
+    z = pipe.vae.encode([image], device="cpu")                                   # PIPE:495
+    assert z.shape == (1, 48, 1, 2, 2)
+    video = pipe.vae.decode(z, device="cpu", tiled=False)                        # PIPE:323
+    assert video.shape == (1, 3, 1, 32, 32) and float(video.float().abs().max()) <= 1
+    with torch.no_grad():
+        w16 = {k[len("model."):]: v.to(BF).float() for k, v in sd.items()}
+        assert rel(z.float(), o.encode(w16, ocfg, [image.float()])) < 2e-2
+    pipe.vae = None
+    with pytest.raises(ValueError):
+        vae_encode.install(pipe)
+
+
 def test_encoder_rejects_bad_input(encoder):
     enc, _ = encoder
     with pytest.raises(ValueError):
