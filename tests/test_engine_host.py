@@ -1,0 +1,171 @@
+"""Host logic of the DiT engine (fairygen_b200/engine.py) on the CPU: every kernel is replaced by a plain-torch statement of its
+contract (include/fairygen_b200.h), and the orchestration — two-row timestep tables, which rows take the t = 0 modulation,
+fused q|k|v weights, RoPE table / grid / token offset, context K|V cache, patchify / unpatchify layouts — must reproduce the
+pinned oracle and the reference's stored forwards.  The kernels themselves are covered by the `-m gpu` tests."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import wan_dit_oracle as o
+
+BF = torch.bfloat16
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_forward.npz"))
+
+
+def _emulated_ops(monkeypatch):
+    from fairygen_b200 import ops
+
+    def ln(x, eps):
+        xf = x.float()
+        return (xf - xf.mean(-1, keepdim=True)) * torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + eps)
+
+    def gemm(a, w, bias, out, epilogue=ops.EPI_BIAS, gate0=None, gate1=None, rows_gate0=0, a2=None, w2=None):
+        acc = a.float() @ w.float().T
+        if a2 is not None:
+            acc = acc + a2.float() @ w2.float().T
+        y = (acc + (0 if bias is None else bias.float())).to(BF).float()
+        if epilogue == ops.EPI_BIAS_GELU_TANH:
+            y = F.gelu(y, approximate="tanh")
+        elif epilogue == ops.EPI_GATED_RESIDUAL:
+            first = (torch.arange(a.shape[0]) < rows_gate0)[:, None]
+            gate = torch.where(first, gate0.float()[None], gate1.float()[None])
+            y = out.float() + (gate * y).to(BF).float()
+        elif epilogue == ops.EPI_RESIDUAL:
+            y = out.float() + y
+        out.copy_(y.to(BF))
+        return out
+
+    def sinusoidal_embedding(ts, out):
+        out.copy_(o.sinusoidal_embedding_1d(out.shape[1], ts).to(BF))
+        return out
+
+    def silu(x, out):
+        out.copy_(F.silu(x.float()).to(BF))
+        return out
+
+    def add_bcast(a, b, out, period=None):
+        rows, cols = a.shape
+        period = cols if period is None else period
+        out.copy_((a.float() + b.reshape(-1)[:period].float().repeat(cols // period)[None]).to(BF))
+        return out
+
+    def ln_modulate(x, out, eps, shift0, scale0, shift1, scale1, rows_mod0):
+        first = (torch.arange(x.shape[0]) < rows_mod0)[:, None]
+        shift = torch.where(first, shift0.float()[None], shift1.float()[None])
+        scale = torch.where(first, scale0.float()[None], scale1.float()[None])
+        out.copy_((ln(x, eps).to(BF).float() * (1 + scale) + shift).to(BF))
+        return out
+
+    def ln_affine(x, out, eps, weight, bias):
+        out.copy_((ln(x, eps) * weight.float() + bias.float()).to(BF))
+        return out
+
+    def rmsnorm_rope(x, eps, weight, rope_tab=None, grid=(1, 1, 1), token_offset=0):
+        xf = x.float()
+        y = ((xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(BF).float() * weight.float()).to(BF).float()
+        if rope_tab is not None:
+            f, h, w = grid
+            rows, dim = x.shape
+            t = torch.arange(rows) + token_offset
+            pos = torch.stack([t // (h * w), (t // w) % h, t % w], 1)                         # [rows, 3]
+            lanes = torch.tensor([0] * 22 + [1] * 21 + [2] * 21)                              # frame / row / column lanes of a head
+            tab = rope_tab[pos[:, lanes], torch.arange(64)]                                    # [rows, 64, 2] (cos, sin)
+            z = y.view(rows, dim // 128, 64, 2)
+            re = z[..., 0] * tab[:, None, :, 0] - z[..., 1] * tab[:, None, :, 1]
+            im = z[..., 0] * tab[:, None, :, 1] + z[..., 1] * tab[:, None, :, 0]
+            y = torch.stack([re, im], -1).reshape(rows, dim)
+        x.copy_(y.to(BF))
+        return x
+
+    def head_norm_max(k, out_f32, heads):
+        out_f32.copy_(k.float().view(k.shape[0], heads, 128).pow(2).sum(-1).max(0).values)
+        return out_f32
+
+    def attention(q, k, v, out, heads, scale=None, lse=None, kmax2=None):
+        qf, kf, vf = (t.float().view(t.shape[0], heads, 128).transpose(0, 1) for t in (q, k, v))
+        p = torch.softmax(qf @ kf.transpose(1, 2) / 128 ** 0.5, -1)
+        out.copy_((p @ vf).transpose(0, 1).reshape(q.shape[0], heads * 128).to(BF))
+        return out
+
+    def patchify_rows(latents, rows_out, grid, token_offset=0):
+        C = latents.shape[0]
+        f, h, w = grid
+        x = latents.view(C, f, h, 2, w, 2).permute(1, 2, 4, 0, 3, 5).reshape(f * h * w, C * 4)     # row[t, c*4 + y*2 + z]
+        rows_out.zero_()
+        n = max(0, min(rows_out.shape[0], f * h * w - token_offset))
+        rows_out[:n, :C * 4] = x[token_offset:token_offset + n]
+        return rows_out
+
+    def unpatchify(head_rows, out, grid):
+        C = out.shape[0]
+        f, h, w = grid
+        x = head_rows[:f * h * w, :4 * C].view(f, h, w, 2, 2, C)                                   # rows[t, y*2C + z*C + c]
+        out.copy_(x.permute(5, 0, 1, 3, 2, 4).reshape(C, f, 2 * h, 2 * w))
+        return out
+
+    def cfg_fm_step(latents, noise_pos, noise_neg, first_frame, cfg_scale, sigma_delta):
+        n = noise_pos if noise_neg is None else (noise_neg.float() + (cfg_scale * (noise_pos.float() - noise_neg.float()).to(BF).float()).to(BF).float()).to(BF)
+        latents.copy_((latents.float() + (n.float().view_as(latents) * sigma_delta).to(BF).float()).to(BF))
+        if first_frame is not None:
+            latents[..., 0:1, :, :] = first_frame.view(latents[..., 0:1, :, :].shape)
+        return latents
+
+    for name, fn in list(locals().items()):
+        if callable(fn) and name != "ln" and hasattr(ops, name):
+            monkeypatch.setattr(ops, name, fn)
+    monkeypatch.setattr(ops, "context", lambda device: None)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+@pytest.fixture()
+def engine(monkeypatch):
+    _emulated_ops(monkeypatch)
+    import fairygen_b200 as fg
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    w = o.make_weights(o.TINY, seed=0)
+    from fairygen_b200 import ops
+    eng = fg.WanDiTEngine.__new__(fg.WanDiTEngine)        # the constructor refuses non-CUDA devices (no CPU path in the product);
+    eng.cfg, eng.device, eng.ctx, eng.sp = cfg, torch.device("cpu"), None, None     # the test sets up the same fields by hand
+    eng.rope_tab = torch.from_numpy(ops.rope_table(cfg.head_dim))
+    eng.blocks, eng._ws, eng._ctx_cache, eng._ctx_cache_order = [], {}, {}, []
+    eng.kernel_launches, eng.timer, eng.loaded = 0, None, False
+    eng.load_state_dict(w)
+    return eng, {k: v.to(BF).float() for k, v in w.items()}
+
+
+@pytest.mark.parametrize("ts_val,fused,key", [(900.0, True, "fused_t900"), (37.0, True, "fused_t37"), (900.0, False, "plain_t900")])
+def test_forward_orchestration_matches_oracle_and_reference(engine, ts_val, fused, key):
+    eng, w16 = engine
+    lat, z0, cp, cn = o.make_inputs(o.TINY, (1, 48, 3, 8, 8), text_len=32, live_text=8)
+    ctx = cp if fused else cn
+    ts = torch.tensor([ts_val])
+    out = eng.forward(lat.to(BF), ts, ctx.to(BF), fused)
+    with torch.no_grad():
+        want = o.dit_forward(w16, o.TINY, lat.to(BF).float(), ts, ctx.to(BF).float(), fused)
+    assert out.shape == lat.shape
+    assert rel(out.float(), want) < 1e-2, rel(out.float(), want)
+    assert rel(out.float(), torch.from_numpy(GOLD[key])) < 1.5e-2            # the reference model's own fp32 output
+    again = eng.forward(lat.to(BF), ts, ctx.to(BF), fused)                    # second call: context K|V from the cache
+    assert torch.equal(out, again)
+
+
+def test_ragged_grid(engine):
+    eng, w16 = engine
+    lat, _, cp, _ = o.make_inputs(o.TINY, (1, 48, 2, 6, 10), text_len=24, live_text=8)
+    ts = torch.tensor([500.0])
+    out = eng.forward(lat.to(BF), ts, cp.to(BF), True)
+    with torch.no_grad():
+        want = o.dit_forward(w16, o.TINY, lat.to(BF).float(), ts, cp.to(BF).float(), True)
+    assert rel(out.float(), want) < 1e-2
+
+
+def test_the_real_constructor_still_refuses_the_cpu():
+    import fairygen_b200 as fg
+    with pytest.raises(RuntimeError):
+        fg.WanDiTEngine(fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2), "cpu")
