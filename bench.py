@@ -62,7 +62,6 @@ def cpu_sample(steps: int, warmup: int, sample_tokens: int = 4096):
     video tokens with all host threads, separately for self-attention (cost ~ S^2) and everything else
     (cost ~ S), and extrapolate both to S = 27 280, x30 blocks, x2 forwards per CFG step."""
     import torch
-    import torch.nn.functional as F
 
     from oracle import wan_dit_oracle as o
 

@@ -15,7 +15,7 @@ What is restructured relative to the reference (results identical up to bf16 rou
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 import torch
 

@@ -21,7 +21,7 @@ import torch
 
 from . import ops
 from .ops import BF16, EPI_BIAS
-from .vae import MEAN38, STD38, VAE38, VAE38Config, VAE38Decoder, _c64, _Conv, _Res, tile_tasks
+from .vae import VAE38, VAE38Config, VAE38Decoder, _c64, _Conv, _Res, tile_tasks
 
 ENC_DIM = 160                                   # `dim` of WanVideoVAE38 (VAE:1356)
 TEMPERAL_DOWNSAMPLE = (False, True, True)       # VAE:1278

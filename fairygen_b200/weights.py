@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import glob
 import hashlib
-import os
 from typing import Dict, Iterable, List, Sequence, Union
 
 import torch

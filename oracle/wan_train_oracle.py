@@ -19,7 +19,6 @@ that executes TMOD:317-352 literally and storing the real model's loss / B2 grad
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional
 
 import torch
