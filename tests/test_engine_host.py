@@ -169,3 +169,23 @@ def test_the_real_constructor_still_refuses_the_cpu():
     import fairygen_b200 as fg
     with pytest.raises(RuntimeError):
         fg.WanDiTEngine(fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2), "cpu")
+
+
+def test_four_step_cfg_denoise_matches_the_reference_loop(engine, monkeypatch):
+    """WanDenoiser (2 forwards + the fused CFG / Euler / first-frame step per iteration, PIPE:285-309) on the emulated kernels
+    against the reference's own 4-step loop (tests/golden/denoise.npz)."""
+    import fairygen_b200 as fg
+    from fairygen_b200 import ops, scheduler
+
+    def step_fused(self, latents, noise_pos, noise_neg, cfg_scale, index, first_frame_latents=None, to_final=False):
+        # FlowMatchScheduler.step_fused without its CUDA-only guard (tests/test_host_logic.py checks the guard itself)
+        ops.cfg_fm_step(latents, noise_pos, noise_neg, first_frame_latents, float(cfg_scale), self.sigma_delta(index, to_final))
+        return latents
+
+    monkeypatch.setattr(scheduler.FlowMatchScheduler, "step_fused", step_fused)
+    eng, _ = engine
+    lat, z0, cp, cn = o.make_inputs(o.TINY, (1, 48, 3, 8, 8), text_len=32, live_text=8)
+    out = fg.WanDenoiser(eng, num_inference_steps=4, cfg_scale=5.0, sigma_shift=5.0)(lat, cp, cn, z0)
+    gold = torch.from_numpy(np.load(os.path.join(os.path.dirname(__file__), "golden", "denoise.npz"))["final"])
+    assert torch.equal(out[:, :, 0:1], z0.to(BF))
+    assert rel(out.float(), gold) < 3e-2, rel(out.float(), gold)            # north star: <= 3e-2 after a schedule
