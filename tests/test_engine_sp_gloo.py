@@ -1,0 +1,81 @@
+"""world_size-2 CPU test (gloo) of the WHOLE DiT forward under Ulysses sequence parallelism: the product's engine, token
+partition, per-rank first-frame rows, RoPE token offsets, exchange (NCCL-variant plumbing: pack / all-to-all / unpack, here over
+gloo) and output gather run for real; the kernels are replaced by the plain-torch contract statements of
+tests/test_engine_host.py.  Each rank's gathered prediction must equal the single-process forward and the oracle, for an even
+split and for a ragged one (S = 105 tokens over 2 ranks: one padded row, masked as a key)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BF = torch.bfloat16
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class _Patch:
+    """The two methods of pytest's monkeypatch that _emulated_ops uses (the worker runs outside pytest)."""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+
+def _bare_engine(fg, ops, cfg, sp):
+    eng = fg.WanDiTEngine.__new__(fg.WanDiTEngine)          # the constructor refuses the CPU (tests/test_engine_host.py)
+    eng.cfg, eng.device, eng.ctx, eng.sp = cfg, torch.device("cpu"), None, sp
+    eng.rope_tab = torch.from_numpy(ops.rope_table(cfg.head_dim))
+    eng.blocks, eng._ws, eng._ctx_cache, eng._ctx_cache_order = [], {}, {}, []
+    eng.kernel_launches, eng.timer, eng.loaded = 0, None, False
+    return eng
+
+
+def _worker(rank, world, port, shape, out_dir):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fairygen_b200 as fg
+    from fairygen_b200 import ops
+    from oracle import wan_dit_oracle as o
+    from test_engine_host import _emulated_ops
+    from test_sp_gloo import _emulated_pack, _emulated_unpack
+
+    _emulated_ops(_Patch)
+    ops.sp_pack_heads, ops.sp_unpack_heads = _emulated_pack, _emulated_unpack
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    w = o.make_weights(o.TINY, seed=0)
+    lat, _, cp, _ = o.make_inputs(o.TINY, shape, text_len=32, live_text=8)
+    ts = torch.tensor([900.0])
+    single = _bare_engine(fg, ops, cfg, None)
+    single.load_state_dict(w)
+    ref = single.forward(lat.to(BF), ts, cp.to(BF), True)
+    par = _bare_engine(fg, ops, cfg, fg.SequenceParallel(exchange="nccl"))
+    par.load_state_dict(w)
+    out = par.forward(lat.to(BF), ts, cp.to(BF), True)
+    with torch.no_grad():
+        want = o.dit_forward({k: v.to(BF).float() for k, v in w.items()}, o.TINY, lat.to(BF).float(), ts, cp.to(BF).float(), True)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())  # noqa: E731
+    torch.save({"vs_single": rel(out.float(), ref.float()), "vs_oracle": rel(out.float(), want), "shape": tuple(out.shape)},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(1, 48, 4, 8, 8), (1, 48, 3, 10, 14)])       # S = 64 (32 + 32) and S = 105 (53 + 52 and a padded row)
+def test_sequence_parallel_forward_world2(tmp_path, shape):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert res["shape"] == shape
+        assert res["vs_single"] < 4e-3, res          # same contracts; only the summation order inside attention differs
+        assert res["vs_oracle"] < 1e-2, res
