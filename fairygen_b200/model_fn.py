@@ -128,10 +128,19 @@ def model_fn_wan_video(
     return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
 
-def install(pipe, fused_scheduler: bool = True):
+def install(pipe, fused_scheduler: bool = True, text_encoder: bool = False, vae: bool = False):
     """Point a reference ``WanVideoPipeline`` at the B200 path.  ``pipe.model_fn`` is the attribute the
     reference itself swaps behaviour through (wan_video.py:81); ``pipe.scheduler`` gets the fused
-    flow-match step with identical ``set_timesteps`` / ``step`` semantics (flow_match.py:29-39, 132-154)."""
+    flow-match step with identical ``set_timesteps`` / ``step`` semantics (flow_match.py:29-39, 132-154).
+    text_encoder / vae = True additionally swap ``pipe.text_encoder`` (text_encoder.install) and route
+    ``pipe.vae.decode`` / ``pipe.vae.encode`` (vae.install, vae_encode.install) through the kernels."""
+    if text_encoder:
+        from . import text_encoder as _te
+        _te.install(pipe)
+    if vae:
+        from . import vae as _vae, vae_encode as _vae_encode
+        _vae.install(pipe)
+        _vae_encode.install(pipe)
     pipe.model_fn = model_fn_wan_video
     if fused_scheduler:
         from .scheduler import FlowMatchScheduler
