@@ -79,3 +79,59 @@ def test_sequence_parallel_forward_world2(tmp_path, shape):
         assert res["shape"] == shape
         assert res["vs_single"] < 4e-3, res          # same contracts; only the summation order inside attention differs
         assert res["vs_oracle"] < 1e-2, res
+
+
+def _layout_worker(rank, world, port, shots, cfg_ways, sp_ways, out_dir):
+    """Shot x CFG-pair x Ulysses layout with the REAL engine and denoiser on 4 gloo processes: a 2-step CFG denoise of every
+    shot must equal the sequential single-process loop (PIPE:285-309; batch_inference.py:45-56)."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fairygen_b200 as fg
+    from fairygen_b200 import ops, scheduler
+    from fairygen_b200.cfg_parallel import Layout, ParallelContext, denoise_shots
+    from oracle import wan_dit_oracle as o
+    from test_engine_host import _emulated_ops
+    from test_sp_gloo import _emulated_pack, _emulated_unpack
+
+    _emulated_ops(_Patch)
+    ops.sp_pack_heads, ops.sp_unpack_heads = _emulated_pack, _emulated_unpack
+
+    def step_fused(self, latents, noise_pos, noise_neg, cfg_scale, index, first_frame_latents=None, to_final=False):
+        ops.cfg_fm_step(latents, noise_pos, noise_neg, first_frame_latents, float(cfg_scale), self.sigma_delta(index, to_final))
+        return latents
+
+    scheduler.FlowMatchScheduler.step_fused = step_fused          # without the CUDA-only guard (tests/test_host_logic.py checks it)
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    w = o.make_weights(o.TINY, seed=0)
+    data = []
+    for i in range(2):
+        lat, z0, cp, cn = o.make_inputs(o.TINY, (1, 48, 2, 6, 10), text_len=24, live_text=8)
+        g = torch.Generator().manual_seed(50 + i)
+        data.append(dict(latents=lat + 0.1 * torch.randn(lat.shape, generator=g), context_pos=cp, context_neg=cn, first_frame_latents=z0))
+    ctx = ParallelContext(Layout(world, shots, cfg_ways, sp_ways), exchange="nccl")
+    eng = _bare_engine(fg, ops, cfg, ctx.sequence_parallel())
+    eng.load_state_dict(w)
+    done = denoise_shots(ctx, lambda: fg.WanDenoiser(eng, 2, cfg_scale=5.0, sigma_shift=5.0), data)
+    single = _bare_engine(fg, ops, cfg, None)
+    single.load_state_dict(w)
+    errs = []
+    for i, lat in done:
+        s = data[i]
+        ref = fg.WanDenoiser(single, 2, cfg_scale=5.0, sigma_shift=5.0)(s["latents"], s["context_pos"], s["context_neg"], s["first_frame_latents"])
+        errs.append(float((lat.double() - ref.double()).norm() / ref.double().norm()))
+    torch.save({"shots": [i for i, _ in done], "errs": errs}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shots,cfg_ways,sp_ways", [(1, 2, 2), (2, 2, 1)])
+def test_shot_cfg_sp_layout_world4(tmp_path, shots, cfg_ways, sp_ways):
+    world = 4
+    mp.spawn(_layout_worker, args=(world, _free_port(), shots, cfg_ways, sp_ways, str(tmp_path)), nprocs=world, join=True)
+    seen = set()
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        seen.update(res["shots"])
+        assert res["shots"] and all(e < 5e-3 for e in res["errs"]), res
+    assert seen == {0, 1}
