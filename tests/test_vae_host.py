@@ -204,6 +204,22 @@ def test_decoder_orchestration_matches_the_oracle(monkeypatch, tiled):
     assert rel(got.float(), want) < 2.5e-2, rel(got.float(), want)
 
 
+def test_full_width_encoder_orchestration(monkeypatch):
+    """The production widths (160 / 320 / 640 channels: 160 is NOT a multiple of the 64-channel grid padding, so every grid of
+    the first stages carries zero padding channels; 96 output channels of the head; 48 latent channels) on one small image."""
+    _emulated_ops(monkeypatch)
+    from fairygen_b200 import vae, vae_encode
+    enc = vae_encode.VAE38Encoder(vae.VAE38, "cpu")
+    w = o.make_enc_weights(o.VAE38, seed=1)
+    enc.load_state_dict(w)
+    image = torch.tanh(latents((3, 1, 32, 32), 41)).to(BF)
+    got = enc.encode([image])
+    with torch.no_grad():
+        want = o.encode({k: v.to(BF).float() for k, v in w.items()}, o.VAE38, [image.float()])
+    assert got.shape == (1, 48, 1, 2, 2)
+    assert rel(got.float(), want) < 2e-2, rel(got.float(), want)
+
+
 def test_install_routes_pipe_vae_encode_and_decode(monkeypatch):
     """vae.install / vae_encode.install on a stand-in for the loaded reference VAE (its `model`, `z_dim`, `state_dict()`)."""
     _emulated_ops(monkeypatch)
