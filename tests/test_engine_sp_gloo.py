@@ -44,6 +44,7 @@ def _worker(rank, world, port, shape, out_dir):
     sys.path.insert(0, os.path.join(REPO, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)      # several processes of many tiny CPU ops: the default thread count oversubscribes the cores badly
     import fairygen_b200 as fg
     from fairygen_b200 import ops
     from oracle import wan_dit_oracle as o
@@ -88,6 +89,7 @@ def _layout_worker(rank, world, port, shots, cfg_ways, sp_ways, out_dir):
     sys.path.insert(0, os.path.join(REPO, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)      # several processes of many tiny CPU ops: the default thread count oversubscribes the cores badly
     import fairygen_b200 as fg
     from fairygen_b200 import ops, scheduler
     from fairygen_b200.cfg_parallel import Layout, ParallelContext, denoise_shots
@@ -135,3 +137,31 @@ def test_shot_cfg_sp_layout_world4(tmp_path, shots, cfg_ways, sp_ways):
         seen.update(res["shots"])
         assert res["shots"] and all(e < 5e-3 for e in res["errs"]), res
     assert seen == {0, 1}
+
+
+def _vae_worker(rank, world, port, out_dir):
+    """VAE38 tiled decode with the windows spread over 2 gloo ranks (assign_windows + one sum all-reduce before the blend)."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)      # several processes of many tiny CPU ops: the default thread count oversubscribes the cores badly
+    from fairygen_b200 import vae
+    from oracle import vae38_oracle as o
+    from test_vae_host import _emulated_ops
+
+    _emulated_ops(_Patch)
+    dec = vae.VAE38Decoder(vae.VAE38Config(z_dim=o.TINY.z_dim, dec_dim=o.TINY.dec_dim), "cpu")
+    dec.load_state_dict(o.make_weights(o.TINY, seed=0))
+    z = torch.randn((1, o.TINY.z_dim, 2, 6, 7), generator=torch.Generator().manual_seed(3)).to(BF)
+    kw = dict(tiled=True, tile_size=(3, 4), tile_stride=(2, 3))
+    alone = dec.decode(z, **kw)
+    shared = dec.decode(z, group=dist.group.WORLD, **kw)
+    torch.save({"err": float((shared.float() - alone.float()).abs().max())}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_vae_windows_over_two_ranks(tmp_path):
+    mp.spawn(_vae_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert torch.load(os.path.join(tmp_path, f"r{r}.pt"))["err"] < 1e-2
