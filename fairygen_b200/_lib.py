@@ -30,6 +30,7 @@ SIGNATURES = {
     "fgb_attn_fwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P]),
     "fgb_attn_fwd_ex": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _I64, _P, _I64, _P]),
     "fgb_head_norm_max": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
+    "fgb_attn_set_stats": (ctypes.c_int, [_P, _P]),
     "fgb_attn_fwd_bounded": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _I64, _P, _I64,
                                             ctypes.POINTER(c_void_p), _I32, _I32, _I32, _P]),
     "fgb_attn_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64,

@@ -127,6 +127,8 @@ class ParallelContext:
             npos = engine.forward(latents, timestep, context_pos, fuse)
             nneg = engine.forward(latents, timestep, context_neg, fuse) if context_neg is not None else None
             return npos, nneg
+        if context_neg is None:
+            raise ValueError("CFG-parallel forward_pair needs a negative context (cfg_scale != 1 with a CFG pair layout)")
         mine = engine.forward(latents, timestep, context_pos if self.cfg_rank == 0 else context_neg, fuse)
         mine = mine.contiguous()
         n = mine.shape[0]

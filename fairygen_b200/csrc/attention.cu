@@ -193,10 +193,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     // One pass over this thread's 64 scores, 32 at a time (the second TMEM load is in flight while the first chunk is
     // processed): tracks the maximum and, if EXPS, writes P = 2^(s*scale - m_used) as packed bf16 into pk and
-    // returns the sum.
-    auto sweep = [&](auto exps_tag, auto max_tag, uint32_t t_s, float m_used, float& row_max, uint32_t (&pk)[32]) -> float {
+    // returns the sum. KIND selects how the exponentials are made (ExpMixed / ExpMixedClamp / ExpMufu).
+    auto sweep = [&](auto exps_tag, auto max_tag, auto kind_tag, uint32_t t_s, float m_used, float& row_max, uint32_t (&pk)[32]) -> float {
       constexpr bool EXPS = decltype(exps_tag)::value;
       constexpr bool MAXV = decltype(max_tag)::value;
+      constexpr int KIND = decltype(kind_tag)::value;
       uint32_t buf[2][32];
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
@@ -219,8 +220,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             float p0, p1;
             if (EMU == 7) {          // DEBUG (FGB_ATTN_EMU=7): no exponential at all — isolates the MUFU cost
               unpack2(x2, p0, p1);
-            } else if ((e & 7) < kFrac) {
-              exp2_emulated(x2, p0, p1);
+            } else if (KIND != ExpMufu::value && (e & 7) < kFrac) {
+              exp2_emulated<KIND == ExpMixedClamp::value>(x2, p0, p1);
             } else {
               float x0, x1;
               unpack2(x2, x0, x1);
@@ -239,11 +240,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       return (a0 + a1) + (b0 + b1);
     };
 
-    // ---- bounded-score mode: fixed per-row reference B_i = ||q_i||·kmax·scale·log2e instead of a running maximum
-    bool bounded = false;
+    // Last, partial KV tile (rare path, kept out of line): overwrite the scores of keys that do not exist with -inf.
+    auto mask_partial = [&](uint32_t t_s, int valid) {
+#pragma unroll 1
+      for (int c = (valid < 0 ? 0 : valid) >> 5; c < 2; ++c) {
+        uint32_t fix[32];
+        tmem_ld32(t_s + c * 32, fix);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c * 32 + e >= valid) fix[e] = 0xff800000u;
+        tmem_st32(t_s + c * 32, fix);
+      }
+      tmem_st_wait();
+    };
+    // One decision per CTA (the two threads of a row must agree; per CTA keeps it simple): AND of `ok` over the 256 softmax threads.
+    volatile int* vote = reinterpret_cast<volatile int*>(bars + 16);
+    auto vote_all = [&](int slot, bool ok) -> bool {
+      if (threadIdx.x == 0) vote[slot] = 1;
+      asm volatile("bar.sync 9, 256;" ::: "memory");
+      if (!ok) vote[slot] = 0;
+      asm volatile("bar.sync 9, 256;" ::: "memory");
+      return vote[slot] != 0;
+    };
+
+    // ---- bounded-score softmax: a fixed per-row reference instead of a running maximum (AttnParams::kmax)
+    int mode = 2;   // 0: reference from the Cauchy-Schwarz bound, 1: anchored on the first tile's maximum, 2: running maximum
     if (p.kmax != nullptr) {
       mbar_wait(q_full, 0);
       const float kmax2 = __ldg(p.kmax + head);   // max_j ||k_j||^2 of this head (fgb_head_norm_max)
+      float bnd[2];
       bool ok = true;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -260,18 +286,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int e = 0; e < 4; ++e) ss += bf16_lo(w[e]) * bf16_lo(w[e]) + bf16_hi(w[e]) * bf16_hi(w[e]);
           }
         }
-        const float bound = sqrtf(ss * kmax2) * p.scale_log2 * 1.0001f;
-        ok = ok && (bound <= 60.0f);
-        m[i] = bound;
+        bnd[i] = sqrtf(ss * kmax2) * p.scale_log2 * 1.0001f;
+        ok = ok && (bnd[i] <= kBoundFixedMax);   // NaN bounds fail the test and end up on the running-max path
+        m[i] = bnd[i] <= kBoundDirect ? bnd[i] : kWindowLo - bnd[i];
       }
-      // one decision per CTA (the two warpgroups of a row must agree; per-CTA keeps it simple): vote through smem
-      if (threadIdx.x == 0) xchg[0] = 1.0f;
-      asm volatile("bar.sync 9, 256;" ::: "memory");
-      if (!ok) xchg[0] = 0.0f;
-      asm volatile("bar.sync 9, 256;" ::: "memory");
-      bounded = xchg[0] != 0.0f;
-      asm volatile("bar.sync 9, 256;" ::: "memory");   // xchg is reused by swap_rows
-      if (!bounded) m[0] = m[1] = -INFINITY;
+      if (vote_all(0, ok)) {
+        mode = 0;
+      } else {
+        // the Cauchy-Schwarz bound alone leaves no safe window: anchor it on the exact maximum of the first KV tile
+        ok = true;
+#pragma unroll 1
+        for (int i = 0; i < 2; ++i) {
+          const uint32_t t_s = tmem_base + lane_bits + i * 128 + wg * 64;
+          mbar_wait(&s_full[i], 0);
+          tc_fence_after();
+          const int valid = p.s_kv - kv_lo * kTile - wg * 64;
+          if (valid < 64) mask_partial(t_s, valid);
+          uint32_t pk[32];
+          float row_max;
+          sweep(TagFalse{}, TagTrue{}, ExpMufu{}, t_s, 0.f, row_max, pk);
+          const float m0 = fmaxf(row_max, swap_rows(row_max)) * p.scale_log2;
+          ok = ok && (bnd[i] - m0 <= kWindowLo + kWindowHi);
+          m[i] = fmaxf(bnd[i] - kWindowHi, fminf(bnd[i], m0 + 20.0f));
+        }
+        mode = vote_all(1, ok) ? 1 : 2;
+        if (mode == 2) m[0] = m[1] = -INFINITY;
+      }
+      if (p.stats != nullptr && threadIdx.x == 0) atomicAdd(p.stats + mode, 1);
     }
 
     for (int j = 0; j < n_kv; ++j) {
@@ -282,25 +323,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(&s_full[i], j & 1);
         tc_fence_after();
         const int valid = p.s_kv - (kv_lo + j) * kTile - wg * 64;  // keys of this half-tile that exist
-        if (valid < 64) {
-          // last, partial KV tile (rare path, kept out of line): overwrite the scores of keys that do not exist with -inf
-#pragma unroll 1
-          for (int c = (valid < 0 ? 0 : valid) >> 5; c < 2; ++c) {
-            uint32_t fix[32];
-            tmem_ld32(t_s + c * 32, fix);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (c * 32 + e >= valid) fix[e] = 0xff800000u;
-            tmem_st32(t_s + c * 32, fix);
-          }
-          tmem_st_wait();
-        }
+        const bool partial = valid < 64;
+        if (partial) mask_partial(t_s, valid);
         uint32_t pk[32];
         float row_max, sum;
         bool redo = false;
-        if (bounded) {             // no maximum, no exchange, no rescale: one pass of exponentials
-          l[i] += sweep(TagTrue{}, TagFalse{}, t_s, m[i], row_max, pk);
+        if (mode < 2) {            // no maximum, no exchange, no rescale: one pass of exponentials
+          if (partial) l[i] += sweep(TagTrue{}, TagFalse{}, ExpMufu{}, t_s, m[i], row_max, pk);
+          else if (mode == 0) l[i] += sweep(TagTrue{}, TagFalse{}, ExpMixed{}, t_s, m[i], row_max, pk);
+          else l[i] += sweep(TagTrue{}, TagFalse{}, ExpMixedClamp{}, t_s, m[i], row_max, pk);
           tmem_st32(t_s, pk);
           tmem_st_wait();
           tc_fence_before();
@@ -312,15 +343,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mbar_arrive(&p_ready[i]);
           continue;
         }
+        auto exp_sweep = [&]() -> float {   // exponentials against m[i] with the side maximum; masked tiles take the MUFU
+          return partial ? sweep(TagTrue{}, TagTrue{}, ExpMufu{}, t_s, m[i], row_max, pk)
+                         : sweep(TagTrue{}, TagTrue{}, ExpMixedClamp{}, t_s, m[i], row_max, pk);
+        };
         if (j == 0) {
-          sweep(TagFalse{}, TagTrue{}, t_s, 0.f, row_max, pk);  // exact maximum of the first tile
+          sweep(TagFalse{}, TagTrue{}, ExpMufu{}, t_s, 0.f, row_max, pk);  // exact maximum of the first tile
           row_max = fmaxf(row_max, swap_rows(row_max));
           m[i] = row_max * p.scale_log2;
           redo = true;
         } else {
           // Speculate that the running maximum has not grown by more than 2^8: exponentiate against the stale
           // maximum while the true maximum is computed on the side (MUFU and ALU pipes in parallel).
-          sum = sweep(TagTrue{}, TagTrue{}, t_s, m[i], row_max, pk);
+          sum = exp_sweep();
           if (kEmu != 9) row_max = fmaxf(row_max, swap_rows(row_max));   // maximum of the whole 128-key row
           const float m_new = kEmu == 9 ? m[i] : fmaxf(m[i], row_max * p.scale_log2);
           // both threads of a row see the same m_new, so both warps of the pair take the same branch
@@ -343,7 +378,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             redo = true;
           }
         }
-        if (redo) sum = sweep(TagTrue{}, TagTrue{}, t_s, m[i], row_max, pk);  // S is still intact in TMEM: P has not been stored yet
+        if (redo) sum = exp_sweep();  // S is still intact in TMEM: P has not been stored yet
         l[i] += sum;
         tmem_st32(t_s, pk);   // P over this thread's own first 32 (consumed) score columns
         tmem_st_wait();
@@ -530,6 +565,7 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   p.lse = static_cast<float*>(lse);
   p.ld_lse = ld_lse;
   p.kmax = static_cast<const float*>(kmax);
+  p.stats = kmax ? ctx->attn_stats : nullptr;
   p.rows_per_peer = o_peers ? rows_per_peer : 0;
   p.col_offset = col_offset;
   for (int i = 0; i < FGB_MAX_PEERS; ++i) p.o_peers[i] = (o_peers && i < n_peers) ? static_cast<__nv_bfloat16*>(o_peers[i]) : nullptr;
@@ -578,6 +614,13 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
     attn_combine_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(p, n_split);
     FGB_LAUNCH_CHECK("attn_combine_kernel");
   }
+  return FGB_OK;
+}
+
+extern "C" int fgb_attn_set_stats(fgb_ctx* ctx, void* counts_dev) {
+  if (!ctx) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_set_stats: ctx is NULL");
+  if (counts_dev && (reinterpret_cast<uintptr_t>(counts_dev) & 3u)) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_set_stats: unaligned");
+  ctx->attn_stats = static_cast<int32_t*>(counts_dev);
   return FGB_OK;
 }
 

@@ -34,11 +34,21 @@ struct AttnParams {
   __nv_bfloat16* o_peers[FGB_MAX_PEERS];
   int32_t rows_per_peer, col_offset;
   // Bounded-score softmax: kmax[head] = max_j ||k_j||^2 over all keys of the head (fp32, NULL = running-max softmax).
-  // |s_ij| <= ||q_i||·kmax (Cauchy-Schwarz), so B_i = ||q_i||·kmax·scale·log2e is a valid FIXED reference for the row:
-  // P = 2^(s - B_i) needs no running max, no rescale and no exchange. Used when every B_i of the CTA is <= 60
-  // (s - B_i >= -120: bf16 / fp32 have the exponent range for it, precision is scale-free); otherwise the CTA falls back.
+  // |s_ij| <= B_i = ||q_i||·sqrt(kmax)·scale·log2e (Cauchy-Schwarz). P = 2^(s - R_i) with a FIXED per-row reference R_i needs no
+  // running max, no rescale and no exchange; it is exact as long as the row's largest score lands inside the exponent window
+  // that bf16 (P) and fp32 (l, O) share: s_max - R_i in [-120, +100] (the row sum of 27 280 terms <= 2^100 stays below 2^115).
+  //   mode 0 (B_i <= 110 for every row of the CTA):  R_i = B_i (B_i <= 60) or 120 - B_i  ->  s - R_i in [-120, 100] for EVERY score
+  //   mode 1 (otherwise): the exact maximum m0 of the row's first KV tile anchors the window (m0 <= s_max <= B_i):
+  //           R_i = max(B_i - 100, min(B_i, m0 + 20)), valid when B_i - m0 <= 220
+  //   mode 2: a CTA with a row that fails both runs the running-max path. stats (optional, int32[3]) counts CTAs per mode.
   const float* kmax;
+  int32_t* stats;
 };
+
+constexpr float kBoundDirect = 60.0f;     // B <= this: R = B
+constexpr float kBoundFixedMax = 110.0f;  // B <= this: R = 120 - B (mode 0)
+constexpr float kWindowLo = 120.0f;       // s_max - R >= -kWindowLo
+constexpr float kWindowHi = 100.0f;       // s_max - R <= +kWindowHi
 
 __device__ __forceinline__ __nv_bfloat16* out_row(const AttnParams& p, int row, int head) {
   if (p.rows_per_peer > 0) {
@@ -57,10 +67,18 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // 2^x for a pair on the FMA/ALU pipes instead of the MUFU (which is as busy as the tensor pipe in this
 // kernel): round-to-nearest split x = n + f via the 1.5*2^23 trick, degree-3 minimax polynomial for 2^f
 // on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), exponent add in integer.
+// CLAMP = false: the caller guarantees x in [-126, 127] (bounded-score mode 0). CLAMP = true: x is clamped at -126 from below
+// with a NaN-propagating max (a NaN score stays NaN, as on the MUFU lanes), so the result of a very negative score is 2^-126
+// instead of 0 — which is why tiles with masked (-inf) scores take the MUFU-only sweep.
+template <bool CLAMP>
 __device__ __forceinline__ void exp2_emulated(uint64_t x2, float& r0, float& r1) {
-  float x0, x1;
-  unpack2(x2, x0, x1);
-  x2 = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  if (CLAMP) {
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    asm("max.NaN.f32 %0, %0, %1;" : "+f"(x0) : "f"(-126.0f));
+    asm("max.NaN.f32 %0, %0, %1;" : "+f"(x1) : "f"(-126.0f));
+    x2 = pack2(x0, x1);
+  }
   const uint64_t kMagic = pack2(12582912.0f, 12582912.0f);
   const uint64_t kNegMagic = pack2(-12582912.0f, -12582912.0f);
   const uint64_t kMinusOne = pack2(-1.0f, -1.0f);
@@ -81,6 +99,10 @@ __device__ __forceinline__ void exp2_emulated(uint64_t x2, float& r0, float& r1)
 
 struct TagTrue { static constexpr bool value = true; };
 struct TagFalse { static constexpr bool value = false; };
+// how a sweep turns scores into exponentials
+struct ExpMixed { static constexpr int value = 0; };       // MUFU + FMA-pipe emulation, no clamp (mode 0, full tiles)
+struct ExpMixedClamp { static constexpr int value = 1; };  // MUFU + clamped emulation (anchored / running-max references)
+struct ExpMufu { static constexpr int value = 2; };        // MUFU only: 2^(-inf) = 0 exactly (tiles with masked keys)
 
 
 }  // namespace fgb

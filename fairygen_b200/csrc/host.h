@@ -20,6 +20,7 @@ struct fgb_ctx {
                            const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
   CUresult (*mem_get_address_range)(CUdeviceptr* base, size_t* size, CUdeviceptr ptr) = nullptr;
+  int32_t* attn_stats = nullptr;   // caller-owned device int32[3] (fgb_attn_set_stats) or NULL
 };
 
 #define FGB_MAX_PEERS 8  // one NVSwitch box

@@ -47,11 +47,18 @@ class WanDiTEngine:
         if sp is not None and cfg.num_heads % sp.world != 0:
             raise ValueError(f"num_heads {cfg.num_heads} not divisible by sequence-parallel world {sp.world}")
         self.rope_tab = torch.from_numpy(ops.rope_table(cfg.head_dim)).to(self.device)
+        self._init_state()
+
+    def _init_state(self) -> None:
+        """Host-side state that does not touch the device (the CPU host-logic tests build an engine around it)."""
         self.blocks = []
         self._ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
         self._ctx_cache: Dict[tuple, tuple] = {}
         self._ctx_cache_order = []
         self.kernel_launches = 0  # kernels launched by forward() calls since the last reset
+        self.ctx_cache_misses = 0        # contexts whose text embedding + 30 cross K|V projections were computed
+        self.ctx_cache_content_hits = 0  # identity misses resolved by content (caller re-created an equal tensor)
+        self.fused_adapters = []         # (lora_sd, alpha, targets) fused by lora_io.fuse_into_engine since the last pack
         self.timer = None         # optional fairygen_b200.profiling.KernelTimer
         self.loaded = False
 
@@ -96,6 +103,22 @@ class WanDiTEngine:
         self.mods_all = torch.cat(mods, dim=0).contiguous()  # [L, 6D]
         self._ctx_cache.clear()
         self._ctx_cache_order.clear()
+        self.fused_adapters = []
+        self.loaded = True
+
+    _WEIGHT_ATTRS = ("w_patch", "b_patch", "w_text0", "b_text0", "w_text2", "b_text2", "w_time0", "b_time0", "w_time2", "b_time2",
+                     "w_tproj", "b_tproj", "w_head", "b_head", "head_mod", "mods_all", "blocks")
+
+    def share_weights_from(self, other: "WanDiTEngine") -> None:
+        """Use `other`'s packed weight tensors (same device, same config) instead of packing a second 10 GB copy — e.g. one
+        engine per parallel layout in one process.  Caches and workspaces stay private."""
+        if not other.loaded or other.cfg != self.cfg or other.device != self.device:
+            raise ValueError("share_weights_from needs a loaded engine of the same config on the same device")
+        for name in self._WEIGHT_ATTRS:
+            setattr(self, name, getattr(other, name))
+        self._ctx_cache.clear()
+        self._ctx_cache_order.clear()
+        self.fused_adapters = other.fused_adapters
         self.loaded = True
 
     # ------------------------------------------------------------------------------------------
@@ -171,13 +194,28 @@ class WanDiTEngine:
         return emb
 
     def _context_kv(self, context: torch.Tensor):
-        """text_embedding + per-block cross-attention K (RMS-normed) | V; cached per context tensor."""
+        """text_embedding + per-block cross-attention K (RMS-normed) | V; cached per context.
+
+        Fast path: the caller passes the same tensor object every step (the reference pipeline does: ``inputs_posi["context"]``,
+        PIPE:296) -> O(1) identity key (storage pointer, shape, dtype, version counter).  A caller that re-creates an equal
+        tensor every step misses that key; the miss is then resolved by CONTENT against the cached contexts (one device
+        compare of <= 4 MB + a sync, only on an identity miss) before 30 K|V GEMMs are re-done."""
         key = (context.data_ptr(), tuple(context.shape), context._version, context.dtype)
         hit = self._ctx_cache.get(key)
         if hit is not None:
             return hit
+        for old_key in reversed(self._ctx_cache_order):
+            cand = self._ctx_cache.get(old_key)
+            if cand is None:
+                continue
+            ref = cand[2]
+            if ref.shape == context.shape and ref.dtype == context.dtype and ref.device == context.device and torch.equal(ref, context):
+                self.ctx_cache_content_hits += 1
+                self._remember_context(key, (cand[0], cand[1], context, cand[3]))
+                return cand
         cfg, dev = self.cfg, self.device
         d = cfg.dim
+        self.ctx_cache_misses += 1
         emb = self.text_embedding(context)
         n = emb.shape[0]
         kv = torch.empty(cfg.num_layers, n, 2 * d, dtype=BF16, device=dev)
@@ -187,12 +225,17 @@ class WanDiTEngine:
             ops.rmsnorm_rope(kv[i][:, :d], cfg.eps, b.cnk)
             ops.head_norm_max(kv[i][:, :d], kmax[i], cfg.num_heads)
         self._launched(3 * cfg.num_layers)
-        val = (kv, n, context, kmax)  # keep `context` alive so its data_ptr cannot be recycled under the key
+        # keep a private copy of the context: it pins the content the entry was computed from (an in-place edit of the caller's
+        # tensor bumps _version and misses the key) and cannot be freed / recycled under the key
+        val = (kv, n, context.detach().clone(), kmax)
+        self._remember_context(key, val)
+        return val
+
+    def _remember_context(self, key, val) -> None:
         self._ctx_cache[key] = val
         self._ctx_cache_order.append(key)
-        while len(self._ctx_cache_order) > 4:
+        while len(self._ctx_cache_order) > 8:
             self._ctx_cache.pop(self._ctx_cache_order.pop(0), None)
-        return val
 
     # ------------------------------------------------------------------------------------------
     # forward
@@ -208,6 +251,9 @@ class WanDiTEngine:
             raise ValueError(f"latents must be (1,{cfg.in_dim},F,H,W), got {tuple(latents.shape)}")
         if latents.shape[3] % 2 or latents.shape[4] % 2:
             raise ValueError("latent height/width must be even (patch 2x2)")
+        if not (context.dim() == 2 or (context.dim() == 3 and context.shape[0] == 1)) or context.shape[-1] != cfg.text_dim:
+            raise ValueError(f"context must be (1,L,{cfg.text_dim}) or (L,{cfg.text_dim}), got {tuple(context.shape)}: a batch of "
+                             "contexts (cfg_merge) is one forward per context — model_fn_wan_video does that split")
         dev, d, H = self.device, cfg.dim, cfg.num_heads
         f, h, w = latents.shape[2], latents.shape[3] // 2, latents.shape[4] // 2
         grid = (f, h, w)

@@ -124,7 +124,8 @@ def load_stage2_checkpoint(path_or_sd) -> Dict[str, torch.Tensor]:
     return out
 
 
-def fuse_into_engine(engine, lora_sd: Dict[str, torch.Tensor], alpha: float = 1.0, targets: Optional[Iterable[str]] = None) -> int:
+def fuse_into_engine(engine, lora_sd: Dict[str, torch.Tensor], alpha: float = 1.0, targets: Optional[Iterable[str]] = None,
+                     _record: bool = True) -> int:
     """W <- W + alpha * B @ A on the engine's packed bf16 weights (fused QKV / cross-KV rows included), in place, on the GPU.
     Returns the number of fused Linears (the reference prints it, general.py:62)."""
     from . import ops
@@ -155,4 +156,9 @@ def fuse_into_engine(engine, lora_sd: Dict[str, torch.Tensor], alpha: float = 1.
         fused += 1
     engine._ctx_cache.clear()          # cached cross-attention K/V were projected with the old weights
     engine._ctx_cache_order.clear()
+    # remembered so that a re-pack from the weight container (model_fn.engine_for, after pipe.load_lora changed the module)
+    # re-applies this adapter instead of silently dropping it; engine.load_state_dict() itself starts from a clean slate
+    if _record and hasattr(engine, "fused_adapters"):
+        engine.fused_adapters.append(({k: v.detach().clone() for k, v in lora_sd.items()}, float(alpha),
+                                      None if targets is None else tuple(wanted)))
     return fused

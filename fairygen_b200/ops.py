@@ -31,6 +31,42 @@ def context(device: torch.device) -> _lib.Context:
     return _ctx_by_device[idx]
 
 
+_attn_stats = {}
+
+
+def _stats_buffer(device) -> torch.Tensor:
+    """Per-device int32[3] the attention kernel counts its CTAs into (fgb_attn_set_stats): [bound only, anchored, fallback]."""
+    c = context(device)
+    buf = _attn_stats.get(c.device_index)
+    if buf is None:
+        buf = torch.zeros(3, dtype=torch.int32, device=torch.device("cuda", c.device_index))
+        _lib.check(_lib.lib().fgb_attn_set_stats(c.handle, c_void_p(buf.data_ptr())), "fgb_attn_set_stats")
+        _attn_stats[c.device_index] = buf
+    return buf
+
+
+def attention_stats_reset(device) -> None:
+    """Start counting the CTAs of bounded-score attention launches on `device` (and zero the counters)."""
+    _stats_buffer(device).zero_()
+
+
+def attention_stats(device):
+    """(CTAs on the fixed-reference fast path [bound only + first-tile anchored], CTAs that fell back to the running-max path)
+    since attention_stats_reset; (0, 0) if counting was never switched on."""
+    c = context(device)
+    buf = _attn_stats.get(c.device_index)
+    if buf is None:
+        return 0, 0
+    a, b, f = (int(x) for x in buf.tolist())
+    return a + b, f
+
+
+def attention_stats_detail(device):
+    buf = _stats_buffer(device)
+    a, b, f = (int(x) for x in buf.tolist())
+    return {"bound_only": a, "first_tile_anchored": b, "running_max_fallback": f}
+
+
 def _h(t: torch.Tensor) -> _lib.Context:
     return context(t.device)
 

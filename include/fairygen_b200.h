@@ -95,11 +95,16 @@ int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int
                     void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s_kv, int32_t heads);
 
-/* Bounded-score softmax. kmax2[head] = max_j ||k[j, head]||^2 (fgb_head_norm_max) gives |q_i·k_j| <= ||q_i||·sqrt(kmax2), a
- * FIXED per-row reference for the exponentials: no running maximum, no rescale of O, no per-tile exchange between the
- * threads that share a row. A CTA uses it when all its bounds are <= 60 in log2 units (no underflow possible), else it
- * falls back to the running-max path; results are the same softmax either way. o_peers may be NULL (then `o` is used). */
+/* Bounded-score softmax. kmax2[head] = max_j ||k[j, head]||^2 (fgb_head_norm_max) gives |q_i·k_j|·scale·log2e <= B_i =
+ * ||q_i||·sqrt(kmax2)·scale·log2e, from which every query row gets a FIXED reference R_i for its exponentials P = 2^(s - R_i):
+ * no running maximum, no rescale of O, no per-tile exchange between the threads that share a row. It is the same softmax as
+ * long as the row's largest score stays inside the exponent window bf16 and fp32 share, which the kernel guarantees per CTA:
+ * B_i <= 110 -> R_i from the bound alone; otherwise R_i is anchored on the exact maximum of the row's first KV tile (valid for
+ * B_i - m0 <= 220); a CTA where neither holds runs the running-max path of fgb_attn_fwd_ex. o_peers may be NULL (then `o` is used).
+ * fgb_attn_set_stats registers an optional caller-owned device int32[3]; every CTA of a bounded launch adds 1 to
+ * counts[mode] (0 = bound only, 1 = first-tile anchored, 2 = running-max fallback). NULL switches the counting off. */
 int fgb_head_norm_max(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t rows, int32_t heads, void* out_f32, void* stream);
+int fgb_attn_set_stats(fgb_ctx* ctx, void* counts_dev_i32x3);
 int fgb_attn_fwd_bounded(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                          void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale, const void* kmax2,
                          void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* const* o_peers,

@@ -133,8 +133,7 @@ def engine(monkeypatch):
     eng = fg.WanDiTEngine.__new__(fg.WanDiTEngine)        # the constructor refuses non-CUDA devices (no CPU path in the product);
     eng.cfg, eng.device, eng.ctx, eng.sp = cfg, torch.device("cpu"), None, None     # the test sets up the same fields by hand
     eng.rope_tab = torch.from_numpy(ops.rope_table(cfg.head_dim))
-    eng.blocks, eng._ws, eng._ctx_cache, eng._ctx_cache_order = [], {}, {}, []
-    eng.kernel_launches, eng.timer, eng.loaded = 0, None, False
+    eng._init_state()
     eng.load_state_dict(w)
     return eng, {k: v.to(BF).float() for k, v in w.items()}
 

@@ -34,8 +34,7 @@ def _bare_engine(fg, ops, cfg, sp):
     eng = fg.WanDiTEngine.__new__(fg.WanDiTEngine)          # the constructor refuses the CPU (tests/test_engine_host.py)
     eng.cfg, eng.device, eng.ctx, eng.sp = cfg, torch.device("cpu"), None, sp
     eng.rope_tab = torch.from_numpy(ops.rope_table(cfg.head_dim))
-    eng.blocks, eng._ws, eng._ctx_cache, eng._ctx_cache_order = [], {}, {}, []
-    eng.kernel_launches, eng.timer, eng.loaded = 0, None, False
+    eng._init_state()
     return eng
 
 

@@ -162,8 +162,7 @@ def _trainer(monkeypatch, stage, recompute):
     eng = fg.WanDiTEngine.__new__(fg.WanDiTEngine)              # see tests/test_engine_host.py: the constructor refuses the CPU
     eng.cfg, eng.device, eng.ctx, eng.sp = cfg, torch.device("cpu"), None, None
     eng.rope_tab = torch.from_numpy(ops.rope_table(cfg.head_dim))
-    eng.blocks, eng._ws, eng._ctx_cache, eng._ctx_cache_order = [], {}, {}, []
-    eng.kernel_launches, eng.timer, eng.loaded = 0, None, False
+    eng._init_state()
     eng.load_state_dict(w)
     lora = o.make_lora(o.TINY, rank=32, seed=2)
     tr = Stage2Trainer(eng, lora, rank=32, stage=stage, recompute=recompute)
