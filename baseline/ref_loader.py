@@ -194,6 +194,7 @@ def make_stub_vae(z_dim: int, device, dtype):
             return torch.stack(outs).to(dtype=dtype)
 
         def decode(self, latents, device=None, tiled=False, tile_size=None, tile_stride=None):
+            self.last_latents = latents.detach().clone()     # what the denoise loop handed to the decoder
             x = latents[:, :3].float()
             x = x.repeat_interleave(4, dim=2)[:, :, 3:]
             return torch.nn.functional.interpolate(x, scale_factor=(1, 16, 16), mode="nearest").clamp(-1, 1)

@@ -485,7 +485,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_reference(2, 1, with_block_sample=False)
+            line["cpu_baseline"] = cpu_reference(2, 1, with_block_sample=True)
         except Exception as e:
             line["cpu_baseline"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     print(json.dumps(line))

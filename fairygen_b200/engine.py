@@ -211,7 +211,7 @@ class WanDiTEngine:
             ref = cand[2]
             if ref.shape == context.shape and ref.dtype == context.dtype and ref.device == context.device and torch.equal(ref, context):
                 self.ctx_cache_content_hits += 1
-                self._remember_context(key, (cand[0], cand[1], context, cand[3]))
+                self._remember_context(key, cand)   # cand[2] is the PRIVATE copy of the content: the caller may edit its tensor later
                 return cand
         cfg, dev = self.cfg, self.device
         d = cfg.dim

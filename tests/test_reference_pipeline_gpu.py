@@ -1,0 +1,172 @@
+"""The drop-in boundary driven by the UNMODIFIED reference pipeline (baseline/_ref, installed by baseline/install_ref.py and
+shipped to the GPU box): ``WanVideoPipeline.__call__`` (wan_video.py:172-329) — units, scheduler, denoise loop, the ~40-key
+``model_fn`` call — runs once with the reference's own ``model_fn_wan_video`` and once after ``fairygen_b200.install(pipe)``;
+both pipelines hold the reference's own ``WanModel`` with the same weights.  Only the models that are not on the DiT hot path
+(tokenizer, text encoder, VAE) are small stand-ins (baseline/ref_loader.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def env():
+    from baseline import ref_loader as rl
+
+    if not rl.available():
+        pytest.skip("baseline/_ref not installed (python baseline/install_ref.py in the build container)")
+    import fairygen_b200 as fg
+    from oracle import wan_dit_oracle as o
+
+    rl.load()
+    rl.select_attention_backend("cuda")
+    return fg, o, rl
+
+
+def rel_l2(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm())
+
+
+def _pipes(fg, o, rl, seed=0):
+    w = {k: v.to("cuda", BF) for k, v in o.make_weights(o.TINY, seed=seed).items()}
+    pipes = []
+    for _ in range(2):
+        dit = rl.build_wan_model(o.TINY, state_dict={k: v.clone() for k, v in w.items()})
+        pipes.append(rl.build_pipeline(dit, "cuda", BF, text_len=32))
+    return pipes
+
+
+def _call(pipe, **kw):
+    from PIL import Image
+
+    img = Image.fromarray((np.random.RandomState(0).rand(128, 128, 3) * 255).astype(np.uint8))
+    args = dict(prompt="a paper boat drifts down the gutter after the rain", negative_prompt="blurry, static", input_image=img, seed=3,
+                height=128, width=128, num_frames=9, num_inference_steps=6, tiled=False, output_type="floatpoint",
+                progress_bar_cmd=lambda x: x)
+    args.update(kw)
+    video = pipe(**args)
+    return video, pipe.vae.last_latents
+
+
+def test_install_drives_the_unmodified_pipeline(env):
+    fg, o, rl = env
+    ref_pipe, our_pipe = _pipes(fg, o, rl)
+    calls = []
+    ref_fn = ref_pipe.model_fn
+
+    def recording_model_fn(**kwargs):        # wraps, does not modify, the reference's model_fn
+        out = ref_fn(**kwargs)
+        calls.append(({k: (v.clone() if torch.is_tensor(v) else v) for k, v in kwargs.items()}, out.clone()))
+        return out
+
+    ref_pipe.model_fn = recording_model_fn
+    video_ref, lat_ref = _call(ref_pipe)
+    assert len(calls) == 12 and len(calls[0][0]) > 40          # 6 steps x (positive, negative); the full keyword soup
+
+    fg.install(our_pipe)
+    assert our_pipe.model_fn is fg.model_fn_wan_video
+    video, lat = _call(our_pipe)
+    fg.ops.sync_check()
+    assert lat.shape == lat_ref.shape and lat.dtype == lat_ref.dtype and lat.device == lat_ref.device
+    err = rel_l2(lat, lat_ref)
+    print(f"6-step pipeline call: latents rel L2 {err:.3e}, video {rel_l2(video, video_ref):.3e}")
+    assert err < 3e-2                                           # north star: <= 3e-2 after a schedule
+    assert torch.equal(lat[:, :, 0:1], lat_ref[:, :, 0:1])      # first frame restored from the (shared) stub VAE encode
+
+    # every recorded reference call, replayed through the drop-in with the reference's exact kwargs: <= 1e-2 per forward
+    worst = 0.0
+    for kwargs, want in calls:
+        kwargs = dict(kwargs)
+        kwargs["dit"] = our_pipe.dit
+        got = fg.model_fn_wan_video(**kwargs)
+        assert got.shape == want.shape and got.dtype == want.dtype and got.device == want.device
+        worst = max(worst, rel_l2(got, want))
+    print(f"per-call worst rel L2 {worst:.3e}")
+    assert worst < 1e-2
+
+
+def test_load_lora_after_install_repacks_and_context_cache_is_content_stable(env):
+    fg, o, rl = env
+    from fairygen_b200 import model_fn as mf
+    from fairygen_b200 import synthetic
+
+    ref_pipe, our_pipe = _pipes(fg, o, rl, seed=1)
+    fg.install(our_pipe)
+    cfg = fg.WanDiTConfig.from_module(our_pipe.dit)
+    lora = synthetic.random_lora(cfg, rank=8, seed=5, device="cuda")
+    for pipe in (ref_pipe, our_pipe):
+        pipe.load_lora(pipe.dit, state_dict={k: v.clone() for k, v in lora.items()}, alpha=1.0)   # LORA:44-62, in-place load_state_dict
+    lat, z0, cp, cn = o.make_inputs(o.TINY, (1, 48, 3, 8, 8), text_len=32, live_text=8)
+    lat, cp = lat.to("cuda", BF), cp.to("cuda", BF)
+    ts = torch.tensor([900.0], device="cuda", dtype=BF)
+    with torch.no_grad():
+        want = ref_pipe.model_fn(dit=ref_pipe.dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
+        eng = mf.engine_for(our_pipe.dit)
+        misses0 = eng.ctx_cache_misses
+        got = our_pipe.model_fn(dit=our_pipe.dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
+        assert rel_l2(got, want) < 1e-2                        # the engine re-packed the fused weights
+        assert eng.ctx_cache_misses == misses0 + 1
+        # a caller that re-creates the context tensor every step: resolved by content, no second projection of the context
+        for _ in range(3):
+            again = our_pipe.model_fn(dit=our_pipe.dit, latents=lat, timestep=ts, context=cp.clone(), fuse_vae_embedding_in_latents=True)
+            assert torch.equal(again, got)
+        assert eng.ctx_cache_misses == misses0 + 1 and eng.ctx_cache_content_hits >= 1
+        # an in-place edit of the SAME tensor object must miss
+        cp2 = cp.clone()
+        a = our_pipe.model_fn(dit=our_pipe.dit, latents=lat, timestep=ts, context=cp2, fuse_vae_embedding_in_latents=True)
+        cp2[:, :4] += 1.0
+        b = our_pipe.model_fn(dit=our_pipe.dit, latents=lat, timestep=ts, context=cp2, fuse_vae_embedding_in_latents=True)
+        assert not torch.equal(a, b) and eng.ctx_cache_misses == misses0 + 2
+        # weight swaps the version counter cannot see (param.data = ...) are caught by the storage pointers
+        w = our_pipe.dit.blocks[0].ffn[0].weight
+        w.data = (w.data * 0.5).clone()
+        ref_pipe.dit.blocks[0].ffn[0].weight.data.mul_(0.5)
+        want2 = ref_pipe.model_fn(dit=ref_pipe.dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
+        got2 = our_pipe.model_fn(dit=our_pipe.dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
+        assert rel_l2(got2, want2) < 1e-2 and rel_l2(got2, got) > 1e-3
+    # the per-call cost of the staleness check stays negligible
+    import time
+    t0 = time.perf_counter()
+    for _ in range(50):
+        mf._weights_version(our_pipe.dit)
+    assert (time.perf_counter() - t0) / 50 < 2e-3
+
+
+def test_adapter_fused_into_the_engine_survives_a_repack_and_cpu_dit_is_refused(env):
+    fg, o, rl = env
+    from fairygen_b200 import lora_io, synthetic
+    from fairygen_b200 import model_fn as mf
+
+    ref_pipe, our_pipe = _pipes(fg, o, rl, seed=2)
+    fg.install(our_pipe)
+    cfg = fg.WanDiTConfig.from_module(our_pipe.dit)
+    lora_a = synthetic.random_lora(cfg, rank=8, seed=6, device="cuda")
+    lora_b = synthetic.random_lora(cfg, rank=8, seed=7, device="cuda")
+    eng = mf.engine_for(our_pipe.dit)
+    lora_io.fuse_into_engine(eng, lora_a)                                      # directly on the packed weights
+    our_pipe.load_lora(our_pipe.dit, state_dict=lora_b)                        # changes the container -> re-pack
+    for sd in (lora_a, lora_b):
+        ref_pipe.load_lora(ref_pipe.dit, state_dict={k: v.clone() for k, v in sd.items()})
+    lat, z0, cp, cn = o.make_inputs(o.TINY, (1, 48, 3, 8, 8), text_len=32, live_text=8)
+    lat, cp = lat.to("cuda", BF), cp.to("cuda", BF)
+    ts = torch.tensor([500.0], device="cuda", dtype=BF)
+    with torch.no_grad():
+        want = ref_pipe.model_fn(dit=ref_pipe.dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
+        got = our_pipe.model_fn(dit=our_pipe.dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
+    assert rel_l2(got, want) < 1e-2 and len(mf.engine_for(our_pipe.dit).fused_adapters) == 1
+    # a DiT that still lives on the host (offload modes): install() defers, the first call explains
+    w = o.make_weights(o.TINY, seed=3)
+    cpu_dit = rl.build_wan_model(o.TINY, state_dict={k: v.to(BF) for k, v in w.items()})
+    cpu_pipe = rl.build_pipeline(cpu_dit, "cuda", BF, text_len=32)
+    fg.install(cpu_pipe)                                                       # does not raise
+    with pytest.raises(RuntimeError, match="move the model to the GPU"):
+        cpu_pipe.model_fn(dit=cpu_dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
+    with pytest.raises(ValueError, match="context must be"):
+        eng.forward(lat, ts, torch.cat([cp, cp]), True)

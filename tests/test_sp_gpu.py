@@ -58,6 +58,70 @@ def test_sp2_equals_single_gpu(tmp_path, shape, exchange):
         assert res["finite"] and res["err"] < 3e-3, res   # same kernels; only the attention work split / key-split tail differs
 
 
+def _oracle_worker(rank, world, port, dims, shape, out_dir):
+    """Ulysses SP over `world` GPUs against the ORACLE (the reference's op chain, bf16, run by torch on this rank's GPU) — and
+    against the unmodified reference where baseline/_ref travelled to the box — not against our own single-GPU engine."""
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+
+    import fairygen_b200 as fg
+    from fairygen_b200 import synthetic
+    from oracle import wan_dit_oracle as o
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    dim, ffn, heads, text_dim = dims
+    cfg = fg.WanDiTConfig(dim=dim, ffn_dim=ffn, text_dim=text_dim, num_heads=heads, num_layers=2)
+    ocfg = o.DiTConfig(dim=dim, ffn_dim=ffn, text_dim=text_dim, num_heads=heads, num_layers=2)
+    sd = synthetic.random_state_dict(cfg, seed=0, device=dev, dtype=BF, lora_rank=32)
+    lat, z0, cp, cn = synthetic.synthetic_inputs(cfg, shape, text_len=128, live_text=24, pin=False)
+    lat, cp = lat.to(dev), cp.to(dev)
+    ts = torch.tensor([996.0], device=dev, dtype=BF)
+    par = fg.WanDiTEngine(cfg, dev, sp=fg.SequenceParallel(exchange="p2p"))
+    par.load_state_dict(sd)
+    out = par.forward(lat, ts, cp, True)
+    fg.ops.sync_check()
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())  # noqa: E731
+    with torch.no_grad():
+        ref16 = o.dit_forward(sd, ocfg, lat, ts, cp, True)
+        ref32 = o.dit_forward({k: v.float() for k, v in sd.items()}, ocfg, lat.float(), ts.float(), cp.float(), True)
+    res = {"err_oracle_bf16": rel(out, ref16), "err_oracle_fp32": rel(out, ref32), "ref_bf16_vs_fp32": rel(ref16, ref32),
+           "finite": bool(torch.isfinite(out.float()).all()), "err_reference": None}
+    from baseline import ref_loader as rl
+
+    if rl.available():
+        ref = rl.load()
+        rl.select_attention_backend(dev)
+        dit = rl.build_wan_model(cfg, state_dict=sd)
+        with torch.no_grad():
+            want = ref.wv.model_fn_wan_video(dit=dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
+        res["err_reference"] = rel(out, want)
+    torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dims,shape", [
+    ((3072, 14336, 24, 4096), (1, 48, 3, 10, 14)),    # TI2V-5B block shapes, 12 heads per rank, S = 105 (ragged: 1 pad row)
+    ((3072, 14336, 24, 4096), (1, 48, 5, 16, 16)),    # S = 320 (even split)
+    ((768, 2048, 6, 512), (1, 48, 3, 10, 14)),        # 3 heads per rank — the per-rank head count of Ulysses SP8 on TI2V-5B
+])
+def test_sp2_vs_oracle_at_north_star_tolerance(tmp_path, dims, shape):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    world = 2
+    mp.spawn(_oracle_worker, args=(world, _free_port(), dims, shape, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        print(res)
+        assert res["finite"] and res["err_oracle_bf16"] < 1e-2, res          # north star: rel L2 <= 1e-2 per forward
+        assert res["err_oracle_fp32"] < 2.0 * res["ref_bf16_vs_fp32"] + 1e-3, res   # no worse than the reference's own bf16 error
+        assert res["err_reference"] is None or res["err_reference"] < 1e-2, res
+
+
 def _cfg_worker(rank, world, port, shape, sp_ways, out_dir):
     """CFG-parallel pair (x Ulysses inside each half): a 3-step denoise must equal the single-GPU sequential loop."""
     sys.path.insert(0, REPO)

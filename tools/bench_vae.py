@@ -14,6 +14,70 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
 
+def _random_sd(shapes, dev):
+    g = torch.Generator(device=dev).manual_seed(0)
+    sd = {}
+    for name, shape in shapes.items():
+        if name.endswith("gamma"):
+            t = 1 + 0.1 * torch.randn(shape, generator=g, device=dev)
+        elif name.endswith("bias"):
+            t = 0.05 * torch.randn(shape, generator=g, device=dev)
+        else:
+            fan = 1
+            for v in shape[1:]:
+                fan *= v
+            t = torch.randn(shape, generator=g, device=dev) * fan ** -0.5
+        sd[name] = t
+    return sd
+
+
+def bench_encode(args):
+    """VAE38 encoder (wan_video_vae.py:1103-1253 via WanVideoVAE.encode, called at PIPE:495 for the first-frame image and by the
+    training data path for whole clips): full-width random-init encoder on (a) the 704x1280 first-frame image of the headline
+    video, tiled as the pipeline does, and (b) the 49-frame 480x832 training clip of BASELINE config 5.  One JSON line."""
+    from fairygen_b200 import vae, vae_encode
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    enc = vae_encode.VAE38Encoder(vae.VAE38, dev)
+    enc.load_state_dict(_random_sd(vae_encode.enc_param_shapes(vae.VAE38), dev))
+    cases = {"first_frame_image_704x1280": (3, 1, 704, 1280), "training_clip_49x480x832": (3, 49, 480, 832)}
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, shape in cases.items():
+        host = torch.tanh(torch.randn(shape, generator=torch.Generator().manual_seed(2))).to(torch.bfloat16).pin_memory()
+        devv = host.to(dev)
+        run = lambda v: enc.encode([v], tiled=True, tile_size=(34, 34), tile_stride=(18, 16))   # noqa: E731  the reference's defaults
+        z = run(devv)
+        torch.cuda.synchronize()
+        enc.kernel_launches = 0
+        e0.record()
+        for _ in range(args.repeat):
+            z = run(devv)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.repeat
+        launches = enc.kernel_launches // args.repeat
+        z_host = torch.empty(z.shape, dtype=z.dtype).pin_memory()
+        e0.record()
+        for _ in range(args.repeat):
+            z_host.copy_(run(host.to(dev, non_blocking=True)), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / args.repeat
+        out[name] = {"ms": round(ms, 2), "ms_e2e_host_in_host_out": round(ms_e2e, 2), "latent_shape": list(z.shape), "gpu_launches": launches,
+                     "input_mpix_per_s": round(shape[1] * shape[2] * shape[3] / ms / 1e3, 1), "finite": bool(torch.isfinite(z.float()).all())}
+    img = out["first_frame_image_704x1280"]
+    print(json.dumps({
+        "metric": "vae38_encode_images_per_s", "value": 1e3 / img["ms"], "unit": "images/s", "n_gpus": 1, "steps": args.repeat, "warmup": 1,
+        "ms_per_step": img["ms"], "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Wan2.2 VAE38 tiled encode (tile 34x34, stride 18x16), full-width encoder, random-init weights"},
+        "e2e": {"value": 1e3 / img["ms_e2e_host_in_host_out"], "unit": "images/s", "h2d_bytes_per_step": 3 * 704 * 1280 * 2,
+                "d2h_bytes_per_step": 48 * 44 * 80 * 2},
+        "gpu_launches": img["gpu_launches"], "cases": out, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=31, help="latent frames (31 = 121 video frames)")
@@ -21,11 +85,15 @@ def main():
     ap.add_argument("--width", type=int, default=80)
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--encode", action="store_true", help="time the VAE38 ENCODER instead (PIPE:490-497 first-frame image; training clip)")
+    ap.add_argument("--repeat", type=int, default=3, help="--encode: timed repetitions per input")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel CUDA time of one decode (torch.profiler / CUPTI) to stderr")
     ap.add_argument("--torch-chain", action="store_true",
                     help="also time the reference's own bf16 op chain (torch / cuDNN kernels, the oracle functions run in bf16) on the "
                          "same windows on this GPU — the baseline leg; blending and the reference's per-tile CPU round trip excluded")
     args = ap.parse_args()
+    if args.encode:
+        return bench_encode(args)
     from fairygen_b200 import ops, vae
 
     dev = torch.device("cuda", 0)
