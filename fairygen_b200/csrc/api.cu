@@ -23,6 +23,15 @@ int make_tmap_bf16_2d(const fgb_ctx* ctx, CUtensorMap* map, const void* base, in
   if ((ld * 2) % 16 != 0) return set_error(FGB_ERR_INVALID, "leading dimension %lld elements is not a multiple of 8", (long long)ld);
   if (rows <= 0 || cols <= 0) return set_error(FGB_ERR_INVALID, "empty matrix %lld x %lld", (long long)rows, (long long)cols);
   if (box_rows < 1 || box_rows > 256 || box_cols != 64) return set_error(FGB_ERR_INVALID, "bad TMA box %d x %d", box_rows, box_cols);
+  // direct-mapped cache: the map depends on nothing but these five values (a tensor map holds an address, not data)
+  uint64_t hkey = reinterpret_cast<uint64_t>(base) * 0x9E3779B97F4A7C15ull;
+  hkey ^= (static_cast<uint64_t>(rows) * 0xC2B2AE3D27D4EB4Full) ^ (static_cast<uint64_t>(cols) << 20) ^ (static_cast<uint64_t>(ld) << 40) ^
+          static_cast<uint64_t>(box_rows);
+  fgb_ctx::TmapSlot& slot = ctx->tmap_cache[(hkey >> 32) % fgb_ctx::kTmapSlots];
+  if (slot.base == base && slot.rows == rows && slot.cols == cols && slot.ld == ld && slot.box_rows == box_rows) {
+    *map = slot.map;
+    return FGB_OK;
+  }
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
@@ -33,6 +42,12 @@ int make_tmap_bf16_2d(const fgb_ctx* ctx, CUtensorMap* map, const void* base, in
   if (r != CUDA_SUCCESS)
     return set_error(FGB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%dx%d)",
                      (int)r, (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
+  slot.base = base;
+  slot.rows = rows;
+  slot.cols = cols;
+  slot.ld = ld;
+  slot.box_rows = box_rows;
+  slot.map = *map;
   return FGB_OK;
 }
 

@@ -17,6 +17,8 @@
 //               residual in fp32 with the reference's bf16 rounding points, 16-byte global stores.
 // Tiles are rasterised in groups of 8 M-blocks so the CTAs resident at one time share A and W
 // tiles through the 126 MB L2.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -323,6 +325,309 @@ static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
   return FGB_OK;
 }
 
+// =====================================================================================================================
+// 2-CTA variant (the DiT forward GEMMs): a cluster of two CTAs on one TPC computes a 256 x 256 output tile with
+// tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16).  Each CTA owns 128 of the 256 rows (accumulator: its own TMEM, 2 x 256
+// columns, double-buffered) and loads its 128 x 64 slice of A plus HALF of the 256 x 64 W tile: per SM the operand traffic of a
+// k-block drops from 48 KB to 32 KB (smem fill, L2 reads) and the tensor core reads 64 instead of 96 bytes per clock from
+// shared memory.  The leader CTA issues the MMAs for the pair; `full` barriers live in the leader (both CTAs' TMA loads signal
+// them), `empty` / `tmem_full` are signalled in both CTAs by multicast commits, `tmem_empty` collects one arrival per epilogue
+// warp of both CTAs.  The epilogue stages 32 x 64 bf16 blocks per warp in shared memory (128-byte swizzle, conflict-free) and
+// writes them with TMA stores: full 128-byte lines, no per-thread row-strided stores.  Tiles are rasterised in supertiles of
+// group_m x band_n tiles so that a W band and an A group stay L2-resident while they are being reused.
+constexpr int kPairBM = 128;       // rows per CTA
+constexpr int kPairTM = 256;       // rows per cluster tile
+constexpr int kPairBN = 256;
+constexpr int kPairStages = 5;
+constexpr int kPairABytes = kPairBM * kBK * 2;          // 16 KB
+constexpr int kPairBBytes = (kPairBN / 2) * kBK * 2;    // 16 KB: this CTA's half of the W tile
+constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
+constexpr int kPairStoreBytes = 32 * 128;               // one staged block: 32 rows x 64 bf16
+constexpr int kPairStagingBytes = 4 * 2 * kPairStoreBytes;   // 4 epilogue warps x 2 buffers
+constexpr int kPairThreads = 192;
+constexpr int kPairSmem = kPairStages * kPairStageBytes + kPairStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct PairParams {
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* c;
+  const __nv_bfloat16* gate0;
+  const __nv_bfloat16* gate1;
+  int64_t ldc;
+  int32_t m, n;
+  int32_t rows_gate0;
+  int32_t m_tiles, n_tiles, tiles, k_blocks;
+  int32_t group_m, band_n;   // supertile: band_n tile columns x group_m tile rows, m fastest inside
+};
+
+__device__ __forceinline__ void pair_tile_coords(const PairParams& p, int tile, int& mt, int& nt) {
+  const int band_tiles = p.m_tiles * p.band_n;          // tiles of a full band
+  const int band = tile / band_tiles;
+  const int n0 = band * p.band_n;
+  const int bn = min(p.n_tiles - n0, p.band_n);         // width of this band
+  const int in_band = tile - band * band_tiles;
+  const int group_tiles = p.group_m * bn;
+  const int group = in_band / group_tiles;
+  const int m0 = group * p.group_m;
+  const int gm = min(p.m_tiles - m0, p.group_m);
+  const int in_group = in_band - group * group_tiles;
+  mt = m0 + in_group % gm;
+  nt = n0 + in_group / gm;
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_c, const PairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kPairStages * kPairABytes;
+  uint8_t* smem_st = smem + kPairStages * kPairStageBytes;                    // 1024-byte aligned (stage sizes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_st + kPairStagingBytes);
+  uint64_t* full = bars;                               // [stages]  TMA (both CTAs) -> MMA; used in the leader
+  uint64_t* empty = bars + kPairStages;                // [stages]  MMA -> TMA, multicast to both CTAs
+  uint64_t* tmem_full = bars + 2 * kPairStages;        // [2]       MMA -> epilogue, multicast to both CTAs
+  uint64_t* tmem_empty = bars + 2 * kPairStages + 2;   // [2]       epilogue warps of both CTAs -> MMA; used in the leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();             // 0 = leader
+  const int n_clusters = gridDim.x >> 1;
+  const int cluster = blockIdx.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();    // barriers of BOTH CTAs are initialised before any remote signal can arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------- TMA producer (both CTAs) -------------------------------
+      uint32_t full_leader[kPairStages];
+#pragma unroll
+      for (int s = 0; s < kPairStages; ++s)
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader[s]) : "r"(smem_u32(&full[s])));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster; tile < p.tiles; tile += n_clusters) {
+        int mt, nt;
+        pair_tile_coords(p, tile, mt, nt);
+        const int row_a = mt * kPairTM + static_cast<int>(rank) * kPairBM;
+        const int row_b = nt * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait_cluster(&empty[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * kPairStageBytes);   // both CTAs' bytes land on the leader's barrier
+          uint32_t fl = full_leader[0];
+#pragma unroll
+          for (int s = 1; s < kPairStages; ++s) fl = (stage == s) ? full_leader[s] : fl;
+          tma_load_2d_2sm(smem_a + stage * kPairABytes, &tmap_a, fl, kb * kBK, row_a, kEvictNormal);
+          tma_load_2d_2sm(smem_b + stage * kPairBBytes, &tmap_b, fl, kb * kBK, row_b, kEvictLast);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      // ------------------------------- MMA issuer (leader only) -------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16(kPairTM, kPairBN, 0, 0);
+      const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(smem_a), 16, 1024);
+      const uint64_t b_desc0 = make_sdesc_sw128(smem_u32(smem_b), 16, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = cluster; tile < p.tiles; tile += n_clusters, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kPairBN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait_cluster(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = a_desc0 + static_cast<uint64_t>((stage * kPairABytes) >> 4);
+          const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * kPairBBytes) >> 4);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_ss_2sm(tmem_d, adesc + static_cast<uint64_t>((k * 32) >> 4), bdesc + static_cast<uint64_t>((k * 32) >> 4), idesc,
+                        (kb | k) != 0);
+          tc_commit_2sm(&empty[stage], 0x3);     // the slot is reusable in BOTH CTAs once these MMAs have read it
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tmem_full[acc], 0x3);     // accumulator halves complete in both CTAs
+      }
+    }
+  } else {
+    // --------------------------------- epilogue (both CTAs) -----------------------------------
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are visible to this warp
+    uint8_t* stage_buf = smem_st + quarter * (2 * kPairStoreBytes);
+    int buf = 0;
+    int local = 0;
+    constexpr bool kReadsC = (EPI == FGB_EPI_GATED_RESIDUAL || EPI == FGB_EPI_RESIDUAL);
+    for (int tile = cluster; tile < p.tiles; tile += n_clusters, ++local) {
+      int mt, nt;
+      pair_tile_coords(p, tile, mt, nt);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait_cluster(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row0 = mt * kPairTM + static_cast<int>(rank) * kPairBM + quarter * 32;   // first row of this warp's block
+      const int row = row0 + lane;
+      const bool row_ok = row < p.m;
+      const __nv_bfloat16* crow = p.c + static_cast<int64_t>(row) * p.ldc;
+      const __nv_bfloat16* gate = nullptr;
+      if (EPI == FGB_EPI_GATED_RESIDUAL) gate = (row < p.rows_gate0) ? p.gate0 : p.gate1;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kPairBN;
+      uint4 xcur[4], xnext[4];
+      auto load_c = [&](int c32, uint4 (&dst)[4]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = nt * kPairBN + c32 * 32 + g * 8;
+          dst[g] = (row_ok && col < p.n) ? *reinterpret_cast<const uint4*>(crow + col) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (kReadsC) load_c(0, xcur);
+#pragma unroll 1
+      for (int c64 = 0; c64 < kPairBN / 64; ++c64) {
+        if (nt * kPairBN + c64 * 64 >= p.n) break;   // warp-uniform
+        uint8_t* sbuf = stage_buf + buf * kPairStoreBytes;
+        // the TMA store that last read this buffer must be done with it (at most one newer store may still be in flight)
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c32 = c64 * 2 + half;
+          const int col0 = nt * kPairBN + c32 * 32;
+          uint32_t r[32];
+          tmem_ld32(taddr + c32 * 32, r);
+          if (kReadsC && c32 + 1 < kPairBN / 32) load_c(c32 + 1, xnext);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            float y[8];
+            uint4 bv = make_uint4(0, 0, 0, 0);
+            if (p.bias && col < p.n) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              y[2 * i] = round_bf16(__uint_as_float(r[g * 8 + 2 * i]) + bf16_lo(bw[i]));
+              y[2 * i + 1] = round_bf16(__uint_as_float(r[g * 8 + 2 * i + 1]) + bf16_hi(bw[i]));
+            }
+            if (EPI == FGB_EPI_BIAS_GELU_TANH) {
+#pragma unroll
+              for (int i = 0; i < 8; i += 2) gelu_tanh_2(y[i], y[i + 1]);
+            }
+            if (kReadsC) {
+              const uint4 xv = xcur[g];
+              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+              if (EPI == FGB_EPI_GATED_RESIDUAL) {
+                uint4 gv = make_uint4(0, 0, 0, 0);
+                if (col < p.n) gv = __ldg(reinterpret_cast<const uint4*>(gate + col));
+                const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  y[2 * i] = bf16_lo(xw[i]) + round_bf16(bf16_lo(gw[i]) * y[2 * i]);
+                  y[2 * i + 1] = bf16_hi(xw[i]) + round_bf16(bf16_hi(gw[i]) * y[2 * i + 1]);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  y[2 * i] = bf16_lo(xw[i]) + y[2 * i];
+                  y[2 * i + 1] = bf16_hi(xw[i]) + y[2 * i + 1];
+                }
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16(y[0], y[1]);
+            o.y = pack_bf16(y[2], y[3]);
+            o.z = pack_bf16(y[4], y[5]);
+            o.w = pack_bf16(y[6], y[7]);
+            // 128-byte swizzle of the staged block: 16-byte chunk index XOR (row & 7) — what the TMA store expects, and
+            // it spreads the 32 lanes of one store instruction over all banks
+            const int chunk = (half * 4 + g) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(sbuf + lane * 128 + chunk * 16) = o;
+          }
+          if (kReadsC) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) xcur[g] = xnext[g];
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_c, sbuf, nt * kPairBN + c64 * 64, row0);   // rows >= m and columns >= n are clipped by the tensor map
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+      // this warp has read its part of the accumulator: one arrival per warp on the leader's barrier
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the leader's MMAs read the peer's shared memory; nobody leaves before everything is consumed
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+template <int EPI>
+static int launch_gemm_pair(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const PairParams& p,
+                            cudaStream_t stream) {
+  auto kfn = gemm_pair_kernel<EPI>;
+  static unsigned long long configured = 0;  // per template instance and device
+  if (first_use_on_device(configured)) {
+    FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+  }
+  int clusters = ctx->sm_count / 2;
+  if (p.tiles < clusters) clusters = p.tiles;
+  kfn<<<2 * clusters, kPairThreads, kPairSmem, stream>>>(ta, tb, tc, p);
+  FGB_LAUNCH_CHECK("gemm_pair_kernel");
+  return FGB_OK;
+}
+
+// Supertile shape, from a sweep on the four GEMM shapes of the denoise step (tools/gemm_sweep.sh, profiles/r02_gemm_sweep*.log):
+// bands of at most 14 tile columns (a 3.6 K-column W band: 22 MB at K = 3072) and SMALL row groups — 4 tile rows, 2 for the
+// long-K FFN2 — so that the ~74 tiles in flight reuse each W tile a few times in quick succession while it is hot in L2 and the
+// A rows they share stay small. FGB_GEMM_BAND_N / FGB_GEMM_GROUP_M override, for tuning.
+static void pair_supertile(int m_tiles, int n_tiles, int k, int* group_m, int* band_n) {
+  static int env_gm = -1, env_bn = -1;
+  if (env_gm < 0) {
+    const char* e = getenv("FGB_GEMM_GROUP_M");
+    env_gm = e ? atoi(e) : 0;
+    e = getenv("FGB_GEMM_BAND_N");
+    env_bn = e ? atoi(e) : 0;
+  }
+  int bn = n_tiles < 14 ? n_tiles : 14;
+  const int bands = (n_tiles + bn - 1) / bn;
+  bn = (n_tiles + bands - 1) / bands;      // even out the bands (36 tile columns -> 3 bands of 12)
+  int gm = k >= 8192 ? 2 : 4;
+  if (gm > m_tiles) gm = m_tiles;
+  *group_m = env_gm > 0 ? env_gm : gm;
+  *band_n = env_bn > 0 ? env_bn : bn;
+}
+
 }  // namespace fgb
 
 extern "C" int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias,
@@ -350,7 +655,42 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
                   "fgb_gemm_bf16: gated residual needs 16-byte aligned gate0/gate1");
 
   CUtensorMap ta, tb, ta2, tb2;
-  int rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kBM);
+  int rc;
+  // the 2-CTA kernel takes the plain forward GEMMs with at least one full cluster tile of rows; everything else (tiny M: the
+  // time / text embeddings; the LoRA K-extension of the trainer) stays on the 1-CTA kernel
+  static int pair_enabled = -1;
+  if (pair_enabled < 0) {
+    const char* e = getenv("FGB_GEMM_PAIR");
+    pair_enabled = e ? atoi(e) : 1;
+  }
+  if (pair_enabled && k2 == 0 && m >= kPairTM && ctx->sm_count >= 2) {
+    CUtensorMap tc;
+    if ((rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kPairBM))) return rc;
+    if ((rc = make_tmap_bf16_2d(ctx, &tb, w, n, k, ldw, kPairBN / 2))) return rc;
+    if ((rc = make_tmap_bf16_2d(ctx, &tc, c, m, n, ldc, 32))) return rc;
+    PairParams pp;
+    pp.bias = static_cast<const __nv_bfloat16*>(bias);
+    pp.c = static_cast<__nv_bfloat16*>(c);
+    pp.gate0 = static_cast<const __nv_bfloat16*>(gate0);
+    pp.gate1 = static_cast<const __nv_bfloat16*>(gate1);
+    pp.ldc = ldc;
+    pp.m = m;
+    pp.n = n;
+    pp.rows_gate0 = rows_gate0;
+    pp.m_tiles = (m + kPairTM - 1) / kPairTM;
+    pp.n_tiles = (n + kPairBN - 1) / kPairBN;
+    pp.tiles = pp.m_tiles * pp.n_tiles;
+    pp.k_blocks = (k + kBK - 1) / kBK;
+    pair_supertile(pp.m_tiles, pp.n_tiles, k, &pp.group_m, &pp.band_n);
+    cudaStream_t ps = static_cast<cudaStream_t>(stream);
+    switch (epilogue) {
+      case FGB_EPI_BIAS: return launch_gemm_pair<FGB_EPI_BIAS>(ctx, ta, tb, tc, pp, ps);
+      case FGB_EPI_BIAS_GELU_TANH: return launch_gemm_pair<FGB_EPI_BIAS_GELU_TANH>(ctx, ta, tb, tc, pp, ps);
+      case FGB_EPI_GATED_RESIDUAL: return launch_gemm_pair<FGB_EPI_GATED_RESIDUAL>(ctx, ta, tb, tc, pp, ps);
+      default: return launch_gemm_pair<FGB_EPI_RESIDUAL>(ctx, ta, tb, tc, pp, ps);
+    }
+  }
+  rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kBM);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(ctx, &tb, w, n, k, ldw, kBN);
   if (rc) return rc;

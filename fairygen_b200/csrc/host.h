@@ -21,6 +21,16 @@ struct fgb_ctx {
                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
   CUresult (*mem_get_address_range)(CUdeviceptr* base, size_t* size, CUdeviceptr ptr) = nullptr;
   int32_t* attn_stats = nullptr;   // caller-owned device int32[3] (fgb_attn_set_stats) or NULL
+  // Encoded tensor maps, keyed by (base, rows, cols, ld, box): a denoise step re-uses the same ~40 (pointer, shape) pairs for
+  // its 600 GEMM / attention launches, so the driver's encoder runs once per pair instead of three times per launch.
+  struct TmapSlot {
+    const void* base = nullptr;
+    int64_t rows = 0, cols = 0, ld = 0;
+    int32_t box_rows = 0;
+    CUtensorMap map;
+  };
+  static constexpr int kTmapSlots = 512;
+  mutable TmapSlot tmap_cache[kTmapSlots];
 };
 
 #define FGB_MAX_PEERS 8  // one NVSwitch box

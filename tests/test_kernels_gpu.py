@@ -29,11 +29,13 @@ def rnd(*shape, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 256, 64), (2, 768, 256), (200, 192, 192), (1000, 3072, 3072), (513, 1536, 256),
-                                   (300, 512, 4096), (2049, 14336, 3072)])
+                                   (300, 512, 4096), (2049, 14336, 3072),
+                                   # the 2-CTA kernel (m >= 256): exact tiles, ragged rows / columns / k, one tile, many waves
+                                   (256, 256, 64), (257, 200, 72), (384, 8, 8), (511, 264, 136), (20000, 3072, 512)])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 def test_gemm_epilogues(env, m, n, k, epi):
     ops, o = env
-    if epi != 0 and m * n * k > 3e10:
+    if epi != 0 and m * n * k > 3.2e10:
         pytest.skip("large shape checked with the plain epilogue only")
     a, w, bias = rnd(m, k, seed=1), rnd(n, k, seed=2, scale=1 / math.sqrt(k)), rnd(n, seed=3, scale=0.5)
     g0, g1, c0 = rnd(n, seed=4), rnd(n, seed=5), rnd(m, n, seed=6)
@@ -359,3 +361,37 @@ def test_bounded_score_attention(env, s_q, s_kv, heads, scale_q):
     km = torch.empty(3, dtype=torch.float32, device="cuda")
     ops.head_norm_max(kk, km, 3)
     assert torch.allclose(km, (kk.float().reshape(257, 3, 128) ** 2).sum(-1).max(0).values, rtol=1e-5)
+
+
+@pytest.mark.parametrize("scale_q,want_mode", [(1.0, "bound_only"), (4.0, "bound_only"), (9.0, "first_tile_anchored"),
+                                               (40.0, "running_max_fallback")])
+def test_bounded_attention_reference_modes(env, scale_q, want_mode):
+    """The three per-CTA modes of fgb_attn_fwd_bounded (AttnParams::kmax): bound <= 110 -> fixed reference from the bound alone;
+    larger bounds -> anchored on the first tile's maximum; hopeless bounds -> running-max fallback.  All must give the same
+    softmax, the CTA counters (fgb_attn_set_stats) must say which one ran, and a partial last KV tile must not leak
+    probability mass (masked keys contribute exactly 0)."""
+    ops, o = env
+    heads, s_q, s_kv = 2, 600, 1000     # 1000 keys: the last KV tile has 104 live keys (wg1 of the last tile sees 40)
+    d = heads * 128
+    q, k, v = rnd(s_q, d, seed=1, scale=scale_q), rnd(s_kv, d, seed=2), rnd(s_kv, d, seed=3)
+    kmax2 = torch.empty(heads, dtype=torch.float32, device="cuda")
+    ops.head_norm_max(k, kmax2, heads)
+    bound = float((q.float().view(s_q, heads, 128).norm(dim=-1).max() * kmax2.max().sqrt()) / math.sqrt(128) * math.log2(math.e))
+    out = torch.full((s_q, d), float("nan"), dtype=BF, device="cuda")
+    lse = torch.empty(heads, ops.stat_rows(s_q), dtype=torch.float32, device="cuda")
+    ops.attention_stats_reset(q.device)
+    ops.attention(q, k, v, out, heads, lse=lse, kmax2=kmax2)
+    ops.sync_check()
+    detail = ops.attention_stats_detail(q.device)
+    print(f"scale_q {scale_q}: max bound {bound:.1f} log2 units, CTAs per mode {detail}")
+    assert detail[want_mode] > 0 and sum(detail.values()) == heads * ((s_q + 255) // 256)
+    ref = o.attention(q[None].float(), k[None].float(), v[None].float(), heads)[0]
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 6e-3
+    sc = torch.einsum("qhd,khd->hqk", q.float().view(s_q, heads, 128), k.float().view(s_kv, heads, 128)) / math.sqrt(128)
+    assert (lse[:, :s_q] - torch.logsumexp(sc, dim=-1) * math.log2(math.e)).abs().max() < 5e-3 * max(1.0, scale_q)
+    # V == 1: every output must be exactly 1 (the row sum and the numerator see the same P, masked keys add nothing)
+    ones = torch.ones_like(v)
+    ops.attention(q, k, ones, out, heads, kmax2=kmax2)
+    ops.sync_check()
+    assert (out.float() - 1).abs().max() < 8e-3
