@@ -102,12 +102,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_wait_parked(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], kTileBytes);
         for (int b = 0; b < 2; ++b)
           tma_load_2d(smem_k + st * kTileBytes + b * kBoxBytes, &tmap_k, &k_full[st], head * 128 + b * 64,
                       (kv_lo + j) * kTile, kEvictLast);
-        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_wait_parked(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], kTileBytes);
         for (int b = 0; b < 2; ++b)
           tma_load_2d(smem_v + st * kTileBytes + b * kBoxBytes, &tmap_v, &v_full[st], head * 128 + b * 64,
@@ -138,7 +138,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint64_t vd = v_desc + static_cast<uint64_t>((st * kTileBytes) >> 4);
         const uint32_t d_tmem = tmem_base + 256 + i * 128;
         const uint32_t p_tmem = tmem_base + i * 128;
-        mbar_wait(&p_ready[i], j & 1);
+        mbar_wait_parked(&p_ready[i], j & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA: 16 rows of 128 B in each d-half box
@@ -147,8 +147,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         tc_commit(&pv_done[i]);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
+      mbar_wait_parked(q_full, 0);
+      mbar_wait_parked(&k_full[0], 0);
       tc_fence_after();
       issue_s(0, 0);
       issue_s(1, 0);
@@ -156,13 +156,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         const int st1 = (j + 1) & 1;
-        mbar_wait(&v_full[st], (j >> 1) & 1);
+        mbar_wait_parked(&v_full[st], (j >> 1) & 1);
         for (int i = 0; i < 2; ++i) {
           issue_pv(i, st, j);
           if (i == 1) tc_commit(&v_empty[st]);
           if (j + 1 < n_kv) {
             if (i == 0) {
-              mbar_wait(&k_full[st1], ((j + 1) >> 1) & 1);
+              mbar_wait_parked(&k_full[st1], ((j + 1) >> 1) & 1);
               tc_fence_after();
             }
             issue_s(i, st1);
@@ -315,77 +315,94 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (p.stats != nullptr && threadIdx.x == 0) atomicAdd(p.stats + mode, 1);
     }
 
-    for (int j = 0; j < n_kv; ++j) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {   // both warpgroups work on query tile i together
-        const uint32_t t_s = tmem_base + lane_bits + i * 128 + wg * 64;  // this thread's 64 score columns
-        const uint32_t t_o = tmem_base + lane_bits + 256 + i * 128;
-        mbar_wait(&s_full[i], j & 1);
-        tc_fence_after();
+    // One (KV tile j, query tile i) step of this thread. MODE and LAST are compile-time so that the steady-state loop of
+    // each mode is one compact instruction stream (a runtime dispatch inside the loop cost instruction-cache misses):
+    // only the last KV tile of a CTA can be partial, so the -inf masking and the MUFU-only sweep live in the peeled copy.
+    auto tile_step = [&](auto mode_tag, auto last_tag, int j, int i) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      constexpr bool LAST = decltype(last_tag)::value;
+      const uint32_t t_s = tmem_base + lane_bits + i * 128 + wg * 64;  // this thread's 64 score columns
+      const uint32_t t_o = tmem_base + lane_bits + 256 + i * 128;
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      bool partial = false;
+      if (LAST) {
         const int valid = p.s_kv - (kv_lo + j) * kTile - wg * 64;  // keys of this half-tile that exist
-        const bool partial = valid < 64;
+        partial = valid < 64;
         if (partial) mask_partial(t_s, valid);
-        uint32_t pk[32];
-        float row_max, sum;
-        bool redo = false;
-        if (mode < 2) {            // no maximum, no exchange, no rescale: one pass of exponentials
-          if (partial) l[i] += sweep(TagTrue{}, TagFalse{}, ExpMufu{}, t_s, m[i], row_max, pk);
-          else if (mode == 0) l[i] += sweep(TagTrue{}, TagFalse{}, ExpMixed{}, t_s, m[i], row_max, pk);
-          else l[i] += sweep(TagTrue{}, TagFalse{}, ExpMixedClamp{}, t_s, m[i], row_max, pk);
-          tmem_st32(t_s, pk);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&p_ready[i]);
-          continue;
-        }
-        if (EMU == 8) {            // DEBUG (FGB_ATTN_EMU=8): no softmax work at all — the tensor / barrier skeleton alone
-          tc_fence_before();
-          mbar_arrive(&p_ready[i]);
-          continue;
-        }
-        auto exp_sweep = [&]() -> float {   // exponentials against m[i] with the side maximum; masked tiles take the MUFU
-          return partial ? sweep(TagTrue{}, TagTrue{}, ExpMufu{}, t_s, m[i], row_max, pk)
-                         : sweep(TagTrue{}, TagTrue{}, ExpMixedClamp{}, t_s, m[i], row_max, pk);
-        };
-        if (j == 0) {
-          sweep(TagFalse{}, TagTrue{}, ExpMufu{}, t_s, 0.f, row_max, pk);  // exact maximum of the first tile
-          row_max = fmaxf(row_max, swap_rows(row_max));
-          m[i] = row_max * p.scale_log2;
-          redo = true;
-        } else {
-          // Speculate that the running maximum has not grown by more than 2^8: exponentiate against the stale
-          // maximum while the true maximum is computed on the side (MUFU and ALU pipes in parallel).
-          sum = exp_sweep();
-          if (kEmu != 9) row_max = fmaxf(row_max, swap_rows(row_max));   // maximum of the whole 128-key row
-          const float m_new = kEmu == 9 ? m[i] : fmaxf(m[i], row_max * p.scale_log2);
-          // both threads of a row see the same m_new, so both warps of the pair take the same branch
-          if (__any_sync(0xffffffffu, m_new - m[i] > 8.0f)) {
-            // rare: rescale the running sum and this warpgroup's half of the O accumulator by 2^(m - m_new), redo the tile
-            const float alpha = fast_exp2(m[i] - m_new);
-            l[i] *= alpha;
-            m[i] = m_new;
-            mbar_wait(&pv_done[i], (j - 1) & 1);  // O_i must be quiescent
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-              uint32_t orr[32];
-              tmem_ld32(t_o + wg * 64 + c * 32, orr);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 32; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
-              tmem_st32(t_o + wg * 64 + c * 32, orr);
-            }
-            redo = true;
-          }
-        }
-        if (redo) sum = exp_sweep();  // S is still intact in TMEM: P has not been stored yet
+      }
+      uint32_t pk[32];
+      float row_max, sum;
+      if (MODE < 2) {            // no maximum, no exchange, no rescale: one pass of exponentials
+        if (LAST && partial) sum = sweep(TagTrue{}, TagFalse{}, ExpMufu{}, t_s, m[i], row_max, pk);
+        else if (MODE == 0) sum = sweep(TagTrue{}, TagFalse{}, ExpMixed{}, t_s, m[i], row_max, pk);
+        else sum = sweep(TagTrue{}, TagFalse{}, ExpMixedClamp{}, t_s, m[i], row_max, pk);
         l[i] += sum;
-        tmem_st32(t_s, pk);   // P over this thread's own first 32 (consumed) score columns
+        tmem_st32(t_s, pk);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[i]);
+        return;
       }
-    }
+      if (EMU == 8) {            // DEBUG (FGB_ATTN_EMU=8): no softmax work at all — the tensor / barrier skeleton alone
+        tc_fence_before();
+        mbar_arrive(&p_ready[i]);
+        return;
+      }
+      bool redo = false;
+      auto exp_sweep = [&]() -> float {   // exponentials against m[i] with the side maximum; masked tiles take the MUFU
+        return (LAST && partial) ? sweep(TagTrue{}, TagTrue{}, ExpMufu{}, t_s, m[i], row_max, pk)
+                                 : sweep(TagTrue{}, TagTrue{}, ExpMixedClamp{}, t_s, m[i], row_max, pk);
+      };
+      if (j == 0) {
+        sweep(TagFalse{}, TagTrue{}, ExpMufu{}, t_s, 0.f, row_max, pk);  // exact maximum of the first tile
+        row_max = fmaxf(row_max, swap_rows(row_max));
+        m[i] = row_max * p.scale_log2;
+        redo = true;
+      } else {
+        // Speculate that the running maximum has not grown by more than 2^8: exponentiate against the stale
+        // maximum while the true maximum is computed on the side (MUFU and ALU pipes in parallel).
+        sum = exp_sweep();
+        if (kEmu != 9) row_max = fmaxf(row_max, swap_rows(row_max));   // maximum of the whole 128-key row
+        const float m_new = kEmu == 9 ? m[i] : fmaxf(m[i], row_max * p.scale_log2);
+        // both threads of a row see the same m_new, so both warps of the pair take the same branch
+        if (__any_sync(0xffffffffu, m_new - m[i] > 8.0f)) {
+          // rare: rescale the running sum and this warpgroup's half of the O accumulator by 2^(m - m_new), redo the tile
+          const float alpha = fast_exp2(m[i] - m_new);
+          l[i] *= alpha;
+          m[i] = m_new;
+          mbar_wait(&pv_done[i], (j - 1) & 1);  // O_i must be quiescent
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(t_o + wg * 64 + c * 32, orr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
+            tmem_st32(t_o + wg * 64 + c * 32, orr);
+          }
+          redo = true;
+        }
+      }
+      if (redo) sum = exp_sweep();  // S is still intact in TMEM: P has not been stored yet
+      l[i] += sum;
+      tmem_st32(t_s, pk);   // P over this thread's own first 32 (consumed) score columns
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[i]);
+    };
+    auto run_tiles = [&](auto mode_tag) {
+      for (int j = 0; j + 1 < n_kv; ++j) {
+        tile_step(mode_tag, TagFalse{}, j, 0);   // both warpgroups work on query tile 0 together, then on tile 1
+        tile_step(mode_tag, TagFalse{}, j, 1);
+      }
+      tile_step(mode_tag, TagTrue{}, n_kv - 1, 0);
+      tile_step(mode_tag, TagTrue{}, n_kv - 1, 1);
+    };
+    if (mode == 0) run_tiles(ModeTag<0>{});
+    else if (mode == 1) run_tiles(ModeTag<1>{});
+    else run_tiles(ModeTag<2>{});
 
     // ---- epilogue: each warpgroup normalises and stores its 64 of the 128 output columns of both tiles
 #pragma unroll 1

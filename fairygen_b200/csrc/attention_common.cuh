@@ -99,6 +99,8 @@ __device__ __forceinline__ void exp2_emulated(uint64_t x2, float& r0, float& r1)
 
 struct TagTrue { static constexpr bool value = true; };
 struct TagFalse { static constexpr bool value = false; };
+template <int M>
+struct ModeTag { static constexpr int value = M; };
 // how a sweep turns scores into exponentials
 struct ExpMixed { static constexpr int value = 0; };       // MUFU + FMA-pipe emulation, no clamp (mode 0, full tiles)
 struct ExpMixedClamp { static constexpr int value = 1; };  // MUFU + clamped emulation (anchored / running-max references)

@@ -84,6 +84,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > FGB_SPIN_LIMIT) __trap();
   }
 }
+// Same wait for the single-thread roles (TMA / MMA issuer) that share an SM sub-partition with compute warps: the suspend-time
+// hint lets the hardware park the thread until the phase completes (or the hint expires) instead of re-issuing the probe +
+// branch every few dozen cycles, which would take issue slots from the compute warps of that sub-partition.
+#ifndef FGB_WAIT_HINT_NS
+#define FGB_WAIT_HINT_NS 100000
+#endif
+#ifndef FGB_PARKED_WAITS
+#define FGB_PARKED_WAITS 1
+#endif
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  if (!FGB_PARKED_WAITS) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(FGB_WAIT_HINT_NS))
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 18)) __trap();   // ~26 s of parked waits
+  }
+}
 // Cluster-scope acquire variant, for barriers that peer CTAs / multicast TMA arrive on.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;

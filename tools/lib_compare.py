@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--what", default="attn,gemm")
     ap.add_argument("--seconds", type=float, default=1.0)
     ap.add_argument("--tokens", type=int, default=27280)
+    ap.add_argument("--ours-only", action="store_true", help="A/B of library builds (FGB_LIB_PATH): skip the vendor kernels")
     args = ap.parse_args()
     from torch.nn.attention import SDPBackend, sdpa_kernel
 
@@ -73,7 +74,8 @@ def main():
 
             res = {"kernel": f"attention S_q={S} S_kv={s_kv}"}
             for rnd in range(2):   # twice, alternating, so neither side always runs on the hotter chip
-                for name, fn in (("ours_bounded", ours), ("cudnn_sdpa", cudnn), ("ours_running_max", ours_runmax)):
+                impls = (("ours_bounded", ours),) if args.ours_only else (("ours_bounded", ours), ("cudnn_sdpa", cudnn), ("ours_running_max", ours_runmax))
+                for name, fn in impls:
                     r = sustained(fn, args.seconds)
                     r["sustained_tflops"] = round(fl / r["sustained_ms"] / 1e9, 1)
                     r["first10_tflops"] = round(fl / r["first10_ms"] / 1e9, 1)
@@ -89,7 +91,8 @@ def main():
             fl = 2.0 * S * n * kk
             res = {"kernel": f"gemm {name} {S}x{n}x{kk}"}
             for rnd in range(2):
-                for lab, fn in (("ours", lambda: ops.gemm(a, w, b, c)), ("cublas", lambda: F.linear(a, w, b))):
+                impls = (("ours", lambda: ops.gemm(a, w, b, c)),) if args.ours_only else (("ours", lambda: ops.gemm(a, w, b, c)), ("cublas", lambda: F.linear(a, w, b)))
+                for lab, fn in impls:
                     r = sustained(fn, args.seconds)
                     r["sustained_tflops"] = round(fl / r["sustained_ms"] / 1e9, 1)
                     r["first10_tflops"] = round(fl / r["first10_ms"] / 1e9, 1)
