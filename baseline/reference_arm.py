@@ -293,7 +293,7 @@ def gpu_reference_forward(cfg, state_dict, latents, timestep, context, dev, forw
             if i > 0:
                 times.append((time.perf_counter() - t0) * 1e3)
     del dit
-    return out, median(times), backend
+    return out, (median(times) if times else None), backend
 
 
 def gpu_reference_denoise(cfg, state_dict, latents, z0, ctx_pos, ctx_neg, dev, steps, num_inference_steps=50, cfg_scale=5.0, shift=5.0):

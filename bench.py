@@ -188,6 +188,8 @@ class Harness:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"   # the version banner goes to stdout, in front of the one JSON line
             dist.init_process_group("nccl", init_method="env://", device_id=self.dev)
         self.cfg = fg.TI2V_5B
         self.sd = synthetic.random_state_dict(self.cfg, seed=0, device=self.dev, dtype=torch.bfloat16, lora_rank=LORA_RANK)
@@ -293,7 +295,7 @@ def _step(den, index, dev_inputs):
     return den.step(index % den.num_steps, lat, cp, cn, z0)
 
 
-def parity_block(h: Harness, den_par):
+def parity_block(h: Harness, den_par, eng_sp=None):
     """2 denoise steps at the ragged shape under the parallel layout vs (a) a plain single-rank engine on rank 0 and (b) the
     UNMODIFIED reference's bf16 denoise loop on rank 0's GPU (its own scheduler + model_fn).  Every rank takes part in the parallel
     run; rank 0 alone runs the comparisons while the others wait at the barrier."""
@@ -306,6 +308,9 @@ def parity_block(h: Harness, den_par):
     lat_par = lat.clone()
     for i in steps:
         den_par.step(i, lat_par, cp, cn, z0)
+    # one DiT forward under PURE Ulysses over all ranks (every rank takes part): the per-forward number of the north star
+    ts0 = den_par.model_timesteps[0:1]
+    fwd_sp = eng_sp.forward(lat, ts0, cp, True) if eng_sp is not None else None
     h.barrier()
     tokens = shape[2] * (shape[3] // 2) * (shape[4] // 2)
     out = {"shape": f"{PARITY_SHAPE[0]}x{PARITY_SHAPE[1]}x{PARITY_SHAPE[2]} (S={tokens})", "denoise_steps": len(steps), "tol": PARITY_TOL}
@@ -324,11 +329,15 @@ def parity_block(h: Harness, den_par):
             lat_ref = ra.gpu_reference_denoise(h.cfg, h.sd, lat, z0, cp, cn, dev, steps, NUM_INFERENCE_STEPS, CFG_SCALE, SIGMA_SHIFT)
             out["rel_l2_vs_reference_bf16"] = rel(lat_par, lat_ref)
             out["rel_l2_single_vs_reference_bf16"] = rel(lat_one, lat_ref)
+            if fwd_sp is not None:
+                want, _, _ = ra.gpu_reference_forward(h.cfg, h.sd, lat, ts0.to(device=dev, dtype=torch.bfloat16), cp, dev, forwards=0)
+                out["rel_l2_vs_reference_bf16_one_forward_pure_sp"] = rel(fwd_sp, want)
+                out["pure_sp_ways"] = eng_sp.sp.world
             out["reference"] = "unmodified reference denoise loop body (baseline/_ref: model_fn_wan_video x2, CFG, FlowMatchScheduler.step) in bf16 on rank 0"
         else:
             out["rel_l2_vs_reference_bf16"] = None
             out["reference"] = "baseline/_ref not installed"
-        worst = max(v for k, v in out.items() if k.startswith("rel_l2_vs") and v is not None)
+        worst = max(v for k, v in out.items() if k.startswith("rel_l2_vs") and isinstance(v, float))
         out["ok"] = bool(worst <= PARITY_TOL and torch.isfinite(lat_par.float()).all())
         del single
         torch.cuda.empty_cache()
@@ -405,9 +414,10 @@ def run_ours(args):
                 _step(den2, i, inputs2)
             ms2 = h.time_steps(den2, inputs2, 2, min(args.steps, 4))
             layouts[label2] = round(1e3 / ms2, 4)
-        del den2, eng2
+        eng_sp = eng2 if args.layout == "auto" else engine      # the engine whose Ulysses group spans all ranks
+        parity = parity_block(h, den, eng_sp if (eng_sp.sp is not None and eng_sp.sp.world == world) else None)
+        del den2, eng2, eng_sp
         torch.cuda.empty_cache()
-        parity = parity_block(h, den)
         flag = torch.tensor([1 if (rank != 0 or parity.get("ok", False)) else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         parity_ok = bool(flag.item())

@@ -49,7 +49,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* k_empty = bars + 5;     // [2]
   uint64_t* v_empty = bars + 7;     // [2]
   uint64_t* s_full = bars + 9;      // [2] per query tile: S_i written by the tensor core
-  uint64_t* p_ready = bars + 11;    // [2] per query tile: P_i stored (and O_i rescaled) by 128 threads
+  uint64_t* p_ready = bars + 11;    // [2] per query tile: first half of every thread's P_i (32 of its 64 keys) stored
+  uint64_t* p_ready2 = bars + 18;   // [2] per query tile: second half stored (and O_i rescaled) — PV starts on the first half
   uint64_t* pv_done = bars + 13;    // [2] per query tile: O_i += P_i V_j finished
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   float* xchg = reinterpret_cast<float*>(bars + 32);   // [2 slots][2 column halves][128 rows]
@@ -81,6 +82,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 256);
+      mbar_init(&p_ready2[i], 256);
       mbar_init(&pv_done[i], 1);
     }
     fence_mbar_init();
@@ -138,12 +140,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint64_t vd = v_desc + static_cast<uint64_t>((st * kTileBytes) >> 4);
         const uint32_t d_tmem = tmem_base + 256 + i * 128;
         const uint32_t p_tmem = tmem_base + i * 128;
+        // 16 keys per MMA: 16 rows of 128 B in each d-half box. P arrives in two halves: MMAs 0,1 / 4,5 consume the first 32
+        // keys of each warpgroup's 64, MMAs 2,3 / 6,7 the second — the tensor core starts PV while the softmax warps are
+        // still exponentiating the second half of the tile.
         mbar_wait_parked(&p_ready[i], j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA: 16 rows of 128 B in each d-half box
-          umma_ts(d_tmem, p_tmem + (kk & 3) * 8 + (kk >> 2) * 64, vd + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv,
-                  (j | kk) != 0);
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1) {
+            mbar_wait_parked(&p_ready2[i], j & 1);
+            tc_fence_after();
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int kk = g * 4 + h * 2 + t;
+              umma_ts(d_tmem, p_tmem + (kk & 3) * 8 + (kk >> 2) * 64, vd + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv,
+                      (j | h | g | t) != 0);
+            }
         }
         tc_commit(&pv_done[i]);
       };
@@ -194,7 +209,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // One pass over this thread's 64 scores, 32 at a time (the second TMEM load is in flight while the first chunk is
     // processed): tracks the maximum and, if EXPS, writes P = 2^(s*scale - m_used) as packed bf16 into pk and
     // returns the sum. KIND selects how the exponentials are made (ExpMixed / ExpMixedClamp / ExpMufu).
-    auto sweep = [&](auto exps_tag, auto max_tag, auto kind_tag, uint32_t t_s, float m_used, float& row_max, uint32_t (&pk)[32]) -> float {
+    // early_bar != nullptr: the first 32 keys' P (pk[0..15]) are stored to TMEM and announced on early_bar as soon as they
+    // exist, before the second 32 scores are touched.
+    auto sweep = [&](auto exps_tag, auto max_tag, auto kind_tag, uint32_t t_s, float m_used, float& row_max, uint32_t (&pk)[32],
+                     uint64_t* early_bar = nullptr) -> float {
       constexpr bool EXPS = decltype(exps_tag)::value;
       constexpr bool MAXV = decltype(max_tag)::value;
       constexpr int KIND = decltype(kind_tag)::value;
@@ -230,6 +248,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
             acc[e & 3] = add2(acc[e & 3], pack2(p0, p1));
             pk[c * 16 + e] = pack_bf16(p0, p1);
+          }
+          if (c == 0 && early_bar != nullptr) {
+            tmem_st16(t_s, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(early_bar);
           }
         }
       }
@@ -334,19 +358,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint32_t pk[32];
       float row_max, sum;
       if (MODE < 2) {            // no maximum, no exchange, no rescale: one pass of exponentials
-        if (LAST && partial) sum = sweep(TagTrue{}, TagFalse{}, ExpMufu{}, t_s, m[i], row_max, pk);
-        else if (MODE == 0) sum = sweep(TagTrue{}, TagFalse{}, ExpMixed{}, t_s, m[i], row_max, pk);
-        else sum = sweep(TagTrue{}, TagFalse{}, ExpMixedClamp{}, t_s, m[i], row_max, pk);
+        if (LAST && partial) sum = sweep(TagTrue{}, TagFalse{}, ExpMufu{}, t_s, m[i], row_max, pk, &p_ready[i]);
+        else if (MODE == 0) sum = sweep(TagTrue{}, TagFalse{}, ExpMixed{}, t_s, m[i], row_max, pk, &p_ready[i]);
+        else sum = sweep(TagTrue{}, TagFalse{}, ExpMixedClamp{}, t_s, m[i], row_max, pk, &p_ready[i]);
         l[i] += sum;
-        tmem_st32(t_s, pk);
+        tmem_st16(t_s + 16, pk + 16);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_ready[i]);
+        mbar_arrive(&p_ready2[i]);
         return;
       }
       if (EMU == 8) {            // DEBUG (FGB_ATTN_EMU=8): no softmax work at all — the tensor / barrier skeleton alone
         tc_fence_before();
         mbar_arrive(&p_ready[i]);
+        mbar_arrive(&p_ready2[i]);
         return;
       }
       bool redo = false;
@@ -390,7 +415,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_st32(t_s, pk);   // P over this thread's own first 32 (consumed) score columns
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_ready[i]);
+      mbar_arrive(&p_ready[i]);    // the running-max path needs the whole row before any P exists: both halves at once
+      mbar_arrive(&p_ready2[i]);
     };
     auto run_tiles = [&](auto mode_tag) {
       for (int j = 0; j + 1 < n_kv; ++j) {

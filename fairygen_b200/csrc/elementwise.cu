@@ -438,10 +438,10 @@ static int launch_ln(int nv, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, 
     ln_kernel<NV, AFFINE><<<grid, kRowWarps * 32, 0, s>>>(x, ldx, y, ldy, rows, eps, sh0, sc0, sh1, sc1, rows_mod0); \
     break;
   switch (nv) {
-    FGB_LN_CASE(1) FGB_LN_CASE(2) FGB_LN_CASE(4) FGB_LN_CASE(6) FGB_LN_CASE(8) FGB_LN_CASE(12) FGB_LN_CASE(16)
+    FGB_LN_CASE(1) FGB_LN_CASE(2) FGB_LN_CASE(3) FGB_LN_CASE(4) FGB_LN_CASE(6) FGB_LN_CASE(8) FGB_LN_CASE(12) FGB_LN_CASE(16)
     FGB_LN_CASE(20)
     default:
-      return set_error(FGB_ERR_UNSUPPORTED, "layer norm: dim %d is not one of 256*{1,2,4,6,8,12,16,20}", nv * 256);
+      return set_error(FGB_ERR_UNSUPPORTED, "layer norm: dim %d is not one of 256*{1,2,3,4,6,8,12,16,20}", nv * 256);
   }
 #undef FGB_LN_CASE
   FGB_LAUNCH_CHECK("ln_kernel");
@@ -503,10 +503,10 @@ extern "C" int fgb_rmsnorm_rope(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows
     rmsnorm_rope_kernel<NV, false><<<grid, kRowWarps * 32, 0, s>>>(xp, ldx, rows, eps, wp, tab, gf, gh, gw, token_offset, none); \
     break;
   switch (dim / 256) {
-    FGB_RMS_CASE(1) FGB_RMS_CASE(2) FGB_RMS_CASE(4) FGB_RMS_CASE(6) FGB_RMS_CASE(8) FGB_RMS_CASE(12) FGB_RMS_CASE(16)
+    FGB_RMS_CASE(1) FGB_RMS_CASE(2) FGB_RMS_CASE(3) FGB_RMS_CASE(4) FGB_RMS_CASE(6) FGB_RMS_CASE(8) FGB_RMS_CASE(12) FGB_RMS_CASE(16)
     FGB_RMS_CASE(20)
     default:
-      return set_error(FGB_ERR_UNSUPPORTED, "rmsnorm: dim %d is not one of 256*{1,2,4,6,8,12,16,20}", dim);
+      return set_error(FGB_ERR_UNSUPPORTED, "rmsnorm: dim %d is not one of 256*{1,2,3,4,6,8,12,16,20}", dim);
   }
 #undef FGB_RMS_CASE
   FGB_LAUNCH_CHECK("rmsnorm_rope_kernel");
@@ -679,10 +679,10 @@ extern "C" int fgb_rmsnorm_rope_scatter(fgb_ctx* ctx, const void* x, int64_t ldx
     rmsnorm_rope_kernel<NV, true><<<grid, kRowWarps * 32, 0, s>>>(xp, ldx, rows, eps, wp, tab, gf, gh, gw, token_offset, sc); \
     break;
   switch (dim / 256) {
-    FGB_RMS_CASE(1) FGB_RMS_CASE(2) FGB_RMS_CASE(4) FGB_RMS_CASE(6) FGB_RMS_CASE(8) FGB_RMS_CASE(12) FGB_RMS_CASE(16)
+    FGB_RMS_CASE(1) FGB_RMS_CASE(2) FGB_RMS_CASE(3) FGB_RMS_CASE(4) FGB_RMS_CASE(6) FGB_RMS_CASE(8) FGB_RMS_CASE(12) FGB_RMS_CASE(16)
     FGB_RMS_CASE(20)
     default:
-      return set_error(FGB_ERR_UNSUPPORTED, "rmsnorm: dim %d is not one of 256*{1,2,4,6,8,12,16,20}", dim);
+      return set_error(FGB_ERR_UNSUPPORTED, "rmsnorm: dim %d is not one of 256*{1,2,3,4,6,8,12,16,20}", dim);
   }
 #undef FGB_RMS_CASE
   FGB_LAUNCH_CHECK("rmsnorm_rope_kernel<scatter>");
