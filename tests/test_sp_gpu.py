@@ -268,3 +268,59 @@ def test_vae_windows_over_two_gpus(tmp_path):
     for r in range(2):
         res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         assert res["finite"] and res["err"] < 1e-2, res       # bf16 output; fp32 sums of 2-4 contributions in another order
+
+
+def _bcast_worker(rank, world, port, ckpt_pattern, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+
+    import fairygen_b200 as fg
+    from fairygen_b200 import synthetic, weights
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    eng = fg.WanDiTEngine(cfg, dev)
+    if rank != 0:
+        def forbidden(*a, **k):
+            raise AssertionError("a non-source rank read the checkpoint from disk")
+        real_load, weights.load_state_dict = weights.load_state_dict, forbidden
+    weights.load_engine_broadcast(eng, ckpt_pattern, src=0)
+    if rank != 0:
+        weights.load_state_dict = real_load
+    direct = fg.WanDiTEngine(cfg, dev)
+    direct.load_state_dict(weights.load_state_dict(ckpt_pattern, device=dev))
+    same = all(torch.equal(a, b) for a, b in zip(weights.packed_tensors(eng), weights.packed_tensors(direct)))
+    lat, z0, cp, cn = synthetic.synthetic_inputs(cfg, (1, 48, 3, 8, 8), text_len=32, live_text=8, pin=False)
+    ts = torch.tensor([900.0])
+    out = eng.forward(lat.to(dev), ts, cp.to(dev), True)
+    ref = direct.forward(lat.to(dev), ts, cp.to(dev), True)
+    fg.ops.sync_check()
+    torch.save({"same": same, "forward_equal": bool(torch.equal(out, ref))}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_load_engine_broadcast_two_gpus(tmp_path):
+    """weights.load_engine_broadcast over NCCL / NVLink: rank 0 reads the sharded checkpoint, rank 1 receives the packed tensors
+    (models/model_loader.py:62-80 has every rank read everything)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import safetensors.torch as st
+    import torch.multiprocessing as mp
+
+    import fairygen_b200 as fg
+    from fairygen_b200.synthetic import param_shapes
+
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    g = torch.Generator().manual_seed(3)
+    sd = {k: torch.randn(s, generator=g).to(BF) for k, s in param_shapes(cfg).items()}
+    names = sorted(sd)
+    st.save_file({k: sd[k] for k in names[::2]}, str(tmp_path / "diffusion_pytorch_model-00001-of-00002.safetensors"))
+    st.save_file({k: sd[k] for k in names[1::2]}, str(tmp_path / "diffusion_pytorch_model-00002-of-00002.safetensors"))
+    mp.spawn(_bcast_worker, args=(2, _free_port(), os.path.join(str(tmp_path), "diffusion_pytorch_model*.safetensors"), str(tmp_path)),
+             nprocs=2, join=True)
+    for r in range(2):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert res["same"] and res["forward_equal"], res
