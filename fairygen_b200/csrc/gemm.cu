@@ -337,11 +337,10 @@ static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
 // group_m x band_n tiles so that a W band and an A group stay L2-resident while they are being reused.
 constexpr int kPairBM = 128;       // rows per CTA
 constexpr int kPairTM = 256;       // rows per cluster tile
-constexpr int kPairBN = 256;
 constexpr int kPairStages = 5;
 constexpr int kPairABytes = kPairBM * kBK * 2;          // 16 KB
-constexpr int kPairBBytes = (kPairBN / 2) * kBK * 2;    // 16 KB: this CTA's half of the W tile
-constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
+constexpr int kPairBBytesMax = (256 / 2) * kBK * 2;     // 16 KB: this CTA's half of a 256-column W tile
+constexpr int kPairStageBytes = kPairABytes + kPairBBytesMax;
 constexpr int kPairStoreBytes = 32 * 128;               // one staged block: 32 rows x 64 bf16
 constexpr int kPairStagingBytes = 4 * 2 * kPairStoreBytes;   // 4 epilogue warps x 2 buffers
 constexpr int kPairThreads = 192;
@@ -374,10 +373,14 @@ __device__ __forceinline__ void pair_tile_coords(const PairParams& p, int tile, 
   nt = n0 + in_group / gm;
 }
 
-template <int EPI>
+// BN = 256: the default. BN = 128: half-width tiles for problems whose 256-wide tile count leaves most of the last wave idle
+// (e.g. N = 3072 on the 6820 rows of a Ulysses SP4 rank: 324 tiles = 4.38 waves of 74 clusters; 648 half tiles = 8.76).
+template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const PairParams p) {
+  constexpr int kPairBN = BN;
+  constexpr int kPairBBytes = (BN / 2) * kBK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -432,7 +435,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int row_b = nt * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait_cluster(&empty[stage], phase ^ 1);
-          if (rank == 0) mbar_expect_tx(&full[stage], 2 * kPairStageBytes);   // both CTAs' bytes land on the leader's barrier
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (kPairABytes + kPairBBytes));   // both CTAs' bytes land on the leader's barrier
           uint32_t fl = full_leader[0];
 #pragma unroll
           for (int s = 1; s < kPairStages; ++s) fl = (stage == s) ? full_leader[s] : fl;
@@ -592,10 +595,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int EPI>
+template <int EPI, int BN>
 static int launch_gemm_pair(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const PairParams& p,
                             cudaStream_t stream) {
-  auto kfn = gemm_pair_kernel<EPI>;
+  auto kfn = gemm_pair_kernel<EPI, BN>;
   static unsigned long long configured = 0;  // per template instance and device
   if (first_use_on_device(configured)) {
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
@@ -666,7 +669,18 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
   if (pair_enabled && k2 == 0 && m >= kPairTM && ctx->sm_count >= 2) {
     CUtensorMap tc;
     if ((rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kPairBM))) return rc;
-    if ((rc = make_tmap_bf16_2d(ctx, &tb, w, n, k, ldw, kPairBN / 2))) return rc;
+    // tile width: 256 columns unless half-width tiles shorten the last, partly filled wave by more than they cost (~4 %)
+    const int clusters = ctx->sm_count / 2;
+    const int m_tiles = (m + kPairTM - 1) / kPairTM;
+    const int waves256 = (m_tiles * ((n + 255) / 256) + clusters - 1) / clusters;
+    const int waves128 = (m_tiles * ((n + 127) / 128) + clusters - 1) / clusters;
+    static int env_bn = -1;
+    if (env_bn < 0) {
+      const char* e = getenv("FGB_GEMM_BN");
+      env_bn = e ? atoi(e) : 0;
+    }
+    const int bn = env_bn ? env_bn : ((0.5 * 1.04 * waves128 < waves256) ? 128 : 256);
+    if ((rc = make_tmap_bf16_2d(ctx, &tb, w, n, k, ldw, bn / 2))) return rc;
     if ((rc = make_tmap_bf16_2d(ctx, &tc, c, m, n, ldc, 32))) return rc;
     PairParams pp;
     pp.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -677,18 +691,25 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
     pp.m = m;
     pp.n = n;
     pp.rows_gate0 = rows_gate0;
-    pp.m_tiles = (m + kPairTM - 1) / kPairTM;
-    pp.n_tiles = (n + kPairBN - 1) / kPairBN;
+    pp.m_tiles = m_tiles;
+    pp.n_tiles = (n + bn - 1) / bn;
     pp.tiles = pp.m_tiles * pp.n_tiles;
     pp.k_blocks = (k + kBK - 1) / kBK;
-    pair_supertile(pp.m_tiles, pp.n_tiles, k, &pp.group_m, &pp.band_n);
+    pair_supertile(pp.m_tiles, pp.n_tiles * bn / 256, k, &pp.group_m, &pp.band_n);
+    pp.band_n = pp.band_n * 256 / bn;      // the band is sized in columns
     cudaStream_t ps = static_cast<cudaStream_t>(stream);
+#define FGB_PAIR_CASE(E)                                                       \
+  case E:                                                                      \
+    return bn == 128 ? launch_gemm_pair<E, 128>(ctx, ta, tb, tc, pp, ps) : launch_gemm_pair<E, 256>(ctx, ta, tb, tc, pp, ps);
     switch (epilogue) {
-      case FGB_EPI_BIAS: return launch_gemm_pair<FGB_EPI_BIAS>(ctx, ta, tb, tc, pp, ps);
-      case FGB_EPI_BIAS_GELU_TANH: return launch_gemm_pair<FGB_EPI_BIAS_GELU_TANH>(ctx, ta, tb, tc, pp, ps);
-      case FGB_EPI_GATED_RESIDUAL: return launch_gemm_pair<FGB_EPI_GATED_RESIDUAL>(ctx, ta, tb, tc, pp, ps);
-      default: return launch_gemm_pair<FGB_EPI_RESIDUAL>(ctx, ta, tb, tc, pp, ps);
+      FGB_PAIR_CASE(FGB_EPI_BIAS)
+      FGB_PAIR_CASE(FGB_EPI_BIAS_GELU_TANH)
+      FGB_PAIR_CASE(FGB_EPI_GATED_RESIDUAL)
+      default:
+        return bn == 128 ? launch_gemm_pair<FGB_EPI_RESIDUAL, 128>(ctx, ta, tb, tc, pp, ps)
+                         : launch_gemm_pair<FGB_EPI_RESIDUAL, 256>(ctx, ta, tb, tc, pp, ps);
     }
+#undef FGB_PAIR_CASE
   }
   rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kBM);
   if (rc) return rc;

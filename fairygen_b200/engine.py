@@ -286,10 +286,12 @@ class WanDiTEngine:
             m0, m1 = mod_tab[0, i].view(6, d), mod_tab[r_main, i].view(6, d)
             # self-attention branch (DIT:224-225)
             k("ln_modulate", ops.ln_modulate, x, a, cfg.eps, m0[0], m0[1], m1[0], m1[1], n_first)
-            k("gemm_qkv", ops.gemm, a, b.wqkv, b.bqkv, qkv)
             if sp is not None and getattr(sp, "exchange", "nccl") == "p2p":
-                sp.attention(self, ws, qkv, o, S, norm=(cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0))
+                def qkv_rows(r0, r1, a=a, b=b, qkv=qkv):
+                    k("gemm_qkv", ops.gemm, a[r0:r1], b.wqkv, b.bqkv, qkv[r0:r1])
+                sp.attention(self, ws, qkv, o, S, norm=(cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0), qkv_gemm=qkv_rows)
             else:
+                k("gemm_qkv", ops.gemm, a, b.wqkv, b.bqkv, qkv)
                 k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)
                 k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, d:2 * d], cfg.eps, b.nk, self.rope_tab, grid, tok0)
                 if sp is None:

@@ -96,7 +96,7 @@ class PeerArena:
 
 
 class SequenceParallel:
-    def __init__(self, group=None, exchange: str = "p2p"):
+    def __init__(self, group=None, exchange: str = "p2p", overlap: bool = True):
         """exchange = "p2p": NVLink peer stores issued by our own kernels (scatter + fused attention epilogue);
         "nccl": pack / all-to-all / unpack (the plain-library variant, kept for comparison and for the CPU tests)."""
         if not dist.is_initialized():
@@ -107,7 +107,12 @@ class SequenceParallel:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.exchange = exchange
+        import os
+        # p2p: run the QKV projection in two row chunks and scatter the first under the second (FGB_SP_OVERLAP=0: A/B switch)
+        self.overlap = overlap and os.environ.get("FGB_SP_OVERLAP", "1") != "0"
         self.arena = None
+        self._side = None      # side stream + events of the overlapped scatter (created on first use)
+        self._ev = None
 
     def peer_arena(self, rows: int, heads: int, device, backward: bool = False) -> PeerArena:
         if self.arena is None or self.arena.rows != rows or (backward and not self.arena.backward):
@@ -133,10 +138,36 @@ class SequenceParallel:
         return out
 
     # ---- the self-attention exchange ---------------------------------------------------------------
-    def attention(self, engine, ws, qkv: torch.Tensor, o: torch.Tensor, tokens: int, norm=None) -> None:
+    def _scatter_rows(self, engine, qkv, r0: int, r1: int, norm) -> None:
+        """Normalise / rotate / send rows [r0, r1) of this rank's fused q|k|v matrix to the head owners (p2p exchange).
+        The kernels address the destination row as rank*rows_given + r; for a row sub-range the peer base pointers are
+        advanced so that it lands on rank*rows + r0 + r of the receive matrix."""
+        ar = self.arena
+        heads = engine.cfg.num_heads
+        d = heads * 128
+        rows = qkv.shape[0]
+        n = r1 - r0
+        row_bytes = 3 * (heads // self.world) * 128 * 2
+        shift = (self.rank * (rows - n) + r0) * row_bytes
+        ptrs = ar.recv_ptrs if shift == 0 else [p + shift for p in ar.recv_ptrs]
+        x = qkv[r0:r1]
+        k = engine._k
+        if norm is None:
+            k("sp_scatter", ops.sp_scatter_heads, x, ptrs, heads, 3, self.world, self.rank)
+            return
+        eps, wq, wk, rope_tab, grid, tok0 = norm
+        # q and k leave for their owners straight from the RMSNorm+RoPE registers; v needs a plain scatter
+        k("rmsnorm_rope", ops.rmsnorm_rope_scatter, x[:, :d], eps, wq, rope_tab, grid, tok0 + r0, ptrs, self.world, self.rank, 0, 3)
+        k("rmsnorm_rope", ops.rmsnorm_rope_scatter, x[:, d:2 * d], eps, wk, rope_tab, grid, tok0 + r0, ptrs, self.world, self.rank, 1, 3)
+        k("sp_scatter", ops.sp_scatter_heads, x[:, 2 * d:], ptrs, heads, 1, self.world, self.rank, 2, 3)
+
+    def attention(self, engine, ws, qkv: torch.Tensor, o: torch.Tensor, tokens: int, norm=None, qkv_gemm=None) -> None:
         """qkv [rows, 3*H*128] -> o [rows, H*128].  norm = None: q, k are already RMS-normed + rotated.
         norm = (eps, weight_q, weight_k, rope_tab, grid, token_offset) (p2p only): the pre-norm q, k are normalised,
-        rotated and sent by one fused kernel each."""
+        rotated and sent by one fused kernel each.
+        qkv_gemm (p2p only): callable (r0, r1) that launches the fused QKV projection for rows [r0, r1) of `qkv`.  The
+        projection then runs in two row chunks and the NVLink scatter of the first chunk (a side stream) overlaps the
+        tensor-core work of the second — the exchange is link-bound (~0.5 TB/s of peer stores), the projection is not."""
         heads = engine.cfg.num_heads
         hpr = heads // self.world
         wloc = hpr * 128
@@ -144,15 +175,26 @@ class SequenceParallel:
         if self.exchange == "p2p":
             ar = self.arena            # created by the engine's workspace; ws["recv"] / ws["o"] are views of it
             rows = qkv.shape[0]
-            d = heads * 128
-            if norm is None:
-                k("sp_scatter", ops.sp_scatter_heads, qkv, ar.recv_ptrs, heads, 3, self.world, self.rank)
+            if qkv_gemm is None:
+                self._scatter_rows(engine, qkv, 0, rows, norm)
+            elif rows < 1024 or not self.overlap:
+                qkv_gemm(0, rows)
+                self._scatter_rows(engine, qkv, 0, rows, norm)
             else:
-                # q and k leave for their owners straight from the RMSNorm+RoPE registers; v needs a plain scatter
-                eps, wq, wk, rope_tab, grid, tok0 = norm
-                k("rmsnorm_rope", ops.rmsnorm_rope_scatter, qkv[:, :d], eps, wq, rope_tab, grid, tok0, ar.recv_ptrs, self.world, self.rank, 0, 3)
-                k("rmsnorm_rope", ops.rmsnorm_rope_scatter, qkv[:, d:2 * d], eps, wk, rope_tab, grid, tok0, ar.recv_ptrs, self.world, self.rank, 1, 3)
-                k("sp_scatter", ops.sp_scatter_heads, qkv[:, 2 * d:], ar.recv_ptrs, heads, 1, self.world, self.rank, 2, 3)
+                half = ((rows // 2 + 255) // 256) * 256      # whole 256-row GEMM tiles in the first chunk
+                main = torch.cuda.current_stream(qkv.device)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=qkv.device)
+                    self._ev = [torch.cuda.Event(), torch.cuda.Event()]
+                qkv_gemm(0, half)
+                self._ev[0].record(main)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(self._ev[0])
+                    self._scatter_rows(engine, qkv, 0, half, norm)
+                    self._ev[1].record(self._side)
+                qkv_gemm(half, rows)
+                self._scatter_rows(engine, qkv, half, rows, norm)
+                main.wait_event(self._ev[1])
             ar.epoch += 1
             k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[0], self.world, self.rank, ar.epoch)
             recv = ar.recv
@@ -162,6 +204,8 @@ class SequenceParallel:
               heads * 128, rows, self.rank * wloc, hpr, kmax2=kmax2)
             k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[1], self.world, self.rank, ar.epoch)
             return
+        if qkv_gemm is not None:
+            qkv_gemm(0, qkv.shape[0])
         k("sp_pack", ops.sp_pack_heads, qkv, ws["send"], heads, 3, self.world)
         recv = k("sp_all_to_all", self.all_to_all, ws["recv"], ws["send"])     # [s_pad tokens, (q|k|v) x hpr x 128]
         kmax2 = ws["kmax2"][:hpr] if "kmax2" in ws else None   # bounded-score softmax, as on the single-GPU and p2p paths
