@@ -211,7 +211,9 @@ class WanDiTEngine:
             ref = cand[2]
             if ref.shape == context.shape and ref.dtype == context.dtype and ref.device == context.device and torch.equal(ref, context):
                 self.ctx_cache_content_hits += 1
-                self._remember_context(key, cand)   # cand[2] is the PRIVATE copy of the content: the caller may edit its tensor later
+                # cand[2] is the PRIVATE copy of the content (the caller may edit its tensor later); the 5th field keeps THIS
+                # tensor alive so that its address cannot be recycled for other data while the identity key exists
+                self._remember_context(key, cand[:4] + (context,))
                 return cand
         cfg, dev = self.cfg, self.device
         d = cfg.dim
@@ -227,7 +229,7 @@ class WanDiTEngine:
         self._launched(3 * cfg.num_layers)
         # keep a private copy of the context: it pins the content the entry was computed from (an in-place edit of the caller's
         # tensor bumps _version and misses the key) and cannot be freed / recycled under the key
-        val = (kv, n, context.detach().clone(), kmax)
+        val = (kv, n, context.detach().clone(), kmax, context)
         self._remember_context(key, val)
         return val
 
@@ -273,7 +275,7 @@ class WanDiTEngine:
         r_main = R - 1                                   # row used by tokens after the first frame
         n_first = max(0, min(rows, h * w - tok0)) if per_token else 0   # tokens of this rank at t = 0
 
-        kv_all, n_ctx, _, kmax_all = self._context_kv(context)
+        kv_all, n_ctx, _, kmax_all = self._context_kv(context)[:4]
 
         # ---- patch embedding: im2row + GEMM (DIT:305, PIPE:1253-1261)
         x, a, qkv, o, cq, hbuf = ws["x"], ws["a"], ws["qkv"], ws["o"], ws["cq"], ws["h"]
