@@ -51,6 +51,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* s_full = bars + 9;      // [2] per query tile: S_i written by the tensor core
   uint64_t* p_ready = bars + 11;    // [2] per query tile: first half of every thread's P_i (32 of its 64 keys) stored
   uint64_t* p_ready2 = bars + 18;   // [2] per query tile: second half stored (and O_i rescaled) — PV starts on the first half
+  uint64_t* q_empty = bars + 20;    // [1] the item's last score MMAs have read Q: the next item's Q may land
   uint64_t* pv_done = bars + 13;    // [2] per query tile: O_i += P_i V_j finished
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   float* xchg = reinterpret_cast<float*>(bars + 32);   // [2 slots][2 column halves][128 rows]
@@ -58,23 +59,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_kv_all = (p.s_kv + kTile - 1) / kTile;
-  int unit = blockIdx.x, kv_lo = 0, kv_hi = n_kv_all, part = -1;
-  if (unit >= p.n_full) {
-    part = unit - p.n_full;
-    const int chunk = part % p.split;
-    unit = p.n_full + part / p.split;
-    kv_lo = static_cast<int>(static_cast<int64_t>(chunk) * n_kv_all / p.split);
-    kv_hi = static_cast<int>(static_cast<int64_t>(chunk + 1) * n_kv_all / p.split);
-  }
-  const int head = unit / p.n_pairs;
-  const int q0 = (unit % p.n_pairs) * (2 * kTile);
-  const int n_kv = kv_hi - kv_lo;   // KV tiles of this CTA; local tile jj is global tile kv_lo + jj
+  // Persistent CTA: work items blockIdx.x, blockIdx.x + gridDim.x, ... of the list [n_full whole units | split units x split
+  // key chunks]. Every role walks the same list; mbarrier parities follow running counters (items, KV tiles), so the TMA
+  // thread prefetches the next item's Q / K / V and the tensor core starts its first score tiles while the softmax warps
+  // are still writing the previous item's output: prologue and epilogue of consecutive items overlap (they dominated the
+  // 4-tile cross-attention launches, where a CTA used to live for 8 tile steps only).
+  int head = 0, q0 = 0, kv_lo = 0, n_kv = 0, part = -1;
+  auto decode_item = [&](int w) {
+    int unit = w, kv_hi = n_kv_all;
+    kv_lo = 0;
+    part = -1;
+    if (unit >= p.n_full) {
+      part = unit - p.n_full;
+      const int chunk = part % p.split;
+      unit = p.n_full + part / p.split;
+      kv_lo = static_cast<int>(static_cast<int64_t>(chunk) * n_kv_all / p.split);
+      kv_hi = static_cast<int>(static_cast<int64_t>(chunk + 1) * n_kv_all / p.split);
+    }
+    head = unit / p.n_pairs;
+    q0 = (unit % p.n_pairs) * (2 * kTile);
+    n_kv = kv_hi - kv_lo;   // KV tiles of this item; local tile jj is global tile kv_lo + jj
+  };
 
   if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
@@ -96,24 +108,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 9) {
     if (elect_one()) {
       // ------------------------------- TMA producer -------------------------------
-      mbar_expect_tx(q_full, 2 * kTileBytes);
-      for (int i = 0; i < 2; ++i)
-        for (int b = 0; b < 2; ++b)
-          tma_load_2d(smem_q + i * kTileBytes + b * kBoxBytes, &tmap_q, q_full, head * 128 + b * 64,
-                      q0 + i * kTile, kEvictFirst);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait_parked(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], kTileBytes);
-        for (int b = 0; b < 2; ++b)
-          tma_load_2d(smem_k + st * kTileBytes + b * kBoxBytes, &tmap_k, &k_full[st], head * 128 + b * 64,
-                      (kv_lo + j) * kTile, kEvictLast);
-        mbar_wait_parked(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], kTileBytes);
-        for (int b = 0; b < 2; ++b)
-          tma_load_2d(smem_v + st * kTileBytes + b * kBoxBytes, &tmap_v, &v_full[st], head * 128 + b * 64,
-                      (kv_lo + j) * kTile, kEvictLast);
+      uint32_t t = 0;    // KV tiles loaded so far (all items): ring stage t & 1, phase (t >> 1) & 1
+      uint32_t it = 0;   // items so far
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
+        decode_item(w);
+        mbar_wait_parked(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, 2 * kTileBytes);
+        for (int i = 0; i < 2; ++i)
+          for (int b = 0; b < 2; ++b)
+            tma_load_2d(smem_q + i * kTileBytes + b * kBoxBytes, &tmap_q, q_full, head * 128 + b * 64,
+                        q0 + i * kTile, kEvictFirst);
+        for (int j = 0; j < n_kv; ++j, ++t) {
+          const int st = t & 1;
+          const uint32_t ph = (t >> 1) & 1;
+          mbar_wait_parked(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], kTileBytes);
+          for (int b = 0; b < 2; ++b)
+            tma_load_2d(smem_k + st * kTileBytes + b * kBoxBytes, &tmap_k, &k_full[st], head * 128 + b * 64,
+                        (kv_lo + j) * kTile, kEvictLast);
+          mbar_wait_parked(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], kTileBytes);
+          for (int b = 0; b < 2; ++b)
+            tma_load_2d(smem_v + st * kTileBytes + b * kBoxBytes, &tmap_v, &v_full[st], head * 128 + b * 64,
+                        (kv_lo + j) * kTile, kEvictLast);
+        }
       }
     }
   } else if (warp == 8) {
@@ -136,52 +154,61 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         tc_commit(&s_full[i]);
       };
-      auto issue_pv = [&](int i, int st, int j) {
+      auto issue_pv = [&](int i, int st, uint32_t g, bool first) {   // g: running KV-tile count (barrier parity)
         const uint64_t vd = v_desc + static_cast<uint64_t>((st * kTileBytes) >> 4);
         const uint32_t d_tmem = tmem_base + 256 + i * 128;
         const uint32_t p_tmem = tmem_base + i * 128;
         // 16 keys per MMA: 16 rows of 128 B in each d-half box. P arrives in two halves: MMAs 0,1 / 4,5 consume the first 32
         // keys of each warpgroup's 64, MMAs 2,3 / 6,7 the second — the tensor core starts PV while the softmax warps are
         // still exponentiating the second half of the tile.
-        mbar_wait_parked(&p_ready[i], j & 1);
+        mbar_wait_parked(&p_ready[i], g & 1);
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h == 1) {
-            mbar_wait_parked(&p_ready2[i], j & 1);
+            mbar_wait_parked(&p_ready2[i], g & 1);
             tc_fence_after();
           }
 #pragma unroll
-          for (int g = 0; g < 2; ++g)
+          for (int wgi = 0; wgi < 2; ++wgi)
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const int kk = g * 4 + h * 2 + t;
+            for (int tt = 0; tt < 2; ++tt) {
+              const int kk = wgi * 4 + h * 2 + tt;
               umma_ts(d_tmem, p_tmem + (kk & 3) * 8 + (kk >> 2) * 64, vd + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv,
-                      (j | h | g | t) != 0);
+                      !(first && (h | wgi | tt) == 0));
             }
         }
         tc_commit(&pv_done[i]);
       };
-      mbar_wait_parked(q_full, 0);
-      mbar_wait_parked(&k_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      tc_commit(&k_empty[0]);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const int st1 = (j + 1) & 1;
-        mbar_wait_parked(&v_full[st], (j >> 1) & 1);
-        for (int i = 0; i < 2; ++i) {
-          issue_pv(i, st, j);
-          if (i == 1) tc_commit(&v_empty[st]);
-          if (j + 1 < n_kv) {
-            if (i == 0) {
-              mbar_wait_parked(&k_full[st1], ((j + 1) >> 1) & 1);
-              tc_fence_after();
+      uint32_t g = 0;    // KV tiles issued so far (all items)
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
+        decode_item(w);
+        mbar_wait_parked(q_full, it & 1);
+        mbar_wait_parked(&k_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        issue_s(0, g & 1);
+        issue_s(1, g & 1);
+        tc_commit(&k_empty[g & 1]);
+        if (n_kv == 1) tc_commit(q_empty);
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const int st = g & 1;
+          const int st1 = (g + 1) & 1;
+          mbar_wait_parked(&v_full[st], (g >> 1) & 1);
+          for (int i = 0; i < 2; ++i) {
+            issue_pv(i, st, g, j == 0);
+            if (i == 1) tc_commit(&v_empty[st]);
+            if (j + 1 < n_kv) {
+              if (i == 0) {
+                mbar_wait_parked(&k_full[st1], ((g + 1) >> 1) & 1);
+                tc_fence_after();
+              }
+              issue_s(i, st1);
+              if (i == 1) {
+                tc_commit(&k_empty[st1]);
+                if (j + 2 == n_kv) tc_commit(q_empty);   // the item's last score MMAs: Q is free for the next item
+              }
             }
-            issue_s(i, st1);
-            if (i == 1) tc_commit(&k_empty[st1]);
           }
         }
       }
@@ -288,10 +315,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       return vote[slot] != 0;
     };
 
+    uint32_t g0 = 0;   // KV tiles of the items before this one: s_full / p_ready / pv_done complete once per tile
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
+    decode_item(w);
+    m[0] = m[1] = -INFINITY;
+    l[0] = l[1] = 0.f;
     // ---- bounded-score softmax: a fixed per-row reference instead of a running maximum (AttnParams::kmax)
     int mode = 2;   // 0: reference from the Cauchy-Schwarz bound, 1: anchored on the first tile's maximum, 2: running maximum
     if (p.kmax != nullptr) {
-      mbar_wait(q_full, 0);
+      mbar_wait(q_full, it & 1);
       const float kmax2 = __ldg(p.kmax + head);   // max_j ||k_j||^2 of this head (fgb_head_norm_max)
       float bnd[2];
       bool ok = true;
@@ -314,7 +347,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         ok = ok && (bnd[i] <= kBoundFixedMax);   // NaN bounds fail the test and end up on the running-max path
         m[i] = bnd[i] <= kBoundDirect ? bnd[i] : kWindowLo - bnd[i];
       }
-      if (vote_all(0, ok)) {
+      if (vote_all((it & 1) * 2, ok)) {
         mode = 0;
       } else {
         // the Cauchy-Schwarz bound alone leaves no safe window: anchor it on the exact maximum of the first KV tile
@@ -322,7 +355,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
           const uint32_t t_s = tmem_base + lane_bits + i * 128 + wg * 64;
-          mbar_wait(&s_full[i], 0);
+          mbar_wait(&s_full[i], g0 & 1);
           tc_fence_after();
           const int valid = p.s_kv - kv_lo * kTile - wg * 64;
           if (valid < 64) mask_partial(t_s, valid);
@@ -333,7 +366,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           ok = ok && (bnd[i] - m0 <= kWindowLo + kWindowHi);
           m[i] = fmaxf(bnd[i] - kWindowHi, fminf(bnd[i], m0 + 20.0f));
         }
-        mode = vote_all(1, ok) ? 1 : 2;
+        mode = vote_all((it & 1) * 2 + 1, ok) ? 1 : 2;
         if (mode == 2) m[0] = m[1] = -INFINITY;
       }
       if (p.stats != nullptr && threadIdx.x == 0) atomicAdd(p.stats + mode, 1);
@@ -347,7 +380,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       constexpr bool LAST = decltype(last_tag)::value;
       const uint32_t t_s = tmem_base + lane_bits + i * 128 + wg * 64;  // this thread's 64 score columns
       const uint32_t t_o = tmem_base + lane_bits + 256 + i * 128;
-      mbar_wait(&s_full[i], j & 1);
+      mbar_wait(&s_full[i], (g0 + j) & 1);
       tc_fence_after();
       bool partial = false;
       if (LAST) {
@@ -396,7 +429,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const float alpha = fast_exp2(m[i] - m_new);
           l[i] *= alpha;
           m[i] = m_new;
-          mbar_wait(&pv_done[i], (j - 1) & 1);  // O_i must be quiescent
+          mbar_wait(&pv_done[i], (g0 + j - 1) & 1);  // O_i must be quiescent
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
@@ -436,7 +469,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int row = q0 + i * kTile + r_local;
       const uint32_t t_o = tmem_base + lane_bits + 256 + i * 128 + wg * 64;
       const float l_row = l[i] + swap_rows(l[i]);   // both halves used the same running max
-      mbar_wait(&pv_done[i], (n_kv - 1) & 1);
+      mbar_wait(&pv_done[i], (g0 + n_kv - 1) & 1);
       tc_fence_after();
       if (part >= 0) {
         // split-KV CTA: un-normalised O and (m, l) go to the workspace; attn_combine_kernel merges the chunks
@@ -476,6 +509,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
     }
+    g0 += n_kv;
+    }   // items
   }
 
   tc_fence_before();
@@ -637,7 +672,8 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
     emu = env ? atoi(env) : kDefaultEmu;
     if (emu < 0 || emu > 9) emu = kDefaultEmu;
   }
-  const int grid = p.n_full + n_split * split;
+  p.n_items = p.n_full + n_split * split;
+  const int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;   // persistent: one CTA per SM walks the list
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (emu) {
     case 0: rc = launch_attn<0>(grid, st, tq, tk, tv, p); break;

@@ -24,6 +24,7 @@ struct AttnParams {
   // the list, each split `split` ways along the keys (wave-quantisation fix, see fgb_attn_fwd_ex). A unit is
   // (head, pair of query tiles): unit = head * n_pairs + pair.
   int32_t n_pairs, n_full, split;
+  int32_t n_items;  // n_full + (split units) * split: the work list the persistent CTAs walk with stride gridDim.x
   float* part_o;    // [split CTA][256 rows][128] un-normalised fp32 partial outputs
   float2* part_ml;  // [split CTA][256 rows] (running max in log2 units, row sum)
   float* lse;       // optional [heads][ld_lse]: log2-domain log-sum-exp of the scaled scores (for the backward pass);

@@ -695,7 +695,7 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
     pp.n_tiles = (n + bn - 1) / bn;
     pp.tiles = pp.m_tiles * pp.n_tiles;
     pp.k_blocks = (k + kBK - 1) / kBK;
-    pair_supertile(pp.m_tiles, pp.n_tiles * bn / 256, k, &pp.group_m, &pp.band_n);
+    pair_supertile(pp.m_tiles, (pp.n_tiles * bn + 255) / 256, k, &pp.group_m, &pp.band_n);
     pp.band_n = pp.band_n * 256 / bn;      // the band is sized in columns
     cudaStream_t ps = static_cast<cudaStream_t>(stream);
 #define FGB_PAIR_CASE(E)                                                       \
