@@ -31,29 +31,41 @@
 namespace fgb {
 
 // EMU: of every 8 score pairs, EMU are exponentiated by exp2_emulated, the rest by MUFU.EX2.
-template <int EMU>
+// PAIR: two CTAs of a cluster (one TPC) work on 512 query rows of one head with tcgen05.mma.cta_group::2: every score / PV
+// MMA has M = 256 (tile i of both CTAs), each CTA stages only HALF of every K tile (64 of its 128 keys) and half of every V
+// tile (64 of its 128 head-dim columns) — the shared-memory fill and the operand reads of the tensor core per SM drop by a
+// third, the L2 -> SM traffic for K/V by half. The leader CTA issues all MMAs; K/V `full` barriers live in the leader (2-CTA
+// TMA signals them), `empty` / s_full / pv_done are multicast commits, P-ready collects one arrival per softmax warp of both
+// CTAs. Everything a softmax thread does is CTA-local and identical in both variants.
+template <int EMU, bool PAIR>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   constexpr int kEmu = EMU;
   constexpr int kFrac = (EMU == 9) ? 3 : EMU;   // pairs of every 8 that take the FMA-pipe exp2
+  constexpr int kStages = PAIR ? 4 : 2;                       // K / V ring depth
+  constexpr int kKVBytes = PAIR ? kTileBytes / 2 : kTileBytes;   // bytes of one K (or V) stage in THIS CTA
+  constexpr int kKBox = PAIR ? kBoxBytes / 2 : kBoxBytes;        // one K box: 64 (pair) or 128 key rows of 128 B
+  constexpr int kItemTiles = PAIR ? 4 : 2;                       // 128-row query tiles per work item
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                                   // [2 tiles][2 boxes][128][64]
-  uint8_t* smem_k = smem + 2 * kTileBytes;                  // [stages][2 boxes][128][64]
-  uint8_t* smem_v = smem_k + kKVStages * kTileBytes;        // [stages][2 boxes][128][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kKVStages * kTileBytes);
-  uint64_t* q_full = bars;          // [1]
-  uint64_t* k_full = bars + 1;      // [2]
-  uint64_t* v_full = bars + 3;      // [2]
-  uint64_t* k_empty = bars + 5;     // [2]
-  uint64_t* v_empty = bars + 7;     // [2]
-  uint64_t* s_full = bars + 9;      // [2] per query tile: S_i written by the tensor core
-  uint64_t* p_ready = bars + 11;    // [2] per query tile: first half of every thread's P_i (32 of its 64 keys) stored
-  uint64_t* p_ready2 = bars + 18;   // [2] per query tile: second half stored (and O_i rescaled) — PV starts on the first half
-  uint64_t* q_empty = bars + 20;    // [1] the item's last score MMAs have read Q: the next item's Q may land
-  uint64_t* pv_done = bars + 13;    // [2] per query tile: O_i += P_i V_j finished
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint8_t* smem_k = smem + 2 * kTileBytes;                  // [stages][2 boxes][128 or 64][64]
+  uint8_t* smem_v = smem_k + kStages * kKVBytes;            // [stages][2 boxes][128][64] or [stages][128][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kStages * kKVBytes);
+  uint64_t* q_full = bars;          // [1] this CTA's Q tiles landed
+  uint64_t* q_empty = bars + 1;     // [1] the item's last score MMAs have read Q: the next item's Q may land
+  uint64_t* q_pair = bars + 2;      // [1] PAIR, leader: the peer's Q tiles landed (remote arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  //                         bars + 4, 5: four vote words
+  uint64_t* s_full = bars + 6;      // [2] per query tile: S_i written by the tensor core
+  uint64_t* p_ready = bars + 8;     // [2] per query tile: first half of every thread's P_i (32 of its 64 keys) stored
+  uint64_t* p_ready2 = bars + 10;   // [2] per query tile: second half stored (and O_i rescaled) — PV starts on the first half
+  uint64_t* pv_done = bars + 12;    // [2] per query tile: O_i += P_i V_j finished
+  uint64_t* k_full = bars + 14;     // [4]
+  uint64_t* v_full = bars + 18;     // [4]
+  uint64_t* k_empty = bars + 22;    // [4]
+  uint64_t* v_empty = bars + 26;    // [4]
   float* xchg = reinterpret_cast<float*>(bars + 32);   // [2 slots][2 column halves][128 rows]
 
   const int warp = threadIdx.x >> 5;
@@ -64,6 +76,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // thread prefetches the next item's Q / K / V and the tensor core starts its first score tiles while the softmax warps
   // are still writing the previous item's output: prologue and epilogue of consecutive items overlap (they dominated the
   // 4-tile cross-attention launches, where a CTA used to live for 8 tile steps only).
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader
   int head = 0, q0 = 0, kv_lo = 0, n_kv = 0, part = -1;
   auto decode_item = [&](int w) {
     int unit = w, kv_hi = n_kv_all;
@@ -77,9 +90,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       kv_hi = static_cast<int>(static_cast<int64_t>(chunk + 1) * n_kv_all / p.split);
     }
     head = unit / p.n_pairs;
-    q0 = (unit % p.n_pairs) * (2 * kTile);
+    q0 = (unit % p.n_pairs) * (kItemTiles * kTile) + static_cast<int>(rank) * (2 * kTile);   // first query row of THIS CTA
     n_kv = kv_hi - kv_lo;   // KV tiles of this item; local tile jj is global tile kv_lo + jj
   };
+  const int w0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;        // first work item of this CTA (pair) and the stride
+  const int w_stride = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -87,86 +102,131 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
+    mbar_init(q_pair, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], PAIR ? 16 : 256);    // PAIR: one arrival per softmax warp of both CTAs
+      mbar_init(&p_ready2[i], PAIR ? 16 : 256);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 256);
-      mbar_init(&p_ready2[i], 256);
-      mbar_init(&pv_done[i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<512>(tmem_slot);
+  if (warp == 8) {
+    if (PAIR) tmem_alloc_2sm<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();    // both CTAs' barriers exist before any remote signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 9) {
     if (elect_one()) {
       // ------------------------------- TMA producer -------------------------------
-      uint32_t t = 0;    // KV tiles loaded so far (all items): ring stage t & 1, phase (t >> 1) & 1
+      uint32_t kf[kStages], vf[kStages];   // PAIR: the leader's full barriers as cluster addresses
+      if (PAIR) {
+#pragma unroll
+        for (int sI = 0; sI < kStages; ++sI) {
+          asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(kf[sI]) : "r"(smem_u32(&k_full[sI])));
+          asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(vf[sI]) : "r"(smem_u32(&v_full[sI])));
+        }
+      }
+      uint32_t t = 0;    // KV tiles loaded so far (all items): ring stage t % kStages, phase (t / kStages) & 1
       uint32_t it = 0;   // items so far
-      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
+      for (int w = w0; w < p.n_items; w += w_stride, ++it) {
         decode_item(w);
-        mbar_wait_parked(q_empty, (it & 1) ^ 1);
+        if (PAIR) mbar_wait_parked_cluster(q_empty, (it & 1) ^ 1);
+        else mbar_wait_parked(q_empty, (it & 1) ^ 1);
         mbar_expect_tx(q_full, 2 * kTileBytes);
         for (int i = 0; i < 2; ++i)
           for (int b = 0; b < 2; ++b)
             tma_load_2d(smem_q + i * kTileBytes + b * kBoxBytes, &tmap_q, q_full, head * 128 + b * 64,
                         q0 + i * kTile, kEvictFirst);
         for (int j = 0; j < n_kv; ++j, ++t) {
-          const int st = t & 1;
-          const uint32_t ph = (t >> 1) & 1;
-          mbar_wait_parked(&k_empty[st], ph ^ 1);
-          mbar_expect_tx(&k_full[st], kTileBytes);
-          for (int b = 0; b < 2; ++b)
-            tma_load_2d(smem_k + st * kTileBytes + b * kBoxBytes, &tmap_k, &k_full[st], head * 128 + b * 64,
-                        (kv_lo + j) * kTile, kEvictLast);
-          mbar_wait_parked(&v_empty[st], ph ^ 1);
-          mbar_expect_tx(&v_full[st], kTileBytes);
-          for (int b = 0; b < 2; ++b)
-            tma_load_2d(smem_v + st * kTileBytes + b * kBoxBytes, &tmap_v, &v_full[st], head * 128 + b * 64,
-                        (kv_lo + j) * kTile, kEvictLast);
+          const int st = t % kStages;
+          const uint32_t ph = (t / kStages) & 1;
+          if (PAIR) {
+            // this CTA's half of the tile: keys [rank*64, +64) of K (both head-dim boxes), head-dim columns [rank*64, +64) of V
+            mbar_wait_parked_cluster(&k_empty[st], ph ^ 1);
+            if (rank == 0) mbar_expect_tx(&k_full[st], 2 * kKVBytes);
+            uint32_t kfl = kf[0], vfl = vf[0];
+#pragma unroll
+            for (int sI = 1; sI < kStages; ++sI) {
+              kfl = (st == sI) ? kf[sI] : kfl;
+              vfl = (st == sI) ? vf[sI] : vfl;
+            }
+            for (int b = 0; b < 2; ++b)
+              tma_load_2d_2sm(smem_k + st * kKVBytes + b * kKBox, &tmap_k, kfl, head * 128 + b * 64,
+                              (kv_lo + j) * kTile + static_cast<int>(rank) * 64, kEvictLast);
+            mbar_wait_parked_cluster(&v_empty[st], ph ^ 1);
+            if (rank == 0) mbar_expect_tx(&v_full[st], 2 * kKVBytes);
+            tma_load_2d_2sm(smem_v + st * kKVBytes, &tmap_v, vfl, head * 128 + static_cast<int>(rank) * 64, (kv_lo + j) * kTile,
+                            kEvictLast);
+          } else {
+            mbar_wait_parked(&k_empty[st], ph ^ 1);
+            mbar_expect_tx(&k_full[st], kTileBytes);
+            for (int b = 0; b < 2; ++b)
+              tma_load_2d(smem_k + st * kTileBytes + b * kBoxBytes, &tmap_k, &k_full[st], head * 128 + b * 64,
+                          (kv_lo + j) * kTile, kEvictLast);
+            mbar_wait_parked(&v_empty[st], ph ^ 1);
+            mbar_expect_tx(&v_full[st], kTileBytes);
+            for (int b = 0; b < 2; ++b)
+              tma_load_2d(smem_v + st * kTileBytes + b * kBoxBytes, &tmap_v, &v_full[st], head * 128 + b * 64,
+                          (kv_lo + j) * kTile, kEvictLast);
+          }
         }
       }
     }
   } else if (warp == 8) {
-    if (elect_one()) {
-      // ------------------------------- MMA issuer ---------------------------------
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // P (TMEM)   x V (MN-major)
+    if (rank == 0 && elect_one()) {
+      // ------------------------------- MMA issuer (PAIR: the leader, for both CTAs) ---------------------------------
+      constexpr uint32_t idesc_s = make_idesc_bf16(PAIR ? 256 : 128, 128, 0, 0);   // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_pv = make_idesc_bf16(PAIR ? 256 : 128, 128, 0, 1);  // P (TMEM)   x V (MN-major)
       // Descriptors are built once; per MMA only a compile-time offset is added to the 14-bit address field.
       const uint64_t q_desc = make_sdesc_sw128(smem_u32(smem_q), 16, 1024);
       const uint64_t k_desc = make_sdesc_sw128(smem_u32(smem_k), 16, 1024);
       const uint64_t v_desc = make_sdesc_sw128(smem_u32(smem_v), kBoxBytes, 1024);
+      auto commit = [&](uint64_t* bar) {
+        if (PAIR) tc_commit_2sm(bar, 0x3);   // same-offset barrier in both CTAs
+        else tc_commit(bar);
+      };
+      auto wait = [&](uint64_t* bar, uint32_t parity) {
+        if (PAIR) mbar_wait_parked_cluster(bar, parity);
+        else mbar_wait_parked(bar, parity);
+      };
       auto issue_s = [&](int i, int st) {
         const uint64_t qd = q_desc + static_cast<uint64_t>((i * kTileBytes) >> 4);
-        const uint64_t kd = k_desc + static_cast<uint64_t>((st * kTileBytes) >> 4);
+        const uint64_t kd = k_desc + static_cast<uint64_t>((st * kKVBytes) >> 4);
         const uint32_t d_tmem = tmem_base + i * 128;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // 16 head-dim elements per MMA
-          const uint64_t off = static_cast<uint64_t>(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
-          umma_ss(d_tmem, qd + off, kd + off, idesc_s, kk != 0);
+          const uint64_t off_q = static_cast<uint64_t>(((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4);
+          const uint64_t off_k = static_cast<uint64_t>(((kk >> 2) * kKBox + (kk & 3) * 32) >> 4);
+          if (PAIR) umma_ss_2sm(d_tmem, qd + off_q, kd + off_k, idesc_s, kk != 0);
+          else umma_ss(d_tmem, qd + off_q, kd + off_k, idesc_s, kk != 0);
         }
-        tc_commit(&s_full[i]);
+        commit(&s_full[i]);
       };
       auto issue_pv = [&](int i, int st, uint32_t g, bool first) {   // g: running KV-tile count (barrier parity)
-        const uint64_t vd = v_desc + static_cast<uint64_t>((st * kTileBytes) >> 4);
+        const uint64_t vd = v_desc + static_cast<uint64_t>((st * kKVBytes) >> 4);
         const uint32_t d_tmem = tmem_base + 256 + i * 128;
         const uint32_t p_tmem = tmem_base + i * 128;
         // 16 keys per MMA: 16 rows of 128 B in each d-half box. P arrives in two halves: MMAs 0,1 / 4,5 consume the first 32
         // keys of each warpgroup's 64, MMAs 2,3 / 6,7 the second — the tensor core starts PV while the softmax warps are
         // still exponentiating the second half of the tile.
-        mbar_wait_parked(&p_ready[i], g & 1);
+        wait(&p_ready[i], g & 1);
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h == 1) {
-            mbar_wait_parked(&p_ready2[i], g & 1);
+            wait(&p_ready2[i], g & 1);
             tc_fence_after();
           }
 #pragma unroll
@@ -174,39 +234,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
             for (int tt = 0; tt < 2; ++tt) {
               const int kk = wgi * 4 + h * 2 + tt;
-              umma_ts(d_tmem, p_tmem + (kk & 3) * 8 + (kk >> 2) * 64, vd + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv,
-                      !(first && (h | wgi | tt) == 0));
+              const uint32_t acc = !(first && (h | wgi | tt) == 0);
+              if (PAIR) umma_ts_2sm(d_tmem, p_tmem + (kk & 3) * 8 + (kk >> 2) * 64, vd + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv, acc);
+              else umma_ts(d_tmem, p_tmem + (kk & 3) * 8 + (kk >> 2) * 64, vd + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv, acc);
             }
         }
-        tc_commit(&pv_done[i]);
+        commit(&pv_done[i]);
       };
       uint32_t g = 0;    // KV tiles issued so far (all items)
       uint32_t it = 0;
-      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
+      for (int w = w0; w < p.n_items; w += w_stride, ++it) {
         decode_item(w);
         mbar_wait_parked(q_full, it & 1);
-        mbar_wait_parked(&k_full[g & 1], (g >> 1) & 1);
+        if (PAIR) mbar_wait_parked_cluster(q_pair, it & 1);
+        wait(&k_full[g % kStages], (g / kStages) & 1);
         tc_fence_after();
-        issue_s(0, g & 1);
-        issue_s(1, g & 1);
-        tc_commit(&k_empty[g & 1]);
-        if (n_kv == 1) tc_commit(q_empty);
+        issue_s(0, g % kStages);
+        issue_s(1, g % kStages);
+        commit(&k_empty[g % kStages]);
+        if (n_kv == 1) commit(q_empty);
         for (int j = 0; j < n_kv; ++j, ++g) {
-          const int st = g & 1;
-          const int st1 = (g + 1) & 1;
-          mbar_wait_parked(&v_full[st], (g >> 1) & 1);
+          const int st = g % kStages;
+          const int st1 = (g + 1) % kStages;
+          wait(&v_full[st], (g / kStages) & 1);
           for (int i = 0; i < 2; ++i) {
             issue_pv(i, st, g, j == 0);
-            if (i == 1) tc_commit(&v_empty[st]);
+            if (i == 1) commit(&v_empty[st]);
             if (j + 1 < n_kv) {
               if (i == 0) {
-                mbar_wait_parked(&k_full[st1], ((g + 1) >> 1) & 1);
+                wait(&k_full[st1], ((g + 1) / kStages) & 1);
                 tc_fence_after();
               }
               issue_s(i, st1);
               if (i == 1) {
-                tc_commit(&k_empty[st1]);
-                if (j + 2 == n_kv) tc_commit(q_empty);   // the item's last score MMAs: Q is free for the next item
+                commit(&k_empty[st1]);
+                if (j + 2 == n_kv) commit(q_empty);   // the item's last score MMAs: Q is free for the next item
               }
             }
           }
@@ -233,6 +295,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       return slot[(wg ^ 1) * kTile + r_local];
     };
 
+    // "my part of P is in TMEM": per thread on the CTA's own barrier, or (PAIR) one arrival per warp on the leader's barrier
+    auto signal_p = [&](uint64_t* bar) {
+      tc_fence_before();
+      if (PAIR) {
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(bar);
+          else mbar_arrive_cluster(bar, 0);
+        }
+      } else {
+        mbar_arrive(bar);
+      }
+    };
+    auto wait_mma = [&](uint64_t* bar, uint32_t parity) {   // barriers the (possibly remote) tensor-core commits signal
+      if (PAIR) mbar_wait_cluster(bar, parity);
+      else mbar_wait(bar, parity);
+    };
     // One pass over this thread's 64 scores, 32 at a time (the second TMEM load is in flight while the first chunk is
     // processed): tracks the maximum and, if EXPS, writes P = 2^(s*scale - m_used) as packed bf16 into pk and
     // returns the sum. KIND selects how the exponentials are made (ExpMixed / ExpMixedClamp / ExpMufu).
@@ -279,8 +358,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if (c == 0 && early_bar != nullptr) {
             tmem_st16(t_s, pk);
             tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(early_bar);
+            signal_p(early_bar);
           }
         }
       }
@@ -306,7 +384,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_st_wait();
     };
     // One decision per CTA (the two threads of a row must agree; per CTA keeps it simple): AND of `ok` over the 256 softmax threads.
-    volatile int* vote = reinterpret_cast<volatile int*>(bars + 16);
+    volatile int* vote = reinterpret_cast<volatile int*>(bars + 4);
     auto vote_all = [&](int slot, bool ok) -> bool {
       if (threadIdx.x == 0) vote[slot] = 1;
       asm volatile("bar.sync 9, 256;" ::: "memory");
@@ -317,10 +395,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     uint32_t g0 = 0;   // KV tiles of the items before this one: s_full / p_ready / pv_done complete once per tile
     uint32_t it = 0;
-    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x, ++it) {
+    for (int w = w0; w < p.n_items; w += w_stride, ++it) {
     decode_item(w);
     m[0] = m[1] = -INFINITY;
     l[0] = l[1] = 0.f;
+    if (PAIR) {
+      // the leader's MMA thread must know that the PEER's Q tiles have landed too: one remote arrival per item
+      mbar_wait(q_full, it & 1);
+      if (rank == 1 && threadIdx.x == 0) mbar_arrive_cluster(q_pair, 0);
+    }
     // ---- bounded-score softmax: a fixed per-row reference instead of a running maximum (AttnParams::kmax)
     int mode = 2;   // 0: reference from the Cauchy-Schwarz bound, 1: anchored on the first tile's maximum, 2: running maximum
     if (p.kmax != nullptr) {
@@ -355,7 +438,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
           const uint32_t t_s = tmem_base + lane_bits + i * 128 + wg * 64;
-          mbar_wait(&s_full[i], g0 & 1);
+          wait_mma(&s_full[i], g0 & 1);
           tc_fence_after();
           const int valid = p.s_kv - kv_lo * kTile - wg * 64;
           if (valid < 64) mask_partial(t_s, valid);
@@ -380,7 +463,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       constexpr bool LAST = decltype(last_tag)::value;
       const uint32_t t_s = tmem_base + lane_bits + i * 128 + wg * 64;  // this thread's 64 score columns
       const uint32_t t_o = tmem_base + lane_bits + 256 + i * 128;
-      mbar_wait(&s_full[i], (g0 + j) & 1);
+      wait_mma(&s_full[i], (g0 + j) & 1);
       tc_fence_after();
       bool partial = false;
       if (LAST) {
@@ -397,14 +480,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         l[i] += sum;
         tmem_st16(t_s + 16, pk + 16);
         tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_ready2[i]);
+        signal_p(&p_ready2[i]);
         return;
       }
       if (EMU == 8) {            // DEBUG (FGB_ATTN_EMU=8): no softmax work at all — the tensor / barrier skeleton alone
-        tc_fence_before();
-        mbar_arrive(&p_ready[i]);
-        mbar_arrive(&p_ready2[i]);
+        signal_p(&p_ready[i]);
+        signal_p(&p_ready2[i]);
         return;
       }
       bool redo = false;
@@ -429,7 +510,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const float alpha = fast_exp2(m[i] - m_new);
           l[i] *= alpha;
           m[i] = m_new;
-          mbar_wait(&pv_done[i], (g0 + j - 1) & 1);  // O_i must be quiescent
+          wait_mma(&pv_done[i], (g0 + j - 1) & 1);  // O_i must be quiescent
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
@@ -447,9 +528,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       l[i] += sum;
       tmem_st32(t_s, pk);   // P over this thread's own first 32 (consumed) score columns
       tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[i]);    // the running-max path needs the whole row before any P exists: both halves at once
-      mbar_arrive(&p_ready2[i]);
+      signal_p(&p_ready[i]);    // the running-max path needs the whole row before any P exists: both halves at once
+      signal_p(&p_ready2[i]);
     };
     auto run_tiles = [&](auto mode_tag) {
       for (int j = 0; j + 1 < n_kv; ++j) {
@@ -469,13 +549,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int row = q0 + i * kTile + r_local;
       const uint32_t t_o = tmem_base + lane_bits + 256 + i * 128 + wg * 64;
       const float l_row = l[i] + swap_rows(l[i]);   // both halves used the same running max
-      mbar_wait(&pv_done[i], (g0 + n_kv - 1) & 1);
+      wait_mma(&pv_done[i], (g0 + n_kv - 1) & 1);
       tc_fence_after();
       if (part >= 0) {
         // split-KV CTA: un-normalised O and (m, l) go to the workspace; attn_combine_kernel merges the chunks
-        const int pr = i * kTile + r_local;
-        float* prow = p.part_o + (static_cast<int64_t>(part) * (2 * kTile) + pr) * 128 + wg * 64;
-        if (wg == 0) p.part_ml[static_cast<int64_t>(part) * (2 * kTile) + pr] = make_float2(m[i], l_row);
+        const int pr = static_cast<int>(rank) * (2 * kTile) + i * kTile + r_local;   // row inside the work item
+        float* prow = p.part_o + (static_cast<int64_t>(part) * (kItemTiles * kTile) + pr) * 128 + wg * 64;
+        if (wg == 0) p.part_ml[static_cast<int64_t>(part) * (kItemTiles * kTile) + pr] = make_float2(m[i], l_row);
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t orr[32];
@@ -513,11 +593,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }   // items
   }
 
+  __syncwarp();   // the single-thread roles rejoin their warps before the (aligned) barrier
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the leader's MMAs read the peer's shared memory and TMEM: nobody leaves early
+  else __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (PAIR) tmem_dealloc_2sm<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -529,20 +612,20 @@ __global__ void __launch_bounds__(256)
 attn_combine_kernel(const AttnParams p, int n_split_units) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int u = gw / (2 * kTile);
-  const int r_local = gw % (2 * kTile);
+  const int u = gw / p.item_rows;
+  const int r_local = gw % p.item_rows;
   if (u >= n_split_units) return;
   const int unit = p.n_full + u;
   const int head = unit / p.n_pairs;
-  const int row = (unit % p.n_pairs) * (2 * kTile) + r_local;
+  const int row = (unit % p.n_pairs) * p.item_rows + r_local;
   if (row >= p.s_q && (p.lse == nullptr || row >= p.ld_lse)) return;
   float mmax = -INFINITY;
   for (int c = 0; c < p.split; ++c)
-    mmax = fmaxf(mmax, p.part_ml[(static_cast<int64_t>(u) * p.split + c) * (2 * kTile) + r_local].x);
+    mmax = fmaxf(mmax, p.part_ml[(static_cast<int64_t>(u) * p.split + c) * p.item_rows + r_local].x);
   float lsum = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c = 0; c < p.split; ++c) {
-    const int64_t pr = (static_cast<int64_t>(u) * p.split + c) * (2 * kTile) + r_local;
+    const int64_t pr = (static_cast<int64_t>(u) * p.split + c) * p.item_rows + r_local;
     const float2 ml = p.part_ml[pr];
     const float w = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - mmax);
     lsum += w * ml.y;
@@ -557,17 +640,43 @@ attn_combine_kernel(const AttnParams p, int n_split_units) {
   if (p.lse != nullptr && lane == 0 && row < p.ld_lse) p.lse[static_cast<int64_t>(head) * p.ld_lse + row] = mmax + log2f(lsum);
 }
 
-template <int EMU>
+template <int EMU, bool PAIR>
 static int launch_attn(int grid, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p) {
-  auto kfn = attn_fwd_kernel<EMU>;
+  auto kfn = attn_fwd_kernel<EMU, PAIR>;
   static unsigned long long configured = 0;  // per template instance and device
   if (first_use_on_device(configured)) {
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   }
-  kfn<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kAttnThreads);
+    cfg.dynamicSmemBytes = kAttnSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FGB_CUDA(cudaLaunchKernelEx(&cfg, kfn, tq, tk, tv, p));
+  } else {
+    kfn<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
+  }
   FGB_LAUNCH_CHECK("attn_fwd_kernel");
   return FGB_OK;
+}
+
+// One CTA per SM (256 query rows per work item; the default), or CTA pairs (512 rows per item, tcgen05 cta_group::2;
+// FGB_ATTN_PAIR=1). Measured on the headline self-attention (profiles/r02_attn_pair_ab.log): the pair variant is bit-correct
+// but 45 % SLOWER (9.83 vs 6.75 ms) — every P-ready / S-ready handshake of the two-tile ping-pong then crosses the cluster
+// (remote mbarrier arrive + multicast commit, a few hundred cycles each way) and the loop is latency-bound, not operand-bound.
+// The environment is read on every call so that a test can exercise both variants in one process.
+static bool attn_use_pair(const fgb_ctx* ctx) {
+  const char* e = getenv("FGB_ATTN_PAIR");
+  return e != nullptr && atoi(e) != 0 && ctx->sm_count >= 2;
 }
 
 // How the last, partly filled wave of CTAs is cut along the keys: returns the split factor g (1 = no split) and the
@@ -600,10 +709,12 @@ static void plan_split(int units, int n_kv, int n_sm, int* split, int* n_split_u
 extern "C" int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s_kv, int32_t heads) {
   using namespace fgb;
   if (!ctx || s_q <= 0 || s_kv <= 0 || heads <= 0) return 0;
-  const int n_pairs = (s_q + 2 * kTile - 1) / (2 * kTile);
+  const bool pair = attn_use_pair(ctx);
+  const int item_rows = pair ? 4 * kTile : 2 * kTile;
+  const int n_pairs = (s_q + item_rows - 1) / item_rows;
   int split, n_split;
-  plan_split(n_pairs * heads, (s_kv + kTile - 1) / kTile, ctx->sm_count, &split, &n_split);
-  return static_cast<int64_t>(n_split) * split * (2 * kTile) * (128 * 4 + 8);
+  plan_split(n_pairs * heads, (s_kv + kTile - 1) / kTile, pair ? ctx->sm_count / 2 : ctx->sm_count, &split, &n_split);
+  return static_cast<int64_t>(n_split) * split * item_rows * (128 * 4 + 8);
 }
 
 static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -629,7 +740,10 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_bf16_2d(ctx, &tq, q, s_q, width, ldq, kTile);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(ctx, &tk, k, s_kv, width, ldk, kTile);
+  const bool pair = attn_use_pair(ctx);
+  const int item_rows = pair ? 4 * kTile : 2 * kTile;
+  const int workers = pair ? ctx->sm_count / 2 : ctx->sm_count;
+  rc = make_tmap_bf16_2d(ctx, &tk, k, s_kv, width, ldk, pair ? kTile / 2 : kTile);   // PAIR: each CTA loads 64 of a tile's 128 keys
   if (rc) return rc;
   rc = make_tmap_bf16_2d(ctx, &tv, v, s_kv, width, ldv, kTile);
   if (rc) return rc;
@@ -648,14 +762,15 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   p.col_offset = col_offset;
   for (int i = 0; i < FGB_MAX_PEERS; ++i) p.o_peers[i] = (o_peers && i < n_peers) ? static_cast<__nv_bfloat16*>(o_peers[i]) : nullptr;
   FGB_CHECK_ARG(lse == nullptr || ld_lse >= s_q, "fgb_attn_fwd: ld_lse=%lld < s_q", (long long)ld_lse);
-  p.n_pairs = (s_q + 2 * kTile - 1) / (2 * kTile);
+  p.item_rows = item_rows;
+  p.n_pairs = (s_q + item_rows - 1) / item_rows;
   const int64_t units64 = static_cast<int64_t>(p.n_pairs) * heads;
   FGB_CHECK_ARG(units64 < (1ll << 30), "fgb_attn_fwd: problem too large");
   const int units = static_cast<int>(units64);
   int split = 1, n_split = 0;
   // the key split needs the caller's scratch (the library never allocates); without it every unit runs whole
-  if (workspace != nullptr) plan_split(units, (s_kv + kTile - 1) / kTile, ctx->sm_count, &split, &n_split);
-  const int64_t need = static_cast<int64_t>(n_split) * split * (2 * kTile) * (128 * 4 + 8);
+  if (workspace != nullptr) plan_split(units, (s_kv + kTile - 1) / kTile, workers, &split, &n_split);
+  const int64_t need = static_cast<int64_t>(n_split) * split * item_rows * (128 * 4 + 8);
   if (need > workspace_bytes) {
     split = 1;
     n_split = 0;
@@ -663,7 +778,7 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   p.split = split;
   p.n_full = units - n_split;
   p.part_o = static_cast<float*>(workspace);
-  p.part_ml = reinterpret_cast<float2*>(static_cast<char*>(workspace) + static_cast<int64_t>(n_split) * split * (2 * kTile) * 128 * 4);
+  p.part_ml = reinterpret_cast<float2*>(static_cast<char*>(workspace) + static_cast<int64_t>(n_split) * split * item_rows * 128 * 4);
 
   // fraction of exponentials moved off the MUFU (EMU of every 8 pairs); FGB_ATTN_EMU overrides for tuning
   static int emu = -1;
@@ -673,23 +788,23 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
     if (emu < 0 || emu > 9) emu = kDefaultEmu;
   }
   p.n_items = p.n_full + n_split * split;
-  const int grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;   // persistent: one CTA per SM walks the list
+  const int grid = (p.n_items < workers ? p.n_items : workers) * (pair ? 2 : 1);   // persistent: one CTA (pair) per SM (pair)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define FGB_ATTN_CASE(E)                                                                                  \
+  case E:                                                                                                 \
+    rc = pair ? launch_attn<E, true>(grid, st, tq, tk, tv, p) : launch_attn<E, false>(grid, st, tq, tk, tv, p); \
+    break;
   switch (emu) {
-    case 0: rc = launch_attn<0>(grid, st, tq, tk, tv, p); break;
-    case 1: rc = launch_attn<1>(grid, st, tq, tk, tv, p); break;
-    case 2: rc = launch_attn<2>(grid, st, tq, tk, tv, p); break;
-    case 3: rc = launch_attn<3>(grid, st, tq, tk, tv, p); break;
-    case 4: rc = launch_attn<4>(grid, st, tq, tk, tv, p); break;
-    case 5: rc = launch_attn<5>(grid, st, tq, tk, tv, p); break;
-    case 6: rc = launch_attn<6>(grid, st, tq, tk, tv, p); break;
-    case 7: rc = launch_attn<7>(grid, st, tq, tk, tv, p); break;
-    case 8: rc = launch_attn<8>(grid, st, tq, tk, tv, p); break;
-    default: rc = launch_attn<9>(grid, st, tq, tk, tv, p); break;
+    FGB_ATTN_CASE(0) FGB_ATTN_CASE(1) FGB_ATTN_CASE(2) FGB_ATTN_CASE(3) FGB_ATTN_CASE(4) FGB_ATTN_CASE(5) FGB_ATTN_CASE(6)
+    FGB_ATTN_CASE(7) FGB_ATTN_CASE(8)
+    default:
+      rc = pair ? launch_attn<9, true>(grid, st, tq, tk, tv, p) : launch_attn<9, false>(grid, st, tq, tk, tv, p);
+      break;
   }
+#undef FGB_ATTN_CASE
   if (rc) return rc;
   if (n_split > 0) {
-    const int warps = n_split * 2 * kTile;
+    const int warps = n_split * item_rows;
     attn_combine_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(p, n_split);
     FGB_LAUNCH_CHECK("attn_combine_kernel");
   }

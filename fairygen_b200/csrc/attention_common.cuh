@@ -24,6 +24,7 @@ struct AttnParams {
   // the list, each split `split` ways along the keys (wave-quantisation fix, see fgb_attn_fwd_ex). A unit is
   // (head, pair of query tiles): unit = head * n_pairs + pair.
   int32_t n_pairs, n_full, split;
+  int32_t item_rows;  // query rows of one work item: 256 (one CTA) or 512 (CTA pair)
   int32_t n_items;  // n_full + (split units) * split: the work list the persistent CTAs walk with stride gridDim.x
   float* part_o;    // [split CTA][256 rows][128] un-normalised fp32 partial outputs
   float2* part_ml;  // [split CTA][256 rows] (running max in log2 units, row sum)

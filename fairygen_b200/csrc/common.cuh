@@ -112,6 +112,23 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
     if (++spins > (1u << 18)) __trap();   // ~26 s of parked waits
   }
 }
+// Parked + cluster-scope acquire: barriers of a single-thread role that peer CTAs (remote arrives, multicast commits, 2-CTA
+// TMA) signal.
+__device__ __forceinline__ void mbar_wait_parked_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(FGB_WAIT_HINT_NS))
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 18)) __trap();
+  }
+}
 // Cluster-scope acquire variant, for barriers that peer CTAs / multicast TMA arrive on.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -289,6 +306,17 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 2-CTA form of umma_ts: each CTA of the pair supplies the A rows of its own TMEM
+__device__ __forceinline__ void umma_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }

@@ -587,6 +587,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) tma_store_wait<0>();
   }
 
+  __syncwarp();   // the single-thread roles rejoin their warps before the (aligned) barrier
   tc_fence_before();
   cluster_sync_all();   // the leader's MMAs read the peer's shared memory; nobody leaves before everything is consumed
   if (warp == 1) {

@@ -395,3 +395,30 @@ def test_bounded_attention_reference_modes(env, scale_q, want_mode):
     ops.attention(q, k, ones, out, heads, kmax2=kmax2)
     ops.sync_check()
     assert (out.float() - 1).abs().max() < 8e-3
+
+
+def test_attention_cta_pair_variant(env, monkeypatch):
+    """The 2-CTA (tcgen05 cta_group::2) variant of the attention kernel, kept behind FGB_ATTN_PAIR=1 (it is slower on this
+    workload, see csrc/attention.cu): same results as the default, including the key-split tail, ragged rows and all three
+    reference modes."""
+    ops, o = env
+    for s_q, s_kv, heads, scale_q in ((600, 1000, 2, 1.0), (300, 4100, 5, 1.0), (1030, 700, 3, 9.0), (520, 260, 2, 40.0), (48, 32, 2, 1.0)):
+        d = heads * 128
+        q, k, v = rnd(s_q, d, seed=1, scale=scale_q), rnd(s_kv, d, seed=2), rnd(s_kv, d, seed=3)
+        kmax2 = torch.empty(heads, dtype=torch.float32, device="cuda")
+        ops.head_norm_max(k, kmax2, heads)
+        outs = []
+        for pair in ("0", "1"):
+            monkeypatch.setenv("FGB_ATTN_PAIR", pair)
+            out = torch.full((s_q, d), float("nan"), dtype=BF, device="cuda")
+            lse = torch.empty(heads, ops.stat_rows(s_q), dtype=torch.float32, device="cuda")
+            ops.attention(q, k, v, out, heads, lse=lse, kmax2=kmax2)
+            plain = torch.full((s_q, d), float("nan"), dtype=BF, device="cuda")
+            ops.attention(q, k, v, plain, heads)
+            ops.sync_check()
+            outs.append((out, lse[:, :s_q].clone(), plain))
+        monkeypatch.delenv("FGB_ATTN_PAIR")
+        ref = o.attention(q[None].float(), k[None].float(), v[None].float(), heads)[0]
+        for out, lse, plain in outs:
+            assert torch.isfinite(out.float()).all() and rel_l2(out, ref) < 6e-3 and rel_l2(plain, ref) < 8e-3
+        assert rel_l2(outs[1][0], outs[0][0]) < 2e-3 and (outs[1][1] - outs[0][1]).abs().max() < 1e-2
