@@ -427,6 +427,125 @@ __global__ void sp_barrier_kernel(PeerPtrs flags, int world, int rank, int epoch
   __threadfence_system();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused Ulysses exchange, receiver side (the sender is the q|k|v GEMM epilogue, fgb_gemm_qkv_scatter)
+// ---------------------------------------------------------------------------------------------
+// Barrier 0 of a block with the row statistics riding along: every rank pushes the sums of squares of its q and k rows
+// (rowsq [2][rows], filled by the GEMM epilogue's atomics) into every peer's stats matrix [2][s_pad] at its own row window,
+// zeroes rowsq and kmax2 for the next use, then runs the epoch exchange of sp_barrier_kernel. One block.
+__global__ void __launch_bounds__(1024)
+sp_stats_barrier_kernel(PeerPtrs flags, PeerPtrs stats, float* __restrict__ rowsq, int rows, int s_pad, float* __restrict__ kmax2, int hpr,
+                        int world, int rank, int epoch, int* __restrict__ status) {
+  for (int idx = threadIdx.x; idx < 2 * rows; idx += blockDim.x) {
+    const int g = idx / rows, r = idx - g * rows;
+    const float v = rowsq[idx];
+    rowsq[idx] = 0.f;
+    for (int q = 0; q < world; ++q) static_cast<float*>(stats.p[q])[static_cast<int64_t>(g) * s_pad + rank * rows + r] = v;
+  }
+  if (static_cast<int>(threadIdx.x) < hpr) kmax2[threadIdx.x] = 0.f;
+  __threadfence_system();
+  __syncthreads();
+  const int q = threadIdx.x;
+  if (q >= world) return;
+  __threadfence_system();
+  int* remote = static_cast<int*>(flags.p[q]) + rank;
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const int* mine = static_cast<const int*>(flags.p[rank]) + q;
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (v - epoch >= 0) break;
+    if (clock64() - t0 > 50000000000ll) {   // ~30 s: a peer died. Report instead of hanging or trapping.
+      if (status) atomicExch(status, epoch);
+      break;
+    }
+  }
+  __threadfence_system();
+}
+
+// RMSNorm (statistics of the FULL row, received with the data) + weight + 3-D RoPE on the received q and k groups, in place:
+// recv [s_pad][3][hpr][128]; the full-row mean square of token t is stats[g*s_pad + t] / dim. Also leaves
+// kmax2[h] = max over the real tokens of ||k[t, h]||^2 (the key bound of the bounded-score softmax). One warp per token row,
+// grid-stride (the running maxima stay in registers).
+__global__ void __launch_bounds__(256)
+recv_norm_rope_kernel(__nv_bfloat16* __restrict__ recv, int s_pad, int tokens, int hpr, const float* __restrict__ stats, int dim,
+                      float eps, const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
+                      const float2* __restrict__ rope_tab, int gf, int gh, int gw, float* __restrict__ kmax2) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int vecs = hpr * 16;                  // 16-byte vectors per group and row
+  const int64_t ld = static_cast<int64_t>(3) * hpr * 128;
+  const float inv_d = 1.0f / dim;
+  float best[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // per pass (head pair) running max of ||k||^2; hpr <= 12
+  const int c0 = (lane & 15) * 4;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < s_pad; t += warps) {
+    float cs[4], sn[4];
+    const bool rotate = rope_tab != nullptr && t < gf * gh * gw;
+    if (rotate) {
+      const int fi = t / (gh * gw), hi = (t / gw) % gh, wi = t % gw;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        const int pos = c < 22 ? fi : (c < 43 ? hi : wi);
+        const float2 e = __ldg(rope_tab + pos * 64 + c);
+        cs[j] = e.x;
+        sn[j] = e.y;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const float rs = rsqrtf(__ldg(stats + static_cast<int64_t>(g) * s_pad + t) * inv_d + eps);
+      uint4* row = reinterpret_cast<uint4*>(recv + static_cast<int64_t>(t) * ld + g * hpr * 128);
+      const uint4* wr = reinterpret_cast<const uint4*>(g == 0 ? wq : wk);
+#pragma unroll
+      for (int pass = 0; pass < 6; ++pass) {
+        const int c = pass * 32 + lane;
+        float ss = 0.f;
+        if (c < vecs) {
+          float f[8];
+          unpack8(row[c], f);
+          const uint4 wv = __ldg(wr + c);
+          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w)   // norm -> bf16, * weight -> bf16 (two elements per op), as rmsnorm_rope_kernel
+            o[w] = mul_bf16x2(pack_bf16(f[2 * w] * rs, f[2 * w + 1] * rs), ww[w]);
+          if (rotate) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
+              o[j] = pack_bf16(a * cs[j] - b * sn[j], a * sn[j] + b * cs[j]);
+            }
+          }
+          row[c] = make_uint4(o[0], o[1], o[2], o[3]);
+          if (g == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ss += bf16_lo(o[j]) * bf16_lo(o[j]) + bf16_hi(o[j]) * bf16_hi(o[j]);
+          }
+        }
+        if (g == 1 && pass * 32 < vecs) {   // warp-uniform
+#pragma unroll
+          for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
+          if (t < tokens) best[pass] = fmaxf(best[pass], ss);
+        }
+      }
+    }
+  }
+  __shared__ float red[8][12];
+  if ((lane & 15) == 0) {
+#pragma unroll
+    for (int pass = 0; pass < 6; ++pass) red[threadIdx.x >> 5][2 * pass + (lane >> 4)] = best[pass];
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < hpr) {
+    float mx = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[w][threadIdx.x]);
+    atomicMax(reinterpret_cast<unsigned int*>(kmax2) + threadIdx.x, __float_as_uint(mx));   // non-negative floats order like their bits
+  }
+}
+
 static inline int grid_1d(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
 
 template <bool AFFINE>
@@ -710,6 +829,44 @@ extern "C" int fgb_head_norm_max(fgb_ctx* ctx, const void* x, int64_t ldx, int32
   }
 #undef FGB_HNM_CASE
   FGB_LAUNCH_CHECK("head_norm_max_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_sp_stats_barrier(fgb_ctx* ctx, void* const* peer_flags, void* const* peer_stats, void* rowsq, int32_t rows,
+                                    int32_t s_pad, void* kmax2, int32_t hpr, int32_t world, int32_t rank, int32_t epoch, void* status,
+                                    void* stream) {
+  FGB_CHECK_ARG(ctx && peer_flags && peer_stats && rowsq && kmax2, "fgb_sp_stats_barrier: NULL argument");
+  FGB_CHECK_ARG(world > 0 && world <= FGB_MAX_PEERS && rank >= 0 && rank < world && rows > 0 && s_pad == rows * world && hpr > 0 && hpr <= 12,
+                "fgb_sp_stats_barrier: rows=%d s_pad=%d hpr=%d world=%d rank=%d", rows, s_pad, hpr, world, rank);
+  PeerPtrs fl, st;
+  for (int i = 0; i < FGB_MAX_PEERS; ++i) {
+    fl.p[i] = i < world ? peer_flags[i] : nullptr;
+    st.p[i] = i < world ? peer_stats[i] : nullptr;
+  }
+  for (int i = 0; i < world; ++i) FGB_CHECK_ARG(fl.p[i] && st.p[i], "fgb_sp_stats_barrier: peer %d", i);
+  sp_stats_barrier_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(fl, st, static_cast<float*>(rowsq), rows, s_pad,
+                                                                            static_cast<float*>(kmax2), hpr, world, rank, epoch,
+                                                                            static_cast<int*>(status));
+  FGB_LAUNCH_CHECK("sp_stats_barrier_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_recv_norm_rope(fgb_ctx* ctx, void* recv, int32_t s_pad, int32_t tokens, int32_t hpr, const void* stats, int32_t dim,
+                                  float eps, const void* wq, const void* wk, const void* rope_tab, int32_t gf, int32_t gh, int32_t gw,
+                                  void* kmax2, void* stream) {
+  FGB_CHECK_ARG(ctx && recv && stats && wq && wk && kmax2, "fgb_recv_norm_rope: NULL argument");
+  FGB_CHECK_ARG(s_pad > 0 && tokens > 0 && tokens <= s_pad && hpr > 0 && hpr <= 12 && dim > 0, "fgb_recv_norm_rope: s_pad=%d tokens=%d hpr=%d",
+                s_pad, tokens, hpr);
+  FGB_CHECK_ARG(aligned16(recv) && aligned16(wq) && aligned16(wk), "fgb_recv_norm_rope: operands must be 16-byte aligned");
+  if (rope_tab)
+    FGB_CHECK_ARG(gf > 0 && gh > 0 && gw > 0 && gf <= 1024 && gh <= 1024 && gw <= 1024, "fgb_recv_norm_rope: grid (%d,%d,%d) outside the RoPE table",
+                  gf, gh, gw);
+  int grid = (s_pad + 7) / 8;
+  if (grid > ctx->sm_count * 6) grid = ctx->sm_count * 6;
+  recv_norm_rope_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(recv), s_pad, tokens, hpr, static_cast<const float*>(stats), dim, eps, static_cast<const bf16*>(wq),
+      static_cast<const bf16*>(wk), static_cast<const float2*>(rope_tab), gf, gh, gw, static_cast<float*>(kmax2));
+  FGB_LAUNCH_CHECK("recv_norm_rope_kernel");
   return FGB_OK;
 }
 

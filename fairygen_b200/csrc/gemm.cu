@@ -356,6 +356,17 @@ struct PairParams {
   int32_t rows_gate0;
   int32_t m_tiles, n_tiles, tiles, k_blocks;
   int32_t group_m, band_n;   // supertile: band_n tile columns x group_m tile rows, m fastest inside
+  // SCATTER (fused Ulysses exchange of the q|k|v projection, fgb_gemm_qkv_scatter): column c of the [m, 3*dim] output belongs
+  // to group c / dim (q, k, v) and head (c % dim) / 128; the 64-column block goes to the receive matrix of the peer that owns
+  // the head — peer = head / hpr, columns (group*hpr + head % hpr)*128 + c % 128 — through that peer's tensor map (whose base is
+  // already this rank's row window). rowsq[g*m + row] += sum of squares of the (bias-added, bf16-rounded) q / k row: the
+  // receiver's RMSNorm needs the statistics of the FULL row, which no single rank holds after the head split.
+  float* rowsq;
+  int32_t dim, hpr;
+};
+
+struct PeerMaps {
+  CUtensorMap m[FGB_MAX_PEERS];
 };
 
 __device__ __forceinline__ void pair_tile_coords(const PairParams& p, int tile, int& mt, int& nt) {
@@ -375,10 +386,10 @@ __device__ __forceinline__ void pair_tile_coords(const PairParams& p, int tile, 
 
 // BN = 256: the default. BN = 128: half-width tiles for problems whose 256-wide tile count leaves most of the last wave idle
 // (e.g. N = 3072 on the 6820 rows of a Ulysses SP4 rank: 324 tiles = 4.38 waves of 74 clusters; 648 half tiles = 8.76).
-template <int EPI, int BN>
+template <int EPI, int BN, bool SCATTER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_c, const PairParams p) {
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ PeerMaps peer_maps, const PairParams p) {
   constexpr int kPairBN = BN;
   constexpr int kPairBBytes = (BN / 2) * kBK * 2;
   extern __shared__ uint8_t smem_raw[];
@@ -505,6 +516,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       };
       if (kReadsC) load_c(0, xcur);
+      float ss = 0.f;   // SCATTER: sum of squares of this row's outputs in this tile (a tile lies inside one of q / k / v)
 #pragma unroll 1
       for (int c64 = 0; c64 < kPairBN / 64; ++c64) {
         if (nt * kPairBN + c64 * 64 >= p.n) break;   // warp-uniform
@@ -535,6 +547,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (EPI == FGB_EPI_BIAS_GELU_TANH) {
 #pragma unroll
               for (int i = 0; i < 8; i += 2) gelu_tanh_2(y[i], y[i + 1]);
+            }
+            if (SCATTER) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ss = fmaf(y[i], y[i], ss);
             }
             if (kReadsC) {
               const uint4 xv = xcur[g];
@@ -574,10 +590,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmap_c, sbuf, nt * kPairBN + c64 * 64, row0);   // rows >= m and columns >= n are clipped by the tensor map
+          const int gcol = nt * kPairBN + c64 * 64;
+          if (SCATTER) {
+            const int grp = gcol / p.dim, head = (gcol - grp * p.dim) >> 7;
+            const int peer = head / p.hpr;
+            tma_store_2d(&peer_maps.m[peer], sbuf, (grp * p.hpr + head - peer * p.hpr) * 128 + (gcol & 127), row0);
+          } else {
+            tma_store_2d(&tmap_c, sbuf, gcol, row0);   // rows >= m and columns >= n are clipped by the tensor map
+          }
           tma_store_commit();
         }
         buf ^= 1;
+      }
+      if (SCATTER) {
+        const int grp = (nt * kPairBN) / p.dim;
+        if (grp < 2 && row_ok) atomicAdd(p.rowsq + static_cast<int64_t>(grp) * p.m + row, ss);
       }
       // this warp has read its part of the accumulator: one arrival per warp on the leader's barrier
       tc_fence_before();
@@ -596,17 +623,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, bool SCATTER = false>
 static int launch_gemm_pair(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const PairParams& p,
-                            cudaStream_t stream) {
-  auto kfn = gemm_pair_kernel<EPI, BN>;
+                            cudaStream_t stream, const PeerMaps* pm = nullptr) {
+  auto kfn = gemm_pair_kernel<EPI, BN, SCATTER>;
+  static PeerMaps no_peers{};
   static unsigned long long configured = 0;  // per template instance and device
   if (first_use_on_device(configured)) {
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
   }
   int clusters = ctx->sm_count / 2;
   if (p.tiles < clusters) clusters = p.tiles;
-  kfn<<<2 * clusters, kPairThreads, kPairSmem, stream>>>(ta, tb, tc, p);
+  kfn<<<2 * clusters, kPairThreads, kPairSmem, stream>>>(ta, tb, tc, pm ? *pm : no_peers, p);
   FGB_LAUNCH_CHECK("gemm_pair_kernel");
   return FGB_OK;
 }
@@ -692,6 +720,8 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
     pp.m = m;
     pp.n = n;
     pp.rows_gate0 = rows_gate0;
+    pp.rowsq = nullptr;
+    pp.dim = pp.hpr = 0;
     pp.m_tiles = m_tiles;
     pp.n_tiles = (n + bn - 1) / bn;
     pp.tiles = pp.m_tiles * pp.n_tiles;
@@ -749,6 +779,52 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
     case FGB_EPI_GATED_RESIDUAL: return launch_gemm<FGB_EPI_GATED_RESIDUAL>(ctx, ta, tb, p, s, pa2, pb2);
     default: return launch_gemm<FGB_EPI_RESIDUAL>(ctx, ta, tb, p, s, pa2, pb2);
   }
+}
+
+extern "C" int fgb_gemm_qkv_scatter(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, int32_t m,
+                                    int32_t dim, int32_t k, void* const* peer_recv, int32_t world, int32_t rank, float* rowsq,
+                                    void* stream) {
+  using namespace fgb;
+  FGB_CHECK_ARG(ctx && a && w && peer_recv && rowsq, "fgb_gemm_qkv_scatter: NULL argument");
+  FGB_CHECK_ARG(m > 0 && k > 0 && k % 8 == 0 && dim > 0 && dim % 256 == 0 && lda >= k && ldw >= k,
+                "fgb_gemm_qkv_scatter: m=%d dim=%d (multiple of 256) k=%d", m, dim, k);
+  const int heads = dim / 128;
+  FGB_CHECK_ARG(world > 0 && world <= FGB_MAX_PEERS && heads % world == 0 && rank >= 0 && rank < world,
+                "fgb_gemm_qkv_scatter: heads=%d world=%d rank=%d", heads, world, rank);
+  FGB_CHECK_ARG(!bias || aligned16(bias), "fgb_gemm_qkv_scatter: bias must be 16-byte aligned");
+  FGB_CHECK_ARG(ctx->sm_count >= 2, "fgb_gemm_qkv_scatter: needs CTA pairs");
+  const int hpr = heads / world;
+  const int64_t ld_recv = static_cast<int64_t>(3) * hpr * 128;
+  const int n = 3 * dim;
+  CUtensorMap ta, tb;
+  PeerMaps pm{};
+  int rc;
+  if ((rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kPairBM))) return rc;
+  if ((rc = make_tmap_bf16_2d(ctx, &tb, w, n, k, ldw, 128))) return rc;
+  for (int q = 0; q < world; ++q) {
+    FGB_CHECK_ARG(peer_recv[q] && aligned16(peer_recv[q]), "fgb_gemm_qkv_scatter: peer receive matrix %d", q);
+    // this rank's row window [rank*m, rank*m + m) of peer q's receive matrix: the map clips the padded tile rows at m
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(peer_recv[q]) + static_cast<int64_t>(rank) * m * ld_recv;
+    if ((rc = make_tmap_bf16_2d(ctx, &pm.m[q], base, m, ld_recv, ld_recv, 32))) return rc;
+  }
+  for (int q = world; q < FGB_MAX_PEERS; ++q) pm.m[q] = pm.m[0];
+  PairParams pp;
+  pp.bias = static_cast<const __nv_bfloat16*>(bias);
+  pp.c = nullptr;
+  pp.gate0 = pp.gate1 = nullptr;
+  pp.ldc = 0;
+  pp.m = m;
+  pp.n = n;
+  pp.rows_gate0 = 0;
+  pp.rowsq = rowsq;
+  pp.dim = dim;
+  pp.hpr = hpr;
+  pp.m_tiles = (m + kPairTM - 1) / kPairTM;
+  pp.n_tiles = (n + 255) / 256;
+  pp.tiles = pp.m_tiles * pp.n_tiles;
+  pp.k_blocks = (k + kBK - 1) / kBK;
+  pair_supertile(pp.m_tiles, pp.n_tiles, k, &pp.group_m, &pp.band_n);
+  return launch_gemm_pair<FGB_EPI_BIAS, 256, true>(ctx, ta, tb, pm.m[0], pp, static_cast<cudaStream_t>(stream), &pm);
 }
 
 extern "C" int fgb_gemm_dgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* w, int64_t ldw, void* dx, int64_t ld_dx,

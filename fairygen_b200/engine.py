@@ -291,7 +291,8 @@ class WanDiTEngine:
             if sp is not None and getattr(sp, "exchange", "nccl") == "p2p":
                 def qkv_rows(r0, r1, a=a, b=b, qkv=qkv):
                     k("gemm_qkv", ops.gemm, a[r0:r1], b.wqkv, b.bqkv, qkv[r0:r1])
-                sp.attention(self, ws, qkv, o, S, norm=(cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0), qkv_gemm=qkv_rows)
+                fused = (a, b.wqkv, b.bqkv, cfg.eps, b.nq, b.nk, self.rope_tab, grid) if (getattr(sp, "fused_send", False) and d % 256 == 0) else None
+                sp.attention(self, ws, qkv, o, S, norm=(cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0), qkv_gemm=qkv_rows, fused=fused)
             else:
                 k("gemm_qkv", ops.gemm, a, b.wqkv, b.bqkv, qkv)
                 k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)

@@ -368,6 +368,33 @@ def sp_return_heads(x, peer_ptrs, ld_dst: int, rows: int, heads: int, groups: in
                                               world, rank, _stream()), "fgb_sp_return_heads")
 
 
+def gemm_qkv_scatter(a, w, bias, dim: int, peer_recv_ptrs, world: int, rank: int, rowsq):
+    """q|k|v = a @ w.T + bias, every 32x64 block TMA-stored into the head owner's receive matrix (fused Ulysses send);
+    rowsq fp32 [2, rows] += sum of squares of each q / k row."""
+    lda, ldw = _rowmajor(a, "a"), _rowmajor(w, "w")
+    m, k = a.shape
+    if w.shape != (3 * dim, k) or rowsq.dtype != torch.float32 or rowsq.numel() != 2 * m or not rowsq.is_contiguous():
+        raise ValueError(f"gemm_qkv_scatter: a {tuple(a.shape)} w {tuple(w.shape)} dim {dim} rowsq {tuple(rowsq.shape)}")
+    _vec(bias, 3 * dim, "bias")
+    _lib.check(_lib.lib().fgb_gemm_qkv_scatter(_h(a).handle, _p(a), lda, _p(w), ldw, _p(bias), m, dim, k, _ptr_array(peer_recv_ptrs), world,
+                                               rank, _p(rowsq), _stream()), "fgb_gemm_qkv_scatter")
+
+
+def sp_stats_barrier(device, flag_ptrs, stats_ptrs, rowsq, rows: int, s_pad: int, kmax2, hpr: int, world: int, rank: int, epoch: int,
+                     status=None):
+    _lib.check(_lib.lib().fgb_sp_stats_barrier(context(device).handle, _ptr_array(flag_ptrs), _ptr_array(stats_ptrs), _p(rowsq), rows, s_pad,
+                                               _p(kmax2), hpr, world, rank, epoch, _p(status), _stream()), "fgb_sp_stats_barrier")
+
+
+def recv_norm_rope(recv, tokens: int, hpr: int, stats, dim: int, eps: float, wq, wk, rope_tab, grid, kmax2):
+    """RMSNorm (received full-row statistics) + weight slice + RoPE on the q, k groups of recv [s_pad, 3*hpr*128], in place;
+    kmax2[h] = max ||k||^2 over the first `tokens` rows."""
+    if recv.dtype != BF16 or recv.dim() != 2 or recv.shape[1] != 3 * hpr * 128 or not recv.is_contiguous():
+        raise ValueError(f"recv_norm_rope: recv {tuple(recv.shape)} hpr {hpr}")
+    _lib.check(_lib.lib().fgb_recv_norm_rope(_h(recv).handle, _p(recv), recv.shape[0], tokens, hpr, _p(stats), dim, eps, _p(wq), _p(wk),
+                                             _p(rope_tab), grid[0], grid[1], grid[2], _p(kmax2), _stream()), "fgb_recv_norm_rope")
+
+
 def sp_barrier(device, flag_ptrs, world: int, rank: int, epoch: int):
     _lib.check(_lib.lib().fgb_sp_barrier(context(device).handle, _ptr_array(flag_ptrs), world, rank, epoch, _stream()), "fgb_sp_barrier")
 

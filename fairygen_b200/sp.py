@@ -63,12 +63,16 @@ class PeerArena:
         self.off_recv = 0
         self.off_o = (s_pad * wloc * 2 + 255) // 256 * 256
         self.off_dqkv = self.off_o + (rows * d * 2 + 255) // 256 * 256      # training only: [rows, 3*H*128] gradient matrix
-        self.off_flags = self.off_dqkv + ((rows * 3 * d * 2 + 255) // 256 * 256 if backward else 0)
-        total = self.off_flags + 2 * 64 * 4
+        self.off_stats = self.off_dqkv + ((rows * 3 * d * 2 + 255) // 256 * 256 if backward else 0)   # fp32 [2][s_pad]: full-row sums of squares of q, k
+        self.off_flags = self.off_stats + (2 * s_pad * 4 + 255) // 256 * 256
+        total = self.off_flags + 2 * 64 * 4 + 64
         self.buf = torch.zeros(total, dtype=torch.uint8, device=device)
         self.recv = self.buf[self.off_recv:self.off_recv + s_pad * wloc * 2].view(torch.bfloat16).view(s_pad, wloc)
         self.o = self.buf[self.off_o:self.off_o + rows * d * 2].view(torch.bfloat16).view(rows, d)
         self.dqkv = self.buf[self.off_dqkv:self.off_dqkv + rows * 3 * d * 2].view(torch.bfloat16).view(rows, 3 * d) if backward else None
+        self.stats = self.buf[self.off_stats:self.off_stats + 2 * s_pad * 4].view(torch.float32).view(2, s_pad)
+        self.status = self.buf[self.off_flags + 2 * 64 * 4:self.off_flags + 2 * 64 * 4 + 4].view(torch.int32)   # barrier time-out report
+        self.rowsq = torch.zeros(2, rows, dtype=torch.float32, device=device)   # local: filled by the q|k|v GEMM epilogue
         handle, offset = ops.ipc_export(self.buf)
         everyone = [None] * world
         dist.all_gather_object(everyone, (handle, offset), group=group)
@@ -84,6 +88,7 @@ class PeerArena:
         self.recv_ptrs = [b + self.off_recv for b in bases]
         self.o_ptrs = [b + self.off_o for b in bases]
         self.dqkv_ptrs = [b + self.off_dqkv for b in bases]
+        self.stats_ptrs = [b + self.off_stats for b in bases]
         self.flag_ptrs = [[b + self.off_flags + which * 64 * 4 for b in bases] for which in (0, 1)]
         self.epoch = 0
         torch.cuda.synchronize(device)
@@ -110,6 +115,7 @@ class SequenceParallel:
         import os
         # p2p: run the QKV projection in two row chunks and scatter the first under the second (FGB_SP_OVERLAP=0: A/B switch)
         self.overlap = overlap and os.environ.get("FGB_SP_OVERLAP", "1") != "0"
+        self.fused_send = os.environ.get("FGB_SP_FUSED", "1") != "0"   # q|k|v projection sends from its epilogue (A/B switch)
         self.arena = None
         self._side = None      # side stream + events of the overlapped scatter (created on first use)
         self._ev = None
@@ -161,13 +167,15 @@ class SequenceParallel:
         k("rmsnorm_rope", ops.rmsnorm_rope_scatter, x[:, d:2 * d], eps, wk, rope_tab, grid, tok0 + r0, ptrs, self.world, self.rank, 1, 3)
         k("sp_scatter", ops.sp_scatter_heads, x[:, 2 * d:], ptrs, heads, 1, self.world, self.rank, 2, 3)
 
-    def attention(self, engine, ws, qkv: torch.Tensor, o: torch.Tensor, tokens: int, norm=None, qkv_gemm=None) -> None:
+    def attention(self, engine, ws, qkv: torch.Tensor, o: torch.Tensor, tokens: int, norm=None, qkv_gemm=None, fused=None) -> None:
         """qkv [rows, 3*H*128] -> o [rows, H*128].  norm = None: q, k are already RMS-normed + rotated.
         norm = (eps, weight_q, weight_k, rope_tab, grid, token_offset) (p2p only): the pre-norm q, k are normalised,
         rotated and sent by one fused kernel each.
         qkv_gemm (p2p only): callable (r0, r1) that launches the fused QKV projection for rows [r0, r1) of `qkv`.  The
         projection then runs in two row chunks and the NVLink scatter of the first chunk (a side stream) overlaps the
-        tensor-core work of the second — the exchange is link-bound (~0.5 TB/s of peer stores), the projection is not."""
+        tensor-core work of the second — the exchange is link-bound (~0.5 TB/s of peer stores), the projection is not.
+        fused (p2p only, the default of the engine): (a, w_qkv, b_qkv, eps, weight_q, weight_k, rope_tab, grid) — the projection
+        itself sends: see the comments below and fgb_gemm_qkv_scatter."""
         heads = engine.cfg.num_heads
         hpr = heads // self.world
         wloc = hpr * 128
@@ -175,6 +183,23 @@ class SequenceParallel:
         if self.exchange == "p2p":
             ar = self.arena            # created by the engine's workspace; ws["recv"] / ws["o"] are views of it
             rows = qkv.shape[0]
+            if fused is not None:
+                # send side fused into the projection: the GEMM epilogue TMA-stores every block into the head owner's receive
+                # matrix; the full-row statistics of q and k travel with barrier 0; RMSNorm + RoPE happen on the receiver
+                a, w, bias, eps, wq, wk, rope_tab, grid = fused
+                k("gemm_qkv", ops.gemm_qkv_scatter, a, w, bias, heads * 128, ar.recv_ptrs, self.world, self.rank, ar.rowsq)
+                ar.epoch += 1
+                kmax2 = ws["kmax2"][:hpr]
+                k("sp_barrier", ops.sp_stats_barrier, qkv.device, ar.flag_ptrs[0], ar.stats_ptrs, ar.rowsq, rows, rows * self.world, kmax2,
+                  hpr, self.world, self.rank, ar.epoch, ar.status)
+                h0 = self.rank * wloc
+                k("rmsnorm_rope", ops.recv_norm_rope, ar.recv, tokens, hpr, ar.stats, heads * 128, eps, wq[h0:h0 + wloc], wk[h0:h0 + wloc],
+                  rope_tab, grid, kmax2)
+                recv = ar.recv
+                k("attn_self", ops.attention_scatter, recv[:, :wloc], recv[:tokens, wloc:2 * wloc], recv[:tokens, 2 * wloc:], ar.o_ptrs,
+                  heads * 128, rows, self.rank * wloc, hpr, kmax2=kmax2)
+                k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[1], self.world, self.rank, ar.epoch)
+                return
             if qkv_gemm is None:
                 self._scatter_rows(engine, qkv, 0, rows, norm)
             elif rows < 1024 or not self.overlap:

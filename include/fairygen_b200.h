@@ -214,6 +214,28 @@ int fgb_rmsnorm_rope_scatter(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t r
 int fgb_sp_return_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* const* peer_bufs, int64_t ld_dst, int32_t rows,
                         int32_t s_pad, int32_t heads, int32_t groups, int32_t world, int32_t rank, void* stream);
 int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* stream);
+
+/* The same exchange with the SEND side fused into the q|k|v projection (DIT:140-142 + USP:125-146) — the default on GPUs:
+ *   fgb_gemm_qkv_scatter  out = a[m,k] · w[3*dim,k]ᵀ + bias, never written locally: the epilogue of the 2-CTA tcgen05 GEMM TMA-stores
+ *                         every 32 x 64 block straight into the receive matrix of the peer that owns the head (peer_recv[q] =
+ *                         base of peer q's [world*m, 3*(heads/world)*128] matrix; this rank writes rows [rank*m, rank*m + m)), so
+ *                         the NVLink traffic overlaps the tensor-core main loop. rowsq (fp32 [2][m], zero on entry) receives the
+ *                         sum of squares of every q and k row: RMSNorm (DIT:99-110) is over the FULL row, which no rank holds
+ *                         after the head split.
+ *   fgb_sp_stats_barrier  barrier 0 of the block with the statistics riding along: pushes rowsq into every peer's stats matrix
+ *                         (peer_stats[q] = fp32 [2][s_pad], rows [rank*rows, +rows)), zeroes rowsq and kmax2, then exchanges the
+ *                         epoch flags like fgb_sp_barrier. A peer that does not answer within ~30 s makes the kernel write the
+ *                         epoch to *status (device int32, may be NULL) and return instead of hanging.
+ *   fgb_recv_norm_rope    receiver side: RMSNorm with the received full-row statistics, weight slice (wq / wk point at this
+ *                         rank's heads), 3-D RoPE (DIT:91-96) on the q and k groups of recv [s_pad, 3*hpr*128], in place; leaves
+ *                         kmax2[h] = max over the first `tokens` rows of ||k[t,h]||^2 (the bound fgb_attn_fwd_bounded wants). */
+int fgb_gemm_qkv_scatter(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, int32_t m, int32_t dim,
+                         int32_t k, void* const* peer_recv, int32_t world, int32_t rank, float* rowsq, void* stream);
+int fgb_sp_stats_barrier(fgb_ctx* ctx, void* const* peer_flags, void* const* peer_stats, void* rowsq, int32_t rows, int32_t s_pad,
+                         void* kmax2, int32_t hpr, int32_t world, int32_t rank, int32_t epoch, void* status, void* stream);
+int fgb_recv_norm_rope(fgb_ctx* ctx, void* recv, int32_t s_pad, int32_t tokens, int32_t hpr, const void* stats, int32_t dim, float eps,
+                       const void* wq, const void* wk, const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, void* kmax2,
+                       void* stream);
 /* fgb_attn_fwd_ex whose output row of global token t goes to o_peers[t / rows_per_peer][(t % rows_per_peer) * ldo +
  * col_offset + head*128 ...] (col_offset = rank * heads * 128 for Ulysses). */
 int fgb_attn_fwd_scatter(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
