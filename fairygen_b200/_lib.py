@@ -29,6 +29,7 @@ SIGNATURES = {
     "fgb_gemm_dgrad_ex": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _I64, _I32, _P]),
     "fgb_attn_fwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P]),
     "fgb_attn_fwd_ex": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _I64, _P, _I64, _P]),
+    "fgb_qk_norm_rope": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "fgb_head_norm_max": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
     "fgb_attn_set_stats": (ctypes.c_int, [_P, _P]),
     "fgb_attn_fwd_bounded": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _I64, _P, _I64,

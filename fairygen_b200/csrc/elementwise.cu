@@ -175,6 +175,100 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Single-GPU self-attention prologue in ONE pass over the fused q|k|v rows: RMSNorm + weight + 3-D RoPE on q and on k
+// (DIT:140-144) and the key bound kmax2[h] = max_rows ||k[row, h]||^2 of the bounded-score softmax — what used to be two
+// rmsnorm_rope launches plus a head_norm_max pass that read k a second time. One warp per row, grid-stride; the per-head
+// running maxima stay in registers (lane 0 and 16 of each vector index own a head).
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowWarps * 32)
+qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int rows, float eps, const __nv_bfloat16* __restrict__ wq,
+                    const __nv_bfloat16* __restrict__ wk, const float2* __restrict__ rope_tab, int gf, int gh, int gw, int token_offset,
+                    float* __restrict__ kmax2) {
+  const int lane = threadIdx.x & 31;
+  constexpr int D = NV * 256;
+  float best[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) best[i] = 0.f;
+  for (int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5); row < rows; row += gridDim.x * kRowWarps) {
+    float cs[4], sn[4];
+    bool rotate = false;
+    if (rope_tab != nullptr) {
+      const int t = token_offset + row;
+      if (t < gf * gh * gw) {
+        rotate = true;
+        const int fi = t / (gh * gw), hi = (t / gw) % gh, wi = t % gw;
+        const int c0 = (lane & 15) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j;
+          const int pos = c < 22 ? fi : (c < 43 ? hi : wi);
+          const float2 e = __ldg(rope_tab + pos * 64 + c);
+          cs[j] = e.x;
+          sn[j] = e.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint4* xr = reinterpret_cast<uint4*>(qkv + static_cast<int64_t>(row) * ld + g * D);
+      uint4 v[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float f[8];
+        unpack8(v[i], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sq += f[e] * f[e];
+      }
+      const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+      const uint4* wr = reinterpret_cast<const uint4*>(g == 0 ? wq : wk);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float f[8];
+        unpack8(v[i], f);
+        const uint4 wv = __ldg(wr + i * 32 + lane);
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)   // norm -> bf16, * weight -> bf16 (two elements per op)
+          o[w] = mul_bf16x2(pack_bf16(f[2 * w] * rs, f[2 * w + 1] * rs), ww[w]);
+        if (rotate) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
+            o[j] = pack_bf16(a * cs[j] - b * sn[j], a * sn[j] + b * cs[j]);
+          }
+        }
+        xr[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+        if (g == 1) {
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ss += bf16_lo(o[j]) * bf16_lo(o[j]) + bf16_hi(o[j]) * bf16_hi(o[j]);
+#pragma unroll
+          for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
+          best[i] = fmaxf(best[i], ss);
+        }
+      }
+    }
+  }
+  __shared__ float red[kRowWarps][2 * NV];
+  if ((lane & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[threadIdx.x >> 5][2 * i + (lane >> 4)] = best[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * NV) {
+    float mx = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRowWarps; ++w) mx = fmaxf(mx, red[w][threadIdx.x]);
+    atomicMax(reinterpret_cast<unsigned int*>(kmax2) + threadIdx.x, __float_as_uint(mx));   // non-negative floats order like their bits
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // out[h] = max over rows of ||x[row, h*128 : (h+1)*128]||^2  — the key-norm bound of the bounded-score softmax
 // (fgb_attn_fwd_bounded). One warp per row (grid-stride); a head is 16 consecutive lanes of one 16-byte vector index.
 // ---------------------------------------------------------------------------------------------
@@ -829,6 +923,39 @@ extern "C" int fgb_head_norm_max(fgb_ctx* ctx, const void* x, int64_t ldx, int32
   }
 #undef FGB_HNM_CASE
   FGB_LAUNCH_CHECK("head_norm_max_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t rows, int32_t dim, float eps, const void* wq, const void* wk,
+                               const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, int32_t token_offset, void* kmax2,
+                               void* stream) {
+  FGB_CHECK_ARG(ctx && qkv && wq && wk && kmax2, "fgb_qk_norm_rope: NULL argument");
+  FGB_CHECK_ARG(rows > 0 && dim > 0 && dim % 256 == 0 && ld >= 2 * static_cast<int64_t>(dim) && ld % 8 == 0, "fgb_qk_norm_rope: rows=%d dim=%d",
+                rows, dim);
+  FGB_CHECK_ARG(aligned16(qkv) && aligned16(wq) && aligned16(wk), "fgb_qk_norm_rope: operands must be 16-byte aligned");
+  if (rope_tab)
+    FGB_CHECK_ARG(gf > 0 && gh > 0 && gw > 0 && gf <= 1024 && gh <= 1024 && gw <= 1024 && token_offset >= 0,
+                  "fgb_qk_norm_rope: grid (%d,%d,%d) outside the RoPE table", gf, gh, gw);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FGB_CUDA(cudaMemsetAsync(kmax2, 0, sizeof(float) * (dim / 128), s));
+  int grid = (rows + kRowWarps - 1) / kRowWarps;
+  if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+  bf16* xp = static_cast<bf16*>(qkv);
+  const bf16* wqp = static_cast<const bf16*>(wq);
+  const bf16* wkp = static_cast<const bf16*>(wk);
+  const float2* tab = static_cast<const float2*>(rope_tab);
+  float* kp = static_cast<float*>(kmax2);
+#define FGB_QK_CASE(NV)                                                                                                            \
+  case NV:                                                                                                                         \
+    qk_norm_rope_kernel<NV><<<grid, kRowWarps * 32, 0, s>>>(xp, ld, rows, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp);         \
+    break;
+  switch (dim / 256) {
+    FGB_QK_CASE(1) FGB_QK_CASE(2) FGB_QK_CASE(3) FGB_QK_CASE(4) FGB_QK_CASE(6) FGB_QK_CASE(8) FGB_QK_CASE(12) FGB_QK_CASE(16) FGB_QK_CASE(20)
+    default:
+      return set_error(FGB_ERR_UNSUPPORTED, "fgb_qk_norm_rope: dim %d is not one of 256*{1,2,3,4,6,8,12,16,20}", dim);
+  }
+#undef FGB_QK_CASE
+  FGB_LAUNCH_CHECK("qk_norm_rope_kernel");
   return FGB_OK;
 }
 

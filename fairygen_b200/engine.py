@@ -295,12 +295,13 @@ class WanDiTEngine:
                 sp.attention(self, ws, qkv, o, S, norm=(cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0), qkv_gemm=qkv_rows, fused=fused)
             else:
                 k("gemm_qkv", ops.gemm, a, b.wqkv, b.bqkv, qkv)
-                k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)
-                k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, d:2 * d], cfg.eps, b.nk, self.rope_tab, grid, tok0)
                 if sp is None:
-                    k("head_norm_max", ops.head_norm_max, qkv[:, d:2 * d], ws["kmax2"], H)
+                    # q and k normalised + rotated and the key bound of the bounded softmax in one pass over the fused rows
+                    k("rmsnorm_rope", ops.qk_norm_rope, qkv, d, cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0, ws["kmax2"])
                     k("attn_self", ops.attention, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, H, kmax2=ws["kmax2"])
                 else:
+                    k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)
+                    k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, d:2 * d], cfg.eps, b.nk, self.rope_tab, grid, tok0)
                     sp.attention(self, ws, qkv, o, S)
             k("gemm_o", ops.gemm, o, b.wo, b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first)
             # cross-attention branch (DIT:226)

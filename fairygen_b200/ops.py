@@ -129,6 +129,18 @@ def attention_workspace(q_rows: int, kv_rows: int, heads: int, device) -> Option
     return ws
 
 
+def qk_norm_rope(qkv, dim: int, eps: float, wq, wk, rope_tab, grid, token_offset: int, kmax2):
+    """In place on columns [0, 2*dim) of the fused q|k|v rows: RMSNorm + weight + RoPE of q and of k (one pass), and
+    kmax2[h] = max over rows of ||k[row, h]||^2 (fp32 [dim/128])."""
+    ld = _rowmajor(qkv, "qkv")
+    if qkv.shape[1] < 2 * dim or kmax2.dtype != torch.float32 or kmax2.numel() != dim // 128 or not kmax2.is_contiguous():
+        raise ValueError(f"qk_norm_rope: qkv {tuple(qkv.shape)} dim {dim} kmax2 {tuple(kmax2.shape)}")
+    _vec(wq, dim, "wq")
+    _vec(wk, dim, "wk")
+    _lib.check(_lib.lib().fgb_qk_norm_rope(_h(qkv).handle, _p(qkv), ld, qkv.shape[0], dim, eps, _p(wq), _p(wk), _p(rope_tab), grid[0], grid[1],
+                                           grid[2], token_offset, _p(kmax2), _stream()), "fgb_qk_norm_rope")
+
+
 def head_norm_max(k, out_f32, heads: int):
     """out_f32[h] = max over rows of ||k[row, h*128:(h+1)*128]||^2 — the key bound of the bounded-score softmax."""
     ldk = _rowmajor(k, "k")

@@ -103,6 +103,10 @@ int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s_kv, int32_
  * B_i - m0 <= 220); a CTA where neither holds runs the running-max path of fgb_attn_fwd_ex. o_peers may be NULL (then `o` is used).
  * fgb_attn_set_stats registers an optional caller-owned device int32[3]; every CTA of a bounded launch adds 1 to
  * counts[mode] (0 = bound only, 1 = first-tile anchored, 2 = running-max fallback). NULL switches the counting off. */
+/* fgb_rmsnorm_rope on the q AND the k slice of fused q|k|v rows (columns [0, dim) and [dim, 2*dim) of qkv, row stride ld) plus
+ * fgb_head_norm_max of the finished k, in one pass: the single-GPU self-attention prologue (DIT:140-144). */
+int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t rows, int32_t dim, float eps, const void* wq, const void* wk,
+                     const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, int32_t token_offset, void* kmax2_f32, void* stream);
 int fgb_head_norm_max(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t rows, int32_t heads, void* out_f32, void* stream);
 int fgb_attn_set_stats(fgb_ctx* ctx, void* counts_dev_i32x3);
 int fgb_attn_fwd_bounded(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

@@ -84,6 +84,11 @@ def _emulated_ops(monkeypatch):
         out_f32.copy_(k.float().view(k.shape[0], heads, 128).pow(2).sum(-1).max(0).values)
         return out_f32
 
+    def qk_norm_rope(qkv, dim, eps, wq, wk, rope_tab, grid, token_offset, kmax2):
+        rmsnorm_rope(qkv[:, :dim], eps, wq, rope_tab, grid, token_offset)
+        rmsnorm_rope(qkv[:, dim:2 * dim], eps, wk, rope_tab, grid, token_offset)
+        head_norm_max(qkv[:, dim:2 * dim], kmax2, dim // 128)
+
     def attention(q, k, v, out, heads, scale=None, lse=None, kmax2=None):
         qf, kf, vf = (t.float().view(t.shape[0], heads, 128).transpose(0, 1) for t in (q, k, v))
         p = torch.softmax(qf @ kf.transpose(1, 2) / 128 ** 0.5, -1)

@@ -422,3 +422,26 @@ def test_attention_cta_pair_variant(env, monkeypatch):
         for out, lse, plain in outs:
             assert torch.isfinite(out.float()).all() and rel_l2(out, ref) < 6e-3 and rel_l2(plain, ref) < 8e-3
         assert rel_l2(outs[1][0], outs[0][0]) < 2e-3 and (outs[1][1] - outs[0][1]).abs().max() < 1e-2
+
+
+@pytest.mark.parametrize("rows,dim,grid,tok0", [(300, 3072, (3, 10, 14), 0), (77, 768, (2, 6, 10), 13), (1000, 256, (10, 10, 10), 0)])
+def test_qk_norm_rope_equals_the_three_separate_kernels(env, rows, dim, grid, tok0):
+    """fgb_qk_norm_rope (one pass over the fused q|k|v rows) == fgb_rmsnorm_rope(q), fgb_rmsnorm_rope(k), fgb_head_norm_max(k),
+    bit for bit on q and k, exactly on the key bound; v is not touched."""
+    ops, o = env
+    import numpy as np
+    heads = dim // 128
+    qkv = rnd(rows, 3 * dim, seed=3)
+    wq, wk = (1 + 0.1 * rnd(dim, seed=4).float()).to(BF), (1 + 0.1 * rnd(dim, seed=5).float()).to(BF)
+    tab = torch.from_numpy(np.ascontiguousarray(ops.rope_table(128))).cuda()
+    ref = qkv.clone()
+    ops.rmsnorm_rope(ref[:, :dim], 1e-6, wq, tab, grid, tok0)
+    ops.rmsnorm_rope(ref[:, dim:2 * dim], 1e-6, wk, tab, grid, tok0)
+    kref = torch.empty(heads, dtype=torch.float32, device="cuda")
+    ops.head_norm_max(ref[:, dim:2 * dim], kref, heads)
+    got = qkv.clone()
+    kmax = torch.full((heads,), -1.0, dtype=torch.float32, device="cuda")
+    ops.qk_norm_rope(got, dim, 1e-6, wq, wk, tab, grid, tok0, kmax)
+    ops.sync_check()
+    assert torch.equal(got, ref)
+    assert torch.allclose(kmax, kref, rtol=1e-6)
