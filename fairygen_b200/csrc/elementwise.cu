@@ -264,7 +264,10 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int rows, float
     float mx = 0.f;
 #pragma unroll
     for (int w = 0; w < kRowWarps; ++w) mx = fmaxf(mx, red[w][threadIdx.x]);
-    atomicMax(reinterpret_cast<unsigned int*>(kmax2) + threadIdx.x, __float_as_uint(mx));   // non-negative floats order like their bits
+    // the maximum only grows: after the first CTAs almost nobody exceeds it any more, so look before the atomic (a stale,
+    // lower value just costs one redundant atomic)
+    if (mx > __ldcg(kmax2 + threadIdx.x))
+      atomicMax(reinterpret_cast<unsigned int*>(kmax2) + threadIdx.x, __float_as_uint(mx));   // non-negative floats order like their bits
   }
 }
 
@@ -938,8 +941,7 @@ extern "C" int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t row
                   "fgb_qk_norm_rope: grid (%d,%d,%d) outside the RoPE table", gf, gh, gw);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   FGB_CUDA(cudaMemsetAsync(kmax2, 0, sizeof(float) * (dim / 128), s));
-  int grid = (rows + kRowWarps - 1) / kRowWarps;
-  if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+  const int grid = (rows + kRowWarps - 1) / kRowWarps;   // one row per warp: many short CTAs keep more loads in flight than a grid-stride loop
   bf16* xp = static_cast<bf16*>(qkv);
   const bf16* wqp = static_cast<const bf16*>(wq);
   const bf16* wkp = static_cast<const bf16*>(wk);

@@ -147,8 +147,8 @@ def test_adapter_fused_into_the_engine_survives_a_repack_and_cpu_dit_is_refused(
     ref_pipe, our_pipe = _pipes(fg, o, rl, seed=2)
     fg.install(our_pipe)
     cfg = fg.WanDiTConfig.from_module(our_pipe.dit)
-    lora_a = synthetic.random_lora(cfg, rank=8, seed=6, device="cuda")
-    lora_b = synthetic.random_lora(cfg, rank=8, seed=7, device="cuda")
+    lora_a = synthetic.random_lora(cfg, rank=16, seed=6, device="cuda")      # fgb_lora_merge: ranks 16 / 32 / 64
+    lora_b = synthetic.random_lora(cfg, rank=16, seed=7, device="cuda")
     eng = mf.engine_for(our_pipe.dit)
     lora_io.fuse_into_engine(eng, lora_a)                                      # directly on the packed weights
     our_pipe.load_lora(our_pipe.dit, state_dict=lora_b)                        # changes the container -> re-pack
@@ -160,7 +160,15 @@ def test_adapter_fused_into_the_engine_survives_a_repack_and_cpu_dit_is_refused(
     with torch.no_grad():
         want = ref_pipe.model_fn(dit=ref_pipe.dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
         got = our_pipe.model_fn(dit=our_pipe.dit, latents=lat, timestep=ts, context=cp, fuse_vae_embedding_in_latents=True)
-    assert rel_l2(got, want) < 1e-2 and len(mf.engine_for(our_pipe.dit).fused_adapters) == 1
+        # the same weights packed afresh with the adapter fused by hand: the re-packed engine must be bit-identical to it
+        fresh = fg.WanDiTEngine(cfg, "cuda")
+        fresh.load_state_dict(our_pipe.dit.state_dict())
+        lora_io.fuse_into_engine(fresh, lora_a)
+        expect = fresh.forward(lat, ts, cp, True)
+    assert len(mf.engine_for(our_pipe.dit).fused_adapters) == 1 and torch.equal(got, expect)
+    # against the reference the two adapters were rounded into the bf16 weights in a different order / precision (the
+    # reference: bf16 matmul + bf16 add per adapter; fgb_lora_merge: fp32 product, one rounding), hence the wider bound
+    assert rel_l2(got, want) < 3e-2
     # a DiT that still lives on the host (offload modes): install() defers, the first call explains
     w = o.make_weights(o.TINY, seed=3)
     cpu_dit = rl.build_wan_model(o.TINY, state_dict={k: v.to(BF) for k, v in w.items()})
