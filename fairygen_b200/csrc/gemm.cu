@@ -337,7 +337,10 @@ static int launch_gemm(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& t
 // group_m x band_n tiles so that a W band and an A group stay L2-resident while they are being reused.
 constexpr int kPairBM = 128;       // rows per CTA
 constexpr int kPairTM = 256;       // rows per cluster tile
-constexpr int kPairStages = 5;
+#ifndef FGB_PAIR_STAGES
+#define FGB_PAIR_STAGES 5
+#endif
+constexpr int kPairStages = FGB_PAIR_STAGES;
 constexpr int kPairABytes = kPairBM * kBK * 2;          // 16 KB
 constexpr int kPairBBytesMax = (256 / 2) * kBK * 2;     // 16 KB: this CTA's half of a 256-column W tile
 constexpr int kPairStageBytes = kPairABytes + kPairBBytesMax;
@@ -698,7 +701,9 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
   if (pair_enabled && k2 == 0 && m >= kPairTM && ctx->sm_count >= 2) {
     CUtensorMap tc;
     if ((rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kPairBM))) return rc;
-    // tile width: 256 columns unless half-width tiles shorten the last, partly filled wave by more than they cost (~4 %)
+    // tile width: 256 columns unless half-width tiles shorten the last, partly filled wave by more than they cost — a half-width
+    // tile runs at ~0.85 of the full-width rate per FLOP (profiles/r02_gemm_sweep3.log: 1105 vs 1281 TFLOP/s at 6820 rows), so
+    // this only pays for small problems (a handful of tiles); the Ulysses-rank shapes (324 tiles = 4.38 waves) stay at 256
     const int clusters = ctx->sm_count / 2;
     const int m_tiles = (m + kPairTM - 1) / kPairTM;
     const int waves256 = (m_tiles * ((n + 255) / 256) + clusters - 1) / clusters;
@@ -708,7 +713,7 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
       const char* e = getenv("FGB_GEMM_BN");
       env_bn = e ? atoi(e) : 0;
     }
-    const int bn = env_bn ? env_bn : ((0.5 * 1.04 * waves128 < waves256) ? 128 : 256);
+    const int bn = env_bn ? env_bn : ((0.5 * 1.3 * waves128 < waves256) ? 128 : 256);
     if ((rc = make_tmap_bf16_2d(ctx, &tb, w, n, k, ldw, bn / 2))) return rc;
     if ((rc = make_tmap_bf16_2d(ctx, &tc, c, m, n, ldc, 32))) return rc;
     PairParams pp;

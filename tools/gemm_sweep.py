@@ -10,7 +10,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from fairygen_b200 import ops  # noqa: E402
 
-S = 27280
+S = int(os.environ.get('ROWS', '27280'))
 shapes = {"qkv": (9216, 3072), "o": (3072, 3072), "ffn1": (14336, 3072), "ffn2": (3072, 14336)}
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(shapes)
 epi = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -37,4 +37,4 @@ for name in which:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     out.append(f"{name} {2.0 * S * n * k / ms / 1e9:.0f}")
-print(f"GM={os.environ.get('FGB_GEMM_GROUP_M', '-')} BN={os.environ.get('FGB_GEMM_BAND_N', '-')} epi={epi}: " + "  ".join(out))
+print(f"rows={S} GM={os.environ.get('FGB_GEMM_GROUP_M', '-')} BAND={os.environ.get('FGB_GEMM_BAND_N', '-')} BN={os.environ.get('FGB_GEMM_BN', '-')} lib={os.path.basename(os.environ.get('FGB_LIB_PATH', 'intree'))} epi={epi}: " + "  ".join(out))
