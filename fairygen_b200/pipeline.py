@@ -25,6 +25,22 @@ class WanDenoiser:
         self.cfg_group = cfg_group  # fairygen_b200.cfg_parallel.CfgParallel or None
         # timesteps as the model sees them: rounded to the pipeline dtype (bf16) at PIPE:293
         self.model_timesteps = self.scheduler.timesteps.to(torch.bfloat16).to(torch.float32)
+        self._host_contexts = []   # [(host copy, device tensor)]: prompt embeddings handed over as HOST tensors
+
+    def _context_on_device(self, context: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """Prompt embeddings are per-video constants (PIPE:404-417 computes them once, before the loop). A caller that hands
+        them over as host tensors on every step gets them uploaded once: the check is a 4 MB compare on the HOST (no device
+        synchronisation, no H2D traffic), and the same device tensor object goes to the engine, whose cross-attention K/V
+        cache then hits by identity."""
+        if context is None or context.device.type != "cpu":
+            return context
+        for host, dev in self._host_contexts:
+            if host.shape == context.shape and host.dtype == context.dtype and torch.equal(host, context):
+                return dev
+        dev = context.to(device=self.engine.device, dtype=torch.bfloat16, non_blocking=True)
+        self._host_contexts.append((context.detach().clone(), dev))
+        del self._host_contexts[:-4]
+        return dev
 
     @property
     def num_steps(self) -> int:
@@ -36,6 +52,7 @@ class WanDenoiser:
         """One denoising step, in place on ``latents`` (1,C,F,H,W) bf16 on the engine's device."""
         ts = self.model_timesteps[index:index + 1]
         fuse = first_frame_latents is not None
+        context_pos, context_neg = self._context_on_device(context_pos), self._context_on_device(context_neg)
         if self.cfg_group is not None and self.cfg_scale != 1.0:
             npos, nneg = self.cfg_group.forward_pair(self.engine, latents, ts, context_pos, context_neg, fuse)
         else:
