@@ -40,19 +40,21 @@ namespace fgb {
 template <int EMU, bool PAIR>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, const AttnParams p) {
   constexpr int kEmu = EMU;
   constexpr int kFrac = (EMU == 9) ? 3 : EMU;   // pairs of every 8 that take the FMA-pipe exp2
   constexpr int kStages = PAIR ? 4 : 2;                       // K / V ring depth
   constexpr int kKVBytes = PAIR ? kTileBytes / 2 : kTileBytes;   // bytes of one K (or V) stage in THIS CTA
   constexpr int kKBox = PAIR ? kBoxBytes / 2 : kBoxBytes;        // one K box: 64 (pair) or 128 key rows of 128 B
   constexpr int kItemTiles = PAIR ? 4 : 2;                       // 128-row query tiles per work item
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (smem - smem_raw > kAttnAlignSlack) __trap();          // the slack left below the 227 KB limit must cover the round-up
   uint8_t* smem_q = smem;                                   // [2 tiles][2 boxes][128][64]
   uint8_t* smem_k = smem + 2 * kTileBytes;                  // [stages][2 boxes][128 or 64][64]
   uint8_t* smem_v = smem_k + kStages * kKVBytes;            // [stages][2 boxes][128][64] or [stages][128][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + kStages * kKVBytes);
+  uint8_t* smem_o = smem_v + kStages * kKVBytes;            // [2 boxes][128][64]: one finished output tile on its way to a TMA store
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + kTileBytes);
   uint64_t* q_full = bars;          // [1] this CTA's Q tiles landed
   uint64_t* q_empty = bars + 1;     // [1] the item's last score MMAs have read Q: the next item's Q may land
   uint64_t* q_pair = bars + 2;      // [1] PAIR, leader: the peer's Q tiles landed (remote arrive)
@@ -100,6 +102,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     mbar_init(q_pair, 1);
@@ -569,13 +572,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // final normalisation: O / l -> bf16 -> global (or the owning peer's buffer)
         const float inv_l = 1.0f / l_row;
         if (wg == 0 && p.lse != nullptr && row < p.ld_lse) p.lse[static_cast<int64_t>(head) * p.ld_lse + row] = m[i] + __log2f(l_row);
-        __nv_bfloat16* orow = row < p.s_q ? out_row(p, row, head) + wg * 64 : nullptr;
+        if (p.tma_out) {
+          // stage the tile in shared memory (128-byte swizzle: chunk ^ (row & 7), conflict-free for one row per lane) and let
+          // the TMA write full 128-byte lines: a per-thread store of 16 bytes per row touched 32 lines per warp instruction
+          // and held the warps for ~2.8 us per work item (profiles/r02_ncu_attn_cross_before_tma_store.txt)
+          if (threadIdx.x == 0) tma_store_wait_read<0>();          // the previous tile's store has read the buffer
+          asm volatile("bar.sync 9, 256;" ::: "memory");
+          uint8_t* srow = smem_o + wg * kBoxBytes + r_local * 128;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t orr[32];
-          tmem_ld32(t_o + c * 32, orr);
-          tmem_ld_wait();
-          if (row < p.s_q) {
+          for (int c = 0; c < 2; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(t_o + c * 32, orr);
+            tmem_ld_wait();
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 o;
@@ -583,7 +591,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               o.y = pack_bf16(__uint_as_float(orr[g * 8 + 2]) * inv_l, __uint_as_float(orr[g * 8 + 3]) * inv_l);
               o.z = pack_bf16(__uint_as_float(orr[g * 8 + 4]) * inv_l, __uint_as_float(orr[g * 8 + 5]) * inv_l);
               o.w = pack_bf16(__uint_as_float(orr[g * 8 + 6]) * inv_l, __uint_as_float(orr[g * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+              *reinterpret_cast<uint4*>(srow + (((c * 4 + g) ^ (r_local & 7)) << 4)) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 9, 256;" ::: "memory");
+          if (threadIdx.x == 0) {
+            tma_store_2d(&tmap_o, smem_o, head * 128, q0 + i * kTile);                    // rows >= s_q are clipped by the tensor map
+            tma_store_2d(&tmap_o, smem_o + kBoxBytes, head * 128 + 64, q0 + i * kTile);
+            tma_store_commit();
+          }
+        } else {
+          __nv_bfloat16* orow = row < p.s_q ? out_row(p, row, head) + wg * 64 : nullptr;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(t_o + c * 32, orr);
+            tmem_ld_wait();
+            if (row < p.s_q) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 o;
+                o.x = pack_bf16(__uint_as_float(orr[g * 8 + 0]) * inv_l, __uint_as_float(orr[g * 8 + 1]) * inv_l);
+                o.y = pack_bf16(__uint_as_float(orr[g * 8 + 2]) * inv_l, __uint_as_float(orr[g * 8 + 3]) * inv_l);
+                o.z = pack_bf16(__uint_as_float(orr[g * 8 + 4]) * inv_l, __uint_as_float(orr[g * 8 + 5]) * inv_l);
+                o.w = pack_bf16(__uint_as_float(orr[g * 8 + 6]) * inv_l, __uint_as_float(orr[g * 8 + 7]) * inv_l);
+                *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+              }
             }
           }
         }
@@ -591,6 +625,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     g0 += n_kv;
     }   // items
+    if (threadIdx.x == 0) tma_store_wait<0>();
   }
 
   __syncwarp();   // the single-thread roles rejoin their warps before the (aligned) barrier
@@ -642,7 +677,7 @@ attn_combine_kernel(const AttnParams p, int n_split_units) {
 
 template <int EMU, bool PAIR>
 static int launch_attn(int grid, cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                       const AttnParams& p) {
+                       const CUtensorMap& to, const AttnParams& p) {
   auto kfn = attn_fwd_kernel<EMU, PAIR>;
   static unsigned long long configured = 0;  // per template instance and device
   if (first_use_on_device(configured)) {
@@ -661,9 +696,9 @@ static int launch_attn(int grid, cudaStream_t stream, const CUtensorMap& tq, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FGB_CUDA(cudaLaunchKernelEx(&cfg, kfn, tq, tk, tv, p));
+    FGB_CUDA(cudaLaunchKernelEx(&cfg, kfn, tq, tk, tv, to, p));
   } else {
-    kfn<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, p);
+    kfn<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tk, tv, to, p);
   }
   FGB_LAUNCH_CHECK("attn_fwd_kernel");
   return FGB_OK;
@@ -747,6 +782,10 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   if (rc) return rc;
   rc = make_tmap_bf16_2d(ctx, &tv, v, s_kv, width, ldv, kTile);
   if (rc) return rc;
+  CUtensorMap to = tq;
+  if (!o_peers) {
+    if ((rc = make_tmap_bf16_2d(ctx, &to, o, s_q, width, ldo, kTile))) return rc;
+  }
 
   AttnParams p;
   p.o = static_cast<__nv_bfloat16*>(o);
@@ -756,6 +795,7 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = static_cast<float*>(lse);
   p.ld_lse = ld_lse;
+  p.tma_out = o_peers ? 0 : 1;
   p.kmax = static_cast<const float*>(kmax);
   p.stats = kmax ? ctx->attn_stats : nullptr;
   p.rows_per_peer = o_peers ? rows_per_peer : 0;
@@ -792,13 +832,13 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define FGB_ATTN_CASE(E)                                                                                  \
   case E:                                                                                                 \
-    rc = pair ? launch_attn<E, true>(grid, st, tq, tk, tv, p) : launch_attn<E, false>(grid, st, tq, tk, tv, p); \
+    rc = pair ? launch_attn<E, true>(grid, st, tq, tk, tv, to, p) : launch_attn<E, false>(grid, st, tq, tk, tv, to, p); \
     break;
   switch (emu) {
     FGB_ATTN_CASE(0) FGB_ATTN_CASE(1) FGB_ATTN_CASE(2) FGB_ATTN_CASE(3) FGB_ATTN_CASE(4) FGB_ATTN_CASE(5) FGB_ATTN_CASE(6)
     FGB_ATTN_CASE(7) FGB_ATTN_CASE(8)
     default:
-      rc = pair ? launch_attn<9, true>(grid, st, tq, tk, tv, p) : launch_attn<9, false>(grid, st, tq, tk, tv, p);
+      rc = pair ? launch_attn<9, true>(grid, st, tq, tk, tv, to, p) : launch_attn<9, false>(grid, st, tq, tk, tv, to, p);
       break;
   }
 #undef FGB_ATTN_CASE

@@ -12,8 +12,13 @@ constexpr int kTile = 128;                  // query rows per tile == keys per K
 constexpr int kBoxBytes = kTile * 64 * 2;   // one TMA box: 128 rows x 64 bf16 = 16 KB
 constexpr int kTileBytes = 2 * kBoxBytes;   // 128 x 128 bf16 = 32 KB (two 64-column boxes)
 constexpr int kKVStages = 2;
-constexpr int kAttnSmem = 2 * kTileBytes /*Q*/ + 2 * kKVStages * kTileBytes /*K,V*/ + 1024 /*align*/ + 256 /*barriers*/ +
+// Q + K/V rings + one 128 x 128 bf16 staging tile for the TMA-store epilogue + barriers + row exchange = 231 680 bytes; the
+// remaining 768 bytes up to the 227 KB limit are the alignment slack (the dynamic segment is declared 1024-byte aligned and
+// the kernel traps if the slack would not do).
+constexpr int kAttnAlignSlack = 768;
+constexpr int kAttnSmem = 2 * kTileBytes /*Q*/ + 2 * kKVStages * kTileBytes /*K,V*/ + kTileBytes /*O staging*/ + kAttnAlignSlack + 256 /*barriers*/ +
                           2 * 2 * kTile * 4 /*row-max exchange*/;
+static_assert(kAttnSmem <= 232448, "attention kernel shared memory exceeds 227 KB");
 
 struct AttnParams {
   __nv_bfloat16* o;
@@ -45,6 +50,7 @@ struct AttnParams {
   //   mode 2: a CTA with a row that fails both runs the running-max path. stats (optional, int32[3]) counts CTAs per mode.
   const float* kmax;
   int32_t* stats;
+  int32_t tma_out;   // 1: `o` is written through the output tensor map (staged tiles, full lines); 0: per-row stores (peers / partials)
 };
 
 constexpr float kBoundDirect = 60.0f;     // B <= this: R = B
