@@ -31,6 +31,8 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 HEIGHT, WIDTH, FRAMES = 704, 1280, 121
+if os.environ.get("FGB_BENCH_SHAPE"):   # experiment hook (e.g. 352x1280x121 at 2 GPUs = the per-rank GEMM shapes of SP4); the line says so
+    HEIGHT, WIDTH, FRAMES = (int(v) for v in os.environ["FGB_BENCH_SHAPE"].split("x"))
 PARITY_SHAPE = (480, 832, 81)   # ragged under SP 4 / 8: S = 8190
 NUM_INFERENCE_STEPS, CFG_SCALE, SIGMA_SHIFT, TEXT_LEN, LORA_RANK = 50, 5.0, 5.0, 512, 32
 METRIC, UNIT = "dit_denoise_steps_per_s", "steps/s"
@@ -77,7 +79,7 @@ def workload_config(n_gpus, layout=None):
     return {
         "workload": "Wan2.2-TI2V-5B denoise step, 704x1280x121 (latent 1x48x31x44x80, S=27280 video tokens, 512 text tokens), "
                     "bf16, CFG on (2 DiT forwards/step, cfg_scale 5), merged rank-32 motion LoRA, 50-step flow-match schedule (shift 5)",
-        "tokens": 27280, "text_tokens": TEXT_LEN, "layers": 30, "parallelism": layout or ("single_gpu" if n_gpus == 1 else f"{n_gpus}_gpus"),
+        "tokens": headline_tokens(), "shape_override": os.environ.get("FGB_BENCH_SHAPE"), "text_tokens": TEXT_LEN, "layers": 30, "parallelism": layout or ("single_gpu" if n_gpus == 1 else f"{n_gpus}_gpus"),
         "l2_policy": "working set per step (10 GB weights + 2 GB activations) >> 126 MB L2; no explicit flush needed",
     }
 
@@ -380,6 +382,11 @@ def run_ours(args):
     launches = engine.kernel_launches + args.steps  # + one fused scheduler kernel per step
     kernels = timer.summary()
     engine.timer = None
+    rank_kernels = None
+    if world > 1 and os.environ.get("FGB_BENCH_RANK_KERNELS"):     # diagnostic: every rank's per-kernel ms/step (rank 0's is the line's)
+        mine = {k: round(v["total_ms"] / args.steps, 3) for k, v in kernels.items()}
+        rank_kernels = [None] * world
+        dist.all_gather_object(rank_kernels, mine)
     fast, fell = ops.attention_stats(dev)
     steps_per_s = 1e3 / ms_per_step
 
@@ -479,6 +486,8 @@ def run_ours(args):
         "attn_fallback_frac": (fell / (fast + fell)) if (fast + fell) else None,
         "attn_ctas": {"fast_path": fast, "fallback": fell, "qk_norm_scale": args.qk_norm_scale},
     }
+    if rank_kernels is not None:
+        line["kernel_ms_per_step_by_rank"] = rank_kernels
     if layouts is not None:
         line["layouts"] = layouts
     if parity is not None:

@@ -366,6 +366,24 @@ struct PairParams {
   // receiver's RMSNorm needs the statistics of the FULL row, which no single rank holds after the head split.
   float* rowsq;
   int32_t dim, hpr;
+  // Stream-K tail (fgb_gemm_bf16_sk; sk_tiles > 0): tiles [0, dp_tiles) are handed out whole, one per cluster and wave
+  // (dp_tiles is a multiple of the cluster count); the K-blocks of the last sk_tiles tiles — what would be a partly filled
+  // last wave — are cut into units of kSkUnit K-blocks and spread evenly over the first sk_clusters clusters, so that wave
+  // takes sk_tiles / sk_clusters of a tile time instead of a whole one. The cluster whose range starts a tile owns it; the
+  // others dump their fp32 partial accumulators into sk_partial (one slot per cluster) and raise a flag per epilogue warp.
+  int32_t dp_tiles, sk_tiles, sk_clusters, sk_upt;   // sk_upt = units per tile
+  float* sk_partial;
+  int32_t* sk_flags;
+};
+
+constexpr int kSkUnit = 4;           // K-blocks per stream-K unit (256 elements of K)
+constexpr int kSkMaxSplit = 4;       // at most this many clusters per tail tile (bounds the owner's reduction)
+
+struct PairItem {
+  int32_t tile, kb0, kb1;
+  int32_t role;        // 0 = whole tile or owner of a split tile (normal epilogue), 1 = contributor (partial dump)
+  int32_t unit_end;    // owner: first unit after its own range; tile_end: first unit after the tile — the contributors are the
+  int32_t tile_end;    // clusters after this one whose unit ranges start before tile_end
 };
 
 struct PeerMaps {
@@ -387,6 +405,54 @@ __device__ __forceinline__ void pair_tile_coords(const PairParams& p, int tile, 
   nt = n0 + in_group / gm;
 }
 
+__device__ __forceinline__ int sk_range_begin(const PairParams& p, int c) {
+  return static_cast<int>(static_cast<int64_t>(c) * (p.sk_tiles * p.sk_upt) / p.sk_clusters);
+}
+
+// The it-th work item of `cluster` (all three roles of a CTA walk the same list): whole tiles first, then at most two
+// stream-K segments — the end of one tail tile (contributor, or owner if the range starts on the tile boundary) and the
+// beginning of the next (owner).
+__device__ __forceinline__ bool pair_next_item(const PairParams& p, int cluster, int n_clusters, int it, PairItem& w) {
+  const int tile = cluster + it * n_clusters;
+  if (tile < p.dp_tiles) {
+    w.tile = tile;
+    w.kb0 = 0;
+    w.kb1 = p.k_blocks;
+    w.role = 0;
+    w.unit_end = w.tile_end = 0;
+    return true;
+  }
+  if (p.sk_tiles == 0 || cluster >= p.sk_clusters) return false;
+  const int seg = it - p.dp_tiles / n_clusters;
+  if (seg > 1) return false;
+  const int u0 = sk_range_begin(p, cluster), u1 = sk_range_begin(p, cluster + 1);
+  if (u0 == u1) return false;
+  int j = u0 / p.sk_upt;
+  int first = u0, last = min(u1, (j + 1) * p.sk_upt);
+  if (seg == 1) {
+    if (u1 <= (j + 1) * p.sk_upt) return false;
+    ++j;
+    first = j * p.sk_upt;
+    last = u1;
+  }
+  w.tile = p.dp_tiles + j;
+  w.kb0 = (first - j * p.sk_upt) * kSkUnit;
+  w.kb1 = min((last - j * p.sk_upt) * kSkUnit, p.k_blocks);
+  w.role = first == j * p.sk_upt ? 0 : 1;
+  w.unit_end = last;
+  w.tile_end = (j + 1) * p.sk_upt;
+  return true;
+}
+
+__device__ __forceinline__ void st_release_gpu(int32_t* p, int32_t v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // BN = 256: the default. BN = 128: half-width tiles for problems whose 256-wide tile count leaves most of the last wave idle
 // (e.g. N = 3072 on the 6820 rows of a Ulysses SP4 rank: 324 tiles = 4.38 waves of 74 clusters; 648 half tiles = 8.76).
 template <int EPI, int BN, bool SCATTER>
@@ -406,6 +472,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_full = bars + 2 * kPairStages;        // [2]       MMA -> epilogue, multicast to both CTAs
   uint64_t* tmem_empty = bars + 2 * kPairStages + 2;   // [2]       epilogue warps of both CTAs -> MMA; used in the leader
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+  uint64_t* sk_bar = bars + 2 * kPairStages + 6;       // [4 warps][2]  stream-K landing slots of the epilogue warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -425,6 +492,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8);
     }
+    for (int a = 0; a < 8; ++a) mbar_init(&sk_bar[a], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
@@ -442,12 +510,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader[s]) : "r"(smem_u32(&full[s])));
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster; tile < p.tiles; tile += n_clusters) {
+      PairItem w;
+      for (int it = 0; pair_next_item(p, cluster, n_clusters, it, w); ++it) {
         int mt, nt;
-        pair_tile_coords(p, tile, mt, nt);
+        pair_tile_coords(p, w.tile, mt, nt);
         const int row_a = mt * kPairTM + static_cast<int>(rank) * kPairBM;
         const int row_b = nt * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait_cluster(&empty[stage], phase ^ 1);
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * (kPairABytes + kPairBBytes));   // both CTAs' bytes land on the leader's barrier
           uint32_t fl = full_leader[0];
@@ -467,14 +536,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint64_t b_desc0 = make_sdesc_sw128(smem_u32(smem_b), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
-      int local = 0;
-      for (int tile = cluster; tile < p.tiles; tile += n_clusters, ++local) {
+      PairItem w;
+      for (int local = 0; pair_next_item(p, cluster, n_clusters, local, w); ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kPairBN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait_cluster(&full[stage], phase);
           tc_fence_after();
           const uint64_t adesc = a_desc0 + static_cast<uint64_t>((stage * kPairABytes) >> 4);
@@ -482,7 +551,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
             umma_ss_2sm(tmem_d, adesc + static_cast<uint64_t>((k * 32) >> 4), bdesc + static_cast<uint64_t>((k * 32) >> 4), idesc,
-                        (kb | k) != 0);
+                        ((kb - w.kb0) | k) != 0);
           tc_commit_2sm(&empty[stage], 0x3);     // the slot is reusable in BOTH CTAs once these MMAs have read it
           if (++stage == kPairStages) { stage = 0; phase ^= 1; }
         }
@@ -494,22 +563,127 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are visible to this warp
     uint8_t* stage_buf = smem_st + quarter * (2 * kPairStoreBytes);
     int buf = 0;
-    int local = 0;
     constexpr bool kReadsC = (EPI == FGB_EPI_GATED_RESIDUAL || EPI == FGB_EPI_RESIDUAL);
-    for (int tile = cluster; tile < p.tiles; tile += n_clusters, ++local) {
+    // stream-K: this warp's [32 rows x BN] fp32 block inside a cluster's partial slot, as float4 [BN/32][8][32 lanes] (a warp
+    // instruction moves 512 contiguous bytes; the owner's same-position thread reads back exactly what was written)
+    constexpr int kSkWarpVec = (kPairBN / 32) * 8 * 32;               // float4 per warp block
+    constexpr int kSkSlotVec = 8 * kSkWarpVec;                        // 2 CTAs x 4 warps
+    const int sk_warp = static_cast<int>(rank) * 4 + quarter;
+    PairItem w;
+    for (int local = 0; pair_next_item(p, cluster, n_clusters, local, w); ++local) {
       int mt, nt;
-      pair_tile_coords(p, tile, mt, nt);
+      pair_tile_coords(p, w.tile, mt, nt);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait_cluster(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kPairBN;
+      if (w.role == 1) {
+        // contributor: fp32 partial accumulators -> this cluster's slot, then the flag of this warp (release)
+        float4* dst = reinterpret_cast<float4*>(p.sk_partial) + static_cast<int64_t>(cluster) * kSkSlotVec + sk_warp * kSkWarpVec + lane;
+#pragma unroll 1
+        for (int c32 = 0; c32 < kPairBN / 32; ++c32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c32 * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(dst + (c32 * 8 + j) * 32, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        }
+        tc_fence_before();
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(&tmem_empty[acc], 0);
+          st_release_gpu(p.sk_flags + cluster * 8 + sk_warp, 1);
+        }
+        continue;
+      }
+      // owner of a split tile: add the contributors' partials (the clusters after this one whose unit ranges begin inside the
+      // tile) into the accumulator before the normal epilogue. A split tile is always the LAST item of its owner, so the operand
+      // ring is idle by now (every stage consumed: tmem_full fired) and serves as the landing zone: each warp pulls its
+      // 32 x BN fp32 block of one contributor in two bulk copies (the copy engine keeps tens of KB in flight per warp, where
+      // per-thread loads would pay one L2 round trip per 32 columns), double-buffered across (contributor, half).
+      const bool split = w.tile_end > w.unit_end;
+      if (split) {
+        constexpr int kHalfBytes = kSkWarpVec * 16 / 2;
+        uint8_t* land = smem + quarter * (2 * kHalfBytes);        // 4 warps x 2 x 16 KB (BN = 256) inside the 160 KB ring
+        uint64_t* lbar = sk_bar + quarter * 2;
+        auto next_contributor = [&](int c) {
+          for (++c; c < p.sk_clusters; ++c) {
+            const int b = sk_range_begin(p, c);
+            if (b >= w.tile_end) return -1;
+            if (sk_range_begin(p, c + 1) != b) return c;
+          }
+          return -1;
+        };
+        auto issue = [&](int c, int half, int slot) {           // lane 0 only
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.sk_partial) +
+                               (static_cast<int64_t>(c) * kSkSlotVec + sk_warp * kSkWarpVec) * 16 + half * kHalfBytes;
+          mbar_expect_tx(&lbar[slot], kHalfBytes);
+          bulk_load(land + slot * kHalfBytes, src, kHalfBytes, &lbar[slot]);
+        };
+        auto wait_flag = [&](int c) {
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(p.sk_flags + c * 8 + sk_warp) == 0) {
+            if (++spins > FGB_SPIN_LIMIT) __trap();
+          }
+          fence_proxy_async_all();    // the partials were written through the generic proxy; the bulk copy reads through the async proxy
+        };
+        int c_issue = next_contributor(cluster), h_issue = 0, n_issued = 0, n_done = 0;
+        int c_cur = c_issue;
+        if (lane == 0) {
+          wait_flag(c_issue);
+          issue(c_issue, 0, 0);
+          issue(c_issue, 1, 1);
+        }
+        n_issued = 2;
+        c_issue = next_contributor(c_issue);
+        while (c_cur >= 0) {
+          for (int half = 0; half < 2; ++half, ++n_done) {
+            const int slot = n_done & 1;
+            mbar_wait(&lbar[slot], (n_done >> 1) & 1);
+            const float4* src = reinterpret_cast<const float4*>(land + slot * kHalfBytes) + lane;
+#pragma unroll 1
+            for (int cc = 0; cc < kPairBN / 64; ++cc) {
+              const int c32 = half * (kPairBN / 64) + cc;
+              uint32_t r[32];
+              tmem_ld32(taddr + c32 * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 v = src[(cc * 8 + j) * 32];
+                r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
+                r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
+                r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
+                r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+              }
+              tmem_st32(taddr + c32 * 32, r);
+            }
+            tmem_st_wait();
+            __syncwarp();                 // every lane is done with this landing slot
+            if (c_issue >= 0 && lane == 0) {
+              if (h_issue == 0) wait_flag(c_issue);
+              issue(c_issue, h_issue, slot);
+            }
+            if (c_issue >= 0) {
+              ++n_issued;
+              if (++h_issue == 2) {
+                h_issue = 0;
+                c_issue = next_contributor(c_issue);
+              }
+            }
+          }
+          c_cur = next_contributor(c_cur);
+        }
+      }
       const int row0 = mt * kPairTM + static_cast<int>(rank) * kPairBM + quarter * 32;   // first row of this warp's block
       const int row = row0 + lane;
       const bool row_ok = row < p.m;
       const __nv_bfloat16* crow = p.c + static_cast<int64_t>(row) * p.ldc;
       const __nv_bfloat16* gate = nullptr;
       if (EPI == FGB_EPI_GATED_RESIDUAL) gate = (row < p.rows_gate0) ? p.gate0 : p.gate1;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kPairBN;
       uint4 xcur[4], xnext[4];
       auto load_c = [&](int c32, uint4 (&dst)[4]) {
 #pragma unroll
@@ -612,7 +786,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // this warp has read its part of the accumulator: one arrival per warp on the leader's barrier
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+      if (lane == 0) {
+        mbar_arrive_cluster(&tmem_empty[acc], 0);
+        if (split) {   // the partials are consumed: lower the flags for the next launch that uses this workspace
+          for (int c = cluster + 1; c < p.sk_clusters; ++c) {
+            const int b = sk_range_begin(p, c);
+            if (b >= w.tile_end) break;
+            if (sk_range_begin(p, c + 1) == b) continue;
+            p.sk_flags[c * 8 + sk_warp] = 0;
+          }
+        }
+      }
     }
     if (lane == 0) tma_store_wait<0>();
   }
@@ -636,7 +820,7 @@ static int launch_gemm_pair(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorM
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
   }
   int clusters = ctx->sm_count / 2;
-  if (p.tiles < clusters) clusters = p.tiles;
+  if (p.sk_tiles == 0 && p.tiles < clusters) clusters = p.tiles;   // the stream-K ranges are cut for the full cluster count
   kfn<<<2 * clusters, kPairThreads, kPairSmem, stream>>>(ta, tb, tc, pm ? *pm : no_peers, p);
   FGB_LAUNCH_CHECK("gemm_pair_kernel");
   return FGB_OK;
@@ -663,7 +847,70 @@ static void pair_supertile(int m_tiles, int n_tiles, int k, int* group_m, int* b
   *band_n = env_bn > 0 ? env_bn : bn;
 }
 
+// Stream-K workspace: [flags: one int32 per (cluster, epilogue warp), padded to 4 KB][one fp32 256 x 256 slot per cluster].
+constexpr int64_t kSkFlagBytes = 4096;
+constexpr int64_t kSkSlotBytes = 256 * 256 * 4;
+static int64_t sk_workspace_bytes(const fgb_ctx* ctx) { return kSkFlagBytes + static_cast<int64_t>(ctx->sm_count / 2) * kSkSlotBytes; }
+
+// Decides whether the last, partly filled wave of a 2-CTA GEMM is cut along K (see PairParams). FGB_GEMM_SK=0 switches it off;
+// FGB_GEMM_SK_MAXFRAC (default 0.9): a tail that fills more than this fraction of the clusters stays whole (nothing to gain);
+// FGB_GEMM_SK_MIN_KB (default 96 K-blocks = K >= 6144): the fix-up (partial dump, flag, bulk pull, accumulate) costs ~15 us, and
+// under the power cap a partly filled wave runs at a higher clock than a full one, so a split only pays when a tile is long —
+// measured on the step's shapes at 6820 rows (profiles/r02_streamk_ab.log): FFN2 (K = 14 336) 13.85 -> 12.92 ms per 30
+// launches, the K = 3072 projections 3.59 -> 3.96 ms.
+static void pair_plan_streamk(fgb_ctx* ctx, PairParams& pp, void* ws, int64_t ws_bytes) {
+  pp.dp_tiles = pp.tiles;
+  pp.sk_tiles = pp.sk_clusters = 0;
+  pp.sk_upt = 1;
+  pp.sk_partial = nullptr;
+  pp.sk_flags = nullptr;
+  if (ctx->sk_min_kblocks < 0) {      // first use: defaults, overridable from the environment (A/B runs) or fgb_gemm_streamk_tune
+    const char* e = getenv("FGB_GEMM_SK_MAXFRAC");
+    ctx->sk_max_frac = e ? atof(e) : 0.9;
+    e = getenv("FGB_GEMM_SK_MIN_KB");
+    ctx->sk_min_kblocks = e ? atoi(e) : 96;
+    e = getenv("FGB_GEMM_SK");
+    ctx->sk_enabled = e ? atoi(e) : 1;
+  }
+  const int enabled = ctx->sk_enabled, min_kb = ctx->sk_min_kblocks;
+  const double max_frac = ctx->sk_max_frac;
+  const int clusters = ctx->sm_count / 2;
+  if (!enabled || !ws || ws_bytes < sk_workspace_bytes(ctx) || clusters * 8 * 4 > kSkFlagBytes) return;
+  const int tail = pp.tiles % clusters;
+  if (tail == 0 || tail > max_frac * clusters || pp.k_blocks < 2 * kSkUnit || pp.k_blocks < min_kb) return;
+  pp.dp_tiles = pp.tiles - tail;
+  pp.sk_tiles = tail;
+  pp.sk_upt = (pp.k_blocks + kSkUnit - 1) / kSkUnit;
+  pp.sk_clusters = clusters < kSkMaxSplit * tail ? clusters : kSkMaxSplit * tail;
+  pp.sk_flags = static_cast<int32_t*>(ws);
+  pp.sk_partial = reinterpret_cast<float*>(static_cast<char*>(ws) + kSkFlagBytes);
+}
+
+static int gemm_impl(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c, int64_t ldc,
+                     int32_t m, int32_t n, int32_t k, int32_t epilogue, const void* gate0, const void* gate1, int32_t rows_gate0,
+                     const void* a2, int64_t lda2, const void* w2, int64_t ldw2, int32_t k2, void* sk_ws, int64_t sk_ws_bytes,
+                     void* stream);
+
 }  // namespace fgb
+
+extern "C" int64_t fgb_gemm_workspace_bytes(fgb_ctx* ctx) { return ctx ? fgb::sk_workspace_bytes(ctx) : 0; }
+
+extern "C" int fgb_gemm_streamk_tune(fgb_ctx* ctx, int32_t min_k, double max_tail_frac) {
+  FGB_CHECK_ARG(ctx && min_k >= 0 && max_tail_frac >= 0.0 && max_tail_frac <= 1.0, "fgb_gemm_streamk_tune: bad argument");
+  const char* e = getenv("FGB_GEMM_SK");
+  ctx->sk_enabled = e ? atoi(e) : 1;
+  ctx->sk_min_kblocks = (min_k + fgb::kBK - 1) / fgb::kBK;
+  ctx->sk_max_frac = max_tail_frac;
+  return FGB_OK;
+}
+
+extern "C" int fgb_gemm_bf16_sk(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c,
+                                int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue, const void* gate0, const void* gate1,
+                                int32_t rows_gate0, void* workspace, int64_t workspace_bytes, void* stream) {
+  FGB_CHECK_ARG(!workspace || fgb::aligned16(workspace), "fgb_gemm_bf16_sk: workspace must be 16-byte aligned");
+  return fgb::gemm_impl(ctx, a, lda, w, ldw, bias, c, ldc, m, n, k, epilogue, gate0, gate1, rows_gate0, nullptr, 0, nullptr, 0, 0,
+                        workspace, workspace_bytes, stream);
+}
 
 extern "C" int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias,
                              void* c, int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue,
@@ -676,6 +923,14 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
                                 void* c, int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue, const void* gate0,
                                 const void* gate1, int32_t rows_gate0, const void* a2, int64_t lda2, const void* w2,
                                 int64_t ldw2, int32_t k2, void* stream) {
+  return fgb::gemm_impl(ctx, a, lda, w, ldw, bias, c, ldc, m, n, k, epilogue, gate0, gate1, rows_gate0, a2, lda2, w2, ldw2, k2, nullptr, 0,
+                        stream);
+}
+
+static int fgb::gemm_impl(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c, int64_t ldc,
+                          int32_t m, int32_t n, int32_t k, int32_t epilogue, const void* gate0, const void* gate1, int32_t rows_gate0,
+                          const void* a2, int64_t lda2, const void* w2, int64_t ldw2, int32_t k2, void* sk_ws, int64_t sk_ws_bytes,
+                          void* stream) {
   using namespace fgb;
   FGB_CHECK_ARG(ctx, "fgb_gemm_bf16: ctx is NULL");
   FGB_CHECK_ARG(a && w && c, "fgb_gemm_bf16: NULL matrix pointer");
@@ -733,6 +988,7 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
     pp.k_blocks = (k + kBK - 1) / kBK;
     pair_supertile(pp.m_tiles, (pp.n_tiles * bn + 255) / 256, k, &pp.group_m, &pp.band_n);
     pp.band_n = pp.band_n * 256 / bn;      // the band is sized in columns
+    pair_plan_streamk(ctx, pp, sk_ws, sk_ws_bytes);
     cudaStream_t ps = static_cast<cudaStream_t>(stream);
 #define FGB_PAIR_CASE(E)                                                       \
   case E:                                                                      \
@@ -788,7 +1044,7 @@ extern "C" int fgb_gemm_bf16_ex(fgb_ctx* ctx, const void* a, int64_t lda, const 
 
 extern "C" int fgb_gemm_qkv_scatter(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, int32_t m,
                                     int32_t dim, int32_t k, void* const* peer_recv, int32_t world, int32_t rank, float* rowsq,
-                                    void* stream) {
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace fgb;
   FGB_CHECK_ARG(ctx && a && w && peer_recv && rowsq, "fgb_gemm_qkv_scatter: NULL argument");
   FGB_CHECK_ARG(m > 0 && k > 0 && k % 8 == 0 && dim > 0 && dim % 256 == 0 && lda >= k && ldw >= k,
@@ -829,6 +1085,8 @@ extern "C" int fgb_gemm_qkv_scatter(fgb_ctx* ctx, const void* a, int64_t lda, co
   pp.tiles = pp.m_tiles * pp.n_tiles;
   pp.k_blocks = (k + kBK - 1) / kBK;
   pair_supertile(pp.m_tiles, pp.n_tiles, k, &pp.group_m, &pp.band_n);
+  FGB_CHECK_ARG(!workspace || aligned16(workspace), "fgb_gemm_qkv_scatter: workspace must be 16-byte aligned");
+  pair_plan_streamk(ctx, pp, workspace, workspace_bytes);
   return launch_gemm_pair<FGB_EPI_BIAS, 256, true>(ctx, ta, tb, pm.m[0], pp, static_cast<cudaStream_t>(stream), &pm);
 }
 

@@ -20,6 +20,9 @@ struct fgb_ctx {
                            const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
   CUresult (*mem_get_address_range)(CUdeviceptr* base, size_t* size, CUdeviceptr ptr) = nullptr;
+  // stream-K tail of the 2-CTA GEMM (gemm.cu: pair_plan_streamk); -1 = not initialised yet
+  int sk_enabled = 1, sk_min_kblocks = -1;
+  double sk_max_frac = 0.9;
   int32_t* attn_stats = nullptr;   // caller-owned device int32[3] (fgb_attn_set_stats) or NULL
   // Encoded tensor maps, keyed by (base, rows, cols, ld, box): a denoise step re-uses the same ~40 (pointer, shape) pairs for
   // its 600 GEMM / attention launches, so the driver's encoder runs once per pair instead of three times per launch.

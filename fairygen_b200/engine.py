@@ -138,6 +138,7 @@ class WanDiTEngine:
                 ts=torch.zeros(2, dtype=torch.float32, device=dev), emb=e(2, cfg.freq_dim), t0=e(2, d), t0s=e(2, d),
                 t=e(2, d), ts_silu=e(2, d), tmod=e(2, 6 * d), mod_tab=e(2, L, 6 * d), head_tab=e(2, 2 * d),
                 kmax2=torch.zeros(cfg.num_heads, dtype=torch.float32, device=dev),
+                sk=ops.gemm_workspace(dev),    # stream-K tail of the block's GEMMs (all launches of a forward are on one stream)
             )
             if self.sp is not None:
                 hpr_w = 3 * d // self.sp.world
@@ -284,17 +285,18 @@ class WanDiTEngine:
         self._launched(2)
 
         k = self._k
+        sk = ws["sk"]
         for i, b in enumerate(self.blocks):
             m0, m1 = mod_tab[0, i].view(6, d), mod_tab[r_main, i].view(6, d)
             # self-attention branch (DIT:224-225)
             k("ln_modulate", ops.ln_modulate, x, a, cfg.eps, m0[0], m0[1], m1[0], m1[1], n_first)
             if sp is not None and getattr(sp, "exchange", "nccl") == "p2p":
                 def qkv_rows(r0, r1, a=a, b=b, qkv=qkv):
-                    k("gemm_qkv", ops.gemm, a[r0:r1], b.wqkv, b.bqkv, qkv[r0:r1])
+                    k("gemm_qkv", ops.gemm, a[r0:r1], b.wqkv, b.bqkv, qkv[r0:r1], sk_ws=sk)
                 fused = (a, b.wqkv, b.bqkv, cfg.eps, b.nq, b.nk, self.rope_tab, grid) if (getattr(sp, "fused_send", False) and d % 256 == 0) else None
                 sp.attention(self, ws, qkv, o, S, norm=(cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0), qkv_gemm=qkv_rows, fused=fused)
             else:
-                k("gemm_qkv", ops.gemm, a, b.wqkv, b.bqkv, qkv)
+                k("gemm_qkv", ops.gemm, a, b.wqkv, b.bqkv, qkv, sk_ws=sk)
                 if sp is None:
                     # q and k normalised + rotated and the key bound of the bounded softmax in one pass over the fused rows
                     k("rmsnorm_rope", ops.qk_norm_rope, qkv, d, cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0, ws["kmax2"])
@@ -303,17 +305,17 @@ class WanDiTEngine:
                     k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)
                     k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, d:2 * d], cfg.eps, b.nk, self.rope_tab, grid, tok0)
                     sp.attention(self, ws, qkv, o, S)
-            k("gemm_o", ops.gemm, o, b.wo, b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first)
+            k("gemm_o", ops.gemm, o, b.wo, b.bo, x, EPI_GATED_RESIDUAL, m0[2], m1[2], n_first, sk_ws=sk)
             # cross-attention branch (DIT:226)
             k("ln_affine", ops.ln_affine, x, a, cfg.eps, b.n3w, b.n3b)
-            k("gemm_cross_q", ops.gemm, a, b.cwq, b.cbq, cq)
+            k("gemm_cross_q", ops.gemm, a, b.cwq, b.cbq, cq, sk_ws=sk)
             k("rmsnorm", ops.rmsnorm_rope, cq, cfg.eps, b.cnq)
             k("attn_cross", ops.attention, cq, kv_all[i][:, :d], kv_all[i][:, d:], o, H, kmax2=kmax_all[i])
-            k("gemm_cross_o", ops.gemm, o, b.cwo, b.cbo, x, EPI_RESIDUAL)
+            k("gemm_cross_o", ops.gemm, o, b.cwo, b.cbo, x, EPI_RESIDUAL, sk_ws=sk)
             # feed-forward branch (DIT:227-228)
             k("ln_modulate", ops.ln_modulate, x, a, cfg.eps, m0[3], m0[4], m1[3], m1[4], n_first)
-            k("gemm_ffn1", ops.gemm, a, b.w1, b.b1, hbuf, EPI_BIAS_GELU_TANH)
-            k("gemm_ffn2", ops.gemm, hbuf, b.w2, b.b2, x, EPI_GATED_RESIDUAL, m0[5], m1[5], n_first)
+            k("gemm_ffn1", ops.gemm, a, b.w1, b.b1, hbuf, EPI_BIAS_GELU_TANH, sk_ws=sk)
+            k("gemm_ffn2", ops.gemm, hbuf, b.w2, b.b2, x, EPI_GATED_RESIDUAL, m0[5], m1[5], n_first, sk_ws=sk)
 
         # ---- head (DIT:261-268) + unpatchify (DIT:346-351)
         h0, h1 = head_tab[0].view(2, d), head_tab[r_main].view(2, d)

@@ -91,8 +91,21 @@ def _vec(t: Optional[torch.Tensor], n: int, what: str) -> None:
         raise ValueError(f"{what}: expected a contiguous bf16 vector of {n} elements")
 
 
-def gemm(a, w, bias, out, epilogue=EPI_BIAS, gate0=None, gate1=None, rows_gate0=0, a2=None, w2=None):
-    """out[m,n] = epilogue(a[m,k] @ w[n,k].T (+ a2[m,k2] @ w2[n,k2].T) + bias); see fgb_gemm_bf16 / fgb_gemm_bf16_ex."""
+def gemm_workspace(device) -> torch.Tensor:
+    """Caller-owned, zero-initialised scratch of the stream-K tail (fgb_gemm_bf16_sk): one per engine; launches that share it must be
+    ordered on one stream."""
+    need = _lib.lib().fgb_gemm_workspace_bytes(context(device).handle)
+    return torch.zeros(int(need), dtype=torch.uint8, device=device)
+
+
+def gemm_streamk_tune(device, min_k: int = 6144, max_tail_frac: float = 0.9) -> None:
+    """Thresholds of the stream-K split (fgb_gemm_streamk_tune); the defaults are the library's."""
+    _lib.check(_lib.lib().fgb_gemm_streamk_tune(context(device).handle, min_k, max_tail_frac), "fgb_gemm_streamk_tune")
+
+
+def gemm(a, w, bias, out, epilogue=EPI_BIAS, gate0=None, gate1=None, rows_gate0=0, a2=None, w2=None, sk_ws=None):
+    """out[m,n] = epilogue(a[m,k] @ w[n,k].T (+ a2[m,k2] @ w2[n,k2].T) + bias); see fgb_gemm_bf16 / fgb_gemm_bf16_ex.
+    sk_ws (gemm_workspace()): the last, partly filled wave of tiles is split along K (fgb_gemm_bf16_sk)."""
     lda, ldw, ldc = _rowmajor(a, "a"), _rowmajor(w, "w"), _rowmajor(out, "out")
     m, k = a.shape
     n = w.shape[0]
@@ -100,6 +113,12 @@ def gemm(a, w, bias, out, epilogue=EPI_BIAS, gate0=None, gate1=None, rows_gate0=
         raise ValueError(f"gemm shape mismatch: a {tuple(a.shape)} w {tuple(w.shape)} out {tuple(out.shape)}")
     _vec(bias, n, "bias"), _vec(gate0, n, "gate0"), _vec(gate1, n, "gate1")
     c = _h(a)
+    if sk_ws is not None and a2 is None and w2 is None:
+        if sk_ws.dtype != torch.uint8 or not sk_ws.is_contiguous() or sk_ws.device != a.device:
+            raise ValueError("gemm: sk_ws must be the uint8 tensor gemm_workspace() returned for this device")
+        _lib.check(_lib.lib().fgb_gemm_bf16_sk(c.handle, _p(a), lda, _p(w), ldw, _p(bias), _p(out), ldc, m, n, k, epilogue,
+                                               _p(gate0), _p(gate1), rows_gate0, _p(sk_ws), sk_ws.numel(), _stream()), "fgb_gemm_bf16_sk")
+        return out
     if a2 is None and w2 is None:
         _lib.check(_lib.lib().fgb_gemm_bf16(c.handle, _p(a), lda, _p(w), ldw, _p(bias), _p(out), ldc, m, n, k, epilogue,
                                             _p(gate0), _p(gate1), rows_gate0, _stream()), "fgb_gemm_bf16")
@@ -380,7 +399,7 @@ def sp_return_heads(x, peer_ptrs, ld_dst: int, rows: int, heads: int, groups: in
                                               world, rank, _stream()), "fgb_sp_return_heads")
 
 
-def gemm_qkv_scatter(a, w, bias, dim: int, peer_recv_ptrs, world: int, rank: int, rowsq):
+def gemm_qkv_scatter(a, w, bias, dim: int, peer_recv_ptrs, world: int, rank: int, rowsq, sk_ws=None):
     """q|k|v = a @ w.T + bias, every 32x64 block TMA-stored into the head owner's receive matrix (fused Ulysses send);
     rowsq fp32 [2, rows] += sum of squares of each q / k row."""
     lda, ldw = _rowmajor(a, "a"), _rowmajor(w, "w")
@@ -389,7 +408,8 @@ def gemm_qkv_scatter(a, w, bias, dim: int, peer_recv_ptrs, world: int, rank: int
         raise ValueError(f"gemm_qkv_scatter: a {tuple(a.shape)} w {tuple(w.shape)} dim {dim} rowsq {tuple(rowsq.shape)}")
     _vec(bias, 3 * dim, "bias")
     _lib.check(_lib.lib().fgb_gemm_qkv_scatter(_h(a).handle, _p(a), lda, _p(w), ldw, _p(bias), m, dim, k, _ptr_array(peer_recv_ptrs), world,
-                                               rank, _p(rowsq), _stream()), "fgb_gemm_qkv_scatter")
+                                               rank, _p(rowsq), _p(sk_ws), 0 if sk_ws is None else sk_ws.numel(), _stream()),
+               "fgb_gemm_qkv_scatter")
 
 
 def sp_stats_barrier(device, flag_ptrs, stats_ptrs, rowsq, rows: int, s_pad: int, kmax2, hpr: int, world: int, rank: int, epoch: int,

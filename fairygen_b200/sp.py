@@ -187,7 +187,7 @@ class SequenceParallel:
                 # send side fused into the projection: the GEMM epilogue TMA-stores every block into the head owner's receive
                 # matrix; the full-row statistics of q and k travel with barrier 0; RMSNorm + RoPE happen on the receiver
                 a, w, bias, eps, wq, wk, rope_tab, grid = fused
-                k("gemm_qkv", ops.gemm_qkv_scatter, a, w, bias, heads * 128, ar.recv_ptrs, self.world, self.rank, ar.rowsq)
+                k("gemm_qkv", ops.gemm_qkv_scatter, a, w, bias, heads * 128, ar.recv_ptrs, self.world, self.rank, ar.rowsq, sk_ws=ws.get("sk"))
                 ar.epoch += 1
                 kmax2 = ws["kmax2"][:hpr]
                 k("sp_barrier", ops.sp_stats_barrier, qkv.device, ar.flag_ptrs[0], ar.stats_ptrs, ar.rowsq, rows, rows * self.world, kmax2,

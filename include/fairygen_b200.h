@@ -68,6 +68,20 @@ int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64
                   void* c, int64_t ldc, int32_t m, int32_t n, int32_t k, int32_t epilogue,
                   const void* gate0, const void* gate1, int32_t rows_gate0, void* stream);
 
+/* fgb_gemm_bf16 with a stream-K tail (the DiT block's Linears, DIT:140-146, 176-185, 208-209, at sizes where the tile count is
+ * not a multiple of the 74 CTA pairs: e.g. 27 280 x 3072 = 1284 tiles = 17.35 waves, or 6820 x 3072 on a Ulysses SP4 rank =
+ * 4.38 waves). The K range of the tiles of the last, partly filled wave is spread over all CTA pairs; partial fp32 accumulators
+ * meet in `workspace` (caller-owned, 16-byte aligned, fgb_gemm_workspace_bytes() bytes, ZERO on first use — the kernel leaves its
+ * flags zero again). Launches that share a workspace must be ordered on one stream. NULL workspace = fgb_gemm_bf16. The result
+ * of a split tile differs from the unsplit one only in fp32 summation order (deterministic for a given shape). */
+int fgb_gemm_bf16_sk(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c, int64_t ldc,
+                     int32_t m, int32_t n, int32_t k, int32_t epilogue, const void* gate0, const void* gate1, int32_t rows_gate0,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+int64_t fgb_gemm_workspace_bytes(fgb_ctx* ctx);
+/* When fgb_gemm_bf16_sk splits: only if k >= min_k (default 6144: the fix-up costs ~15 us, a short-K tile is ~20 us) and the
+ * tail fills at most max_tail_frac of the CTA pairs (default 0.9). Tests set min_k = 0 to drive the split path on small shapes. */
+int fgb_gemm_streamk_tune(fgb_ctx* ctx, int32_t min_k, double max_tail_frac);
+
 /* Same with a second operand pair folded in as extra K-blocks:  acc = A·Wᵀ + A2·W2ᵀ  (a2 [m, k2], w2 [n, k2], k2 % 8 == 0).
  * Used by the stage-2 LoRA forward (training_module.py:317-352): y = W₁x + b + (B2*mask*2)(A1 x) without re-merging the
  * weight every step — A2 = A1·x (rank r), W2 = the masked B2. */
@@ -234,7 +248,8 @@ int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t
  *                         rank's heads), 3-D RoPE (DIT:91-96) on the q and k groups of recv [s_pad, 3*hpr*128], in place; leaves
  *                         kmax2[h] = max over the first `tokens` rows of ||k[t,h]||^2 (the bound fgb_attn_fwd_bounded wants). */
 int fgb_gemm_qkv_scatter(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, int32_t m, int32_t dim,
-                         int32_t k, void* const* peer_recv, int32_t world, int32_t rank, float* rowsq, void* stream);
+                         int32_t k, void* const* peer_recv, int32_t world, int32_t rank, float* rowsq, void* workspace,
+                         int64_t workspace_bytes, void* stream);   /* workspace: as fgb_gemm_bf16_sk, may be NULL */
 int fgb_sp_stats_barrier(fgb_ctx* ctx, void* const* peer_flags, void* const* peer_stats, void* rowsq, int32_t rows, int32_t s_pad,
                          void* kmax2, int32_t hpr, int32_t world, int32_t rank, int32_t epoch, void* status, void* stream);
 int fgb_recv_norm_rope(fgb_ctx* ctx, void* recv, int32_t s_pad, int32_t tokens, int32_t hpr, const void* stats, int32_t dim, float eps,

@@ -22,7 +22,10 @@ def _emulated_ops(monkeypatch):
         xf = x.float()
         return (xf - xf.mean(-1, keepdim=True)) * torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + eps)
 
-    def gemm(a, w, bias, out, epilogue=ops.EPI_BIAS, gate0=None, gate1=None, rows_gate0=0, a2=None, w2=None):
+    def gemm_workspace(device):
+        return torch.zeros(16, dtype=torch.uint8)
+
+    def gemm(a, w, bias, out, epilogue=ops.EPI_BIAS, gate0=None, gate1=None, rows_gate0=0, a2=None, w2=None, sk_ws=None):
         acc = a.float() @ w.float().T
         if a2 is not None:
             acc = acc + a2.float() @ w2.float().T

@@ -56,6 +56,47 @@ def test_gemm_epilogues(env, m, n, k, epi):
     assert rel_l2(out, ref.to(BF)) < 2e-3
 
 
+@pytest.mark.parametrize("m,n,k", [(6820, 3072, 3072),     # Ulysses SP4 rank: 324 tiles = 4 waves + 28 tail tiles over 74 CTA pairs
+                                   (1000, 768, 512),       # 12 tiles < 74 pairs: no whole wave, 2 units per tile, idle pairs
+                                   (2561, 9216, 1000),     # ragged m / k; 396 tiles = 5 waves + 26; last unit of a tile is short
+                                   (19000, 1024, 1536),    # 300 tiles = 4 waves + 4: at most 4 pairs per tail tile
+                                   (4100, 1088, 14336)])   # long K (FFN2), ragged n: 85 tiles = 1 wave + 11
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_streamk_tail_matches_unsplit(env, m, n, k, epi):
+    """fgb_gemm_bf16_sk: the K range of the last, partly filled wave is spread over all CTA pairs. Same contract as the unsplit
+    kernel (fp32 reference, 2e-3), near-identical to the unsplit result (summation order only), and the workspace flags are
+    left clean: a second launch on the same workspace gives the same bits."""
+    ops, o = env
+    a, w, bias = rnd(m, k, seed=1), rnd(n, k, seed=2, scale=1 / math.sqrt(k)), rnd(n, seed=3, scale=0.5)
+    g0, g1, c0 = rnd(n, seed=4), rnd(n, seed=5), rnd(m, n, seed=6)
+    rows0 = m // 3
+    dev = torch.device("cuda", 0)
+    ws = ops.gemm_workspace(dev)
+    plain, out, again = c0.clone(), c0.clone(), c0.clone()
+    ops.gemm(a, w, bias, plain, epi, g0, g1, rows0)
+    ops.gemm_streamk_tune(dev, min_k=0)          # split short-K tiles too (the default only splits k >= 6144)
+    try:
+        ops.gemm(a, w, bias, out, epi, g0, g1, rows0, sk_ws=ws)
+        ops.gemm(a, w, bias, again, epi, g0, g1, rows0, sk_ws=ws)
+        ops.sync_check()
+    finally:
+        ops.gemm_streamk_tune(dev)
+    y = (a.float() @ w.float().T + bias.float()).to(BF).float()
+    if epi == 0:
+        ref = y
+    elif epi == 1:
+        ref = F.gelu(y, approximate="tanh")
+    elif epi == 2:
+        gate = torch.where((torch.arange(m, device="cuda") < rows0)[:, None], g0.float()[None], g1.float()[None])
+        ref = c0.float() + (gate * y).to(BF).float()
+    else:
+        ref = c0.float() + y
+    assert rel_l2(out, ref.to(BF)) < 2e-3
+    assert rel_l2(out, plain) < 1e-3
+    assert torch.equal(out, again)
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0        # every flag lowered again
+
+
 def test_gemm_no_bias_and_strided_views(env):
     ops, o = env
     a_wide = rnd(300, 1024, seed=1)

@@ -24,7 +24,8 @@ for name in which:
     b = torch.randn(n, device=dev, dtype=torch.bfloat16, generator=g)
     c = torch.zeros(S, n, device=dev, dtype=torch.bfloat16)
     g0 = torch.randn(n, device=dev, dtype=torch.bfloat16, generator=g)
-    fn = lambda: ops.gemm(a, w, b, c, epi, g0, g0, 880)  # noqa: E731
+    sk = ops.gemm_workspace(dev) if os.environ.get("SK", "0") != "0" else None     # SK=1: stream-K tail (fgb_gemm_bf16_sk)
+    fn = lambda: ops.gemm(a, w, b, c, epi, g0, g0, 880, sk_ws=sk)  # noqa: E731
     for _ in range(5):
         fn()
     torch.cuda.synchronize()
@@ -37,4 +38,4 @@ for name in which:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     out.append(f"{name} {2.0 * S * n * k / ms / 1e9:.0f}")
-print(f"rows={S} GM={os.environ.get('FGB_GEMM_GROUP_M', '-')} BAND={os.environ.get('FGB_GEMM_BAND_N', '-')} BN={os.environ.get('FGB_GEMM_BN', '-')} lib={os.path.basename(os.environ.get('FGB_LIB_PATH', 'intree'))} epi={epi}: " + "  ".join(out))
+print(f"rows={S} SK={os.environ.get('SK', '0')} GM={os.environ.get('FGB_GEMM_GROUP_M', '-')} BAND={os.environ.get('FGB_GEMM_BAND_N', '-')} BN={os.environ.get('FGB_GEMM_BN', '-')} lib={os.path.basename(os.environ.get('FGB_LIB_PATH', 'intree'))} epi={epi}: " + "  ".join(out))
