@@ -26,7 +26,16 @@ from .ops import BF16, EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_GATED_RESIDUAL, EPI_RES
 
 class _Block:
     __slots__ = ("wqkv", "bqkv", "wo", "bo", "nq", "nk", "cwq", "cbq", "cwkv", "cbkv", "cwo", "cbo", "cnq", "cnk",
-                 "n3w", "n3b", "w1", "b1", "w2", "b2")
+                 "n3w", "n3b", "w1", "b1", "w2", "b2", "private")
+
+    def own(self, attr: str) -> torch.Tensor:
+        """The weight `attr` as a tensor this engine may write: load_state_dict() does not copy a weight that already is bf16 on
+        the device (no second 10 GB), so wo / cwq / cwo / w1 / w2 may alias the caller's module — an in-place LoRA fusion into
+        the engine must not reach the module's parameters (copy on first write; the concatenated wqkv / cwkv are always ours)."""
+        if attr not in self.private:
+            setattr(self, attr, getattr(self, attr).clone())
+            self.private.add(attr)
+        return getattr(self, attr)
 
 
 def _dev_bf16(t: torch.Tensor, device) -> torch.Tensor:
@@ -85,6 +94,7 @@ class WanDiTEngine:
         for i in range(cfg.num_layers):
             p = f"blocks.{i}."
             b = _Block()
+            b.private = {"wqkv", "cwkv"}
             sa, ca = p + "self_attn.", p + "cross_attn."
             b.wqkv = torch.cat([g(sa + "q.weight"), g(sa + "k.weight"), g(sa + "v.weight")], dim=0).contiguous()
             b.bqkv = torch.cat([g(sa + "q.bias"), g(sa + "k.bias"), g(sa + "v.bias")], dim=0).contiguous()

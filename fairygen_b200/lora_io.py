@@ -132,18 +132,18 @@ def fuse_into_engine(engine, lora_sd: Dict[str, torch.Tensor], alpha: float = 1.
 
     names = name_dict(lora_sd)
     dev, d = engine.device, engine.cfg.dim
-    slots = {}
+    slots = {}       # module name -> (block, weight attribute, first row, rows)
     for i, b in enumerate(engine.blocks):
         p = f"blocks.{i}."
         for j, proj in enumerate("qkv"):
-            slots[p + "self_attn." + proj] = b.wqkv[j * d:(j + 1) * d]
-        slots[p + "self_attn.o"] = b.wo
-        slots[p + "cross_attn.q"] = b.cwq
+            slots[p + "self_attn." + proj] = (b, "wqkv", j * d, d)
+        slots[p + "self_attn.o"] = (b, "wo", 0, None)
+        slots[p + "cross_attn.q"] = (b, "cwq", 0, None)
         for j, proj in enumerate("kv"):
-            slots[p + "cross_attn." + proj] = b.cwkv[j * d:(j + 1) * d]
-        slots[p + "cross_attn.o"] = b.cwo
-        slots[p + "ffn.0"] = b.w1
-        slots[p + "ffn.2"] = b.w2
+            slots[p + "cross_attn." + proj] = (b, "cwkv", j * d, d)
+        slots[p + "cross_attn.o"] = (b, "cwo", 0, None)
+        slots[p + "ffn.0"] = (b, "w1", 0, None)
+        slots[p + "ffn.2"] = (b, "w2", 0, None)
     wanted = set(targets) if targets is not None else None
     fused = 0
     for module, (kb, ka) in names.items():
@@ -151,7 +151,10 @@ def fuse_into_engine(engine, lora_sd: Dict[str, torch.Tensor], alpha: float = 1.
             continue
         up = lora_sd[kb].detach().to(device=dev, dtype=torch.bfloat16).contiguous()
         down = lora_sd[ka].detach().to(device=dev, dtype=torch.bfloat16).contiguous()
-        w = slots[module]
+        blk, attr, r0, nrows = slots[module]
+        w = blk.own(attr)            # never the caller's parameter: weights that alias the module are copied on first write
+        if nrows is not None:
+            w = w[r0:r0 + nrows]
         ops.lora_merge(w, down, up, None, None, w, 1.0, float(alpha))   # in place: each output tile reads only itself
         fused += 1
     engine._ctx_cache.clear()          # cached cross-attention K/V were projected with the old weights

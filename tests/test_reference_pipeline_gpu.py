@@ -150,7 +150,11 @@ def test_adapter_fused_into_the_engine_survives_a_repack_and_cpu_dit_is_refused(
     lora_a = synthetic.random_lora(cfg, rank=16, seed=6, device="cuda")      # fgb_lora_merge: ranks 16 / 32 / 64
     lora_b = synthetic.random_lora(cfg, rank=16, seed=7, device="cuda")
     eng = mf.engine_for(our_pipe.dit)
+    module_w = our_pipe.dit.blocks[0].self_attn.o.weight
+    before = module_w.detach().clone()
     lora_io.fuse_into_engine(eng, lora_a)                                      # directly on the packed weights
+    # the engine does not copy weights that already are bf16 on the device: the fusion must not reach the module's parameters
+    assert torch.equal(module_w, before) and eng.blocks[0].wo.data_ptr() != module_w.data_ptr()
     our_pipe.load_lora(our_pipe.dit, state_dict=lora_b)                        # changes the container -> re-pack
     for sd in (lora_a, lora_b):
         ref_pipe.load_lora(ref_pipe.dit, state_dict={k: v.clone() for k, v in sd.items()})
