@@ -535,12 +535,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       signal_p(&p_ready2[i]);
     };
     auto run_tiles = [&](auto mode_tag) {
-      for (int j = 0; j + 1 < n_kv; ++j) {
+      // the peeled copy (masking, MUFU-only sweep) runs only when the item's last KV tile really is partial: a full last tile
+      // goes through the loop body, so that an item touches ONE copy of the tile step — with 4 KV tiles per item
+      // (cross-attention) the second copy pushed the per-item code footprint past the instruction cache (8.8 % no-instruction
+      // stalls against 1.4 % in self-attention, profiles/r02_ncu_attn_cross_summary.csv)
+      const bool tail_partial = p.s_kv - (kv_lo + n_kv - 1) * kTile < kTile;
+      const int n_plain = tail_partial ? n_kv - 1 : n_kv;
+      for (int j = 0; j < n_plain; ++j) {
         tile_step(mode_tag, TagFalse{}, j, 0);   // both warpgroups work on query tile 0 together, then on tile 1
         tile_step(mode_tag, TagFalse{}, j, 1);
       }
-      tile_step(mode_tag, TagTrue{}, n_kv - 1, 0);
-      tile_step(mode_tag, TagTrue{}, n_kv - 1, 1);
+      if (tail_partial) {
+        tile_step(mode_tag, TagTrue{}, n_kv - 1, 0);
+        tile_step(mode_tag, TagTrue{}, n_kv - 1, 1);
+      }
     };
     if (mode == 0) run_tiles(ModeTag<0>{});
     else if (mode == 1) run_tiles(ModeTag<1>{});

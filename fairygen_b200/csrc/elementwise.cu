@@ -5,6 +5,8 @@
 // diffusion/flow_match.py, "FM") with one pass over HBM each: every row is read once with 16-byte
 // loads (12 in flight per lane at D = 3072), reduced with warp shuffles, and written once.
 // Arithmetic is fp32 with the reference's bf16 rounding points reproduced in registers.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -643,12 +645,280 @@ recv_norm_rope_kernel(__nv_bfloat16* __restrict__ recv, int s_pad, int tokens, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row-streaming variants of the three row kernels above (LayerNorm+modulate / affine, RMSNorm(+RoPE), fused q|k RMSNorm+RoPE
+// with the key bound) for the large launches of the denoise step.
+//
+// The one-row-per-warp kernels keep one row per warp in flight and only while that warp is in its load phase (64-79 % of
+// the HBM copy rate, BENCH_r01). Here one persistent CTA per SM decouples the two: a single producer thread keeps a ring of
+// kSlots rows in flight with 1-D bulk copies (cp.async.bulk, completion on mbarriers) — 132 KB per SM at D = 3072,
+// independent of what the consumers are doing — and 11 consumer warps take rows out of shared memory (16 bytes per lane,
+// conflict-free), release the slot as soon as the row is in registers, and do the same arithmetic and the same 16-byte
+// stores as before. Items are dealt round-robin over the CTAs: item n of CTA b is global item b + n*gridDim.x.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStreamWarps = 11;      // + 1 producer warp = 12 warps: registers are allocated per 4 warps, a 13th warp would cap a thread at 128
+constexpr int kStreamThreads = (kStreamWarps + 1) * 32;
+
+template <int NV>
+struct StreamCfg {
+  static constexpr int kRowBytes = NV * 512;
+  // A slot is always consumed by the SAME warp (kSlots is a multiple of kStreamWarps and a warp takes every kStreamWarps-th item),
+  // so a warp looks at a slot's `full` barrier for fill n only after it consumed fill n-1 itself. With a free slot -> warp
+  // mapping a fast warp could test the parity of fill n while fill n-1 had not even landed (bulk copies complete out of
+  // order when one of them misses the TLB), see the opposite parity as "done", read a stale row and arrive on `empty` once
+  // too often: wrong rows and, a few launches in a hundred at > 128 MB, a dead ring (caught by the spin-limit trap).
+  static constexpr int kSlots = (2 * kStreamWarps * kRowBytes <= 160 * 1024) ? 2 * kStreamWarps : kStreamWarps;
+  static constexpr int kSmem = kSlots * kRowBytes + 2 * kSlots * 8 + 128;
+};
+
+// OP: struct with `void row(int item, int lane, uint4 (&v)[NV])` (consumes one row / row segment held in registers) and
+// `void finish(int warp, int lane)` (after the CTA's last row; may use the barrier below), plus
+// `const __nv_bfloat16* src(int item) const` (where the item's NV*512 bytes start).
+template <int NV, class OP>
+__global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(int items, OP op) {
+  using C = StreamCfg<NV>;
+  extern __shared__ uint8_t stream_smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stream_smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + C::kSlots * C::kRowBytes);
+  uint64_t* empty = full + C::kSlots;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kSlots; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == kStreamWarps) {
+    if (elect_one()) {
+      int k = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
+        const int slot = k % C::kSlots;
+        mbar_wait(&empty[slot], ((k / C::kSlots) & 1) ^ 1);
+        mbar_expect_tx(&full[slot], C::kRowBytes);
+        bulk_load(ring + slot * C::kRowBytes, op.src(item), C::kRowBytes, &full[slot]);
+      }
+    }
+  } else {
+    for (int k = warp;; k += kStreamWarps) {
+      const int item = blockIdx.x + k * gridDim.x;
+      if (item >= items) break;
+      const int slot = k % C::kSlots;
+      mbar_wait(&full[slot], (k / C::kSlots) & 1);
+      const uint4* src = reinterpret_cast<const uint4*>(ring + slot * C::kRowBytes);
+      uint4 v[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = src[i * 32 + lane];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);     // the row is in registers: the slot can be refilled
+      op.row(item, lane, v);
+    }
+  }
+  __syncwarp();
+  op.finish(warp, lane);
+}
+
+template <int NV, bool AFFINE>
+struct LnStreamOp {
+  const __nv_bfloat16* x;
+  int64_t ldx;
+  __nv_bfloat16* y;
+  int64_t ldy;
+  float eps;
+  const __nv_bfloat16 *shift0, *scale0, *shift1, *scale1;
+  int rows_mod0;
+  __device__ __forceinline__ const __nv_bfloat16* src(int item) const { return x + static_cast<int64_t>(item) * ldx; }
+  __device__ __forceinline__ void row(int row, int lane, uint4 (&v)[NV]) {
+    constexpr int D = NV * 256;
+    const float K = __shfl_sync(0xffffffffu, bf16_lo(v[0].x), 0);
+    float s1 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      unpack8(v[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[e] - K;
+        s1 += d;
+        q1 = fmaf(d, d, q1);
+      }
+    }
+    s1 = warp_sum(s1) * (1.0f / D);
+    q1 = warp_sum(q1) * (1.0f / D);
+    const float mean = K + s1;
+    const float rstd = rsqrtf(fmaxf(q1 - s1 * s1, 0.f) + eps);
+    const bool first = AFFINE || row < rows_mod0;
+    const uint4* sh = reinterpret_cast<const uint4*>(first ? shift0 : shift1);
+    const uint4* sc = reinterpret_cast<const uint4*>(first ? scale0 : scale1);
+    uint4* yr = reinterpret_cast<uint4*>(y + static_cast<int64_t>(row) * ldy);
+    const float nmr = -mean * rstd;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      unpack8(v[i], f);
+      const uint4 av = __ldg(sc + i * 32 + lane), bv = __ldg(sh + i * 32 + lane);
+      if (AFFINE) {
+        float a[8], b[8];
+        unpack8(av, a);
+        unpack8(bv, b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], rstd, nmr) * a[e] + b[e];
+        yr[i * 32 + lane] = pack8(f);
+      } else {
+        const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t n = pack_bf16(fmaf(f[2 * w], rstd, nmr), fmaf(f[2 * w + 1], rstd, nmr));
+          o[w] = add_bf16x2(mul_bf16x2(n, add_bf16x2(0x3F803F80u, aw[w])), bw[w]);
+        }
+        yr[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  __device__ __forceinline__ void finish(int, int) {}
+};
+
+// SEGS = 1: RMSNorm(+RoPE) of [rows, D] in place (weight w0). SEGS = 2: the q and k groups of the fused q|k|v rows (item =
+// row*2 + group; weights w0 / w1) plus the key bound kmax2[h] = max ||k[row, h]||^2.
+template <int NV, int SEGS>
+struct RmsStreamOp {
+  __nv_bfloat16* x;
+  int64_t ldx;
+  float eps;
+  const __nv_bfloat16 *w0, *w1;
+  const float2* rope_tab;
+  int gf, gh, gw, token_offset;
+  float* kmax2;
+  float best[SEGS == 2 ? NV : 1];
+  __device__ __forceinline__ __nv_bfloat16* dst(int item) const {
+    return SEGS == 2 ? x + static_cast<int64_t>(item >> 1) * ldx + (item & 1) * (NV * 256) : x + static_cast<int64_t>(item) * ldx;
+  }
+  __device__ __forceinline__ const __nv_bfloat16* src(int item) const { return dst(item); }
+  __device__ __forceinline__ void row(int item, int lane, uint4 (&v)[NV]) {
+    constexpr int D = NV * 256;
+    const int r = SEGS == 2 ? item >> 1 : item;
+    const int g = SEGS == 2 ? item & 1 : 0;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      unpack8(v[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sq += f[e] * f[e];
+    }
+    const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+    float cs[4], sn[4];
+    bool rotate = false;
+    if (rope_tab != nullptr) {
+      const int t = token_offset + r;
+      if (t < gf * gh * gw) {
+        rotate = true;
+        const int fi = t / (gh * gw), hi = (t / gw) % gh, wi = t % gw;
+        const int c0 = (lane & 15) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j;
+          const int pos = c < 22 ? fi : (c < 43 ? hi : wi);
+          const float2 e = __ldg(rope_tab + pos * 64 + c);
+          cs[j] = e.x;
+          sn[j] = e.y;
+        }
+      }
+    }
+    const uint4* wr = reinterpret_cast<const uint4*>(g == 0 ? w0 : w1);
+    uint4* xr = reinterpret_cast<uint4*>(dst(item));
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      unpack8(v[i], f);
+      const uint4 wv = __ldg(wr + i * 32 + lane);
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) o[w] = mul_bf16x2(pack_bf16(f[2 * w] * rs, f[2 * w + 1] * rs), ww[w]);
+      if (rotate) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16_lo(o[j]), b = bf16_hi(o[j]);
+          o[j] = pack_bf16(a * cs[j] - b * sn[j], a * sn[j] + b * cs[j]);
+        }
+      }
+      xr[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+      if (SEGS == 2) {
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ss += bf16_lo(o[j]) * bf16_lo(o[j]) + bf16_hi(o[j]) * bf16_hi(o[j]);
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
+        if (g == 1) best[i] = fmaxf(best[i], ss);
+      }
+    }
+  }
+  __device__ __forceinline__ void finish(int warp, int lane) {
+    if (SEGS != 2) return;
+    __shared__ float red[kStreamWarps][2 * NV];
+    if (warp < kStreamWarps && (lane & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) red[warp][2 * i + (lane >> 4)] = best[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * NV) {
+      float mx = 0.f;
+#pragma unroll
+      for (int w = 0; w < kStreamWarps; ++w) mx = fmaxf(mx, red[w][threadIdx.x]);
+      if (mx > __ldcg(kmax2 + threadIdx.x))
+        atomicMax(reinterpret_cast<unsigned int*>(kmax2) + threadIdx.x, __float_as_uint(mx));   // non-negative floats order like their bits
+    }
+  }
+};
+
+// rows below this stay on the one-row-per-warp kernels: a persistent grid needs a few rows per warp.
+// Which kernels stream (FGB_EW_STREAM: bit 0 = LayerNorm kernels, bit 1 = RMSNorm kernels; default 1): measured inside the
+// power-capped denoise step (profiles/r02_ew_stream_ab.log), the two LayerNorm kernels gain (ln_modulate 8.35 -> 7.83 ms,
+// ln_affine 4.92 -> 4.04 ms per step) while the in-place RMSNorm kernels lose (10.2 -> 12.3 ms, 3.9 -> 4.7 ms); alone at full
+// clocks the one-row-per-warp kernels already run at 0.91-0.93 of the copy rate and the ring does not help either.
+constexpr int kStreamMinRows = 2048;
+static bool stream_enabled(int bit) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("FGB_EW_STREAM");
+    mask = e ? atoi(e) : 1;
+  }
+  return (mask >> bit) & 1;
+}
+
+template <int NV, class OP>
+static int launch_row_stream(const fgb_ctx* ctx, cudaStream_t s, int items, const OP& op) {
+  auto kfn = row_stream_kernel<NV, OP>;
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured))
+    FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<NV>::kSmem));
+  const int grid = items < ctx->sm_count ? items : ctx->sm_count;
+  kfn<<<grid, kStreamThreads, StreamCfg<NV>::kSmem, s>>>(items, op);
+  FGB_LAUNCH_CHECK("row_stream_kernel");
+  return FGB_OK;
+}
+
 static inline int grid_1d(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
 
 template <bool AFFINE>
-static int launch_ln(int nv, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, int64_t ldx, __nv_bfloat16* y,
+static int launch_ln(const fgb_ctx* ctx, int nv, dim3 grid, cudaStream_t s, const __nv_bfloat16* x, int64_t ldx, __nv_bfloat16* y,
                      int64_t ldy, int rows, float eps, const __nv_bfloat16* sh0, const __nv_bfloat16* sc0,
                      const __nv_bfloat16* sh1, const __nv_bfloat16* sc1, int rows_mod0) {
+  if (rows >= kStreamMinRows && stream_enabled(0)) {
+#define FGB_LNS_CASE(NV)                                                                                     \
+  case NV:                                                                                                   \
+    return launch_row_stream<NV>(ctx, s, rows, LnStreamOp<NV, AFFINE>{x, ldx, y, ldy, eps, sh0, sc0, sh1, sc1, rows_mod0});
+    switch (nv) {
+      FGB_LNS_CASE(1) FGB_LNS_CASE(2) FGB_LNS_CASE(3) FGB_LNS_CASE(4) FGB_LNS_CASE(6) FGB_LNS_CASE(8) FGB_LNS_CASE(12) FGB_LNS_CASE(16)
+      FGB_LNS_CASE(20)
+      default: break;
+    }
+#undef FGB_LNS_CASE
+  }
 #define FGB_LN_CASE(NV)                                                                                    \
   case NV:                                                                                                 \
     ln_kernel<NV, AFFINE><<<grid, kRowWarps * 32, 0, s>>>(x, ldx, y, ldy, rows, eps, sh0, sc0, sh1, sc1, rows_mod0); \
@@ -678,7 +948,7 @@ extern "C" int fgb_ln_modulate(fgb_ctx* ctx, const void* x, int64_t ldx, void* y
                     aligned16(shift1) && aligned16(scale1),
                 "fgb_ln_modulate: operands must be 16-byte aligned");
   dim3 grid((rows + kRowWarps - 1) / kRowWarps);
-  return launch_ln<false>(dim / 256, grid, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), ldx,
+  return launch_ln<false>(ctx, dim / 256, grid, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), ldx,
                           static_cast<bf16*>(y), ldy, rows, eps, static_cast<const bf16*>(shift0),
                           static_cast<const bf16*>(scale0), static_cast<const bf16*>(shift1),
                           static_cast<const bf16*>(scale1), rows_mod0);
@@ -691,7 +961,7 @@ extern "C" int fgb_ln_affine(fgb_ctx* ctx, const void* x, int64_t ldx, void* y, 
   FGB_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(weight) && aligned16(bias),
                 "fgb_ln_affine: operands must be 16-byte aligned");
   dim3 grid((rows + kRowWarps - 1) / kRowWarps);
-  return launch_ln<true>(dim / 256, grid, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), ldx,
+  return launch_ln<true>(ctx, dim / 256, grid, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), ldx,
                          static_cast<bf16*>(y), ldy, rows, eps, static_cast<const bf16*>(bias),
                          static_cast<const bf16*>(weight), static_cast<const bf16*>(bias),
                          static_cast<const bf16*>(weight), rows);
@@ -713,6 +983,19 @@ extern "C" int fgb_rmsnorm_rope(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows
   bf16* xp = static_cast<bf16*>(x);
   const bf16* wp = static_cast<const bf16*>(weight);
   const float2* tab = static_cast<const float2*>(rope_tab);
+  if (rows >= kStreamMinRows && stream_enabled(1)) {
+#define FGB_RMSS_CASE(NV)                                                                                       \
+  case NV: {                                                                                                    \
+    RmsStreamOp<NV, 1> op{xp, ldx, eps, wp, wp, tab, gf, gh, gw, token_offset, nullptr, {0.f}};                  \
+    return launch_row_stream<NV>(ctx, s, rows, op);                                                             \
+  }
+    switch (dim / 256) {
+      FGB_RMSS_CASE(1) FGB_RMSS_CASE(2) FGB_RMSS_CASE(3) FGB_RMSS_CASE(4) FGB_RMSS_CASE(6) FGB_RMSS_CASE(8) FGB_RMSS_CASE(12)
+      FGB_RMSS_CASE(16) FGB_RMSS_CASE(20)
+      default: break;
+    }
+#undef FGB_RMSS_CASE
+  }
   ScatterSpec none{};
 #define FGB_RMS_CASE(NV)                                                                                         \
   case NV:                                                                                                       \
@@ -947,6 +1230,19 @@ extern "C" int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t row
   const bf16* wkp = static_cast<const bf16*>(wk);
   const float2* tab = static_cast<const float2*>(rope_tab);
   float* kp = static_cast<float*>(kmax2);
+  if (rows >= kStreamMinRows && stream_enabled(1)) {
+#define FGB_QKS_CASE(NV)                                                                                        \
+  case NV: {                                                                                                    \
+    RmsStreamOp<NV, 2> op{xp, ld, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp, {0.f}};                      \
+    return launch_row_stream<NV>(ctx, s, 2 * rows, op);                                                         \
+  }
+    switch (dim / 256) {
+      FGB_QKS_CASE(1) FGB_QKS_CASE(2) FGB_QKS_CASE(3) FGB_QKS_CASE(4) FGB_QKS_CASE(6) FGB_QKS_CASE(8) FGB_QKS_CASE(12) FGB_QKS_CASE(16)
+      FGB_QKS_CASE(20)
+      default: break;
+    }
+#undef FGB_QKS_CASE
+  }
 #define FGB_QK_CASE(NV)                                                                                                            \
   case NV:                                                                                                                         \
     qk_norm_rope_kernel<NV><<<grid, kRowWarps * 32, 0, s>>>(xp, ld, rows, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp);         \

@@ -9,6 +9,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 GOLDEN = os.path.join(REPO, "tests", "golden")
+# the row-streaming variants of BOTH elementwise kernel families are exercised by the GPU tests (the library's default streams
+# the LayerNorm kernels only; it reads the variable once, at the first launch)
+os.environ.setdefault("FGB_EW_STREAM", "3")
 
 
 def pytest_configure(config):

@@ -486,3 +486,50 @@ def test_qk_norm_rope_equals_the_three_separate_kernels(env, rows, dim, grid, to
     ops.sync_check()
     assert torch.equal(got, ref)
     assert torch.allclose(kmax, kref, rtol=1e-6)
+
+
+@pytest.mark.parametrize("rows,dim", [(5000, 3072), (2049, 768), (4097, 4096), (3000, 5120)])
+def test_row_streaming_kernels_equal_the_per_warp_kernels(env, rows, dim):
+    """Launches of >= 2048 rows take the persistent row-streaming kernels (bulk-copy ring + consumer warps); the arithmetic is
+    the per-warp kernels', so the same rows computed in chunks of < 2048 rows (per-warp path) must give the same bits —
+    ln_modulate (two modulation rows), ln_affine, rmsnorm (+RoPE, in place, strided view) and the fused q|k pass with its key bound."""
+    ops, o = env
+    import numpy as np
+    chunk = 1500
+    x = rnd(rows, dim, seed=1, scale=2.0) + 0.5
+    sh0, sc0, sh1, sc1 = (rnd(dim, seed=s, scale=0.3) for s in (2, 3, 4, 5))
+    n0 = rows // 3
+    big, small = torch.empty_like(x), torch.empty_like(x)
+    ops.ln_modulate(x, big, 1e-6, sh0, sc0, sh1, sc1, n0)
+    for r0 in range(0, rows, chunk):
+        r1 = min(rows, r0 + chunk)
+        ops.ln_modulate(x[r0:r1], small[r0:r1], 1e-6, sh0, sc0, sh1, sc1, max(0, min(r1 - r0, n0 - r0)))
+    assert torch.equal(big, small)
+    ops.ln_affine(x, big, 1e-6, sc0, sh0)
+    for r0 in range(0, rows, chunk):
+        ops.ln_affine(x[r0:r0 + chunk], small[r0:r0 + chunk], 1e-6, sc0, sh0)
+    assert torch.equal(big, small)
+    # RMSNorm + RoPE in place on a strided column slice, ragged against the grid (rows beyond the grid are not rotated)
+    heads = dim // 128
+    grid = (5, 20, rows // 100 - 3)
+    tab = torch.from_numpy(np.ascontiguousarray(ops.rope_table(128))).cuda()
+    wq, wk = (1 + 0.1 * rnd(dim, seed=4).float()).to(BF), (1 + 0.1 * rnd(dim, seed=5).float()).to(BF)
+    qkv = rnd(rows, 3 * dim, seed=3)
+    a, b = qkv.clone(), qkv.clone()
+    ops.rmsnorm_rope(a[:, :dim], 1e-6, wq, tab, grid, 7)
+    ops.rmsnorm_rope(a[:, dim:2 * dim], 1e-6, wk)
+    for r0 in range(0, rows, chunk):
+        ops.rmsnorm_rope(b[r0:r0 + chunk, :dim], 1e-6, wq, tab, grid, 7 + r0)
+        ops.rmsnorm_rope(b[r0:r0 + chunk, dim:2 * dim], 1e-6, wk)
+    assert torch.equal(a, b)
+    a, b = qkv.clone(), qkv.clone()
+    ka = torch.full((heads,), -1.0, dtype=torch.float32, device="cuda")
+    ops.qk_norm_rope(a, dim, 1e-6, wq, wk, tab, grid, 7, ka)
+    kb = torch.zeros(heads, dtype=torch.float32, device="cuda")
+    for r0 in range(0, rows, chunk):
+        kc = torch.empty(heads, dtype=torch.float32, device="cuda")
+        ops.qk_norm_rope(b[r0:r0 + chunk], dim, 1e-6, wq, wk, tab, grid, 7 + r0, kc)
+        kb = torch.maximum(kb, kc)
+    ops.sync_check()
+    assert torch.equal(a, b) and torch.equal(a[:, 2 * dim:], qkv[:, 2 * dim:])
+    assert torch.allclose(ka, kb, rtol=1e-6)
