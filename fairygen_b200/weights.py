@@ -86,7 +86,7 @@ def packed_tensors(engine) -> List[torch.Tensor]:
              "b_tproj", "w_head", "b_head", "head_mod", "mods_all"]
     out = [getattr(engine, n) for n in names]
     for b in engine.blocks:
-        out.extend(getattr(b, n) for n in b.__slots__)
+        out.extend(getattr(b, n) for n in b.__slots__ if n != "private")   # `private` is the block's copy-on-write bookkeeping
     return out
 
 
