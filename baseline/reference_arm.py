@@ -258,14 +258,17 @@ def attn_vs_library(fg, cfg, tokens: int, text_len: int, dev, iters: int = 5) ->
         o = torch.empty(tokens, d, device=dev, dtype=torch.bfloat16)
         kmax2 = torch.zeros(H, device=dev, dtype=torch.float32)
 
-        def ours_with_bound_pass():   # a caller without the fused q/k norm pass computes the key bound separately
+        qmax2 = torch.zeros(H, device=dev, dtype=torch.float32)
+
+        def ours_with_bound_pass():   # a caller without the fused q/k norm pass computes the key bound separately (per-row query bounds)
             ops.head_norm_max(k, kmax2, H)
             ops.attention(q, k, v, o, H, kmax2=kmax2)
 
-        def ours():   # as the engine runs it: the key bound is a by-product of fgb_qk_norm_rope (self) / cached with the context K|V (cross)
-            ops.attention(q, k, v, o, H, kmax2=kmax2)
+        def ours():   # as the engine runs it: both bounds are by-products of the norm kernels in front (the key bound of the cross-attention is cached with the context K|V)
+            ops.attention(q, k, v, o, H, kmax2=kmax2, qmax2=qmax2)
 
         ops.head_norm_max(k, kmax2, H)
+        ops.head_norm_max(q, qmax2, H)
         q3, k3, v3 = q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0)
         qh, kh, vh = (t.view(-1, H, 128).transpose(0, 1).unsqueeze(0) for t in (q, k, v))
         saved = wd.FLASH_ATTN_2_AVAILABLE

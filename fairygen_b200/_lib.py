@@ -29,7 +29,10 @@ SIGNATURES = {
     "fgb_gemm_dgrad_ex": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _I64, _I32, _P]),
     "fgb_attn_fwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P]),
     "fgb_attn_fwd_ex": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _I64, _P, _I64, _P]),
-    "fgb_qk_norm_rope": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "fgb_qk_norm_rope": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "fgb_rmsnorm_hmax": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
+    "fgb_attn_fwd_bounded_qk": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _P, _I64, _P, _I64,
+                                               ctypes.POINTER(c_void_p), _I32, _I32, _I32, _P]),
     "fgb_head_norm_max": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
     "fgb_attn_set_stats": (ctypes.c_int, [_P, _P]),
     "fgb_attn_fwd_bounded": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _P, _I64, _P, _I64,
@@ -52,7 +55,7 @@ SIGNATURES = {
     "fgb_gemm_streamk_tune": (ctypes.c_int, [_P, _I32, ctypes.c_double]),
     "fgb_sp_stats_barrier": (ctypes.c_int, [_P, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), _P, _I32, _I32, _P, _I32, _I32, _I32,
                                             _I32, _P, _P]),
-    "fgb_recv_norm_rope": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, _F, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
+    "fgb_recv_norm_rope": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, _F, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "fgb_attn_fwd_scatter": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, ctypes.POINTER(c_void_p), _I32, _I64, _I32, _I32, _I32, _I32,
                                             _I32, _F, _P, _I64, _P]),
     "fgb_gemm_dgrad": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P]),

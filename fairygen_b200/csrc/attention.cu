@@ -30,6 +30,25 @@
 
 namespace fgb {
 
+#ifndef FGB_ATTN_TRACE
+#define FGB_ATTN_TRACE 0
+#endif
+#if FGB_ATTN_TRACE
+// Debug build only (make EXTRA=-DFGB_ATTN_TRACE=1): softmax thread 0 of CTA 0 stamps the phases of its first items with the
+// global nanosecond timer; tools/kcheck (KCHECK_TRACE=1) prints them through fgb_debug_attn_trace.
+__device__ unsigned long long g_attn_trace[16 * 16];
+__device__ __forceinline__ void trace_stamp(uint32_t item, int slot) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && item < 16) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_attn_trace[item * 16 + slot] = t;
+  }
+}
+#define FGB_TRACE(item, slot) trace_stamp(item, slot)
+#else
+#define FGB_TRACE(item, slot)
+#endif
+
 // EMU: of every 8 score pairs, EMU are exponentiated by exp2_emulated, the rest by MUFU.EX2.
 // PAIR: two CTAs of a cluster (one TPC) work on 512 query rows of one head with tcgen05.mma.cta_group::2: every score / PV
 // MMA has M = 256 (tile i of both CTAs), each CTA stages only HALF of every K tile (64 of its 128 keys) and half of every V
@@ -400,6 +419,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint32_t it = 0;
     for (int w = w0; w < p.n_items; w += w_stride, ++it) {
     decode_item(w);
+    FGB_TRACE(it, 0);
     m[0] = m[1] = -INFINITY;
     l[0] = l[1] = 0.f;
     if (PAIR) {
@@ -409,8 +429,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     // ---- bounded-score softmax: a fixed per-row reference instead of a running maximum (AttnParams::kmax)
     int mode = 2;   // 0: reference from the Cauchy-Schwarz bound, 1: anchored on the first tile's maximum, 2: running maximum
-    if (p.kmax != nullptr) {
+    bool head_bound = false;
+    if (p.kmax != nullptr && p.qmax != nullptr) {
+      // head-level bound: one reference for all rows, nothing to read from the Q tile, nothing to agree on
+      const float b = sqrtf(__ldg(p.qmax + head) * __ldg(p.kmax + head)) * p.scale_log2 * 1.0001f;
+      if (b <= kBoundFixedMax) {     // NaN fails
+        head_bound = true;
+        mode = 0;
+        m[0] = m[1] = b <= kBoundDirect ? b : kWindowLo - b;
+        if (p.stats != nullptr && threadIdx.x == 0) atomicAdd(p.stats + 0, 1);
+      }
+    }
+    if (p.kmax != nullptr && !head_bound) {
       mbar_wait(q_full, it & 1);
+      FGB_TRACE(it, 1);
       const float kmax2 = __ldg(p.kmax + head);   // max_j ||k_j||^2 of this head (fgb_head_norm_max)
       float bnd[2];
       bool ok = true;
@@ -457,6 +489,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       if (p.stats != nullptr && threadIdx.x == 0) atomicAdd(p.stats + mode, 1);
     }
+    FGB_TRACE(it, 2);
 
     // One (KV tile j, query tile i) step of this thread. MODE and LAST are compile-time so that the steady-state loop of
     // each mode is one compact instruction stream (a runtime dispatch inside the loop cost instruction-cache misses):
@@ -543,7 +576,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int n_plain = tail_partial ? n_kv - 1 : n_kv;
       for (int j = 0; j < n_plain; ++j) {
         tile_step(mode_tag, TagFalse{}, j, 0);   // both warpgroups work on query tile 0 together, then on tile 1
+        if (j < 4) FGB_TRACE(it, 3 + 2 * j);
         tile_step(mode_tag, TagFalse{}, j, 1);
+        if (j < 4) FGB_TRACE(it, 4 + 2 * j);
       }
       if (tail_partial) {
         tile_step(mode_tag, TagTrue{}, n_kv - 1, 0);
@@ -584,27 +619,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           // stage the tile in shared memory (128-byte swizzle: chunk ^ (row & 7), conflict-free for one row per lane) and let
           // the TMA write full 128-byte lines: a per-thread store of 16 bytes per row touched 32 lines per warp instruction
           // and held the warps for ~2.8 us per work item (profiles/r02_ncu_attn_cross_before_tma_store.txt)
-          if (threadIdx.x == 0) tma_store_wait_read<0>();          // the previous tile's store has read the buffer
-          asm volatile("bar.sync 9, 256;" ::: "memory");
-          uint8_t* srow = smem_o + wg * kBoxBytes + r_local * 128;
-#pragma unroll 1
+          // both 32-column chunks are fetched and normalised into packed registers BEFORE the buffer hand-over, so that for the
+          // second tile this work overlaps the TMA store of the first one reading the staging buffer (an item's epilogue was
+          // 2.35 us of a 9.5 us cross-attention item, profiles/r02_attn_cross_trace.log)
+          uint32_t pko[32];
+#pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t orr[32];
             tmem_ld32(t_o + c * 32, orr);
             tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 o;
-              o.x = pack_bf16(__uint_as_float(orr[g * 8 + 0]) * inv_l, __uint_as_float(orr[g * 8 + 1]) * inv_l);
-              o.y = pack_bf16(__uint_as_float(orr[g * 8 + 2]) * inv_l, __uint_as_float(orr[g * 8 + 3]) * inv_l);
-              o.z = pack_bf16(__uint_as_float(orr[g * 8 + 4]) * inv_l, __uint_as_float(orr[g * 8 + 5]) * inv_l);
-              o.w = pack_bf16(__uint_as_float(orr[g * 8 + 6]) * inv_l, __uint_as_float(orr[g * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(srow + (((c * 4 + g) ^ (r_local & 7)) << 4)) = o;
-            }
+            for (int e = 0; e < 16; ++e)
+              pko[c * 16 + e] = pack_bf16(__uint_as_float(orr[2 * e]) * inv_l, __uint_as_float(orr[2 * e + 1]) * inv_l);
           }
+          if (threadIdx.x == 0) tma_store_wait_read<0>();          // the previous tile's store has read the buffer
+          asm volatile("bar.sync 9, 256;" ::: "memory");
+          uint8_t* srow = smem_o + wg * kBoxBytes + r_local * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(srow + ((g ^ (r_local & 7)) << 4)) = make_uint4(pko[4 * g], pko[4 * g + 1], pko[4 * g + 2], pko[4 * g + 3]);
           fence_proxy_async_smem();
           asm volatile("bar.sync 9, 256;" ::: "memory");
-          if (threadIdx.x == 0) {
+          if (threadIdx.x == 0) {      // (one store per warpgroup behind 128-thread barriers measured slower: profiles/r02_attn_head_bound_ab.log)
             tma_store_2d(&tmap_o, smem_o, head * 128, q0 + i * kTile);                    // rows >= s_q are clipped by the tensor map
             tma_store_2d(&tmap_o, smem_o + kBoxBytes, head * 128 + 64, q0 + i * kTile);
             tma_store_commit();
@@ -630,7 +666,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
+      FGB_TRACE(it, 11 + i);
     }
+    FGB_TRACE(it, 13);
     g0 += n_kv;
     }   // items
     if (threadIdx.x == 0) tma_store_wait<0>();
@@ -763,7 +801,7 @@ extern "C" int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s
 static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                          int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
                          void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* const* o_peers,
-                         int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, const void* kmax, void* stream) {
+                         int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, const void* kmax, const void* qmax, void* stream) {
   using namespace fgb;
   FGB_CHECK_ARG(ctx, "fgb_attn_fwd: ctx is NULL");
   FGB_CHECK_ARG(q && k && v && (o || o_peers), "fgb_attn_fwd: NULL tensor pointer");
@@ -805,6 +843,7 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   p.ld_lse = ld_lse;
   p.tma_out = o_peers ? 0 : 1;
   p.kmax = static_cast<const float*>(kmax);
+  p.qmax = kmax ? static_cast<const float*>(qmax) : nullptr;
   p.stats = kmax ? ctx->attn_stats : nullptr;
   p.rows_per_peer = o_peers ? rows_per_peer : 0;
   p.col_offset = col_offset;
@@ -859,6 +898,12 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
   return FGB_OK;
 }
 
+#if FGB_ATTN_TRACE
+extern "C" int fgb_debug_attn_trace(unsigned long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, fgb::g_attn_trace, sizeof(unsigned long long) * (n < 256 ? n : 256)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 extern "C" int fgb_attn_set_stats(fgb_ctx* ctx, void* counts_dev) {
   if (!ctx) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_set_stats: ctx is NULL");
   if (counts_dev && (reinterpret_cast<uintptr_t>(counts_dev) & 3u)) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_set_stats: unaligned");
@@ -870,7 +915,7 @@ extern "C" int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const v
                                int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
                                void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* stream) {
   return attn_fwd_impl(ctx, q, ldq, k, ldk, v, ldv, o, ldo, s_q, s_kv, heads, scale, lse, ld_lse, workspace, workspace_bytes, nullptr, 0,
-                       0, 0, nullptr, stream);
+                       0, 0, nullptr, nullptr, stream);
 }
 
 extern "C" int fgb_attn_fwd_bounded(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -879,7 +924,17 @@ extern "C" int fgb_attn_fwd_bounded(fgb_ctx* ctx, const void* q, int64_t ldq, co
                                     void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, void* stream) {
   if (!kmax) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_fwd_bounded: kmax is NULL");
   return attn_fwd_impl(ctx, q, ldq, k, ldk, v, ldv, o, ldo, s_q, s_kv, heads, scale, lse, ld_lse, workspace, workspace_bytes, o_peers,
-                       n_peers, rows_per_peer, col_offset, kmax, stream);
+                       n_peers, rows_per_peer, col_offset, kmax, nullptr, stream);
+}
+
+extern "C" int fgb_attn_fwd_bounded_qk(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                       int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
+                                       const void* kmax, const void* qmax, void* lse, int64_t ld_lse, void* workspace,
+                                       int64_t workspace_bytes, void* const* o_peers, int32_t n_peers, int32_t rows_per_peer,
+                                       int32_t col_offset, void* stream) {
+  if (!kmax) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_fwd_bounded_qk: kmax is NULL");
+  return attn_fwd_impl(ctx, q, ldq, k, ldk, v, ldv, o, ldo, s_q, s_kv, heads, scale, lse, ld_lse, workspace, workspace_bytes, o_peers,
+                       n_peers, rows_per_peer, col_offset, kmax, qmax, stream);
 }
 
 extern "C" int fgb_attn_fwd_scatter(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -888,7 +943,7 @@ extern "C" int fgb_attn_fwd_scatter(fgb_ctx* ctx, const void* q, int64_t ldq, co
                                     int64_t workspace_bytes, void* stream) {
   if (!o_peers) return fgb::set_error(FGB_ERR_INVALID, "fgb_attn_fwd_scatter: o_peers is NULL");
   return attn_fwd_impl(ctx, q, ldq, k, ldk, v, ldv, nullptr, ldo, s_q, s_kv, heads, scale, nullptr, 0, workspace, workspace_bytes, o_peers,
-                       n_peers, rows_per_peer, col_offset, nullptr, stream);
+                       n_peers, rows_per_peer, col_offset, nullptr, nullptr, stream);
 }
 
 extern "C" int fgb_attn_fwd(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,

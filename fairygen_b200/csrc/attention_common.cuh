@@ -49,6 +49,12 @@ struct AttnParams {
   //           R_i = max(B_i - 100, min(B_i, m0 + 20)), valid when B_i - m0 <= 220
   //   mode 2: a CTA with a row that fails both runs the running-max path. stats (optional, int32[3]) counts CTAs per mode.
   const float* kmax;
+  // Optional qmax[head] = max_i ||q_i||^2 over ALL query rows of the head (a by-product of the q/k norm kernels). When
+  // B_head = sqrt(qmax·kmax)·scale·log2e <= 110 the whole head runs mode 0 with ONE reference for every row (R = B_head, or
+  // 120 - B_head above 60): no per-row norm pass over the Q tile and no CTA vote at the start of each work item — 1.3 us of a
+  // 9.5 us cross-attention item (profiles/r02_attn_cross_trace.log). P, l and O all carry 8 exponent bits, so a looser
+  // reference costs no precision inside the window. Heads that fail the test take the per-row path above.
+  const float* qmax;
   int32_t* stats;
   int32_t tma_out;   // 1: `o` is written through the output tensor map (staged tiles, full lines); 0: per-row stores (peers / partials)
 };

@@ -100,10 +100,23 @@ template <int NV, bool SCATTER>
 __global__ void __launch_bounds__(kRowWarps * 32)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float eps,
                     const __nv_bfloat16* __restrict__ weight, const float2* __restrict__ rope_tab, int gf, int gh,
-                    int gw, int token_offset, const ScatterSpec sc) {
+                    int gw, int token_offset, const ScatterSpec sc, float* __restrict__ hmax2 = nullptr) {
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
+  // hmax2 (optional): hmax2[h] = max over rows of ||out[row, h*128 : +128]||^2 — the query bound of fgb_attn_fwd_bounded_qk
+  __shared__ float hred[kRowWarps][2 * NV];
+  if (hmax2 != nullptr) {
+    if ((lane & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) hred[threadIdx.x >> 5][2 * i + (lane >> 4)] = 0.f;
+    }
+    if (row >= rows) {     // the block reduction below needs every warp
+      __syncthreads();
+      return;
+    }
+  } else if (row >= rows) {
+    return;
+  }
   constexpr int D = NV * 256;
   uint4* xr = reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * ldx);
   uint4 v[NV];
@@ -160,6 +173,14 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
       }
     }
     const uint4 out = make_uint4(o[0], o[1], o[2], o[3]);
+    if (!SCATTER && hmax2 != nullptr) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ss += bf16_lo(o[j]) * bf16_lo(o[j]) + bf16_hi(o[j]) * bf16_hi(o[j]);
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
+      if ((lane & 15) == 0) hred[threadIdx.x >> 5][2 * i + (lane >> 4)] = ss;
+    }
     if (SCATTER) {
       // fused Ulysses exchange: the normalised, rotated head slice goes straight to the peer that owns the head
       const int col = (i * 32 + lane) * 8;
@@ -174,6 +195,16 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
       xr[i * 32 + lane] = out;
     }
   }
+  if (!SCATTER && hmax2 != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < 2 * NV) {
+      float mx = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) mx = fmaxf(mx, hred[w][threadIdx.x]);
+      if (mx > __ldcg(hmax2 + threadIdx.x))
+        atomicMax(reinterpret_cast<unsigned int*>(hmax2) + threadIdx.x, __float_as_uint(mx));   // non-negative floats order like their bits
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -186,12 +217,12 @@ template <int NV>
 __global__ void __launch_bounds__(kRowWarps * 32)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int rows, float eps, const __nv_bfloat16* __restrict__ wq,
                     const __nv_bfloat16* __restrict__ wk, const float2* __restrict__ rope_tab, int gf, int gh, int gw, int token_offset,
-                    float* __restrict__ kmax2) {
+                    float* __restrict__ kmax2, float* __restrict__ qmax2) {
   const int lane = threadIdx.x & 31;
   constexpr int D = NV * 256;
-  float best[NV];
+  float best[NV], bestq[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) best[i] = 0.f;
+  for (int i = 0; i < NV; ++i) best[i] = bestq[i] = 0.f;
   for (int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5); row < rows; row += gridDim.x * kRowWarps) {
     float cs[4], sn[4];
     bool rotate = false;
@@ -245,31 +276,38 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int rows, float
           }
         }
         xr[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
-        if (g == 1) {
+        if (g == 1 || qmax2 != nullptr) {
           float ss = 0.f;
 #pragma unroll
           for (int j = 0; j < 4; ++j) ss += bf16_lo(o[j]) * bf16_lo(o[j]) + bf16_hi(o[j]) * bf16_hi(o[j]);
 #pragma unroll
           for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
-          best[i] = fmaxf(best[i], ss);
+          if (g == 1) best[i] = fmaxf(best[i], ss);
+          else bestq[i] = fmaxf(bestq[i], ss);
         }
       }
     }
   }
-  __shared__ float red[kRowWarps][2 * NV];
+  __shared__ float red[2][kRowWarps][2 * NV];
   if ((lane & 15) == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) red[threadIdx.x >> 5][2 * i + (lane >> 4)] = best[i];
+    for (int i = 0; i < NV; ++i) {
+      red[0][threadIdx.x >> 5][2 * i + (lane >> 4)] = best[i];
+      red[1][threadIdx.x >> 5][2 * i + (lane >> 4)] = bestq[i];
+    }
   }
   __syncthreads();
-  if (threadIdx.x < 2 * NV) {
-    float mx = 0.f;
+  if (threadIdx.x < 4 * NV) {
+    const int which = threadIdx.x / (2 * NV), h = threadIdx.x % (2 * NV);
+    float* dst = which == 0 ? kmax2 : qmax2;
+    if (dst != nullptr) {
+      float mx = 0.f;
 #pragma unroll
-    for (int w = 0; w < kRowWarps; ++w) mx = fmaxf(mx, red[w][threadIdx.x]);
-    // the maximum only grows: after the first CTAs almost nobody exceeds it any more, so look before the atomic (a stale,
-    // lower value just costs one redundant atomic)
-    if (mx > __ldcg(kmax2 + threadIdx.x))
-      atomicMax(reinterpret_cast<unsigned int*>(kmax2) + threadIdx.x, __float_as_uint(mx));   // non-negative floats order like their bits
+      for (int w = 0; w < kRowWarps; ++w) mx = fmaxf(mx, red[which][w][h]);
+      // the maximum only grows: after the first CTAs almost nobody exceeds it any more, so look before the atomic (a stale,
+      // lower value just costs one redundant atomic)
+      if (mx > __ldcg(dst + h)) atomicMax(reinterpret_cast<unsigned int*>(dst) + h, __float_as_uint(mx));   // non-negative floats order like their bits
+    }
   }
 }
 
@@ -570,13 +608,14 @@ sp_stats_barrier_kernel(PeerPtrs flags, PeerPtrs stats, float* __restrict__ rows
 __global__ void __launch_bounds__(256)
 recv_norm_rope_kernel(__nv_bfloat16* __restrict__ recv, int s_pad, int tokens, int hpr, const float* __restrict__ stats, int dim,
                       float eps, const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
-                      const float2* __restrict__ rope_tab, int gf, int gh, int gw, float* __restrict__ kmax2) {
+                      const float2* __restrict__ rope_tab, int gf, int gh, int gw, float* __restrict__ kmax2, float* __restrict__ qmax2) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int vecs = hpr * 16;                  // 16-byte vectors per group and row
   const int64_t ld = static_cast<int64_t>(3) * hpr * 128;
   const float inv_d = 1.0f / dim;
   float best[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // per pass (head pair) running max of ||k||^2; hpr <= 12
+  float bestq[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // the same for q (qmax2 != NULL)
   const int c0 = (lane & 15) * 4;
   for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < s_pad; t += warps) {
     float cs[4], sn[4];
@@ -618,30 +657,41 @@ recv_norm_rope_kernel(__nv_bfloat16* __restrict__ recv, int s_pad, int tokens, i
             }
           }
           row[c] = make_uint4(o[0], o[1], o[2], o[3]);
-          if (g == 1) {
+          if (g == 1 || qmax2 != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) ss += bf16_lo(o[j]) * bf16_lo(o[j]) + bf16_hi(o[j]) * bf16_hi(o[j]);
           }
         }
-        if (g == 1 && pass * 32 < vecs) {   // warp-uniform
+        if ((g == 1 || qmax2 != nullptr) && pass * 32 < vecs) {   // warp-uniform
 #pragma unroll
           for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
-          if (t < tokens) best[pass] = fmaxf(best[pass], ss);
+          if (g == 1) {
+            if (t < tokens) best[pass] = fmaxf(best[pass], ss);
+          } else {
+            bestq[pass] = fmaxf(bestq[pass], ss);     // padded query rows are computed (and discarded) too: keep them inside the bound
+          }
         }
       }
     }
   }
-  __shared__ float red[8][12];
+  __shared__ float red[2][8][12];
   if ((lane & 15) == 0) {
 #pragma unroll
-    for (int pass = 0; pass < 6; ++pass) red[threadIdx.x >> 5][2 * pass + (lane >> 4)] = best[pass];
+    for (int pass = 0; pass < 6; ++pass) {
+      red[0][threadIdx.x >> 5][2 * pass + (lane >> 4)] = best[pass];
+      red[1][threadIdx.x >> 5][2 * pass + (lane >> 4)] = bestq[pass];
+    }
   }
   __syncthreads();
-  if (static_cast<int>(threadIdx.x) < hpr) {
-    float mx = 0.f;
+  if (static_cast<int>(threadIdx.x) < 2 * 12) {
+    const int which = threadIdx.x / 12, h = threadIdx.x % 12;
+    float* dst = which == 0 ? kmax2 : qmax2;
+    if (h < hpr && dst != nullptr) {
+      float mx = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[w][threadIdx.x]);
-    atomicMax(reinterpret_cast<unsigned int*>(kmax2) + threadIdx.x, __float_as_uint(mx));   // non-negative floats order like their bits
+      for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[which][w][h]);
+      atomicMax(reinterpret_cast<unsigned int*>(dst) + h, __float_as_uint(mx));   // non-negative floats order like their bits
+    }
   }
 }
 
@@ -791,8 +841,8 @@ struct RmsStreamOp {
   const __nv_bfloat16 *w0, *w1;
   const float2* rope_tab;
   int gf, gh, gw, token_offset;
-  float* kmax2;
-  float best[SEGS == 2 ? NV : 1];
+  float *kmax2, *qmax2;
+  float best[SEGS == 2 ? NV : 1], bestq[SEGS == 2 ? NV : 1];
   __device__ __forceinline__ __nv_bfloat16* dst(int item) const {
     return SEGS == 2 ? x + static_cast<int64_t>(item >> 1) * ldx + (item & 1) * (NV * 256) : x + static_cast<int64_t>(item) * ldx;
   }
@@ -854,23 +904,30 @@ struct RmsStreamOp {
 #pragma unroll
         for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
         if (g == 1) best[i] = fmaxf(best[i], ss);
+        else bestq[i] = fmaxf(bestq[i], ss);
       }
     }
   }
   __device__ __forceinline__ void finish(int warp, int lane) {
     if (SEGS != 2) return;
-    __shared__ float red[kStreamWarps][2 * NV];
+    __shared__ float red[2][kStreamWarps][2 * NV];
     if (warp < kStreamWarps && (lane & 15) == 0) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) red[warp][2 * i + (lane >> 4)] = best[i];
+      for (int i = 0; i < NV; ++i) {
+        red[0][warp][2 * i + (lane >> 4)] = best[i];
+        red[1][warp][2 * i + (lane >> 4)] = bestq[i];
+      }
     }
     __syncthreads();
-    if (threadIdx.x < 2 * NV) {
-      float mx = 0.f;
+    if (threadIdx.x < 4 * NV) {
+      const int which = threadIdx.x / (2 * NV), h = threadIdx.x % (2 * NV);
+      float* dst = which == 0 ? kmax2 : qmax2;
+      if (dst != nullptr) {
+        float mx = 0.f;
 #pragma unroll
-      for (int w = 0; w < kStreamWarps; ++w) mx = fmaxf(mx, red[w][threadIdx.x]);
-      if (mx > __ldcg(kmax2 + threadIdx.x))
-        atomicMax(reinterpret_cast<unsigned int*>(kmax2) + threadIdx.x, __float_as_uint(mx));   // non-negative floats order like their bits
+        for (int w = 0; w < kStreamWarps; ++w) mx = fmaxf(mx, red[which][w][h]);
+        if (mx > __ldcg(dst + h)) atomicMax(reinterpret_cast<unsigned int*>(dst) + h, __float_as_uint(mx));   // non-negative floats order like their bits
+      }
     }
   }
 };
@@ -986,7 +1043,7 @@ extern "C" int fgb_rmsnorm_rope(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows
   if (rows >= kStreamMinRows && stream_enabled(1)) {
 #define FGB_RMSS_CASE(NV)                                                                                       \
   case NV: {                                                                                                    \
-    RmsStreamOp<NV, 1> op{xp, ldx, eps, wp, wp, tab, gf, gh, gw, token_offset, nullptr, {0.f}};                  \
+    RmsStreamOp<NV, 1> op{xp, ldx, eps, wp, wp, tab, gf, gh, gw, token_offset, nullptr, nullptr, {0.f}, {0.f}};                  \
     return launch_row_stream<NV>(ctx, s, rows, op);                                                             \
   }
     switch (dim / 256) {
@@ -1008,6 +1065,31 @@ extern "C" int fgb_rmsnorm_rope(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows
       return set_error(FGB_ERR_UNSUPPORTED, "rmsnorm: dim %d is not one of 256*{1,2,3,4,6,8,12,16,20}", dim);
   }
 #undef FGB_RMS_CASE
+  FGB_LAUNCH_CHECK("rmsnorm_rope_kernel");
+  return FGB_OK;
+}
+
+extern "C" int fgb_rmsnorm_hmax(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows, int32_t dim, float eps, const void* weight, void* hmax2,
+                               void* stream) {
+  FGB_CHECK_ARG(ctx && x && weight && hmax2, "fgb_rmsnorm_hmax: NULL argument");
+  FGB_CHECK_ARG(rows > 0 && dim > 0 && dim % 256 == 0, "fgb_rmsnorm_hmax: rows=%d dim=%d (dim must be a multiple of 256)", rows, dim);
+  FGB_CHECK_ARG(ldx % 8 == 0 && aligned16(x) && aligned16(weight), "fgb_rmsnorm_hmax: operands must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FGB_CUDA(cudaMemsetAsync(hmax2, 0, sizeof(float) * (dim / 128), s));
+  dim3 grid((rows + kRowWarps - 1) / kRowWarps);
+  ScatterSpec none{};
+#define FGB_RMSH_CASE(NV)                                                                                        \
+  case NV:                                                                                                       \
+    rmsnorm_rope_kernel<NV, false><<<grid, kRowWarps * 32, 0, s>>>(static_cast<bf16*>(x), ldx, rows, eps, static_cast<const bf16*>(weight), \
+                                                                   nullptr, 1, 1, 1, 0, none, static_cast<float*>(hmax2)); \
+    break;
+  switch (dim / 256) {
+    FGB_RMSH_CASE(1) FGB_RMSH_CASE(2) FGB_RMSH_CASE(3) FGB_RMSH_CASE(4) FGB_RMSH_CASE(6) FGB_RMSH_CASE(8) FGB_RMSH_CASE(12) FGB_RMSH_CASE(16)
+    FGB_RMSH_CASE(20)
+    default:
+      return set_error(FGB_ERR_UNSUPPORTED, "rmsnorm: dim %d is not one of 256*{1,2,3,4,6,8,12,16,20}", dim);
+  }
+#undef FGB_RMSH_CASE
   FGB_LAUNCH_CHECK("rmsnorm_rope_kernel");
   return FGB_OK;
 }
@@ -1214,7 +1296,7 @@ extern "C" int fgb_head_norm_max(fgb_ctx* ctx, const void* x, int64_t ldx, int32
 
 extern "C" int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t rows, int32_t dim, float eps, const void* wq, const void* wk,
                                const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, int32_t token_offset, void* kmax2,
-                               void* stream) {
+                               void* qmax2, void* stream) {
   FGB_CHECK_ARG(ctx && qkv && wq && wk && kmax2, "fgb_qk_norm_rope: NULL argument");
   FGB_CHECK_ARG(rows > 0 && dim > 0 && dim % 256 == 0 && ld >= 2 * static_cast<int64_t>(dim) && ld % 8 == 0, "fgb_qk_norm_rope: rows=%d dim=%d",
                 rows, dim);
@@ -1224,6 +1306,8 @@ extern "C" int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t row
                   "fgb_qk_norm_rope: grid (%d,%d,%d) outside the RoPE table", gf, gh, gw);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   FGB_CUDA(cudaMemsetAsync(kmax2, 0, sizeof(float) * (dim / 128), s));
+  if (qmax2) FGB_CUDA(cudaMemsetAsync(qmax2, 0, sizeof(float) * (dim / 128), s));
+  float* qp = static_cast<float*>(qmax2);
   const int grid = (rows + kRowWarps - 1) / kRowWarps;   // one row per warp: many short CTAs keep more loads in flight than a grid-stride loop
   bf16* xp = static_cast<bf16*>(qkv);
   const bf16* wqp = static_cast<const bf16*>(wq);
@@ -1233,7 +1317,7 @@ extern "C" int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t row
   if (rows >= kStreamMinRows && stream_enabled(1)) {
 #define FGB_QKS_CASE(NV)                                                                                        \
   case NV: {                                                                                                    \
-    RmsStreamOp<NV, 2> op{xp, ld, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp, {0.f}};                      \
+    RmsStreamOp<NV, 2> op{xp, ld, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp, qp, {0.f}, {0.f}};                      \
     return launch_row_stream<NV>(ctx, s, 2 * rows, op);                                                         \
   }
     switch (dim / 256) {
@@ -1245,7 +1329,7 @@ extern "C" int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t row
   }
 #define FGB_QK_CASE(NV)                                                                                                            \
   case NV:                                                                                                                         \
-    qk_norm_rope_kernel<NV><<<grid, kRowWarps * 32, 0, s>>>(xp, ld, rows, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp);         \
+    qk_norm_rope_kernel<NV><<<grid, kRowWarps * 32, 0, s>>>(xp, ld, rows, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp, qp);     \
     break;
   switch (dim / 256) {
     FGB_QK_CASE(1) FGB_QK_CASE(2) FGB_QK_CASE(3) FGB_QK_CASE(4) FGB_QK_CASE(6) FGB_QK_CASE(8) FGB_QK_CASE(12) FGB_QK_CASE(16) FGB_QK_CASE(20)
@@ -1278,8 +1362,9 @@ extern "C" int fgb_sp_stats_barrier(fgb_ctx* ctx, void* const* peer_flags, void*
 
 extern "C" int fgb_recv_norm_rope(fgb_ctx* ctx, void* recv, int32_t s_pad, int32_t tokens, int32_t hpr, const void* stats, int32_t dim,
                                   float eps, const void* wq, const void* wk, const void* rope_tab, int32_t gf, int32_t gh, int32_t gw,
-                                  void* kmax2, void* stream) {
+                                  void* kmax2, void* qmax2, void* stream) {
   FGB_CHECK_ARG(ctx && recv && stats && wq && wk && kmax2, "fgb_recv_norm_rope: NULL argument");
+  if (qmax2) FGB_CUDA(cudaMemsetAsync(qmax2, 0, sizeof(float) * hpr, static_cast<cudaStream_t>(stream)));
   FGB_CHECK_ARG(s_pad > 0 && tokens > 0 && tokens <= s_pad && hpr > 0 && hpr <= 12 && dim > 0, "fgb_recv_norm_rope: s_pad=%d tokens=%d hpr=%d",
                 s_pad, tokens, hpr);
   FGB_CHECK_ARG(aligned16(recv) && aligned16(wq) && aligned16(wk), "fgb_recv_norm_rope: operands must be 16-byte aligned");
@@ -1290,7 +1375,7 @@ extern "C" int fgb_recv_norm_rope(fgb_ctx* ctx, void* recv, int32_t s_pad, int32
   if (grid > ctx->sm_count * 6) grid = ctx->sm_count * 6;
   recv_norm_rope_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<bf16*>(recv), s_pad, tokens, hpr, static_cast<const float*>(stats), dim, eps, static_cast<const bf16*>(wq),
-      static_cast<const bf16*>(wk), static_cast<const float2*>(rope_tab), gf, gh, gw, static_cast<float*>(kmax2));
+      static_cast<const bf16*>(wk), static_cast<const float2*>(rope_tab), gf, gh, gw, static_cast<float*>(kmax2), static_cast<float*>(qmax2));
   FGB_LAUNCH_CHECK("recv_norm_rope_kernel");
   return FGB_OK;
 }

@@ -148,6 +148,7 @@ class WanDiTEngine:
                 ts=torch.zeros(2, dtype=torch.float32, device=dev), emb=e(2, cfg.freq_dim), t0=e(2, d), t0s=e(2, d),
                 t=e(2, d), ts_silu=e(2, d), tmod=e(2, 6 * d), mod_tab=e(2, L, 6 * d), head_tab=e(2, 2 * d),
                 kmax2=torch.zeros(cfg.num_heads, dtype=torch.float32, device=dev),
+                qmax2=torch.zeros(2, cfg.num_heads, dtype=torch.float32, device=dev),   # head-level query bounds: [self, cross]
                 sk=ops.gemm_workspace(dev),    # stream-K tail of the block's GEMMs (all launches of a forward are on one stream)
             )
             if self.sp is not None:
@@ -309,8 +310,8 @@ class WanDiTEngine:
                 k("gemm_qkv", ops.gemm, a, b.wqkv, b.bqkv, qkv, sk_ws=sk)
                 if sp is None:
                     # q and k normalised + rotated and the key bound of the bounded softmax in one pass over the fused rows
-                    k("rmsnorm_rope", ops.qk_norm_rope, qkv, d, cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0, ws["kmax2"])
-                    k("attn_self", ops.attention, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, H, kmax2=ws["kmax2"])
+                    k("rmsnorm_rope", ops.qk_norm_rope, qkv, d, cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0, ws["kmax2"], ws["qmax2"][0])
+                    k("attn_self", ops.attention, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, H, kmax2=ws["kmax2"], qmax2=ws["qmax2"][0])
                 else:
                     k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)
                     k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, d:2 * d], cfg.eps, b.nk, self.rope_tab, grid, tok0)
@@ -319,8 +320,8 @@ class WanDiTEngine:
             # cross-attention branch (DIT:226)
             k("ln_affine", ops.ln_affine, x, a, cfg.eps, b.n3w, b.n3b)
             k("gemm_cross_q", ops.gemm, a, b.cwq, b.cbq, cq, sk_ws=sk)
-            k("rmsnorm", ops.rmsnorm_rope, cq, cfg.eps, b.cnq)
-            k("attn_cross", ops.attention, cq, kv_all[i][:, :d], kv_all[i][:, d:], o, H, kmax2=kmax_all[i])
+            k("rmsnorm", ops.rmsnorm_rope, cq, cfg.eps, b.cnq, hmax2=ws["qmax2"][1])
+            k("attn_cross", ops.attention, cq, kv_all[i][:, :d], kv_all[i][:, d:], o, H, kmax2=kmax_all[i], qmax2=ws["qmax2"][1])
             k("gemm_cross_o", ops.gemm, o, b.cwo, b.cbo, x, EPI_RESIDUAL, sk_ws=sk)
             # feed-forward branch (DIT:227-228)
             k("ln_modulate", ops.ln_modulate, x, a, cfg.eps, m0[3], m0[4], m1[3], m1[4], n_first)

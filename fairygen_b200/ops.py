@@ -148,16 +148,22 @@ def attention_workspace(q_rows: int, kv_rows: int, heads: int, device) -> Option
     return ws
 
 
-def qk_norm_rope(qkv, dim: int, eps: float, wq, wk, rope_tab, grid, token_offset: int, kmax2):
+def _head_max(t, heads: int, name: str):
+    if t is not None and (t.dtype != torch.float32 or t.numel() != heads or not t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous float32 [{heads}] tensor")
+
+
+def qk_norm_rope(qkv, dim: int, eps: float, wq, wk, rope_tab, grid, token_offset: int, kmax2, qmax2=None):
     """In place on columns [0, 2*dim) of the fused q|k|v rows: RMSNorm + weight + RoPE of q and of k (one pass), and
-    kmax2[h] = max over rows of ||k[row, h]||^2 (fp32 [dim/128])."""
+    kmax2[h] = max over rows of ||k[row, h]||^2 (fp32 [dim/128]); qmax2 (optional) the same for q."""
     ld = _rowmajor(qkv, "qkv")
     if qkv.shape[1] < 2 * dim or kmax2.dtype != torch.float32 or kmax2.numel() != dim // 128 or not kmax2.is_contiguous():
         raise ValueError(f"qk_norm_rope: qkv {tuple(qkv.shape)} dim {dim} kmax2 {tuple(kmax2.shape)}")
+    _head_max(qmax2, dim // 128, "qmax2")
     _vec(wq, dim, "wq")
     _vec(wk, dim, "wk")
     _lib.check(_lib.lib().fgb_qk_norm_rope(_h(qkv).handle, _p(qkv), ld, qkv.shape[0], dim, eps, _p(wq), _p(wk), _p(rope_tab), grid[0], grid[1],
-                                           grid[2], token_offset, _p(kmax2), _stream()), "fgb_qk_norm_rope")
+                                           grid[2], token_offset, _p(kmax2), _p(qmax2), _stream()), "fgb_qk_norm_rope")
 
 
 def head_norm_max(k, out_f32, heads: int):
@@ -170,7 +176,7 @@ def head_norm_max(k, out_f32, heads: int):
 
 
 def attention(q, k, v, out, heads: int, scale: Optional[float] = None, lse: Optional[torch.Tensor] = None,
-              kmax2: Optional[torch.Tensor] = None):
+              kmax2: Optional[torch.Tensor] = None, qmax2: Optional[torch.Tensor] = None):
     """out = softmax(q k^T scale) v per 128-wide head; q/out [s_q, heads*128], k/v [s_kv, heads*128].
     lse (optional, fp32 [heads, ld] with ld >= s_q, ld % 64 == 0) receives the log2-domain log-sum-exp rows
     for the backward pass."""
@@ -188,9 +194,10 @@ def attention(q, k, v, out, heads: int, scale: Optional[float] = None, lse: Opti
     if kmax2 is not None:   # bounded-score softmax: fixed per-row reference from ||q_i||·max_j||k_j||, no running maximum
         if kmax2.dtype != torch.float32 or kmax2.numel() != heads or not kmax2.is_contiguous():
             raise ValueError("kmax2 must be a contiguous float32 [heads] tensor (head_norm_max of k)")
-        _lib.check(_lib.lib().fgb_attn_fwd_bounded(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), ldo, s_q, s_kv, heads, scale,
-                                                   _p(kmax2), _p(lse), 0 if lse is None else lse.shape[1], _p(ws),
-                                                   0 if ws is None else ws.numel(), None, 0, 0, 0, _stream()), "fgb_attn_fwd_bounded")
+        _head_max(qmax2, heads, "qmax2")
+        _lib.check(_lib.lib().fgb_attn_fwd_bounded_qk(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), ldo, s_q, s_kv, heads, scale,
+                                                      _p(kmax2), _p(qmax2), _p(lse), 0 if lse is None else lse.shape[1], _p(ws),
+                                                      0 if ws is None else ws.numel(), None, 0, 0, 0, _stream()), "fgb_attn_fwd_bounded_qk")
         return out
     _lib.check(_lib.lib().fgb_attn_fwd_ex(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, _p(out), ldo, s_q, s_kv, heads,
                                           scale, _p(lse), 0 if lse is None else lse.shape[1], _p(ws),
@@ -243,11 +250,18 @@ def ln_affine(x, out, eps, weight, bias):
     return out
 
 
-def rmsnorm_rope(x, eps, weight, rope_tab=None, grid=(1, 1, 1), token_offset=0):
-    """In place on x [rows, dim] (may be a strided column slice of a wider buffer)."""
+def rmsnorm_rope(x, eps, weight, rope_tab=None, grid=(1, 1, 1), token_offset=0, hmax2=None):
+    """In place on x [rows, dim] (may be a strided column slice of a wider buffer). hmax2 (fp32 [dim/128], no RoPE only):
+    also leaves the per-head maximum of the squared norms of the output rows (fgb_rmsnorm_hmax)."""
     ldx = _rowmajor(x, "x")
     rows, dim = x.shape
     _vec(weight, dim, "weight")
+    if hmax2 is not None:
+        if rope_tab is not None:
+            raise ValueError("rmsnorm_rope: hmax2 is for the un-rotated form (the cross-attention query)")
+        _head_max(hmax2, dim // 128, "hmax2")
+        _lib.check(_lib.lib().fgb_rmsnorm_hmax(_h(x).handle, _p(x), ldx, rows, dim, eps, _p(weight), _p(hmax2), _stream()), "fgb_rmsnorm_hmax")
+        return x
     if rope_tab is not None and (rope_tab.dtype != torch.float32 or tuple(rope_tab.shape) != (1024, 64, 2) or not rope_tab.is_contiguous()):
         raise ValueError("rope_tab must be a contiguous float32 [1024, 64, 2] table")
     c = _h(x)
@@ -418,13 +432,13 @@ def sp_stats_barrier(device, flag_ptrs, stats_ptrs, rowsq, rows: int, s_pad: int
                                                _p(kmax2), hpr, world, rank, epoch, _p(status), _stream()), "fgb_sp_stats_barrier")
 
 
-def recv_norm_rope(recv, tokens: int, hpr: int, stats, dim: int, eps: float, wq, wk, rope_tab, grid, kmax2):
+def recv_norm_rope(recv, tokens: int, hpr: int, stats, dim: int, eps: float, wq, wk, rope_tab, grid, kmax2, qmax2=None):
     """RMSNorm (received full-row statistics) + weight slice + RoPE on the q, k groups of recv [s_pad, 3*hpr*128], in place;
-    kmax2[h] = max ||k||^2 over the first `tokens` rows."""
+    kmax2[h] = max ||k||^2 over the first `tokens` rows; qmax2 (optional) = max ||q||^2 over all rows."""
     if recv.dtype != BF16 or recv.dim() != 2 or recv.shape[1] != 3 * hpr * 128 or not recv.is_contiguous():
         raise ValueError(f"recv_norm_rope: recv {tuple(recv.shape)} hpr {hpr}")
     _lib.check(_lib.lib().fgb_recv_norm_rope(_h(recv).handle, _p(recv), recv.shape[0], tokens, hpr, _p(stats), dim, eps, _p(wq), _p(wk),
-                                             _p(rope_tab), grid[0], grid[1], grid[2], _p(kmax2), _stream()), "fgb_recv_norm_rope")
+                                             _p(rope_tab), grid[0], grid[1], grid[2], _p(kmax2), _p(qmax2), _stream()), "fgb_recv_norm_rope")
 
 
 def sp_barrier(device, flag_ptrs, world: int, rank: int, epoch: int):
@@ -432,7 +446,7 @@ def sp_barrier(device, flag_ptrs, world: int, rank: int, epoch: int):
 
 
 def attention_scatter(q, k, v, o_peer_ptrs, ldo: int, rows_per_peer: int, col_offset: int, heads: int, scale: Optional[float] = None,
-                      kmax2: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None):
+                      kmax2: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None, qmax2: Optional[torch.Tensor] = None):
     """attention() whose output rows go straight into the token-major o buffers of the ranks that own the tokens."""
     ldq, ldk, ldv = _rowmajor(q, "q"), _rowmajor(k, "k"), _rowmajor(v, "v")
     s_q, s_kv = q.shape[0], k.shape[0]
@@ -442,10 +456,11 @@ def attention_scatter(q, k, v, o_peer_ptrs, ldo: int, rows_per_peer: int, col_of
     c = _h(q)
     ws = attention_workspace(s_q, s_kv, heads, q.device)
     if kmax2 is not None:
-        _lib.check(_lib.lib().fgb_attn_fwd_bounded(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, None, ldo, s_q, s_kv, heads, scale,
-                                                   _p(kmax2), _p(lse), 0 if lse is None else lse.shape[1], _p(ws),
-                                                   0 if ws is None else ws.numel(), _ptr_array(o_peer_ptrs),
-                                                   len(o_peer_ptrs), rows_per_peer, col_offset, _stream()), "fgb_attn_fwd_bounded")
+        _head_max(qmax2, heads, "qmax2")
+        _lib.check(_lib.lib().fgb_attn_fwd_bounded_qk(c.handle, _p(q), ldq, _p(k), ldk, _p(v), ldv, None, ldo, s_q, s_kv, heads, scale,
+                                                      _p(kmax2), _p(qmax2), _p(lse), 0 if lse is None else lse.shape[1], _p(ws),
+                                                      0 if ws is None else ws.numel(), _ptr_array(o_peer_ptrs),
+                                                      len(o_peer_ptrs), rows_per_peer, col_offset, _stream()), "fgb_attn_fwd_bounded_qk")
         return
     if lse is not None:
         raise ValueError("attention_scatter: lse needs the bounded form (pass kmax2)")

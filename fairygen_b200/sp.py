@@ -193,11 +193,12 @@ class SequenceParallel:
                 k("sp_barrier", ops.sp_stats_barrier, qkv.device, ar.flag_ptrs[0], ar.stats_ptrs, ar.rowsq, rows, rows * self.world, kmax2,
                   hpr, self.world, self.rank, ar.epoch, ar.status)
                 h0 = self.rank * wloc
+                qmax2 = ws["qmax2"][0][:hpr] if "qmax2" in ws else None
                 k("rmsnorm_rope", ops.recv_norm_rope, ar.recv, tokens, hpr, ar.stats, heads * 128, eps, wq[h0:h0 + wloc], wk[h0:h0 + wloc],
-                  rope_tab, grid, kmax2)
+                  rope_tab, grid, kmax2, qmax2)
                 recv = ar.recv
                 k("attn_self", ops.attention_scatter, recv[:, :wloc], recv[:tokens, wloc:2 * wloc], recv[:tokens, 2 * wloc:], ar.o_ptrs,
-                  heads * 128, rows, self.rank * wloc, hpr, kmax2=kmax2)
+                  heads * 128, rows, self.rank * wloc, hpr, kmax2=kmax2, qmax2=qmax2)
                 k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[1], self.world, self.rank, ar.epoch)
                 return
             if qkv_gemm is None:

@@ -120,13 +120,25 @@ int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s_kv, int32_
 /* fgb_rmsnorm_rope on the q AND the k slice of fused q|k|v rows (columns [0, dim) and [dim, 2*dim) of qkv, row stride ld) plus
  * fgb_head_norm_max of the finished k, in one pass: the single-GPU self-attention prologue (DIT:140-144). */
 int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t rows, int32_t dim, float eps, const void* wq, const void* wk,
-                     const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, int32_t token_offset, void* kmax2_f32, void* stream);
+                     const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, int32_t token_offset, void* kmax2_f32, void* qmax2_f32 /* optional: the same maximum for q */, void* stream);
 int fgb_head_norm_max(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t rows, int32_t heads, void* out_f32, void* stream);
 int fgb_attn_set_stats(fgb_ctx* ctx, void* counts_dev_i32x3);
 int fgb_attn_fwd_bounded(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                          void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale, const void* kmax2,
                          void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* const* o_peers,
                          int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, void* stream);
+/* The same with qmax2[head] = max_i ||q[i, head]||^2 (optional, NULL = fgb_attn_fwd_bounded): a head whose bound
+ * sqrt(qmax2·kmax2)·scale·log2e <= 110 uses ONE reference for all its rows, so a work item starts without the per-row norm pass
+ * over the Q tile and without the CTA vote (1.3 us of a 9.5 us cross-attention item). fgb_qk_norm_rope / fgb_rmsnorm_hmax /
+ * fgb_recv_norm_rope leave qmax2 as a by-product; fgb_head_norm_max on q gives it to a standalone caller. */
+int fgb_attn_fwd_bounded_qk(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                            void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale, const void* kmax2,
+                            const void* qmax2, void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes,
+                            void* const* o_peers, int32_t n_peers, int32_t rows_per_peer, int32_t col_offset, void* stream);
+/* fgb_rmsnorm_rope without RoPE (the cross-attention query, DIT:176, 99-110) that also leaves hmax2[h] = max over rows of the
+ * squared norm of the OUTPUT head slice (fp32 [dim/128], zeroed by the call). */
+int fgb_rmsnorm_hmax(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows, int32_t dim, float eps, const void* weight, void* hmax2_f32,
+                     void* stream);
 
 /* Backward of fgb_attn_fwd(_ex): given dout = dL/do, writes dq [s_q, heads*128], dk and dv [s_kv, heads*128] (bf16).
  * The reference obtains this from torch autograd through flash_attention (DIT:27-60) during the stage-2 LoRA
@@ -254,7 +266,7 @@ int fgb_sp_stats_barrier(fgb_ctx* ctx, void* const* peer_flags, void* const* pee
                          void* kmax2, int32_t hpr, int32_t world, int32_t rank, int32_t epoch, void* status, void* stream);
 int fgb_recv_norm_rope(fgb_ctx* ctx, void* recv, int32_t s_pad, int32_t tokens, int32_t hpr, const void* stats, int32_t dim, float eps,
                        const void* wq, const void* wk, const void* rope_tab, int32_t gf, int32_t gh, int32_t gw, void* kmax2,
-                       void* stream);
+                       void* qmax2 /* optional, zeroed by the call */, void* stream);
 /* fgb_attn_fwd_ex whose output row of global token t goes to o_peers[t / rows_per_peer][(t % rows_per_peer) * ldo +
  * col_offset + head*128 ...] (col_offset = rank * heads * 128 for Ulysses). */
 int fgb_attn_fwd_scatter(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

@@ -66,7 +66,7 @@ def _emulated_ops(monkeypatch):
         out.copy_((ln(x, eps) * weight.float() + bias.float()).to(BF))
         return out
 
-    def rmsnorm_rope(x, eps, weight, rope_tab=None, grid=(1, 1, 1), token_offset=0):
+    def rmsnorm_rope(x, eps, weight, rope_tab=None, grid=(1, 1, 1), token_offset=0, hmax2=None):
         xf = x.float()
         y = ((xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(BF).float() * weight.float()).to(BF).float()
         if rope_tab is not None:
@@ -81,18 +81,22 @@ def _emulated_ops(monkeypatch):
             im = z[..., 0] * tab[:, None, :, 1] + z[..., 1] * tab[:, None, :, 0]
             y = torch.stack([re, im], -1).reshape(rows, dim)
         x.copy_(y.to(BF))
+        if hmax2 is not None:
+            hmax2.copy_(x.float().view(x.shape[0], -1, 128).pow(2).sum(-1).max(0).values)
         return x
 
     def head_norm_max(k, out_f32, heads):
         out_f32.copy_(k.float().view(k.shape[0], heads, 128).pow(2).sum(-1).max(0).values)
         return out_f32
 
-    def qk_norm_rope(qkv, dim, eps, wq, wk, rope_tab, grid, token_offset, kmax2):
+    def qk_norm_rope(qkv, dim, eps, wq, wk, rope_tab, grid, token_offset, kmax2, qmax2=None):
         rmsnorm_rope(qkv[:, :dim], eps, wq, rope_tab, grid, token_offset)
         rmsnorm_rope(qkv[:, dim:2 * dim], eps, wk, rope_tab, grid, token_offset)
         head_norm_max(qkv[:, dim:2 * dim], kmax2, dim // 128)
+        if qmax2 is not None:
+            head_norm_max(qkv[:, :dim], qmax2, dim // 128)
 
-    def attention(q, k, v, out, heads, scale=None, lse=None, kmax2=None):
+    def attention(q, k, v, out, heads, scale=None, lse=None, kmax2=None, qmax2=None):
         qf, kf, vf = (t.float().view(t.shape[0], heads, 128).transpose(0, 1) for t in (q, k, v))
         p = torch.softmax(qf @ kf.transpose(1, 2) / 128 ** 0.5, -1)
         out.copy_((p @ vf).transpose(0, 1).reshape(q.shape[0], heads * 128).to(BF))

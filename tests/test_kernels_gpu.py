@@ -438,6 +438,70 @@ def test_bounded_attention_reference_modes(env, scale_q, want_mode):
     assert (out.float() - 1).abs().max() < 8e-3
 
 
+@pytest.mark.parametrize("scale_q,want_mode", [(1.0, "bound_only"), (3.0, "bound_only"), (9.0, "first_tile_anchored"), (40.0, "running_max_fallback")])
+@pytest.mark.parametrize("s_q,s_kv", [(600, 1000), (1300, 512)])
+def test_head_level_query_bound(env, scale_q, want_mode, s_q, s_kv):
+    """fgb_attn_fwd_bounded_qk: with qmax2[h] = max_i ||q_i||^2 a head whose bound sqrt(qmax2 kmax2)·scale·log2e <= 110 runs every
+    row against ONE reference (no per-row norm pass, no CTA vote); heads above the window fall through to the per-row modes.
+    Same softmax as the per-row form and as the fp32 reference; log-sum-exp consistent; V == 1 gives exactly 1. One head is made
+    an outlier so that both branches run in one launch."""
+    ops, o = env
+    heads = 3
+    d = heads * 128
+    q, k, v = rnd(s_q, d, seed=1), rnd(s_kv, d, seed=2), rnd(s_kv, d, seed=3)
+    q[:, 128:256] *= scale_q                    # head 1 carries the large queries; heads 0 and 2 stay small
+    kmax2, qmax2 = (torch.empty(heads, dtype=torch.float32, device="cuda") for _ in range(2))
+    ops.head_norm_max(k, kmax2, heads)
+    ops.head_norm_max(q, qmax2, heads)
+    out, per_row = (torch.full((s_q, d), float("nan"), dtype=BF, device="cuda") for _ in range(2))
+    lse = torch.empty(heads, ops.stat_rows(s_q), dtype=torch.float32, device="cuda")
+    ops.attention_stats_reset(q.device)
+    ops.attention(q, k, v, out, heads, lse=lse, kmax2=kmax2, qmax2=qmax2)
+    ops.sync_check()
+    detail = ops.attention_stats_detail(q.device)
+    items = (s_q + 255) // 256
+    head_bound = (qmax2 * kmax2).sqrt() / math.sqrt(128) * math.log2(math.e)
+    print(f"scale_q {scale_q}: head bounds {[round(float(b), 1) for b in head_bound]}, CTAs per mode {detail}")
+    assert sum(detail.values()) == heads * items and detail[want_mode] >= items and detail["bound_only"] >= 2 * items
+    ops.attention(q, k, v, per_row, heads, kmax2=kmax2)
+    ops.sync_check()
+    ref = o.attention(q[None].float(), k[None].float(), v[None].float(), heads)[0]
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 6e-3 and rel_l2(out, per_row) < 4e-3
+    sc = torch.einsum("qhd,khd->hqk", q.float().view(s_q, heads, 128), k.float().view(s_kv, heads, 128)) / math.sqrt(128)
+    assert (lse[:, :s_q] - torch.logsumexp(sc, dim=-1) * math.log2(math.e)).abs().max() < 5e-3 * max(1.0, scale_q)
+    ops.attention(q, k, torch.ones_like(v), out, heads, kmax2=kmax2, qmax2=qmax2)
+    ops.sync_check()
+    assert (out.float() - 1).abs().max() < 8e-3
+
+
+def test_norm_kernels_leave_the_query_bound(env):
+    """qmax2 as a by-product: fgb_qk_norm_rope (per-warp and row-streaming path) and fgb_rmsnorm_hmax == fgb_head_norm_max of
+    their own output, and the normalised rows are unchanged by asking for it."""
+    ops, o = env
+    import numpy as np
+    tab = torch.from_numpy(np.ascontiguousarray(ops.rope_table(128))).cuda()
+    for rows, dim in ((300, 768), (2500, 3072)):
+        heads = dim // 128
+        wq, wk = (1 + 0.1 * rnd(dim, seed=4).float()).to(BF), (1 + 0.1 * rnd(dim, seed=5).float()).to(BF)
+        qkv = rnd(rows, 3 * dim, seed=3)
+        a, b = qkv.clone(), qkv.clone()
+        ka, kb, qa, want = (torch.full((heads,), -1.0, dtype=torch.float32, device="cuda") for _ in range(4))
+        ops.qk_norm_rope(a, dim, 1e-6, wq, wk, tab, (5, 10, 10), 3, ka, qa)
+        ops.qk_norm_rope(b, dim, 1e-6, wq, wk, tab, (5, 10, 10), 3, kb)
+        ops.head_norm_max(a[:, :dim], want, heads)
+        ops.sync_check()
+        assert torch.equal(a, b) and torch.equal(ka, kb) and torch.allclose(qa, want, rtol=1e-6)
+        x = rnd(rows, dim, seed=6)
+        y, z = x.clone(), x.clone()
+        hm = torch.full((heads,), -1.0, dtype=torch.float32, device="cuda")
+        ops.rmsnorm_rope(y, 1e-6, wq, hmax2=hm)
+        ops.rmsnorm_rope(z, 1e-6, wq)
+        ops.head_norm_max(y, want, heads)
+        ops.sync_check()
+        assert torch.equal(y, z) and torch.allclose(hm, want, rtol=1e-6)
+
+
 def test_attention_cta_pair_variant(env, monkeypatch):
     """The 2-CTA (tcgen05 cta_group::2) variant of the attention kernel, kept behind FGB_ATTN_PAIR=1 (it is slower on this
     workload, see csrc/attention.cu): same results as the default, including the key-split tail, ragged rows and all three

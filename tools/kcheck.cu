@@ -108,6 +108,10 @@ static void compare(const std::vector<bf16>& got, const std::vector<float>& ref,
          bad >= 0 ? __bfloat162float(got[bad]) : 0.f, bad >= 0 ? ref[bad] : 0.f, rel < 5e-3 ? "PASS" : "FAIL");
 }
 
+#ifdef KCHECK_TRACE
+extern "C" int fgb_debug_attn_trace(unsigned long long* host, int n);
+#endif
+
 int main(int argc, char** argv) {
   if (argc < 2) { printf("usage: kcheck gemm|attn ...\n"); return 1; }
   fgb_ctx* ctx = nullptr;
@@ -190,12 +194,17 @@ int main(int argc, char** argv) {
     printf("attn workspace %lld bytes\n", (long long)ws_bytes);
     // KCHECK_BOUNDED=1: bounded-score softmax (the engine's default): key-norm bound first, then fgb_attn_fwd_bounded
     float* kmax2 = nullptr;
+    float* qmax2 = nullptr;   // KCHECK_BOUNDED=2: also the head-level query bound (fgb_attn_fwd_bounded_qk)
     if (getenv("KCHECK_BOUNDED")) {
       CK(cudaMalloc(&kmax2, H * 4));
       FK(fgb_head_norm_max(ctx, k, W, SKV, H, kmax2, nullptr));
+      if (atoi(getenv("KCHECK_BOUNDED")) >= 2) {
+        CK(cudaMalloc(&qmax2, H * 4));
+        FK(fgb_head_norm_max(ctx, q, W, SQ, H, qmax2, nullptr));
+      }
     }
     auto run = [&]() {
-      if (kmax2) return fgb_attn_fwd_bounded(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, kmax2, lse, LDS, ws, ws_bytes, nullptr, 0, 0, 0, nullptr);
+      if (kmax2) return fgb_attn_fwd_bounded_qk(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, kmax2, qmax2, lse, LDS, ws, ws_bytes, nullptr, 0, 0, 0, nullptr);
       return fgb_attn_fwd_ex(ctx, q, W, k, W, v, W, o, W, SQ, SKV, H, scale, lse, LDS, ws, ws_bytes, nullptr);
     };
     FK(run());
@@ -238,6 +247,20 @@ int main(int argc, char** argv) {
       printf("attn s_q=%d s_kv=%d heads=%d: %.3f ms  %.1f TFLOP/s\n", SQ, SKV, H, ms,
              4.0 * SQ * SKV * (double)W / ms * 1e-9);
     }
+#ifdef KCHECK_TRACE
+    {   // debug library build (-DFGB_ATTN_TRACE=1): phase stamps of softmax thread 0 of CTA 0, first 16 items of the last launch
+      unsigned long long tr[256];
+      if (fgb_debug_attn_trace(tr, 256) == 0) {
+        for (int it = 1; it < 16; ++it) {
+          printf("item %2d: start +%5lld | q %5lld bound %5lld |", it, (long long)(tr[it * 16] - tr[(it - 1) * 16]),
+                 (long long)(tr[it * 16 + 1] - tr[it * 16]), (long long)(tr[it * 16 + 2] - tr[it * 16 + 1]));
+          for (int s = 3; s <= 10; ++s) printf(" %5lld", (long long)(tr[it * 16 + s] - tr[it * 16 + s - 1]));
+          printf(" | epi %5lld %5lld %5lld\n", (long long)(tr[it * 16 + 11] - tr[it * 16 + 10]),
+                 (long long)(tr[it * 16 + 12] - tr[it * 16 + 11]), (long long)(tr[it * 16 + 13] - tr[it * 16 + 12]));
+        }
+      }
+    }
+#endif
   } else if (!strcmp(argv[1], "attnbwd") && argc >= 5) {
     // timing only (parity lives in tests/test_kernels_gpu.py against torch autograd)
     int SQ = atoi(argv[2]), SKV = atoi(argv[3]), H = atoi(argv[4]);

@@ -59,11 +59,14 @@ def main():
             o = torch.empty_like(q)
             kmax2 = torch.zeros(H, device=dev, dtype=torch.float32)
             ops.head_norm_max(k, kmax2, H)
+            qmax2 = torch.zeros(H, device=dev, dtype=torch.float32)
+            ops.head_norm_max(q, qmax2, H)
+            use_q = os.environ.get("QMAX", "1") != "0"      # QMAX=0: per-row bounds only (A/B of the head-level bound)
             qh, kh, vh = (t.view(-1, H, 128).transpose(0, 1).unsqueeze(0) for t in (q, k, v))
             fl = 4.0 * S * s_kv * D
 
             def ours():
-                ops.attention(q, k, v, o, H, kmax2=kmax2)
+                ops.attention(q, k, v, o, H, kmax2=kmax2, qmax2=qmax2 if use_q else None)
 
             def ours_runmax():
                 ops.attention(q, k, v, o, H)
