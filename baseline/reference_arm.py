@@ -264,7 +264,10 @@ def attn_vs_library(fg, cfg, tokens: int, text_len: int, dev, iters: int = 5) ->
             ops.head_norm_max(k, kmax2, H)
             ops.attention(q, k, v, o, H, kmax2=kmax2)
 
-        def ours():   # as the engine runs it: both bounds are by-products of the norm kernels in front (the key bound of the cross-attention is cached with the context K|V)
+        def ours():   # as the engine runs it: the key bound is a by-product of fgb_qk_norm_rope (self) / cached with the context K|V (cross)
+            ops.attention(q, k, v, o, H, kmax2=kmax2)
+
+        def ours_head_bound():   # fgb_attn_fwd_bounded_qk with the head-level query bound given (engine: FGB_QMAX, off by default)
             ops.attention(q, k, v, o, H, kmax2=kmax2, qmax2=qmax2)
 
         ops.head_norm_max(k, kmax2, H)
@@ -287,7 +290,7 @@ def attn_vs_library(fg, cfg, tokens: int, text_len: int, dev, iters: int = 5) ->
                     return F.scaled_dot_product_attention(qh, kh, vh)
             return run
 
-        cands = {"ours_ms": ours, "ours_with_bound_pass_ms": ours_with_bound_pass}
+        cands = {"ours_ms": ours, "ours_with_bound_pass_ms": ours_with_bound_pass, "ours_head_bound_ms": ours_head_bound}
         if fa2_ok:
             cands["reference_flash_attention[flash_attn_2]_ms"] = ref_fa2
         cands["reference_flash_attention[sdpa]_ms"] = ref_sdpa
@@ -305,6 +308,7 @@ def attn_vs_library(fg, cfg, tokens: int, text_len: int, dev, iters: int = 5) ->
         finally:
             wd.FLASH_ATTN_2_AVAILABLE = saved
         res = {"ours_ms": round(timed.pop("ours_ms"), 4), "ours_with_bound_pass_ms": round(timed.pop("ours_with_bound_pass_ms"), 4),
+               "ours_head_bound_ms": round(timed.pop("ours_head_bound_ms"), 4),
                "timing": "each candidate back-to-back for ~0.3 s, candidates alternating twice (sustained clocks)"}
         libs.update(timed)
         ours()

@@ -25,6 +25,15 @@ struct ScatterSpec {
   int s_local, heads, world, rank, grp, groups;
 };
 
+// Squared norm of one 128-wide head = the sum of `ss` over the 16 lanes that hold it. (A one-instruction variant —
+// redux.sync.add on a rounded-up fixed-point image — was measured SLOWER than these four shuffle + add steps on sm_100a:
+// qk_norm_rope 130 -> 161 us alone, profiles/r02_attn_head_bound_ab.log.)
+__device__ __forceinline__ float head_ss(float ss) {
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  return ss;
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm (no affine) + adaLN modulate, or LayerNorm with affine.      DIT:205-207, 63-64, 224-227
 // NV = dim / 256 16-byte vectors per lane.
@@ -96,7 +105,7 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __res
 // ---------------------------------------------------------------------------------------------
 // RMSNorm over the full row (all heads) + optional 3-D RoPE, in place.      DIT:91-110, 140-144
 // ---------------------------------------------------------------------------------------------
-template <int NV, bool SCATTER>
+template <int NV, bool SCATTER, bool HMAX = false>
 __global__ void __launch_bounds__(kRowWarps * 32)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float eps,
                     const __nv_bfloat16* __restrict__ weight, const float2* __restrict__ rope_tab, int gf, int gh,
@@ -104,8 +113,8 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   // hmax2 (optional): hmax2[h] = max over rows of ||out[row, h*128 : +128]||^2 — the query bound of fgb_attn_fwd_bounded_qk
-  __shared__ float hred[kRowWarps][2 * NV];
-  if (hmax2 != nullptr) {
+  __shared__ float hred[HMAX ? kRowWarps : 1][HMAX ? 2 * NV : 1];
+  if (HMAX) {
     if ((lane & 15) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) hred[threadIdx.x >> 5][2 * i + (lane >> 4)] = 0.f;
@@ -173,13 +182,12 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
       }
     }
     const uint4 out = make_uint4(o[0], o[1], o[2], o[3]);
-    if (!SCATTER && hmax2 != nullptr) {
+    if (HMAX) {
       float ss = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) ss += bf16_lo(o[j]) * bf16_lo(o[j]) + bf16_hi(o[j]) * bf16_hi(o[j]);
-#pragma unroll
-      for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
-      if ((lane & 15) == 0) hred[threadIdx.x >> 5][2 * i + (lane >> 4)] = ss;
+      const float hs = head_ss(ss);
+      if ((lane & 15) == 0) hred[threadIdx.x >> 5][2 * i + (lane >> 4)] = hs;
     }
     if (SCATTER) {
       // fused Ulysses exchange: the normalised, rotated head slice goes straight to the peer that owns the head
@@ -195,7 +203,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
       xr[i * 32 + lane] = out;
     }
   }
-  if (!SCATTER && hmax2 != nullptr) {
+  if (HMAX) {
     __syncthreads();
     if (threadIdx.x < 2 * NV) {
       float mx = 0.f;
@@ -213,7 +221,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
 // rmsnorm_rope launches plus a head_norm_max pass that read k a second time. One warp per row, grid-stride; the per-head
 // running maxima stay in registers (lane 0 and 16 of each vector index own a head).
 // ---------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool QMAX>
 __global__ void __launch_bounds__(kRowWarps * 32)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int rows, float eps, const __nv_bfloat16* __restrict__ wq,
                     const __nv_bfloat16* __restrict__ wk, const float2* __restrict__ rope_tab, int gf, int gh, int gw, int token_offset,
@@ -276,28 +284,27 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int rows, float
           }
         }
         xr[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
-        if (g == 1 || qmax2 != nullptr) {
+        if (g == 1 || QMAX) {
           float ss = 0.f;
 #pragma unroll
           for (int j = 0; j < 4; ++j) ss += bf16_lo(o[j]) * bf16_lo(o[j]) + bf16_hi(o[j]) * bf16_hi(o[j]);
-#pragma unroll
-          for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
-          if (g == 1) best[i] = fmaxf(best[i], ss);
-          else bestq[i] = fmaxf(bestq[i], ss);
+          const float hs = head_ss(ss);
+          if (g == 1) best[i] = fmaxf(best[i], hs);
+          else bestq[i] = fmaxf(bestq[i], hs);
         }
       }
     }
   }
-  __shared__ float red[2][kRowWarps][2 * NV];
+  __shared__ float red[QMAX ? 2 : 1][kRowWarps][2 * NV];
   if ((lane & 15) == 0) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       red[0][threadIdx.x >> 5][2 * i + (lane >> 4)] = best[i];
-      red[1][threadIdx.x >> 5][2 * i + (lane >> 4)] = bestq[i];
+      if (QMAX) red[1][threadIdx.x >> 5][2 * i + (lane >> 4)] = bestq[i];
     }
   }
   __syncthreads();
-  if (threadIdx.x < 4 * NV) {
+  if (threadIdx.x < (QMAX ? 4 : 2) * NV) {
     const int which = threadIdx.x / (2 * NV), h = threadIdx.x % (2 * NV);
     float* dst = which == 0 ? kmax2 : qmax2;
     if (dst != nullptr) {
@@ -663,12 +670,11 @@ recv_norm_rope_kernel(__nv_bfloat16* __restrict__ recv, int s_pad, int tokens, i
           }
         }
         if ((g == 1 || qmax2 != nullptr) && pass * 32 < vecs) {   // warp-uniform
-#pragma unroll
-          for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
+          const float hs = head_ss(ss);
           if (g == 1) {
-            if (t < tokens) best[pass] = fmaxf(best[pass], ss);
+            if (t < tokens) best[pass] = fmaxf(best[pass], hs);
           } else {
-            bestq[pass] = fmaxf(bestq[pass], ss);     // padded query rows are computed (and discarded) too: keep them inside the bound
+            bestq[pass] = fmaxf(bestq[pass], hs);     // padded query rows are computed (and discarded) too: keep them inside the bound
           }
         }
       }
@@ -901,10 +907,9 @@ struct RmsStreamOp {
         float ss = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) ss += bf16_lo(o[j]) * bf16_lo(o[j]) + bf16_hi(o[j]) * bf16_hi(o[j]);
-#pragma unroll
-        for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // 16 lanes = one head
-        if (g == 1) best[i] = fmaxf(best[i], ss);
-        else bestq[i] = fmaxf(bestq[i], ss);
+        const float hs = head_ss(ss);
+        if (g == 1) best[i] = fmaxf(best[i], hs);
+        else bestq[i] = fmaxf(bestq[i], hs);
       }
     }
   }
@@ -1080,7 +1085,7 @@ extern "C" int fgb_rmsnorm_hmax(fgb_ctx* ctx, void* x, int64_t ldx, int32_t rows
   ScatterSpec none{};
 #define FGB_RMSH_CASE(NV)                                                                                        \
   case NV:                                                                                                       \
-    rmsnorm_rope_kernel<NV, false><<<grid, kRowWarps * 32, 0, s>>>(static_cast<bf16*>(x), ldx, rows, eps, static_cast<const bf16*>(weight), \
+    rmsnorm_rope_kernel<NV, false, true><<<grid, kRowWarps * 32, 0, s>>>(static_cast<bf16*>(x), ldx, rows, eps, static_cast<const bf16*>(weight), \
                                                                    nullptr, 1, 1, 1, 0, none, static_cast<float*>(hmax2)); \
     break;
   switch (dim / 256) {
@@ -1329,7 +1334,8 @@ extern "C" int fgb_qk_norm_rope(fgb_ctx* ctx, void* qkv, int64_t ld, int32_t row
   }
 #define FGB_QK_CASE(NV)                                                                                                            \
   case NV:                                                                                                                         \
-    qk_norm_rope_kernel<NV><<<grid, kRowWarps * 32, 0, s>>>(xp, ld, rows, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp, qp);     \
+    if (qp) qk_norm_rope_kernel<NV, true><<<grid, kRowWarps * 32, 0, s>>>(xp, ld, rows, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp, qp); \
+    else qk_norm_rope_kernel<NV, false><<<grid, kRowWarps * 32, 0, s>>>(xp, ld, rows, eps, wqp, wkp, tab, gf, gh, gw, token_offset, kp, qp); \
     break;
   switch (dim / 256) {
     FGB_QK_CASE(1) FGB_QK_CASE(2) FGB_QK_CASE(3) FGB_QK_CASE(4) FGB_QK_CASE(6) FGB_QK_CASE(8) FGB_QK_CASE(12) FGB_QK_CASE(16) FGB_QK_CASE(20)

@@ -70,6 +70,8 @@ class WanDiTEngine:
         self.fused_adapters = []         # (lora_sd, alpha, targets) fused by lora_io.fuse_into_engine since the last pack
         self.timer = None         # optional fairygen_b200.profiling.KernelTimer
         self.loaded = False
+        import os
+        self.query_bounds = int(os.environ.get("FGB_QMAX", "0"))   # bit 0: self-attention, bit 1: cross-attention (see _workspace)
 
     # ------------------------------------------------------------------------------------------
     # weights
@@ -148,7 +150,11 @@ class WanDiTEngine:
                 ts=torch.zeros(2, dtype=torch.float32, device=dev), emb=e(2, cfg.freq_dim), t0=e(2, d), t0s=e(2, d),
                 t=e(2, d), ts_silu=e(2, d), tmod=e(2, 6 * d), mod_tab=e(2, L, 6 * d), head_tab=e(2, 2 * d),
                 kmax2=torch.zeros(cfg.num_heads, dtype=torch.float32, device=dev),
-                qmax2=torch.zeros(2, cfg.num_heads, dtype=torch.float32, device=dev),   # head-level query bounds: [self, cross]
+                # head-level query bounds [self, cross] for fgb_attn_fwd_bounded_qk (FGB_QMAX bit 0 / bit 1; default off). Inside the
+                # step the 16-lane sums that produce them cost the issue-bound norm kernels what the attention kernels gain:
+                # cross-q rmsnorm +2.0-2.7 ms vs cross-attention -2.1 ms per step, qk_norm_rope +3.4 ms vs self-attention -1.7 ms
+                # (profiles/r02_attn_head_bound_ab.log). A caller that has the bounds for free passes them to ops.attention.
+                qmax2=torch.zeros(2, cfg.num_heads, dtype=torch.float32, device=dev),
                 sk=ops.gemm_workspace(dev),    # stream-K tail of the block's GEMMs (all launches of a forward are on one stream)
             )
             if self.sp is not None:
@@ -297,6 +303,8 @@ class WanDiTEngine:
 
         k = self._k
         sk = ws["sk"]
+        qmax_self = ws["qmax2"][0] if self.query_bounds & 1 else None
+        qmax_cross = ws["qmax2"][1] if self.query_bounds & 2 else None
         for i, b in enumerate(self.blocks):
             m0, m1 = mod_tab[0, i].view(6, d), mod_tab[r_main, i].view(6, d)
             # self-attention branch (DIT:224-225)
@@ -310,8 +318,8 @@ class WanDiTEngine:
                 k("gemm_qkv", ops.gemm, a, b.wqkv, b.bqkv, qkv, sk_ws=sk)
                 if sp is None:
                     # q and k normalised + rotated and the key bound of the bounded softmax in one pass over the fused rows
-                    k("rmsnorm_rope", ops.qk_norm_rope, qkv, d, cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0, ws["kmax2"], ws["qmax2"][0])
-                    k("attn_self", ops.attention, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, H, kmax2=ws["kmax2"], qmax2=ws["qmax2"][0])
+                    k("rmsnorm_rope", ops.qk_norm_rope, qkv, d, cfg.eps, b.nq, b.nk, self.rope_tab, grid, tok0, ws["kmax2"], qmax_self)
+                    k("attn_self", ops.attention, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, H, kmax2=ws["kmax2"], qmax2=qmax_self)
                 else:
                     k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, :d], cfg.eps, b.nq, self.rope_tab, grid, tok0)
                     k("rmsnorm_rope", ops.rmsnorm_rope, qkv[:, d:2 * d], cfg.eps, b.nk, self.rope_tab, grid, tok0)
@@ -320,8 +328,8 @@ class WanDiTEngine:
             # cross-attention branch (DIT:226)
             k("ln_affine", ops.ln_affine, x, a, cfg.eps, b.n3w, b.n3b)
             k("gemm_cross_q", ops.gemm, a, b.cwq, b.cbq, cq, sk_ws=sk)
-            k("rmsnorm", ops.rmsnorm_rope, cq, cfg.eps, b.cnq, hmax2=ws["qmax2"][1])
-            k("attn_cross", ops.attention, cq, kv_all[i][:, :d], kv_all[i][:, d:], o, H, kmax2=kmax_all[i], qmax2=ws["qmax2"][1])
+            k("rmsnorm", ops.rmsnorm_rope, cq, cfg.eps, b.cnq, hmax2=qmax_cross)
+            k("attn_cross", ops.attention, cq, kv_all[i][:, :d], kv_all[i][:, d:], o, H, kmax2=kmax_all[i], qmax2=qmax_cross)
             k("gemm_cross_o", ops.gemm, o, b.cwo, b.cbo, x, EPI_RESIDUAL, sk_ws=sk)
             # feed-forward branch (DIT:227-228)
             k("ln_modulate", ops.ln_modulate, x, a, cfg.eps, m0[3], m0[4], m1[3], m1[4], n_first)

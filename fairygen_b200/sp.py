@@ -193,7 +193,7 @@ class SequenceParallel:
                 k("sp_barrier", ops.sp_stats_barrier, qkv.device, ar.flag_ptrs[0], ar.stats_ptrs, ar.rowsq, rows, rows * self.world, kmax2,
                   hpr, self.world, self.rank, ar.epoch, ar.status)
                 h0 = self.rank * wloc
-                qmax2 = ws["qmax2"][0][:hpr] if "qmax2" in ws else None
+                qmax2 = ws["qmax2"][0][:hpr] if ("qmax2" in ws and getattr(engine, "query_bounds", 0) & 1) else None
                 k("rmsnorm_rope", ops.recv_norm_rope, ar.recv, tokens, hpr, ar.stats, heads * 128, eps, wq[h0:h0 + wloc], wk[h0:h0 + wloc],
                   rope_tab, grid, kmax2, qmax2)
                 recv = ar.recv
