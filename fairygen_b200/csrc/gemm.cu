@@ -372,6 +372,10 @@ struct PairParams {
   // takes sk_tiles / sk_clusters of a tile time instead of a whole one. The cluster whose range starts a tile owns it; the
   // others dump their fp32 partial accumulators into sk_partial (one slot per cluster) and raise a flag per epilogue warp.
   int32_t dp_tiles, sk_tiles, sk_clusters, sk_upt;   // sk_upt = units per tile
+  // Half-width tail (BN = 256 only, exclusive with stream-K): when the last wave holds at most half as many tiles as there are
+  // clusters, each of its hw_tiles tiles is handed out as TWO 256 x 128 items (N = 128 MMAs, 64-row W boxes), so that wave takes
+  // ~0.6 of a tile time instead of a whole one — no partial sums, no workspace, no fix-up.
+  int32_t hw_tiles;
   float* sk_partial;
   int32_t* sk_flags;
 };
@@ -384,6 +388,7 @@ struct PairItem {
   int32_t role;        // 0 = whole tile or owner of a split tile (normal epilogue), 1 = contributor (partial dump)
   int32_t unit_end;    // owner: first unit after its own range; tile_end: first unit after the tile — the contributors are the
   int32_t tile_end;    // clusters after this one whose unit ranges start before tile_end
+  int32_t n_off, bn;   // half-width tail items: column offset inside the tile and width (128); bn = 0: the kernel's full width
 };
 
 struct PeerMaps {
@@ -420,6 +425,20 @@ __device__ __forceinline__ bool pair_next_item(const PairParams& p, int cluster,
     w.kb1 = p.k_blocks;
     w.role = 0;
     w.unit_end = w.tile_end = 0;
+    w.n_off = w.bn = 0;
+    return true;
+  }
+  w.n_off = w.bn = 0;
+  if (p.hw_tiles > 0) {
+    const int h = tile - p.dp_tiles;
+    if (h >= 2 * p.hw_tiles) return false;
+    w.tile = p.dp_tiles + (h >> 1);
+    w.kb0 = 0;
+    w.kb1 = p.k_blocks;
+    w.role = 0;
+    w.unit_end = w.tile_end = 0;
+    w.n_off = (h & 1) * 128;
+    w.bn = 128;
     return true;
   }
   if (p.sk_tiles == 0 || cluster >= p.sk_clusters) return false;
@@ -458,7 +477,8 @@ __device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t* p) {
 template <int EPI, int BN, bool SCATTER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ PeerMaps peer_maps, const PairParams p) {
+                 const __grid_constant__ CUtensorMap tmap_bh, const __grid_constant__ CUtensorMap tmap_c,
+                 const __grid_constant__ PeerMaps peer_maps, const PairParams p) {
   constexpr int kPairBN = BN;
   constexpr int kPairBBytes = (BN / 2) * kBK * 2;
   extern __shared__ uint8_t smem_raw[];
@@ -484,6 +504,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_c);
+    if (p.hw_tiles > 0) tma_prefetch_desc(&tmap_bh);
     for (int s = 0; s < kPairStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -515,15 +536,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int mt, nt;
         pair_tile_coords(p, w.tile, mt, nt);
         const int row_a = mt * kPairTM + static_cast<int>(rank) * kPairBM;
-        const int row_b = nt * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
+        const int bn = w.bn ? w.bn : kPairBN;
+        const int row_b = nt * kPairBN + w.n_off + static_cast<int>(rank) * (bn / 2);
+        const CUtensorMap* mb = w.bn ? &tmap_bh : &tmap_b;          // 64-row boxes for a half-width item
+        const uint32_t stage_tx = 2 * (kPairABytes + (bn / 2) * kBK * 2);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait_cluster(&empty[stage], phase ^ 1);
-          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (kPairABytes + kPairBBytes));   // both CTAs' bytes land on the leader's barrier
+          if (rank == 0) mbar_expect_tx(&full[stage], stage_tx);   // both CTAs' bytes land on the leader's barrier
           uint32_t fl = full_leader[0];
 #pragma unroll
           for (int s = 1; s < kPairStages; ++s) fl = (stage == s) ? full_leader[s] : fl;
           tma_load_2d_2sm(smem_a + stage * kPairABytes, &tmap_a, fl, kb * kBK, row_a, kEvictNormal);
-          tma_load_2d_2sm(smem_b + stage * kPairBBytes, &tmap_b, fl, kb * kBK, row_b, kEvictLast);
+          tma_load_2d_2sm(smem_b + stage * kPairBBytes, mb, fl, kb * kBK, row_b, kEvictLast);
           if (++stage == kPairStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -531,13 +555,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
       // ------------------------------- MMA issuer (leader only) -------------------------------
-      constexpr uint32_t idesc = make_idesc_bf16(kPairTM, kPairBN, 0, 0);
+      constexpr uint32_t idesc_full = make_idesc_bf16(kPairTM, kPairBN, 0, 0);
+      constexpr uint32_t idesc_half = make_idesc_bf16(kPairTM, 128, 0, 0);
       const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(smem_a), 16, 1024);
       const uint64_t b_desc0 = make_sdesc_sw128(smem_u32(smem_b), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       PairItem w;
       for (int local = 0; pair_next_item(p, cluster, n_clusters, local, w); ++local) {
+        const uint32_t idesc = w.bn ? idesc_half : idesc_full;
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
@@ -685,18 +711,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const __nv_bfloat16* gate = nullptr;
       if (EPI == FGB_EPI_GATED_RESIDUAL) gate = (row < p.rows_gate0) ? p.gate0 : p.gate1;
       uint4 xcur[4], xnext[4];
+      const int bn = w.bn ? w.bn : kPairBN;          // columns of this item
+      const int col_base = nt * kPairBN + w.n_off;   // its first column
       auto load_c = [&](int c32, uint4 (&dst)[4]) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int col = nt * kPairBN + c32 * 32 + g * 8;
+          const int col = col_base + c32 * 32 + g * 8;
           dst[g] = (row_ok && col < p.n) ? *reinterpret_cast<const uint4*>(crow + col) : make_uint4(0, 0, 0, 0);
         }
       };
       if (kReadsC) load_c(0, xcur);
       float ss = 0.f;   // SCATTER: sum of squares of this row's outputs in this tile (a tile lies inside one of q / k / v)
 #pragma unroll 1
-      for (int c64 = 0; c64 < kPairBN / 64; ++c64) {
-        if (nt * kPairBN + c64 * 64 >= p.n) break;   // warp-uniform
+      for (int c64 = 0; c64 < bn / 64; ++c64) {
+        if (col_base + c64 * 64 >= p.n) break;   // warp-uniform
         uint8_t* sbuf = stage_buf + buf * kPairStoreBytes;
         // the TMA store that last read this buffer must be done with it (at most one newer store may still be in flight)
         if (lane == 0) tma_store_wait_read<1>();
@@ -704,10 +732,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int c32 = c64 * 2 + half;
-          const int col0 = nt * kPairBN + c32 * 32;
+          const int col0 = col_base + c32 * 32;
           uint32_t r[32];
           tmem_ld32(taddr + c32 * 32, r);
-          if (kReadsC && c32 + 1 < kPairBN / 32) load_c(c32 + 1, xnext);
+          if (kReadsC && c32 + 1 < bn / 32) load_c(c32 + 1, xnext);
           tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -767,7 +795,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          const int gcol = nt * kPairBN + c64 * 64;
+          const int gcol = col_base + c64 * 64;
           if (SCATTER) {
             const int grp = gcol / p.dim, head = (gcol - grp * p.dim) >> 7;
             const int peer = head / p.hpr;
@@ -780,7 +808,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         buf ^= 1;
       }
       if (SCATTER) {
-        const int grp = (nt * kPairBN) / p.dim;
+        const int grp = col_base / p.dim;
         if (grp < 2 && row_ok) atomicAdd(p.rowsq + static_cast<int64_t>(grp) * p.m + row, ss);
       }
       // this warp has read its part of the accumulator: one arrival per warp on the leader's barrier
@@ -812,7 +840,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 template <int EPI, int BN, bool SCATTER = false>
 static int launch_gemm_pair(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const PairParams& p,
-                            cudaStream_t stream, const PeerMaps* pm = nullptr) {
+                            cudaStream_t stream, const PeerMaps* pm = nullptr, const CUtensorMap* tbh = nullptr) {
   auto kfn = gemm_pair_kernel<EPI, BN, SCATTER>;
   static PeerMaps no_peers{};
   static unsigned long long configured = 0;  // per template instance and device
@@ -820,8 +848,8 @@ static int launch_gemm_pair(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorM
     FGB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
   }
   int clusters = ctx->sm_count / 2;
-  if (p.sk_tiles == 0 && p.tiles < clusters) clusters = p.tiles;   // the stream-K ranges are cut for the full cluster count
-  kfn<<<2 * clusters, kPairThreads, kPairSmem, stream>>>(ta, tb, tc, pm ? *pm : no_peers, p);
+  if (p.sk_tiles == 0 && p.hw_tiles == 0 && p.tiles < clusters) clusters = p.tiles;   // split tails are laid out for the full cluster count
+  kfn<<<2 * clusters, kPairThreads, kPairSmem, stream>>>(ta, tb, tbh ? *tbh : tb, tc, pm ? *pm : no_peers, p);
   FGB_LAUNCH_CHECK("gemm_pair_kernel");
   return FGB_OK;
 }
@@ -884,6 +912,23 @@ static void pair_plan_streamk(fgb_ctx* ctx, PairParams& pp, void* ws, int64_t ws
   pp.sk_clusters = clusters < kSkMaxSplit * tail ? clusters : kSkMaxSplit * tail;
   pp.sk_flags = static_cast<int32_t*>(ws);
   pp.sk_partial = reinterpret_cast<float*>(static_cast<char*>(ws) + kSkFlagBytes);
+}
+
+// Half-width tail (see PairParams::hw_tiles): for 256-wide launches whose last wave is at most half full and is not already
+// split along K. FGB_GEMM_HW=0 switches it off.
+static void pair_plan_half_tail(const fgb_ctx* ctx, PairParams& pp, int bn) {
+  pp.hw_tiles = 0;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("FGB_GEMM_HW");
+    enabled = e ? atoi(e) : 1;
+  }
+  const int clusters = ctx->sm_count / 2;
+  if (!enabled || bn != 256 || pp.sk_tiles > 0 || pp.n % 256 != 0) return;
+  const int tail = pp.tiles % clusters;
+  if (tail == 0 || 2 * tail > clusters || pp.tiles < clusters) return;
+  pp.dp_tiles = pp.tiles - tail;
+  pp.hw_tiles = tail;
 }
 
 static int gemm_impl(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c, int64_t ldc,
@@ -989,17 +1034,20 @@ static int fgb::gemm_impl(fgb_ctx* ctx, const void* a, int64_t lda, const void* 
     pair_supertile(pp.m_tiles, (pp.n_tiles * bn + 255) / 256, k, &pp.group_m, &pp.band_n);
     pp.band_n = pp.band_n * 256 / bn;      // the band is sized in columns
     pair_plan_streamk(ctx, pp, sk_ws, sk_ws_bytes);
+    pair_plan_half_tail(ctx, pp, bn);
+    CUtensorMap tbh = tb;
+    if (pp.hw_tiles > 0 && (rc = make_tmap_bf16_2d(ctx, &tbh, w, n, k, ldw, 64))) return rc;
     cudaStream_t ps = static_cast<cudaStream_t>(stream);
 #define FGB_PAIR_CASE(E)                                                       \
   case E:                                                                      \
-    return bn == 128 ? launch_gemm_pair<E, 128>(ctx, ta, tb, tc, pp, ps) : launch_gemm_pair<E, 256>(ctx, ta, tb, tc, pp, ps);
+    return bn == 128 ? launch_gemm_pair<E, 128>(ctx, ta, tb, tc, pp, ps) : launch_gemm_pair<E, 256>(ctx, ta, tb, tc, pp, ps, nullptr, &tbh);
     switch (epilogue) {
       FGB_PAIR_CASE(FGB_EPI_BIAS)
       FGB_PAIR_CASE(FGB_EPI_BIAS_GELU_TANH)
       FGB_PAIR_CASE(FGB_EPI_GATED_RESIDUAL)
       default:
         return bn == 128 ? launch_gemm_pair<FGB_EPI_RESIDUAL, 128>(ctx, ta, tb, tc, pp, ps)
-                         : launch_gemm_pair<FGB_EPI_RESIDUAL, 256>(ctx, ta, tb, tc, pp, ps);
+                         : launch_gemm_pair<FGB_EPI_RESIDUAL, 256>(ctx, ta, tb, tc, pp, ps, nullptr, &tbh);
     }
 #undef FGB_PAIR_CASE
   }
@@ -1087,7 +1135,10 @@ extern "C" int fgb_gemm_qkv_scatter(fgb_ctx* ctx, const void* a, int64_t lda, co
   pair_supertile(pp.m_tiles, pp.n_tiles, k, &pp.group_m, &pp.band_n);
   FGB_CHECK_ARG(!workspace || aligned16(workspace), "fgb_gemm_qkv_scatter: workspace must be 16-byte aligned");
   pair_plan_streamk(ctx, pp, workspace, workspace_bytes);
-  return launch_gemm_pair<FGB_EPI_BIAS, 256, true>(ctx, ta, tb, pm.m[0], pp, static_cast<cudaStream_t>(stream), &pm);
+  pair_plan_half_tail(ctx, pp, 256);
+  CUtensorMap tbh = tb;
+  if (pp.hw_tiles > 0 && (rc = make_tmap_bf16_2d(ctx, &tbh, w, n, k, ldw, 64))) return rc;
+  return launch_gemm_pair<FGB_EPI_BIAS, 256, true>(ctx, ta, tb, pm.m[0], pp, static_cast<cudaStream_t>(stream), &pm, &tbh);
 }
 
 extern "C" int fgb_gemm_dgrad(fgb_ctx* ctx, const void* dy, int64_t ld_dy, const void* w, int64_t ldw, void* dx, int64_t ld_dx,

@@ -36,7 +36,9 @@ def assert_head_bound(got, exact):
 @pytest.mark.parametrize("m,n,k", [(128, 256, 64), (2, 768, 256), (200, 192, 192), (1000, 3072, 3072), (513, 1536, 256),
                                    (300, 512, 4096), (2049, 14336, 3072),
                                    # the 2-CTA kernel (m >= 256): exact tiles, ragged rows / columns / k, one tile, many waves
-                                   (256, 256, 64), (257, 200, 72), (384, 8, 8), (511, 264, 136), (20000, 3072, 512)])
+                                   (256, 256, 64), (257, 200, 72), (384, 8, 8), (511, 264, 136), (20000, 3072, 512),
+                                   # half-width tail: 81 tiles = one wave of 74 + 7 tiles as 14 half-width items; 1284 = 17 waves + 26
+                                   (6820, 768, 512), (27280, 3072, 128)])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 def test_gemm_epilogues(env, m, n, k, epi):
     ops, o = env
