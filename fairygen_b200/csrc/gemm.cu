@@ -855,7 +855,7 @@ static int launch_gemm_pair(fgb_ctx* ctx, const CUtensorMap& ta, const CUtensorM
 }
 
 // Supertile shape, from a sweep on the four GEMM shapes of the denoise step (tools/gemm_sweep.sh, profiles/r02_gemm_sweep*.log):
-// bands of at most 14 tile columns (a 3.6 K-column W band: 22 MB at K = 3072) and SMALL row groups — 4 tile rows, 2 for the
+// bands of at most 14 tile columns (a 3.6 K-column W band: 22 MB at K = 3072) and SMALL row groups — 4 tile rows, 1 for the
 // long-K FFN2 — so that the ~74 tiles in flight reuse each W tile a few times in quick succession while it is hot in L2 and the
 // A rows they share stay small. FGB_GEMM_BAND_N / FGB_GEMM_GROUP_M override, for tuning.
 static void pair_supertile(int m_tiles, int n_tiles, int k, int* group_m, int* band_n) {
@@ -869,7 +869,7 @@ static void pair_supertile(int m_tiles, int n_tiles, int k, int* group_m, int* b
   int bn = n_tiles < 14 ? n_tiles : 14;
   const int bands = (n_tiles + bn - 1) / bn;
   bn = (n_tiles + bands - 1) / bands;      // even out the bands (36 tile columns -> 3 bands of 12)
-  int gm = k >= 8192 ? 2 : 4;
+  int gm = k >= 8192 ? 1 : 4;     // long K: single tile rows (profiles/r02_gemm_sweep4.log: FFN2 1225 vs 1203 TFLOP/s for 1 vs 2 rows)
   if (gm > m_tiles) gm = m_tiles;
   *group_m = env_gm > 0 ? env_gm : gm;
   *band_n = env_bn > 0 ? env_bn : bn;
