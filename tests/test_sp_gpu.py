@@ -106,6 +106,9 @@ def _oracle_worker(rank, world, port, dims, shape, out_dir):
     ((3072, 14336, 24, 4096), (1, 48, 3, 10, 14)),    # TI2V-5B block shapes, 12 heads per rank, S = 105 (ragged: 1 pad row)
     ((3072, 14336, 24, 4096), (1, 48, 5, 16, 16)),    # S = 320 (even split)
     ((768, 2048, 6, 512), (1, 48, 3, 10, 14)),        # 3 heads per rank — the per-rank head count of Ulysses SP8 on TI2V-5B
+    # S = 1400, 700 rows per rank: the q|k|v GEMM-with-send has 3 x 36 = 108 tiles = one wave of 74 CTA pairs + 34, so its last
+    # wave runs as 68 half-width items whose 64-column blocks still go to the right head owners
+    ((3072, 14336, 24, 4096), (1, 48, 5, 28, 40)),
 ])
 def test_sp2_vs_oracle_at_north_star_tolerance(tmp_path, dims, shape):
     if torch.cuda.device_count() < 2:
