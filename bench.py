@@ -42,7 +42,7 @@ PARITY_TOL = 1e-2
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (self-attention at S = 27 280, 24 heads)
     from the newest committed `ncu --set full` summary; None if there is none.  Only meaningful for the 1-GPU shape."""
-    for name in ("r02_ncu_attn_summary.csv", "r01_ncu_attn_summary.csv"):
+    for name in ("r02final_ncu_attn_summary.csv", "r02_ncu_attn_summary.csv", "r01_ncu_attn_summary.csv"):
         path = os.path.join(REPO, "profiles", name)
         try:
             tot = 0.0
