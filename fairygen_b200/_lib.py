@@ -53,6 +53,7 @@ SIGNATURES = {
     "fgb_gemm_bf16_sk": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _I64, _P]),
     "fgb_gemm_workspace_bytes": (c_int64, [_P]),
     "fgb_gemm_streamk_tune": (ctypes.c_int, [_P, _I32, ctypes.c_double]),
+    "fgb_gemm_schedule_check": (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, ctypes.POINTER(c_int32), ctypes.POINTER(c_int32)]),
     "fgb_sp_stats_barrier": (ctypes.c_int, [_P, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), _P, _I32, _I32, _P, _I32, _I32, _I32,
                                             _I32, _P, _P]),
     "fgb_recv_norm_rope": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _I32, _F, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),

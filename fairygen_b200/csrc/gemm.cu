@@ -17,7 +17,9 @@
 //               residual in fp32 with the reference's bf16 rounding points, 16-byte global stores.
 // Tiles are rasterised in groups of 8 M-blocks so the CTAs resident at one time share A and W
 // tiles through the 126 MB L2.
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "host.h"
@@ -395,7 +397,7 @@ struct PeerMaps {
   CUtensorMap m[FGB_MAX_PEERS];
 };
 
-__device__ __forceinline__ void pair_tile_coords(const PairParams& p, int tile, int& mt, int& nt) {
+__host__ __device__ __forceinline__ void pair_tile_coords(const PairParams& p, int tile, int& mt, int& nt) {
   const int band_tiles = p.m_tiles * p.band_n;          // tiles of a full band
   const int band = tile / band_tiles;
   const int n0 = band * p.band_n;
@@ -410,14 +412,14 @@ __device__ __forceinline__ void pair_tile_coords(const PairParams& p, int tile, 
   nt = n0 + in_group / gm;
 }
 
-__device__ __forceinline__ int sk_range_begin(const PairParams& p, int c) {
+__host__ __device__ __forceinline__ int sk_range_begin(const PairParams& p, int c) {
   return static_cast<int>(static_cast<int64_t>(c) * (p.sk_tiles * p.sk_upt) / p.sk_clusters);
 }
 
 // The it-th work item of `cluster` (all three roles of a CTA walk the same list): whole tiles first, then at most two
 // stream-K segments — the end of one tail tile (contributor, or owner if the range starts on the tile boundary) and the
 // beginning of the next (owner).
-__device__ __forceinline__ bool pair_next_item(const PairParams& p, int cluster, int n_clusters, int it, PairItem& w) {
+__host__ __device__ __forceinline__ bool pair_next_item(const PairParams& p, int cluster, int n_clusters, int it, PairItem& w) {
   const int tile = cluster + it * n_clusters;
   if (tile < p.dp_tiles) {
     w.tile = tile;
@@ -936,6 +938,35 @@ static int gemm_impl(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, in
                      const void* a2, int64_t lda2, const void* w2, int64_t ldw2, int32_t k2, void* sk_ws, int64_t sk_ws_bytes,
                      void* stream);
 
+// Everything about a 2-CTA launch that depends on the SHAPE only (tile width, tile counts, raster, stream-K / half-width tail):
+// one place for gemm_impl and for the host-side schedule check (fgb_gemm_schedule_check). Returns the tile width.
+static int pair_plan_shape(fgb_ctx* ctx, PairParams& pp, int m, int n, int k, void* sk_ws, int64_t sk_ws_bytes) {
+  // tile width: 256 columns unless half-width tiles shorten the last, partly filled wave by more than they cost — a half-width
+  // tile runs at ~0.85 of the full-width rate per FLOP (profiles/r02_gemm_sweep3.log: 1105 vs 1281 TFLOP/s at 6820 rows), so
+  // this only pays for small problems (a handful of tiles); the Ulysses-rank shapes (324 tiles = 4.38 waves) stay at 256
+  const int clusters = ctx->sm_count / 2;
+  const int m_tiles = (m + kPairTM - 1) / kPairTM;
+  const int waves256 = (m_tiles * ((n + 255) / 256) + clusters - 1) / clusters;
+  const int waves128 = (m_tiles * ((n + 127) / 128) + clusters - 1) / clusters;
+  static int env_bn = -1;
+  if (env_bn < 0) {
+    const char* e = getenv("FGB_GEMM_BN");
+    env_bn = e ? atoi(e) : 0;
+  }
+  const int bn = env_bn ? env_bn : ((0.5 * 1.3 * waves128 < waves256) ? 128 : 256);
+  pp.m = m;
+  pp.n = n;
+  pp.m_tiles = m_tiles;
+  pp.n_tiles = (n + bn - 1) / bn;
+  pp.tiles = pp.m_tiles * pp.n_tiles;
+  pp.k_blocks = (k + kBK - 1) / kBK;
+  pair_supertile(pp.m_tiles, (pp.n_tiles * bn + 255) / 256, k, &pp.group_m, &pp.band_n);
+  pp.band_n = pp.band_n * 256 / bn;      // the band is sized in columns
+  pair_plan_streamk(ctx, pp, sk_ws, sk_ws_bytes);
+  pair_plan_half_tail(ctx, pp, bn);
+  return bn;
+}
+
 }  // namespace fgb
 
 extern "C" int64_t fgb_gemm_workspace_bytes(fgb_ctx* ctx) { return ctx ? fgb::sk_workspace_bytes(ctx) : 0; }
@@ -955,6 +986,86 @@ extern "C" int fgb_gemm_bf16_sk(fgb_ctx* ctx, const void* a, int64_t lda, const 
   FGB_CHECK_ARG(!workspace || fgb::aligned16(workspace), "fgb_gemm_bf16_sk: workspace must be 16-byte aligned");
   return fgb::gemm_impl(ctx, a, lda, w, ldw, bias, c, ldc, m, n, k, epilogue, gate0, gate1, rows_gate0, nullptr, 0, nullptr, 0, 0,
                         workspace, workspace_bytes, stream);
+}
+
+// Host-side walk of the work list of one 2-CTA GEMM launch (no device needed): every (tile, K-block, column half) must be
+// computed exactly once; a split tile has exactly one owner, the owner's item is its cluster's last, and the contributors the
+// owner will wait for are exactly the clusters that dump a partial for that tile; a cluster contributes at most once.
+extern "C" int fgb_gemm_schedule_check(int32_t m, int32_t n, int32_t k, int32_t sm_count, int32_t with_workspace, int32_t min_k,
+                                       int32_t* n_split_tiles, int32_t* n_half_items) {
+  using namespace fgb;
+  if (m < kPairTM || n <= 0 || k <= 0 || sm_count < 2) return set_error(FGB_ERR_INVALID, "fgb_gemm_schedule_check: bad shape");
+  fgb_ctx ctx;
+  ctx.sm_count = sm_count;
+  ctx.sk_enabled = 1;
+  ctx.sk_min_kblocks = (min_k + kBK - 1) / kBK;
+  ctx.sk_max_frac = 0.9;
+  PairParams pp{};
+  static char fake_ws[16];
+  const int bn = pair_plan_shape(&ctx, pp, m, n, k, with_workspace ? fake_ws : nullptr, with_workspace ? sk_workspace_bytes(&ctx) : 0);
+  int clusters = sm_count / 2;
+  if (pp.sk_tiles == 0 && pp.hw_tiles == 0 && pp.tiles < clusters) clusters = pp.tiles;
+  const int halves = bn / 128;     // coverage is counted per 128-column half
+  std::vector<int> cover(static_cast<size_t>(pp.tiles) * pp.k_blocks * halves, 0);
+  std::vector<int> owner(pp.tiles, -1), contrib_of_cluster(clusters, -1);
+  std::vector<std::vector<int>> contributors(pp.tiles);
+  int splits = 0, half_items = 0;
+  for (int c = 0; c < clusters; ++c) {
+    PairItem w;
+    int n_items = 0;
+    for (int it = 0; pair_next_item(pp, c, clusters, it, w); ++it) ++n_items;
+    for (int it = 0; pair_next_item(pp, c, clusters, it, w); ++it) {
+      if (w.tile < 0 || w.tile >= pp.tiles || w.kb0 < 0 || w.kb1 > pp.k_blocks || w.kb0 >= w.kb1)
+        return set_error(FGB_ERR_INVALID, "schedule: cluster %d item %d out of range (tile %d kb [%d,%d))", c, it, w.tile, w.kb0, w.kb1);
+      int mt, nt;
+      pair_tile_coords(pp, w.tile, mt, nt);
+      if (mt < 0 || mt >= pp.m_tiles || nt < 0 || nt >= pp.n_tiles) return set_error(FGB_ERR_INVALID, "schedule: tile %d -> (%d,%d)", w.tile, mt, nt);
+      const int h0 = w.bn ? w.n_off / 128 : 0, h1 = w.bn ? h0 + w.bn / 128 : halves;
+      if (w.bn) ++half_items;
+      for (int kb = w.kb0; kb < w.kb1; ++kb)
+        for (int h = h0; h < h1; ++h) ++cover[(static_cast<size_t>(w.tile) * pp.k_blocks + kb) * halves + h];
+      const bool partial = w.kb0 > 0 || w.kb1 < pp.k_blocks;
+      if (w.role == 1) {
+        if (w.kb0 == 0) return set_error(FGB_ERR_INVALID, "schedule: contributor of tile %d starts at K-block 0", w.tile);
+        if (contrib_of_cluster[c] >= 0) return set_error(FGB_ERR_INVALID, "schedule: cluster %d contributes twice", c);
+        contrib_of_cluster[c] = w.tile;
+        contributors[w.tile].push_back(c);
+      } else {
+        if (w.kb0 != 0 && partial) return set_error(FGB_ERR_INVALID, "schedule: owner of tile %d starts at K-block %d", w.tile, w.kb0);
+        if (!w.bn) {
+          if (owner[w.tile] >= 0) return set_error(FGB_ERR_INVALID, "schedule: tile %d has two owners", w.tile);
+          owner[w.tile] = c;
+        }
+        if (w.tile_end > w.unit_end) {     // split: must be the cluster's last item, and the wait list must match the dumps
+          ++splits;
+          if (it != n_items - 1) return set_error(FGB_ERR_INVALID, "schedule: split tile %d is not the last item of cluster %d", w.tile, c);
+        }
+      }
+    }
+  }
+  for (size_t i = 0; i < cover.size(); ++i)
+    if (cover[i] != 1) return set_error(FGB_ERR_INVALID, "schedule: (tile, K-block, half) %zu computed %d times (m=%d n=%d k=%d)", i, cover[i], m, n, k);
+  // the owner's wait list, computed the way the kernel does, against the clusters that really dump a partial for the tile
+  for (int t = 0; t < pp.tiles; ++t) {
+    if (contributors[t].empty()) continue;
+    const int o = owner[t];
+    if (o < 0) return set_error(FGB_ERR_INVALID, "schedule: split tile %d has no owner", t);
+    const int tile_end = (t - pp.dp_tiles + 1) * pp.sk_upt;
+    std::vector<int> waits;
+    for (int c = o + 1; c < pp.sk_clusters; ++c) {
+      const int b = sk_range_begin(pp, c);
+      if (b >= tile_end) break;
+      if (sk_range_begin(pp, c + 1) == b) continue;
+      waits.push_back(c);
+    }
+    std::vector<int> dumps = contributors[t];
+    std::sort(dumps.begin(), dumps.end());
+    if (waits != dumps) return set_error(FGB_ERR_INVALID, "schedule: tile %d: owner %d waits for %zu clusters, %zu dump", t, o, waits.size(), dumps.size());
+    if (static_cast<int>(dumps.size()) > kSkMaxSplit) return set_error(FGB_ERR_INVALID, "schedule: tile %d split %zu ways", t, dumps.size() + 1);
+  }
+  if (n_split_tiles) *n_split_tiles = splits;
+  if (n_half_items) *n_half_items = half_items;
+  return FGB_OK;
 }
 
 extern "C" int fgb_gemm_bf16(fgb_ctx* ctx, const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias,
@@ -1001,40 +1112,18 @@ static int fgb::gemm_impl(fgb_ctx* ctx, const void* a, int64_t lda, const void* 
   if (pair_enabled && k2 == 0 && m >= kPairTM && ctx->sm_count >= 2) {
     CUtensorMap tc;
     if ((rc = make_tmap_bf16_2d(ctx, &ta, a, m, k, lda, kPairBM))) return rc;
-    // tile width: 256 columns unless half-width tiles shorten the last, partly filled wave by more than they cost — a half-width
-    // tile runs at ~0.85 of the full-width rate per FLOP (profiles/r02_gemm_sweep3.log: 1105 vs 1281 TFLOP/s at 6820 rows), so
-    // this only pays for small problems (a handful of tiles); the Ulysses-rank shapes (324 tiles = 4.38 waves) stay at 256
-    const int clusters = ctx->sm_count / 2;
-    const int m_tiles = (m + kPairTM - 1) / kPairTM;
-    const int waves256 = (m_tiles * ((n + 255) / 256) + clusters - 1) / clusters;
-    const int waves128 = (m_tiles * ((n + 127) / 128) + clusters - 1) / clusters;
-    static int env_bn = -1;
-    if (env_bn < 0) {
-      const char* e = getenv("FGB_GEMM_BN");
-      env_bn = e ? atoi(e) : 0;
-    }
-    const int bn = env_bn ? env_bn : ((0.5 * 1.3 * waves128 < waves256) ? 128 : 256);
+    PairParams pp;
+    const int bn = pair_plan_shape(ctx, pp, m, n, k, sk_ws, sk_ws_bytes);
     if ((rc = make_tmap_bf16_2d(ctx, &tb, w, n, k, ldw, bn / 2))) return rc;
     if ((rc = make_tmap_bf16_2d(ctx, &tc, c, m, n, ldc, 32))) return rc;
-    PairParams pp;
     pp.bias = static_cast<const __nv_bfloat16*>(bias);
     pp.c = static_cast<__nv_bfloat16*>(c);
     pp.gate0 = static_cast<const __nv_bfloat16*>(gate0);
     pp.gate1 = static_cast<const __nv_bfloat16*>(gate1);
     pp.ldc = ldc;
-    pp.m = m;
-    pp.n = n;
     pp.rows_gate0 = rows_gate0;
     pp.rowsq = nullptr;
     pp.dim = pp.hpr = 0;
-    pp.m_tiles = m_tiles;
-    pp.n_tiles = (n + bn - 1) / bn;
-    pp.tiles = pp.m_tiles * pp.n_tiles;
-    pp.k_blocks = (k + kBK - 1) / kBK;
-    pair_supertile(pp.m_tiles, (pp.n_tiles * bn + 255) / 256, k, &pp.group_m, &pp.band_n);
-    pp.band_n = pp.band_n * 256 / bn;      // the band is sized in columns
-    pair_plan_streamk(ctx, pp, sk_ws, sk_ws_bytes);
-    pair_plan_half_tail(ctx, pp, bn);
     CUtensorMap tbh = tb;
     if (pp.hw_tiles > 0 && (rc = make_tmap_bf16_2d(ctx, &tbh, w, n, k, ldw, 64))) return rc;
     cudaStream_t ps = static_cast<cudaStream_t>(stream);

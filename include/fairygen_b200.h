@@ -81,6 +81,13 @@ int64_t fgb_gemm_workspace_bytes(fgb_ctx* ctx);
 /* When fgb_gemm_bf16_sk splits: only if k >= min_k (default 6144: the fix-up costs ~15 us, a short-K tile is ~20 us) and the
  * tail fills at most max_tail_frac of the CTA pairs (default 0.9). Tests set min_k = 0 to drive the split path on small shapes. */
 int fgb_gemm_streamk_tune(fgb_ctx* ctx, int32_t min_k, double max_tail_frac);
+/* Host-only self-check of the work list a 2-CTA GEMM launch of this shape would walk on a GPU with sm_count SMs (no device
+ * needed): every (tile, K-block, 128-column half) exactly once, one owner per split tile whose wait list equals the clusters
+ * that dump a partial, split tiles last in their owner's list. with_workspace / min_k as fgb_gemm_bf16_sk / _streamk_tune.
+ * Returns FGB_OK or FGB_ERR_INVALID with fgb_last_error(); the counts (optional) say how many tiles were split along K and how
+ * many half-width tail items there are. Used by the CPU test suite (tests/test_gemm_schedule.py). */
+int fgb_gemm_schedule_check(int32_t m, int32_t n, int32_t k, int32_t sm_count, int32_t with_workspace, int32_t min_k,
+                            int32_t* n_split_tiles, int32_t* n_half_items);
 
 /* Same with a second operand pair folded in as extra K-blocks:  acc = A·Wᵀ + A2·W2ᵀ  (a2 [m, k2], w2 [n, k2], k2 % 8 == 0).
  * Used by the stage-2 LoRA forward (training_module.py:317-352): y = W₁x + b + (B2*mask*2)(A1 x) without re-merging the
