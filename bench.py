@@ -465,8 +465,10 @@ def run_ours(args):
     for name in ("ln_modulate", "ln_affine", "rmsnorm_rope", "rmsnorm"):
         kt = kernels.get(name)
         if kt and kt["avg_ms"] > 0:
-            gbs = x_bytes / (kt["avg_ms"] * 1e-3) / 1e9
-            hbm[name] = {"achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3), "bytes_per_launch": x_bytes,
+            # the q/k norm + RoPE launch (fgb_qk_norm_rope; fgb_recv_norm_rope under Ulysses) reads and writes BOTH q and k: 2 x 2X/P
+            nbytes = 2 * x_bytes if name == "rmsnorm_rope" else x_bytes
+            gbs = nbytes / (kt["avg_ms"] * 1e-3) / 1e9
+            hbm[name] = {"achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3), "bytes_per_launch": nbytes,
                          "avg_launch_us": round(kt["avg_ms"] * 1e3, 2)}
 
     line = {
