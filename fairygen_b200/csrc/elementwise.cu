@@ -34,6 +34,57 @@ __device__ __forceinline__ float head_ss(float ss) {
   return ss;
 }
 
+// LayerNorm arithmetic shared by the one-row-per-warp kernel and the row-streaming kernel (same bits from both). The kernels
+// are issue-bound at the capped in-step clock, so statistics and normalisation run as packed fp32x2 operations (two elements per
+// FADD2 / FFMA2): each lane's result is the IEEE result of the scalar operation; only the order of the partial sums differs
+// from a single sequential accumulator (even and odd elements are summed separately).
+template <int NV>
+__device__ __forceinline__ void ln_row_stats(const uint4 (&v)[NV], float eps, float& mean, float& rstd) {
+  constexpr int D = NV * 256;
+  // One pass for both moments, shifted by the row's first element K so that E[(x-K)^2] - E[x-K]^2 does not cancel:
+  // mean = K + s/D, var = q/D - (s/D)^2.
+  const float K = __shfl_sync(0xffffffffu, bf16_lo(v[0].x), 0);
+  const uint64_t nk2 = pack2(-K, -K);
+  uint64_t s2 = pack2(0.f, 0.f), q2 = pack2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t d2 = add2(pack2(bf16_lo(w[j]), bf16_hi(w[j])), nk2);
+      s2 = add2(s2, d2);
+      q2 = fma2(d2, d2, q2);
+    }
+  }
+  float sa, sb, qa, qb;
+  unpack2(s2, sa, sb);
+  unpack2(q2, qa, qb);
+  const float s1 = warp_sum(sa + sb) * (1.0f / D);
+  const float q1 = warp_sum(qa + qb) * (1.0f / D);
+  mean = K + s1;
+  rstd = rsqrtf(fmaxf(q1 - s1 * s1, 0.f) + eps);
+}
+
+// One 16-byte vector of the row: normalise and apply (weight, bias) [AFFINE: F.layer_norm, one rounding] or the adaLN
+// modulation row (scale, shift) with the reference's bf16 rounding points (DIT:63-64).
+template <bool AFFINE>
+__device__ __forceinline__ uint4 ln_apply(const uint4& xv, const uint4& av, const uint4& bv, float rstd, float nmr) {
+  const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+  const uint64_t r2 = pack2(rstd, rstd), n2 = pack2(nmr, nmr);
+  uint32_t o[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    uint64_t t2 = fma2(pack2(bf16_lo(xw[w]), bf16_hi(xw[w])), r2, n2);
+    if (AFFINE) t2 = fma2(t2, pack2(bf16_lo(aw[w]), bf16_hi(aw[w])), pack2(bf16_lo(bw[w]), bf16_hi(bw[w])));
+    float lo, hi;
+    unpack2(t2, lo, hi);
+    const uint32_t n = pack_bf16(lo, hi);
+    // norm(x) -> bf16 ; (1 + scale) -> bf16 ; product -> bf16 ; + shift -> bf16, two elements per op
+    o[w] = AFFINE ? n : add_bf16x2(mul_bf16x2(n, add_bf16x2(0x3F803F80u, aw[w])), bw[w]);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm (no affine) + adaLN modulate, or LayerNorm with affine.      DIT:205-207, 63-64, 224-227
 // NV = dim / 256 16-byte vectors per lane.
@@ -51,25 +102,8 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __res
   uint4 v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = ldg_nc_v4(xr + i * 32 + lane);
-  // One pass for both moments, shifted by the row's first element K so that E[(x-K)^2] - E[x-K]^2 does not cancel:
-  // mean = K + s/D, var = q/D - (s/D)^2.
-  const float K = __shfl_sync(0xffffffffu, bf16_lo(v[0].x), 0);
-  float s1 = 0.f, q1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float f[8];
-    unpack8(v[i], f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float d = f[e] - K;
-      s1 += d;
-      q1 = fmaf(d, d, q1);
-    }
-  }
-  s1 = warp_sum(s1) * (1.0f / D);
-  q1 = warp_sum(q1) * (1.0f / D);
-  const float mean = K + s1;
-  const float rstd = rsqrtf(fmaxf(q1 - s1 * s1, 0.f) + eps);
+  float mean, rstd;
+  ln_row_stats<NV>(v, eps, mean, rstd);
   // AFFINE: (shift0, scale0) carry (bias, weight). Otherwise pick the modulation row of this token.
   const bool first = AFFINE || row < rows_mod0;
   const uint4* sh = reinterpret_cast<const uint4*>(first ? shift0 : shift1);
@@ -77,29 +111,7 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __res
   uint4* yr = reinterpret_cast<uint4*>(y + static_cast<int64_t>(row) * ldy);
   const float nmr = -mean * rstd;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float f[8];
-    unpack8(v[i], f);
-    const uint4 av = __ldg(sc + i * 32 + lane), bv = __ldg(sh + i * 32 + lane);
-    if (AFFINE) {
-      float a[8], b[8];
-      unpack8(av, a);
-      unpack8(bv, b);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], rstd, nmr) * a[e] + b[e];   // F.layer_norm with weight/bias: one rounding
-      yr[i * 32 + lane] = pack8(f);
-    } else {
-      // norm(x) -> bf16 ; (1 + scale) -> bf16 ; product -> bf16 ; + shift -> bf16   (DIT:63-64), two elements per op
-      const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
-      uint32_t o[4];
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint32_t n = pack_bf16(fmaf(f[2 * w], rstd, nmr), fmaf(f[2 * w + 1], rstd, nmr));
-        o[w] = add_bf16x2(mul_bf16x2(n, add_bf16x2(0x3F803F80u, aw[w])), bw[w]);
-      }
-      yr[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-  }
+  for (int i = 0; i < NV; ++i) yr[i * 32 + lane] = ln_apply<AFFINE>(v[i], __ldg(sc + i * 32 + lane), __ldg(sh + i * 32 + lane), rstd, nmr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -787,52 +799,15 @@ struct LnStreamOp {
   int rows_mod0;
   __device__ __forceinline__ const __nv_bfloat16* src(int item) const { return x + static_cast<int64_t>(item) * ldx; }
   __device__ __forceinline__ void row(int row, int lane, uint4 (&v)[NV]) {
-    constexpr int D = NV * 256;
-    const float K = __shfl_sync(0xffffffffu, bf16_lo(v[0].x), 0);
-    float s1 = 0.f, q1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float f[8];
-      unpack8(v[i], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = f[e] - K;
-        s1 += d;
-        q1 = fmaf(d, d, q1);
-      }
-    }
-    s1 = warp_sum(s1) * (1.0f / D);
-    q1 = warp_sum(q1) * (1.0f / D);
-    const float mean = K + s1;
-    const float rstd = rsqrtf(fmaxf(q1 - s1 * s1, 0.f) + eps);
+    float mean, rstd;
+    ln_row_stats<NV>(v, eps, mean, rstd);
     const bool first = AFFINE || row < rows_mod0;
     const uint4* sh = reinterpret_cast<const uint4*>(first ? shift0 : shift1);
     const uint4* sc = reinterpret_cast<const uint4*>(first ? scale0 : scale1);
     uint4* yr = reinterpret_cast<uint4*>(y + static_cast<int64_t>(row) * ldy);
     const float nmr = -mean * rstd;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float f[8];
-      unpack8(v[i], f);
-      const uint4 av = __ldg(sc + i * 32 + lane), bv = __ldg(sh + i * 32 + lane);
-      if (AFFINE) {
-        float a[8], b[8];
-        unpack8(av, a);
-        unpack8(bv, b);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], rstd, nmr) * a[e] + b[e];
-        yr[i * 32 + lane] = pack8(f);
-      } else {
-        const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const uint32_t n = pack_bf16(fmaf(f[2 * w], rstd, nmr), fmaf(f[2 * w + 1], rstd, nmr));
-          o[w] = add_bf16x2(mul_bf16x2(n, add_bf16x2(0x3F803F80u, aw[w])), bw[w]);
-        }
-        yr[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
-      }
-    }
+    for (int i = 0; i < NV; ++i) yr[i * 32 + lane] = ln_apply<AFFINE>(v[i], __ldg(sc + i * 32 + lane), __ldg(sh + i * 32 + lane), rstd, nmr);
   }
   __device__ __forceinline__ void finish(int, int) {}
 };
