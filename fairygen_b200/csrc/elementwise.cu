@@ -114,6 +114,36 @@ ln_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __res
   for (int i = 0; i < NV; ++i) yr[i * 32 + lane] = ln_apply<AFFINE>(v[i], __ldg(sc + i * 32 + lane), __ldg(sh + i * 32 + lane), rstd, nmr);
 }
 
+// RMSNorm arithmetic shared by every kernel that normalises a row (same bits from all of them): sum of squares and the
+// scale step as packed fp32x2 operations (see ln_row_stats).
+template <int NV>
+__device__ __forceinline__ float rms_row_sumsq(const uint4 (&v)[NV]) {
+  uint64_t q2 = pack2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t x2 = pack2(bf16_lo(w[j]), bf16_hi(w[j]));
+      q2 = fma2(x2, x2, q2);
+    }
+  }
+  float a, b;
+  unpack2(q2, a, b);
+  return a + b;     // this lane's part; the caller sums over the warp
+}
+// norm -> bf16, * weight -> bf16 (DIT:99-110), two elements per operation
+__device__ __forceinline__ void rms_scale_weight(const uint4& xv, const uint4& wv, float rs, uint32_t (&o)[4]) {
+  const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+  const uint64_t r2 = pack2(rs, rs);
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    float lo, hi;
+    unpack2(mul2(pack2(bf16_lo(xw[w]), bf16_hi(xw[w])), r2), lo, hi);
+    o[w] = mul_bf16x2(pack_bf16(lo, hi), ww[w]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // RMSNorm over the full row (all heads) + optional 3-D RoPE, in place.      DIT:91-110, 140-144
 // ---------------------------------------------------------------------------------------------
@@ -143,14 +173,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
   uint4 v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float f[8];
-    unpack8(v[i], f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) sq += f[e] * f[e];
-  }
+  const float sq = rms_row_sumsq<NV>(v);
   const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
 
   // Every vector of this lane starts at column (i*32+lane)*8, i.e. head-local complex lanes
@@ -178,14 +201,8 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, int rows, float 
   const uint4* wr = reinterpret_cast<const uint4*>(weight);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    float f[8];
-    unpack8(v[i], f);
-    const uint4 wv = __ldg(wr + i * 32 + lane);
-    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
     uint32_t o[4];
-#pragma unroll
-    for (int w = 0; w < 4; ++w)   // norm -> bf16, * weight -> bf16 (two elements per op)
-      o[w] = mul_bf16x2(pack_bf16(f[2 * w] * rs, f[2 * w + 1] * rs), ww[w]);
+    rms_scale_weight(v[i], __ldg(wr + i * 32 + lane), rs, o);
     if (rotate) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -268,26 +285,13 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int rows, float
       uint4 v[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
-      float sq = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        float f[8];
-        unpack8(v[i], f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sq += f[e] * f[e];
-      }
+      const float sq = rms_row_sumsq<NV>(v);
       const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
       const uint4* wr = reinterpret_cast<const uint4*>(g == 0 ? wq : wk);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        float f[8];
-        unpack8(v[i], f);
-        const uint4 wv = __ldg(wr + i * 32 + lane);
-        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
         uint32_t o[4];
-#pragma unroll
-        for (int w = 0; w < 4; ++w)   // norm -> bf16, * weight -> bf16 (two elements per op)
-          o[w] = mul_bf16x2(pack_bf16(f[2 * w] * rs, f[2 * w + 1] * rs), ww[w]);
+        rms_scale_weight(v[i], __ldg(wr + i * 32 + lane), rs, o);
         if (rotate) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -660,14 +664,8 @@ recv_norm_rope_kernel(__nv_bfloat16* __restrict__ recv, int s_pad, int tokens, i
         const int c = pass * 32 + lane;
         float ss = 0.f;
         if (c < vecs) {
-          float f[8];
-          unpack8(row[c], f);
-          const uint4 wv = __ldg(wr + c);
-          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
           uint32_t o[4];
-#pragma unroll
-          for (int w = 0; w < 4; ++w)   // norm -> bf16, * weight -> bf16 (two elements per op), as rmsnorm_rope_kernel
-            o[w] = mul_bf16x2(pack_bf16(f[2 * w] * rs, f[2 * w + 1] * rs), ww[w]);
+          rms_scale_weight(row[c], __ldg(wr + c), rs, o);
           if (rotate) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -832,14 +830,7 @@ struct RmsStreamOp {
     constexpr int D = NV * 256;
     const int r = SEGS == 2 ? item >> 1 : item;
     const int g = SEGS == 2 ? item & 1 : 0;
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float f[8];
-      unpack8(v[i], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sq += f[e] * f[e];
-    }
+    const float sq = rms_row_sumsq<NV>(v);
     const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
     float cs[4], sn[4];
     bool rotate = false;
@@ -863,13 +854,8 @@ struct RmsStreamOp {
     uint4* xr = reinterpret_cast<uint4*>(dst(item));
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      float f[8];
-      unpack8(v[i], f);
-      const uint4 wv = __ldg(wr + i * 32 + lane);
-      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
       uint32_t o[4];
-#pragma unroll
-      for (int w = 0; w < 4; ++w) o[w] = mul_bf16x2(pack_bf16(f[2 * w] * rs, f[2 * w + 1] * rs), ww[w]);
+      rms_scale_weight(v[i], __ldg(wr + i * 32 + lane), rs, o);
       if (rotate) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
