@@ -40,6 +40,7 @@ SIGNATURES = {
     "fgb_attn_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64, _P, _I64,
                                     _I32, _I32, _I32, _F, _P]),
     "fgb_attn_workspace_bytes": (c_int64, [_P, _I32, _I32, _I32]),
+    "fgb_attn_schedule_check": (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, ctypes.POINTER(c_int32), ctypes.POINTER(c_int32)]),
     "fgb_ipc_export": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(c_int64)]),
     "fgb_ipc_open": (ctypes.c_int, [_P, _P, _I64, ctypes.POINTER(c_void_p)]),
     "fgb_ipc_close": (ctypes.c_int, [_P, _P, _I64]),

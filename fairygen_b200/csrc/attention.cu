@@ -25,6 +25,7 @@
 //                    columns as packed bf16 (tcgen05.st); O is normalised at the end.
 // TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P_i aliases columns [0,32) and [64,96) of S_i.
 #include <cstdlib>
+#include <vector>
 
 #include "attention_common.cuh"
 
@@ -895,6 +896,51 @@ static int attn_fwd_impl(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k
     attn_combine_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(p, n_split);
     FGB_LAUNCH_CHECK("attn_combine_kernel");
   }
+  return FGB_OK;
+}
+
+// Host-side walk of the work list of one attention launch (no device needed): the persistent CTAs take items w0, w0 + stride, ...
+// of [n_full whole units | split units x split key chunks]; every (unit, KV tile) must be visited exactly once, chunks must be
+// non-empty, and the partial buffers must fit the workspace fgb_attn_workspace_bytes() asks for. The item -> (unit, KV range)
+// arithmetic below is the kernel's decode_item, restated (the kernel keeps its lambda so that its code does not change).
+extern "C" int fgb_attn_schedule_check(int32_t s_q, int32_t s_kv, int32_t heads, int32_t sm_count, int32_t with_workspace,
+                                       int32_t* split_out, int32_t* n_split_units_out) {
+  using namespace fgb;
+  if (s_q <= 0 || s_kv <= 0 || heads <= 0 || sm_count <= 0) return set_error(FGB_ERR_INVALID, "fgb_attn_schedule_check: bad shape");
+  const int item_rows = 2 * kTile;
+  const int n_pairs = (s_q + item_rows - 1) / item_rows;
+  const int units = n_pairs * heads;
+  const int n_kv_all = (s_kv + kTile - 1) / kTile;
+  int split = 1, n_split = 0;
+  if (with_workspace) plan_split(units, n_kv_all, sm_count, &split, &n_split);
+  fgb_ctx ctx;
+  ctx.sm_count = sm_count;
+  const int64_t need = static_cast<int64_t>(n_split) * split * item_rows * (128 * 4 + 8);
+  if (with_workspace && need != fgb_attn_workspace_bytes(&ctx, s_q, s_kv, heads))
+    return set_error(FGB_ERR_INVALID, "attention schedule: workspace %lld != fgb_attn_workspace_bytes", (long long)need);
+  const int n_full = units - n_split, n_items = n_full + n_split * split;
+  std::vector<int> seen(static_cast<size_t>(units) * n_kv_all, 0);
+  const int workers = n_items < sm_count ? n_items : sm_count;
+  int visited = 0;
+  for (int cta = 0; cta < workers; ++cta)
+    for (int w = cta; w < n_items; w += workers, ++visited) {
+      int unit = w, kv_lo = 0, kv_hi = n_kv_all;
+      if (unit >= n_full) {
+        const int part = unit - n_full, chunk = part % split;
+        unit = n_full + part / split;
+        kv_lo = static_cast<int>(static_cast<int64_t>(chunk) * n_kv_all / split);
+        kv_hi = static_cast<int>(static_cast<int64_t>(chunk + 1) * n_kv_all / split);
+        if (part >= n_split * split) return set_error(FGB_ERR_INVALID, "attention schedule: partial slot %d outside the workspace", part);
+      }
+      if (unit < 0 || unit >= units || kv_hi <= kv_lo)
+        return set_error(FGB_ERR_INVALID, "attention schedule: item %d -> unit %d, KV tiles [%d,%d)", w, unit, kv_lo, kv_hi);
+      for (int j = kv_lo; j < kv_hi; ++j) ++seen[static_cast<size_t>(unit) * n_kv_all + j];
+    }
+  if (visited != n_items) return set_error(FGB_ERR_INVALID, "attention schedule: %d of %d items visited", visited, n_items);
+  for (size_t i = 0; i < seen.size(); ++i)
+    if (seen[i] != 1) return set_error(FGB_ERR_INVALID, "attention schedule: (unit, KV tile) %zu visited %d times", i, seen[i]);
+  if (split_out) *split_out = split;
+  if (n_split_units_out) *n_split_units_out = n_split;
   return FGB_OK;
 }
 

@@ -115,6 +115,11 @@ int fgb_attn_fwd_ex(fgb_ctx* ctx, const void* q, int64_t ldq, const void* k, int
                     int64_t ldv, void* o, int64_t ldo, int32_t s_q, int32_t s_kv, int32_t heads, float scale,
                     void* lse, int64_t ld_lse, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t fgb_attn_workspace_bytes(fgb_ctx* ctx, int32_t s_q, int32_t s_kv, int32_t heads);
+/* Host-only self-check of the work list an attention launch of this shape walks on sm_count SMs (no device needed): every
+ * (256-query unit, KV tile) exactly once, non-empty key chunks, partial slots inside the workspace. The counts (optional) say
+ * how the last wave is cut: `split` key chunks for each of `n_split_units` units. Used by tests/test_gemm_schedule.py. */
+int fgb_attn_schedule_check(int32_t s_q, int32_t s_kv, int32_t heads, int32_t sm_count, int32_t with_workspace, int32_t* split,
+                            int32_t* n_split_units);
 
 /* Bounded-score softmax. kmax2[head] = max_j ||k[j, head]||^2 (fgb_head_norm_max) gives |q_i·k_j|·scale·log2e <= B_i =
  * ||q_i||·sqrt(kmax2)·scale·log2e, from which every query row gets a FIXED reference R_i for its exponentials P = 2^(s - R_i):

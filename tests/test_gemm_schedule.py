@@ -52,3 +52,30 @@ def test_sweep_of_shapes_and_machine_sizes():
                         check(m, n, k, sms=sms, ws=ws, min_k=min_k)
                         n_checked += 1
     assert n_checked == 5 * 10 * 7 * 6 * 3
+
+
+def check_attn(s_q, s_kv, heads, sms=148, ws=1):
+    lib = _lib.lib()
+    split, n_split = ctypes.c_int32(-1), ctypes.c_int32(-1)
+    rc = lib.fgb_attn_schedule_check(s_q, s_kv, heads, sms, ws, ctypes.byref(split), ctypes.byref(n_split))
+    assert rc == 0, (s_q, s_kv, heads, sms, ws, lib.fgb_last_error().decode())
+    return split.value, n_split.value
+
+
+def test_attention_work_lists():
+    """The persistent attention kernel's list [whole units | split units x key chunks] (plan_split + decode_item): every
+    (256-query unit, KV tile) once, for the headline shape on 1 / 2 / 4 / 8-way head splits and a sweep of ragged shapes."""
+    # headline self-attention: 107 pairs x 24 heads = 2568 units = 17 waves of 148 + 52 -> the tail is cut along the keys
+    split, n = check_attn(27280, 27280, 24)
+    assert n == 2568 % 148 and split > 1
+    # 3 heads per rank (Ulysses SP8): 321 units = 2 waves + 25
+    split, n = check_attn(27280, 27280, 3)
+    assert n == 321 % 148 and split >= 2
+    assert check_attn(27280, 512, 24) == (1, 0)              # cross-attention: 4 KV tiles, nothing to split
+    assert check_attn(27280, 27280, 24, ws=0) == (1, 0)       # no workspace, no split
+    for sms in (148, 132, 16, 1):
+        for s_q in (1, 255, 256, 257, 4100, 8190, 27280):
+            for s_kv in (1, 127, 128, 129, 512, 2047, 2048, 4100, 27280):
+                for heads in (1, 2, 3, 6, 12, 24):
+                    for ws in (0, 1):
+                        check_attn(s_q, s_kv, heads, sms=sms, ws=ws)
