@@ -200,3 +200,60 @@ def test_four_step_cfg_denoise_matches_the_reference_loop(engine, monkeypatch):
     gold = torch.from_numpy(np.load(os.path.join(os.path.dirname(__file__), "golden", "denoise.npz"))["final"])
     assert torch.equal(out[:, :, 0:1], z0.to(BF))
     assert rel(out.float(), gold) < 3e-2, rel(out.float(), gold)            # north star: <= 3e-2 after a schedule
+
+
+def test_query_bound_plumbing_does_not_change_the_forward(engine):
+    """FGB_QMAX / engine.query_bounds: the norm kernels are asked for the per-head query bounds and the attention calls receive
+    them (fgb_attn_fwd_bounded_qk) — the result is the same softmax, so the forward must not move."""
+    eng, w16 = engine
+    lat, z0, cp, cn = o.make_inputs(o.TINY, (1, 48, 3, 8, 8), text_len=32, live_text=8)
+    ts = torch.tensor([500.0])
+    base = eng.forward(lat.to(BF), ts, cp.to(BF), True)
+    seen = []
+    from fairygen_b200 import ops
+    inner = ops.attention
+
+    def spy(q, k, v, out, heads, scale=None, lse=None, kmax2=None, qmax2=None):
+        seen.append(None if qmax2 is None else qmax2.clone())
+        return inner(q, k, v, out, heads, scale=scale, lse=lse, kmax2=kmax2, qmax2=qmax2)
+
+    ops.attention = spy
+    try:
+        for bits, want in ((0, [False, False]), (1, [True, False]), (2, [False, True]), (3, [True, True])):
+            eng.query_bounds = bits
+            seen.clear()
+            out = eng.forward(lat.to(BF), ts, cp.to(BF), True)
+            assert torch.equal(out, base)
+            per_block = [(s is not None) for s in seen[:2]]          # block 0: self-attention call, cross-attention call
+            assert per_block == want, (bits, per_block)
+            for s in seen:
+                assert s is None or (s.shape == (eng.cfg.num_heads,) and bool((s > 0).all()))
+    finally:
+        ops.attention = inner
+        eng.query_bounds = 0
+
+
+def test_denoiser_uploads_host_prompt_embeddings_once():
+    """WanDenoiser.step accepts the prompt embeddings as HOST tensors on every step (what a pipeline that keeps them on the CPU
+    does): equal content resolves to the same device tensor (so the engine's context cache hits by identity), new content
+    uploads once, device tensors pass through, and only the last four contexts are remembered."""
+    import types
+
+    from fairygen_b200.pipeline import WanDenoiser
+
+    den = WanDenoiser.__new__(WanDenoiser)
+    den.engine = types.SimpleNamespace(device=torch.device("cpu"))
+    den._host_contexts = []
+    a = torch.randn(1, 16, 8)
+    d1 = den._context_on_device(a)
+    assert d1.dtype == BF and den._context_on_device(a) is d1 and den._context_on_device(a.clone()) is d1
+    b = a.clone()
+    b[0, 0, 0] += 1
+    d2 = den._context_on_device(b)
+    assert d2 is not d1 and den._context_on_device(b.clone()) is d2 and den._context_on_device(a) is d1
+    a.add_(1)                                   # the caller edits its tensor in place: the private host copy still says "old content"
+    assert den._context_on_device(a) is not d1
+    assert den._context_on_device(None) is None
+    for i in range(6):
+        den._context_on_device(torch.full((1, 4, 8), float(i)))
+    assert len(den._host_contexts) == 4
