@@ -409,6 +409,8 @@ def run_ours(args):
     h.barrier()
     e2e_ms = h.max_over_ranks(e0.elapsed_time(e1)) / args.steps
     finite = bool(torch.isfinite(out_h.float()).all())
+    if getattr(engine, "sp", None) is not None:
+        engine.sp.check()       # an exchange barrier that gave up on a peer invalidates the run: fail here, not in the numbers
 
     # ---- N > 1: the other layout, then parity at the ragged shape (every rank takes part)
     layouts = None

@@ -49,6 +49,7 @@ SIGNATURES = {
                                                 _I32, _I32, _I32, _I32, _P]),
     "fgb_sp_return_heads": (ctypes.c_int, [_P, _P, _I64, ctypes.POINTER(c_void_p), _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "fgb_sp_barrier": (ctypes.c_int, [_P, ctypes.POINTER(c_void_p), _I32, _I32, _I32, _P]),
+    "fgb_sp_barrier_status": (ctypes.c_int, [_P, ctypes.POINTER(c_void_p), _I32, _I32, _I32, _P, _I64, _P]),
     "fgb_gemm_qkv_scatter": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _I32, _I32, _I32, ctypes.POINTER(c_void_p), _I32, _I32, _P, _P, _I64,
                                             _P]),
     "fgb_gemm_bf16_sk": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _P, _I64, _P]),

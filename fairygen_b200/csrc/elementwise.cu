@@ -568,11 +568,12 @@ __global__ void sp_return_heads_kernel(const __nv_bfloat16* __restrict__ x, int6
 
 // Cross-GPU barrier for the exchange: thread q publishes `epoch` in peer q's flag slot [rank] (release, system scope)
 // and then waits until peer q has published `epoch` in ours (acquire). All earlier peer stores of this stream are
-// complete (kernel boundary) and made visible by the fence. Bounded: traps after ~30 s (ranks can be seconds apart at
-// start-up) instead of hanging the box.
-__global__ void sp_barrier_kernel(PeerPtrs flags, int world, int rank, int epoch) {
-  const int q = threadIdx.x;
-  if (q >= world) return;
+// complete (kernel boundary) and made visible by the fence. Bounded: after `limit` clocks (default ~30 s; ranks can be
+// seconds apart at start-up) the waiting thread writes the epoch to *status and gives up, so the host can name the failure
+// (fgb_sp_barrier_status); without a status word the kernel traps instead of hanging the box.
+constexpr long long kBarrierClocks = 50000000000ll;
+
+__device__ __forceinline__ void sp_epoch_exchange(const PeerPtrs& flags, int q, int rank, int epoch, int* status, long long limit) {
   __threadfence_system();
   int* remote = static_cast<int*>(flags.p[q]) + rank;
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
@@ -582,9 +583,19 @@ __global__ void sp_barrier_kernel(PeerPtrs flags, int world, int rank, int epoch
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
     if (v - epoch >= 0) break;
-    if (clock64() - t0 > 50000000000ll) __trap();
+    if (clock64() - t0 > limit) {   // a peer died or never launched: report instead of hanging
+      if (status == nullptr) __trap();
+      atomicExch(status, epoch);
+      break;
+    }
   }
   __threadfence_system();
+}
+
+__global__ void sp_barrier_kernel(PeerPtrs flags, int world, int rank, int epoch, int* __restrict__ status, long long limit) {
+  const int q = threadIdx.x;
+  if (q >= world) return;
+  sp_epoch_exchange(flags, q, rank, epoch, status, limit);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -607,21 +618,7 @@ sp_stats_barrier_kernel(PeerPtrs flags, PeerPtrs stats, float* __restrict__ rows
   __syncthreads();
   const int q = threadIdx.x;
   if (q >= world) return;
-  __threadfence_system();
-  int* remote = static_cast<int*>(flags.p[q]) + rank;
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
-  const int* mine = static_cast<const int*>(flags.p[rank]) + q;
-  const long long t0 = clock64();
-  for (;;) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-    if (v - epoch >= 0) break;
-    if (clock64() - t0 > 50000000000ll) {   // ~30 s: a peer died. Report instead of hanging or trapping.
-      if (status) atomicExch(status, epoch);
-      break;
-    }
-  }
-  __threadfence_system();
+  sp_epoch_exchange(flags, q, rank, epoch, status, kBarrierClocks);
 }
 
 // RMSNorm (statistics of the FULL row, received with the data) + weight + 3-D RoPE on the received q and k groups, in place:
@@ -1182,14 +1179,21 @@ extern "C" int fgb_sp_scatter_heads(fgb_ctx* ctx, const void* x, int64_t ldx, vo
   return FGB_OK;
 }
 
-extern "C" int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* stream) {
+extern "C" int fgb_sp_barrier_status(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* status,
+                                     int64_t timeout_clocks, void* stream) {
   FGB_CHECK_ARG(ctx && peer_flags && world > 0 && world <= FGB_MAX_PEERS && rank >= 0 && rank < world, "fgb_sp_barrier: bad argument");
+  FGB_CHECK_ARG(timeout_clocks >= 0, "fgb_sp_barrier: timeout_clocks=%lld", static_cast<long long>(timeout_clocks));
   PeerPtrs pp;
   for (int i = 0; i < FGB_MAX_PEERS; ++i) pp.p[i] = i < world ? peer_flags[i] : nullptr;
   for (int i = 0; i < world; ++i) FGB_CHECK_ARG(pp.p[i], "fgb_sp_barrier: peer flag array %d is NULL", i);
-  sp_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pp, world, rank, epoch);
+  sp_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pp, world, rank, epoch, static_cast<int*>(status),
+                                                                     timeout_clocks > 0 ? timeout_clocks : kBarrierClocks);
   FGB_LAUNCH_CHECK("sp_barrier_kernel");
   return FGB_OK;
+}
+
+extern "C" int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* stream) {
+  return fgb_sp_barrier_status(ctx, peer_flags, world, rank, epoch, nullptr, 0, stream);
 }
 
 extern "C" int fgb_rmsnorm_rope_scatter(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t rows, int32_t dim, float eps,

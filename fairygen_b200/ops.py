@@ -441,8 +441,16 @@ def recv_norm_rope(recv, tokens: int, hpr: int, stats, dim: int, eps: float, wq,
                                              _p(rope_tab), grid[0], grid[1], grid[2], _p(kmax2), _p(qmax2), _stream()), "fgb_recv_norm_rope")
 
 
-def sp_barrier(device, flag_ptrs, world: int, rank: int, epoch: int):
-    _lib.check(_lib.lib().fgb_sp_barrier(context(device).handle, _ptr_array(flag_ptrs), world, rank, epoch, _stream()), "fgb_sp_barrier")
+def sp_barrier(device, flag_ptrs, world: int, rank: int, epoch: int, status: Optional[torch.Tensor] = None, timeout_clocks: int = 0):
+    """Epoch barrier of the Ulysses exchange.  With ``status`` (device int32, zero while healthy) a peer that does not answer
+    within ``timeout_clocks`` SM clocks (0 = ~30 s) is reported there and the kernel returns; without it the kernel traps."""
+    if status is None:
+        _lib.check(_lib.lib().fgb_sp_barrier(context(device).handle, _ptr_array(flag_ptrs), world, rank, epoch, _stream()), "fgb_sp_barrier")
+        return
+    if status.dtype != torch.int32 or status.numel() < 1:
+        raise ValueError(f"sp_barrier: status must be a device int32, got {status.dtype} x {status.numel()}")
+    _lib.check(_lib.lib().fgb_sp_barrier_status(context(device).handle, _ptr_array(flag_ptrs), world, rank, epoch, _p(status),
+                                                int(timeout_clocks), _stream()), "fgb_sp_barrier_status")
 
 
 def attention_scatter(q, k, v, o_peer_ptrs, ldo: int, rows_per_peer: int, col_offset: int, heads: int, scale: Optional[float] = None,

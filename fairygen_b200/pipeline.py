@@ -73,4 +73,7 @@ class WanDenoiser:
             lat[:, :, 0:1] = z0  # ImageEmbedderFused plants the clean first frame (PIPE:496)
         for i in (steps if steps is not None else range(self.num_steps)):
             self.step(i, lat, cp, cn, z0)
+        sp = getattr(self.engine, "sp", None)
+        if sp is not None:
+            sp.check()      # a timed-out exchange barrier leaves stale peer data in the result: say so here, once per video
         return lat

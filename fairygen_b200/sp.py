@@ -132,7 +132,20 @@ class SequenceParallel:
         ar = self.arena
         if which == 0:
             ar.epoch += 1
-        ops.sp_barrier(device, ar.flag_ptrs[which], self.world, self.rank, ar.epoch)
+        ops.sp_barrier(device, ar.flag_ptrs[which], self.world, self.rank, ar.epoch, ar.status)
+
+    def check(self) -> None:
+        """Raise if a barrier of the exchange gave up on a peer (fgb_sp_barrier_status / fgb_sp_stats_barrier write the epoch
+        of the first time-out into the arena's status word and let the stream run on): everything computed since then read
+        stale peer data.  One 4-byte device read — call it where a result leaves the GPU (WanDenoiser does, after the loop)."""
+        ar = self.arena
+        if ar is None or self.exchange != "p2p":
+            return
+        epoch = int(ar.status.item())
+        if epoch != 0:
+            raise RuntimeError(f"fairygen_b200 sequence parallel: rank {self.rank} of {self.world} waited ~30 s at exchange barrier "
+                               f"epoch {epoch} (now at {ar.epoch}) for a peer that never arrived — a rank died or fell out of step; "
+                               "results since that epoch are invalid")
 
     # ---- collectives (thin: NCCL on device tensors, gloo in the CPU tests) ----------------------
     def all_to_all(self, recv: torch.Tensor, send: torch.Tensor) -> torch.Tensor:
@@ -199,7 +212,7 @@ class SequenceParallel:
                 recv = ar.recv
                 k("attn_self", ops.attention_scatter, recv[:, :wloc], recv[:tokens, wloc:2 * wloc], recv[:tokens, 2 * wloc:], ar.o_ptrs,
                   heads * 128, rows, self.rank * wloc, hpr, kmax2=kmax2, qmax2=qmax2)
-                k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[1], self.world, self.rank, ar.epoch)
+                k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[1], self.world, self.rank, ar.epoch, ar.status)
                 return
             if qkv_gemm is None:
                 self._scatter_rows(engine, qkv, 0, rows, norm)
@@ -222,13 +235,13 @@ class SequenceParallel:
                 self._scatter_rows(engine, qkv, half, rows, norm)
                 main.wait_event(self._ev[1])
             ar.epoch += 1
-            k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[0], self.world, self.rank, ar.epoch)
+            k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[0], self.world, self.rank, ar.epoch, ar.status)
             recv = ar.recv
             kmax2 = ws["kmax2"][:hpr]
             k("head_norm_max", ops.head_norm_max, recv[:tokens, wloc:2 * wloc], kmax2, hpr)
             k("attn_self", ops.attention_scatter, recv[:, :wloc], recv[:tokens, wloc:2 * wloc], recv[:tokens, 2 * wloc:], ar.o_ptrs,
               heads * 128, rows, self.rank * wloc, hpr, kmax2=kmax2)
-            k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[1], self.world, self.rank, ar.epoch)
+            k("sp_barrier", ops.sp_barrier, qkv.device, ar.flag_ptrs[1], self.world, self.rank, ar.epoch, ar.status)
             return
         if qkv_gemm is not None:
             qkv_gemm(0, qkv.shape[0])

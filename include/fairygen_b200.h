@@ -256,6 +256,13 @@ int fgb_rmsnorm_rope_scatter(fgb_ctx* ctx, const void* x, int64_t ldx, int32_t r
 int fgb_sp_return_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* const* peer_bufs, int64_t ld_dst, int32_t rows,
                         int32_t s_pad, int32_t heads, int32_t groups, int32_t world, int32_t rank, void* stream);
 int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* stream);
+/* The same barrier reporting a dead peer instead of trapping: a peer that has not published `epoch` within timeout_clocks SM
+ * clocks (0 = the default, ~30 s) makes the waiting thread write `epoch` to *status (device int32, zero while healthy) and
+ * return; the kernels behind it then run on stale peer data, so the host must look at *status before it trusts a result
+ * (fairygen_b200.sp.SequenceParallel.check). fgb_sp_barrier = this call with status NULL: no way to report, the kernel traps
+ * (the stream then fails with a launch error at the next call) rather than hang the box. */
+int fgb_sp_barrier_status(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* status,
+                          int64_t timeout_clocks, void* stream);
 
 /* The same exchange with the SEND side fused into the q|k|v projection (DIT:140-142 + USP:125-146) — the default on GPUs:
  *   fgb_gemm_qkv_scatter  out = a[m,k] · w[3*dim,k]ᵀ + bias, never written locally: the epilogue of the 2-CTA tcgen05 GEMM TMA-stores
@@ -266,8 +273,7 @@ int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t
  *                         after the head split.
  *   fgb_sp_stats_barrier  barrier 0 of the block with the statistics riding along: pushes rowsq into every peer's stats matrix
  *                         (peer_stats[q] = fp32 [2][s_pad], rows [rank*rows, +rows)), zeroes rowsq and kmax2, then exchanges the
- *                         epoch flags like fgb_sp_barrier. A peer that does not answer within ~30 s makes the kernel write the
- *                         epoch to *status (device int32, may be NULL) and return instead of hanging.
+ *                         epoch flags like fgb_sp_barrier_status (default time-out; status NULL = trap on time-out).
  *   fgb_recv_norm_rope    receiver side: RMSNorm with the received full-row statistics, weight slice (wq / wk point at this
  *                         rank's heads), 3-D RoPE (DIT:91-96) on the q and k groups of recv [s_pad, 3*hpr*128], in place; leaves
  *                         kmax2[h] = max over the first `tokens` rows of ||k[t,h]||^2 (the bound fgb_attn_fwd_bounded wants). */

@@ -108,3 +108,34 @@ def test_synthetic_state_dict_is_deterministic_and_lora_changes_targets_only():
     assert set(a) == set(synthetic.param_shapes(tiny))
     changed = {k for k in a if not torch.equal(a[k], b[k])}
     assert changed == {t + ".weight" for t in synthetic.lora_targets(tiny)}
+
+
+def test_exchange_barrier_timeout_surfaces_on_the_host():
+    """SequenceParallel.check reads the arena's status word (written by fgb_sp_barrier_status / fgb_sp_stats_barrier when a peer
+    never reaches an epoch) and raises; WanDenoiser calls it once per video, after the loop."""
+    import types
+
+    from fairygen_b200.pipeline import WanDenoiser
+
+    par = sp.SequenceParallel.__new__(sp.SequenceParallel)
+    par.world, par.rank, par.exchange = 4, 2, "p2p"
+    par.arena = None
+    par.check()                                                     # nothing mapped yet: nothing to report
+    par.arena = types.SimpleNamespace(status=torch.zeros(1, dtype=torch.int32), epoch=12)
+    par.check()
+    par.arena.status[0] = 9
+    with pytest.raises(RuntimeError, match=r"rank 2 of 4 .* epoch 9 \(now at 12\)"):
+        par.check()
+    par.exchange = "nccl"                                           # the library variant has no flags of ours
+    par.check()
+    par.exchange = "p2p"
+
+    den = WanDenoiser.__new__(WanDenoiser)
+    den.engine = types.SimpleNamespace(device=torch.device("cpu"), sp=par)
+    den._host_contexts = []
+    den.scheduler = types.SimpleNamespace(timesteps=[])
+    lat = torch.zeros(1, 4, 2, 2, 2)
+    with pytest.raises(RuntimeError, match="never arrived"):
+        den(lat, torch.zeros(1, 4, 8), None, steps=range(0))
+    par.arena.status[0] = 0
+    assert den(lat, torch.zeros(1, 4, 8), None, steps=range(0)).dtype == torch.bfloat16

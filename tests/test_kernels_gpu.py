@@ -606,3 +606,29 @@ def test_row_streaming_kernels_equal_the_per_warp_kernels(env, rows, dim):
     ops.sync_check()
     assert torch.equal(a, b) and torch.equal(a[:, 2 * dim:], qkv[:, 2 * dim:])
     assert torch.allclose(ka, kb, rtol=1e-6)
+
+
+def test_exchange_barrier_reports_a_missing_peer(env):
+    """fgb_sp_barrier_status on ONE GPU with a stand-in peer (a second flag array on the same device that nobody drives): the
+    barrier publishes its epoch to the peer, gives up after the requested number of clocks, writes the epoch to the status word
+    and returns (the reference's NCCL all-to-all, USP:136-141, would hang; VERDICT r1 asked for a status instead of a trap).
+    Once the "peer" has published, the same call passes and leaves the status alone."""
+    ops, _ = env
+    dev = torch.device("cuda", 0)
+    mine = torch.zeros(64, dtype=torch.int32, device=dev)
+    peer = torch.zeros(64, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ptrs = [mine.data_ptr(), peer.data_ptr()]
+    ops.sp_barrier(dev, ptrs, 2, 0, 5, status=status, timeout_clocks=3_000_000)       # ~2 ms
+    ops.sync_check()
+    assert int(status.item()) == 5
+    assert int(peer[0].item()) == 5 and int(mine[0].item()) == 5 and int(mine[1].item()) == 0
+    status.zero_()
+    mine[1] = 7                                    # the peer is already one exchange ahead: epochs only have to be reached
+    ops.sp_barrier(dev, ptrs, 2, 0, 6, status=status, timeout_clocks=3_000_000)
+    ops.sync_check()
+    assert int(status.item()) == 0 and int(peer[0].item()) == 6
+    with pytest.raises(ValueError):
+        ops.sp_barrier(dev, ptrs, 2, 0, 7, status=torch.zeros(1, device=dev))
+    with pytest.raises(RuntimeError):
+        ops.sp_barrier(dev, ptrs, 9, 0, 7, status=status)
