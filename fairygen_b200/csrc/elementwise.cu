@@ -579,13 +579,15 @@ __device__ __forceinline__ void sp_epoch_exchange(const PeerPtrs& flags, int q, 
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
   const int* mine = static_cast<const int*>(flags.p[rank]) + q;
   const long long t0 = clock64();
-  for (;;) {
+  for (unsigned spins = 1;; ++spins) {
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
     if (v - epoch >= 0) break;
+    // slow path only: an exchange that has already lost a peer does not wait another `limit` at each of its later barriers
+    if ((spins & 1023u) == 0 && status != nullptr && *reinterpret_cast<volatile int*>(status) != 0) break;
     if (clock64() - t0 > limit) {   // a peer died or never launched: report instead of hanging
       if (status == nullptr) __trap();
-      atomicExch(status, epoch);
+      atomicCAS(status, 0, epoch);  // the FIRST epoch that timed out stays in the status word
       break;
     }
   }

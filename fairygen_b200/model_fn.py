@@ -160,6 +160,13 @@ def model_fn_wan_video(
                 sp = SequenceParallel()
                 object.__setattr__(dit, "_fairygen_b200_sp", sp)
     eng = engine_for(dit, sp)
+    if sp is not None:
+        # a barrier of the exchange that gave up on a dead peer leaves its epoch in the arena (fgb_sp_barrier_status): look every
+        # 32 forwards (one 4-byte read; a sync the host-side run-ahead absorbs) so that a lost rank ends the job with a message
+        sp.forwards_since_check = getattr(sp, "forwards_since_check", 0) + 1
+        if sp.forwards_since_check >= 32:
+            sp.forwards_since_check = 0
+            sp.check()
 
     # merged CFG (PIPE:785-803, 1240-1243): one latent, a batch of contexts -> one forward per context
     outs = []

@@ -258,7 +258,8 @@ int fgb_sp_return_heads(fgb_ctx* ctx, const void* x, int64_t ldx, void* const* p
 int fgb_sp_barrier(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* stream);
 /* The same barrier reporting a dead peer instead of trapping: a peer that has not published `epoch` within timeout_clocks SM
  * clocks (0 = the default, ~30 s) makes the waiting thread write `epoch` to *status (device int32, zero while healthy) and
- * return; the kernels behind it then run on stale peer data, so the host must look at *status before it trusts a result
+ * return (later barriers of the same exchange see the word set and stop waiting after ~1000 polls; the first epoch stays in
+ * it); the kernels behind it then run on stale peer data, so the host must look at *status before it trusts a result
  * (fairygen_b200.sp.SequenceParallel.check). fgb_sp_barrier = this call with status NULL: no way to report, the kernel traps
  * (the stream then fails with a launch error at the next call) rather than hang the box. */
 int fgb_sp_barrier_status(fgb_ctx* ctx, void* const* peer_flags, int32_t world, int32_t rank, int32_t epoch, void* status,
