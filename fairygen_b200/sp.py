@@ -66,7 +66,7 @@ class PeerArena:
         self.off_stats = self.off_dqkv + ((rows * 3 * d * 2 + 255) // 256 * 256 if backward else 0)   # fp32 [2][s_pad]: full-row sums of squares of q, k
         self.off_flags = self.off_stats + (2 * s_pad * 4 + 255) // 256 * 256
         total = self.off_flags + 2 * 64 * 4 + 64
-        self.buf = torch.zeros(total, dtype=torch.uint8, device=device)
+        self.buf = self._allocate(total, device)
         self.recv = self.buf[self.off_recv:self.off_recv + s_pad * wloc * 2].view(torch.bfloat16).view(s_pad, wloc)
         self.o = self.buf[self.off_o:self.off_o + rows * d * 2].view(torch.bfloat16).view(rows, d)
         self.dqkv = self.buf[self.off_dqkv:self.off_dqkv + rows * 3 * d * 2].view(torch.bfloat16).view(rows, 3 * d) if backward else None
@@ -91,8 +91,15 @@ class PeerArena:
         self.stats_ptrs = [b + self.off_stats for b in bases]
         self.flag_ptrs = [[b + self.off_flags + which * 64 * 4 for b in bases] for which in (0, 1)]
         self.epoch = 0
-        torch.cuda.synchronize(device)
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize(device)
         dist.barrier(group=group)   # every arena is zeroed and mapped before the first peer store
+
+    @staticmethod
+    def _allocate(nbytes: int, device) -> torch.Tensor:
+        """Backing store of the arena: zeroed device memory (a hook: tests/test_engine_p2p_host.py maps it into shared host
+        memory so that the peer-store exchange can run between CPU processes)."""
+        return torch.zeros(nbytes, dtype=torch.uint8, device=device)
 
     def close(self):
         for ptr, off in self._opened:
