@@ -146,6 +146,8 @@ def _exchange_kernels(ops, shm):
         qf, kf, vf = (t.float().view(t.shape[0], heads, 128).transpose(0, 1) for t in (q, k, v))
         p = torch.softmax(qf @ kf.transpose(1, 2) / 128 ** 0.5, -1)
         out = (p @ vf).transpose(0, 1).reshape(q.shape[0], heads * 128).to(BF)
+        if lse is not None:                                                   # log2-domain log-sum-exp rows of the local heads
+            lse[:, :q.shape[0]] = torch.logsumexp(qf @ kf.transpose(1, 2) / 128 ** 0.5, -1) * 1.4426950408889634
         for peer, ptr in enumerate(o_peer_ptrs):                              # row of global token t -> its owner, at the head columns
             o = shm.view(ptr, (rows_per_peer, ldo), BF)
             o[:, col_offset:col_offset + heads * 128] = out[peer * rows_per_peer:(peer + 1) * rows_per_peer]
@@ -157,6 +159,13 @@ def _exchange_kernels(ops, shm):
         for q in range(world):
             recv = shm.view(peer_ptrs[q], (world * s_local, groups_total, hpr * 128), BF)
             recv[rank * s_local:(rank + 1) * s_local, group_first:group_first + groups] = xv[:, :, q]
+
+    def sp_return_heads(x, peer_ptrs, ld_dst, rows, heads, groups, world, rank):
+        hpr = heads // world                                                  # x: this rank's heads, ALL tokens -> the token owners
+        xv = x.reshape(x.shape[0], groups, hpr * 128)
+        for peer, ptr in enumerate(peer_ptrs):
+            dst = shm.view(ptr, (rows, ld_dst), BF)[:, :groups * heads * 128].view(rows, groups, heads * 128)
+            dst[:, :, rank * hpr * 128:(rank + 1) * hpr * 128] = xv[peer * rows:(peer + 1) * rows]
 
     def rmsnorm_rope_scatter(x, eps, weight, rope_tab, grid, token_offset, peer_ptrs, world, rank, group, groups_total):
         xf = x.float()
@@ -237,3 +246,76 @@ def test_peer_store_exchange_forward(tmp_path, world, dims, shape, fused):
         assert max(res["vs_oracle"]) < 1e-2, res          # north star: rel L2 <= 1e-2 per forward
         # one epoch per block and forward (2 layers x 2 forwards), both flag sets at it on every rank, nothing else written
         assert res["epoch"] == 4 and res["status"] == 0 and res["flags"] == [[4] * world, [4] * world] and res["untouched"] == 0, res
+
+
+def _train_worker(rank, world, port, shape, recompute, out_dir):
+    """One stage-2 LoRA training step (forward with saved activations, loss, hand-ordered backward) with the tokens of the video
+    split over the ranks: the exchange runs forward (q|k|v out, O back) AND backward (O, dO out, dq|dk|dv back through
+    fgb_sp_return_heads into the arena's gradient region), the B2 gradients are summed over the group."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import fairygen_b200 as fg
+    from fairygen_b200 import ops, sp as spmod
+    from fairygen_b200.training import Stage2Trainer
+    from oracle import wan_dit_oracle as o
+    from oracle import wan_train_oracle as t
+    from test_engine_sp_gloo import _bare_engine
+    from test_training_host import _emulated_ops as _training_ops
+
+    holder = {}
+    _training_ops(_Patch, holder)
+    shm = _SharedArenas(out_dir, rank)
+    _exchange_kernels(ops, shm)
+    spmod.PeerArena._allocate = staticmethod(shm.allocate)
+
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    w, lora = o.make_weights(o.TINY, seed=0), o.make_lora(o.TINY, rank=32, seed=2)
+    b2, masks = t.make_b2(o.TINY, rank=32), t.make_masks(o.TINY, rank=32)
+    x0, _, ctx, _ = o.make_inputs(o.TINY, shape, text_len=32, live_text=8)
+    noise = torch.randn(shape, generator=torch.Generator().manual_seed(9))
+
+    def run(sp):
+        eng = _bare_engine(fg, ops, cfg, sp)
+        eng.load_state_dict(w)
+        tr = Stage2Trainer(eng, lora, rank=32, stage=2, recompute=recompute)
+        holder["trainer"] = tr
+        tr.load_b2(b2)
+        tr.zero_grad()
+        loss, pred = tr.step(x0, noise, 500, ctx, masks=masks, return_pred=True)
+        return tr, float(loss), pred.float().clone(), {n: tr.grad[n].clone() for n in tr.targets}
+
+    _, loss1, pred1, grads1 = run(None)
+    par = fg.SequenceParallel(exchange="p2p")
+    trp, lossp, predp, gradsp = run(par)
+    par.check()
+    r = lambda v: v.to(BF).float()  # noqa: E731
+    _, pred_ref, grads_ref = t.loss_and_grads({k: r(v) for k, v in w.items()}, o.TINY, {k: r(v) for k, v in lora.items()},
+                                              {k: r(v) for k, v in b2.items()}, masks, r(x0), r(noise), 500, r(ctx), timestep_dtype=BF)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))  # noqa: E731
+    torch.save({"loss": (lossp, loss1), "pred_vs_single": rel(predp, pred1), "pred_vs_oracle": rel(predp, pred_ref),
+                "grad_vs_single": max(rel(gradsp[n], grads1[n]) for n in trp.targets),
+                "grad_vs_oracle": max(rel(gradsp[n], grads_ref[n]) for n in trp.targets),
+                "masked_zero": all(bool(torch.all(gradsp[n][masks[n] == 0] == 0)) for n in trp.targets),
+                "epoch": par.arena.epoch, "status": int(par.arena.status.item()),
+                "flags": [shm.view(par.arena.flag_ptrs[which][rank], (64,), torch.int32)[:world].tolist() for which in (0, 1)]},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,recompute", [((1, 48, 3, 10, 14), False),      # S = 105: ragged split, one padded row
+                                             ((1, 48, 4, 8, 8), True)])       # S = 64, activations re-computed per block (PIPE:1348-1360)
+def test_peer_store_exchange_training_step_world2(tmp_path, shape, recompute):
+    world = 2
+    mp.spawn(_train_worker, args=(world, _free_port(), shape, recompute, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert res["pred_vs_single"] < 4e-3 and res["pred_vs_oracle"] < 1e-2, res
+        assert abs(res["loss"][0] - res["loss"][1]) < 2e-3 * abs(res["loss"][1]), res
+        assert res["grad_vs_single"] < 3e-2 and res["grad_vs_oracle"] < 5e-2 and res["masked_zero"], res
+        # per block one exchange forward and one backward (+ one more forward when the block is re-computed)
+        epochs = 2 * (3 if recompute else 2)
+        assert res["epoch"] == epochs and res["status"] == 0 and res["flags"] == [[epochs] * world, [epochs] * world], res
