@@ -269,3 +269,70 @@ def test_encoder_rejects_bad_input(encoder):
         enc.encode([torch.zeros(3, 1, 24, 32)])          # height not a multiple of 16
     with pytest.raises(ValueError):
         enc.encode([torch.zeros(4, 1, 32, 32)])
+
+
+def test_window_assignment_covers_every_window_once_and_balances():
+    """assign_windows (the multi-GPU split of the tiled decode, tiled_decode of wan_video_vae.py:1081-1152 made parallel): every
+    window goes to exactly one rank, and no rank carries more than the mean load plus one window."""
+    from fairygen_b200 import vae
+    for (H, W, size, stride) in ((44, 80, (34, 34), (18, 16)), (30, 52, (34, 34), (18, 16)), (6, 7, (3, 4), (2, 3))):
+        tasks = vae.tile_tasks(H, W, size, stride)
+        area = lambda t: (min(t[1], H) - t[0]) * (min(t[3], W) - t[2])  # noqa: E731
+        for world in (1, 2, 3, 4, 8):
+            mine = vae.assign_windows(tasks, H, W, world)
+            assert len(mine) == world and sorted(t for m in mine for t in m) == sorted(tasks)
+            loads = [sum(area(t) for t in m) for m in mine]
+            assert max(loads) <= sum(loads) / world + max(area(t) for t in tasks), (H, W, world, loads)
+
+
+def _windows_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, repo)
+    sys.path.insert(0, os.path.join(repo, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from fairygen_b200 import vae
+    from test_vae_host import _emulated_ops as emu
+
+    class _Patch:
+        @staticmethod
+        def setattr(obj, name, value):
+            setattr(obj, name, value)
+
+    emu(_Patch)
+    dec = vae.VAE38Decoder(vae.VAE38Config(z_dim=o.TINY.z_dim, dec_dim=o.TINY.dec_dim), "cpu")
+    dec.load_state_dict(o.make_weights(o.TINY, seed=0))
+    z = torch.randn((1, o.TINY.z_dim, 2, 6, 7), generator=torch.Generator().manual_seed(3)).to(BF)
+    kw = dict(tiled=True, tile_size=(3, 4), tile_stride=(2, 3))
+    alone = dec.decode(z, **kw)
+    launches_alone, dec.kernel_launches = dec.kernel_launches, 0
+    shared = dec.decode(z, group=dist.group.WORLD, **kw)
+    torch.save({"err": float((shared.float() - alone.float()).abs().max()), "launches": (dec.kernel_launches, launches_alone)},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_decode_windows_over_two_ranks(tmp_path):
+    """CPU twin (gloo) of tests/test_sp_gpu.py::test_vae_windows_over_two_gpus: the windows of a tiled decode spread over two
+    ranks, one sum all-reduce of the blended video and its weights — every rank ends with the single-rank result, having
+    decoded only its share of the windows."""
+    import os
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_windows_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    shares = []
+    for r in range(2):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert res["err"] < 1e-2, res                 # bf16 output; fp32 sums of 2-4 contributions in another order
+        shares.append(res["launches"][0])
+        assert res["launches"][0] < res["launches"][1], res
+    assert abs(sum(shares) - res["launches"][1]) <= 2, (shares, res)     # together: the windows once (+ one blend_finish per rank)
