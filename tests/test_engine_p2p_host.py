@@ -319,3 +319,58 @@ def test_peer_store_exchange_training_step_world2(tmp_path, shape, recompute):
         # per block one exchange forward and one backward (+ one more forward when the block is re-computed)
         epochs = 2 * (3 if recompute else 2)
         assert res["epoch"] == epochs and res["status"] == 0 and res["flags"] == [[epochs] * world, [epochs] * world], res
+
+
+def _layout_worker(rank, world, port, out_dir):
+    """The headline layout of the 8-GPU line in small: CFG pair x Ulysses groups with the PEER-STORE exchange (two disjoint SP
+    groups, each with its own arenas and epochs; the pair exchanges predictions) — a 2-step CFG denoise must equal the sequential
+    single-process loop (PIPE:285-309)."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import fairygen_b200 as fg
+    from fairygen_b200 import ops, scheduler, sp as spmod
+    from fairygen_b200.cfg_parallel import Layout, ParallelContext, denoise_shots
+    from oracle import wan_dit_oracle as o
+    from test_engine_host import _emulated_ops
+    from test_engine_sp_gloo import _bare_engine
+
+    _emulated_ops(_Patch)
+    shm = _SharedArenas(out_dir, rank)
+    _exchange_kernels(ops, shm)
+    spmod.PeerArena._allocate = staticmethod(shm.allocate)
+
+    def step_fused(self, latents, noise_pos, noise_neg, cfg_scale, index, first_frame_latents=None, to_final=False):
+        ops.cfg_fm_step(latents, noise_pos, noise_neg, first_frame_latents, float(cfg_scale), self.sigma_delta(index, to_final))
+        return latents
+
+    scheduler.FlowMatchScheduler.step_fused = step_fused          # without the CUDA-only guard (tests/test_host_logic.py checks it)
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    w = o.make_weights(o.TINY, seed=0)
+    lat, z0, cp, cn = o.make_inputs(o.TINY, (1, 48, 3, 10, 14), text_len=24, live_text=8)       # S = 105: ragged over 2 ranks
+    shot = dict(latents=lat, context_pos=cp, context_neg=cn, first_frame_latents=z0)
+    ctx = ParallelContext(Layout(world, 1, 2, 2), exchange="p2p")
+    par = ctx.sequence_parallel()
+    assert par.exchange == "p2p" and par.world == 2
+    eng = _bare_engine(fg, ops, cfg, par)
+    eng.load_state_dict(w)
+    done = denoise_shots(ctx, lambda: fg.WanDenoiser(eng, 2, cfg_scale=5.0, sigma_shift=5.0), [shot])
+    single = _bare_engine(fg, ops, cfg, None)
+    single.load_state_dict(w)
+    ref = fg.WanDenoiser(single, 2, cfg_scale=5.0, sigma_shift=5.0)(lat, cp, cn, z0)
+    errs = [float((out.double() - ref.double()).norm() / ref.double().norm()) for _, out in done]
+    torch.save({"errs": errs, "epoch": par.arena.epoch, "status": int(par.arena.status.item()), "coords": ctx.layout.coords(rank)},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cfg_pair_times_peer_store_groups_world4(tmp_path):
+    world = 4
+    mp.spawn(_layout_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert res["errs"] and all(e < 5e-3 for e in res["errs"]), res
+        assert res["epoch"] == 2 * 2 and res["status"] == 0, res        # each rank runs ONE forward per step: 2 steps x 2 blocks
