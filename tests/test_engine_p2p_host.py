@@ -95,7 +95,7 @@ def _rope(y, rope_tab, grid, token0=0):
 def _exchange_kernels(ops, shm):
     """Contract statements of the exchange kernels, working through the peer pointers."""
 
-    def epoch_exchange(flag_ptrs, world, rank, epoch, status, limit_s=60.0):
+    def epoch_exchange(flag_ptrs, world, rank, epoch, status, limit_s=float(os.environ.get("FGB_TEST_BARRIER_LIMIT_S", "60"))):
         for q in range(world):                                               # publish: peer q's slot [rank]
             shm.view(flag_ptrs[q], (64,), torch.int32)[rank] = epoch
         mine = shm.view(flag_ptrs[rank], (64,), torch.int32)
@@ -111,7 +111,10 @@ def _exchange_kernels(ops, shm):
                 time.sleep(0.0002)
 
     def sp_barrier(device, flag_ptrs, world, rank, epoch, status=None, timeout_clocks=0):
-        epoch_exchange(flag_ptrs, world, rank, epoch, status, 60.0 if timeout_clocks == 0 else timeout_clocks / 1.5e9)
+        if timeout_clocks == 0:
+            epoch_exchange(flag_ptrs, world, rank, epoch, status)
+        else:
+            epoch_exchange(flag_ptrs, world, rank, epoch, status, timeout_clocks / 1.5e9)
 
     def gemm_qkv_scatter(a, w, bias, dim, peer_recv_ptrs, world, rank, rowsq, sk_ws=None):
         m = a.shape[0]
@@ -374,3 +377,65 @@ def test_cfg_pair_times_peer_store_groups_world4(tmp_path):
         res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         assert res["errs"] and all(e < 5e-3 for e in res["errs"]), res
         assert res["epoch"] == 2 * 2 and res["status"] == 0, res        # each rank runs ONE forward per step: 2 steps x 2 blocks
+
+
+def _lost_peer_worker(rank, world, port, out_dir):
+    """Rank 1 maps its arena and then never launches the forward (a dead rank): rank 0's first barrier gives up, writes its epoch
+    to the status word, every later barrier of the forward returns at once, and the host check names rank and epoch."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), FGB_TEST_BARRIER_LIMIT_S="1.0")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import fairygen_b200 as fg
+    from fairygen_b200 import ops, sp as spmod
+    from oracle import wan_dit_oracle as o
+    from test_engine_host import _emulated_ops
+    from test_engine_sp_gloo import _bare_engine
+
+    _emulated_ops(_Patch)
+    shm = _SharedArenas(out_dir, rank)
+    _exchange_kernels(ops, shm)
+    spmod.PeerArena._allocate = staticmethod(shm.allocate)
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    shape = (1, 48, 4, 8, 8)
+    lat, z0, cp, cn = o.make_inputs(o.TINY, shape, text_len=32, live_text=8)
+    par = fg.SequenceParallel(exchange="p2p")
+    eng = _bare_engine(fg, ops, cfg, par)
+    eng.load_state_dict(o.make_weights(o.TINY, seed=0))
+    res = {}
+    if rank == 0:
+        t0 = time.time()
+        out = eng.forward(lat.to(BF), torch.tensor([900.0]), cp.to(BF), True)
+        res["seconds"] = time.time() - t0
+        res["shape"] = tuple(out.shape)
+        try:
+            par.check()
+            res["raised"] = None
+        except RuntimeError as e:
+            res["raised"] = str(e)
+        den = fg.WanDenoiser.__new__(fg.WanDenoiser)          # the denoiser's end-of-video check sees the same word
+        den.engine, den._host_contexts = eng, []
+        den.scheduler = type("S", (), {"timesteps": []})()
+        try:
+            den(lat, cp, None, steps=range(0))
+            res["denoiser_raised"] = False
+        except RuntimeError:
+            res["denoiser_raised"] = True
+    else:
+        par.peer_arena(32, cfg.num_heads, torch.device("cpu"))               # maps its arena (collective), then goes silent ...
+        rows = torch.zeros(32, cfg.out_dim * 4, dtype=BF)
+        par.all_gather_rows(rows, torch.empty(64, cfg.out_dim * 4, dtype=BF))   # ... except for the library collective at the end
+    torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_a_lost_peer_is_reported_not_waited_for(tmp_path):
+    world = 2
+    mp.spawn(_lost_peer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = torch.load(os.path.join(tmp_path, "r0.pt"))
+    assert res["shape"] == (1, 48, 4, 8, 8)
+    assert res["seconds"] < 10.0, res                     # ONE barrier waited out its limit (1 s here), the other three did not
+    assert res["raised"] is not None and "rank 0 of 2" in res["raised"] and "epoch 1 " in res["raised"], res
+    assert res["denoiser_raised"], res
