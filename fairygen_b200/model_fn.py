@@ -63,6 +63,13 @@ def _weights_version(dit):
     return ver, ptr, len(getattr(dit, _PARAMS_ATTR))
 
 
+def _require_device_weights(device) -> None:
+    if device.type != "cuda":
+        raise RuntimeError(f"fairygen_b200: the DiT's weights are on `{device}`; the B200 path packs them from device memory — "
+                           "move the model to the GPU first (the reference's offload / vram-management modes are outside the "
+                           "hot path: disable them or call pipe.load_models_to_device(['dit']) before the first step)")
+
+
 def engine_for(dit, sp=None) -> WanDiTEngine:
     """Engine attached to a reference ``WanModel``; packs (or re-packs after ``load_lora``) lazily.  Adapters fused directly
     into the packed weights (``lora_io.fuse_into_engine``) are re-applied after a re-pack."""
@@ -70,10 +77,7 @@ def engine_for(dit, sp=None) -> WanDiTEngine:
     version = _weights_version(dit)
     if eng is None or (sp is not None and eng.sp is not sp):
         device = next(dit.parameters()).device
-        if device.type != "cuda":
-            raise RuntimeError(f"fairygen_b200: the DiT's weights are on `{device}`; the B200 path packs them from device memory — "
-                               "move the model to the GPU first (the reference's offload / vram-management modes are outside the "
-                               "hot path: disable them or call pipe.load_models_to_device(['dit']) before the first step)")
+        _require_device_weights(device)
         eng = WanDiTEngine(WanDiTConfig.from_module(dit), device=device, sp=sp)
         object.__setattr__(dit, _ENGINE_ATTR, eng)
         object.__setattr__(dit, _VERSION_ATTR, None)
