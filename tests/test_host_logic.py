@@ -139,3 +139,14 @@ def test_exchange_barrier_timeout_surfaces_on_the_host():
         den(lat, torch.zeros(1, 4, 8), None, steps=range(0))
     par.arena.status[0] = 0
     assert den(lat, torch.zeros(1, 4, 8), None, steps=range(0)).dtype == torch.bfloat16
+
+
+def test_engine_for_refuses_a_dit_on_the_host():
+    """The drop-in packs from device memory: a DiT whose weights still live on the host (the reference's offload modes) is an
+    error with instructions at the first call, not a silent CPU path."""
+    from fairygen_b200 import model_fn as mf
+
+    dit = torch.nn.Linear(4, 4)
+    with pytest.raises(RuntimeError, match="move the model to the GPU"):
+        mf.engine_for(dit)
+    mf._require_device_weights(torch.device("cuda", 0))      # a device pointer is all it asks for
