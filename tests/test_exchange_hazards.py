@@ -35,8 +35,11 @@ class _Recorder:
 
 def _regions(ar):
     s_pad, wloc3 = ar.recv.shape
-    return {"recv": (ar.off_recv, wloc3 * 2, s_pad), "o": (ar.off_o, ar.o.shape[1] * 2, ar.o.shape[0]),
-            "stats": (ar.off_stats, s_pad * 4, 2)}
+    regions = {"recv": (ar.off_recv, wloc3 * 2, s_pad), "o": (ar.off_o, ar.o.shape[1] * 2, ar.o.shape[0]),
+               "stats": (ar.off_stats, s_pad * 4, 2)}
+    if ar.dqkv is not None:                                                  # training: the gradient matrix the peers return into
+        regions["dqkv"] = (ar.off_dqkv, ar.dqkv.shape[1] * 2, ar.dqkv.shape[0])
+    return regions
 
 
 def _rects(ar, t):
@@ -87,7 +90,15 @@ def _recording_exchange(ops, shm, log, par):
         log.append(("bar", which_set(flag_ptrs), epoch))
         return inner["sp_barrier"](device, flag_ptrs, world, rank, epoch, status, timeout_clocks)
 
-    for fn in (gemm_qkv_scatter, sp_scatter_heads, sp_stats_barrier, attention_scatter, sp_barrier):
+    inner["sp_return_heads"] = ops.sp_return_heads
+
+    def sp_return_heads(x, peer_ptrs, ld_dst, rows, heads, groups, world, rank):
+        hb = (heads // world) * 128 * 2
+        log.append(("acc", "sp_return_heads", [(p, "dqkv", 0, rows, (g * heads * 128) * 2 + rank * hb, (g * heads * 128) * 2 + (rank + 1) * hb)
+                                               for p in range(world) for g in range(groups)]))
+        return inner["sp_return_heads"](x, peer_ptrs, ld_dst, rows, heads, groups, world, rank)
+
+    for fn in (gemm_qkv_scatter, sp_scatter_heads, sp_stats_barrier, attention_scatter, sp_barrier, sp_return_heads):
         setattr(ops, fn.__name__, fn)
     # fgb_rmsnorm_rope_scatter sends through the same layout as fgb_sp_scatter_heads: route it through the logging version
     # (its contract statement calls sp_scatter_heads by closure, so re-state the send here)
@@ -205,3 +216,90 @@ def test_every_cross_rank_conflict_is_ordered_by_a_barrier(tmp_path, world, dims
         assert found, (which, nth)
         regions = {f[2].split(": ")[1].split(" ")[0] for f in found}
         assert "recv" in regions, (which, nth, regions)
+
+
+def _train_worker(rank, world, port, shape, recompute, out_dir):
+    """The stage-2 training step of tests/test_engine_p2p_host.py with the recorder on.  The trainer calls the kernels directly, so
+    every entry point of `ops` is wrapped to log the arena memory its tensor arguments cover, and so is Tensor.copy_ (the trainer
+    saves `recv` before barrier 1 and `o` after it with plain copies)."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import types
+
+    import fairygen_b200 as fg
+    from fairygen_b200 import ops, sp as spmod
+    from fairygen_b200.training import Stage2Trainer
+    from oracle import wan_dit_oracle as o
+    from oracle import wan_train_oracle as t
+    from test_engine_sp_gloo import _bare_engine
+    from test_training_host import _emulated_ops as _training_ops
+
+    holder = {}
+    _training_ops(_Patch, holder)
+    shm = _SharedArenas(out_dir, rank)
+    spmod.PeerArena._allocate = staticmethod(shm.allocate)
+    par = fg.SequenceParallel(exchange="p2p")
+    log = []
+    _recording_exchange(ops, shm, log, par)
+
+    def logged(name, fn):
+        def call(*args, **kwargs):
+            ar = par.arena
+            if ar is not None:
+                rects = [r for a in list(args) + list(kwargs.values()) if torch.is_tensor(a) for r in _rects(ar, a)]
+                if rects:
+                    log.append(("acc", name, rects))
+            return fn(*args, **kwargs)
+        return call
+
+    for name in dir(ops):
+        fn = getattr(ops, name)
+        if isinstance(fn, types.FunctionType) and not name.startswith("_"):
+            setattr(ops, name, logged(name, fn))
+    plain_copy = torch.Tensor.copy_
+
+    def copy_(self, src, *args, **kwargs):
+        ar = par.arena
+        if ar is not None and torch.is_tensor(src):
+            rects = _rects(ar, src) + _rects(ar, self)
+            if rects:
+                log.append(("acc", "Tensor.copy_", rects))
+        return plain_copy(self, src, *args, **kwargs)
+
+    torch.Tensor.copy_ = copy_
+    cfg = fg.WanDiTConfig(dim=256, ffn_dim=512, text_dim=128, num_heads=2, num_layers=2)
+    w, lora = o.make_weights(o.TINY, seed=0), o.make_lora(o.TINY, rank=32, seed=2)
+    eng = _bare_engine(fg, ops, cfg, par)
+    eng.load_state_dict(w)
+    tr = Stage2Trainer(eng, lora, rank=32, stage=2, recompute=recompute)
+    holder["trainer"] = tr
+    tr.load_b2(t.make_b2(o.TINY, rank=32))
+    x0, _, ctx, _ = o.make_inputs(o.TINY, shape, text_len=32, live_text=8)
+    noise = torch.randn(shape, generator=torch.Generator().manual_seed(9))
+    for step in range(2):                                                    # two steps: the second forward follows the first backward
+        tr.zero_grad()
+        tr.step(x0, noise, 500, ctx, masks=t.make_masks(o.TINY, rank=32))
+    par.check()
+    torch.Tensor.copy_ = plain_copy
+    torch.save(log, os.path.join(out_dir, f"log{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("recompute", [False, True])
+def test_training_exchange_forward_and_backward_is_race_free(tmp_path, recompute):
+    world, shape = 2, (1, 48, 3, 10, 14)
+    mp.spawn(_train_worker, args=(world, _free_port(), shape, recompute, str(tmp_path)), nprocs=world, join=True)
+    logs = [torch.load(os.path.join(tmp_path, f"log{r}.pt")) for r in range(world)]
+    exchanges = 2 * 2 * (3 if recompute else 2)                               # steps x blocks x (forward [+ re-computed forward] + backward)
+    for log in logs:
+        assert [e[1:] for e in log if e[0] == "bar"] == [(s, e + 1) for e in range(exchanges) for s in (0, 1)]
+        names = {e[1] for e in log if e[0] == "acc"}
+        assert {"attention_scatter", "sp_return_heads", "attention_bwd", "Tensor.copy_", "sp_scatter_heads"} <= names, names
+        assert any(r[1] == "dqkv" and r[0] == logs.index(log) for e in log if e[0] == "acc" for r in e[2])   # its consumers were seen
+    assert hazards(logs) == []
+    for which, nth in ((1, 1), (0, 4), (1, exchanges - 1)):
+        assert hazards(_without_barrier(logs, which, nth)), (which, nth)
